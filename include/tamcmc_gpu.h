@@ -1,0 +1,141 @@
+/*
+ * tamcmc_gpu.h -- C ABI of the B200-native hot path of TAMCMC-C:
+ * power-spectrum model + Whittle chi^2(2 dof) log-likelihood for every parallel-tempered chain.
+ *
+ * The reference (OthmanB/TAMCMC-C v1.86.78) has no FFI for this path; its "operator API" is the
+ * C++ switch Model_def::call_model / call_likelihood over free functions.  Each entry point below
+ * names the reference interface it replaces (file:line relative to the upstream repo root).
+ * INTEGRATION.md shows the binding a maintainer adds in tamcmc/sources/model_def.cpp.
+ *
+ * Conventions: plain pointers and sizes, caller-owned output buffers, no allocation on the
+ * evaluation path, never exit(): every call returns a tamcmc_status.  A context is not
+ * re-entrant; one host thread issues one batched call per MCMC step.
+ * There is NO CPU fallback: with no usable CUDA device every call fails with TAMCMC_ERR_CUDA.
+ */
+#ifndef TAMCMC_GPU_H
+#define TAMCMC_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAMCMC_GPU_ABI_VERSION 1
+
+typedef enum {
+    TAMCMC_OK = 0,
+    TAMCMC_ERR_ARG = 1,          /* bad pointer / size / plength inconsistent with Nparams */
+    TAMCMC_ERR_MODEL = 2,        /* model id unknown, obsolete or not on this path
+                                    (reference: exit(), model_def.cpp:231-237, 352-384) */
+    TAMCMC_ERR_CUDA = 3,         /* CUDA runtime error, or no device: tamcmc_gpu_last_error() has the text */
+    TAMCMC_ERR_WINDOW = 4,       /* some chain hit imax-imin<=0 in set_imin_imax
+                                    (reference: exit(), build_lorentzian.cpp:650-665); its logL is NaN,
+                                    status_out[] tells which chain */
+    TAMCMC_ERR_NONFINITE = 5,    /* some chain produced a non-finite mode quantity; its logL is NaN */
+    TAMCMC_ERR_LIKELIHOOD = 6    /* likelihood id not on this path (model_def.cpp:405-416) */
+} tamcmc_status;
+
+/* per-chain status bits written to status_out[] (0 = evaluated normally) */
+#define TAMCMC_CHAIN_WINDOW     1
+#define TAMCMC_CHAIN_NONFINITE  2
+#define TAMCMC_CHAIN_BADCFG     4
+#define TAMCMC_CHAIN_INACTIVE   8   /* active_mask[chain]==0 */
+
+/* model ids = case labels of Model_def::call_model (model_def.cpp:220-388) =
+ * Config/default/models_ctrl.list */
+#define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC     3   /* models.cpp:1943 */
+#define TAMCMC_MODEL_MS_GLOBAL_A1L_ETAA3_HARVEYLIKE           6   /* models.cpp:25   */
+#define TAMCMC_MODEL_MS_LOCAL_BASIC                          11   /* models.cpp:3012 */
+#define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC_V2 12   /* models.cpp:2128 */
+#define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC_V3 13   /* models.cpp:2338 */
+#define TAMCMC_MODEL_MS_GLOBAL_AJ_HARVEYLIKE                 23   /* models.cpp:1195 */
+
+/* likelihood ids = Config/default/likelihoods_ctrl.list (model_def.cpp:396-403) */
+#define TAMCMC_LIKELIHOOD_CHI22P 0      /* likelihood_chi22p, likelihoods.cpp:17-28 */
+
+typedef struct tamcmc_gpu_ctx tamcmc_gpu_ctx;
+
+/* One star (or one slice of a star) = the reference's `Data` {x, y, Nx} (headers/data.h) plus the
+ * model selection of its Model_def (model_fct_name_switch, plength: model_def.h:40-66). */
+typedef struct {
+    int model_id;
+    int plength[11];        /* io_ms_global.cpp:1315-1325 */
+    int Nparams;            /* length of one parameter row */
+    const double *x;        /* host, length N: frequencies (microHz), regular grid */
+    const double *y;        /* host, length N: power spectrum */
+    long N;                 /* bins held by THIS context */
+    /* bin-sharding over GPUs (leave zero for a whole spectrum): this context holds global bins
+     * [bin_offset, bin_offset+N) of a spectrum of N_global bins whose first two and last
+     * frequencies are x_first, x_second, x_last (needed by set_imin_imax and `step`). */
+    long N_global;
+    long bin_offset;
+    double x_first, x_second, x_last;
+} tamcmc_gpu_star;
+
+/* Replaces: the data/model set-up of Model_def::Model_def (model_def.cpp:28-160) for the hot path.
+ * Uploads x, y once; allocates every device buffer the evaluation path needs.
+ * Tcoefs[Nchains]: tempering coefficients (MALA.cpp:75-80); p: likelihood_params (model_def.cpp:399). */
+int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star *stars, int Nchains,
+                      const double *Tcoefs, double p, int likelihood_id, tamcmc_gpu_ctx **out);
+
+void tamcmc_gpu_destroy(tamcmc_gpu_ctx *ctx);
+
+/* Replaces: the per-chain OpenMP fan-out of call_model + call_likelihood inside
+ * Model_def::generate_model (model_def.cpp:466-482) driven by MALA::update_position_MH
+ * (MALA.cpp:648-668): ONE batched evaluation of all chains of all stars.
+ *   params      host [nstars][Nchains][params_stride] row-major, params_stride = tamcmc_gpu_params_stride()
+ *   active_mask host [nstars][Nchains] or NULL; 0 reproduces the logPrior==-inf short-circuit
+ *               (model_def.cpp:476-480): the chain is skipped and logL_out is NaN
+ *   logL_out    host [nstars][Nchains]: TEMPERED log-likelihood -p*S/Tcoefs[m] (model_def.cpp:401)
+ *   status_out  host [nstars][Nchains] or NULL: TAMCMC_CHAIN_* bits
+ * Host<->device copies of params and results are part of this call. */
+int tamcmc_gpu_eval(tamcmc_gpu_ctx *ctx, const double *params, const unsigned char *active_mask,
+                    double *logL_out, int *status_out);
+
+/* Same evaluation with DEVICE-resident inputs/outputs on the caller's CUDA stream (cudaStream_t
+ * passed as void*; NULL = the context's own stream).  d_params has the layout of `params` above,
+ * d_logL is [nstars][Nchains].  Asynchronous: the caller synchronises the stream.
+ * If raw_sum != 0, d_logL receives S = sum_i(ln M_i + y_i/M_i) over the bins held by this context
+ * (the quantity a bin-sharded run all-reduces before applying -p/T). */
+int tamcmc_gpu_eval_device(tamcmc_gpu_ctx *ctx, const double *d_params, const unsigned char *d_active,
+                           double *d_logL, int raw_sum, void *stream);
+
+/* Waits for the context's own stream (after tamcmc_gpu_eval_device with stream == NULL) and, when
+ * profiling is on, accumulates the CUDA-event durations of that evaluation's kernels. */
+int tamcmc_gpu_sync(tamcmc_gpu_ctx *ctx);
+
+/* Replaces: Model_def::call_model_explicit (model_def.cpp:209-218) as used by tools/getmodel.cpp:201
+ * and the diagnostics mean-model (MALA.cpp:722,735): the model spectrum for ONE parameter row.
+ * model_out: host, N doubles of star `star`. */
+int tamcmc_gpu_model(tamcmc_gpu_ctx *ctx, int star, const double *params_row, double *model_out);
+
+/* Parity/debug: the bin windows of set_imin_imax (build_lorentzian.cpp:595-676) for one parameter
+ * row, in the reference's call order.  Arrays of capacity `cap`; *nmodes receives the count. */
+int tamcmc_gpu_windows(tamcmc_gpu_ctx *ctx, int star, const double *params_row, int cap,
+                       int *nmodes, int *l, int *imin, int *imax);
+
+/* Parity/debug: the expanded component table (nu_nlm, height H*V_m, width) for one parameter row. */
+int tamcmc_gpu_components(tamcmc_gpu_ctx *ctx, int star, const double *params_row, int cap,
+                          int *ncomp, int *mode_index, int *m, double *nu, double *height, double *width);
+
+/* sizes */
+int  tamcmc_gpu_params_stride(const tamcmc_gpu_ctx *ctx);   /* doubles per parameter row (max Nparams) */
+int  tamcmc_gpu_nstars(const tamcmc_gpu_ctx *ctx);
+int  tamcmc_gpu_nchains(const tamcmc_gpu_ctx *ctx);
+long tamcmc_gpu_pairs_last(tamcmc_gpu_ctx *ctx);            /* sum over chains and modes of (2l+1)*(imax-imin)
+                                                               for the last evaluation (SURVEY.md 8d "P") */
+
+/* measurement support: CUDA-event timing of the kernels on the context's stream */
+int tamcmc_gpu_set_profiling(tamcmc_gpu_ctx *ctx, int on);
+int tamcmc_gpu_get_kernel_ms(tamcmc_gpu_ctx *ctx, long *nlaunch, double *expand_ms_total, double *whittle_ms_total);
+long tamcmc_gpu_launch_count(const tamcmc_gpu_ctx *ctx);    /* kernels launched by this context so far */
+/* DFMA microbenchmark: achieved FP64 TFLOP/s of `device` (FMA = 2 flops); the roofline denominator */
+int tamcmc_gpu_fp64_peak(int device, double *tflops);
+
+const char *tamcmc_gpu_strerror(int status);
+const char *tamcmc_gpu_last_error(void);
+int tamcmc_gpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,291 @@
+"""tamcmc-c_b200: B200-native hot path of TAMCMC-C (model spectrum + Whittle logL).
+
+This Python module is only the ctypes binding of the C ABI in include/tamcmc_gpu.h
+(used by tests/, bench.py and __graft_entry__.py).  The product is the shared library
+`libtamcmc_gpu.so` built from csrc/ (hand-written sm_100a CUDA); the reference-facing
+host mirror is the C++ header host/model_def_gpu.hpp.  There is no CPU fallback: if the
+library is missing or no CUDA device is usable, every call raises.
+
+The directory name has a hyphen, so import it through `__graft_entry__.load_package()`
+(module alias `tamcmc_c_b200`).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import synth  # noqa: F401  (synthetic inputs; numpy only)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtamcmc_gpu.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_ucp = C.POINTER(C.c_ubyte)
+
+OK, ERR_ARG, ERR_MODEL, ERR_CUDA, ERR_WINDOW, ERR_NONFINITE, ERR_LIKELIHOOD = range(7)
+CHAIN_WINDOW, CHAIN_NONFINITE, CHAIN_BADCFG, CHAIN_INACTIVE = 1, 2, 4, 8
+
+# every symbol include/tamcmc_gpu.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "tamcmc_gpu_create", "tamcmc_gpu_destroy", "tamcmc_gpu_eval", "tamcmc_gpu_eval_device",
+    "tamcmc_gpu_sync", "tamcmc_gpu_model", "tamcmc_gpu_windows", "tamcmc_gpu_components",
+    "tamcmc_gpu_params_stride", "tamcmc_gpu_nstars", "tamcmc_gpu_nchains", "tamcmc_gpu_pairs_last",
+    "tamcmc_gpu_set_profiling", "tamcmc_gpu_get_kernel_ms", "tamcmc_gpu_launch_count",
+    "tamcmc_gpu_fp64_peak", "tamcmc_gpu_strerror", "tamcmc_gpu_last_error", "tamcmc_gpu_abi_version",
+]
+
+
+class StarStruct(C.Structure):
+    _fields_ = [
+        ("model_id", C.c_int),
+        ("plength", C.c_int * 11),
+        ("Nparams", C.c_int),
+        ("x", _dp),
+        ("y", _dp),
+        ("N", C.c_long),
+        ("N_global", C.c_long),
+        ("bin_offset", C.c_long),
+        ("x_first", C.c_double),
+        ("x_second", C.c_double),
+        ("x_last", C.c_double),
+    ]
+
+
+class TamcmcError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(msg)
+        self.status = status
+
+
+_lib = None
+
+
+def lib():
+    """Load libtamcmc_gpu.so (fails loudly: there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TamcmcError(ERR_CUDA, "libtamcmc_gpu.so not built: run __graft_entry__.build() (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.tamcmc_gpu_create.restype = C.c_int
+    L.tamcmc_gpu_create.argtypes = [C.c_int, C.c_int, C.POINTER(StarStruct), C.c_int, _dp, C.c_double, C.c_int, C.POINTER(vp)]
+    L.tamcmc_gpu_destroy.restype = None
+    L.tamcmc_gpu_destroy.argtypes = [vp]
+    L.tamcmc_gpu_eval.restype = C.c_int
+    L.tamcmc_gpu_eval.argtypes = [vp, _dp, _ucp, _dp, _ip]
+    L.tamcmc_gpu_eval_device.restype = C.c_int
+    L.tamcmc_gpu_eval_device.argtypes = [vp, vp, vp, vp, C.c_int, vp]
+    L.tamcmc_gpu_sync.restype = C.c_int
+    L.tamcmc_gpu_sync.argtypes = [vp]
+    L.tamcmc_gpu_model.restype = C.c_int
+    L.tamcmc_gpu_model.argtypes = [vp, C.c_int, _dp, _dp]
+    L.tamcmc_gpu_windows.restype = C.c_int
+    L.tamcmc_gpu_windows.argtypes = [vp, C.c_int, _dp, C.c_int, _ip, _ip, _ip, _ip]
+    L.tamcmc_gpu_components.restype = C.c_int
+    L.tamcmc_gpu_components.argtypes = [vp, C.c_int, _dp, C.c_int, _ip, _ip, _ip, _dp, _dp, _dp]
+    for f in ("tamcmc_gpu_params_stride", "tamcmc_gpu_nstars", "tamcmc_gpu_nchains"):
+        getattr(L, f).restype = C.c_int
+        getattr(L, f).argtypes = [vp]
+    L.tamcmc_gpu_pairs_last.restype = C.c_long
+    L.tamcmc_gpu_pairs_last.argtypes = [vp]
+    L.tamcmc_gpu_set_profiling.restype = C.c_int
+    L.tamcmc_gpu_set_profiling.argtypes = [vp, C.c_int]
+    L.tamcmc_gpu_get_kernel_ms.restype = C.c_int
+    L.tamcmc_gpu_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_long), _dp, _dp]
+    L.tamcmc_gpu_launch_count.restype = C.c_long
+    L.tamcmc_gpu_launch_count.argtypes = [vp]
+    L.tamcmc_gpu_fp64_peak.restype = C.c_int
+    L.tamcmc_gpu_fp64_peak.argtypes = [C.c_int, _dp]
+    L.tamcmc_gpu_strerror.restype = C.c_char_p
+    L.tamcmc_gpu_strerror.argtypes = [C.c_int]
+    L.tamcmc_gpu_last_error.restype = C.c_char_p
+    L.tamcmc_gpu_abi_version.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _raise(rc):
+    L = lib()
+    msg = L.tamcmc_gpu_strerror(rc).decode()
+    if rc == ERR_CUDA:
+        msg += " -- " + L.tamcmc_gpu_last_error().decode()
+    raise TamcmcError(rc, msg)
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Star:
+    """Host-side description of one star/slice (reference: Data{x,y,Nx} + model selection)."""
+
+    def __init__(self, model_id, plength, Nparams, x, y, N_global=0, bin_offset=0, x_first=0.0, x_second=0.0, x_last=0.0):
+        self.model_id = int(model_id)
+        self.plength = np.ascontiguousarray(plength, dtype=np.int32)
+        self.Nparams = int(Nparams)
+        self.x = _d(x)
+        self.y = _d(y)
+        self.N_global, self.bin_offset = int(N_global), int(bin_offset)
+        self.x_first, self.x_second, self.x_last = float(x_first), float(x_second), float(x_last)
+
+    @classmethod
+    def shard(cls, model_id, plength, Nparams, x, y, lo, hi):
+        """Bins [lo,hi) of a spectrum (bin-sharding over GPUs)."""
+        x = _d(x)
+        return cls(model_id, plength, Nparams, x[lo:hi], _d(y)[lo:hi], N_global=len(x), bin_offset=lo,
+                   x_first=x[0], x_second=x[1], x_last=x[-1])
+
+    def struct(self):
+        s = StarStruct()
+        s.model_id = self.model_id
+        for i in range(11):
+            s.plength[i] = int(self.plength[i])
+        s.Nparams = self.Nparams
+        s.x = self.x.ctypes.data_as(_dp)
+        s.y = self.y.ctypes.data_as(_dp)
+        s.N = len(self.x)
+        s.N_global, s.bin_offset = self.N_global, self.bin_offset
+        s.x_first, s.x_second, s.x_last = self.x_first, self.x_second, self.x_last
+        return s
+
+
+class Context:
+    """Thin owner of a tamcmc_gpu_ctx.  Mirrors the hot-path half of the reference's Model_def:
+    eval() = generate_model's call_model + call_likelihood for all chains (model_def.cpp:466-482),
+    model() = call_model_explicit (model_def.cpp:209-218)."""
+
+    def __init__(self, stars, Nchains, Tcoefs, p=1.0, likelihood_id=0, device=0):
+        if isinstance(stars, Star):
+            stars = [stars]
+        self.stars = list(stars)
+        self.Nchains = int(Nchains)
+        L = lib()
+        arr = (StarStruct * len(self.stars))(*[s.struct() for s in self.stars])
+        T = _d(Tcoefs)
+        if len(T) != self.Nchains:
+            raise TamcmcError(ERR_ARG, "len(Tcoefs) != Nchains")
+        h = C.c_void_p()
+        rc = L.tamcmc_gpu_create(int(device), len(self.stars), arr, self.Nchains, T.ctypes.data_as(_dp), float(p), int(likelihood_id), C.byref(h))
+        if rc != OK:
+            _raise(rc)
+        self.h = h
+        self.nstars = len(self.stars)
+        self.params_stride = L.tamcmc_gpu_params_stride(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tamcmc_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def pack_params(self, params):
+        """params: array [nstars, Nchains, Nparams_s] (or [Nchains, Nparams] for one star, or a list
+        of per-star arrays) -> contiguous [nstars, Nchains, params_stride]."""
+        if isinstance(params, np.ndarray) and params.ndim == 2:
+            params = [params]
+        out = np.zeros((self.nstars, self.Nchains, self.params_stride))
+        for s in range(self.nstars):
+            p = _d(params[s])
+            out[s, :, : p.shape[1]] = p
+        return out
+
+    def eval(self, params, active=None, raise_on_error=True):
+        """One batched evaluation from HOST buffers: returns (logL[nstars, Nchains], status)."""
+        P = params if (isinstance(params, np.ndarray) and params.ndim == 3 and params.shape[2] == self.params_stride
+                       and params.flags.c_contiguous and params.dtype == np.float64) else self.pack_params(params)
+        out = np.empty((self.nstars, self.Nchains))
+        st = np.empty((self.nstars, self.Nchains), dtype=np.int32)
+        am = None
+        if active is not None:
+            am_arr = np.ascontiguousarray(active, dtype=np.uint8).reshape(self.nstars, self.Nchains)
+            am = am_arr.ctypes.data_as(_ucp)
+        rc = lib().tamcmc_gpu_eval(self.h, P.ctypes.data_as(_dp), am, out.ctypes.data_as(_dp), st.ctypes.data_as(_ip))
+        if rc != OK and raise_on_error:
+            _raise(rc)
+        self.last_rc = rc
+        return out, st
+
+    def eval_device(self, d_params_ptr, d_logL_ptr, d_active_ptr=None, raw_sum=False, stream=None):
+        rc = lib().tamcmc_gpu_eval_device(self.h, C.c_void_p(d_params_ptr), C.c_void_p(d_active_ptr) if d_active_ptr else None,
+                                          C.c_void_p(d_logL_ptr), 1 if raw_sum else 0, C.c_void_p(stream) if stream else None)
+        if rc != OK:
+            _raise(rc)
+
+    def sync(self):
+        rc = lib().tamcmc_gpu_sync(self.h)
+        if rc != OK:
+            _raise(rc)
+
+    def model(self, params_row, star=0):
+        row = _d(params_row)
+        out = np.empty(len(self.stars[star].x))
+        rc = lib().tamcmc_gpu_model(self.h, star, row.ctypes.data_as(_dp), out.ctypes.data_as(_dp))
+        if rc != OK:
+            _raise(rc)
+        return out
+
+    def windows(self, params_row, star=0, cap=8192, raise_on_error=True):
+        row = _d(params_row)
+        n = C.c_int(0)
+        l = np.zeros(cap, dtype=np.int32)
+        i0 = np.zeros(cap, dtype=np.int32)
+        i1 = np.zeros(cap, dtype=np.int32)
+        rc = lib().tamcmc_gpu_windows(self.h, star, row.ctypes.data_as(_dp), cap, C.byref(n), l.ctypes.data_as(_ip),
+                                      i0.ctypes.data_as(_ip), i1.ctypes.data_as(_ip))
+        if rc != OK and raise_on_error:
+            _raise(rc)
+        k = min(n.value, cap)
+        return rc, l[:k].copy(), i0[:k].copy(), i1[:k].copy()
+
+    def components(self, params_row, star=0, cap=65536):
+        row = _d(params_row)
+        n = C.c_int(0)
+        mi = np.zeros(cap, dtype=np.int32)
+        m = np.zeros(cap, dtype=np.int32)
+        nu = np.zeros(cap)
+        h = np.zeros(cap)
+        w = np.zeros(cap)
+        rc = lib().tamcmc_gpu_components(self.h, star, row.ctypes.data_as(_dp), cap, C.byref(n), mi.ctypes.data_as(_ip),
+                                         m.ctypes.data_as(_ip), nu.ctypes.data_as(_dp), h.ctypes.data_as(_dp), w.ctypes.data_as(_dp))
+        if rc != OK:
+            _raise(rc)
+        k = min(n.value, cap)
+        return mi[:k].copy(), m[:k].copy(), nu[:k].copy(), h[:k].copy(), w[:k].copy()
+
+    def pairs_last(self):
+        return int(lib().tamcmc_gpu_pairs_last(self.h))
+
+    def set_profiling(self, on=True):
+        lib().tamcmc_gpu_set_profiling(self.h, 1 if on else 0)
+
+    def kernel_ms(self):
+        n = C.c_long(0)
+        a = C.c_double(0)
+        b = C.c_double(0)
+        lib().tamcmc_gpu_get_kernel_ms(self.h, C.byref(n), C.byref(a), C.byref(b))
+        return n.value, a.value, b.value
+
+    def launch_count(self):
+        return int(lib().tamcmc_gpu_launch_count(self.h))
+
+
+def fp64_peak(device=0):
+    v = C.c_double(0)
+    rc = lib().tamcmc_gpu_fp64_peak(int(device), C.byref(v))
+    if rc != OK:
+        _raise(rc)
+    return v.value

@@ -1,0 +1,564 @@
+// capi.cu -- implementation of the C ABI declared in include/tamcmc_gpu.h.
+//
+// Owns the device memory, the stream and the launch sequence
+//     H2D(params) -> expand kernel -> fused model+Whittle kernel -> D2H(logL, status).
+// No CPU evaluation path exists here: without a CUDA device every entry point fails.
+#include "../../include/tamcmc_gpu.h"
+#include "kernels.h"
+#include "tamcmc_dev.h"
+
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail_cuda(cudaError_t e, const char* what)
+{
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return TAMCMC_ERR_CUDA;
+}
+#define CK(call)                                            \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+// ---- Pslm / Qlm tables (host, long double).  Formulas: Ritzwoller & Lavely (1991) polynomials
+// normalised so that Pslm(l)=l (Schou, Christensen-Dalsgaard & Thompson 1994), as used by the
+// reference in tamcmc/sources/acoefs.cpp:51-110; Qlm with the 2/3 factor as
+// tamcmc/sources/build_lorentzian.cpp:583-592. ----
+long double Hslm(int s, int l, int m)
+{
+    const double L = (double)(l * (l + 1)), M = (double)m;
+    switch (s) {
+    case 5: return 252 * std::pow(M, 5) - 140 * (2 * L - 3) * std::pow(M, 3) + (20 * L * (3 * L - 10) + 48) * M;
+    case 6: return 924 * std::pow(M, 6) - 420 * std::pow(M, 4) * (3 * L - 7) + 84 * std::pow(M, 2) * (5 * L * L - 25 * L + 14)
+                 - 20 * L * (L * L - 8 * L + 12);
+    }
+    return 0;
+}
+long double Pslm_host(int s, int l, int m)
+{
+    const double M = (double)m, dl = (double)l;
+    const int LL = l * (l + 1);
+    long double H, c;
+    switch (s) {
+    case 1: return m;
+    case 2: return (l > 0) ? (long double)((3 * M * M - LL) / (2 * l - 1)) : 0.0L;
+    case 3: return (l > 1) ? (long double)((5 * M * M * M - (3 * LL - 1) * M) / ((l - 1) * (2 * l - 1))) : 0.0L;
+    case 4:
+        H = (35 * std::pow(M, 4) - 5 * (6 * LL - 5) * M * M) + 3 * LL * (LL - 2);
+        c = 2 * (l - 1) * (2 * l - 1) * (2 * l - 3);
+        return (c != 0) ? H / c : 0.0L;
+    case 5:
+        H = Hslm(5, l, m);
+        c = 8 * (4 * std::pow(dl, 4) - 20 * std::pow(dl, 3) + 35 * dl * dl - 25 * dl + 6);
+        return (c != 0) ? H / c : 0.0L;
+    case 6:
+        H = Hslm(6, l, m);
+        c = 64 * std::pow(dl, 5) - 480 * std::pow(dl, 4) + 1360 * std::pow(dl, 3) - 1800 * dl * dl + 1096 * dl - 240;
+        return (c != 0) ? H / c : 0.0L;
+    }
+    return 0.0L;
+}
+double Qlm_host(int l, int m)
+{
+    const long double Dnl = 2. / 3;
+    double Q = (l * (l + 1) - 3 * (double)m * (double)m) / ((2 * l - 1) * (2 * l + 3));
+    Q = (double)(Q * Dnl);
+    return Q;
+}
+
+bool g_tables_uploaded[64] = {false};
+
+int upload_tables(int device)
+{
+    if (device >= 0 && device < 64 && g_tables_uploaded[device]) return TAMCMC_OK;
+    double hi[7][4][7], lo[7][4][7], Q[4][7];
+    std::memset(hi, 0, sizeof(hi)); std::memset(lo, 0, sizeof(lo)); std::memset(Q, 0, sizeof(Q));
+    for (int s = 1; s <= 6; s++)
+        for (int l = 0; l <= 3; l++)
+            for (int m = -l; m <= l; m++) {
+                const long double P = Pslm_host(s, l, m);
+                const double h = (double)P;
+                hi[s][l][m + 3] = h;
+                lo[s][l][m + 3] = (double)(P - (long double)h);
+            }
+    for (int l = 0; l <= 3; l++)
+        for (int m = -l; m <= l; m++) Q[l][m + 3] = Qlm_host(l, m);
+    CK(tamcmc_upload_tables(&hi[0][0][0], &lo[0][0][0], &Q[0][0]));
+    CK(tamcmc_whittle_configure());
+    if (device >= 0 && device < 64) g_tables_uploaded[device] = true;
+    return TAMCMC_OK;
+}
+
+int modes_of(int model_id, const int* pl)
+{
+    switch (model_id) {
+    case 3: case 6: case 12: case 13: return pl[0] * (pl[1] + 1);
+    case 11: case 23: return pl[2] + pl[3] + pl[4] + pl[5];
+    }
+    return -1;
+}
+
+}  // namespace
+
+struct tamcmc_gpu_ctx {
+    int device = 0;
+    int nstars = 0, Nchains = 0;
+    int params_stride = 0, modes_stride = 0, tiles_stride = 0, total_tiles = 0;
+    long long total_bins_padded = 0;
+    double p = 1.0;
+    std::vector<StarDesc> h_stars;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // device
+    StarDesc* d_stars = nullptr;
+    int* d_tile_star = nullptr;
+    double *d_x = nullptr, *d_y = nullptr, *d_lnx = nullptr;
+    double* d_params = nullptr;
+    unsigned char* d_active = nullptr;
+    ModeRec* d_modes = nullptr;
+    CompRec* d_comps = nullptr;
+    NoiseRec* d_noise = nullptr;
+    int* d_asym = nullptr;
+    double* d_Tcoefs = nullptr;
+    double* d_partial = nullptr;
+    unsigned int* d_counters = nullptr;
+    void* d_out = nullptr;          // [SC] double logL then [SC] int status
+    double* d_model = nullptr;      // max Nloc
+    // pinned host staging
+    double* h_params = nullptr;
+    unsigned char* h_active = nullptr;
+    void* h_out = nullptr;
+    // measurement
+    bool profiling = false;
+    long nlaunch_prof = 0;
+    double expand_ms = 0, whittle_ms = 0;
+    long launches = 0;
+    long pairs_last = -1;
+
+    int SC() const { return nstars * Nchains; }
+    double* d_logL() const { return reinterpret_cast<double*>(d_out); }
+    int* d_status() const { return reinterpret_cast<int*>(reinterpret_cast<double*>(d_out) + nstars * Nchains); }
+    size_t out_bytes() const { return (size_t)SC() * (sizeof(double) + sizeof(int)); }
+};
+
+namespace {
+
+ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL)
+{
+    ExpandArgs a;
+    a.stars = c->d_stars; a.params = d_params; a.active = d_active;
+    a.modes = c->d_modes; a.comps = c->d_comps; a.noise = c->d_noise;
+    a.status = c->d_status(); a.asym_flag = c->d_asym; a.out_logL = d_logL;
+    a.Nchains = c->Nchains; a.params_stride = c->params_stride; a.modes_stride = c->modes_stride;
+    return a;
+}
+
+WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum)
+{
+    WhittleArgs a;
+    a.stars = c->d_stars; a.tile_star = c->d_tile_star;
+    a.x = c->d_x; a.y = c->d_y; a.lnx = c->d_lnx;
+    a.modes = c->d_modes; a.comps = c->d_comps; a.noise = c->d_noise;
+    a.status = c->d_status(); a.asym_flag = c->d_asym; a.Tcoefs = c->d_Tcoefs;
+    a.partial = c->d_partial; a.counters = c->d_counters;
+    a.out = d_out; a.model_out = c->d_model;
+    a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
+    a.raw_sum = raw_sum; a.tile_begin = 0; a.chain_begin = 0;
+    return a;
+}
+
+// expand + fused kernel on `st`
+int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
+                int raw_sum, cudaStream_t st)
+{
+    ExpandArgs ea = make_expand_args(c, d_params, d_active, d_logL);
+    WhittleArgs wa = make_whittle_args(c, d_logL, raw_sum);
+    const bool prof = c->profiling && st == c->stream;
+    if (prof) CK(cudaEventRecord(c->ev[0], st));
+    CK(tamcmc_launch_expand(ea, c->SC(), st));
+    if (prof) CK(cudaEventRecord(c->ev[1], st));
+    CK(tamcmc_launch_whittle(wa, c->total_tiles, c->Nchains, false, st));
+    if (prof) CK(cudaEventRecord(c->ev[2], st));
+    c->launches += 2;
+    return TAMCMC_OK;
+}
+
+int collect_profile(tamcmc_gpu_ctx* c)
+{
+    if (!c->profiling) return TAMCMC_OK;
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+    CK(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+    c->expand_ms += a; c->whittle_ms += b; c->nlaunch_prof++;
+    return TAMCMC_OK;
+}
+
+int status_to_rc(const int* st, int n)
+{
+    int rc = TAMCMC_OK;
+    for (int i = 0; i < n; i++) {
+        if (st[i] & TAMCMC_ST_BADCFG) return TAMCMC_ERR_MODEL;
+        if (st[i] & TAMCMC_ST_WINDOW) rc = TAMCMC_ERR_WINDOW;
+        else if ((st[i] & TAMCMC_ST_NONFINITE) && rc == TAMCMC_OK) rc = TAMCMC_ERR_NONFINITE;
+    }
+    return rc;
+}
+
+// evaluate one parameter row as chain 0 of `star` (all other chains masked); used by the debug entries
+int expand_single(tamcmc_gpu_ctx* c, int star, const double* row)
+{
+    if (!c || !row || star < 0 || star >= c->nstars) return TAMCMC_ERR_ARG;
+    const int SC = c->SC();
+    std::memset(c->h_params, 0, sizeof(double) * (size_t)SC * c->params_stride);
+    std::memset(c->h_active, 0, (size_t)SC);
+    const int sc = star * c->Nchains;
+    std::memcpy(c->h_params + (size_t)sc * c->params_stride, row, sizeof(double) * (size_t)c->h_stars[star].Nparams);
+    c->h_active[sc] = 1;
+    CK(cudaMemcpyAsync(c->d_params, c->h_params, sizeof(double) * (size_t)SC * c->params_stride, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_active, c->h_active, (size_t)SC, cudaMemcpyHostToDevice, c->stream));
+    ExpandArgs ea = make_expand_args(c, c->d_params, c->d_active, c->d_logL());
+    CK(tamcmc_launch_expand(ea, SC, c->stream));
+    c->launches += 1;
+    return TAMCMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tamcmc_gpu_abi_version(void) { return TAMCMC_GPU_ABI_VERSION; }
+
+const char* tamcmc_gpu_last_error(void) { return g_last_error.c_str(); }
+
+const char* tamcmc_gpu_strerror(int s)
+{
+    switch (s) {
+    case TAMCMC_OK: return "ok";
+    case TAMCMC_ERR_ARG: return "invalid argument";
+    case TAMCMC_ERR_MODEL: return "model id unknown, obsolete or not on the GPU path";
+    case TAMCMC_ERR_CUDA: return "CUDA error (no CPU fallback exists)";
+    case TAMCMC_ERR_WINDOW: return "set_imin_imax: imax - imin <= 0 for some chain";
+    case TAMCMC_ERR_NONFINITE: return "non-finite mode quantity for some chain";
+    case TAMCMC_ERR_LIKELIHOOD: return "likelihood id not on the GPU path";
+    }
+    return "unknown status";
+}
+
+int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int Nchains,
+                      const double* Tcoefs, double p, int likelihood_id, tamcmc_gpu_ctx** out)
+{
+    if (!out) return TAMCMC_ERR_ARG;
+    *out = nullptr;
+    if (nstars <= 0 || !stars || Nchains <= 0 || !Tcoefs) return TAMCMC_ERR_ARG;
+    if (likelihood_id != TAMCMC_LIKELIHOOD_CHI22P) return TAMCMC_ERR_LIKELIHOOD;
+    int ndev = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+        if (ndev <= 0 || device < 0 || device >= ndev) { g_last_error = "no usable CUDA device"; return TAMCMC_ERR_CUDA; }
+    }
+    CK(cudaSetDevice(device));
+    { int rc = upload_tables(device); if (rc) return rc; }
+
+    tamcmc_gpu_ctx* c = new tamcmc_gpu_ctx();
+    c->device = device; c->nstars = nstars; c->Nchains = Nchains; c->p = p;
+    c->h_stars.resize(nstars);
+    long long off = 0; int tiles = 0; int maxN = 0;
+    for (int s = 0; s < nstars; s++) {
+        const tamcmc_gpu_star& in = stars[s];
+        StarDesc& sd = c->h_stars[s];
+        const int nm = modes_of(in.model_id, in.plength);
+        if (nm < 0) { delete c; return TAMCMC_ERR_MODEL; }
+        int need = 0;
+        for (int k = 0; k < 11; k++) { if (in.plength[k] < 0) { delete c; return TAMCMC_ERR_ARG; } need += in.plength[k]; }
+        if (!in.x || !in.y || in.N < 2 || in.N > 2000000000L || in.Nparams < need || nm == 0) { delete c; return TAMCMC_ERR_ARG; }
+        if (in.model_id == 3 || in.model_id == 6 || in.model_id == 12 || in.model_id == 13) {
+            // the reference indexes fl_l[n] for n < Nmax and l <= lmax (models.cpp:2026-2075)
+            for (int l = 0; l <= in.plength[1] && l <= 3; l++)
+                if (in.plength[2 + l] < in.plength[0]) { delete c; return TAMCMC_ERR_ARG; }
+            if (in.plength[1] > 3 || in.plength[0] < 2) { delete c; return TAMCMC_ERR_ARG; }
+        }
+        if ((in.model_id == 23) && (in.plength[0] < 2 || in.plength[2] < 2)) { delete c; return TAMCMC_ERR_ARG; }
+        sd.off = off;
+        sd.Nloc = (int)in.N;
+        const bool sharded = in.N_global > 0;
+        sd.Nglob = sharded ? (int)in.N_global : (int)in.N;
+        sd.bin0 = sharded ? (int)in.bin_offset : 0;
+        sd.x0 = sharded ? in.x_first : in.x[0];
+        sd.xlast = sharded ? in.x_last : in.x[in.N - 1];
+        sd.step = sharded ? (in.x_second - in.x_first) : (in.x[1] - in.x[0]);
+        if (sharded && (in.bin_offset < 0 || in.bin_offset + in.N > in.N_global)) { delete c; return TAMCMC_ERR_ARG; }
+        sd.ntiles = (sd.Nloc + TAMCMC_TILE - 1) / TAMCMC_TILE;
+        sd.tile0 = tiles;
+        sd.model_id = in.model_id;
+        sd.Nparams = in.Nparams;
+        sd.nmodes_cap = nm;
+        for (int k = 0; k < 11; k++) sd.plength[k] = in.plength[k];
+        tiles += sd.ntiles;
+        off += (long long)sd.ntiles * TAMCMC_TILE;
+        if (in.Nparams > c->params_stride) c->params_stride = in.Nparams;
+        if (nm > c->modes_stride) c->modes_stride = nm;
+        if (sd.ntiles > c->tiles_stride) c->tiles_stride = sd.ntiles;
+        if (sd.Nloc > maxN) maxN = sd.Nloc;
+    }
+    c->total_tiles = tiles;
+    c->total_bins_padded = off;
+    const int SC = c->SC();
+
+#define CKC(call)                                                                  \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) { int rc__ = fail_cuda(e__, #call); tamcmc_gpu_destroy(c); return rc__; } \
+    } while (0)
+
+    CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) CKC(cudaEventCreate(&c->ev[i]));
+    CKC(cudaMalloc(&c->d_stars, sizeof(StarDesc) * nstars));
+    CKC(cudaMalloc(&c->d_tile_star, sizeof(int) * tiles));
+    CKC(cudaMalloc(&c->d_x, sizeof(double) * off));
+    CKC(cudaMalloc(&c->d_y, sizeof(double) * off));
+    CKC(cudaMalloc(&c->d_lnx, sizeof(double) * off));
+    CKC(cudaMalloc(&c->d_params, sizeof(double) * ((size_t)SC * c->params_stride + 64)));
+    CKC(cudaMemset(c->d_params, 0, sizeof(double) * ((size_t)SC * c->params_stride + 64)));
+    CKC(cudaMalloc(&c->d_active, (size_t)SC));
+    CKC(cudaMalloc(&c->d_modes, sizeof(ModeRec) * (size_t)SC * c->modes_stride));
+    CKC(cudaMalloc(&c->d_comps, sizeof(CompRec) * (size_t)SC * c->modes_stride * TAMCMC_MAX_COMP_PER_MODE));
+    CKC(cudaMalloc(&c->d_noise, sizeof(NoiseRec) * (size_t)SC));
+    CKC(cudaMalloc(&c->d_asym, sizeof(int) * (size_t)SC));
+    CKC(cudaMalloc(&c->d_Tcoefs, sizeof(double) * Nchains));
+    CKC(cudaMalloc(&c->d_partial, sizeof(double) * (size_t)SC * c->tiles_stride));
+    CKC(cudaMalloc(&c->d_counters, sizeof(unsigned int) * (size_t)SC));
+    CKC(cudaMemset(c->d_counters, 0, sizeof(unsigned int) * (size_t)SC));
+    CKC(cudaMalloc(&c->d_out, c->out_bytes()));
+    CKC(cudaMemset(c->d_out, 0, c->out_bytes()));
+    CKC(cudaMalloc(&c->d_model, sizeof(double) * (size_t)maxN));
+    CKC(cudaMallocHost(&c->h_params, sizeof(double) * (size_t)SC * c->params_stride));
+    CKC(cudaMallocHost(&c->h_active, (size_t)SC));
+    CKC(cudaMallocHost(&c->h_out, c->out_bytes()));
+
+    // upload spectra (padded to a multiple of the tile: x pad = last x, y pad = 0)
+    {
+        std::vector<double> hx((size_t)off), hy((size_t)off, 0.0);
+        std::vector<int> ts((size_t)tiles);
+        for (int s = 0; s < nstars; s++) {
+            const StarDesc& sd = c->h_stars[s];
+            std::memcpy(&hx[(size_t)sd.off], stars[s].x, sizeof(double) * (size_t)sd.Nloc);
+            std::memcpy(&hy[(size_t)sd.off], stars[s].y, sizeof(double) * (size_t)sd.Nloc);
+            for (long long i = sd.Nloc; i < (long long)sd.ntiles * TAMCMC_TILE; i++) hx[(size_t)(sd.off + i)] = stars[s].x[sd.Nloc - 1];
+            for (int t = 0; t < sd.ntiles; t++) ts[(size_t)(sd.tile0 + t)] = s;
+        }
+        CKC(cudaMemcpy(c->d_x, hx.data(), sizeof(double) * off, cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(c->d_y, hy.data(), sizeof(double) * off, cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(c->d_tile_star, ts.data(), sizeof(int) * tiles, cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(c->d_stars, c->h_stars.data(), sizeof(StarDesc) * nstars, cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(c->d_Tcoefs, Tcoefs, sizeof(double) * Nchains, cudaMemcpyHostToDevice));
+        CKC(tamcmc_launch_lnx(c->d_x, c->d_lnx, off, c->stream));
+        c->launches += 1;
+        CKC(cudaStreamSynchronize(c->stream));
+    }
+#undef CKC
+    *out = c;
+    return TAMCMC_OK;
+}
+
+void tamcmc_gpu_destroy(tamcmc_gpu_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_stars); cudaFree(c->d_tile_star); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx);
+    cudaFree(c->d_params); cudaFree(c->d_active); cudaFree(c->d_modes); cudaFree(c->d_comps); cudaFree(c->d_noise);
+    cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_counters); cudaFree(c->d_out);
+    cudaFree(c->d_model);
+    if (c->h_params) cudaFreeHost(c->h_params);
+    if (c->h_active) cudaFreeHost(c->h_active);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int tamcmc_gpu_params_stride(const tamcmc_gpu_ctx* c) { return c ? c->params_stride : 0; }
+int tamcmc_gpu_nstars(const tamcmc_gpu_ctx* c) { return c ? c->nstars : 0; }
+int tamcmc_gpu_nchains(const tamcmc_gpu_ctx* c) { return c ? c->Nchains : 0; }
+long tamcmc_gpu_launch_count(const tamcmc_gpu_ctx* c) { return c ? c->launches : 0; }
+
+int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char* active_mask,
+                    double* logL_out, int* status_out)
+{
+    if (!c || !params || !logL_out) return TAMCMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    const int SC = c->SC();
+    const size_t pbytes = sizeof(double) * (size_t)SC * c->params_stride;
+    std::memcpy(c->h_params, params, pbytes);
+    CK(cudaMemcpyAsync(c->d_params, c->h_params, pbytes, cudaMemcpyHostToDevice, c->stream));
+    const unsigned char* d_act = nullptr;
+    if (active_mask) {
+        std::memcpy(c->h_active, active_mask, (size_t)SC);
+        CK(cudaMemcpyAsync(c->d_active, c->h_active, (size_t)SC, cudaMemcpyHostToDevice, c->stream));
+        d_act = c->d_active;
+    }
+    { int rc = launch_eval(c, c->d_params, d_act, c->d_logL(), 0, c->stream); if (rc) return rc; }
+    CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    { int rc = collect_profile(c); if (rc) return rc; }
+    std::memcpy(logL_out, c->h_out, sizeof(double) * (size_t)SC);
+    const int* st = reinterpret_cast<const int*>(reinterpret_cast<const double*>(c->h_out) + SC);
+    if (status_out) std::memcpy(status_out, st, sizeof(int) * (size_t)SC);
+    c->pairs_last = -1;
+    return status_to_rc(st, SC);
+}
+
+int tamcmc_gpu_eval_device(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active,
+                           double* d_logL, int raw_sum, void* stream)
+{
+    if (!c || !d_params || !d_logL) return TAMCMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c->stream;
+    return launch_eval(c, d_params, d_active, d_logL, raw_sum, st);
+}
+
+int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, double* model_out)
+{
+    if (!model_out) return TAMCMC_ERR_ARG;
+    { int rc = expand_single(c, star, params_row); if (rc) return rc; }
+    const StarDesc& sd = c->h_stars[star];
+    WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0);
+    wa.tile_begin = sd.tile0; wa.chain_begin = 0;
+    CK(tamcmc_launch_whittle(wa, sd.ntiles, 1, true, c->stream));
+    c->launches += 1;
+    CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int SC = c->SC();
+    const int* st = reinterpret_cast<const int*>(reinterpret_cast<const double*>(c->h_out) + SC);
+    const int s0 = st[star * c->Nchains];
+    if (s0 & TAMCMC_ST_BADCFG) return TAMCMC_ERR_MODEL;
+    if (s0 & TAMCMC_ST_WINDOW) return TAMCMC_ERR_WINDOW;
+    if (s0 & TAMCMC_ST_NONFINITE) return TAMCMC_ERR_NONFINITE;
+    CK(cudaMemcpy(model_out, c->d_model, sizeof(double) * (size_t)sd.Nloc, cudaMemcpyDeviceToHost));
+    return TAMCMC_OK;
+}
+
+int tamcmc_gpu_windows(tamcmc_gpu_ctx* c, int star, const double* params_row, int cap,
+                       int* nmodes, int* l, int* imin, int* imax)
+{
+    if (!nmodes || !l || !imin || !imax || cap < 0) return TAMCMC_ERR_ARG;
+    { int rc = expand_single(c, star, params_row); if (rc) return rc; }
+    const StarDesc& sd = c->h_stars[star];
+    std::vector<ModeRec> mr((size_t)sd.nmodes_cap);
+    const size_t sc = (size_t)star * c->Nchains;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(mr.data(), c->d_modes + sc * c->modes_stride, sizeof(ModeRec) * mr.size(), cudaMemcpyDeviceToHost));
+    int st = 0;
+    CK(cudaMemcpy(&st, c->d_status() + sc, sizeof(int), cudaMemcpyDeviceToHost));
+    *nmodes = sd.nmodes_cap;
+    for (int i = 0; i < sd.nmodes_cap && i < cap; i++) { l[i] = mr[i].l; imin[i] = mr[i].i0; imax[i] = mr[i].i1; }
+    if (st & TAMCMC_ST_BADCFG) return TAMCMC_ERR_MODEL;
+    if (st & TAMCMC_ST_WINDOW) return TAMCMC_ERR_WINDOW;
+    if (st & TAMCMC_ST_NONFINITE) return TAMCMC_ERR_NONFINITE;
+    return TAMCMC_OK;
+}
+
+int tamcmc_gpu_components(tamcmc_gpu_ctx* c, int star, const double* params_row, int cap,
+                          int* ncomp, int* mode_index, int* m, double* nu, double* height, double* width)
+{
+    if (!ncomp || cap < 0) return TAMCMC_ERR_ARG;
+    { int rc = expand_single(c, star, params_row); if (rc) return rc; }
+    const StarDesc& sd = c->h_stars[star];
+    const size_t sc = (size_t)star * c->Nchains;
+    std::vector<ModeRec> mr((size_t)sd.nmodes_cap);
+    std::vector<CompRec> cr((size_t)sd.nmodes_cap * TAMCMC_MAX_COMP_PER_MODE);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(mr.data(), c->d_modes + sc * c->modes_stride, sizeof(ModeRec) * mr.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cr.data(), c->d_comps + sc * c->modes_stride * TAMCMC_MAX_COMP_PER_MODE, sizeof(CompRec) * cr.size(), cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int i = 0; i < sd.nmodes_cap; i++)
+        for (int k = 0; k < mr[i].ncomp; k++) {
+            const CompRec& q = cr[(size_t)i * TAMCMC_MAX_COMP_PER_MODE + k];
+            if (n < cap) {
+                if (mode_index) mode_index[n] = i;
+                if (m) m[n] = q.m;
+                if (nu) nu[n] = q.nu;
+                if (height) height[n] = (q.flags & TAMCMC_CF_FAST) ? 1.0 / q.a : q.a;
+                if (width) width[n] = mr[i].gamma;
+            }
+            n++;
+        }
+    *ncomp = n;
+    return TAMCMC_OK;
+}
+
+long tamcmc_gpu_pairs_last(tamcmc_gpu_ctx* c)
+{
+    if (!c) return -1;
+    if (c->pairs_last >= 0) return c->pairs_last;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    const int SC = c->SC();
+    std::vector<ModeRec> mr((size_t)SC * c->modes_stride);
+    std::vector<int> st((size_t)SC);
+    if (cudaMemcpy(mr.data(), c->d_modes, sizeof(ModeRec) * mr.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (cudaMemcpy(st.data(), c->d_status(), sizeof(int) * SC, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    long P = 0;
+    for (int sc = 0; sc < SC; sc++) {
+        if (st[sc]) continue;
+        const StarDesc& sd = c->h_stars[sc / c->Nchains];
+        for (int i = 0; i < sd.nmodes_cap; i++) {
+            const ModeRec& r = mr[(size_t)sc * c->modes_stride + i];
+            long lo = r.i0 > sd.bin0 ? r.i0 : sd.bin0, hi = r.i1 < sd.bin0 + sd.Nloc ? r.i1 : sd.bin0 + sd.Nloc;
+            if (hi > lo) P += (long)(2 * r.l + 1) * (hi - lo);
+        }
+    }
+    c->pairs_last = P;
+    return P;
+}
+
+int tamcmc_gpu_set_profiling(tamcmc_gpu_ctx* c, int on)
+{
+    if (!c) return TAMCMC_ERR_ARG;
+    c->profiling = on != 0;
+    c->nlaunch_prof = 0; c->expand_ms = 0; c->whittle_ms = 0;
+    return TAMCMC_OK;
+}
+
+int tamcmc_gpu_get_kernel_ms(tamcmc_gpu_ctx* c, long* nlaunch, double* expand_ms_total, double* whittle_ms_total)
+{
+    if (!c) return TAMCMC_ERR_ARG;
+    if (nlaunch) *nlaunch = c->nlaunch_prof;
+    if (expand_ms_total) *expand_ms_total = c->expand_ms;
+    if (whittle_ms_total) *whittle_ms_total = c->whittle_ms;
+    return TAMCMC_OK;
+}
+
+int tamcmc_gpu_sync(tamcmc_gpu_ctx* c)
+{
+    if (!c) return TAMCMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return collect_profile(c);
+}
+
+int tamcmc_gpu_fp64_peak(int device, double* tflops)
+{
+    if (!tflops) return TAMCMC_ERR_ARG;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    if (ndev <= 0 || device < 0 || device >= ndev) { g_last_error = "no usable CUDA device"; return TAMCMC_ERR_CUDA; }
+    CK(cudaSetDevice(device));
+    float ms = 0;
+    CK(tamcmc_fp64_peak(tflops, &ms, 4096));
+    return TAMCMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// kernels.h -- launch interfaces between capi.cu and the kernel translation units.
+#pragma once
+#include "tamcmc_dev.h"
+#include <cuda_runtime.h>
+
+struct ExpandArgs {
+    const StarDesc* stars;
+    const double* params;            // [nstars*Nchains][params_stride]
+    const unsigned char* active;     // [nstars*Nchains] or nullptr
+    ModeRec* modes;                  // [nstars*Nchains][modes_stride]
+    CompRec* comps;                  // [nstars*Nchains][modes_stride*7]
+    NoiseRec* noise;                 // [nstars*Nchains]
+    int* status;                     // [nstars*Nchains]
+    int* asym_flag;                  // [nstars*Nchains]
+    double* out_logL;                // [nstars*Nchains] (NaN written for non-OK chains)
+    int Nchains;
+    int params_stride;
+    int modes_stride;
+};
+
+struct WhittleArgs {
+    const StarDesc* stars;
+    const int* tile_star;            // [total_tiles] flat tile -> star
+    const double* x;                 // concatenated local bins
+    const double* y;
+    const double* lnx;
+    const ModeRec* modes;
+    const CompRec* comps;
+    const NoiseRec* noise;
+    const int* status;
+    const int* asym_flag;
+    const double* Tcoefs;            // [Nchains]
+    double* partial;                 // [nstars*Nchains][tiles_stride]
+    unsigned int* counters;          // [nstars*Nchains] tile tickets (self-resetting)
+    double* out;                     // [nstars*Nchains]: tempered logL, or raw sum S if raw_sum
+    double* model_out;               // WRITE_MODEL: [Nloc] of the selected star, chain 0
+    double p;                        // likelihood parameter (truncated to long like model_def.cpp:399)
+    int Nchains;
+    int modes_stride;
+    int tiles_stride;
+    int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)
+    int tile_begin;                  // grid offset: flat tile = blockIdx.x + tile_begin
+    int chain_begin;                 // chain = blockIdx.y + chain_begin
+};
+
+cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const double* Q);
+cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
+cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int total_tiles, int nchains_total, bool write_model, cudaStream_t st);
+cudaError_t tamcmc_whittle_configure();   // one-time function attributes
+cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st);
+// DFMA throughput microbenchmark: returns achieved FP64 TFLOP/s (2 flops per DFMA)
+cudaError_t tamcmc_fp64_peak(double* tflops, float* ms, int iters);

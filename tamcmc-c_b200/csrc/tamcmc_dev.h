@@ -1,0 +1,72 @@
+// tamcmc_dev.h -- device-side data layout shared by the expander, the fused
+// model+Whittle kernel and the C-ABI implementation.  Not part of the public ABI.
+//
+// HBM layout per context (see DESIGN.md "Data layout in HBM"):
+//   x, y, lnx        : one concatenated FP64 array each over all stars' local bins
+//   params           : [nstars][Nchains][Nparams_max] FP64, row-major (uploaded every step)
+//   modes / comps    : [nstars][Nchains][max_modes] ModeRec, [..][max_modes*7] CompRec
+//   noise            : [nstars][Nchains] NoiseRec
+//   partial          : [nstars][Nchains][max_tiles] FP64 per-tile partial sums
+//   out              : [nstars*Nchains] FP64 logL followed by [nstars*Nchains] int32 status
+#pragma once
+#include <cstdint>
+
+#define TAMCMC_MAX_COMP_PER_MODE 7   // l <= 3 -> 2l+1 <= 7 (reference: acoefs.cpp supports l<=3)
+#define TAMCMC_MAX_HARVEY 8
+#define TAMCMC_TILE 1024             // bins per CTA tile
+#define TAMCMC_THREADS 128           // threads per CTA (8 bins per thread)
+#define TAMCMC_BINS_PER_THREAD (TAMCMC_TILE / TAMCMC_THREADS)
+
+// per-chain status bits (device -> host)
+#define TAMCMC_ST_OK 0
+#define TAMCMC_ST_WINDOW 1      // set_imin_imax: imax-imin <= 0 (reference: exit, build_lorentzian.cpp:650-665)
+#define TAMCMC_ST_NONFINITE 2   // NaN/Inf in a derived mode quantity
+#define TAMCMC_ST_BADCFG 4      // unsupported configuration value (e.g. filter_code, decompose_Alm)
+#define TAMCMC_ST_INACTIVE 8    // active_mask[chain]==0: prior short-circuit (model_def.cpp:476-480)
+
+// component flags
+#define TAMCMC_CF_FAST 1        // scaled form t' = (1+e^2)/A, merged with 2 FP64 ops
+#define TAMCMC_CF_SLOW 2        // general form (A, t), merged with 3 FP64 ops (extreme dynamic range)
+
+struct __align__(16) ModeRec {
+    int i0, i1;          // GLOBAL bin window [i0, i1)  (set_imin_imax, bit-exact)
+    int l;               // degree
+    int ncomp;           // number of live components (height != 0)
+    double fc;           // central frequency fc_l
+    double gamma;        // width
+    double qa;           // asym / fc
+    double qb0;          // 1 - asym                    (w(x) = qb0 + x*qa)
+    double qc;           // (0.5*gamma*asym/fc)^2
+    double pad;
+};
+
+struct __align__(8) CompRec {
+    double nu;           // nu_nlm
+    double s;            // FAST: 2/(gamma*sqrt(A)) ; SLOW: 2/gamma
+    double a;            // FAST: 1/A               ; SLOW: A
+    int flags; int m;
+};
+
+struct NoiseRec {
+    int nh;                              // live Harvey terms (tau != 0 and H != 0)
+    int pad;
+    double N0;                           // white noise
+    double H[TAMCMC_MAX_HARVEY];         // heights
+    double lnsc[TAMCMC_MAX_HARVEY];      // ln(1e-3 * tau)
+    double pw[TAMCMC_MAX_HARVEY];        // exponents
+};
+
+struct StarDesc {
+    long long off;       // offset of this star's local bins in the concatenated x/y/lnx arrays
+    int Nloc;            // local bins held by this context
+    int Nglob;           // bins of the whole spectrum (window clipping)
+    int bin0;            // global index of local bin 0
+    int tile0;           // first flat tile index
+    int ntiles;
+    int model_id;
+    int Nparams;
+    int nmodes_cap;      // modes per chain (capacity == exact count for the MS families)
+    int plength[11];
+    double x0, xlast;    // global x[0], x[N-1]
+    double step;         // x[1]-x[0] (MS models, models.cpp:1952) or x[2]-x[1] (RGB v4, models.cpp:4714)
+};

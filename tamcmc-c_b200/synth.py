@@ -1,0 +1,144 @@
+"""Synthetic Kepler-like inputs for the hot path (fixed seeds; numpy only).
+
+Parameter-vector layouts follow the reference's `.model` reader:
+plength = [Nmax, lmax, Nfl0, Nfl1, Nfl2, Nfl3, Nsplit, Nwidth, Nnoise, Ninc, Ncfg]
+(tamcmc/sources/io_ms_global.cpp:1315-1325) and
+params  = [H | V_l | fl0 | fl1 | fl2 | fl3 | split | W | noise | inc | cfg]
+(tamcmc/sources/io_ms_global.cpp:1329-1398).  The recipes are the ones SURVEY.md 8(d)
+names; `make_params_aj_model` mirrors the input recipe of the reference's own unit test
+(test/lorentzian_test/unit_tests/test_build_l_mode.cpp:769-874) with a fixed seed.
+"""
+import numpy as np
+
+# Kepler long-cadence-free resolution used by the reference tests:
+# test/lorentzian_test/unit_tests/test_build_l_mode.cpp:107
+RESOL_4YR = 1e6 / (4.0 * 365.0 * 86400.0)
+
+MODEL_CLASSIC = 3
+MODEL_A1L_ETAA3 = 6
+MODEL_LOCAL_BASIC = 11
+MODEL_CLASSIC_V2 = 12
+MODEL_CLASSIC_V3 = 13
+MODEL_AJALM = 21
+MODEL_AJ = 23
+
+
+def freq_axis(N, x0, step=RESOL_4YR):
+    return x0 + step * np.arange(N, dtype=np.float64)
+
+
+def tcoefs(Nchains, lam):
+    """T_m = lambda^m (Config/default/config_default.cfg: Tcoef)."""
+    return lam ** np.arange(Nchains, dtype=np.float64)
+
+
+def ms_global_modes(rng, Nmax=20, lmax=3, f0=650.0, dnu=85.0, scatter=0.01):
+    """Central frequencies fl[l][n] of a main-sequence comb."""
+    n = np.arange(Nmax)
+    off = {0: 0.0, 1: 0.5 * dnu - 2.0, 2: -6.0, 3: 0.5 * dnu - 14.0}
+    fl = []
+    for l in range(lmax + 1):
+        fl.append(f0 + dnu * n + off[l] + rng.uniform(-scatter * dnu, scatter * dnu, Nmax))
+    return fl
+
+
+def classic_params(rng, Nmax=20, lmax=3, f0=650.0, dnu=85.0, asym=0.0, inc=45.0, a1=1.0, a3=0.01,
+                   trunc_c=30.0, do_amp=0, noise=None, wmin=1.0, wmax=8.0):
+    """model_MS_Global_a1etaa3_HarveyLike_Classic (models.cpp:1943): Nsplit=6
+    [a1, eta, a3, magb, magalfa, asym], Ninc=1, Ncfg=2."""
+    if noise is None:
+        noise = [0.0, 0.0, 1.0, 1.0, 100.0, 2.0, 0.5, 10.0, 2.0, 0.1]
+    fl = ms_global_modes(rng, Nmax, lmax, f0, dnu)
+    n = np.arange(Nmax)
+    H = rng.uniform(10.0, 20.0, Nmax)
+    W = wmin + (wmax - wmin) * (0.5 - 0.5 * np.cos(np.pi * n / max(Nmax - 1, 1))) + rng.uniform(0, 0.05, Nmax)
+    V = np.array([1.5, 0.53, 0.08])[:lmax]
+    split = np.array([a1, 0.0, a3, 0.0, 0.0, asym])
+    params = np.concatenate([H, V] + fl + [split, W, np.asarray(noise, float), [inc], [trunc_c, float(do_amp)]])
+    plength = np.array([Nmax, lmax] + [Nmax if l <= lmax else 0 for l in range(4)] +
+                       [len(split), Nmax, len(noise), 1, 2], dtype=np.int32)
+    return params, plength
+
+
+def aj_params(rng, Nmax=20, lmax=3, f0=650.0, dnu=85.0, asym=0.0, inc=45.0, a1=1.0, trunc_c=30.0,
+              do_amp=0, noise=None, eta_switch=1.0, wmin=1.0, wmax=8.0):
+    """model_MS_Global_aj_HarveyLike (models.cpp:1195): Nsplit=14 =
+    [a1_0,a1_1, a2_0,a2_1, ..., a6_0,a6_1, eta_switch, asym]."""
+    if noise is None:
+        noise = [0.0, 0.0, 1.0, 1.0, 100.0, 2.0, 0.5, 10.0, 2.0, 0.1]
+    fl = ms_global_modes(rng, Nmax, lmax, f0, dnu)
+    n = np.arange(Nmax)
+    H = rng.uniform(10.0, 20.0, Nmax)
+    W = wmin + (wmax - wmin) * (0.5 - 0.5 * np.cos(np.pi * n / max(Nmax - 1, 1))) + rng.uniform(0, 0.05, Nmax)
+    V = np.array([1.5, 0.53, 0.08])[:lmax]
+    aj = np.zeros(12)
+    aj[0] = a1
+    aj[1] = 0.02
+    aj[2] = rng.uniform(-0.1 * a1, 0.1 * a1)
+    aj[4] = rng.uniform(-0.025 * a1, 0.025 * a1)
+    aj[6] = rng.uniform(-0.025 * a1, 0.025 * a1)
+    aj[8] = rng.uniform(-0.01 * a1, 0.01 * a1)
+    aj[10] = rng.uniform(-0.005 * a1, 0.005 * a1)
+    split = np.concatenate([aj, [eta_switch, asym]])
+    params = np.concatenate([H, V] + fl + [split, W, np.asarray(noise, float), [inc], [trunc_c, float(do_amp)]])
+    plength = np.array([Nmax, lmax] + [Nmax if l <= lmax else 0 for l in range(4)] +
+                       [len(split), Nmax, len(noise), 1, 2], dtype=np.int32)
+    return params, plength
+
+
+def make_params_aj_model(rng, lmax, Nfreqs, Dnu, epsilon, d0l, asym_on=None):
+    """The reference unit test's input recipe for model_MS_Global_aj_HarveyLike
+    (test_build_l_mode.cpp:769-874), seeded.  Note the reference's `el/2` is an
+    INTEGER division (el is int)."""
+    trunc = 50.0
+    fl = []
+    for el in range(lmax + 1):
+        for en in range(Nfreqs):
+            sc = rng.uniform(-Dnu / 100, Dnu / 100)
+            fl.append((en + epsilon + el // 2) * Dnu + d0l * el * (el + 1) + sc)
+    fl = np.array(fl)
+    aj = np.zeros(13)
+    aj[0] = rng.uniform(0.1, 5)
+    aj[2] = rng.uniform(-0.1 * aj[0], 0.1 * aj[0])
+    aj[4] = rng.uniform(-0.025 * aj[0], 0.025 * aj[0])
+    aj[6] = rng.uniform(-0.025 * aj[0], 0.025 * aj[0])
+    aj[8] = rng.uniform(-0.01 * aj[0], 0.01 * aj[0])
+    aj[10] = rng.uniform(-0.005 * aj[0], 0.005 * aj[0])
+    aj[12] = 0.0
+    if asym_on is None:
+        asym_on = bool(rng.integers(0, 2))
+    asym = rng.uniform(-100, 100.0) if asym_on else 0.0
+    vis = np.array([1.5, 0.53, 0.07])[:lmax]
+    H = rng.uniform(10, 20, Nfreqs)
+    W = rng.uniform(0.5, 2, Nfreqs)
+    noise = np.array([0, 1, 1, 0, 1, 1, 0.1], float)
+    inc = rng.uniform(0.0, 90.0)
+    params = np.concatenate([H, vis, fl, aj, [asym], W, noise, [inc], [trunc, 0.0], [0.0]])
+    Nfl = [Nfreqs if l <= lmax else 0 for l in range(4)]
+    plength = np.array([Nfreqs, lmax] + Nfl + [len(aj) + 1, Nfreqs, len(noise), 1, 2], dtype=np.int32)
+    return params, plength
+
+
+def perturb_chains(rng, params, plength, Nchains, rel=0.01):
+    """Chain parameter vectors = truth + small perturbations of the fitted quantities
+    (heights, frequencies, widths, noise); configuration slots are left untouched."""
+    Nmax, lmax = int(plength[0]), int(plength[1])
+    Nf = int(plength[2] + plength[3] + plength[4] + plength[5])
+    Nsplit, Nwidth, Nnoise, Ninc = (int(plength[i]) for i in (6, 7, 8, 9))
+    P = np.tile(params, (Nchains, 1))
+    o = 0
+    P[:, o:o + Nmax] *= 1 + rel * rng.standard_normal((Nchains, Nmax)); o += Nmax
+    P[:, o:o + lmax] *= 1 + rel * rng.standard_normal((Nchains, lmax)); o += lmax
+    P[:, o:o + Nf] += 0.1 * rel * 85.0 * rng.standard_normal((Nchains, Nf)); o += Nf
+    o += Nsplit
+    P[:, o:o + Nwidth] *= 1 + rel * rng.standard_normal((Nchains, Nwidth)); o += Nwidth
+    nz = params[o:o + Nnoise] != 0
+    P[:, o:o + Nnoise][:, nz] *= 1 + rel * rng.standard_normal((Nchains, int(nz.sum()))); o += Nnoise
+    P[:, o:o + Ninc] += rel * 10 * rng.standard_normal((Nchains, Ninc))
+    P[0] = params
+    return np.ascontiguousarray(P)
+
+
+def chi2_2dof_spectrum(rng, model):
+    """y_i = M_i * E_i, E ~ Exp(1): a chi^2 with 2 d.o.f. power spectrum around the model."""
+    return model * rng.exponential(1.0, size=model.shape)
