@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- likelihood evaluations/s of the fused model + Whittle logL hot path.
+
+Workload (BASELINE.json configs[1], "C2"): MS_Global a1etaa3 HarveyLike (Classic) fit, 20 radial
+orders l=0..3 (80 modes, 320 Lorentzian components), 10 parallel-tempered chains, 250 000-bin
+synthetic Kepler-like spectrum.  One "step" = one MCMC step's worth of likelihood work for one star:
+all 10 chains evaluated in one batched launch.  With N GPUs every rank holds its own independent
+star (stars shard one-to-one over GPUs with no data-path collective: weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            -> this repo's CUDA path
+  python bench.py --impl reference [...]                          -> the reference's CPU algorithm
+                                                                    (oracle port)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NBINS = 250000
+NCHAINS = 10
+LAMBDA_T = 1.7
+WORKLOAD = "C2: MS_Global a1etaa3 HarveyLike Classic, Nmax=20 lmax=3 (80 modes/320 components), 10 chains, 250k bins"
+METRIC = "likelihood evals/sec (model+Whittle logL, all tempered chains)"
+
+
+def make_star(synth, star_index):
+    """Synthetic C2 star: seed 12345 + star index."""
+    rng = np.random.default_rng(12345 + star_index)
+    params, pl = synth.classic_params(rng)
+    x = synth.freq_axis(NBINS, 500.0)
+    return rng, params, pl, x
+
+
+def algorithmic_flops(P_pairs, P_asym, nbins, nchains):
+    """F_alg = 6 P + 7 P_asym + 20 N per evaluation (P summed over chains here)."""
+    return 6.0 * P_pairs + 7.0 * P_asym + 20.0 * nbins * nchains
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(synth, seconds=12.0, nthreads=0):
+    """The oracle port (reference algorithm, OpenMP over chains like MALA.cpp:648) timed on the host
+    cores on a bounded sample of the same workload.  Test/benchmark infrastructure only."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    O = _oracle.get()
+    rng, params, pl, x = make_star(synth, 0)
+    rc, M = O.call_model(3, params, pl, x)
+    y = synth.chi2_2dof_spectrum(rng, M)
+    P = synth.perturb_chains(rng, params, pl, NCHAINS)
+    T = synth.tcoefs(NCHAINS, LAMBDA_T)
+    cores = os.cpu_count() or 1
+    O.eval_chains(3, P, pl, x, y, T, nthreads=nthreads)    # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        O.eval_chains(3, P, pl, x, y, T, nthreads=nthreads)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds and n >= 3:
+            break
+    out = {"value": NCHAINS * n / el, "unit": "evals/s", "cores": min(cores, NCHAINS) if nthreads == 0 else nthreads,
+           "host_cores": cores, "kind": "port",
+           "sample": "%d full 10-chain C2 steps (%.1f s), reference-faithful port: per-mode full-vector copies + multi-pass temporaries, one OpenMP thread per chain" % (n, el)}
+    if hasattr(O.L, "orc_eval_chains_fast"):
+        O.eval_chains(3, P, pl, x, y, T, nthreads=nthreads, fast=True)
+        n2, t0 = 0, time.perf_counter()
+        while True:
+            O.eval_chains(3, P, pl, x, y, T, nthreads=nthreads, fast=True)
+            n2 += 1
+            el2 = time.perf_counter() - t0
+            if el2 >= seconds / 3 and n2 >= 3:
+                break
+        out["best_effort_value"] = NCHAINS * n2 / el2
+        out["best_effort_note"] = "same arithmetic, window-only single pass, no copies"
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference itself does not
+    build here (needs Eigen/Boost/GSL), so this is the oracle port with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g
+    synth = g.load_package().synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    O = _oracle.get()
+    rng, params, pl, x = make_star(synth, 0)
+    rc, M = O.call_model(3, params, pl, x)
+    y = synth.chi2_2dof_spectrum(rng, M)
+    P = synth.perturb_chains(rng, params, pl, NCHAINS)
+    T = synth.tcoefs(NCHAINS, LAMBDA_T)
+    cores = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 1)):
+        O.eval_chains(3, P, pl, x, y, T)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.eval_chains(3, P, pl, x, y, T)
+    el = time.perf_counter() - t0
+    v = NCHAINS * args.steps / el
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chains": NCHAINS, "bins": NBINS},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": min(cores, NCHAINS), "host_cores": cores, "kind": "port",
+                             "sample": "%d full 10-chain C2 steps; oracle port of the reference algorithm (reference needs Eigen/Boost/GSL: not buildable here)" % args.steps},
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stars-per-gpu", type=int, default=1, help="independent C2 stars batched per launch on each GPU")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 50:
+            args.steps = 50          # bounded: a CPU step is ~0.1-0.3 s
+        return run_reference(args)
+
+    import torch
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    synth = pkg.synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- inputs: this rank's independent star(s); y = M_true * Exp(1) with M_true from the GPU model entry ----
+    S = args.stars_per_gpu
+    stars, Ps = [], []
+    T = synth.tcoefs(NCHAINS, LAMBDA_T)
+    for s in range(S):
+        rng, params, pl, x = make_star(synth, rank * S + s)
+        with pkg.Context(pkg.Star(3, pl, len(params), x, np.ones_like(x)), 1, [1.0], device=local_rank) as c0:
+            M = c0.model(params)
+        y = synth.chi2_2dof_spectrum(rng, M)
+        stars.append(pkg.Star(3, pl, len(params), x, y))
+        Ps.append(synth.perturb_chains(rng, params, pl, NCHAINS))
+    ctx = pkg.Context(stars, NCHAINS, T, device=local_rank)
+    P_host = ctx.pack_params(Ps)
+    evals_per_step = S * NCHAINS
+
+    stream = torch.cuda.current_stream()
+    d_params = torch.tensor(P_host, device="cuda")
+    d_logL = torch.zeros(S * NCHAINS, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MiB > 126 MB L2
+
+    def step_device():
+        ctx.eval_device(d_params.data_ptr(), d_logL.data_ptr(), stream=stream.cuda_stream)
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    L_host, st = ctx.eval(P_host)
+    assert (st == 0).all()
+    assert np.array_equal(L_host.ravel(), d_logL.cpu().numpy()), "device-resident and host entry points disagree"
+    pairs = ctx.pairs_last()
+
+    # ---- timed region 1: device-resident inputs, CUDA events per step, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()
+        ev0[i].record(stream)
+        step_device()
+        ev1[i].record(stream)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    launches = ctx.launch_count() - launches0
+
+    # ---- timed region 2 (e2e): the C-ABI call with HOST buffers, H2D + D2H inside ----
+    for _ in range(3):
+        ctx.eval(P_host)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.eval(P_host)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- kernel-only timing for the roofline: CUDA events around the fused kernel on its launch stream ----
+    ctx.set_profiling(True)
+    for _ in range(min(args.steps, 50)):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.eval_device(d_params.data_ptr(), d_logL.data_ptr())
+        ctx.sync()
+    nprof, expand_ms, whittle_ms = ctx.kernel_ms()
+    ctx.set_profiling(False)
+
+    # ---- max over ranks, aggregate ----
+    t_dev, t_e2e = dev_ms, e2e_s * 1e3
+    if dist:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    total_evals = evals_per_step * args.steps * world
+    value = total_evals / (t_dev * 1e-3)
+    e2e_value = total_evals / (t_e2e * 1e-3)
+
+    if rank == 0:
+        peak_tf = pkg.fp64_peak(local_rank)
+        k_ms = whittle_ms / max(nprof, 1)
+        F = algorithmic_flops(pairs, 0.0, NBINS * S, NCHAINS)
+        achieved = F / (k_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = 24.0 * NBINS * S + 8.0 * P_host.size + 8.0 * S * NCHAINS    # x, y, ln x once per step + params in + logL out
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("whittle_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chains": NCHAINS, "bins": NBINS, "stars_per_gpu": S,
+                       "parallelism": "independent stars, one per GPU, no collective" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB write); inputs 6 MB << L2",
+                       "timing": "sum of per-step CUDA-event durations on the launch stream, max over ranks"},
+            "mcmc_steps_per_s": value / NCHAINS / S if S else None,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(P_host.nbytes),
+                    "d2h_bytes_per_step": int(S * NCHAINS * 12), "ms_per_step": t_e2e / args.steps,
+                    "path": "tamcmc_gpu_eval (C ABI, host buffers, pinned staging, H2D+kernels+D2H+sync per step)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": traffic, "kernel": "tamcmc_whittle_kernel", "kernel_ms": k_ms, "expand_kernel_ms": expand_ms / max(nprof, 1),
+                         "algorithmic_flops_per_launch": F, "pairs_per_launch": pairs,
+                         "peak_source": "DFMA microbenchmark run in this process (tamcmc_gpu_fp64_peak); FP64 is not in MEASURED_PEAKS.json",
+                         "hbm": {"achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "algorithmic_bytes_per_launch": alg_bytes}},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(synth)
+        print(json.dumps(line))
+    ctx.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

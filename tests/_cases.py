@@ -1,0 +1,74 @@
+"""Seeded parameter cases shared by the CPU and GPU parity tests (numpy only)."""
+import numpy as np
+
+
+def _noise_variants(rng, k):
+    base = [
+        [0.0, 0.0, 1.0, 1.0, 100.0, 2.0, 0.5, 10.0, 2.0, 0.1],
+        [2.0, 300.0, 1.7, 1.0, 100.0, 2.3, 0.5, 10.0, 3.9, 0.1],
+        [0.0, 1.0, 1.0, 0.0, 1.0, 1.0, 0.1],
+        [0.3],
+    ]
+    return base[k % len(base)]
+
+
+def ms_case(synth, model_id, seed, N=20000, x0=900.0, step=None, Nmax=6, lmax=3, asym=0.0, do_amp=0,
+            inc=None, a1=None, trunc_c=20.0, f0=None, dnu=None, wmin=0.3, wmax=4.0):
+    """(params, plength, x) for one MS model id with seeded randomised inputs."""
+    rng = np.random.default_rng(seed)
+    step = synth.RESOL_4YR * 4 if step is None else step
+    x = synth.freq_axis(N, x0, step)
+    span = x[-1] - x[0]
+    dnu = span / (Nmax + 1.5) if dnu is None else dnu
+    f0 = x0 + 0.6 * dnu if f0 is None else f0
+    inc = rng.uniform(0.0, 90.0) if inc is None else inc
+    a1 = rng.uniform(0.2, 3.0) if a1 is None else a1
+    noise = _noise_variants(rng, seed)
+    if model_id in (3, 12, 13, 6):
+        params, pl = synth.classic_params(rng, Nmax=Nmax, lmax=lmax, f0=f0, dnu=dnu, asym=asym, inc=inc, a1=a1,
+                                          a3=rng.uniform(-0.05, 0.05), trunc_c=trunc_c, do_amp=do_amp, noise=noise,
+                                          wmin=wmin, wmax=wmax)
+        Nf = Nmax * (lmax + 1)
+        o_split = Nmax + lmax + Nf
+        if model_id == 6:
+            # Nsplit=7: [a1(l=1), eta, a3, magb, magalfa, asym, a1(l=2)] (models.cpp:87-91)
+            split = np.concatenate([params[o_split:o_split + 6], [rng.uniform(0.2, 3.0)]])
+            params = np.concatenate([params[:o_split], split, params[o_split + 6:]])
+            pl = pl.copy(); pl[6] = 7
+        if model_id == 12:
+            # Ninc=9 m-height ratios [l=1: m0,m1 | l=2: m0,m1,m2 | l=3: m0..m3] (models.cpp:2196-2214)
+            o_inc = len(params) - 3
+            ratios = rng.uniform(0.05, 0.6, 9)
+            params = np.concatenate([params[:o_inc], ratios, params[o_inc + 1:]])
+            pl = pl.copy(); pl[9] = 9
+        if model_id == 13:
+            # heights H_nlm in the "inclination" block, indexed (l+1)*n + |m| (models.cpp:2423-2462)
+            o_inc = len(params) - 3
+            ninc = 4 * Nmax + 4
+            hs = rng.uniform(0.5, 8.0, ninc)
+            params = np.concatenate([params[:o_inc], hs, params[o_inc + 1:]])
+            pl = pl.copy(); pl[9] = ninc
+        return params, pl, x
+    if model_id == 23:
+        params, pl = synth.aj_params(rng, Nmax=Nmax, lmax=lmax, f0=f0, dnu=dnu, asym=asym, inc=inc, a1=a1,
+                                     trunc_c=trunc_c, do_amp=do_amp, noise=noise, eta_switch=float(seed % 2),
+                                     wmin=wmin, wmax=wmax)
+        return params, pl, x
+    if model_id == 11:
+        # model_MS_local_basic (models.cpp:3012): per-mode heights and widths, Nsplit=6
+        # [.., eta0, a3, sqrt(a1)cos(i), sqrt(a1)sin(i), asym], white noise only
+        Nfl = [rng.integers(1, 3) if l <= lmax else 0 for l in range(4)]
+        Nf = int(sum(Nfl))
+        fl = np.sort(rng.uniform(x[0] + 0.15 * span, x[-1] - 0.15 * span, Nf))
+        H = rng.uniform(1.0, 20.0, Nf)
+        W = rng.uniform(wmin, wmax, Nf)
+        ci, si = np.sqrt(a1) * np.cos(np.radians(inc)), np.sqrt(a1) * np.sin(np.radians(inc))
+        split = np.array([0.0, rng.uniform(0, 1.5e8), rng.uniform(-0.05, 0.05), ci, si, asym])
+        noise = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.25])
+        params = np.concatenate([H, np.zeros(lmax), fl, split, W, noise, [0.0], [trunc_c, float(do_amp)]])
+        pl = np.array([Nf, lmax] + [int(v) for v in Nfl] + [6, Nf, 7, 1, 2], dtype=np.int32)
+        return params, pl, x
+    raise ValueError(model_id)
+
+
+ALL_MODELS = (3, 6, 11, 12, 13, 23)
