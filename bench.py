@@ -211,10 +211,13 @@ def main():
     P_host = ctx.pack_params(Ps)
     evals_per_step = S * NCHAINS
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # non-default stream: its handle is what the C ABI launches on
+    torch.cuda.set_stream(stream)
     d_params = torch.tensor(P_host, device="cuda")
     d_logL = torch.zeros(S * NCHAINS, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MiB > 126 MB L2
+
+    assert stream.cuda_stream != 0
 
     def step_device():
         ctx.eval_device(d_params.data_ptr(), d_logL.data_ptr(), stream=stream.cuda_stream)

@@ -76,6 +76,10 @@ double Qlm_host(int l, int m)
     return Q;
 }
 
+// function_rot.cpp:90-101: int factorial and combi with INTEGER divisions (combi(n,r) = n!/(n-r)!/r! in int)
+int fact_i(int n) { long f = 1; for (long i = 1; i <= n; i++) f *= i; return (int)f; }
+int combi_i(int n, int r) { return fact_i(n) / fact_i(n - r) / fact_i(r); }
+
 bool g_tables_uploaded[64] = {false};
 
 int upload_tables(int device)
@@ -94,6 +98,20 @@ int upload_tables(int device)
     for (int l = 0; l <= 3; l++)
         for (int m = -l; m <= l; m++) Q[l][m + 3] = Qlm_host(l, m);
     CK(tamcmc_upload_tables(&hi[0][0][0], &lo[0][0][0], &Q[0][0]));
+    {
+        // integer factors of dmm(l, i, 0, beta), i >= 0 (function_rot.cpp:76-88)
+        double coef[4][4][4], nnum[4][4], nden[4];
+        std::memset(coef, 0, sizeof(coef)); std::memset(nnum, 0, sizeof(nnum)); std::memset(nden, 0, sizeof(nden));
+        for (int l = 0; l <= 3; l++) {
+            nden[l] = std::sqrt((double)(fact_i(l) * fact_i(l)));
+            for (int i = 0; i <= l; i++) {
+                nnum[l][i] = std::sqrt((double)(fact_i(l + i) * fact_i(l - i)));
+                for (int s2 = 0; s2 <= l - i; s2++)
+                    coef[l][i][s2] = (double)combi_i(l, l - i - s2) * (double)combi_i(l, s2) * (((l - i - s2) & 1) ? -1.0 : 1.0);
+            }
+        }
+        CK(tamcmc_upload_dmm_tables(&coef[0][0][0], &nnum[0][0], &nden[0]));
+    }
     CK(tamcmc_whittle_configure());
     if (device >= 0 && device < 64) g_tables_uploaded[device] = true;
     return TAMCMC_OK;

@@ -27,6 +27,21 @@
 __constant__ double c_Pslm_hi[7][4][7];
 __constant__ double c_Pslm_lo[7][4][7];
 __constant__ double c_Qlm[4][7];
+// dmm(l, i, 0, beta) for i >= 0 (function_rot.cpp:76-88) with the integer factors tabulated by the host:
+// coef[l][i][s] = combi(l, l-i-s) * combi(l, s) * (-1)^(l-i-s)   (INTEGER-division combi, function_rot.cpp:90-92)
+// nnum[l][i]    = sqrt(factorial(l+i) * factorial(l-i)),  nden[l] = sqrt(factorial(l) * factorial(l))
+__constant__ double c_dmm_coef[4][4][4];
+__constant__ double c_dmm_nnum[4][4];
+__constant__ double c_dmm_nden[4];
+
+cudaError_t tamcmc_upload_dmm_tables(const double* coef, const double* nnum, const double* nden)
+{
+    cudaError_t e = cudaMemcpyToSymbol(c_dmm_coef, coef, sizeof(double) * 4 * 4 * 4);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_dmm_nnum, nnum, sizeof(double) * 4 * 4);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_dmm_nden, nden, sizeof(double) * 4);
+}
 
 cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const double* Q)
 {
@@ -66,43 +81,34 @@ __device__ __forceinline__ dd dd_mul_d_dd(double a, double bhi, double blo)
     return r;
 }
 
-// ---- function_rot.cpp:90-101: int factorial, INTEGER-division combi ----
-__device__ int d_factorial(int n)
+// x^n for a small non-negative integer n by repeated multiplication (the reference calls pow();
+// the two agree to a few ulp, far inside the 1e-10 budget, and nothing here feeds a bin window)
+__device__ __forceinline__ double ipow(double x, int n)
 {
-    long long f = 1;
-    for (long long i = 1; i <= n; i++) f = f * i;
-    return (int)f;
-}
-__device__ double d_combi(int n, int r) { return (double)(d_factorial(n) / d_factorial(n - r) / d_factorial(r)); }
-
-// function_rot.cpp:76-88
-__device__ double d_dmm(int l, int m1, int m2, double beta)
-{
-    double sum = 0, var = 0;
-    for (int s = 0; s <= l - m1; s++) {
-        var = d_combi(l + m2, l - m1 - s) * d_combi(l - m2, s) * (((l - m1 - s) & 1) ? -1.0 : 1.0);
-        var = var * pow(cos(beta / 2.), (double)(2 * s + m1 + m2)) * pow(sin(beta / 2.), (double)(2 * l - 2 * s - m1 - m2));
-        sum = sum + var;
-    }
-    sum = sum * sqrt((double)(d_factorial(l + m1) * d_factorial(l - m1)));
-    sum = sum / sqrt((double)(d_factorial(l + m2) * d_factorial(l - m2)));
-    return sum;
+    double r = 1.0;
+    for (int k = 0; k < n; k++) r *= x;
+    return r;
 }
 
-// function_rot.cpp:15-74: only column l of the rotation matrix is used.  Following the four
-// fill loops, that column ends up as: row i>0: dmm(l,i,0,b); row i<0: dmm(l,-i,0,b)*(-1)^i;
-// row 0: dmm(l,0,0,-b).
-__device__ void d_amplitude_ratio(int l, double beta_deg, double* V)
+// One entry of amplitude_ratio(l, inc) (function_rot.cpp:15-74): V(m=i) = d^l_{i,0}(inc)^2.  Following the four
+// fill loops of function_rot, column l of the matrix holds dmm(l,|i|,0,+-beta) up to a sign, which the square
+// removes; dmm's sum over s (function_rot.cpp:79-83) runs over the host-tabulated integer factors.
+__device__ double d_amplitude_ratio_entry(int l, int i, double beta_deg)
 {
     const double PI = 3.141592653589793238462643;
     const double angle = PI * beta_deg / 180.;
-    for (int i = -l; i <= l; i++) {
-        double v;
-        if (i > 0) v = d_dmm(l, i, 0, angle);
-        else if (i < 0) v = d_dmm(l, -i, 0, angle) * ((i & 1) ? -1.0 : 1.0);
-        else v = d_dmm(l, 0, 0, -angle);
-        V[i + l] = v * v;
+    const int a = i < 0 ? -i : i;
+    double si, co;
+    sincos(angle / 2., &si, &co);
+    double sum = 0;
+    for (int s = 0; s <= l - a; s++) {
+        double var = c_dmm_coef[l][a][s];
+        var = var * ipow(co, 2 * s + a) * ipow(si, 2 * l - 2 * s - a);
+        sum = sum + var;
     }
+    sum = sum * c_dmm_nnum[l][a];
+    sum = sum / c_dmm_nden[l];
+    return sum * sum;
 }
 
 // interpol.cpp:13-43
@@ -186,7 +192,7 @@ __device__ int d_set_imin_imax(double x0, double xlast, int N, int l, double fc_
 struct Common {
     double ratios[4][7];   // amplitude_ratio(l, inc) or user ratios; [0][0] = 1
     double Vl[4];          // |V_l| (Vl[0] = 1)
-    double eta0, trunc_c, asym, inc;
+    double eta0, trunc_c, asym;
     double a1, a3;         // Classic-type global splitting
     double a11, a12;       // a1l models
     double aterm[12];      // aj: [a1_0,a1_1,...,a6_0,a6_1]; ajAlm: [a1_0,a1_1,a3_0,a3_1,a5_0,a5_1,eps0,eps1,th0,dl]
@@ -299,10 +305,10 @@ __device__ double nu_aj(int l, int m, double fc, const double* a /*a1..a6*/, dou
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
 {
+    extern __shared__ double sp[];             // this chain's parameter row, staged once
     const int sc = blockIdx.x;                 // star*Nchains + chain
     const int star = sc / A.Nchains;
     const StarDesc sd = A.stars[star];
-    const double* params = A.params + (size_t)sc * A.params_stride;
     ModeRec* modes = A.modes + (size_t)sc * A.modes_stride;
     CompRec* comps = A.comps + (size_t)sc * A.modes_stride * TAMCMC_MAX_COMP_PER_MODE;
     NoiseRec* noise = A.noise + sc;
@@ -320,19 +326,48 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
     const int o_noise = o_width + Nwidth;
     const int o_inc = o_noise + Nnoise;
     const int o_cfg = o_inc + Ninc;
-    const double* fl0_all = params + Nmax + lmax;
-    const double* Wl0_all = params + o_width;
 
     if (tid == 0) {
         s_status = 0;
         if (A.active && !A.active[sc]) s_status = TAMCMC_ST_INACTIVE;
     }
+    {
+        const double* g = A.params + (size_t)sc * A.params_stride;
+        for (int k = tid; k < A.params_stride; k += blockDim.x) sp[k] = g[k];
+    }
     __syncthreads();
     const bool inactive = (s_status & TAMCMC_ST_INACTIVE) != 0;
+    const double* params = sp;
+    const double* fl0_all = params + Nmax + lmax;
+    const double* Wl0_all = params + o_width;
 
-    // ---------------- phase 1: per-chain common quantities ----------------
+    // ---------------- phase 1: per-chain common quantities, spread over three warps ----------------
     if (!inactive) {
-        if (tid == 0) {
+        if (tid < 15) {
+            // warp 0, lanes 0..14: the 3+5+7 entries of amplitude_ratio(l, inc), l = 1..3 (or the ratio parameters)
+            const int l = (tid < 3) ? 1 : (tid < 8) ? 2 : 3;
+            const int i = tid - ((l == 1) ? 0 : (l == 2) ? 3 : 8) - l;       // m = -l..l
+            const bool have = (model == 11) ? (pl[2 + l] >= 1) : (lmax >= l);
+            if (have) {
+                if (model == 12) {
+                    // models.cpp:2196-2214: m-ratios read from the "inclination" block, symmetric in m
+                    const int base = (l == 1) ? 0 : (l == 2) ? 2 : 5;
+                    cm.ratios[l][i + l] = fabs(params[o_inc + base + (i < 0 ? -i : i)]);
+                } else if (model != 13) {
+                    double inc;
+                    if (model == 11) {       // models.cpp:3057-3058
+                        const double PI = 3.141592653589793238462643383279502884;
+                        inc = atan(params[o_split + 4] / params[o_split + 3]) * 180. / PI;
+                    } else inc = params[o_inc];
+                    cm.ratios[l][i + l] = d_amplitude_ratio_entry(l, i, inc);
+                }
+            }
+        } else if (tid >= 16 && tid <= 18) {
+            const int l = tid - 15;
+            const bool have = (model == 11) ? (pl[2 + l] >= 1) : (lmax >= l);
+            cm.Vl[l] = (have && model != 11) ? fabs(params[Nmax + l - 1]) : 1.0;
+        } else if (tid == 32) {
+            // warp 1, lane 0: scalar parameters and eta0
             cm.trunc_c = params[o_cfg];
             cm.do_amp = (params[o_cfg + 1] != 0.0);
             cm.ratios[0][0] = 1.0;
@@ -345,7 +380,6 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
                 cm.eta0 = d_eta0_fct(fl0_all, Nfl0);
                 cm.a3 = params[o_split + 2];
                 cm.asym = params[o_split + 5];
-                cm.inc = params[o_noise + Nnoise];
                 break;
             case 6:                      // models.cpp:87-91
                 cm.a11 = fabs(params[o_split]);
@@ -353,46 +387,27 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
                 cm.eta0 = d_eta0_fct(fl0_all, Nfl0);
                 cm.a3 = params[o_split + 2];
                 cm.asym = params[o_split + 5];
-                cm.inc = params[o_noise + Nnoise];
                 break;
-            case 11: {                   // models.cpp:3057-3075 (Nvis plays the role of lmax)
-                const double PI = 3.141592653589793238462643383279502884;
-                double inc = atan(params[o_split + 4] / params[o_split + 3]);
-                cm.inc = inc * 180. / PI;
+            case 11:                     // models.cpp:3059-3075 (Nvis plays the role of lmax)
                 cm.a1 = params[o_split + 3] * params[o_split + 3] + params[o_split + 4] * params[o_split + 4];
                 cm.eta0 = params[o_split + 1];
                 cm.a3 = params[o_split + 2];
                 cm.asym = params[o_split + 5];
-                break; }
+                break;
             case 23:                     // models.cpp:1257-1270
                 for (int k = 0; k < 12; k++) cm.aterm[k] = params[o_split + k];
                 cm.asym = params[o_split + 13];
                 cm.eta0 = (params[o_split + 12] == 1) ? d_eta0_fct(fl0_all, Nfl0) : 0.0;
-                cm.inc = params[o_noise + Nnoise];
                 break;
             default:
                 cm.status = TAMCMC_ST_BADCFG;
-                cm.eta0 = 0; cm.asym = 0; cm.inc = 0;
+                cm.eta0 = 0; cm.asym = 0;
                 break;
             }
             if (cm.status) atomicOr(&s_status, cm.status);
+        } else if (tid == 64) {
+            // warp 2, lane 0: Harvey-like background parameters
             emit_noise(noise, params + o_noise, Nnoise, (model == 11) ? 0 : (Nnoise - 1) / 3, &s_status);
-        }
-        __syncthreads();
-        // visibilities: threads 1..3 (one degree each); models 12 use parameter ratios
-        if (tid >= 1 && tid <= 3) {
-            const int l = tid;
-            const bool have = (model == 11) ? (pl[2 + l] >= 1) : (lmax >= l);
-            if (have) {
-                if (model != 11) cm.Vl[l] = fabs(params[Nmax + l - 1]); else cm.Vl[l] = 1.0;
-                if (model == 12) {
-                    // models.cpp:2196-2214: m-ratios read from the "inclination" block, symmetric in m
-                    const int base = (l == 1) ? 0 : (l == 2) ? 2 : 5;
-                    for (int m = -l; m <= l; m++) cm.ratios[l][m + l] = fabs(params[o_noise + Nnoise + base + (m < 0 ? -m : m)]);
-                } else if (model != 13) {
-                    d_amplitude_ratio(l, cm.inc, cm.ratios[l]);
-                }
-            }
         }
     }
     __syncthreads();
@@ -451,7 +466,7 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
                     const double PI = 3.141592653589793238462643383279502884;
                     const int pos0 = (l + 1) * n;
                     for (int m = -l; m <= l; m++) {
-                        double h = (l == 0) ? params[n] : params[o_noise + Nnoise + pos0 + (m < 0 ? -m : m)];
+                        double h = (l == 0) ? params[n] : params[o_inc + pos0 + (m < 0 ? -m : m)];
                         if (cm.do_amp) h = h / (PI * W);
                         hh[m + l] = fabs(h);
                     }
@@ -476,6 +491,6 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
 
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st)
 {
-    tamcmc_expand_kernel<<<nblocks, 128, 0, st>>>(a);
+    tamcmc_expand_kernel<<<nblocks, 128, sizeof(double) * (size_t)a.params_stride, st>>>(a);
     return cudaGetLastError();
 }

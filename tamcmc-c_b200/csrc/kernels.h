@@ -44,6 +44,7 @@ struct WhittleArgs {
 };
 
 cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const double* Q);
+cudaError_t tamcmc_upload_dmm_tables(const double* coef, const double* nnum, const double* nden);
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
 cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int total_tiles, int nchains_total, bool write_model, cudaStream_t st);
 cudaError_t tamcmc_whittle_configure();   // one-time function attributes
