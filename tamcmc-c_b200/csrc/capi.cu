@@ -81,6 +81,7 @@ int fact_i(int n) { long f = 1; for (long i = 1; i <= n; i++) f *= i; return (in
 int combi_i(int n, int r) { return fact_i(n) / fact_i(n - r) / fact_i(r); }
 
 bool g_tables_uploaded[64] = {false};
+int g_grid_ctas[64] = {0};
 
 int upload_tables(int device)
 {
@@ -112,7 +113,8 @@ int upload_tables(int device)
         }
         CK(tamcmc_upload_dmm_tables(&coef[0][0][0], &nnum[0][0], &nden[0]));
     }
-    CK(tamcmc_whittle_configure());
+    CK(tamcmc_expand_configure());
+    { int g = 0; CK(tamcmc_whittle_configure(&g)); g_grid_ctas[device < 64 && device >= 0 ? device : 0] = g; }
     if (device >= 0 && device < 64) g_tables_uploaded[device] = true;
     return TAMCMC_OK;
 }
@@ -139,7 +141,12 @@ struct tamcmc_gpu_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     // device
     StarDesc* d_stars = nullptr;
-    int* d_tile_star = nullptr;
+    unsigned int* d_queue = nullptr;
+    TileRec* d_tilerec = nullptr;
+    QueueCtl* d_qctl = nullptr;
+    unsigned int qcap = 0;
+    int grid_ctas = 0;
+    int max_tiles = 0;
     double *d_x = nullptr, *d_y = nullptr, *d_lnx = nullptr;
     double* d_params = nullptr;
     unsigned char* d_active = nullptr;
@@ -177,21 +184,25 @@ ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const uns
     a.stars = c->d_stars; a.params = d_params; a.active = d_active;
     a.modes = c->d_modes; a.comps = c->d_comps; a.noise = c->d_noise;
     a.status = c->d_status(); a.asym_flag = c->d_asym; a.out_logL = d_logL;
+    a.queue = c->d_queue; a.qctl = c->d_qctl; a.qcap = c->qcap;
+    a.tilerec = c->d_tilerec; a.x = c->d_x; a.lnx = c->d_lnx;
     a.Nchains = c->Nchains; a.params_stride = c->params_stride; a.modes_stride = c->modes_stride;
+    a.tiles_stride = c->tiles_stride; a.max_tiles = c->max_tiles;
     return a;
 }
 
 WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum)
 {
     WhittleArgs a;
-    a.stars = c->d_stars; a.tile_star = c->d_tile_star;
+    a.stars = c->d_stars;
     a.x = c->d_x; a.y = c->d_y; a.lnx = c->d_lnx;
     a.modes = c->d_modes; a.comps = c->d_comps; a.noise = c->d_noise;
-    a.status = c->d_status(); a.asym_flag = c->d_asym; a.Tcoefs = c->d_Tcoefs;
+    a.asym_flag = c->d_asym; a.Tcoefs = c->d_Tcoefs;
+    a.queue = c->d_queue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec;
     a.partial = c->d_partial; a.counters = c->d_counters;
     a.out = d_out; a.model_out = c->d_model;
     a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
-    a.raw_sum = raw_sum; a.tile_begin = 0; a.chain_begin = 0;
+    a.raw_sum = raw_sum;
     return a;
 }
 
@@ -202,10 +213,11 @@ int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* 
     ExpandArgs ea = make_expand_args(c, d_params, d_active, d_logL);
     WhittleArgs wa = make_whittle_args(c, d_logL, raw_sum);
     const bool prof = c->profiling && st == c->stream;
+    CK(cudaMemsetAsync(c->d_qctl, 0, sizeof(QueueCtl), st));
     if (prof) CK(cudaEventRecord(c->ev[0], st));
     CK(tamcmc_launch_expand(ea, c->SC(), st));
     if (prof) CK(cudaEventRecord(c->ev[1], st));
-    CK(tamcmc_launch_whittle(wa, c->total_tiles, c->Nchains, false, st));
+    CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, st));
     if (prof) CK(cudaEventRecord(c->ev[2], st));
     c->launches += 2;
     return TAMCMC_OK;
@@ -245,6 +257,7 @@ int expand_single(tamcmc_gpu_ctx* c, int star, const double* row)
     CK(cudaMemcpyAsync(c->d_params, c->h_params, sizeof(double) * (size_t)SC * c->params_stride, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_active, c->h_active, (size_t)SC, cudaMemcpyHostToDevice, c->stream));
     ExpandArgs ea = make_expand_args(c, c->d_params, c->d_active, c->d_logL());
+    CK(cudaMemsetAsync(c->d_qctl, 0, sizeof(QueueCtl), c->stream));
     CK(tamcmc_launch_expand(ea, SC, c->stream));
     c->launches += 1;
     return TAMCMC_OK;
@@ -327,9 +340,12 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         if (in.Nparams > c->params_stride) c->params_stride = in.Nparams;
         if (nm > c->modes_stride) c->modes_stride = nm;
         if (sd.ntiles > c->tiles_stride) c->tiles_stride = sd.ntiles;
+        if (sd.ntiles > TAMCMC_MAX_TILES) { delete c; return TAMCMC_ERR_ARG; }
         if (sd.Nloc > maxN) maxN = sd.Nloc;
     }
     c->total_tiles = tiles;
+    c->max_tiles = c->tiles_stride;
+    if ((size_t)nstars * (size_t)Nchains * (size_t)c->tiles_stride > 0xfffffff0ull) { delete c; return TAMCMC_ERR_ARG; }
     c->total_bins_padded = off;
     const int SC = c->SC();
 
@@ -342,7 +358,12 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) CKC(cudaEventCreate(&c->ev[i]));
     CKC(cudaMalloc(&c->d_stars, sizeof(StarDesc) * nstars));
-    CKC(cudaMalloc(&c->d_tile_star, sizeof(int) * tiles));
+    c->qcap = (unsigned int)((size_t)SC * (size_t)c->tiles_stride);
+    CKC(cudaMalloc(&c->d_queue, sizeof(unsigned int) * 2 * (size_t)c->qcap));
+    CKC(cudaMalloc(&c->d_qctl, sizeof(QueueCtl)));
+    CKC(cudaMalloc(&c->d_tilerec, sizeof(TileRec) * (size_t)c->qcap));
+    CKC(cudaMemset(c->d_qctl, 0, sizeof(QueueCtl)));
+    c->grid_ctas = g_grid_ctas[device < 64 ? device : 0];
     CKC(cudaMalloc(&c->d_x, sizeof(double) * off));
     CKC(cudaMalloc(&c->d_y, sizeof(double) * off));
     CKC(cudaMalloc(&c->d_lnx, sizeof(double) * off));
@@ -367,17 +388,14 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     // upload spectra (padded to a multiple of the tile: x pad = last x, y pad = 0)
     {
         std::vector<double> hx((size_t)off), hy((size_t)off, 0.0);
-        std::vector<int> ts((size_t)tiles);
         for (int s = 0; s < nstars; s++) {
             const StarDesc& sd = c->h_stars[s];
             std::memcpy(&hx[(size_t)sd.off], stars[s].x, sizeof(double) * (size_t)sd.Nloc);
             std::memcpy(&hy[(size_t)sd.off], stars[s].y, sizeof(double) * (size_t)sd.Nloc);
             for (long long i = sd.Nloc; i < (long long)sd.ntiles * TAMCMC_TILE; i++) hx[(size_t)(sd.off + i)] = stars[s].x[sd.Nloc - 1];
-            for (int t = 0; t < sd.ntiles; t++) ts[(size_t)(sd.tile0 + t)] = s;
         }
         CKC(cudaMemcpy(c->d_x, hx.data(), sizeof(double) * off, cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_y, hy.data(), sizeof(double) * off, cudaMemcpyHostToDevice));
-        CKC(cudaMemcpy(c->d_tile_star, ts.data(), sizeof(int) * tiles, cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_stars, c->h_stars.data(), sizeof(StarDesc) * nstars, cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_Tcoefs, Tcoefs, sizeof(double) * Nchains, cudaMemcpyHostToDevice));
         CKC(tamcmc_launch_lnx(c->d_x, c->d_lnx, off, c->stream));
@@ -394,7 +412,7 @@ void tamcmc_gpu_destroy(tamcmc_gpu_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_stars); cudaFree(c->d_tile_star); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx);
+    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_tilerec); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx);
     cudaFree(c->d_params); cudaFree(c->d_active); cudaFree(c->d_modes); cudaFree(c->d_comps); cudaFree(c->d_noise);
     cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_counters); cudaFree(c->d_out);
     cudaFree(c->d_model);
@@ -452,8 +470,7 @@ int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, doub
     { int rc = expand_single(c, star, params_row); if (rc) return rc; }
     const StarDesc& sd = c->h_stars[star];
     WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0);
-    wa.tile_begin = sd.tile0; wa.chain_begin = 0;
-    CK(tamcmc_launch_whittle(wa, sd.ntiles, 1, true, c->stream));
+    CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->stream));
     c->launches += 1;
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -195,55 +195,27 @@ struct Common {
     double eta0, trunc_c, asym;
     double a1, a3;         // Classic-type global splitting
     double a11, a12;       // a1l models
-    double aterm[12];      // aj: [a1_0,a1_1,...,a6_0,a6_1]; ajAlm: [a1_0,a1_1,a3_0,a3_1,a5_0,a5_1,eps0,eps1,th0,dl]
+    double aterm[12];      // aj: [a1_0,a1_1,...,a6_0,a6_1]
     int do_amp;
     int status;
 };
 
-// one mode -> ModeRec + CompRecs.  nu[m+l], height[m+l] = H_l * V(m) for m=-l..l.
-__device__ void emit_mode(const StarDesc& sd, ModeRec* mrec, CompRec* comps, int l, double fc, double gamma,
-                          double fs_window, double c, double asym, const double* nu, const double* height,
-                          int* status)
-{
-    ModeRec mr;
-    int i0, i1;
-    int bad = d_set_imin_imax(sd.x0, sd.xlast, sd.Nglob, l, fc, gamma, fs_window, c, sd.step, &i0, &i1);
-    if (bad) atomicOr(status, TAMCMC_ST_WINDOW);
-    mr.i0 = i0; mr.i1 = i1; mr.l = l; mr.fc = fc; mr.gamma = gamma;
-    mr.qa = asym / fc;
-    mr.qb0 = 1.0 - asym;
-    { double k2 = 0.5 * gamma * asym / fc; mr.qc = k2 * k2; }
-    mr.pad = 0.0;
-    if (!isfinite(fc) || !isfinite(gamma) || (asym != 0.0 && (!isfinite(mr.qa) || !isfinite(mr.qc))))
-        atomicOr(status, TAMCMC_ST_NONFINITE);
+constexpr int EXP_THREADS = 128;
+constexpr int EXP_BATCH = 128;                 // modes expanded per pass
+constexpr int TILE_BASE_COST = 16;             // per-tile fixed work in (component, bin)-pair units / 1024
 
-    const double sg = 2.0 / gamma;
-    // largest |x - nu| inside the window, for the dynamic-range classification
-    const double xlo = sd.x0 + (double)i0 * sd.step, xhi = sd.x0 + (double)i1 * sd.step;
-    int nc = 0;
-    for (int m = -l; m <= l; m++) {
-        const double A = height[m + l];
-        const double v = nu[m + l];
-        if (!isfinite(A) || !isfinite(v)) { atomicOr(status, TAMCMC_ST_NONFINITE); continue; }
-        if (A == 0.0 || !(gamma > 0.0)) continue;   // contributes exactly 0 (gamma==0: see DESIGN.md deviations)
-        const double dmax = fmax(fabs(xlo - v), fabs(xhi - v));
-        const double emax = sg * dmax;
-        CompRec cr;
-        cr.nu = v; cr.m = m;
-        if (A >= 1e-20 && A <= 1e20 && emax < 1e5 && sg < 1e12) {
-            cr.flags = TAMCMC_CF_FAST;
-            cr.s = sg / sqrt(A);
-            cr.a = 1.0 / A;
-        } else {
-            cr.flags = TAMCMC_CF_SLOW;
-            cr.s = sg;
-            cr.a = A;
-        }
-        comps[nc++] = cr;
-    }
-    mr.ncomp = nc;
-    *mrec = mr;
-}
+// per-mode scratch between the three passes of a batch
+struct ModeTmp {
+    int l;
+    int have;              // mode exists in this batch
+    double fc, W, fsw;     // central frequency, width, splitting used by the window
+    double f_s;            // splitting used by nu (a1etaa3 family)
+    double H;              // common height (multiplied by the m-ratios), or < 0 when per-m heights are used
+    double a[6];           // a1..a6 of this mode (aj family)
+    double eta0;           // eta0 seen by this mode
+    int hoff;              // model 13: offset of the per-m heights in the parameter vector
+    int n;
+};
 
 __device__ void emit_noise(NoiseRec* out, const double* noise_params, int Nnoise, int Nharvey, int* status)
 {
@@ -251,7 +223,7 @@ __device__ void emit_noise(NoiseRec* out, const double* noise_params, int Nnoise
     NoiseRec nr;
     int nh = 0;
     if (Nharvey > TAMCMC_MAX_HARVEY) { atomicOr(status, TAMCMC_ST_BADCFG); Nharvey = TAMCMC_MAX_HARVEY; }
-    for (int k = 0; k < TAMCMC_MAX_HARVEY; k++) { nr.H[k] = 0; nr.lnsc[k] = 0; nr.pw[k] = 0; }
+    for (int k = 0; k < TAMCMC_MAX_HARVEY; k++) { nr.H[k] = 0; nr.lnsc[k] = 0; nr.pw[k] = 0; nr.cpi[k] = 0; nr.spi[k] = 0; }
     for (int k = 0; k < Nharvey; k++) {
         const double H = fabs(noise_params[3 * k]);
         const double tau = fabs(noise_params[3 * k + 1]);
@@ -261,6 +233,8 @@ __device__ void emit_noise(NoiseRec* out, const double* noise_params, int Nnoise
             nr.H[nh] = H;
             nr.lnsc[nh] = log((1e-3) * tau);
             nr.pw[nh] = pw;
+            { const double ang = 3.14159265358979323846 / fmax(pw, 1.0); sincos(ang, &nr.spi[nh], &nr.cpi[nh]); }
+            { double b = 1.0; nr.binom[nh][0] = 1.0; for (int q = 1; q < TAMCMC_BG_TERMS; q++) { b = b * (pw - (double)(q - 1)) / (double)q; nr.binom[nh][q] = b; } }
             nh++;
         }
     }
@@ -298,12 +272,48 @@ __device__ double nu_aj(int l, int m, double fc, const double* a /*a1..a6*/, dou
     return v;
 }
 
+// Taylor series in u = x - xc of one Harvey-like term H / (1 + (tau' x)^p) (noise_models.cpp:30-31),
+// valid on the tile when |u|/xc is small against the distance to the nearest singularity
+// (x = 0 and (tau' x)^p = -1).  Returns false when the tile must use the per-bin exp() path.
+__device__ bool harvey_series(double H, double lnsc, double pw, double cpi, double spi, const double* binom,
+                              double xc, double lnxc, double umax, double* out /*NB, accumulated*/)
+{
+    constexpr int NB = TAMCMC_BG_TERMS;
+    if (!(xc > 0.0)) return false;
+    const double L = lnsc + lnxc;
+    const double tx = exp(L);            // tau' * xc
+    const double zc = exp(pw * L);       // (tau' * xc)^p
+    if (!(zc < 1e30) || !(tx > 0.0)) return false;
+    const double itx = 1.0 / tx;
+    const double dr = cpi * itx - 1.0, di = spi * itx;
+    const double rho = fmin(1.0, sqrt(dr * dr + di * di));
+    if (!(umax <= 0.04 * rho * xc)) return false;     // 0.04^NB = 1e-14 truncation
+    double q[NB], g[NB];
+    q[0] = 1.0 + zc;
+#pragma unroll
+    for (int k = 1; k < NB; k++) q[k] = zc * binom[k];
+    g[0] = 1.0 / q[0];
+#pragma unroll
+    for (int n = 1; n < NB; n++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 1; k <= n; k++) acc = fma(q[k], g[n - k], acc);
+        g[n] = -g[0] * acc;
+    }
+    const double ixc = 1.0 / xc;
+    double scl = H;
+#pragma unroll
+    for (int n = 0; n < NB; n++) { out[n] += g[n] * scl; scl *= ixc; }
+    return true;
+}
+
 }  // namespace
 
 // -------------------------------------------------------------------------------------------
-// expand kernel: grid = nstars*Nchains CTAs, 128 threads
+// expand kernel: grid = nstars*Nchains CTAs, 128 threads.
+// dynamic shared memory: params row [params_stride] doubles, then per-tile cost ints [max_tiles + 1]
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
+__global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A)
 {
     extern __shared__ double sp[];             // this chain's parameter row, staged once
     const int sc = blockIdx.x;                 // star*Nchains + chain
@@ -312,10 +322,50 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
     ModeRec* modes = A.modes + (size_t)sc * A.modes_stride;
     CompRec* comps = A.comps + (size_t)sc * A.modes_stride * TAMCMC_MAX_COMP_PER_MODE;
     NoiseRec* noise = A.noise + sc;
+    int* tcost = reinterpret_cast<int*>(sp + A.params_stride);   // [ntiles + 1] difference array -> cost
+
+    // ---- blockIdx.y >= 1: background CTAs.  One thread per tile of this chain builds the tile record
+    // (origin, extent, Taylor series of the Harvey background); they run beside the mode CTAs. ----
+    if (blockIdx.y > 0) {
+        __shared__ NoiseRec s_nz;
+        __shared__ int s_dummy;
+        if (A.active && !A.active[sc]) return;
+        const int* pl = sd.plength;
+        const int o_noise = pl[0] + pl[1] + pl[2] + pl[3] + pl[4] + pl[5] + pl[6] + pl[7];
+        if (threadIdx.x == 0) {
+            s_dummy = 0;
+            emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (sd.model_id == 11) ? 0 : (pl[8] - 1) / 3, &s_dummy);
+        }
+        __syncthreads();
+        const int tile = (blockIdx.y - 1) * blockDim.x + threadIdx.x;
+        if (tile >= sd.ntiles) return;
+        const int lb0 = tile * TAMCMC_TILE;
+        const int nvalid = min(TAMCMC_TILE, sd.Nloc - lb0);
+        const double* xs = A.x + sd.off + lb0;
+        TileRec tr;
+        tr.xc = xs[nvalid >> 1];
+        tr.umax = fmax(fabs(xs[0] - tr.xc), fabs(xs[TAMCMC_TILE - 1] - tr.xc));
+        const double lnxc = A.lnx[sd.off + lb0 + (nvalid >> 1)];
+        for (int k = 0; k < TAMCMC_BG_TERMS; k++) tr.bg[k] = 0.0;
+        bool ok = true;
+        for (int h = 0; h < s_nz.nh && ok; h++)
+            ok = harvey_series(s_nz.H[h], s_nz.lnsc[h], s_nz.pw[h], s_nz.cpi[h], s_nz.spi[h], s_nz.binom[h], tr.xc, lnxc, tr.umax, tr.bg);
+        tr.series_ok = ok ? 1 : 0;
+        tr.pad[0] = tr.pad[1] = tr.pad[2] = 0;
+        A.tilerec[(size_t)sc * A.tiles_stride + tile] = tr;
+        return;
+    }
 
     __shared__ Common cm;
     __shared__ int s_status;
+    __shared__ ModeTmp mt[EXP_BATCH];
+    __shared__ double slot_s[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
+    __shared__ double slot_ia[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
+    __shared__ double slot_nu[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
+    __shared__ double slot_A[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
+    __shared__ int s_red[EXP_THREADS / 32];
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int* pl = sd.plength;
     const int Nmax = pl[0], lmax = pl[1], Nfl0 = pl[2], Nfl1 = pl[3], Nfl2 = pl[4], Nfl3 = pl[5];
     const int Nsplit = pl[6], Nwidth = pl[7], Nnoise = pl[8], Ninc = pl[9];
@@ -326,6 +376,7 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
     const int o_noise = o_width + Nwidth;
     const int o_inc = o_noise + Nnoise;
     const int o_cfg = o_inc + Ninc;
+    const int ntiles = sd.ntiles;
 
     if (tid == 0) {
         s_status = 0;
@@ -334,6 +385,7 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
     {
         const double* g = A.params + (size_t)sc * A.params_stride;
         for (int k = tid; k < A.params_stride; k += blockDim.x) sp[k] = g[k];
+        for (int k = tid; k <= ntiles; k += blockDim.x) tcost[k] = 0;
     }
     __syncthreads();
     const bool inactive = (s_status & TAMCMC_ST_INACTIVE) != 0;
@@ -412,73 +464,195 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
     }
     __syncthreads();
 
-    // ---------------- phase 2: one thread per mode ----------------
+    // ---------------- phase 2: modes in batches of 128; three passes per batch ----------------
     const int nmodes = sd.nmodes_cap;
-    if (!inactive && !(s_status & TAMCMC_ST_BADCFG)) {
-        for (int j = tid; j < nmodes; j += blockDim.x) {
-            int l, n;
-            double fc, W, H, fsw;
-            double nu[7], hh[7];
-            // reference call order -> mode index j
-            if (model == 3 || model == 12 || model == 13 || model == 6) {
-                l = j % (lmax + 1); n = j / (lmax + 1);          // n-major, l interleaved (models.cpp:2026-2085)
-            } else {
-                // l-major: all l=0, then l=1, ... (models.cpp:1287-1376, 3082-3134)
-                int r = j; l = 0;
-                while (l < 3 && r >= pl[2 + l]) { r -= pl[2 + l]; l++; }
-                n = r;
-            }
-            const int o_fl = Nmax + lmax + (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0);
-            fc = params[o_fl + n];
-
-            if (model == 11) {
-                // models.cpp:3082-3134: individual heights and widths per mode
-                const int idx = (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0) + n;
-                W = fabs(params[o_width + idx]);
-                H = cm.do_amp ? amp_to_height(params[idx], W) : fabs(params[idx]);
-                for (int m = -l; m <= l; m++) { nu[m + l] = nu_a1etaa3(l, m, fc, cm.a1, cm.eta0, cm.a3); hh[m + l] = H * cm.ratios[l][m + l]; }
-                fsw = cm.a1;
-            } else if (model == 23) {
-                // models.cpp:1287-1376
-                double a[6] = {0, 0, 0, 0, 0, 0};
-                if (l == 0) {
-                    W = fabs(Wl0_all[n]);
-                    H = cm.do_amp ? amp_to_height(params[n], W) : fabs(params[n]);
+    const bool run = !inactive && !(s_status & TAMCMC_ST_BADCFG);
+    for (int base = 0; run && base < nmodes; base += EXP_BATCH) {
+        // ---- pass A: one thread per mode: degree, frequency, width, height rule, splittings ----
+        {
+            const int j = base + tid;
+            ModeTmp t;
+            t.have = 0;
+            if (tid < EXP_BATCH && j < nmodes) {
+                int l, n;
+                if (model == 3 || model == 12 || model == 13 || model == 6) {
+                    l = j % (lmax + 1); n = j / (lmax + 1);          // n-major, l interleaved (models.cpp:2026-2085)
                 } else {
-                    W = fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
-                    const double Hi = d_lin_interpol(fl0_all, params, Nmax, fc);
-                    const double PI = 3.14159265358979323846;
-                    H = cm.do_amp ? fabs(Hi / (PI * W) * cm.Vl[l]) : fabs(Hi * cm.Vl[l]);
-                    const int na = 2 * l;            // l=1: a1,a2; l=2: a1..a4; l=3: a1..a6
-                    for (int k = 0; k < na; k++) a[k] = cm.aterm[2 * k] + cm.aterm[2 * k + 1] * (fc * 1e-3);
+                    // l-major: all l=0, then l=1, ... (models.cpp:1287-1376, 3082-3134)
+                    int r = j; l = 0;
+                    while (l < 3 && r >= pl[2 + l]) { r -= pl[2 + l]; l++; }
+                    n = r;
                 }
-                for (int m = -l; m <= l; m++) { nu[m + l] = nu_aj(l, m, fc, a, (l == 0) ? 0.0 : cm.eta0); hh[m + l] = H * cm.ratios[l][m + l]; }
-                fsw = a[0];                           // optimum_lorentzian_calc_aj: window uses a1 (build_lorentzian.cpp:513)
-            } else {
-                // Classic family and a1l: widths interpolated on the l=0 ladder, heights H[n]*V_l
-                W = (l == 0) ? fabs(Wl0_all[n]) : fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
-                double f_s;
-                if (model == 6) {                     // build_lorentzian.cpp:58-66, 383-396
-                    f_s = (l == 0) ? 0.0 : (l == 1) ? cm.a11 : (l == 2) ? cm.a12 : (cm.a11 + cm.a12) / 2.;
-                } else f_s = cm.a1;
-                if (model == 13) {
-                    // models.cpp:2409-2470: per-m heights from the parameter vector, |H|/(pi W) if do_amp
-                    const double PI = 3.141592653589793238462643383279502884;
-                    const int pos0 = (l + 1) * n;
-                    for (int m = -l; m <= l; m++) {
-                        double h = (l == 0) ? params[n] : params[o_inc + pos0 + (m < 0 ? -m : m)];
-                        if (cm.do_amp) h = h / (PI * W);
-                        hh[m + l] = fabs(h);
+                const int o_fl = Nmax + lmax + (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0);
+                const double fc = params[o_fl + n];
+                t.have = 1; t.l = l; t.n = n; t.fc = fc; t.hoff = -1; t.eta0 = cm.eta0;
+                for (int k = 0; k < 6; k++) t.a[k] = 0.0;
+                if (model == 11) {
+                    // models.cpp:3082-3134: individual heights and widths per mode
+                    const int idx = (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0) + n;
+                    t.W = fabs(params[o_width + idx]);
+                    t.H = cm.do_amp ? amp_to_height(params[idx], t.W) : fabs(params[idx]);
+                    t.f_s = cm.a1; t.fsw = cm.a1;
+                } else if (model == 23) {
+                    // models.cpp:1287-1376
+                    if (l == 0) {
+                        t.W = fabs(Wl0_all[n]);
+                        t.H = cm.do_amp ? amp_to_height(params[n], t.W) : fabs(params[n]);
+                        t.eta0 = 0.0;
+                    } else {
+                        t.W = fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
+                        const double Hi = d_lin_interpol(fl0_all, params, Nmax, fc);
+                        const double PI = 3.14159265358979323846;
+                        t.H = cm.do_amp ? fabs(Hi / (PI * t.W) * cm.Vl[l]) : fabs(Hi * cm.Vl[l]);
+                        const int na = 2 * l;            // l=1: a1,a2; l=2: a1..a4; l=3: a1..a6
+                        for (int k = 0; k < na; k++) t.a[k] = cm.aterm[2 * k] + cm.aterm[2 * k + 1] * (fc * 1e-3);
                     }
+                    t.f_s = 0.0;
+                    t.fsw = t.a[0];                       // optimum_lorentzian_calc_aj: window uses a1 (build_lorentzian.cpp:513)
                 } else {
-                    if (l == 0) H = cm.do_amp ? amp_to_height(params[n], W) : fabs(params[n]);
-                    else H = cm.do_amp ? amp_to_height(params[n], W) * cm.Vl[l] : fabs(params[n] * cm.Vl[l]);
-                    for (int m = -l; m <= l; m++) hh[m + l] = H * cm.ratios[l][m + l];
+                    // Classic family and a1l: widths interpolated on the l=0 ladder, heights H[n]*V_l
+                    t.W = (l == 0) ? fabs(Wl0_all[n]) : fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
+                    if (model == 6) {                     // build_lorentzian.cpp:58-66, 383-396
+                        t.f_s = (l == 0) ? 0.0 : (l == 1) ? cm.a11 : (l == 2) ? cm.a12 : (cm.a11 + cm.a12) / 2.;
+                    } else t.f_s = cm.a1;
+                    t.fsw = t.f_s;
+                    if (model == 13) {
+                        // models.cpp:2409-2470: per-m heights from the parameter vector, |H|/(pi W) if do_amp
+                        t.H = -1.0;
+                        t.hoff = (l == 0) ? n : o_inc + (l + 1) * n;
+                    } else {
+                        if (l == 0) t.H = cm.do_amp ? amp_to_height(params[n], t.W) : fabs(params[n]);
+                        else t.H = cm.do_amp ? amp_to_height(params[n], t.W) * cm.Vl[l] : fabs(params[n] * cm.Vl[l]);
+                    }
                 }
-                for (int m = -l; m <= l; m++) nu[m + l] = nu_a1etaa3(l, m, fc, f_s, cm.eta0, cm.a3);
-                fsw = f_s;
             }
-            emit_mode(sd, modes + j, comps + (size_t)j * TAMCMC_MAX_COMP_PER_MODE, l, fc, W, fsw, cm.trunc_c, cm.asym, nu, hh, &s_status);
+            if (tid < EXP_BATCH) mt[tid] = t;
+        }
+        __syncthreads();
+        // ---- pass B: one thread per (mode, m) slot: nu_nlm and height ----
+        for (int sl = tid; sl < EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE; sl += blockDim.x) {
+            const int jj = sl / TAMCMC_MAX_COMP_PER_MODE, k = sl - jj * TAMCMC_MAX_COMP_PER_MODE;
+            const ModeTmp& t = mt[jj];
+            if (!t.have || k > 2 * t.l) continue;
+            const int l = t.l, m = k - l;
+            double nu, h;
+            if (model == 23) nu = nu_aj(l, m, t.fc, t.a, t.eta0);
+            else nu = nu_a1etaa3(l, m, t.fc, t.f_s, t.eta0, cm.a3);
+            if (t.H >= 0.0) h = t.H * cm.ratios[l][k];
+            else {
+                const double PI = 3.141592653589793238462643383279502884;
+                h = (l == 0) ? params[t.hoff] : params[t.hoff + (m < 0 ? -m : m)];
+                if (cm.do_amp) h = h / (PI * t.W);
+                h = fabs(h);
+            }
+            slot_nu[sl] = nu; slot_A[sl] = h;
+            slot_s[sl] = (2.0 / t.W) / sqrt(h); slot_ia[sl] = 1.0 / h;     // scaled FAST form (used if the slot qualifies)
+        }
+        __syncthreads();
+        // ---- pass C: one thread per mode: bit-exact window, component classification, tables ----
+        if (tid < EXP_BATCH && mt[tid].have) {
+            const ModeTmp& t = mt[tid];
+            const int j = base + tid;
+            const int l = t.l;
+            ModeRec mr;
+            int i0, i1;
+            const int bad = d_set_imin_imax(sd.x0, sd.xlast, sd.Nglob, l, t.fc, t.W, t.fsw, cm.trunc_c, sd.step, &i0, &i1);
+            if (bad) atomicOr(&s_status, TAMCMC_ST_WINDOW);
+            mr.i0 = i0; mr.i1 = i1; mr.l = l; mr.fc = t.fc; mr.gamma = t.W;
+            mr.qa = cm.asym / t.fc;
+            mr.qb0 = 1.0 - cm.asym;
+            { const double k2 = 0.5 * t.W * cm.asym / t.fc; mr.qc = k2 * k2; }
+            mr.pad = 0;
+            if (!isfinite(t.fc) || !isfinite(t.W) || (cm.asym != 0.0 && (!isfinite(mr.qa) || !isfinite(mr.qc))))
+                atomicOr(&s_status, TAMCMC_ST_NONFINITE);
+            const double sg = 2.0 / t.W;
+            const double xlo = sd.x0 + (double)i0 * sd.step, xhi = sd.x0 + (double)i1 * sd.step;
+            CompRec* out = comps + (size_t)j * TAMCMC_MAX_COMP_PER_MODE;
+            int nf = 0, ns = 0;
+            unsigned fastmask = 0, livemask = 0;
+            for (int k = 0; k <= 2 * l; k++) {
+                const double Ah = slot_A[tid * TAMCMC_MAX_COMP_PER_MODE + k];
+                const double v = slot_nu[tid * TAMCMC_MAX_COMP_PER_MODE + k];
+                if (!isfinite(Ah) || !isfinite(v)) { atomicOr(&s_status, TAMCMC_ST_NONFINITE); continue; }
+                if (Ah == 0.0 || !(t.W > 0.0)) continue;     // contributes exactly 0 (gamma == 0: DESIGN.md deviations)
+                const double emax = sg * fmax(fabs(xlo - v), fabs(xhi - v));
+                if (!(emax < 1e100)) { atomicOr(&s_status, TAMCMC_ST_NONFINITE); continue; }
+                livemask |= 1u << k;
+                // FAST: t' = (1+e^2)/A stays inside [1e-8, 1e16] over the whole window, so 16 merges between
+                // two exponent renormalisations cannot leave the FP64 range
+                if (Ah >= 1e-8 && Ah <= 1e8 && emax < 1e4) fastmask |= 1u << k;
+            }
+            for (int pass = 0; pass < 2; pass++)
+                for (int k = 0; k <= 2 * l; k++) {
+                    if (!(livemask & (1u << k))) continue;
+                    const bool fast = (fastmask >> k) & 1u;
+                    if (fast != (pass == 0)) continue;
+                    const double Ah = slot_A[tid * TAMCMC_MAX_COMP_PER_MODE + k];
+                    CompRec cr;
+                    cr.nu = slot_nu[tid * TAMCMC_MAX_COMP_PER_MODE + k]; cr.m = k - l;
+                    if (fast) { cr.flags = TAMCMC_CF_FAST; cr.s = slot_s[tid * TAMCMC_MAX_COMP_PER_MODE + k]; cr.a = slot_ia[tid * TAMCMC_MAX_COMP_PER_MODE + k]; nf++; }
+                    else { cr.flags = TAMCMC_CF_SLOW; cr.s = sg; cr.a = Ah; ns++; }
+                    out[nf + ns - 1] = cr;
+                }
+            mr.nfast = nf; mr.ncomp = nf + ns;
+            modes[j] = mr;
+            // per-tile cost: difference array over the LOCAL tiles this window touches
+            if (!bad && mr.ncomp > 0) {
+                const int lo = max(i0, sd.bin0) - sd.bin0, hi = min(i1, sd.bin0 + sd.Nloc) - sd.bin0;
+                if (hi > lo) {
+                    atomicAdd(&tcost[lo / TAMCMC_TILE], mr.ncomp);
+                    atomicAdd(&tcost[(hi - 1) / TAMCMC_TILE + 1], -mr.ncomp);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---------------- phase 3: tile costs -> heavy-first work queue ----------------
+    const bool enqueue = run && (s_status == 0);
+    if (enqueue) {
+        // inclusive scan of the difference array (serial per warp-strided chunk would need carries; ntiles is
+        // a few hundred: one warp scans it in 32-wide steps with a running carry)
+        if (warp == 0) {
+            int carry = 0;
+            for (int t0 = 0; t0 < ntiles; t0 += 32) {
+                const int t = t0 + lane;
+                int v = (t < ntiles) ? tcost[t] : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
+                v += carry;
+                if (t < ntiles) tcost[t] = v + TILE_BASE_COST;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+        int mx = 0;
+        for (int t = tid; t < ntiles; t += blockDim.x) mx = max(mx, tcost[t]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+        if (lane == 0) s_red[warp] = mx;
+        __syncthreads();
+        mx = 0;
+        for (int w = 0; w < EXP_THREADS / 32; w++) mx = max(mx, s_red[w]);
+        const int thr = max(mx / 2, TILE_BASE_COST + 1);
+        const int rounds = (ntiles + blockDim.x - 1) / blockDim.x;
+        for (int r = 0; r < rounds; r++) {
+            const int t = r * blockDim.x + tid;
+            const bool valid = t < ntiles;
+            const bool heavy = valid && tcost[t] >= thr;
+            const unsigned mh = __ballot_sync(0xffffffffu, heavy);
+            const unsigned ml = __ballot_sync(0xffffffffu, valid && !heavy);
+            unsigned bh = 0, bl = 0;
+            if (lane == 0) {
+                if (mh) bh = atomicAdd(&A.qctl->count[0], (unsigned)__popc(mh));
+                if (ml) bl = atomicAdd(&A.qctl->count[1], (unsigned)__popc(ml));
+            }
+            bh = __shfl_sync(0xffffffffu, bh, 0);
+            bl = __shfl_sync(0xffffffffu, bl, 0);
+            const unsigned below = (1u << lane) - 1u;
+            const unsigned item = (unsigned)sc * (unsigned)A.tiles_stride + (unsigned)t;
+            if (heavy) A.queue[bh + __popc(mh & below)] = item;
+            else if (valid) A.queue[A.qcap + bl + __popc(ml & below)] = item;
         }
     }
     __syncthreads();
@@ -489,8 +663,15 @@ __global__ void __launch_bounds__(128) tamcmc_expand_kernel(ExpandArgs A)
     }
 }
 
+cudaError_t tamcmc_expand_configure()
+{
+    return cudaFuncSetAttribute(tamcmc_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
+
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st)
 {
-    tamcmc_expand_kernel<<<nblocks, 128, sizeof(double) * (size_t)a.params_stride, st>>>(a);
+    const size_t smem = sizeof(double) * (size_t)a.params_stride + sizeof(int) * (size_t)(a.max_tiles + 2);
+    dim3 grid((unsigned)nblocks, 1u + (unsigned)((a.max_tiles + EXP_THREADS - 1) / EXP_THREADS), 1u);
+    tamcmc_expand_kernel<<<grid, EXP_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }

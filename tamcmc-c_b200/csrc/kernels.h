@@ -13,41 +13,50 @@ struct ExpandArgs {
     int* status;                     // [nstars*Nchains]
     int* asym_flag;                  // [nstars*Nchains]
     double* out_logL;                // [nstars*Nchains] (NaN written for non-OK chains)
+    unsigned int* queue;             // [2][qcap] work items sc*tiles_stride + tile: heavy tiles, then light tiles
+    TileRec* tilerec;                // [nstars*Nchains][tiles_stride]
+    const double* x;                 // concatenated spectra (tile centres / extents)
+    const double* lnx;
+    QueueCtl* qctl;                  // zeroed before every expand launch
+    unsigned int qcap;
     int Nchains;
     int params_stride;
     int modes_stride;
+    int tiles_stride;
+    int max_tiles;                   // largest ntiles of any star (sizes the dynamic shared memory)
 };
 
 struct WhittleArgs {
     const StarDesc* stars;
-    const int* tile_star;            // [total_tiles] flat tile -> star
-    const double* x;                 // concatenated local bins
+    const double* x;                 // concatenated local bins, tile-padded
     const double* y;
     const double* lnx;
     const ModeRec* modes;
     const CompRec* comps;
     const NoiseRec* noise;
-    const int* status;
     const int* asym_flag;
     const double* Tcoefs;            // [Nchains]
+    const unsigned int* queue;
+    const TileRec* tilerec;
+    QueueCtl* qctl;
+    unsigned int qcap;
     double* partial;                 // [nstars*Nchains][tiles_stride]
     unsigned int* counters;          // [nstars*Nchains] tile tickets (self-resetting)
     double* out;                     // [nstars*Nchains]: tempered logL, or raw sum S if raw_sum
-    double* model_out;               // WRITE_MODEL: [Nloc] of the selected star, chain 0
+    double* model_out;               // WRITE_MODEL: [Nloc] of the (single) evaluated star/chain
     double p;                        // likelihood parameter (truncated to long like model_def.cpp:399)
     int Nchains;
     int modes_stride;
     int tiles_stride;
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)
-    int tile_begin;                  // grid offset: flat tile = blockIdx.x + tile_begin
-    int chain_begin;                 // chain = blockIdx.y + chain_begin
 };
 
 cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const double* Q);
 cudaError_t tamcmc_upload_dmm_tables(const double* coef, const double* nnum, const double* nden);
+cudaError_t tamcmc_expand_configure();
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
-cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int total_tiles, int nchains_total, bool write_model, cudaStream_t st);
-cudaError_t tamcmc_whittle_configure();   // one-time function attributes
+cudaError_t tamcmc_whittle_configure(int* grid_ctas);   // one-time function attributes; returns the persistent grid size
+cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st);
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st);
 // DFMA throughput microbenchmark: returns achieved FP64 TFLOP/s (2 flops per DFMA)
 cudaError_t tamcmc_fp64_peak(double* tflops, float* ms, int iters);

@@ -2,10 +2,11 @@
 // model+Whittle kernel and the C-ABI implementation.  Not part of the public ABI.
 //
 // HBM layout per context (see DESIGN.md "Data layout in HBM"):
-//   x, y, lnx        : one concatenated FP64 array each over all stars' local bins
+//   x, y, lnx        : one concatenated FP64 array each over all stars' local bins (tile-padded)
 //   params           : [nstars][Nchains][Nparams_max] FP64, row-major (uploaded every step)
 //   modes / comps    : [nstars][Nchains][max_modes] ModeRec, [..][max_modes*7] CompRec
 //   noise            : [nstars][Nchains] NoiseRec
+//   queue            : [2][nstars*Nchains*max_tiles] uint32 work items (heavy tiles, light tiles)
 //   partial          : [nstars][Nchains][max_tiles] FP64 per-tile partial sums
 //   out              : [nstars*Nchains] FP64 logL followed by [nstars*Nchains] int32 status
 #pragma once
@@ -13,9 +14,15 @@
 
 #define TAMCMC_MAX_COMP_PER_MODE 7   // l <= 3 -> 2l+1 <= 7 (reference: acoefs.cpp supports l<=3)
 #define TAMCMC_MAX_HARVEY 8
-#define TAMCMC_TILE 1024             // bins per CTA tile
-#define TAMCMC_THREADS 128           // threads per CTA (8 bins per thread)
-#define TAMCMC_BINS_PER_THREAD (TAMCMC_TILE / TAMCMC_THREADS)
+#define TAMCMC_BG_TERMS 10           // Taylor coefficients of the Harvey background per tile
+#define TAMCMC_TILE 1024             // bins per tile
+#define TAMCMC_CONSUMERS 256         // consumer threads per CTA (4 bins per thread)
+#define TAMCMC_THREADS (TAMCMC_CONSUMERS + 32)   // + one producer warp
+#define TAMCMC_BINS_PER_THREAD (TAMCMC_TILE / TAMCMC_CONSUMERS)
+#define TAMCMC_MAX_TILES 16384       // tiles per star the expander's cost scan supports (16.7M bins)
+#ifndef TAMCMC_MIN_CTAS
+#define TAMCMC_MIN_CTAS 3            // resident CTAs per SM the fused kernel is compiled for
+#endif
 
 // per-chain status bits (device -> host)
 #define TAMCMC_ST_OK 0
@@ -29,15 +36,17 @@
 #define TAMCMC_CF_SLOW 2        // general form (A, t), merged with 3 FP64 ops (extreme dynamic range)
 
 struct __align__(16) ModeRec {
+    // first 16 bytes = everything the tile classification needs (one 128-bit load)
     int i0, i1;          // GLOBAL bin window [i0, i1)  (set_imin_imax, bit-exact)
+    int ncomp;           // number of live components (height != 0); FAST ones are stored first
+    int nfast;           // leading components in the scaled FAST form
     int l;               // degree
-    int ncomp;           // number of live components (height != 0)
+    int pad;
     double fc;           // central frequency fc_l
     double gamma;        // width
     double qa;           // asym / fc
     double qb0;          // 1 - asym                    (w(x) = qb0 + x*qa)
     double qc;           // (0.5*gamma*asym/fc)^2
-    double pad;
 };
 
 struct __align__(8) CompRec {
@@ -48,12 +57,15 @@ struct __align__(8) CompRec {
 };
 
 struct NoiseRec {
-    int nh;                              // live Harvey terms (tau != 0 and H != 0)
+    int nh;                              // live Harvey terms (tau != 0)
     int pad;
     double N0;                           // white noise
     double H[TAMCMC_MAX_HARVEY];         // heights
     double lnsc[TAMCMC_MAX_HARVEY];      // ln(1e-3 * tau)
     double pw[TAMCMC_MAX_HARVEY];        // exponents
+    double cpi[TAMCMC_MAX_HARVEY];       // cos(pi/p), sin(pi/p): direction of the nearest pole of 1/(1+z^p)
+    double spi[TAMCMC_MAX_HARVEY];
+    double binom[TAMCMC_MAX_HARVEY][TAMCMC_BG_TERMS];   // generalised binomial coefficients C(p, k)
 };
 
 struct StarDesc {
@@ -70,3 +82,15 @@ struct StarDesc {
     double x0, xlast;    // global x[0], x[N-1]
     double step;         // x[1]-x[0] (MS models, models.cpp:1952) or x[2]-x[1] (RGB v4, models.cpp:4714)
 };
+
+// per (star, chain, tile) record built by the background CTAs of the expand launch
+struct __align__(16) TileRec {
+    double bg[TAMCMC_BG_TERMS];   // Taylor coefficients in u = x - xc of sum_h H_h/(1+(tau_h x)^p_h)
+    double xc;                    // tile-local origin x[tile centre]
+    double umax;                  // max |x - xc| over the tile
+    int series_ok;                // 0: the tile must evaluate the background exactly per bin
+    int pad[3];
+};
+
+// work queue header: count[0] items in the heavy queue, count[1] in the light queue, head = pop cursor
+struct QueueCtl { unsigned int count[2]; unsigned int head; unsigned int pad; };
