@@ -31,7 +31,9 @@ typedef enum {
                                     (reference: exit(), build_lorentzian.cpp:650-665); its logL is NaN,
                                     status_out[] tells which chain */
     TAMCMC_ERR_NONFINITE = 5,    /* some chain produced a non-finite mode quantity; its logL is NaN */
-    TAMCMC_ERR_LIKELIHOOD = 6    /* likelihood id not on this path (model_def.cpp:405-416) */
+    TAMCMC_ERR_LIKELIHOOD = 6,   /* likelihood id not on this path (model_def.cpp:405-416) */
+    TAMCMC_ERR_POOL = 7          /* the device pool for per-tile component lists is too small for these
+                                    parameters; affected chains are NaN; enlarge with TAMCMC_GPU_POOL_MB */
 } tamcmc_status;
 
 /* per-chain status bits written to status_out[] (0 = evaluated normally) */
@@ -128,6 +130,10 @@ long tamcmc_gpu_pairs_last(tamcmc_gpu_ctx *ctx);            /* sum over chains a
 int tamcmc_gpu_set_profiling(tamcmc_gpu_ctx *ctx, int on);
 int tamcmc_gpu_get_kernel_ms(tamcmc_gpu_ctx *ctx, long *nlaunch, double *expand_ms_total, double *whittle_ms_total);
 long tamcmc_gpu_launch_count(const tamcmc_gpu_ctx *ctx);    /* kernels launched by this context so far */
+/* profiling aid, only in libraries built with -DTAMCMC_TRACE (TAMCMC_ERR_ARG otherwise): per-CTA %globaltimer
+ * stamps of the last fused-kernel launch, 64 slots per CTA: [0] start, [1] end, [2+2i]/[3+2i] begin/end of the
+ * i-th wait for a work segment */
+int tamcmc_gpu_debug_trace(tamcmc_gpu_ctx *ctx, unsigned long long *out, int nctas);
 /* DFMA microbenchmark: achieved FP64 TFLOP/s of `device` (FMA = 2 flops); the roofline denominator */
 int tamcmc_gpu_fp64_peak(int device, double *tflops);
 

@@ -9,12 +9,14 @@ import bench
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 asym = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
 trunc = float(sys.argv[3]) if len(sys.argv) > 3 else 30.0
+zeroH = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 stars, Ps = [], []
 T = synth.tcoefs(10, 1.7)
 for s in range(S):
     rng = np.random.default_rng(12345 + s)
     params, pl = synth.classic_params(rng, asym=asym, trunc_c=trunc)
     x = synth.freq_axis(bench.NBINS, 500.0)
+    if zeroH: params[:20] = 0.0
     with pkg.Context(pkg.Star(3, pl, len(params), x, np.ones_like(x)), 1, [1.0]) as c0:
         M = c0.model(params)
     y = synth.chi2_2dof_spectrum(rng, M)

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "tamcmc_gpu_sync", "tamcmc_gpu_model", "tamcmc_gpu_windows", "tamcmc_gpu_components",
     "tamcmc_gpu_params_stride", "tamcmc_gpu_nstars", "tamcmc_gpu_nchains", "tamcmc_gpu_pairs_last",
     "tamcmc_gpu_set_profiling", "tamcmc_gpu_get_kernel_ms", "tamcmc_gpu_launch_count",
-    "tamcmc_gpu_fp64_peak", "tamcmc_gpu_strerror", "tamcmc_gpu_last_error", "tamcmc_gpu_abi_version",
+    "tamcmc_gpu_debug_trace", "tamcmc_gpu_fp64_peak", "tamcmc_gpu_strerror", "tamcmc_gpu_last_error", "tamcmc_gpu_abi_version",
 ]
 
 
@@ -97,6 +97,8 @@ def lib():
     L.tamcmc_gpu_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_long), _dp, _dp]
     L.tamcmc_gpu_launch_count.restype = C.c_long
     L.tamcmc_gpu_launch_count.argtypes = [vp]
+    L.tamcmc_gpu_debug_trace.restype = C.c_int
+    L.tamcmc_gpu_debug_trace.argtypes = [vp, C.POINTER(C.c_ulonglong), C.c_int]
     L.tamcmc_gpu_fp64_peak.restype = C.c_int
     L.tamcmc_gpu_fp64_peak.argtypes = [C.c_int, _dp]
     L.tamcmc_gpu_strerror.restype = C.c_char_p

@@ -143,6 +143,9 @@ struct tamcmc_gpu_ctx {
     StarDesc* d_stars = nullptr;
     unsigned int* d_queue = nullptr;
     TileRec* d_tilerec = nullptr;
+    unsigned char* d_pool = nullptr;
+    unsigned long long pool_bytes = 0;
+    unsigned long long* d_trace = nullptr;   // profiling aid (TAMCMC_TRACE builds)
     QueueCtl* d_qctl = nullptr;
     unsigned int qcap = 0;
     int grid_ctas = 0;
@@ -156,13 +159,19 @@ struct tamcmc_gpu_ctx {
     int* d_asym = nullptr;
     double* d_Tcoefs = nullptr;
     double* d_partial = nullptr;
-    unsigned int* d_counters = nullptr;
     void* d_out = nullptr;          // [SC] double logL then [SC] int status
     double* d_model = nullptr;      // max Nloc
     // pinned host staging
     double* h_params = nullptr;
     unsigned char* h_active = nullptr;
     void* h_out = nullptr;
+    QueueCtl* h_qctl = nullptr;
+    // CUDA graphs of the device-side sequence (memset, expand, tile lists, fused kernel, finalize), keyed by the
+    // buffer pointers of the call
+    struct GraphEntry { const double* p; const unsigned char* a; double* o; int raw; cudaGraphExec_t exec; };
+    GraphEntry graphs[4] = {};
+    int ngraphs = 0;
+    bool use_graphs = true;
     // measurement
     bool profiling = false;
     long nlaunch_prof = 0;
@@ -198,28 +207,70 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum)
     a.x = c->d_x; a.y = c->d_y; a.lnx = c->d_lnx;
     a.modes = c->d_modes; a.comps = c->d_comps; a.noise = c->d_noise;
     a.asym_flag = c->d_asym; a.Tcoefs = c->d_Tcoefs;
-    a.queue = c->d_queue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec;
-    a.partial = c->d_partial; a.counters = c->d_counters;
+    a.queue = c->d_queue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec; a.pool = c->d_pool;
+    a.partial = c->d_partial;
     a.out = d_out; a.model_out = c->d_model;
     a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
-    a.raw_sum = raw_sum;
+    a.raw_sum = raw_sum; a.trace = c->d_trace;
     return a;
 }
 
-// expand + fused kernel on `st`
-int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
-                int raw_sum, cudaStream_t st)
+TileListArgs make_tilelist_args(tamcmc_gpu_ctx* c)
+{
+    TileListArgs a;
+    a.stars = c->d_stars; a.modes = c->d_modes; a.comps = c->d_comps; a.asym_flag = c->d_asym;
+    a.queue = c->d_queue; a.qctl = c->d_qctl; a.tilerec = c->d_tilerec; a.pool = c->d_pool; a.pool_bytes = c->pool_bytes;
+    a.qcap = c->qcap; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
+    return a;
+}
+
+// memset + expand + tile lists + fused kernel + finalize, enqueued on `st`
+int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
+                     int raw_sum, cudaStream_t st, bool prof)
 {
     ExpandArgs ea = make_expand_args(c, d_params, d_active, d_logL);
     WhittleArgs wa = make_whittle_args(c, d_logL, raw_sum);
-    const bool prof = c->profiling && st == c->stream;
     CK(cudaMemsetAsync(c->d_qctl, 0, sizeof(QueueCtl), st));
     if (prof) CK(cudaEventRecord(c->ev[0], st));
     CK(tamcmc_launch_expand(ea, c->SC(), st));
+    CK(tamcmc_launch_tilelist(make_tilelist_args(c), c->qcap, st));
     if (prof) CK(cudaEventRecord(c->ev[1], st));
     CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, st));
+    CK(tamcmc_launch_finalize(wa, c->d_status(), c->SC(), st));
     if (prof) CK(cudaEventRecord(c->ev[2], st));
-    c->launches += 2;
+    return TAMCMC_OK;
+}
+
+// One evaluation on `st`.  Outside profiling the five device operations are replayed as one CUDA graph.
+int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
+                int raw_sum, cudaStream_t st)
+{
+    c->launches += 4;
+    const bool prof = c->profiling && st == c->stream;
+    if (prof || !c->use_graphs) return enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof);
+    for (int i = 0; i < c->ngraphs; i++) {
+        const tamcmc_gpu_ctx::GraphEntry& g = c->graphs[i];
+        if (g.p == d_params && g.a == d_active && g.o == d_logL && g.raw == raw_sum) { CK(cudaGraphLaunch(g.exec, st)); return TAMCMC_OK; }
+    }
+    if (c->ngraphs == 4) {           // evict the oldest
+        cudaGraphExecDestroy(c->graphs[0].exec);
+        for (int i = 1; i < 4; i++) c->graphs[i - 1] = c->graphs[i];
+        c->ngraphs = 3;
+    }
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, c->stream, false);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture");
+    tamcmc_gpu_ctx::GraphEntry g;
+    g.p = d_params; g.a = d_active; g.o = d_logL; g.raw = raw_sum; g.exec = nullptr;
+    e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGraphInstantiate");
+    c->graphs[c->ngraphs++] = g;
+    CK(cudaGraphLaunch(g.exec, st));
     return TAMCMC_OK;
 }
 
@@ -281,6 +332,7 @@ const char* tamcmc_gpu_strerror(int s)
     case TAMCMC_ERR_WINDOW: return "set_imin_imax: imax - imin <= 0 for some chain";
     case TAMCMC_ERR_NONFINITE: return "non-finite mode quantity for some chain";
     case TAMCMC_ERR_LIKELIHOOD: return "likelihood id not on the GPU path";
+    case TAMCMC_ERR_POOL: return "component-list pool too small (TAMCMC_GPU_POOL_MB)";
     }
     return "unknown status";
 }
@@ -303,6 +355,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
 
     tamcmc_gpu_ctx* c = new tamcmc_gpu_ctx();
     c->device = device; c->nstars = nstars; c->Nchains = Nchains; c->p = p;
+    if (const char* e = std::getenv("TAMCMC_GPU_NO_GRAPH")) c->use_graphs = !(e[0] == '1');
     c->h_stars.resize(nstars);
     long long off = 0; int tiles = 0; int maxN = 0;
     for (int s = 0; s < nstars; s++) {
@@ -359,9 +412,29 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     for (int i = 0; i < 3; i++) CKC(cudaEventCreate(&c->ev[i]));
     CKC(cudaMalloc(&c->d_stars, sizeof(StarDesc) * nstars));
     c->qcap = (unsigned int)((size_t)SC * (size_t)c->tiles_stride);
-    CKC(cudaMalloc(&c->d_queue, sizeof(unsigned int) * 2 * (size_t)c->qcap));
+    CKC(cudaMalloc(&c->d_queue, sizeof(unsigned int) * TAMCMC_NBUCKETS * (size_t)c->qcap));
     CKC(cudaMalloc(&c->d_qctl, sizeof(QueueCtl)));
     CKC(cudaMalloc(&c->d_tilerec, sizeof(TileRec) * (size_t)c->qcap));
+    {
+        // list pool: worst case = every component of every mode listed (as a general entry) in every tile;
+        // capped, because typical lists are ~50x smaller.  TAMCMC_GPU_POOL_MB overrides the size.
+        unsigned long long worst = 0;
+        for (int s = 0; s < nstars; s++) {
+            const StarDesc& sd = c->h_stars[s];
+            const unsigned long long per_tile = (unsigned long long)sd.nmodes_cap * (TAMCMC_MAX_COMP_PER_MODE * 64ull + 32ull + 16ull) + 256ull;
+            worst += (unsigned long long)Nchains * (unsigned long long)sd.ntiles * per_tile;
+        }
+        unsigned long long cap = 64ull << 20;
+        const unsigned long long typical = 12288ull * (unsigned long long)c->qcap;
+        if (typical > cap) cap = typical;
+        if (const char* e = std::getenv("TAMCMC_GPU_POOL_MB")) { const long mb = std::atol(e); if (mb > 0) cap = (unsigned long long)mb << 20; }
+        c->pool_bytes = worst < cap ? worst : cap;
+        CKC(cudaMalloc(&c->d_pool, c->pool_bytes));
+    }
+#ifdef TAMCMC_TRACE
+    CKC(cudaMalloc(&c->d_trace, sizeof(unsigned long long) * 64 * 4096));
+    CKC(cudaMemset(c->d_trace, 0, sizeof(unsigned long long) * 64 * 4096));
+#endif
     CKC(cudaMemset(c->d_qctl, 0, sizeof(QueueCtl)));
     c->grid_ctas = g_grid_ctas[device < 64 ? device : 0];
     CKC(cudaMalloc(&c->d_x, sizeof(double) * off));
@@ -375,15 +448,14 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     CKC(cudaMalloc(&c->d_noise, sizeof(NoiseRec) * (size_t)SC));
     CKC(cudaMalloc(&c->d_asym, sizeof(int) * (size_t)SC));
     CKC(cudaMalloc(&c->d_Tcoefs, sizeof(double) * Nchains));
-    CKC(cudaMalloc(&c->d_partial, sizeof(double) * (size_t)SC * c->tiles_stride));
-    CKC(cudaMalloc(&c->d_counters, sizeof(unsigned int) * (size_t)SC));
-    CKC(cudaMemset(c->d_counters, 0, sizeof(unsigned int) * (size_t)SC));
+    CKC(cudaMalloc(&c->d_partial, sizeof(double) * 3 * (size_t)SC * c->tiles_stride));
     CKC(cudaMalloc(&c->d_out, c->out_bytes()));
     CKC(cudaMemset(c->d_out, 0, c->out_bytes()));
     CKC(cudaMalloc(&c->d_model, sizeof(double) * (size_t)maxN));
     CKC(cudaMallocHost(&c->h_params, sizeof(double) * (size_t)SC * c->params_stride));
     CKC(cudaMallocHost(&c->h_active, (size_t)SC));
     CKC(cudaMallocHost(&c->h_out, c->out_bytes()));
+    CKC(cudaMallocHost(&c->h_qctl, sizeof(QueueCtl)));
 
     // upload spectra (padded to a multiple of the tile: x pad = last x, y pad = 0)
     {
@@ -412,13 +484,15 @@ void tamcmc_gpu_destroy(tamcmc_gpu_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_tilerec); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx);
+    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_tilerec); cudaFree(c->d_pool); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx);
     cudaFree(c->d_params); cudaFree(c->d_active); cudaFree(c->d_modes); cudaFree(c->d_comps); cudaFree(c->d_noise);
-    cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_counters); cudaFree(c->d_out);
+    cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_out);
     cudaFree(c->d_model);
     if (c->h_params) cudaFreeHost(c->h_params);
     if (c->h_active) cudaFreeHost(c->h_active);
     if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_qctl) cudaFreeHost(c->h_qctl);
+    for (int i = 0; i < c->ngraphs; i++) cudaGraphExecDestroy(c->graphs[i].exec);
     for (int i = 0; i < 3; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -446,9 +520,14 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char
     }
     { int rc = launch_eval(c, c->d_params, d_act, c->d_logL(), 0, c->stream); if (rc) return rc; }
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_qctl, c->d_qctl, sizeof(QueueCtl), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     { int rc = collect_profile(c); if (rc) return rc; }
     std::memcpy(logL_out, c->h_out, sizeof(double) * (size_t)SC);
+    if (c->h_qctl->overflow) {
+        g_last_error = "component-list pool overflow: raise TAMCMC_GPU_POOL_MB";
+        return TAMCMC_ERR_POOL;
+    }
     const int* st = reinterpret_cast<const int*>(reinterpret_cast<const double*>(c->h_out) + SC);
     if (status_out) std::memcpy(status_out, st, sizeof(int) * (size_t)SC);
     c->pairs_last = -1;
@@ -470,8 +549,9 @@ int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, doub
     { int rc = expand_single(c, star, params_row); if (rc) return rc; }
     const StarDesc& sd = c->h_stars[star];
     WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0);
+    CK(tamcmc_launch_tilelist(make_tilelist_args(c), c->qcap, c->stream));
     CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->stream));
-    c->launches += 1;
+    c->launches += 2;
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     const int SC = c->SC();
@@ -572,6 +652,17 @@ int tamcmc_gpu_get_kernel_ms(tamcmc_gpu_ctx* c, long* nlaunch, double* expand_ms
     if (nlaunch) *nlaunch = c->nlaunch_prof;
     if (expand_ms_total) *expand_ms_total = c->expand_ms;
     if (whittle_ms_total) *whittle_ms_total = c->whittle_ms;
+    return TAMCMC_OK;
+}
+
+int tamcmc_gpu_debug_trace(tamcmc_gpu_ctx* c, unsigned long long* out, int nctas)
+{
+    if (!c || !out || nctas <= 0 || nctas > 4096) return TAMCMC_ERR_ARG;
+    if (!c->d_trace) return TAMCMC_ERR_ARG;      // library not built with -DTAMCMC_TRACE
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, c->d_trace, sizeof(unsigned long long) * 64 * (size_t)nctas, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(c->d_trace, 0, sizeof(unsigned long long) * 64 * 4096));
     return TAMCMC_OK;
 }
 

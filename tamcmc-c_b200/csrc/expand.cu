@@ -350,9 +350,9 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         bool ok = true;
         for (int h = 0; h < s_nz.nh && ok; h++)
             ok = harvey_series(s_nz.H[h], s_nz.lnsc[h], s_nz.pw[h], s_nz.cpi[h], s_nz.spi[h], s_nz.binom[h], tr.xc, lnxc, tr.umax, tr.bg);
-        tr.series_ok = ok ? 1 : 0;
-        tr.pad[0] = tr.pad[1] = tr.pad[2] = 0;
-        A.tilerec[(size_t)sc * A.tiles_stride + tile] = tr;
+        TileRec* dst = A.tilerec + (size_t)sc * A.tiles_stride + tile;     // list descriptor fields: tile-list kernel
+        for (int k = 0; k < TAMCMC_BG_TERMS; k++) dst->bg[k] = tr.bg[k];
+        dst->xc = tr.xc; dst->umax = tr.umax; dst->series_ok = ok ? 1 : 0;
         return;
     }
 
@@ -634,25 +634,23 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         __syncthreads();
         mx = 0;
         for (int w = 0; w < EXP_THREADS / 32; w++) mx = max(mx, s_red[w]);
-        const int thr = max(mx / 2, TILE_BASE_COST + 1);
         const int rounds = (ntiles + blockDim.x - 1) / blockDim.x;
         for (int r = 0; r < rounds; r++) {
             const int t = r * blockDim.x + tid;
             const bool valid = t < ntiles;
-            const bool heavy = valid && tcost[t] >= thr;
-            const unsigned mh = __ballot_sync(0xffffffffu, heavy);
-            const unsigned ml = __ballot_sync(0xffffffffu, valid && !heavy);
-            unsigned bh = 0, bl = 0;
-            if (lane == 0) {
-                if (mh) bh = atomicAdd(&A.qctl->count[0], (unsigned)__popc(mh));
-                if (ml) bl = atomicAdd(&A.qctl->count[1], (unsigned)__popc(ml));
-            }
-            bh = __shfl_sync(0xffffffffu, bh, 0);
-            bl = __shfl_sync(0xffffffffu, bl, 0);
+            // cost class: quarters of the chain's heaviest tile, heaviest first
+            int cls = TAMCMC_NBUCKETS - 1;
+            if (valid) { const int q = (4 * (tcost[t] - TILE_BASE_COST)) / max(mx - TILE_BASE_COST, 1); cls = min(max(TAMCMC_NBUCKETS - 1 - q, 0), TAMCMC_NBUCKETS - 1); }
             const unsigned below = (1u << lane) - 1u;
             const unsigned item = (unsigned)sc * (unsigned)A.tiles_stride + (unsigned)t;
-            if (heavy) A.queue[bh + __popc(mh & below)] = item;
-            else if (valid) A.queue[A.qcap + bl + __popc(ml & below)] = item;
+#pragma unroll
+            for (int k = 0; k < TAMCMC_NBUCKETS; k++) {
+                const unsigned mk = __ballot_sync(0xffffffffu, valid && cls == k);
+                unsigned bk = 0;
+                if (lane == 0 && mk) bk = atomicAdd(&A.qctl->count[k], (unsigned)__popc(mk));
+                bk = __shfl_sync(0xffffffffu, bk, 0);
+                if (valid && cls == k) A.queue[(size_t)k * A.qcap + bk + __popc(mk & below)] = item;
+            }
         }
     }
     __syncthreads();

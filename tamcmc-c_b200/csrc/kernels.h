@@ -38,16 +38,17 @@ struct WhittleArgs {
     const double* Tcoefs;            // [Nchains]
     const unsigned int* queue;
     const TileRec* tilerec;
+    const unsigned char* pool;
     QueueCtl* qctl;
     unsigned int qcap;
-    double* partial;                 // [nstars*Nchains][tiles_stride]
-    unsigned int* counters;          // [nstars*Nchains] tile tickets (self-resetting)
+    double* partial;                 // [nstars*Nchains][tiles_stride][3]: sum y/M, mantissa and exponent of prod 1/M
     double* out;                     // [nstars*Nchains]: tempered logL, or raw sum S if raw_sum
     double* model_out;               // WRITE_MODEL: [Nloc] of the (single) evaluated star/chain
     double p;                        // likelihood parameter (truncated to long like model_def.cpp:399)
     int Nchains;
     int modes_stride;
     int tiles_stride;
+    unsigned long long* trace;       // profiling aid (builds with -DTAMCMC_TRACE): [grid][64] globaltimer stamps
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)
 };
 
@@ -55,8 +56,25 @@ cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const d
 cudaError_t tamcmc_upload_dmm_tables(const double* coef, const double* nnum, const double* nden);
 cudaError_t tamcmc_expand_configure();
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
+struct TileListArgs {
+    const StarDesc* stars;
+    const ModeRec* modes;
+    const CompRec* comps;
+    const int* asym_flag;
+    const unsigned int* queue;
+    QueueCtl* qctl;
+    TileRec* tilerec;
+    unsigned char* pool;
+    unsigned long long pool_bytes;
+    unsigned int qcap;
+    int Nchains;
+    int modes_stride;
+    int tiles_stride;
+};
+cudaError_t tamcmc_launch_tilelist(const TileListArgs& a, unsigned int max_items, cudaStream_t st);
 cudaError_t tamcmc_whittle_configure(int* grid_ctas);   // one-time function attributes; returns the persistent grid size
 cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st);
+cudaError_t tamcmc_launch_finalize(const WhittleArgs& a, const int* status, int nsc, cudaStream_t st);
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st);
 // DFMA throughput microbenchmark: returns achieved FP64 TFLOP/s (2 flops per DFMA)
 cudaError_t tamcmc_fp64_peak(double* tflops, float* ms, int iters);

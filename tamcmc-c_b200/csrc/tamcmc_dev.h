@@ -15,13 +15,13 @@
 #define TAMCMC_MAX_COMP_PER_MODE 7   // l <= 3 -> 2l+1 <= 7 (reference: acoefs.cpp supports l<=3)
 #define TAMCMC_MAX_HARVEY 8
 #define TAMCMC_BG_TERMS 10           // Taylor coefficients of the Harvey background per tile
-#define TAMCMC_TILE 1024             // bins per tile
-#define TAMCMC_CONSUMERS 256         // consumer threads per CTA (4 bins per thread)
+#define TAMCMC_TILE 1536             // bins per tile
+#define TAMCMC_CONSUMERS 384         // consumer threads per CTA (4 bins per thread); ONE persistent CTA per SM
 #define TAMCMC_THREADS (TAMCMC_CONSUMERS + 32)   // + one producer warp
 #define TAMCMC_BINS_PER_THREAD (TAMCMC_TILE / TAMCMC_CONSUMERS)
 #define TAMCMC_MAX_TILES 16384       // tiles per star the expander's cost scan supports (16.7M bins)
 #ifndef TAMCMC_MIN_CTAS
-#define TAMCMC_MIN_CTAS 3            // resident CTAs per SM the fused kernel is compiled for
+#define TAMCMC_MIN_CTAS 1            // resident CTAs per SM the fused kernel is compiled for
 #endif
 
 // per-chain status bits (device -> host)
@@ -83,14 +83,30 @@ struct StarDesc {
     double step;         // x[1]-x[0] (MS models, models.cpp:1952) or x[2]-x[1] (RGB v4, models.cpp:4714)
 };
 
-// per (star, chain, tile) record built by the background CTAs of the expand launch
+// ---- per-tile component lists (built by the tile-list kernel, streamed by TMA into the fused kernel) ----
+#define TAMCMC_CAPF 352              // fast entries per shared-memory segment
+#define TAMCMC_CAPH 64               // mode headers per segment (asymmetric profiles)
+#define TAMCMC_CAPG 24               // general entries per segment
+
+struct __align__(16) FastEntry { double s, c, a, pad; };                 // e' = fma(u, s, c); t' = fma(e', e', a)
+struct __align__(16) ModeHdr { double qa, qb, qc; int begin, count; };   // asym fast path: q(u) and its fast entries
+struct __align__(16) GenEntry { double s, c, aadd, num, qa, qb, qc; int lo, hi; };
+struct __align__(16) SegDesc { int f0, nf, h0, nh, g0, ng, pad0, pad1; }; // slices of the tile's three arrays
+
+// per (star, chain, tile) record: background series from the background CTAs of the expand launch, list
+// descriptor from the tile-list kernel.  The tile's lists live in the pool at pool_off:
+//   FastEntry fast[TF] | ModeHdr hdr[TH] | GenEntry gen[TG] | SegDesc seg[nseg_cap]
 struct __align__(16) TileRec {
     double bg[TAMCMC_BG_TERMS];   // Taylor coefficients in u = x - xc of sum_h H_h/(1+(tau_h x)^p_h)
     double xc;                    // tile-local origin x[tile centre]
     double umax;                  // max |x - xc| over the tile
+    unsigned long long pool_off;  // byte offset of the tile's lists in the pool
     int series_ok;                // 0: the tile must evaluate the background exactly per bin
-    int pad[3];
+    int nseg;                     // segments (1 unless a list exceeds the shared-memory capacities)
+    int TF, TH, TG;               // total entries of the three arrays
+    int s0_nf, s0_nh, s0_ng;      // first segment (f0 = h0 = g0 = 0)
 };
 
-// work queue header: count[0] items in the heavy queue, count[1] in the light queue, head = pop cursor
-struct QueueCtl { unsigned int count[2]; unsigned int head; unsigned int pad; };
+// work queue header: count[k] items in cost bucket k (k = 0 heaviest), head = pop cursor
+#define TAMCMC_NBUCKETS 4            // work-queue cost classes, heaviest first
+struct QueueCtl { unsigned int count[TAMCMC_NBUCKETS]; unsigned int head; unsigned int overflow; unsigned long long pool_cursor; unsigned long long pad; };

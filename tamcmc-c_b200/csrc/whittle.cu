@@ -34,24 +34,20 @@ constexpr int BPT = TAMCMC_BINS_PER_THREAD;
 constexpr int TILE = TAMCMC_TILE;
 constexpr int GROUP = 16;                                  // fast components merged between two renormalisations
 constexpr int NB = TAMCMC_BG_TERMS;
-constexpr int CAPF = 352;                                  // fast components per segment
-constexpr int CAPG = 24;                                   // general entries per segment
-constexpr int CAPH = 64;                                   // mode headers per segment (asym fast path)
-constexpr int PLCAP = 480;                                 // modes classified per producer pass (multiple of 96)
+constexpr int CAPF = TAMCMC_CAPF;                          // fast entries per segment
+constexpr int CAPG = TAMCMC_CAPG;                          // general entries per segment
+constexpr int CAPH = TAMCMC_CAPH;                          // mode headers per segment (asym fast path)
+constexpr int NBUF = 4;                                    // segment ring depth
 
-struct ModeHdr { double qa, qb, qc; int begin, count; };
-struct GenEntry { double s, c, aadd, num, qa, qb, qc; int lo, hi; };
-
-enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16 };
+enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_POISON = 32 };
 
 struct __align__(16) Segment {
-    double x[TILE];          // TMA destination (first segment of a tile)
+    double x[TILE];          // TMA destinations: spectrum tile (first segment of a tile) ...
     double y[TILE];
-    double2 sc[CAPF];        // fast list: {s', c'} with e' = fma(u, s', c')
-    double a[CAPF];          // fast list: 1/A
-    GenEntry gen[CAPG];
+    FastEntry fast[CAPF];    // ... and the slices of the tile's lists built by the tile-list kernel
     ModeHdr hdr[CAPH];
-    double bg[NB];           // background Taylor coefficients in u (incl. nothing of N0)
+    GenEntry gen[CAPG];
+    double bg[NB];           // background Taylor coefficients in u
     double xc, N0;
     int nfast, ngen, nhdr, flags;
     int sc_index, tile, nvalid, lb0;
@@ -59,11 +55,12 @@ struct __align__(16) Segment {
 };
 
 struct Smem {
-    Segment seg[2];
-    unsigned long long full[2], empty[2];
-    int4 plist[PLCAP];       // producer scratch: modes overlapping the tile
-    double red[NC / 32];
-    int is_last;
+    Segment seg[NBUF];
+    unsigned long long full[NBUF], empty[NBUF];
+    double red_s[NBUF][NC / 32];
+    double red_m[NBUF][NC / 32];
+    int red_e[NBUF][NC / 32];
+    unsigned int cnt[NBUF];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -94,7 +91,23 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+#ifdef TAMCMC_TRACE
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TRACE(slot, val) do { if (A.trace && (slot) < 64) A.trace[(size_t)blockIdx.x * 64 + (slot)] = (val); } while (0)
+#else
+#define TRACE(slot, val) do { } while (0)
+#endif
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
+
+// 1/x to ~1 ulp: hardware approximation (rel. error 2^-23) + two Newton steps.  x = 0 -> inf, NaN -> NaN.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
 
 // (N, D) *= 2^-k with k = exponent(D): exact, integer pipe only.  D > 0 always; N >= 0, and N == 0
 // only while D == 1 (nothing merged yet), where k == 0.
@@ -107,7 +120,7 @@ __device__ __forceinline__ void renorm(double& N, double& D)
 }
 
 // ------------------------------------------------------------------------------------------------
-// producer warp
+// producer warp: pops work items and streams their data into the segment ring with TMA bulk copies
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned pop_item(const WhittleArgs& A, int lane)
 {
@@ -116,41 +129,27 @@ __device__ __forceinline__ unsigned pop_item(const WhittleArgs& A, int lane)
     return __shfl_sync(0xffffffffu, idx, 0);
 }
 
-// publish the open segment: header by lane 0, then every lane arrives on the full barrier; the first
-// segment of a tile also carries the TMA bulk loads of x and y
-__device__ __forceinline__ void publish_segment(Smem& sm, int b, int lane, bool first, int flags, int nf, int ng, int nhd,
-                                                int sc, int tile, int nvalid, int lb0, long long off, double xc, double N0,
-                                                const double* xs, const double* ys)
-{
-    Segment* sg = &sm.seg[b];
-    if (lane == 0) {
-        sg->nfast = nf; sg->ngen = ng; sg->nhdr = nhd; sg->flags = flags;
-        sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
-    }
-    __syncwarp();
-    if (first && lane == 0) {
-        mbar_arrive_expect_tx(&sm.full[b], 2u * TILE * sizeof(double));
-        tma_load_1d(sg->x, xs, TILE * sizeof(double), &sm.full[b]);
-        tma_load_1d(sg->y, ys, TILE * sizeof(double), &sm.full[b]);
-    } else mbar_arrive(&sm.full[b]);
-}
-
 __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
 {
-    unsigned use[2] = {0, 0};         // how many times each segment buffer has been filled
+    unsigned use[NBUF];               // how many times each segment buffer has been filled
+    for (int i = 0; i < NBUF; i++) use[i] = 0;
     int b = 0;
-    const unsigned nheavy = A.qctl->count[0], nlight = A.qctl->count[1], ntot = nheavy + nlight;
-    const unsigned below = (1u << lane) - 1u;
+    unsigned cum[TAMCMC_NBUCKETS + 1];
+    cum[0] = 0;
+    for (int k = 0; k < TAMCMC_NBUCKETS; k++) cum[k + 1] = cum[k] + A.qctl->count[k];
+    const unsigned ntot = cum[TAMCMC_NBUCKETS];
     unsigned idx = pop_item(A, lane);
     for (;;) {
         if (idx >= ntot) {
             if (use[b]) mbar_wait(&sm.empty[b], (use[b] - 1) & 1);
-            if (lane == 0) sm.seg[b].flags = SEG_DONE;
+            if (lane == 0) { sm.seg[b].flags = SEG_DONE; mbar_arrive(&sm.full[b]); }
             __syncwarp();
             mbar_arrive(&sm.full[b]);
             return;
         }
-        const unsigned item = (idx < nheavy) ? A.queue[idx] : A.queue[A.qcap + (idx - nheavy)];
+        int bucket = 0;
+        while (idx >= cum[bucket + 1]) bucket++;
+        const unsigned item = A.queue[(size_t)bucket * A.qcap + (idx - cum[bucket])];
         idx = pop_item(A, lane);                      // next item: the atomic's latency hides behind this tile
         const int sc = (int)(item / (unsigned)A.tiles_stride);
         const int tile = (int)(item - (unsigned)sc * (unsigned)A.tiles_stride);
@@ -158,155 +157,48 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
         const TileRec* tr = A.tilerec + item;
         // one round trip: star fields, tile record, chain flags
         const long long soff = sd->off;
-        const int Nloc = sd->Nloc, bin0 = sd->bin0, nmodes = sd->nmodes_cap;
+        const int Nloc = sd->Nloc;
         const double xc = tr->xc;
         const int series_ok = tr->series_ok;
+        const int nseg = tr->nseg;
+        const unsigned long long poff = tr->pool_off;
+        const int TF = tr->TF, TH = tr->TH;
+        int nf = tr->s0_nf, nh = tr->s0_nh, ng = tr->s0_ng, f0 = 0, h0 = 0, g0 = 0;
         const double bgk = (lane < NB) ? tr->bg[lane] : 0.0;
         const bool asym = A.asym_flag[sc] != 0;
         const double N0 = A.noise[sc].N0;
-        const ModeRec* modes = A.modes + (size_t)sc * A.modes_stride;
-        const CompRec* comps = A.comps + (size_t)sc * A.modes_stride * TAMCMC_MAX_COMP_PER_MODE;
 
         const int lb0 = tile * TILE;
-        const int g0 = bin0 + lb0;
         const int nvalid = min(TILE, Nloc - lb0);
-        const int gend = g0 + nvalid;
         const long long off = soff + lb0;
-        const double* xs = A.x + off;
-        const double* ys = A.y + off;
+        const unsigned char* lists = A.pool + poff;
+        const SegDesc* segs = reinterpret_cast<const SegDesc*>(lists + 32ull * TF + 32ull * TH + 64ull * tr->TG);
 
-        bool first = true;
-        int nf = 0, ng = 0, nhd = 0;          // fill levels of the open segment (warp-uniform)
-        if (use[b]) mbar_wait(&sm.empty[b], (use[b] - 1) & 1);
-
-        for (int chunk = 0; chunk < nmodes; chunk += PLCAP) {
-            // ---- pass 1: classify the chain's modes against the tile (16-byte headers), ordered compaction ----
-            int nlist = 0;
-            const int cend = min(nmodes, chunk + PLCAP);
-            for (int base = chunk; base < cend; base += 96) {
-                int4 h[3];
-#pragma unroll
-                for (int r = 0; r < 3; r++) {
-                    const int mi = base + 32 * r + lane;
-                    h[r] = (mi < cend) ? *reinterpret_cast<const int4*>(modes + mi) : make_int4(0, 0, 0, 0);
+        const int nsegs = (nseg > 0) ? nseg : 1;      // nseg == 0: list pool overflow -> poisoned tile (NaN)
+        for (int j = 0; j < nsegs; j++) {
+            if (j > 0) { const SegDesc d = segs[j]; f0 = d.f0; nf = d.nf; h0 = d.h0; nh = d.nh; g0 = d.g0; ng = d.ng; }
+            if (use[b]) mbar_wait(&sm.empty[b], (use[b] - 1) & 1);
+            Segment* sg = &sm.seg[b];
+            const bool first = (j == 0), last = (j == nsegs - 1);
+            if (lane == 0) {
+                const unsigned bytes = (first ? 2u * TILE * (unsigned)sizeof(double) : 0u) + 32u * (unsigned)nf + 32u * (unsigned)nh + 64u * (unsigned)ng;
+                if (bytes) mbar_arrive_expect_tx(&sm.full[b], bytes); else mbar_arrive(&sm.full[b]);
+                if (first) {
+                    tma_load_1d(sg->x, A.x + off, TILE * sizeof(double), &sm.full[b]);
+                    tma_load_1d(sg->y, A.y + off, TILE * sizeof(double), &sm.full[b]);
                 }
-#pragma unroll
-                for (int r = 0; r < 3; r++) {
-                    const int mi = base + 32 * r + lane;
-                    // h = {i0, i1, ncomp, nfast}
-                    const bool ov = (h[r].z > 0) && (h[r].x < gend) && (h[r].y > g0);
-                    const unsigned mk = __ballot_sync(0xffffffffu, ov);
-                    if (ov) {
-                        const int full = (h[r].x <= g0 && h[r].y >= gend) ? 1 : 0;
-                        sm.plist[nlist + __popc(mk & below)] = make_int4(mi | (full << 30), h[r].x, h[r].y, h[r].z | (h[r].w << 8));
-                    }
-                    nlist += __popc(mk);
-                }
+                if (nf) tma_load_1d(sg->fast, lists + 32ull * f0, 32u * (unsigned)nf, &sm.full[b]);
+                if (nh) tma_load_1d(sg->hdr, lists + 32ull * TF + 32ull * h0, 32u * (unsigned)nh, &sm.full[b]);
+                if (ng) tma_load_1d(sg->gen, lists + 32ull * TF + 32ull * TH + 64ull * g0, 64u * (unsigned)ng, &sm.full[b]);
+                sg->nfast = nf; sg->ngen = ng; sg->nhdr = nh;
+                sg->flags = (first ? SEG_FIRST : 0) | (last ? SEG_LAST : 0) | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (nseg > 0 ? 0 : SEG_POISON);
+                sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
             }
+            if (last && lane < NB) sg->bg[lane] = bgk;
             __syncwarp();
-            // ---- pass 2: emit the listed modes, 32 (or 3) at a time ----
-            for (int r0 = 0; r0 < nlist; r0 += 32) {
-                const bool have = (r0 + lane) < nlist;
-                const int4 pe = have ? sm.plist[r0 + lane] : make_int4(0, 0, 0, 0);
-                const int mi = pe.x & 0x3fffffff;
-                const bool full = ((pe.x >> 30) & 1) != 0;
-                const int ncomp = have ? (pe.w & 0xff) : 0;
-                const int nfast = (have && full) ? (pe.w >> 8) : 0;
-                const int ngen = ncomp - nfast;
-                int sub_lo = 0;
-                while (sub_lo < 32) {
-                    int sub_hi = 32;
-                    bool mine = lane >= sub_lo;
-                    int tf = mine ? nfast : 0, tg = mine ? ngen : 0, th = (mine && nfast > 0) ? 1 : 0;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) {
-                        tf += __shfl_xor_sync(0xffffffffu, tf, d);
-                        tg += __shfl_xor_sync(0xffffffffu, tg, d);
-                        th += __shfl_xor_sync(0xffffffffu, th, d);
-                    }
-                    if (tg > CAPG) {
-                        // too many general entries for one segment: 3 modes at a time (3 x 7 <= CAPG)
-                        sub_hi = sub_lo + 3;
-                        mine = lane >= sub_lo && lane < sub_hi;
-                        tf = mine ? nfast : 0; tg = mine ? ngen : 0; th = (mine && nfast > 0) ? 1 : 0;
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) {
-                            tf += __shfl_xor_sync(0xffffffffu, tf, d);
-                            tg += __shfl_xor_sync(0xffffffffu, tg, d);
-                            th += __shfl_xor_sync(0xffffffffu, th, d);
-                        }
-                    }
-                    if (nf + tf > CAPF || ng + tg > CAPG || nhd + th > CAPH) {
-                        // close the open segment (not the last of the tile), continue in the other buffer
-                        publish_segment(sm, b, lane, first, (first ? SEG_FIRST : 0) | (asym ? SEG_ASYM : 0), nf, ng, nhd,
-                                        sc, tile, nvalid, lb0, off, xc, N0, xs, ys);
-                        use[b]++; b ^= 1; first = false;
-                        if (use[b]) mbar_wait(&sm.empty[b], (use[b] - 1) & 1);
-                        nf = ng = nhd = 0;
-                    }
-                    Segment* sg = &sm.seg[b];
-                    // exclusive offsets inside the segment
-                    const int mf = mine ? nfast : 0, mg = mine ? ngen : 0, mh = (mine && nfast > 0) ? 1 : 0;
-                    int of = mf, og = mg, oh = mh;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int a1 = __shfl_up_sync(0xffffffffu, of, d), a2 = __shfl_up_sync(0xffffffffu, og, d), a3 = __shfl_up_sync(0xffffffffu, oh, d);
-                        if (lane >= d) { of += a1; og += a2; oh += a3; }
-                    }
-                    of = nf + of - mf; og = ng + og - mg; oh = nhd + oh - mh;
-                    if (mine && ncomp > 0) {
-                        const CompRec* cp = comps + (size_t)mi * TAMCMC_MAX_COMP_PER_MODE;
-                        double qa = 0.0, qb = 1.0, qc = 0.0;
-                        if (asym || ngen > 0) {
-                            const ModeRec* mr = modes + mi;
-                            qa = mr->qa; qb = mr->qb0 + xc * qa; qc = mr->qc;
-                        }
-                        if (nfast > 0) {
-                            ModeHdr hh; hh.qa = qa; hh.qb = qb; hh.qc = qc; hh.begin = of; hh.count = nfast;
-                            sg->hdr[oh] = hh;
-                        }
-                        // components in two batches of up to 4: the loads of a batch are independent
-#pragma unroll
-                        for (int k0 = 0; k0 < 8; k0 += 4) {
-                            double cnu[4], cs[4], ca[4];
-#pragma unroll
-                            for (int kk = 0; kk < 4; kk++) {
-                                const int k = k0 + kk;
-                                if (k < ncomp) { cnu[kk] = cp[k].nu; cs[kk] = cp[k].s; ca[kk] = cp[k].a; }
-                            }
-#pragma unroll
-                            for (int kk = 0; kk < 4; kk++) {
-                                const int k = k0 + kk;
-                                if (k < ncomp) {
-                                    const double cc = -(cnu[kk] - xc) * cs[kk];
-                                    if (k < nfast) {
-                                        sg->sc[of + k] = make_double2(cs[kk], cc);
-                                        sg->a[of + k] = ca[kk];
-                                    } else {
-                                        // components are stored FAST-first; a FAST one lands here only on a window edge
-                                        const bool ff = k < (pe.w >> 8);
-                                        GenEntry ge;
-                                        ge.s = cs[kk]; ge.c = cc; ge.aadd = ff ? ca[kk] : 1.0; ge.num = ff ? 1.0 : ca[kk];
-                                        ge.qa = qa; ge.qb = qb; ge.qc = qc;
-                                        ge.lo = pe.y - g0; ge.hi = pe.z - g0;
-                                        sg->gen[og + (k - nfast)] = ge;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    nf += tf; ng += tg; nhd += th;
-                    sub_lo = sub_hi;
-                }
-            }
-            __syncwarp();
+            mbar_arrive(&sm.full[b]);
+            use[b]++; b = (b + 1 == NBUF) ? 0 : b + 1;
         }
-
-        // last segment of the tile: background record, then publish
-        if (lane < NB) sm.seg[b].bg[lane] = bgk;
-        publish_segment(sm, b, lane, first, (first ? SEG_FIRST : 0) | SEG_LAST | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0),
-                        nf, ng, nhd, sc, tile, nvalid, lb0, off, xc, N0, xs, ys);
-        use[b]++; b ^= 1;
     }
 }
 
@@ -317,17 +209,28 @@ template <bool WRITE_MODEL>
 __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
-    unsigned use[2] = {0, 0};
+    unsigned use[NBUF];
+    for (int i = 0; i < NBUF; i++) use[i] = 0;
     int b = 0;
     double u[BPT], N[BPT], D[BPT], yv[BPT];
 #pragma unroll
     for (int j = 0; j < BPT; j++) { u[j] = 0; N[j] = 0; D[j] = 1; yv[j] = 0; }
 
+#ifdef TAMCMC_TRACE
+    int tslot = 2;
+    if (tid == 0) { TRACE(0, gtime()); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); TRACE(63, (unsigned long long)smid + 1); }
+#endif
     for (;;) {
+#ifdef TAMCMC_TRACE
+        if (tid == 0) TRACE(tslot, gtime());        // begin waiting for a segment
+#endif
         mbar_wait(&sm.full[b], use[b] & 1);
         use[b]++;
         const Segment& sg = sm.seg[b];
         const int flags = sg.flags;
+#ifdef TAMCMC_TRACE
+        if (tid == 0) { TRACE(tslot + 1, gtime()); tslot += 2; if (flags & SEG_DONE) TRACE(1, gtime()); }
+#endif
         if (flags & SEG_DONE) return;
         const bool asym = (flags & SEG_ASYM) != 0;
 
@@ -352,8 +255,8 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
             for (; k + GROUP <= tot_fast; k += GROUP) {
 #pragma unroll
                 for (int kk = 0; kk < GROUP; kk++) {
-                    const double2 p = sg.sc[k + kk];
-                    const double a = sg.a[k + kk];
+                    const double2 p = *reinterpret_cast<const double2*>(&sg.fast[k + kk].s);
+                    const double a = sg.fast[k + kk].a;
 #pragma unroll
                     for (int j = 0; j < BPT; j++) {
                         const double e = fma(u[j], p.x, p.y);
@@ -365,9 +268,10 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
 #pragma unroll
                 for (int j = 0; j < BPT; j++) renorm(N[j], D[j]);
             }
+#pragma unroll 4
             for (; k < tot_fast; k++) {
-                const double2 p = sg.sc[k];
-                const double a = sg.a[k];
+                const double2 p = *reinterpret_cast<const double2*>(&sg.fast[k].s);
+                const double a = sg.fast[k].a;
 #pragma unroll
                 for (int j = 0; j < BPT; j++) {
                     const double e = fma(u[j], p.x, p.y);
@@ -389,8 +293,8 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
 #pragma unroll
                 for (int j = 0; j < BPT; j++) { const double w = fma(u[j], h.qa, h.qb); q[j] = fma(w, w, h.qc); }
                 for (int k = h.begin; k < h.begin + h.count; k++) {
-                    const double2 p = sg.sc[k];
-                    const double a = sg.a[k];
+                    const double2 p = *reinterpret_cast<const double2*>(&sg.fast[k].s);
+                    const double a = sg.fast[k].a;
 #pragma unroll
                     for (int j = 0; j < BPT; j++) {
                         const double e = fma(u[j], p.x, p.y);
@@ -410,22 +314,21 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
             for (int j = 0; j < BPT; j++) renorm(N[j], D[j]);
         }
 
-        // ---------- general path: window edges and extreme-dynamic-range components.  The tile is cut in
-        // 512-bin segments (one per register pair of every thread): a segment the window covers is merged
-        // unmasked, a segment holding a window edge under a per-bin mask, others are skipped; all three
-        // decisions are CTA-uniform. ----------
+        // ---------- general path: window edges and extreme-dynamic-range components.  Every warp owns a
+        // contiguous run of 64 bins per register pair (bins 2*tid + 2*NC*pj + r): a run the window covers is merged unmasked, a run holding
+        // a window edge under a per-bin mask, the others are skipped; the three-way decision is warp-uniform. ----------
         const int tot_gen = sg.ngen;
         for (int g = 0; g < tot_gen; g++) {
             const GenEntry ge = sg.gen[g];
 #pragma unroll
             for (int pj = 0; pj < BPT / 2; pj++) {
-                const int s0 = 2 * NC * pj, s1 = s0 + 2 * NC;
-                if (ge.hi <= s0 || ge.lo >= s1) continue;
-                const bool whole = (ge.lo <= s0 && ge.hi >= s1);
+                const int w0 = 2 * NC * pj + 64 * warp, w1 = w0 + 64;
+                if (ge.hi <= w0 || ge.lo >= w1) continue;
+                const bool whole = (ge.lo <= w0 && ge.hi >= w1);
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
                     const int j = 2 * pj + r;
-                    const int bb = 2 * tid + s0 + r;
+                    const int bb = 2 * tid + 2 * NC * pj + r;
                     const bool in = whole || ((bb >= ge.lo) && (bb < ge.hi));
                     const double e = fma(u[j], ge.s, ge.c);
                     const double t = fma(e, e, ge.aadd);
@@ -481,68 +384,67 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
                 for (int j = 0; j < BPT; j++) bgv[j] = N0;
             }
 
-            // ---------- M = N/D + background; Whittle terms ----------
-            double s1 = 0.0, prod = 1.0;
+            // ---------- M = N/D + background; Whittle terms.  y_i/M_i is summed; ln M_i is carried as the
+            // product of the 1/M_i split exactly into mantissa and integer exponent (no log in this kernel:
+            // the finalize kernel takes one log per tile). ----------
+            double s1 = 0.0, pm = 1.0;
+            int pe = 0;
 #pragma unroll
             for (int j = 0; j < BPT; j++) {
                 const int bb = 2 * tid + 2 * NC * (j >> 1) + (j & 1);
                 const double num = fma(bgv[j], D[j], N[j]);
                 if (WRITE_MODEL) { if (bb < nvalid) A.model_out[lb0 + bb] = num / D[j]; }
                 if (bb < nvalid) {
-                    const double minv = D[j] / num;           // 1/M_i
+                    const double minv = D[j] * fast_rcp(num); // 1/M_i
                     s1 = fma(yv[j], minv, s1);                // y_i / M_i
-                    prod *= minv;                             // ln M_i summed as -ln(prod)
+                    const int hi = __double2hiint(minv);
+                    const int k = (hi & 0x7ff00000) - 0x3ff00000;
+                    pm *= __hiloint2double(hi - k, __double2loint(minv));
+                    pe += k >> 20;
                 }
             }
-            double v = s1 - log(prod);
-            const int ntiles = A.stars[sc / A.Nchains].ntiles;
-            // every consumer has read its segment data: hand the buffer back before the reduction
-            mbar_arrive(&sm.empty[b]);
-
-            // ---------- deterministic block reduction over the 8 consumer warps ----------
+            if (flags & SEG_POISON) s1 = nan("");       // the tile's lists did not fit the pool
+            // ---------- barrier-free tile completion.  Every warp deposits its (shuffle-tree) sums in the slots of
+            // this segment buffer; the LAST warp to do so combines the slots in warp order (deterministic whatever
+            // the arrival order) and stores the tile's partial (sum y/M, mantissa and exponent of prod 1/M).  Nobody
+            // waits for anybody: warps that finish early go on to the next segment. ----------
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-            if (lane == 0) sm.red[warp] = v;
-            consumer_sync();
-            if (tid == 0) {
-                double t = sm.red[0];
-#pragma unroll
-                for (int w = 1; w < NC / 32; w++) t += sm.red[w];
-                A.partial[(size_t)sc * A.tiles_stride + tile] = t;
-                __threadfence();
-                const unsigned int ticket = atomicAdd(&A.counters[sc], 1u);
-                sm.is_last = (ticket == (unsigned int)(ntiles - 1));
+            for (int d = 16; d > 0; d >>= 1) {
+                s1 += __shfl_down_sync(0xffffffffu, s1, d);
+                pm *= __shfl_down_sync(0xffffffffu, pm, d);     // mantissas in [1,2): 128 of them stay below 2^128
+                pe += __shfl_down_sync(0xffffffffu, pe, d);
             }
-            consumer_sync();
-            if (sm.is_last) {
-                // last CTA to finish a tile of this (star, chain): sum the per-tile partials in index order
-                __threadfence();
-                const volatile double* part = A.partial + (size_t)sc * A.tiles_stride;
-                double acc = 0.0;
-                for (int t = tid; t < ntiles; t += NC) acc += part[t];
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-                consumer_sync();                          // sm.red reads above are complete
-                if (lane == 0) sm.red[warp] = acc;
-                consumer_sync();
-                if (tid == 0) {
-                    double S = sm.red[0];
-#pragma unroll
-                    for (int w = 1; w < NC / 32; w++) S += sm.red[w];
-                    if (A.raw_sum) A.out[sc] = S;
-                    else {
-                        // likelihood_chi22p: f = -p*S with p truncated to long (model_def.cpp:399), / Tcoefs[m] (:401)
-                        const double pl = (double)(long long)A.p;
-                        A.out[sc] = (-pl * S) / A.Tcoefs[sc % A.Nchains];
-                    }
-                    A.counters[sc] = 0u;                  // ready for the next launch
+            unsigned int prev = 0;
+            if (lane == 0) {
+                sm.red_s[b][warp] = s1; sm.red_m[b][warp] = pm; sm.red_e[b][warp] = pe;
+                __threadfence_block();
+                prev = atomicAdd(&sm.cnt[b], 1u);
+            }
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev == (unsigned int)(NC / 32 - 1) && lane == 0) {
+                __threadfence_block();
+                sm.cnt[b] = 0u;
+                double S = sm.red_s[b][0], Mm = sm.red_m[b][0];
+                int E = sm.red_e[b][0];
+                for (int w = 1; w < NC / 32; w++) {
+                    S += sm.red_s[b][w];
+                    Mm *= sm.red_m[b][w];
+                    E += sm.red_e[b][w];
+                    // keep the running mantissa product in range
+                    const int hi = __double2hiint(Mm);
+                    const int k = (hi & 0x7ff00000) - 0x3ff00000;
+                    Mm = __hiloint2double(hi - k, __double2loint(Mm));
+                    E += k >> 20;
                 }
+                double* part = A.partial + 3 * ((size_t)sc * A.tiles_stride + tile);
+                part[0] = S; part[1] = Mm; part[2] = (double)E;
             }
-            consumer_sync();                              // sm.red / sm.is_last reusable
+            __syncwarp();
+            mbar_arrive(&sm.empty[b]);                    // the slot array of this buffer is free again
         } else {
             mbar_arrive(&sm.empty[b]);
         }
-        b ^= 1;
+        b = (b + 1 == NBUF) ? 0 : b + 1;
     }
 }
 
@@ -553,13 +455,36 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(&sm.full[0], 32); mbar_init(&sm.full[1], 32);
-        mbar_init(&sm.empty[0], NC); mbar_init(&sm.empty[1], NC);
+        for (int i = 0; i < NBUF; i++) { mbar_init(&sm.full[i], 33); mbar_init(&sm.empty[i], NC); sm.cnt[i] = 0u; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid >= NC) producer_loop(A, sm, tid - NC);
     else consumer_loop<WRITE_MODEL>(A, sm, tid);
+}
+
+// One warp per (star, chain): sum of the per-tile partials in tile order.  Each tile contributes
+// sum(y/M) - ln(prod 1/M) = S - ln(m) - E ln 2;  likelihood_chi22p: f = -p*S_total with p truncated to long
+// (model_def.cpp:399), divided by Tcoefs[m] (model_def.cpp:401).
+__global__ void __launch_bounds__(128) tamcmc_finalize_kernel(WhittleArgs A, const int* __restrict__ status, int nsc)
+{
+    const int sc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (sc >= nsc || status[sc] != 0) return;
+    const int ntiles = A.stars[sc / A.Nchains].ntiles;
+    const double* part = A.partial + 3 * (size_t)sc * A.tiles_stride;
+    const double LN2 = 0.693147180559945309417232121458;
+    double acc = 0.0;
+    for (int t = lane; t < ntiles; t += 32) acc += part[3 * t] - (log(part[3 * t + 1]) + part[3 * t + 2] * LN2);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if (lane == 0) {
+        if (A.raw_sum) A.out[sc] = acc;
+        else {
+            const double pl = (double)(long long)A.p;
+            A.out[sc] = (-pl * acc) / A.Tcoefs[sc % A.Nchains];
+        }
+    }
 }
 
 __global__ void tamcmc_lnx_kernel(const double* __restrict__ x, double* __restrict__ lnx, long long n)
@@ -609,6 +534,12 @@ cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool writ
     const size_t smem = sizeof(Smem);
     if (write_model) tamcmc_whittle_kernel<true><<<grid_ctas, NT, smem, st>>>(a);
     else tamcmc_whittle_kernel<false><<<grid_ctas, NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t tamcmc_launch_finalize(const WhittleArgs& a, const int* status, int nsc, cudaStream_t st)
+{
+    tamcmc_finalize_kernel<<<(nsc + 3) / 4, 128, 0, st>>>(a, status, nsc);
     return cudaGetLastError();
 }
 
