@@ -59,3 +59,11 @@ per_sm_end = {}
 for i in range(n): per_sm_end.setdefault(int(sm[i]), []).append(int(end[i]))
 ends = np.array([max(v) for v in per_sm_end.values()]); cnt = np.array([len(v) for v in per_sm_end.values()])
 print("SMs %d, CTAs/SM min %d max %d; per-SM last end: p10 %d p50 %d p90 %d max %d" % (len(ends), cnt.min(), cnt.max(), *np.percentile(ends, [10, 50, 90, 100]).astype(int)))
+# expand-kernel phase stamps of CTA (0,0) and of the first background CTA (nctas == 1 selects that row)
+eb = np.zeros((1, 64), dtype=np.uint64)
+ctx.eval(P)
+rc = pkg.lib().tamcmc_gpu_debug_trace(ctx.h, eb.ctypes.data_as(C.POINTER(C.c_ulonglong)), 1)
+e = eb[0].astype(np.int64)
+names = ["start", "params staged", "phase1 done", "passA done", "passB done", "passC done", "queue done"]
+print("expand mode-CTA phases (ns since start):", [(names[i], int(e[i] - e[0])) for i in range(1, 7) if e[i]])
+print("expand background CTA: %d ns (starts %d ns after the mode CTA)" % (e[33] - e[32], e[32] - e[0]))

@@ -143,6 +143,8 @@ struct tamcmc_gpu_ctx {
     StarDesc* d_stars = nullptr;
     unsigned int* d_queue = nullptr;
     TileRec* d_tilerec = nullptr;
+    unsigned int* d_ready = nullptr;
+    unsigned int* d_epoch = nullptr;
     unsigned char* d_pool = nullptr;
     unsigned long long pool_bytes = 0;
     unsigned long long* d_trace = nullptr;   // profiling aid (TAMCMC_TRACE builds)
@@ -196,7 +198,16 @@ ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const uns
     a.queue = c->d_queue; a.qctl = c->d_qctl; a.qcap = c->qcap;
     a.tilerec = c->d_tilerec; a.x = c->d_x; a.lnx = c->d_lnx;
     a.Nchains = c->Nchains; a.params_stride = c->params_stride; a.modes_stride = c->modes_stride;
-    a.tiles_stride = c->tiles_stride; a.max_tiles = c->max_tiles;
+    a.tiles_stride = c->tiles_stride; a.max_tiles = c->max_tiles; a.trace = c->d_trace ? c->d_trace + 64 * 2048 : nullptr;
+    return a;
+}
+
+TileListArgs make_tilelist_args(tamcmc_gpu_ctx* c)
+{
+    TileListArgs a;
+    a.stars = c->d_stars; a.modes = c->d_modes; a.comps = c->d_comps; a.asym_flag = c->d_asym;
+    a.queue = c->d_queue; a.qctl = c->d_qctl; a.tilerec = c->d_tilerec; a.pool = c->d_pool; a.pool_bytes = c->pool_bytes;
+    a.qcap = c->qcap; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
     return a;
 }
 
@@ -212,15 +223,7 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum)
     a.out = d_out; a.model_out = c->d_model;
     a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
     a.raw_sum = raw_sum; a.trace = c->d_trace;
-    return a;
-}
-
-TileListArgs make_tilelist_args(tamcmc_gpu_ctx* c)
-{
-    TileListArgs a;
-    a.stars = c->d_stars; a.modes = c->d_modes; a.comps = c->d_comps; a.asym_flag = c->d_asym;
-    a.queue = c->d_queue; a.qctl = c->d_qctl; a.tilerec = c->d_tilerec; a.pool = c->d_pool; a.pool_bytes = c->pool_bytes;
-    a.qcap = c->qcap; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
+    a.tl = make_tilelist_args(c); a.ready = c->d_ready; a.epoch = c->d_epoch;
     return a;
 }
 
@@ -233,10 +236,9 @@ int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned c
     CK(cudaMemsetAsync(c->d_qctl, 0, sizeof(QueueCtl), st));
     if (prof) CK(cudaEventRecord(c->ev[0], st));
     CK(tamcmc_launch_expand(ea, c->SC(), st));
-    CK(tamcmc_launch_tilelist(make_tilelist_args(c), c->qcap, st));
     if (prof) CK(cudaEventRecord(c->ev[1], st));
     CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, st));
-    CK(tamcmc_launch_finalize(wa, c->d_status(), c->SC(), st));
+    CK(tamcmc_launch_finalize(wa, c->d_status(), c->SC(), c->d_epoch, st));
     if (prof) CK(cudaEventRecord(c->ev[2], st));
     return TAMCMC_OK;
 }
@@ -245,7 +247,7 @@ int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned c
 int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
                 int raw_sum, cudaStream_t st)
 {
-    c->launches += 4;
+    c->launches += 3;
     const bool prof = c->profiling && st == c->stream;
     if (prof || !c->use_graphs) return enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof);
     for (int i = 0; i < c->ngraphs; i++) {
@@ -414,6 +416,10 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     c->qcap = (unsigned int)((size_t)SC * (size_t)c->tiles_stride);
     CKC(cudaMalloc(&c->d_queue, sizeof(unsigned int) * TAMCMC_NBUCKETS * (size_t)c->qcap));
     CKC(cudaMalloc(&c->d_qctl, sizeof(QueueCtl)));
+    CKC(cudaMalloc(&c->d_ready, sizeof(unsigned int) * TAMCMC_NBUCKETS * (size_t)c->qcap));
+    CKC(cudaMemset(c->d_ready, 0, sizeof(unsigned int) * TAMCMC_NBUCKETS * (size_t)c->qcap));
+    CKC(cudaMalloc(&c->d_epoch, sizeof(unsigned int)));
+    { const unsigned int one = 1u; CKC(cudaMemcpy(c->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice)); }
     CKC(cudaMalloc(&c->d_tilerec, sizeof(TileRec) * (size_t)c->qcap));
     {
         // list pool: worst case = every component of every mode listed (as a general entry) in every tile;
@@ -484,7 +490,7 @@ void tamcmc_gpu_destroy(tamcmc_gpu_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_tilerec); cudaFree(c->d_pool); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx);
+    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_ready); cudaFree(c->d_epoch); cudaFree(c->d_tilerec); cudaFree(c->d_pool); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx);
     cudaFree(c->d_params); cudaFree(c->d_active); cudaFree(c->d_modes); cudaFree(c->d_comps); cudaFree(c->d_noise);
     cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_out);
     cudaFree(c->d_model);
@@ -549,9 +555,9 @@ int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, doub
     { int rc = expand_single(c, star, params_row); if (rc) return rc; }
     const StarDesc& sd = c->h_stars[star];
     WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0);
-    CK(tamcmc_launch_tilelist(make_tilelist_args(c), c->qcap, c->stream));
     CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->stream));
-    c->launches += 2;
+    CK(tamcmc_launch_finalize(wa, c->d_status(), c->SC(), c->d_epoch, c->stream));   // also bumps the ready-flag epoch
+    c->launches += 3;
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     const int SC = c->SC();
@@ -661,7 +667,7 @@ int tamcmc_gpu_debug_trace(tamcmc_gpu_ctx* c, unsigned long long* out, int nctas
     if (!c->d_trace) return TAMCMC_ERR_ARG;      // library not built with -DTAMCMC_TRACE
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemcpy(out, c->d_trace, sizeof(unsigned long long) * 64 * (size_t)nctas, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, c->d_trace + (nctas == 1 ? 64 * 2048 : 0), sizeof(unsigned long long) * 64 * (size_t)nctas, cudaMemcpyDeviceToHost));
     CK(cudaMemset(c->d_trace, 0, sizeof(unsigned long long) * 64 * 4096));
     return TAMCMC_OK;
 }

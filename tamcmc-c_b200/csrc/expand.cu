@@ -54,6 +54,13 @@ cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const d
 
 namespace {
 
+#ifdef TAMCMC_TRACE
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ETRACE(slot) do { if (A.trace && threadIdx.x == 0 && blockIdx.x == 0) A.trace[(blockIdx.y ? 32 : 0) + (slot)] = gtime(); } while (0)
+#else
+#define ETRACE(slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ double Phi(int s, int l, int m) { return c_Pslm_hi[s][l][m + 3]; }
 __device__ __forceinline__ double Plo(int s, int l, int m) { return c_Pslm_lo[s][l][m + 3]; }
 __device__ __forceinline__ double Qlm(int l, int m) { return c_Qlm[l][m + 3]; }
@@ -324,6 +331,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
     NoiseRec* noise = A.noise + sc;
     int* tcost = reinterpret_cast<int*>(sp + A.params_stride);   // [ntiles + 1] difference array -> cost
 
+    ETRACE(0);
     // ---- blockIdx.y >= 1: background CTAs.  One thread per tile of this chain builds the tile record
     // (origin, extent, Taylor series of the Harvey background); they run beside the mode CTAs. ----
     if (blockIdx.y > 0) {
@@ -353,6 +361,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         TileRec* dst = A.tilerec + (size_t)sc * A.tiles_stride + tile;     // list descriptor fields: tile-list kernel
         for (int k = 0; k < TAMCMC_BG_TERMS; k++) dst->bg[k] = tr.bg[k];
         dst->xc = tr.xc; dst->umax = tr.umax; dst->series_ok = ok ? 1 : 0;
+        ETRACE(1);
         return;
     }
 
@@ -388,6 +397,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         for (int k = tid; k <= ntiles; k += blockDim.x) tcost[k] = 0;
     }
     __syncthreads();
+    ETRACE(1);
     const bool inactive = (s_status & TAMCMC_ST_INACTIVE) != 0;
     const double* params = sp;
     const double* fl0_all = params + Nmax + lmax;
@@ -464,6 +474,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
     }
     __syncthreads();
 
+    ETRACE(2);
     // ---------------- phase 2: modes in batches of 128; three passes per batch ----------------
     const int nmodes = sd.nmodes_cap;
     const bool run = !inactive && !(s_status & TAMCMC_ST_BADCFG);
@@ -529,6 +540,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
             if (tid < EXP_BATCH) mt[tid] = t;
         }
         __syncthreads();
+        ETRACE(3);
         // ---- pass B: one thread per (mode, m) slot: nu_nlm and height ----
         for (int sl = tid; sl < EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE; sl += blockDim.x) {
             const int jj = sl / TAMCMC_MAX_COMP_PER_MODE, k = sl - jj * TAMCMC_MAX_COMP_PER_MODE;
@@ -549,6 +561,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
             slot_s[sl] = (2.0 / t.W) / sqrt(h); slot_ia[sl] = 1.0 / h;     // scaled FAST form (used if the slot qualifies)
         }
         __syncthreads();
+        ETRACE(4);
         // ---- pass C: one thread per mode: bit-exact window, component classification, tables ----
         if (tid < EXP_BATCH && mt[tid].have) {
             const ModeTmp& t = mt[tid];
@@ -608,6 +621,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         __syncthreads();
     }
 
+    ETRACE(5);
     // ---------------- phase 3: tile costs -> heavy-first work queue ----------------
     const bool enqueue = run && (s_status == 0);
     if (enqueue) {
@@ -654,6 +668,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         }
     }
     __syncthreads();
+    ETRACE(6);
     if (tid == 0) {
         A.status[sc] = s_status;
         A.asym_flag[sc] = (!inactive && cm.asym != 0.0) ? 1 : 0;

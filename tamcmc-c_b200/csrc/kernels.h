@@ -24,8 +24,24 @@ struct ExpandArgs {
     int modes_stride;
     int tiles_stride;
     int max_tiles;                   // largest ntiles of any star (sizes the dynamic shared memory)
+    unsigned long long* trace;       // profiling aid (TAMCMC_TRACE builds)
 };
 
+struct TileListArgs {
+    const StarDesc* stars;
+    const ModeRec* modes;
+    const CompRec* comps;
+    const int* asym_flag;
+    const unsigned int* queue;
+    QueueCtl* qctl;
+    TileRec* tilerec;
+    unsigned char* pool;
+    unsigned long long pool_bytes;
+    unsigned int qcap;
+    int Nchains;
+    int modes_stride;
+    int tiles_stride;
+};
 struct WhittleArgs {
     const StarDesc* stars;
     const double* x;                 // concatenated local bins, tile-padded
@@ -49,6 +65,9 @@ struct WhittleArgs {
     int modes_stride;
     int tiles_stride;
     unsigned long long* trace;       // profiling aid (builds with -DTAMCMC_TRACE): [grid][64] globaltimer stamps
+    TileListArgs tl;                 // builder warps: inputs of the per-tile list construction
+    unsigned int* ready;             // [qcap * NBUCKETS] per queue position: == epoch once the item's lists are built
+    const unsigned int* epoch;       // device launch counter (never 0); bumped by the finalize kernel
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)
 };
 
@@ -56,25 +75,9 @@ cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const d
 cudaError_t tamcmc_upload_dmm_tables(const double* coef, const double* nnum, const double* nden);
 cudaError_t tamcmc_expand_configure();
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
-struct TileListArgs {
-    const StarDesc* stars;
-    const ModeRec* modes;
-    const CompRec* comps;
-    const int* asym_flag;
-    const unsigned int* queue;
-    QueueCtl* qctl;
-    TileRec* tilerec;
-    unsigned char* pool;
-    unsigned long long pool_bytes;
-    unsigned int qcap;
-    int Nchains;
-    int modes_stride;
-    int tiles_stride;
-};
-cudaError_t tamcmc_launch_tilelist(const TileListArgs& a, unsigned int max_items, cudaStream_t st);
 cudaError_t tamcmc_whittle_configure(int* grid_ctas);   // one-time function attributes; returns the persistent grid size
 cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st);
-cudaError_t tamcmc_launch_finalize(const WhittleArgs& a, const int* status, int nsc, cudaStream_t st);
+cudaError_t tamcmc_launch_finalize(const WhittleArgs& a, const int* status, int nsc, unsigned int* epoch, cudaStream_t st);
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st);
 // DFMA throughput microbenchmark: returns achieved FP64 TFLOP/s (2 flops per DFMA)
 cudaError_t tamcmc_fp64_peak(double* tflops, float* ms, int iters);

@@ -17,7 +17,8 @@
 #define TAMCMC_BG_TERMS 10           // Taylor coefficients of the Harvey background per tile
 #define TAMCMC_TILE 1536             // bins per tile
 #define TAMCMC_CONSUMERS 384         // consumer threads per CTA (4 bins per thread); ONE persistent CTA per SM
-#define TAMCMC_THREADS (TAMCMC_CONSUMERS + 32)   // + one producer warp
+#define TAMCMC_BUILDERS 3            // list-builder warps per CTA of the fused kernel
+#define TAMCMC_THREADS (TAMCMC_CONSUMERS + 32 + 32 * TAMCMC_BUILDERS)   // + one TMA producer warp + builders
 #define TAMCMC_BINS_PER_THREAD (TAMCMC_TILE / TAMCMC_CONSUMERS)
 #define TAMCMC_MAX_TILES 16384       // tiles per star the expander's cost scan supports (16.7M bins)
 #ifndef TAMCMC_MIN_CTAS

@@ -1,20 +1,10 @@
-// tilelist.cu -- per-tile component lists (sm_100a).
-//
-// One warp per (star, chain, tile) work item of the queue.  The warp classifies the chain's modes against the
-// tile (bit-exact windows from the expander), and writes into the list pool
-//     FastEntry fast[TF] : components whose window covers the whole tile, in tile-local scaled form
-//     ModeHdr   hdr[TH]  : per-mode asymmetry polynomial + its fast-entry range (asymmetric chains only)
-//     GenEntry  gen[TG]  : components on a window edge / with extreme dynamic range (masked general path)
-//     SegDesc   seg[..]  : how the fused kernel cuts the three arrays into shared-memory sized segments
-// and the list descriptor into the tile record.  The fused kernel's producer warp then only issues TMA bulk
-// copies; all the latency-bound list building happens here, tens of thousands of tiles in parallel.
+// tilelist_body.cuh -- one warp builds the component lists of one (star, chain, tile) work item.
+// Included by tilelist.cu (standalone kernel) and whittle.cu (builder warps of the fused kernel).
+#pragma once
 #include "tamcmc_dev.h"
 #include "kernels.h"
-#include <cuda_runtime.h>
 
-namespace {
-
-constexpr int WPB = 8;    // warps (tiles) per CTA
+namespace tamcmc_tl {
 
 __device__ __forceinline__ int warp_sum(int v)
 {
@@ -30,15 +20,11 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane)
     return x - v;
 }
 
-__global__ void __launch_bounds__(WPB * 32) tamcmc_tilelist_kernel(TileListArgs A)
+// classifies the chain's modes against the tile (bit-exact windows from the expander) and writes
+//   FastEntry fast[TF] | ModeHdr hdr[TH] | GenEntry gen[TG] | SegDesc seg[..]   into the list pool,
+// and the list descriptor into the tile record
+__device__ void build_tile_lists(const TileListArgs& A, unsigned int item, int lane)
 {
-    const int lane = threadIdx.x & 31;
-    const unsigned int widx = blockIdx.x * WPB + (threadIdx.x >> 5);
-    unsigned int rem = widx, item = 0;
-    int bucket = 0;
-    for (; bucket < TAMCMC_NBUCKETS; bucket++) { const unsigned int n = A.qctl->count[bucket]; if (rem < n) break; rem -= n; }
-    if (bucket == TAMCMC_NBUCKETS) return;
-    item = A.queue[(size_t)bucket * A.qcap + rem];
     const int sc = (int)(item / (unsigned)A.tiles_stride);
     const int tile = (int)(item - (unsigned)sc * (unsigned)A.tiles_stride);
     const StarDesc* sd = A.stars + sc / A.Nchains;
@@ -157,11 +143,4 @@ __global__ void __launch_bounds__(WPB * 32) tamcmc_tilelist_kernel(TileListArgs 
     }
 }
 
-}  // namespace
-
-cudaError_t tamcmc_launch_tilelist(const TileListArgs& a, unsigned int max_items, cudaStream_t st)
-{
-    if (max_items == 0) return cudaSuccess;
-    tamcmc_tilelist_kernel<<<(max_items + WPB - 1) / WPB, WPB * 32, 0, st>>>(a);
-    return cudaGetLastError();
-}
+}  // namespace tamcmc_tl

@@ -23,6 +23,7 @@
 // takes the mask-free fast path, a mode that only partly overlaps it takes the masked general path.
 #include "tamcmc_dev.h"
 #include "kernels.h"
+#include "tilelist_body.cuh"
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -119,6 +120,38 @@ __device__ __forceinline__ void renorm(double& N, double& D)
     N = __hiloint2double(__double2hiint(N) - k, __double2loint(N));
 }
 
+// Pop order -> position in the (heaviest-first) queue.  The first gridDim.x pops take the LIGHTEST items (from the
+// end of the queue): their lists are the quickest to build, so every CTA's consumers have work while the
+// builders prepare the heavy tiles; afterwards items go heaviest-first, which keeps the tail short.
+__device__ __forceinline__ unsigned pop_to_pos(unsigned idx, unsigned ntot)
+{
+    const unsigned g = min((unsigned)gridDim.x, ntot);
+    return (idx < g) ? (ntot - 1u - idx) : (idx - g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// builder warps: the lists of queue position q are built by builder (q mod total builders); heaviest tiles
+// first, so consumers start after one list-build latency and the rest hides behind the arithmetic.  Builders
+// never wait; the producer spins on ready[q] (all CTAs of the persistent grid are co-resident).
+// ------------------------------------------------------------------------------------------------
+__device__ void builder_loop(const WhittleArgs& A, int builder, int lane)
+{
+    unsigned cum[TAMCMC_NBUCKETS + 1];
+    cum[0] = 0;
+    for (int k = 0; k < TAMCMC_NBUCKETS; k++) cum[k + 1] = cum[k] + A.qctl->count[k];
+    const unsigned ntot = cum[TAMCMC_NBUCKETS];
+    const unsigned stride = gridDim.x * TAMCMC_BUILDERS;
+    const unsigned epoch = *A.epoch;
+    for (unsigned q = blockIdx.x * TAMCMC_BUILDERS + builder; q < ntot; q += stride) {
+        const unsigned pos = pop_to_pos(q, ntot);
+        int bucket = 0;
+        while (pos >= cum[bucket + 1]) bucket++;
+        tamcmc_tl::build_tile_lists(A.tl, A.queue[(size_t)bucket * A.qcap + (pos - cum[bucket])], lane);
+        __syncwarp();
+        if (lane == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.ready + q), "r"(epoch) : "memory"); }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // producer warp: pops work items and streams their data into the segment ring with TMA bulk copies
 // ------------------------------------------------------------------------------------------------
@@ -138,6 +171,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
     cum[0] = 0;
     for (int k = 0; k < TAMCMC_NBUCKETS; k++) cum[k + 1] = cum[k] + A.qctl->count[k];
     const unsigned ntot = cum[TAMCMC_NBUCKETS];
+    const unsigned epoch = *A.epoch;
     unsigned idx = pop_item(A, lane);
     for (;;) {
         if (idx >= ntot) {
@@ -147,9 +181,14 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
             mbar_arrive(&sm.full[b]);
             return;
         }
+        const unsigned pos = pop_to_pos(idx, ntot);
         int bucket = 0;
-        while (idx >= cum[bucket + 1]) bucket++;
-        const unsigned item = A.queue[(size_t)bucket * A.qcap + (idx - cum[bucket])];
+        while (pos >= cum[bucket + 1]) bucket++;
+        const unsigned item = A.queue[(size_t)bucket * A.qcap + (pos - cum[bucket])];
+        {   // wait until a builder warp (of any CTA) has published this item's lists
+            unsigned r;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(A.ready + idx) : "memory"); if (r != epoch) __nanosleep(64); } while (r != epoch);
+        }
         idx = pop_item(A, lane);                      // next item: the atomic's latency hides behind this tile
         const int sc = (int)(item / (unsigned)A.tiles_stride);
         const int tile = (int)(item - (unsigned)sc * (unsigned)A.tiles_stride);
@@ -459,15 +498,17 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid >= NC) producer_loop(A, sm, tid - NC);
+    if (tid >= NC + 32) builder_loop(A, (tid - NC - 32) >> 5, tid & 31);
+    else if (tid >= NC) producer_loop(A, sm, tid - NC);
     else consumer_loop<WRITE_MODEL>(A, sm, tid);
 }
 
 // One warp per (star, chain): sum of the per-tile partials in tile order.  Each tile contributes
 // sum(y/M) - ln(prod 1/M) = S - ln(m) - E ln 2;  likelihood_chi22p: f = -p*S_total with p truncated to long
 // (model_def.cpp:399), divided by Tcoefs[m] (model_def.cpp:401).
-__global__ void __launch_bounds__(128) tamcmc_finalize_kernel(WhittleArgs A, const int* __restrict__ status, int nsc)
+__global__ void __launch_bounds__(128) tamcmc_finalize_kernel(WhittleArgs A, const int* __restrict__ status, int nsc, unsigned int* epoch)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned e = *epoch + 1u; *epoch = e ? e : 1u; }   // next launch's ready-flag value
     const int sc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (sc >= nsc || status[sc] != 0) return;
@@ -537,9 +578,9 @@ cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool writ
     return cudaGetLastError();
 }
 
-cudaError_t tamcmc_launch_finalize(const WhittleArgs& a, const int* status, int nsc, cudaStream_t st)
+cudaError_t tamcmc_launch_finalize(const WhittleArgs& a, const int* status, int nsc, unsigned int* epoch, cudaStream_t st)
 {
-    tamcmc_finalize_kernel<<<(nsc + 3) / 4, 128, 0, st>>>(a, status, nsc);
+    tamcmc_finalize_kernel<<<(nsc + 3) / 4, 128, 0, st>>>(a, status, nsc, epoch);
     return cudaGetLastError();
 }
 
