@@ -1,0 +1,115 @@
+// ref_shim_api.cpp -- extern "C" entry points into the REFERENCE's own hot-path functions, compiled where
+// they lie under /root/reference against oracle/eigen_shim (see oracle/Makefile, target `ref`).
+// TEST INFRASTRUCTURE ONLY: used by tests/test_oracle_vs_reference.py and tests/golden/make_golden_from_reference_cpp.py
+// to pin the plain-C oracle.  No reference source is copied here: only declarations from its headers are used.
+#include <Eigen/Dense>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include "build_lorentzian.h"   // reference header: set_imin_imax, build_l_mode_*, optimum_lorentzian_calc_*, Qlm
+#include "function_rot.h"       // amplitude_ratio
+#include "acoefs.h"             // Pslm, eval_acoefs
+#include "interpol.h"           // lin_interpol
+#include "linfit.h"             // linfit
+#include "noise_models.h"       // harvey_like
+#include "likelihoods.h"        // likelihood_chi22p, likelihood_chi_square
+#include "models.h"             // model_MS_Global_*, model_MS_local_*, model_RGB_asympt_* (tamcmc/sources/models.cpp)
+
+using Eigen::VectorXd;
+using Eigen::VectorXi;
+
+// The Alm activity term needs GSL and Boost (absent here); the pin never takes that branch.
+long double Alm(const int, const int, const long double, const long double, std::string) { std::abort(); }
+double Alm_interp_iter_preinitialised(const int, const int, const long double, const long double, const std::string, gsl_funcs) { std::abort(); }
+
+static VectorXd vec(const double* p, long n) { VectorXd v(n); for (long i = 0; i < n; i++) v[i] = p[i]; return v; }
+static void out(const VectorXd& v, double* p) { for (long i = 0; i < (long)v.size(); i++) p[i] = v[i]; }
+
+extern "C" {
+
+long double ref_Pslm(int s, int l, int m) { return Pslm(s, l, m); }
+double ref_Qlm(int l, int m) { return Qlm(l, m); }
+void ref_amplitude_ratio(int l, double beta, double* V) { out(amplitude_ratio(l, beta), V); }
+double ref_lin_interpol(const double* x, const double* y, long n, double xi) { return lin_interpol(vec(x, n), vec(y, n), xi); }
+void ref_linfit(const double* x, const double* y, long n, double* o) { out(linfit(vec(x, n), vec(y, n)), o); }
+void ref_eval_acoefs(int l, const double* nu, double* aj) { VectorXd v = vec(nu, 2 * l + 1); out(eval_acoefs(l, v), aj); }
+
+void ref_set_imin_imax(const double* x, long N, int l, double fc, double gamma, double f_s, double c, double step, int* iv)
+{
+    // NB: the reference exits the process when imax - imin <= 0; callers only pass valid windows
+    VectorXi r = set_imin_imax(vec(x, N), l, fc, gamma, f_s, c, step);
+    iv[0] = r[0]; iv[1] = r[1];
+}
+
+void ref_build_l_mode_a1etaa3(const double* xl, long n, double H, double fc, double f_s, double eta0, double a3, double asym,
+                              double gamma, int l, const double* V, double* res)
+{ out(build_l_mode_a1etaa3(vec(xl, n), H, fc, f_s, eta0, a3, asym, gamma, l, vec(V, 2 * l + 1)), res); }
+
+void ref_build_l_mode_a1etaa3_v2(const double* xl, long n, const double* Hlm, double fc, double f_s, double eta0, double a3,
+                                 double asym, double gamma, int l, double* res)
+{ out(build_l_mode_a1etaa3_v2(vec(xl, n), vec(Hlm, 2 * l + 1), fc, f_s, eta0, a3, asym, gamma, l), res); }
+
+void ref_build_l_mode_a1l_etaa3(const double* xl, long n, double H, double fc, double f_s1, double f_s2, double eta0, double a3,
+                                double asym, double gamma, int l, const double* V, double* res)
+{ out(build_l_mode_a1l_etaa3(vec(xl, n), H, fc, f_s1, f_s2, eta0, a3, asym, gamma, l, vec(V, 2 * l + 1)), res); }
+
+void ref_build_l_mode_a1l_a2a3(const double* xl, long n, double H, double fc, double f_s1, double f_s2, double a2, double a3,
+                               double asym, double gamma, int l, const double* V, double* res)
+{ out(build_l_mode_a1l_a2a3(vec(xl, n), H, fc, f_s1, f_s2, a2, a3, asym, gamma, l, vec(V, 2 * l + 1)), res); }
+
+void ref_build_l_mode_aj(const double* xl, long n, double H, double fc, double a1, double a2, double a3, double a4, double a5,
+                         double a6, double eta0, double asym, double gamma, int l, const double* V, double* res)
+{ out(build_l_mode_aj(vec(xl, n), H, fc, a1, a2, a3, a4, a5, a6, eta0, asym, gamma, l, vec(V, 2 * l + 1)), res); }
+
+// y_out = optimum_lorentzian_calc_a1etaa3(x, y, ...): the full-length vector the reference returns
+void ref_optimum_lorentzian_calc_a1etaa3(const double* x, const double* y, long N, double H, double fc, double f_s, double eta0,
+                                         double a3, double asym, double gamma, int l, const double* V, double step, double c, double* y_out)
+{ out(optimum_lorentzian_calc_a1etaa3(vec(x, N), vec(y, N), H, fc, f_s, eta0, a3, asym, gamma, l, vec(V, 2 * l + 1), step, c), y_out); }
+
+// Optim_L variant: returns i0 and N, fills block[N]
+void ref_optimum_lorentzian_calc_aj(const double* x, long N, double H, double fc, double a1, double a2, double a3, double a4,
+                                    double a5, double a6, double eta0, double asym, double gamma, int l, const double* V,
+                                    double step, double c, int* i0, int* n, double* block)
+{
+    Optim_L r = optimum_lorentzian_calc_aj(vec(x, N), H, fc, a1, a2, a3, a4, a5, a6, eta0, asym, gamma, l, vec(V, 2 * l + 1), step, c);
+    *i0 = r.i0; *n = r.N; out(r.y, block);
+}
+
+void ref_harvey_like(const double* noise, int n_noise, const double* x, const double* y, long N, int Nharvey, double* y_out)
+{ out(harvey_like(vec(noise, n_noise), vec(x, N), vec(y, N), Nharvey), y_out); }
+
+long double ref_likelihood_chi22p(const double* y, const double* model, long N, long p) { return likelihood_chi22p(vec(y, N), vec(model, N), p); }
+long double ref_likelihood_chi_square(const double* y, const double* model, const double* sigma, long N)
+{ return likelihood_chi_square(vec(y, N), vec(model, N), vec(sigma, N)); }
+
+// The reference's own model functions (tamcmc/sources/models.cpp), selected like Model_def::call_model
+// (tamcmc/sources/model_def.cpp:220-388).  Returns 0, or 2 for ids that are obsolete/unknown there or need the
+// GSL-backed Alm grids (21).
+int ref_call_model(int model_id, const double* params, int nparams, const int* plength, const double* x, long N, double* model_out)
+{
+    VectorXd p = vec(params, nparams), xv = vec(x, N), m;
+    VectorXi pl(11);
+    for (int i = 0; i < 11; i++) pl[i] = plength[i];
+    switch (model_id) {
+    case 3: m = model_MS_Global_a1etaa3_HarveyLike_Classic(p, pl, xv, false); break;
+    case 6: m = model_MS_Global_a1l_etaa3_HarveyLike(p, pl, xv, false); break;
+    case 7: m = model_MS_Global_a1n_etaa3_HarveyLike(p, pl, xv, false); break;
+    case 8: m = model_MS_Global_a1nl_etaa3_HarveyLike(p, pl, xv, false); break;
+    case 11: m = model_MS_local_basic(p, pl, xv, false); break;
+    case 12: m = model_MS_Global_a1etaa3_HarveyLike_Classic_v2(p, pl, xv, false); break;
+    case 13: m = model_MS_Global_a1etaa3_HarveyLike_Classic_v3(p, pl, xv, false); break;
+    case 14: m = model_MS_local_Hnlm(p, pl, xv, false); break;
+    case 18: m = model_MS_Global_a1n_a2a3_HarveyLike(p, pl, xv, false); break;
+    case 19: m = model_MS_Global_a1nl_a2a3_HarveyLike(p, pl, xv, false); break;
+    case 23: m = model_MS_Global_aj_HarveyLike(p, pl, xv, false); break;
+    case 25: m = model_RGB_asympt_aj_AppWidth_HarveyLike_v4(p, pl, xv, false); break;
+    case 27: m = model_RGB_asympt_aj_CteWidth_HarveyLike_v4(p, pl, xv, false); break;
+    default: return 2;
+    }
+    out(m, model_out);
+    return 0;
+}
+
+double ref_eta0_fct(const double* fl0, long n) { return eta0_fct(vec(fl0, n)); }
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+"""ctypes wrapper around oracle/_ref/libtamcmc_refshim.so: the REFERENCE's own hot-path sources compiled against the
+Eigen-API shim (oracle/Makefile `ref`).  Test infrastructure only.  Available where /root/reference was present
+at build time (the build container); the built .so travels to the GPU box with the snapshot."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "libtamcmc_refshim.so")
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def available():
+    return os.path.exists(SO)
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Ref:
+    def __init__(self):
+        L = C.CDLL(SO)
+        self.L = L
+        L.ref_Pslm.restype = C.c_longdouble
+        L.ref_Pslm.argtypes = [C.c_int] * 3
+        L.ref_Qlm.restype = C.c_double
+        L.ref_Qlm.argtypes = [C.c_int] * 2
+        L.ref_amplitude_ratio.argtypes = [C.c_int, C.c_double, _dp]
+        L.ref_lin_interpol.restype = C.c_double
+        L.ref_lin_interpol.argtypes = [_dp, _dp, C.c_long, C.c_double]
+        L.ref_eta0_fct.restype = C.c_double
+        L.ref_eta0_fct.argtypes = [_dp, C.c_long]
+        L.ref_set_imin_imax.argtypes = [_dp, C.c_long, C.c_int] + [C.c_double] * 5 + [_ip]
+        L.ref_build_l_mode_a1etaa3.argtypes = [_dp, C.c_long] + [C.c_double] * 7 + [C.c_int, _dp, _dp]
+        L.ref_build_l_mode_aj.argtypes = [_dp, C.c_long] + [C.c_double] * 11 + [C.c_int, _dp, _dp]
+        L.ref_harvey_like.argtypes = [_dp, C.c_int, _dp, _dp, C.c_long, C.c_int, _dp]
+        L.ref_likelihood_chi22p.restype = C.c_longdouble
+        L.ref_likelihood_chi22p.argtypes = [_dp, _dp, C.c_long, C.c_long]
+        L.ref_call_model.restype = C.c_int
+        L.ref_call_model.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, C.c_long, _dp]
+
+    def Pslm(self, s, l, m):
+        return float(self.L.ref_Pslm(s, l, m))
+
+    def Qlm(self, l, m):
+        return self.L.ref_Qlm(l, m)
+
+    def amplitude_ratio(self, l, beta):
+        V = np.zeros(2 * l + 1)
+        self.L.ref_amplitude_ratio(l, float(beta), _p(V))
+        return V
+
+    def lin_interpol(self, x, y, xi):
+        x, y = _d(x), _d(y)
+        return self.L.ref_lin_interpol(_p(x), _p(y), len(x), float(xi))
+
+    def eta0_fct(self, fl0):
+        fl0 = _d(fl0)
+        return self.L.ref_eta0_fct(_p(fl0), len(fl0))
+
+    def set_imin_imax(self, x, l, fc, gamma, f_s, c, step):
+        x = _d(x)
+        iv = np.zeros(2, dtype=np.int32)
+        self.L.ref_set_imin_imax(_p(x), len(x), l, fc, gamma, f_s, c, step, iv.ctypes.data_as(_ip))
+        return int(iv[0]), int(iv[1])
+
+    def build_l_mode_a1etaa3(self, xl, H, fc, fs, eta0, a3, asym, gamma, l, V):
+        xl, V = _d(xl), _d(V)
+        out = np.zeros_like(xl)
+        self.L.ref_build_l_mode_a1etaa3(_p(xl), len(xl), H, fc, fs, eta0, a3, asym, gamma, l, _p(V), _p(out))
+        return out
+
+    def build_l_mode_aj(self, xl, H, fc, a, eta0, asym, gamma, l, V):
+        xl, V = _d(xl), _d(V)
+        out = np.zeros_like(xl)
+        self.L.ref_build_l_mode_aj(_p(xl), len(xl), H, fc, *[float(t) for t in a], eta0, asym, gamma, l, _p(V), _p(out))
+        return out
+
+    def harvey_like(self, noise, x, y, Nharvey):
+        noise, x, y = _d(noise), _d(x), _d(y)
+        out = np.zeros_like(x)
+        self.L.ref_harvey_like(_p(noise), len(noise), _p(x), _p(y), len(x), Nharvey, _p(out))
+        return out
+
+    def chi22p(self, y, model, p=1):
+        y, model = _d(y), _d(model)
+        return float(self.L.ref_likelihood_chi22p(_p(y), _p(model), len(y), int(p)))
+
+    def call_model(self, model_id, params, plength, x):
+        params, x = _d(params), _d(x)
+        pl = np.ascontiguousarray(plength, dtype=np.int32)
+        out = np.zeros(len(x))
+        rc = self.L.ref_call_model(model_id, _p(params), len(params), pl.ctypes.data_as(_ip), _p(x), len(x), _p(out))
+        return rc, out
+
+
+_inst = None
+
+
+def get():
+    global _inst
+    if _inst is None:
+        _inst = Ref()
+    return _inst
