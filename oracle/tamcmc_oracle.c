@@ -1293,3 +1293,99 @@ int orc_eval_chains(int model_id, const double *params, int Nparams, const int *
     }
     return rc_all;
 }
+
+/* ------------------------------------------------------------------------- */
+/* best-effort CPU variant (second CPU baseline line of bench.py only)       */
+/* ------------------------------------------------------------------------- */
+/* Same per-element arithmetic as the reference-faithful path (each mode's m-components are summed in m
+ * order into a local value that is then added to the model, then the Harvey terms, then the Whittle sum),
+ * but window-only, single pass per mode, no full-vector copies and no temporaries.  Implemented for
+ * model_MS_Global_a1etaa3_HarveyLike_Classic (models.cpp:1943-2121); other models use the faithful path. */
+static int classic_fast(const double *params, const int *pl, const double *x, const double *y, long N,
+                        double *model, double p, double Tcoef, double *logL)
+{
+    const double step = x[1] - x[0];
+    const long double pi = PI_L;
+    const int Nmax = pl[0], lmax = pl[1], Nfl0 = pl[2], Nfl1 = pl[3], Nfl2 = pl[4], Nfl3 = pl[5];
+    const int Nsplit = pl[6], Nwidth = pl[7], Nnoise = pl[8], Ninc = pl[9];
+    const int Nf = Nfl0 + Nfl1 + Nfl2 + Nfl3;
+    const int do_amp = (params[Nmax + lmax + Nf + Nsplit + Nwidth + Nnoise + Ninc + 1] != 0);
+    const double trunc_c = params[Nmax + lmax + Nf + Nsplit + Nwidth + Nnoise + Ninc];
+    const double inclination = params[Nmax + lmax + Nf + Nsplit + Nwidth + Nnoise];
+    const double *fl0_all = params + Nmax + lmax, *Wl0_all = params + Nmax + lmax + Nf + Nsplit;
+    const double a1 = fabs(params[Nmax + lmax + Nf]), a3 = params[Nmax + lmax + Nf + 2], asym = params[Nmax + lmax + Nf + 5];
+    const double eta0 = orc_eta0_fct(fl0_all, Nfl0);
+    double ratios[4][7], Vl[4] = {1, 0, 0, 0};
+    long n, i; int l, m, iv[2], rc, k;
+    ratios[0][0] = 1;
+    for (l = 1; l <= lmax && l <= 3; l++) { Vl[l] = fabs(params[Nmax + l - 1]); orc_amplitude_ratio(l, inclination, ratios[l]); }
+    for (i = 0; i < N; i++) model[i] = 0;
+    for (n = 0; n < Nmax; n++)
+        for (l = 0; l <= lmax; l++) {
+            const int off = Nmax + lmax + (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0);
+            const double fc = params[off + n];
+            const double W = (l == 0) ? fabs(Wl0_all[n]) : fabs(orc_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
+            double H, nu[7], hv[7];
+            if (l == 0) H = do_amp ? (double)fabsl(params[n] / (pi * W)) : fabs(params[n]);
+            else H = do_amp ? (double)(fabsl(params[n] / (pi * W)) * Vl[l]) : fabs(params[n] * Vl[l]);
+            rc = orc_set_imin_imax(x, N, l, fc, W, a1, trunc_c, step, iv);
+            if (rc) return rc;
+            for (m = -l; m <= l; m++) {
+                nu[m + l] = (l != 0) ? fc * (1. + eta0 * pow(a1 * 1e-6, 2) * orc_Qlm(l, m)) + m * a1 + orc_Pslm(3, l, m) * a3 : fc;
+                hv[m + l] = H * ratios[l][m + l];
+            }
+            {
+                const double g2 = pow(W, 2), k2 = 0.5 * W * asym / fc;
+                for (i = iv[0]; i < iv[1]; i++) {
+                    double r = 0;
+                    for (k = 0; k <= 2 * l; k++) {
+                        const double d = x[i] - nu[k];
+                        const double prof = 4 * (d * d) / g2;
+                        if (asym == 0) r = r + hv[k] * (1.0 / (1 + prof));
+                        else { const double w = 1 + asym * (x[i] / fc - 1); r = r + hv[k] * ((w * w + k2 * k2) * (1.0 / (1 + prof))); }
+                    }
+                    model[i] = model[i] + r;
+                }
+            }
+        }
+    {
+        const double *np_ = params + Nmax + lmax + Nf + Nsplit + Nwidth;
+        const int Nharvey = (Nnoise - 1) / 3;
+        const double white = fabs(np_[Nnoise - 1]);
+        double s1 = 0, s2 = 0;
+        for (i = 0; i < N; i++) {
+            double v = model[i];
+            for (k = 0; k < Nharvey; k++)
+                if (np_[3 * k + 1] != 0) v = v + fabs(np_[3 * k]) * (1.0 / (pow((1e-3) * fabs(np_[3 * k + 1]) * x[i], fabs(np_[3 * k + 2])) + 1));
+            v = v + white;
+            s1 += y[i] * (1.0 / v);
+            s2 += log(v);
+        }
+        *logL = (double)(((long double)(-(long)p) * (long double)(s1 + s2)) / Tcoef);
+    }
+    return ORC_OK;
+}
+
+int orc_eval_chains_fast(int model_id, const double *params, int Nparams, const int *plength,
+                         const double *x, const double *y, long N, int Nchains, const double *Tcoefs, double p,
+                         double *logL_out, int nthreads)
+{
+    int rc_all = 0, c;
+    if (model_id != ORC_MODEL_MS_GLOBAL_CLASSIC)
+        return orc_eval_chains(model_id, params, Nparams, plength, x, y, N, Nchains, Tcoefs, p, logL_out, nthreads);
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (c = 0; c < Nchains; c++) {
+        double *model = (double *)malloc(sizeof(double) * (size_t)N);
+        int rc = classic_fast(params + (size_t)c * Nparams, plength, x, y, N, model, p, Tcoefs[c], &logL_out[c]);
+        if (rc) {
+            logL_out[c] = NAN;
+#pragma omp critical
+            rc_all = rc;
+        }
+        free(model);
+    }
+    return rc_all;
+}
