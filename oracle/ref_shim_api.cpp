@@ -4,6 +4,7 @@
 // to pin the plain-C oracle.  No reference source is copied here: only declarations from its headers are used.
 #include <Eigen/Dense>
 #include <cstdlib>
+#include <omp.h>
 #include <cstring>
 #include <string>
 #include "build_lorentzian.h"   // reference header: set_imin_imax, build_l_mode_*, optimum_lorentzian_calc_*, Qlm
@@ -109,6 +110,44 @@ int ref_call_model(int model_id, const double* params, int nparams, const int* p
     out(m, model_out);
     return 0;
 }
+
+// One MCMC step's worth of likelihood work with the reference's own functions: the per-chain OpenMP fan-out of
+// MALA.cpp:648 around call_model + call_likelihood (model_def.cpp:466-482, 390-401): model.row(m) = model_X(...);
+// logL = likelihood_chi22p(y, model.row(m), p) / Tcoefs[m].  `model` is kept as the reference's MatrixXd(Nchains, N)
+// so the strided row store / row read are part of the timed work like in the reference.
+int ref_eval_chains(int model_id, const double* params, int nparams, const int* plength, const double* x, const double* y,
+                    long N, int Nchains, const double* Tcoefs, double p_like, double* logL_out, int nthreads)
+{
+    const VectorXd xv = vec(x, N), yv = vec(y, N);
+    VectorXi pl(11);
+    for (int i = 0; i < 11; i++) pl[i] = plength[i];
+    Eigen::MatrixXd model(Nchains, N);
+    int rc = 0;
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for default(shared)
+    for (int chain = 0; chain < Nchains; chain++) {
+        const VectorXd pv = vec(params + (size_t)chain * nparams, nparams);
+        VectorXd m;
+        switch (model_id) {
+        case 3: m = model_MS_Global_a1etaa3_HarveyLike_Classic(pv, pl, xv, false); break;
+        case 6: m = model_MS_Global_a1l_etaa3_HarveyLike(pv, pl, xv, false); break;
+        case 11: m = model_MS_local_basic(pv, pl, xv, false); break;
+        case 12: m = model_MS_Global_a1etaa3_HarveyLike_Classic_v2(pv, pl, xv, false); break;
+        case 13: m = model_MS_Global_a1etaa3_HarveyLike_Classic_v3(pv, pl, xv, false); break;
+        case 23: m = model_MS_Global_aj_HarveyLike(pv, pl, xv, false); break;
+        case 25: m = model_RGB_asympt_aj_AppWidth_HarveyLike_v4(pv, pl, xv, false); break;
+        case 27: m = model_RGB_asympt_aj_CteWidth_HarveyLike_v4(pv, pl, xv, false); break;
+        default: rc = 2; continue;
+        }
+        model.row(chain) = m;
+        const double p = p_like;
+        const long double logL = likelihood_chi22p(yv, model.row(chain), p);
+        logL_out[chain] = (double)(logL / Tcoefs[chain]);
+    }
+    return rc;
+}
+
+int ref_max_threads(void) { return omp_get_max_threads(); }
 
 double ref_eta0_fct(const double* fl0, long n) { return eta0_fct(vec(fl0, n)); }
 

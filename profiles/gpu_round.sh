@@ -1,0 +1,23 @@
+#!/bin/bash
+# One GPU round (run under gpurun on ONE B200): parity tests, the bench line, the ncu launch list of the
+# same bench command and one `--set full` capture of the fused kernel.  Outputs go to gpurun_out/<tag>_*;
+# profiles/summarise_round.py turns them into the tracked summaries under profiles/.
+#   usage: gpurun --timeout 1500 -- 'bash profiles/gpu_round.sh r1'
+TAG=${1:-r1}
+OUT=gpurun_out
+mkdir -p $OUT
+set -o pipefail
+python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
+echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest.log
+tail -3 $OUT/${TAG}_pytest.log
+python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err || { echo "bench failed"; tail -20 $OUT/${TAG}_bench.err; exit 1; }
+cat $OUT/${TAG}_bench.json
+python bench.py --impl reference --steps 10 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
+cat $OUT/${TAG}_bench_reference.json
+BCMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+$BCMD > $OUT/${TAG}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $BCMD > $OUT/${TAG}_ncu_launches.log 2>&1
+echo "ncu launches rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:tamcmc_whittle_kernel -s 4 -c 2 -f -o $OUT/${TAG}_whittle $BCMD > $OUT/${TAG}_ncu_full.log 2>&1
+echo "ncu full rc=$?"
+ls -la $OUT | tail -12

@@ -17,7 +17,8 @@ import numpy as np
 from . import synth  # noqa: F401  (synthetic inputs; numpy only)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtamcmc_gpu.so")
+# TAMCMC_GPU_LIB selects another build of the SAME CUDA library (e.g. the -DTAMCMC_TRACE profiling build)
+LIB_PATH = os.environ.get("TAMCMC_GPU_LIB") or os.path.join(_HERE, "libtamcmc_gpu.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

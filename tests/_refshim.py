@@ -12,8 +12,15 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
 
+SO_O3 = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "libtamcmc_refshim_O3.so")   # bench arm (-O3 like the reference's release build)
+
+
 def available():
     return os.path.exists(SO)
+
+
+def available_O3():
+    return os.path.exists(SO_O3)
 
 
 def _d(a):
@@ -25,8 +32,8 @@ def _p(a):
 
 
 class Ref:
-    def __init__(self):
-        L = C.CDLL(SO)
+    def __init__(self, so=SO):
+        L = C.CDLL(so)
         self.L = L
         L.ref_Pslm.restype = C.c_longdouble
         L.ref_Pslm.argtypes = [C.c_int] * 3
@@ -45,6 +52,9 @@ class Ref:
         L.ref_likelihood_chi22p.argtypes = [_dp, _dp, C.c_long, C.c_long]
         L.ref_call_model.restype = C.c_int
         L.ref_call_model.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, C.c_long, _dp]
+        L.ref_eval_chains.restype = C.c_int
+        L.ref_eval_chains.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _dp, C.c_long, C.c_int, _dp, C.c_double, _dp, C.c_int]
+        L.ref_max_threads.restype = C.c_int
 
     def Pslm(self, s, l, m):
         return float(self.L.ref_Pslm(s, l, m))
@@ -101,7 +111,30 @@ class Ref:
         return rc, out
 
 
+    def eval_chains(self, model_id, params, plength, x, y, Tcoefs, p=1.0, nthreads=0):
+        """The reference's per-chain OpenMP fan-out of call_model + call_likelihood (MALA.cpp:648, model_def.cpp:466-482)."""
+        params = _d(params)
+        Nchains, Nparams = params.shape
+        x, y, T = _d(x), _d(y), _d(Tcoefs)
+        pl = np.ascontiguousarray(plength, dtype=np.int32)
+        out = np.zeros(Nchains)
+        rc = self.L.ref_eval_chains(model_id, _p(params), Nparams, pl.ctypes.data_as(_ip), _p(x), _p(y), len(x), Nchains, _p(T),
+                                    float(p), _p(out), int(nthreads))
+        return rc, out
+
+    def max_threads(self):
+        return int(self.L.ref_max_threads())
+
+
 _inst = None
+_inst_O3 = None
+
+
+def get_O3():
+    global _inst_O3
+    if _inst_O3 is None:
+        _inst_O3 = Ref(SO_O3)
+    return _inst_O3
 
 
 def get():

@@ -1,0 +1,66 @@
+"""The C++ host mirror of the reference's Model_def (tamcmc-c_b200/host/model_def_gpu.hpp) compiled with g++ against
+the C ABI: without a GPU it must fail loudly (no CPU fallback); on the GPU it must match the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import _cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EXE = os.path.join(HERE, "cpp", "test_model_def_gpu")
+LIBDIR = os.path.join(ROOT, "tamcmc-c_b200")
+
+
+def _build():
+    src = os.path.join(HERE, "cpp", "test_model_def_gpu.cpp")
+    hdr = os.path.join(LIBDIR, "host", "model_def_gpu.hpp")
+    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return EXE
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", EXE, src, "-L" + LIBDIR, "-ltamcmc_gpu",
+                           "-L" + cuda_lib, "-lcudart", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath," + cuda_lib])
+    return EXE
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_cpp_mirror_builds_and_fails_loudly_without_gpu(pkg):
+    pkg.lib()          # the shared library must exist (built by __graft_entry__.build())
+    exe = _build()
+    if _have_gpu():
+        pytest.skip("CUDA device present: covered by the gpu-marked test")
+    r = subprocess.run([exe, "nogpu"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "status 3" in r.stdout      # TAMCMC_ERR_CUDA
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_matches_oracle(pkg, oracle, tmp_path):
+    exe = _build()
+    Nmodels = 5
+    params, pl, x = _cases.ms_case(pkg.synth, 3, seed=4, N=20000, asym=12.0)
+    rc, M = oracle.call_model(3, params, pl, x)
+    assert rc == 0
+    rng = np.random.default_rng(8)
+    y = pkg.synth.chi2_2dof_spectrum(rng, M)
+    P = pkg.synth.perturb_chains(rng, params, pl, Nmodels)
+    T = pkg.synth.tcoefs(Nmodels, 1.7)
+    rc, L = oracle.eval_chains(3, P, pl, x, y, T)
+    assert rc == 0
+    logPrior = np.array([-3.0, 0.0, -np.inf, -1.5, -np.inf])
+    f = tmp_path / "case.bin"
+    hdr = np.concatenate([[3, len(x), Nmodels, len(params), 1.0], pl.astype(float)])
+    with open(f, "wb") as fh:
+        for a in (hdr, x, y, T, P.ravel(), logPrior, L, M):
+            fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    r = subprocess.run([exe, str(f)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
