@@ -51,6 +51,24 @@ typedef enum {
 #define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC_V3 13   /* models.cpp:2338 */
 #define TAMCMC_MODEL_MS_GLOBAL_AJ_HARVEYLIKE                 23   /* models.cpp:1195 */
 
+/* Generic MODE TABLE (not a reference model id): the entry for model functions whose mode list is resolved by host
+ * code that stays in the reference -- the ARMM mixed-mode solver of model_RGB_asympt_aj_*_HarveyLike_v4
+ * (models.cpp:4684-5079), the GSL Alm grids of model_MS_Global_ajAlm_HarveyLike (models.cpp:1411-1746).  The host passes
+ * exactly what those functions pass to optimum_lorentzian_calc_aj / _ajAlm (build_lorentzian.cpp:502-522, 480-499) and to
+ * harvey_like (noise_models.cpp:15-39); windows, profiles, background and likelihood run on the GPU.
+ *   plength = [capacity = max modes per chain, step_mode, 0,0,0,0,0,0, Nnoise, 0, 0]
+ *             step_mode 0: step = x[1]-x[0] (MS models, models.cpp:1952); 1: step = x[2]-x[1] (RGB v4, models.cpp:4714)
+ *   Nparams = TAMCMC_MT_HEADER + Nnoise + TAMCMC_MT_STRIDE * capacity
+ *   row     = [nmodes, inclination(deg), trunc_c, asym, noise[Nnoise] (abs() is applied like models.cpp:5017),
+ *              nmodes x {l, fc, H_l, gamma_l, a1, a2, a3, a4, a5, a6, eta0, extra[m=-3..3], 0, 0}]
+ *             m-heights are H_l * amplitude_ratio(l, inclination)[m]; the window uses a1 as f_s;
+ *             nu_nlm = build_l_mode_aj's (build_lorentzian.cpp:222-226) + extra[m]  (extra = fc*epsilon_nl*Alm(l,m) reproduces
+ *             build_l_mode_ajAlm, build_lorentzian.cpp:182-190).  H_l and gamma_l must be >= 0 (the model functions pass
+ *             abs() values); the same per-mode columns as the reference's own `mode_params` table (models.cpp:4941). */
+#define TAMCMC_MODEL_MODE_TABLE 1000
+#define TAMCMC_MT_HEADER 4
+#define TAMCMC_MT_STRIDE 20
+
 /* likelihood ids = Config/default/likelihoods_ctrl.list (model_def.cpp:396-403) */
 #define TAMCMC_LIKELIHOOD_CHI22P 0      /* likelihood_chi22p, likelihoods.cpp:17-28 */
 

@@ -23,6 +23,37 @@ using Eigen::VectorXi;
 long double Alm(const int, const int, const long double, const long double, std::string) { std::abort(); }
 double Alm_interp_iter_preinitialised(const int, const int, const long double, const long double, const std::string, gsl_funcs) { std::abort(); }
 
+// ---- recording wrapper around the reference's optimum_lorentzian_calc_aj (build_lorentzian.cpp:502-522) ----
+// build_lorentzian.cpp is compiled with that symbol renamed to refreal_optimum_lorentzian_calc_aj (oracle/Makefile);
+// models.cpp therefore calls THIS function, which appends the call's arguments to the active recording (if any) and
+// forwards to the reference's implementation.  One row = {l, fc, H, W, a1..a6, eta0, asym, step, c, V[0..6]}.
+Optim_L refreal_optimum_lorentzian_calc_aj(const VectorXd& x, const double H_l, const double fc_l, const double a1, const double a2,
+                                           const double a3, const double a4, const double a5, const double a6, const double eta0,
+                                           const double asym, const double gamma_l, const int l, const VectorXd& V, const double step,
+                                           const double c);
+static double* g_rec = nullptr;
+static int g_rec_cap = 0, g_rec_n = 0;
+enum { REC_STRIDE = 21 };
+Optim_L optimum_lorentzian_calc_aj(const VectorXd& x, const double H_l, const double fc_l, const double a1, const double a2,
+                                   const double a3, const double a4, const double a5, const double a6, const double eta0,
+                                   const double asym, const double gamma_l, const int l, const VectorXd& V, const double step,
+                                   const double c)
+{
+    if (g_rec) {
+#pragma omp critical(refshim_rec)
+        {
+            if (g_rec_n < g_rec_cap) {
+                double* r = g_rec + (size_t)g_rec_n * REC_STRIDE;
+                r[0] = l; r[1] = fc_l; r[2] = H_l; r[3] = gamma_l; r[4] = a1; r[5] = a2; r[6] = a3; r[7] = a4; r[8] = a5; r[9] = a6;
+                r[10] = eta0; r[11] = asym; r[12] = step; r[13] = c;
+                for (int k = 0; k < 7; k++) r[14 + k] = (k < (int)V.size()) ? V[k] : 0.0;
+            }
+            g_rec_n++;
+        }
+    }
+    return refreal_optimum_lorentzian_calc_aj(x, H_l, fc_l, a1, a2, a3, a4, a5, a6, eta0, asym, gamma_l, l, V, step, c);
+}
+
 static VectorXd vec(const double* p, long n) { VectorXd v(n); for (long i = 0; i < n; i++) v[i] = p[i]; return v; }
 static void out(const VectorXd& v, double* p) { for (long i = 0; i < (long)v.size(); i++) p[i] = v[i]; }
 
@@ -148,6 +179,18 @@ int ref_eval_chains(int model_id, const double* params, int nparams, const int* 
 }
 
 int ref_max_threads(void) { return omp_get_max_threads(); }
+
+// ref_call_model while recording every optimum_lorentzian_calc_aj call the model function makes: rows[cap][21]
+// (see REC_STRIDE above); *nrows receives the number of calls.  Not thread-safe (one recording at a time).
+int ref_call_model_recorded(int model_id, const double* params, int nparams, const int* plength, const double* x, long N,
+                            double* model_out, double* rows, int cap, int* nrows)
+{
+    g_rec = rows; g_rec_cap = cap; g_rec_n = 0;
+    const int rc = ref_call_model(model_id, params, nparams, plength, x, N, model_out);
+    *nrows = g_rec_n;
+    g_rec = nullptr; g_rec_cap = 0;
+    return rc;
+}
 
 double ref_eta0_fct(const double* fl0, long n) { return eta0_fct(vec(fl0, n)); }
 

@@ -1295,6 +1295,108 @@ int orc_eval_chains(int model_id, const double *params, int Nparams, const int *
 }
 
 /* ------------------------------------------------------------------------- */
+/* generic mode table (include/tamcmc_gpu.h: TAMCMC_MODEL_MODE_TABLE)         */
+/* ------------------------------------------------------------------------- */
+/* What every model function of the aj family does AFTER it has resolved its mode list on the host: one
+ * optimum_lorentzian_calc_aj call per mode (e.g. models.cpp:4931-5006 for model_RGB_asympt_aj_AppWidth_HarveyLike_v4,
+ * models.cpp:1287-1376 for model_MS_Global_aj_HarveyLike), accumulated into model_final, then
+ * harvey_like(noise_params.array().abs(), ...) (models.cpp:5011-5017).  A mode whose per-m extra shifts are not all
+ * zero follows build_l_mode_ajAlm's order instead (build_lorentzian.cpp:182-190): nu = fc + a1 P1 + a3 P3 + a5 P5,
+ * + centrifugal term, + extra[m] (= fc*epsilon_nl*Alm(l,m), supplied by the caller).
+ * row = [nmodes, inclination, trunc_c, asym, noise[Nnoise], nmodes x {l, fc, H, W, a1..a6, eta0, extra[-3..3], 0, 0}] */
+#define ORC_MT_HDR 4
+#define ORC_MT_STRIDE 20
+int orc_mode_table_model(const double *row, int Nnoise, int step_mode, const double *x, long N, double *out)
+{
+    const int nmodes = (int)row[0];
+    const double inclination = row[1], trunc_c = row[2], asym = row[3];
+    const double step = step_mode ? x[2] - x[1] : x[1] - x[0];     /* models.cpp:4714 vs models.cpp:1952 */
+    const double *modes = row + ORC_MT_HDR + Nnoise;
+    double ratios[4][7];
+    double *model = zeros(N);
+    int j, l, m, rc = 0, Nharvey;
+    ratios[0][0] = 1;
+    for (l = 1; l <= 3; l++) orc_amplitude_ratio(l, inclination, ratios[l]);
+    for (j = 0; j < nmodes && !rc; j++) {
+        const double *r = modes + (size_t)j * ORC_MT_STRIDE;
+        orc_Optim_L blk;
+        int has_extra = 0;
+        l = (int)r[0];
+        if (l < 0 || l > 3) { rc = ORC_ERR_ARG; break; }
+        for (m = 0; m < 7; m++) if (r[11 + m] != 0) has_extra = 1;
+        if (!has_extra) {
+            rc = orc_optimum_lorentzian_calc_aj(x, N, r[2], r[1], r[4], r[5], r[6], r[7], r[8], r[9], r[10], asym, r[3], l,
+                                                ratios[l], step, trunc_c, &blk);
+        } else {
+            /* epsilon_nl * Alm_m * fc == extra: pass fc-normalised values so the product restores extra[m] */
+            double Alm_m[7];
+            for (m = -l; m <= l; m++) Alm_m[m + l] = r[11 + 3 + m];
+            {
+                int iv[2]; long nw; double *x_l;
+                blk.y = 0; blk.i0 = 0; blk.N = 0;
+                rc = orc_set_imin_imax(x, N, l, r[1], r[3], r[4], trunc_c, step, iv);
+                trace_push(l, iv);
+                if (!rc) {
+                    scratch_t sc; long i;
+                    nw = iv[1] - iv[0];
+                    x_l = (double *)malloc(sizeof(double) * (size_t)nw);
+                    blk.y = (double *)malloc(sizeof(double) * (size_t)nw);
+                    memcpy(x_l, x + iv[0], sizeof(double) * (size_t)nw);
+                    scratch_alloc(&sc, nw);
+                    for (i = 0; i < nw; i++) blk.y[i] = 0;
+                    for (m = -l; m <= l; m++) {
+                        double nu;
+                        if (l != 0) {
+                            nu = r[1] + r[4] * orc_Pslm(1, l, m) + r[6] * orc_Pslm(3, l, m) + r[8] * orc_Pslm(5, l, m);
+                            if (r[10] > 0) nu = nu + r[1] * r[10] * orc_Qlm(l, m) * pow(r[4] * 1e-6, 2);
+                            nu = nu + Alm_m[m + l];
+                        } else nu = r[1];
+                        add_component(x_l, nw, nu, r[2] * ratios[l][m + l], r[1], asym, r[3], sc.profile, sc.tmp, sc.tmp2, sc.asymetry, blk.y);
+                    }
+                    scratch_free(&sc);
+                    free(x_l);
+                    blk.i0 = iv[0]; blk.N = (int)nw;
+                }
+            }
+        }
+        if (!rc) add_block(model, &blk);
+    }
+    if (!rc) {
+        double *noise_abs = (double *)malloc(sizeof(double) * (size_t)(Nnoise > 0 ? Nnoise : 1));
+        abs_copy(row + ORC_MT_HDR, Nnoise, noise_abs);
+        Nharvey = (Nnoise - 1) / 3;
+        orc_harvey_like(noise_abs, Nnoise, x, N, &model, Nharvey);
+        free(noise_abs);
+        memcpy(out, model, sizeof(double) * (size_t)N);
+    }
+    free(model);
+    return rc;
+}
+
+int orc_mode_table_eval_chains(const double *rows, int row_stride, int Nnoise, int step_mode, const double *x, const double *y,
+                               long N, int Nchains, const double *Tcoefs, double p, double *logL_out, int nthreads)
+{
+    int rc_all = 0, c;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (c = 0; c < Nchains; c++) {
+        double *model = (double *)malloc(sizeof(double) * (size_t)N);
+        int rc = orc_mode_table_model(rows + (size_t)c * row_stride, Nnoise, step_mode, x, N, model);
+        if (rc) {
+            logL_out[c] = NAN;
+#pragma omp critical
+            rc_all = rc;
+        } else logL_out[c] = (double)orc_call_likelihood_chi22p(y, model, N, p, Tcoefs[c]);
+        free(model);
+    }
+    return rc_all;
+}
+
+/* ------------------------------------------------------------------------- */
 /* best-effort CPU variant (second CPU baseline line of bench.py only)       */
 /* ------------------------------------------------------------------------- */
 /* Same per-element arithmetic as the reference-faithful path (each mode's m-components are summed in m

@@ -140,6 +140,12 @@ int orc_eval_chains_fast(int model_id, const double *params, int Nparams, const 
                          const double *x, const double *y, long N, int Nchains, const double *Tcoefs, double p,
                          double *logL_out, int nthreads);
 
+/* generic mode table (TAMCMC_MODEL_MODE_TABLE of include/tamcmc_gpu.h): what the aj-family model functions do after
+ * resolving their mode list (models.cpp:4931-5017) */
+int orc_mode_table_model(const double *row, int Nnoise, int step_mode, const double *x, long N, double *out);
+int orc_mode_table_eval_chains(const double *rows, int row_stride, int Nnoise, int step_mode, const double *x, const double *y,
+                               long N, int Nchains, const double *Tcoefs, double p, double *logL_out, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,6 +124,7 @@ int modes_of(int model_id, const int* pl)
     switch (model_id) {
     case 3: case 6: case 12: case 13: return pl[0] * (pl[1] + 1);
     case 11: case 23: return pl[2] + pl[3] + pl[4] + pl[5];
+    case TAMCMC_MODEL_ID_MODE_TABLE: return pl[0];
     }
     return -1;
 }
@@ -367,6 +368,14 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         if (nm < 0) { delete c; return TAMCMC_ERR_MODEL; }
         int need = 0;
         for (int k = 0; k < 11; k++) { if (in.plength[k] < 0) { delete c; return TAMCMC_ERR_ARG; } need += in.plength[k]; }
+        const bool mode_table = in.model_id == TAMCMC_MODEL_ID_MODE_TABLE;
+        if (mode_table) {
+            // plength = [capacity (modes per chain), step_mode, 0,0,0,0,0,0, Nnoise, 0, 0]
+            need = TAMCMC_MT_HDR + in.plength[8] + TAMCMC_MT_STRIDE * in.plength[0];
+            if (in.plength[1] > 1 || in.plength[8] < 1) { delete c; return TAMCMC_ERR_ARG; }
+            for (int k = 2; k < 11; k++) if (k != 8 && in.plength[k] != 0) { delete c; return TAMCMC_ERR_ARG; }
+            if (in.plength[1] == 1 && (in.N < 3 || in.N_global > 0)) { delete c; return TAMCMC_ERR_ARG; }
+        }
         if (!in.x || !in.y || in.N < 2 || in.N > 2000000000L || in.Nparams < need || nm == 0) { delete c; return TAMCMC_ERR_ARG; }
         if (in.model_id == 3 || in.model_id == 6 || in.model_id == 12 || in.model_id == 13) {
             // the reference indexes fl_l[n] for n < Nmax and l <= lmax (models.cpp:2026-2075)
@@ -383,6 +392,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         sd.x0 = sharded ? in.x_first : in.x[0];
         sd.xlast = sharded ? in.x_last : in.x[in.N - 1];
         sd.step = sharded ? (in.x_second - in.x_first) : (in.x[1] - in.x[0]);
+        if (mode_table && in.plength[1] == 1) sd.step = in.x[2] - in.x[1];      // RGB v4 models: models.cpp:4714
         if (sharded && (in.bin_offset < 0 || in.bin_offset + in.N > in.N_global)) { delete c; return TAMCMC_ERR_ARG; }
         sd.ntiles = (sd.Nloc + TAMCMC_TILE - 1) / TAMCMC_TILE;
         sd.tile0 = tiles;
@@ -400,6 +410,8 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     }
     c->total_tiles = tiles;
     c->max_tiles = c->tiles_stride;
+    // the expander stages one parameter row + the per-tile cost array in (at most 96 KB of) shared memory
+    if (sizeof(double) * (size_t)c->params_stride + sizeof(int) * (size_t)(c->max_tiles + 2) > 96u * 1024u) { delete c; return TAMCMC_ERR_ARG; }
     if ((size_t)nstars * (size_t)Nchains * (size_t)c->tiles_stride > 0xfffffff0ull) { delete c; return TAMCMC_ERR_ARG; }
     c->total_bins_padded = off;
     const int SC = c->SC();
@@ -582,8 +594,10 @@ int tamcmc_gpu_windows(tamcmc_gpu_ctx* c, int star, const double* params_row, in
     CK(cudaMemcpy(mr.data(), c->d_modes + sc * c->modes_stride, sizeof(ModeRec) * mr.size(), cudaMemcpyDeviceToHost));
     int st = 0;
     CK(cudaMemcpy(&st, c->d_status() + sc, sizeof(int), cudaMemcpyDeviceToHost));
-    *nmodes = sd.nmodes_cap;
-    for (int i = 0; i < sd.nmodes_cap && i < cap; i++) { l[i] = mr[i].l; imin[i] = mr[i].i0; imax[i] = mr[i].i1; }
+    int nlive = sd.nmodes_cap;
+    if (sd.model_id == TAMCMC_MODEL_ID_MODE_TABLE && params_row[0] >= 0 && params_row[0] <= sd.nmodes_cap) nlive = (int)params_row[0];
+    *nmodes = nlive;
+    for (int i = 0; i < nlive && i < cap; i++) { l[i] = mr[i].l; imin[i] = mr[i].i0; imax[i] = mr[i].i1; }
     if (st & TAMCMC_ST_BADCFG) return TAMCMC_ERR_MODEL;
     if (st & TAMCMC_ST_WINDOW) return TAMCMC_ERR_WINDOW;
     if (st & TAMCMC_ST_NONFINITE) return TAMCMC_ERR_NONFINITE;

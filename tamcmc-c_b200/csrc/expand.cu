@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         __shared__ int s_dummy;
         if (A.active && !A.active[sc]) return;
         const int* pl = sd.plength;
-        const int o_noise = pl[0] + pl[1] + pl[2] + pl[3] + pl[4] + pl[5] + pl[6] + pl[7];
+        const int o_noise = (sd.model_id == TAMCMC_MODEL_ID_MODE_TABLE) ? TAMCMC_MT_HDR : pl[0] + pl[1] + pl[2] + pl[3] + pl[4] + pl[5] + pl[6] + pl[7];
         if (threadIdx.x == 0) {
             s_dummy = 0;
             emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (sd.model_id == 11) ? 0 : (pl[8] - 1) / 3, &s_dummy);
@@ -380,11 +380,13 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
     const int Nsplit = pl[6], Nwidth = pl[7], Nnoise = pl[8], Ninc = pl[9];
     const int Nf = Nfl0 + Nfl1 + Nfl2 + Nfl3;
     const int model = sd.model_id;
+    const bool mode_table = (model == TAMCMC_MODEL_ID_MODE_TABLE);
     const int o_split = Nmax + lmax + Nf;
     const int o_width = o_split + Nsplit;
-    const int o_noise = o_width + Nwidth;
+    const int o_noise = mode_table ? TAMCMC_MT_HDR : o_width + Nwidth;
     const int o_inc = o_noise + Nnoise;
     const int o_cfg = o_inc + Ninc;
+    const int o_modes = TAMCMC_MT_HDR + Nnoise;      // mode table: first mode record
     const int ntiles = sd.ntiles;
 
     if (tid == 0) {
@@ -409,9 +411,11 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
             // warp 0, lanes 0..14: the 3+5+7 entries of amplitude_ratio(l, inc), l = 1..3 (or the ratio parameters)
             const int l = (tid < 3) ? 1 : (tid < 8) ? 2 : 3;
             const int i = tid - ((l == 1) ? 0 : (l == 2) ? 3 : 8) - l;       // m = -l..l
-            const bool have = (model == 11) ? (pl[2 + l] >= 1) : (lmax >= l);
+            const bool have = mode_table ? true : (model == 11) ? (pl[2 + l] >= 1) : (lmax >= l);
             if (have) {
-                if (model == 12) {
+                if (mode_table) {
+                    cm.ratios[l][i + l] = d_amplitude_ratio_entry(l, i, params[1]);
+                } else if (model == 12) {
                     // models.cpp:2196-2214: m-ratios read from the "inclination" block, symmetric in m
                     const int base = (l == 1) ? 0 : (l == 2) ? 2 : 5;
                     cm.ratios[l][i + l] = fabs(params[o_inc + base + (i < 0 ? -i : i)]);
@@ -426,12 +430,12 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
             }
         } else if (tid >= 16 && tid <= 18) {
             const int l = tid - 15;
-            const bool have = (model == 11) ? (pl[2 + l] >= 1) : (lmax >= l);
+            const bool have = mode_table ? false : (model == 11) ? (pl[2 + l] >= 1) : (lmax >= l);
             cm.Vl[l] = (have && model != 11) ? fabs(params[Nmax + l - 1]) : 1.0;
         } else if (tid == 32) {
             // warp 1, lane 0: scalar parameters and eta0
-            cm.trunc_c = params[o_cfg];
-            cm.do_amp = (params[o_cfg + 1] != 0.0);
+            cm.trunc_c = mode_table ? params[2] : params[o_cfg];
+            cm.do_amp = mode_table ? 0 : (params[o_cfg + 1] != 0.0);
             cm.ratios[0][0] = 1.0;
             cm.Vl[0] = 1.0;
             cm.status = 0;
@@ -461,6 +465,11 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
                 cm.asym = params[o_split + 13];
                 cm.eta0 = (params[o_split + 12] == 1) ? d_eta0_fct(fl0_all, Nfl0) : 0.0;
                 break;
+            case TAMCMC_MODEL_ID_MODE_TABLE:   // modes already resolved by a host expander (e.g. models.cpp:4788-4911)
+                cm.asym = params[3];
+                cm.eta0 = 0.0;
+                if (!(params[0] >= 0.0 && params[0] <= (double)sd.nmodes_cap)) cm.status = TAMCMC_ST_BADCFG;
+                break;
             default:
                 cm.status = TAMCMC_ST_BADCFG;
                 cm.eta0 = 0; cm.asym = 0;
@@ -478,13 +487,25 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
     // ---------------- phase 2: modes in batches of 128; three passes per batch ----------------
     const int nmodes = sd.nmodes_cap;
     const bool run = !inactive && !(s_status & TAMCMC_ST_BADCFG);
+    const int nmodes_live = (mode_table && run) ? (int)params[0] : nmodes;     // mode table: per-chain mode count
     for (int base = 0; run && base < nmodes; base += EXP_BATCH) {
         // ---- pass A: one thread per mode: degree, frequency, width, height rule, splittings ----
         {
             const int j = base + tid;
             ModeTmp t;
             t.have = 0;
-            if (tid < EXP_BATCH && j < nmodes) {
+            if (mode_table && tid < EXP_BATCH && j < nmodes_live) {
+                // one optimum_lorentzian_calc_aj call of the host model function (e.g. models.cpp:4937, 4952, 4977, 5001)
+                const double* r = params + o_modes + TAMCMC_MT_STRIDE * j;
+                const int l = (int)r[0];
+                if (!(r[0] >= 0.0 && r[0] <= 3.0) || !(r[2] >= 0.0) || !(r[3] >= 0.0)) atomicOr(&s_status, (r[0] == r[0] && r[2] == r[2] && r[3] == r[3]) ? TAMCMC_ST_BADCFG : TAMCMC_ST_NONFINITE);
+                else {
+                    t.have = 1; t.l = l; t.n = j; t.fc = r[1]; t.H = r[2]; t.W = r[3];
+                    for (int k = 0; k < 6; k++) t.a[k] = r[4 + k];
+                    t.eta0 = r[10]; t.fsw = r[4]; t.f_s = 0.0;
+                    t.hoff = o_modes + TAMCMC_MT_STRIDE * j + 11 + 3;     // extra[m] = params[hoff + m]
+                }
+            } else if (!mode_table && tid < EXP_BATCH && j < nmodes) {
                 int l, n;
                 if (model == 3 || model == 12 || model == 13 || model == 6) {
                     l = j % (lmax + 1); n = j / (lmax + 1);          // n-major, l interleaved (models.cpp:2026-2085)
@@ -549,6 +570,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
             const int l = t.l, m = k - l;
             double nu, h;
             if (model == 23) nu = nu_aj(l, m, t.fc, t.a, t.eta0);
+            else if (mode_table) { nu = nu_aj(l, m, t.fc, t.a, t.eta0); if (l != 0) nu = nu + params[t.hoff + m]; }   // build_lorentzian.cpp:182-190
             else nu = nu_a1etaa3(l, m, t.fc, t.f_s, t.eta0, cm.a3);
             if (t.H >= 0.0) h = t.H * cm.ratios[l][k];
             else {
@@ -563,6 +585,13 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         __syncthreads();
         ETRACE(4);
         // ---- pass C: one thread per mode: bit-exact window, component classification, tables ----
+        if (tid < EXP_BATCH && !mt[tid].have && base + tid < nmodes) {
+            // unused slot of a mode table (or a rejected record): an empty record, so stale data is never listed
+            ModeRec mr;
+            mr.i0 = 0; mr.i1 = 0; mr.ncomp = 0; mr.nfast = 0; mr.l = 0; mr.pad = 0;
+            mr.fc = 0; mr.gamma = 0; mr.qa = 0; mr.qb0 = 1; mr.qc = 0;
+            modes[base + tid] = mr;
+        }
         if (tid < EXP_BATCH && mt[tid].have) {
             const ModeTmp& t = mt[tid];
             const int j = base + tid;

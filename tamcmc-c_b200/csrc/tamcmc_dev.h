@@ -25,6 +25,12 @@
 #define TAMCMC_MIN_CTAS 1            // resident CTAs per SM the fused kernel is compiled for
 #endif
 
+// generic mode table (public id TAMCMC_MODEL_MODE_TABLE, include/tamcmc_gpu.h): a parameter row is
+//   [nmodes, inclination, trunc_c, asym, noise[Nnoise], nmodes x {l, fc, H, W, a1..a6, eta0, extra[-3..3], 0, 0}]
+#define TAMCMC_MODEL_ID_MODE_TABLE 1000
+#define TAMCMC_MT_HDR 4
+#define TAMCMC_MT_STRIDE 20
+
 // per-chain status bits (device -> host)
 #define TAMCMC_ST_OK 0
 #define TAMCMC_ST_WINDOW 1      // set_imin_imax: imax-imin <= 0 (reference: exit, build_lorentzian.cpp:650-665)

@@ -21,6 +21,8 @@ MODEL_CLASSIC_V2 = 12
 MODEL_CLASSIC_V3 = 13
 MODEL_AJALM = 21
 MODEL_AJ = 23
+MODEL_MODE_TABLE = 1000      # include/tamcmc_gpu.h: TAMCMC_MODEL_MODE_TABLE
+MT_HEADER, MT_STRIDE = 4, 20
 
 
 def freq_axis(N, x0, step=RESOL_4YR):
@@ -142,3 +144,34 @@ def perturb_chains(rng, params, plength, Nchains, rel=0.01):
 def chi2_2dof_spectrum(rng, model):
     """y_i = M_i * E_i, E ~ Exp(1): a chi^2 with 2 d.o.f. power spectrum around the model."""
     return model * rng.exponential(1.0, size=model.shape)
+
+
+def mode_table_plength(capacity, Nnoise, step_mode=0):
+    """plength of the generic mode table (include/tamcmc_gpu.h)."""
+    pl = np.zeros(11, dtype=np.int32)
+    pl[0], pl[1], pl[8] = capacity, step_mode, Nnoise
+    return pl
+
+
+def mode_table_nparams(capacity, Nnoise):
+    return MT_HEADER + Nnoise + MT_STRIDE * capacity
+
+
+def mode_table_row(capacity, inclination, trunc_c, asym, noise, modes, extra=None):
+    """Pack one chain's resolved modes into a mode-table parameter row.
+    modes: array [nmodes, >=11] with columns l, fc, H, W, a1..a6, eta0 (the first 11 columns of the reference's own
+    `mode_params` table, models.cpp:4941, with eta0 unscaled); extra: optional [nmodes, 7] per-m frequency shifts."""
+    modes = np.asarray(modes, dtype=np.float64)
+    noise = np.asarray(noise, dtype=np.float64)
+    n = len(modes)
+    if n > capacity:
+        raise ValueError("more modes than the table capacity")
+    row = np.zeros(mode_table_nparams(capacity, len(noise)))
+    row[0:4] = [n, inclination, trunc_c, asym]
+    row[4:4 + len(noise)] = noise
+    rec = np.zeros((capacity, MT_STRIDE))
+    rec[:n, :11] = modes[:, :11]
+    if extra is not None:
+        rec[:n, 11:18] = np.asarray(extra, dtype=np.float64)
+    row[4 + len(noise):] = rec.ravel()
+    return row

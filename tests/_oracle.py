@@ -77,6 +77,10 @@ class Oracle:
         L.orc_call_model.argtypes = [C.c_int, _dp, _ip, _dp, C.c_long, _dp, self._alm_t, C.c_void_p]
         L.orc_eval_chains.restype = C.c_int
         L.orc_eval_chains.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _dp, C.c_long, C.c_int, _dp, C.c_double, _dp, C.c_int]
+        L.orc_mode_table_model.restype = C.c_int
+        L.orc_mode_table_model.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_long, _dp]
+        L.orc_mode_table_eval_chains.restype = C.c_int
+        L.orc_mode_table_eval_chains.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_long, C.c_int, _dp, C.c_double, _dp, C.c_int]
         if hasattr(L, "orc_eval_chains_fast"):
             L.orc_eval_chains_fast.restype = C.c_int
             L.orc_eval_chains_fast.argtypes = L.orc_eval_chains.argtypes
@@ -125,6 +129,30 @@ class Oracle:
         if trace:
             n = self.L.orc_trace_end()
             return rc, out, (tl[:n].copy(), t0[:n].copy(), t1[:n].copy())
+        return rc, out
+
+    def mode_table_model(self, row, Nnoise, step_mode, x, trace=False):
+        row, x = _as_d(row), _as_d(x)
+        out = np.zeros(len(x))
+        if trace:
+            cap = 8192
+            tl = np.zeros(cap, dtype=np.int32)
+            t0 = np.zeros(cap, dtype=np.int32)
+            t1 = np.zeros(cap, dtype=np.int32)
+            self.L.orc_trace_begin(tl.ctypes.data_as(_ip), t0.ctypes.data_as(_ip), t1.ctypes.data_as(_ip), cap)
+        rc = self.L.orc_mode_table_model(_p(row), int(Nnoise), int(step_mode), _p(x), len(x), _p(out))
+        if trace:
+            n = self.L.orc_trace_end()
+            return rc, out, (tl[:n].copy(), t0[:n].copy(), t1[:n].copy())
+        return rc, out
+
+    def mode_table_eval_chains(self, rows, Nnoise, step_mode, x, y, Tcoefs, p=1.0, nthreads=0):
+        rows = _as_d(rows)
+        Nchains, stride = rows.shape
+        x, y, T = _as_d(x), _as_d(y), _as_d(Tcoefs)
+        out = np.zeros(Nchains)
+        rc = self.L.orc_mode_table_eval_chains(_p(rows), stride, int(Nnoise), int(step_mode), _p(x), _p(y), len(x), Nchains, _p(T),
+                                               float(p), _p(out), int(nthreads))
         return rc, out
 
     def chi22p(self, y, model, p=1):

@@ -52,6 +52,8 @@ class Ref:
         L.ref_likelihood_chi22p.argtypes = [_dp, _dp, C.c_long, C.c_long]
         L.ref_call_model.restype = C.c_int
         L.ref_call_model.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, C.c_long, _dp]
+        L.ref_call_model_recorded.restype = C.c_int
+        L.ref_call_model_recorded.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, C.c_long, _dp, _dp, C.c_int, _ip]
         L.ref_eval_chains.restype = C.c_int
         L.ref_eval_chains.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _dp, C.c_long, C.c_int, _dp, C.c_double, _dp, C.c_int]
         L.ref_max_threads.restype = C.c_int
@@ -110,6 +112,19 @@ class Ref:
         rc = self.L.ref_call_model(model_id, _p(params), len(params), pl.ctypes.data_as(_ip), _p(x), len(x), _p(out))
         return rc, out
 
+
+    def call_model_recorded(self, model_id, params, plength, x, cap=4096):
+        """The reference's model function + one row {l, fc, H, W, a1..a6, eta0, asym, step, c, V[7]} per
+        optimum_lorentzian_calc_aj call it made (the mode list its host code resolved, e.g. the ARMM mixed modes)."""
+        params, x = _d(params), _d(x)
+        pl = np.ascontiguousarray(plength, dtype=np.int32)
+        out = np.zeros(len(x))
+        rows = np.zeros((cap, 21))
+        n = C.c_int(0)
+        rc = self.L.ref_call_model_recorded(model_id, _p(params), len(params), pl.ctypes.data_as(_ip), _p(x), len(x), _p(out),
+                                            _p(rows), cap, C.byref(n))
+        assert n.value <= cap
+        return rc, out, rows[: n.value].copy()
 
     def eval_chains(self, model_id, params, plength, x, y, Tcoefs, p=1.0, nthreads=0):
         """The reference's per-chain OpenMP fan-out of call_model + call_likelihood (MALA.cpp:648, model_def.cpp:466-482)."""
