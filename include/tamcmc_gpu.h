@@ -155,6 +155,18 @@ int tamcmc_gpu_debug_trace(tamcmc_gpu_ctx *ctx, unsigned long long *out, int nct
 /* DFMA microbenchmark: achieved FP64 TFLOP/s of `device` (FMA = 2 flops); the roofline denominator */
 int tamcmc_gpu_fp64_peak(int device, double *tflops);
 
+/* ---- host expanders (plain host code inside the same library; they produce MODE TABLE rows) ---- */
+/* Alm(l, m, theta0, delta) in radians for filter_code 0 ("gate") / 2 ("triangle"); user callbacks have this signature */
+typedef double (*tamcmc_alm_fn)(int l, int m, double theta0, double delta, int filter_code, void *user);
+/* Replaces: Alm() of external/Alm/Alm_cpp/activity.cpp:221-246 (direct integral; same 64-point Gauss-Legendre rule in theta) */
+double tamcmc_host_alm(int l, int m, double theta0, double delta, int filter_code);
+/* Replaces: the host half of model_MS_Global_ajAlm_HarveyLike (models.cpp:1411-1746; model id 21 of models_ctrl.list):
+ * params/plength in that model's layout -> one MODE TABLE row of `capacity` modes (row_out must hold
+ * TAMCMC_MT_HEADER + Nnoise + TAMCMC_MT_STRIDE*capacity doubles).  alm == NULL uses tamcmc_host_alm; pass a callback to
+ * use the reference's GSL grid interpolation instead (Alm_interp_iter_preinitialised, bilinear_interpol.cpp:118-130). */
+int tamcmc_host_expand_ajAlm(const double *params, const int *plength, tamcmc_alm_fn alm, void *alm_user, int capacity,
+                             double *row_out, int *nmodes_out);
+
 const char *tamcmc_gpu_strerror(int status);
 const char *tamcmc_gpu_last_error(void);
 int tamcmc_gpu_abi_version(void);

@@ -34,7 +34,10 @@ ABI_SYMBOLS = [
     "tamcmc_gpu_params_stride", "tamcmc_gpu_nstars", "tamcmc_gpu_nchains", "tamcmc_gpu_pairs_last",
     "tamcmc_gpu_set_profiling", "tamcmc_gpu_get_kernel_ms", "tamcmc_gpu_launch_count",
     "tamcmc_gpu_debug_trace", "tamcmc_gpu_fp64_peak", "tamcmc_gpu_strerror", "tamcmc_gpu_last_error", "tamcmc_gpu_abi_version",
+    "tamcmc_host_alm", "tamcmc_host_expand_ajAlm",
 ]
+
+ALM_FN = C.CFUNCTYPE(C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p)
 
 
 class StarStruct(C.Structure):
@@ -106,6 +109,10 @@ def lib():
     L.tamcmc_gpu_strerror.argtypes = [C.c_int]
     L.tamcmc_gpu_last_error.restype = C.c_char_p
     L.tamcmc_gpu_abi_version.restype = C.c_int
+    L.tamcmc_host_alm.restype = C.c_double
+    L.tamcmc_host_alm.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+    L.tamcmc_host_expand_ajAlm.restype = C.c_int
+    L.tamcmc_host_expand_ajAlm.argtypes = [_dp, _ip, ALM_FN, vp, C.c_int, _dp, _ip]
     _lib = L
     return L
 
@@ -284,6 +291,24 @@ class Context:
 
     def launch_count(self):
         return int(lib().tamcmc_gpu_launch_count(self.h))
+
+
+def host_alm(l, m, theta0, delta, filter_code=0):
+    """Alm(l, m, theta0, delta) [radians] of the gate (0) / triangle (2) filter (activity.cpp:221-246)."""
+    return lib().tamcmc_host_alm(int(l), int(m), float(theta0), float(delta), int(filter_code))
+
+
+def expand_ajAlm(params, plength, capacity, alm=None):
+    """Host expander of model_MS_Global_ajAlm_HarveyLike (models.cpp:1411-1746): -> (mode-table row, nmodes)."""
+    p = _d(params)
+    pl = np.ascontiguousarray(plength, dtype=np.int32)
+    row = np.zeros(synth.mode_table_nparams(capacity, int(pl[8])))
+    n = C.c_int(0)
+    cb = ALM_FN(alm) if alm is not None else C.cast(None, ALM_FN)
+    rc = lib().tamcmc_host_expand_ajAlm(p.ctypes.data_as(_dp), pl.ctypes.data_as(_ip), cb, None, int(capacity), row.ctypes.data_as(_dp), C.byref(n))
+    if rc != OK:
+        _raise(rc)
+    return row, n.value
 
 
 def fp64_peak(device=0):

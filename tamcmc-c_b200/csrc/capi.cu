@@ -6,6 +6,7 @@
 #include "../../include/tamcmc_gpu.h"
 #include "kernels.h"
 #include "tamcmc_dev.h"
+#include "host_math.hpp"
 
 #include <cuda_runtime.h>
 #include <cmath>
@@ -30,55 +31,10 @@ int fail_cuda(cudaError_t e, const char* what)
         if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
     } while (0)
 
-// ---- Pslm / Qlm tables (host, long double).  Formulas: Ritzwoller & Lavely (1991) polynomials
-// normalised so that Pslm(l)=l (Schou, Christensen-Dalsgaard & Thompson 1994), as used by the
-// reference in tamcmc/sources/acoefs.cpp:51-110; Qlm with the 2/3 factor as
-// tamcmc/sources/build_lorentzian.cpp:583-592. ----
-long double Hslm(int s, int l, int m)
-{
-    const double L = (double)(l * (l + 1)), M = (double)m;
-    switch (s) {
-    case 5: return 252 * std::pow(M, 5) - 140 * (2 * L - 3) * std::pow(M, 3) + (20 * L * (3 * L - 10) + 48) * M;
-    case 6: return 924 * std::pow(M, 6) - 420 * std::pow(M, 4) * (3 * L - 7) + 84 * std::pow(M, 2) * (5 * L * L - 25 * L + 14)
-                 - 20 * L * (L * L - 8 * L + 12);
-    }
-    return 0;
-}
-long double Pslm_host(int s, int l, int m)
-{
-    const double M = (double)m, dl = (double)l;
-    const int LL = l * (l + 1);
-    long double H, c;
-    switch (s) {
-    case 1: return m;
-    case 2: return (l > 0) ? (long double)((3 * M * M - LL) / (2 * l - 1)) : 0.0L;
-    case 3: return (l > 1) ? (long double)((5 * M * M * M - (3 * LL - 1) * M) / ((l - 1) * (2 * l - 1))) : 0.0L;
-    case 4:
-        H = (35 * std::pow(M, 4) - 5 * (6 * LL - 5) * M * M) + 3 * LL * (LL - 2);
-        c = 2 * (l - 1) * (2 * l - 1) * (2 * l - 3);
-        return (c != 0) ? H / c : 0.0L;
-    case 5:
-        H = Hslm(5, l, m);
-        c = 8 * (4 * std::pow(dl, 4) - 20 * std::pow(dl, 3) + 35 * dl * dl - 25 * dl + 6);
-        return (c != 0) ? H / c : 0.0L;
-    case 6:
-        H = Hslm(6, l, m);
-        c = 64 * std::pow(dl, 5) - 480 * std::pow(dl, 4) + 1360 * std::pow(dl, 3) - 1800 * dl * dl + 1096 * dl - 240;
-        return (c != 0) ? H / c : 0.0L;
-    }
-    return 0.0L;
-}
-double Qlm_host(int l, int m)
-{
-    const long double Dnl = 2. / 3;
-    double Q = (l * (l + 1) - 3 * (double)m * (double)m) / ((2 * l - 1) * (2 * l + 3));
-    Q = (double)(Q * Dnl);
-    return Q;
-}
-
-// function_rot.cpp:90-101: int factorial and combi with INTEGER divisions (combi(n,r) = n!/(n-r)!/r! in int)
-int fact_i(int n) { long f = 1; for (long i = 1; i <= n; i++) f *= i; return (int)f; }
-int combi_i(int n, int r) { return fact_i(n) / fact_i(n - r) / fact_i(r); }
+using tamcmc_host::Pslm;
+using tamcmc_host::Qlm;
+using tamcmc_host::fact_i;
+using tamcmc_host::combi_i;
 
 bool g_tables_uploaded[64] = {false};
 int g_grid_ctas[64] = {0};
@@ -91,13 +47,13 @@ int upload_tables(int device)
     for (int s = 1; s <= 6; s++)
         for (int l = 0; l <= 3; l++)
             for (int m = -l; m <= l; m++) {
-                const long double P = Pslm_host(s, l, m);
+                const long double P = Pslm(s, l, m);
                 const double h = (double)P;
                 hi[s][l][m + 3] = h;
                 lo[s][l][m + 3] = (double)(P - (long double)h);
             }
     for (int l = 0; l <= 3; l++)
-        for (int m = -l; m <= l; m++) Q[l][m + 3] = Qlm_host(l, m);
+        for (int m = -l; m <= l; m++) Q[l][m + 3] = Qlm(l, m);
     CK(tamcmc_upload_tables(&hi[0][0][0], &lo[0][0][0], &Q[0][0]));
     {
         // integer factors of dmm(l, i, 0, beta), i >= 0 (function_rot.cpp:76-88)

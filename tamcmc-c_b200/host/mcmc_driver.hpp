@@ -1,0 +1,221 @@
+// mcmc_driver.hpp -- the CALLER of the hot path: a fixed-seed restatement of the reference's adaptive
+// Metropolis + parallel-tempering loop, restructured around ONE batched likelihood evaluation per step
+// (INTEGRATION.md section 3).  Header-only C++17, no Eigen.
+//
+// Reference (tamcmc/sources/MALA.cpp):
+//   constructor / Tcoefs = lambda^m                      :55-107
+//   init_proposal (cov0 = diag(err^2), sigma, mu)        :246-292
+//   new_prop_values (Cholesky of (cov+eps2)*sigma)       :339-369
+//   update_position_MH (Metropolis ratio, NaN -> reject) :463-553
+//   update_proposal (Robbins-Monro: mu, cov, sigma)      :296-319  with p1/p2/p3 projections :135-177
+//   parallel_tempering (adjacent swap, tempered logL)    :397-461
+//   execute (gamma = c0/(1+i), learning windows, mixing) :623-745
+//
+// Differences from the reference, all deliberate and documented in DESIGN.md:
+//   * propose-all -> one evaluation of all chains -> accept-all (chains are independent within a step);
+//   * one seeded std::mt19937_64 drives every draw on the calling thread (the reference seeds from time(NULL) and
+//     races on the shared generator inside its OpenMP loop, MALA.cpp:62,648);
+//   * priors are a user callback (priors_calc.cpp stays in the reference); -inf prior -> the chain is masked out
+//     exactly like model_def.cpp:469-480.
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <random>
+#include <vector>
+
+namespace tamcmc {
+
+struct DriverConfig {
+    int Nchains = 10;
+    double lambda_temp = 1.7;                 // Tcoefs[m] = lambda^m
+    double c0 = 10.0, epsilon1 = 1e-12, epsi2 = 1e-10, A1 = 1e14, target_acceptance = 0.234;   // config_default.cfg:11-16
+    std::vector<long> Nt_learn = {1000, 1500, 100000};       // config_default.cfg:17
+    std::vector<long> periods_learn = {1, 1};                 // config_default.cfg:18
+    long dN_mixing = 1;                                       // config_default.cfg:28
+    std::uint64_t seed = 1;
+};
+
+// Evaluator: int(const double* params [Nchains][stride], const unsigned char* active [Nchains], double* logL [Nchains])
+//            returns 0, or a status; NaN logL is data (MALA.cpp:490,522).
+using Evaluator = std::function<int(const double*, const unsigned char*, double*)>;
+using Prior = std::function<double(const double* params_row)>;      // log prior of one full parameter vector
+
+class Driver {
+public:
+    // state with the reference's names (model_def.h:54-66, MALA.h)
+    std::vector<double> Tcoefs, sigma;                    // [Nchains]
+    std::vector<double> mu, vars;                         // [Nchains][Nvars]
+    std::vector<double> covarmat;                         // [Nchains][Nvars][Nvars]
+    std::vector<double> params;                           // [Nchains][stride]
+    std::vector<double> logLikelihood, logPrior, logPosterior, Pmove;
+    std::vector<int> moved;
+    long n_swap_tried = 0, n_swap_done = 0, n_eval_calls = 0;
+    std::vector<long> n_accept;
+
+    Driver(const DriverConfig& cfg_, int Nparams_, int stride_, const std::vector<double>& params0, const std::vector<int>& relax_index,
+           const std::vector<double>& errors, Evaluator ev, Prior pr)
+        : cfg(cfg_), Nchains(cfg_.Nchains), Nparams(Nparams_), stride(stride_), Nvars((int)relax_index.size()), index_to_relax(relax_index),
+          eval(std::move(ev)), prior(std::move(pr)), rng(cfg_.seed)
+    {
+        Tcoefs.resize(Nchains); sigma.resize(Nchains);
+        for (int m = 0; m < Nchains; m++) Tcoefs[m] = std::pow(cfg.lambda_temp, m);                         // MALA.cpp:98-99
+        mu.assign((size_t)Nchains * Nvars, 0.0); vars = mu;
+        covarmat.assign((size_t)Nchains * Nvars * Nvars, 0.0);
+        params.assign((size_t)Nchains * stride, 0.0);
+        for (int m = 0; m < Nchains; m++) {
+            for (int k = 0; k < Nparams; k++) params[(size_t)m * stride + k] = params0[(size_t)k];
+            for (int v = 0; v < Nvars; v++) {
+                vars[(size_t)m * Nvars + v] = params0[(size_t)index_to_relax[v]];
+                mu[(size_t)m * Nvars + v] = vars[(size_t)m * Nvars + v];                                      // MALA.cpp:286
+                covarmat[((size_t)m * Nvars + v) * Nvars + v] = errors[v] * errors[v];                         // MALA.cpp:270-276
+            }
+            sigma[m] = std::pow(2.38, 2) * std::pow(Tcoefs[m], 0.2) / Nvars;                                   // MALA.cpp:277
+        }
+        logLikelihood.assign(Nchains, 0.0); logPrior = logLikelihood; logPosterior = logLikelihood; Pmove = logLikelihood;
+        moved.assign(Nchains, 0); n_accept.assign(Nchains, 0);
+        prop_params = params; prop_vars = vars; prop_logL = logLikelihood; prop_logPrior = logLikelihood; active.assign(Nchains, 1);
+        // initial model (Model_def constructor, model_def.cpp:142-147)
+        for (int m = 0; m < Nchains; m++) { logPrior[m] = prior(&params[(size_t)m * stride]); active[m] = std::isinf(logPrior[m]) ? 0 : 1; }
+        eval(params.data(), active.data(), logLikelihood.data());
+        n_eval_calls++;
+        for (int m = 0; m < Nchains; m++) logPosterior[m] = active[m] ? logLikelihood[m] + logPrior[m] : -std::numeric_limits<double>::infinity();
+    }
+
+    // one iteration i of MALA::execute (MALA.cpp:646-700)
+    void step(long i)
+    {
+        gamma = cfg.c0 / (1.0 + (double)i);                                                                   // MALA.cpp:646
+        // ---- propose all chains (MALA.cpp:481-486) ----
+        for (int m = 0; m < Nchains; m++) {
+            new_prop_values(m);
+            for (int k = 0; k < Nparams; k++) prop_params[(size_t)m * stride + k] = params[(size_t)m * stride + k];
+            for (int v = 0; v < Nvars; v++) prop_params[(size_t)m * stride + index_to_relax[v]] = prop_vars[(size_t)m * Nvars + v];
+            prop_logPrior[m] = prior(&prop_params[(size_t)m * stride]);
+            active[m] = (prop_logPrior[m] == -std::numeric_limits<double>::infinity()) ? 0 : 1;               // model_def.cpp:469
+        }
+        // ---- ONE batched evaluation (was: generate_model per chain inside the OpenMP loop) ----
+        eval(prop_params.data(), active.data(), prop_logL.data());
+        n_eval_calls++;
+        // ---- accept / reject (MALA.cpp:490-548), learn (MALA.cpp:656-668) ----
+        for (int m = 0; m < Nchains; m++) {
+            const double u = uniform01();
+            double r;
+            const double prop_post = active[m] ? prop_logL[m] + prop_logPrior[m] : -std::numeric_limits<double>::infinity();
+            if (!active[m]) r = 0.0;
+            else if (std::isnan(prop_logL[m])) r = 0.0;
+            else { r = std::exp(prop_post - logPosterior[m]); if (r > 1.0) r = 1.0; if (std::isnan(r)) r = 0.0; }
+            if (u <= r && active[m] && !std::isnan(prop_logL[m])) {
+                for (int k = 0; k < Nparams; k++) params[(size_t)m * stride + k] = prop_params[(size_t)m * stride + k];
+                for (int v = 0; v < Nvars; v++) vars[(size_t)m * Nvars + v] = prop_vars[(size_t)m * Nvars + v];
+                logLikelihood[m] = prop_logL[m]; logPrior[m] = prop_logPrior[m]; logPosterior[m] = prop_post;
+                moved[m] = 1; n_accept[m]++;
+            } else moved[m] = 0;
+            Pmove[m] = r;
+            int learn = 0, which = 0;
+            for (size_t l = 0; l + 1 < cfg.Nt_learn.size() && l < cfg.periods_learn.size(); l++)
+                if (i >= cfg.Nt_learn[l] && i < cfg.Nt_learn[l + 1]) { learn = 1; which = (int)l; }
+            if (learn && (i % cfg.periods_learn[(size_t)which]) == 0) update_proposal(m, Pmove[m]);
+        }
+        // ---- parallel tempering (MALA.cpp:688-700, 397-461) ----
+        if (Nchains > 1 && cfg.dN_mixing > 0 && i % cfg.dN_mixing == 0 && i != 0) parallel_tempering();
+    }
+
+    int n_vars() const { return Nvars; }
+    int n_chains() const { return Nchains; }
+
+private:
+    DriverConfig cfg;
+    int Nchains, Nparams, stride, Nvars;
+    std::vector<int> index_to_relax;
+    Evaluator eval;
+    Prior prior;
+    std::mt19937_64 rng;
+    double gamma = 0.0;
+    std::vector<double> prop_params, prop_vars, prop_logL, prop_logPrior, chol, z;
+    std::vector<unsigned char> active;
+
+    double uniform01() { return std::generate_canonical<double, 53>(rng); }
+    double normal01()
+    {   // Box-Muller on the seeded generator: the same sequence on every platform
+        double u1 = uniform01();
+        if (u1 < 1e-300) u1 = 1e-300;
+        return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925286766559 * uniform01());
+    }
+
+    // MALA.cpp:339-369: ran = vars + chol((covarmat + epsilon2) * sigma) * N(0, I)
+    void new_prop_values(int m)
+    {
+        const int n = Nvars;
+        chol.assign((size_t)n * n, 0.0); z.resize((size_t)n);
+        const double* C = &covarmat[(size_t)m * n * n];
+        for (int a = 0; a < n; a++)
+            for (int b = 0; b <= a; b++) {
+                double s = (C[(size_t)a * n + b] + (a == b ? cfg.epsi2 : 0.0)) * sigma[m];
+                for (int k = 0; k < b; k++) s -= chol[(size_t)a * n + k] * chol[(size_t)b * n + k];
+                chol[(size_t)a * n + b] = (a == b) ? std::sqrt(s > 0 ? s : 0.0) : (chol[(size_t)b * n + b] > 0 ? s / chol[(size_t)b * n + b] : 0.0);
+            }
+        for (int tries = 0; tries < 8; tries++) {
+            bool finite = true;
+            for (int a = 0; a < n; a++) z[(size_t)a] = normal01();
+            for (int a = 0; a < n; a++) {
+                double s = vars[(size_t)m * n + a];
+                for (int k = 0; k <= a; k++) s += chol[(size_t)a * n + k] * z[(size_t)k];
+                prop_vars[(size_t)m * n + a] = s;
+                finite = finite && std::isfinite(s);
+            }
+            if (finite) break;
+        }
+    }
+
+    // MALA.cpp:296-319 with the projections p1/p2/p3 (MALA.cpp:135-177)
+    void update_proposal(int m, double acceptance)
+    {
+        const int n = Nvars;
+        double* mu_m = &mu[(size_t)m * n];
+        double* C = &covarmat[(size_t)m * n * n];
+        const double* v = &vars[(size_t)m * n];
+        double nrm = 0.0;
+        for (int a = 0; a < n; a++) { mu_m[a] = mu_m[a] + gamma * (v[a] - mu_m[a]); nrm += mu_m[a] * mu_m[a]; }
+        nrm = std::sqrt(nrm);
+        if (nrm > cfg.A1) for (int a = 0; a < n; a++) mu_m[a] *= cfg.A1 / nrm;
+        double fro = 0.0;
+        for (int a = 0; a < n; a++)
+            for (int b = 0; b < n; b++) {
+                const double mat = (v[a] - mu_m[a]) * (v[b] - mu_m[b]);
+                C[(size_t)a * n + b] = C[(size_t)a * n + b] + gamma * (mat - C[(size_t)a * n + b]);
+                fro += C[(size_t)a * n + b] * C[(size_t)a * n + b];
+            }
+        fro = std::sqrt(fro);
+        if (fro > cfg.A1) for (size_t k = 0; k < (size_t)n * n; k++) C[k] *= cfg.A1 / fro;
+        double s = sigma[m] + gamma * (acceptance - cfg.target_acceptance);
+        if (s < cfg.epsilon1) s = cfg.epsilon1;
+        if (s > cfg.A1) s = cfg.A1;
+        sigma[m] = s;
+    }
+
+    // MALA.cpp:397-461: swap two adjacent chains; the stored likelihoods are TEMPERED
+    void parallel_tempering()
+    {
+        const double u = uniform01();
+        const int A = (int)(rng() % (std::uint64_t)(Nchains - 1)), B = A + 1;      // random_int_vals(0, Nchains-1), MALA.cpp:179-189
+        const double LA_TB = logLikelihood[A] * Tcoefs[A] / Tcoefs[B];
+        const double LB_TA = logLikelihood[B] * Tcoefs[B] / Tcoefs[A];
+        double r = std::exp(LA_TB + LB_TA - logLikelihood[A] - logLikelihood[B]);
+        if (r > 1.0) r = 1.0;
+        n_swap_tried++;
+        if (u <= r) {
+            for (int k = 0; k < stride; k++) std::swap(params[(size_t)A * stride + k], params[(size_t)B * stride + k]);
+            for (int v = 0; v < Nvars; v++) std::swap(vars[(size_t)A * Nvars + v], vars[(size_t)B * Nvars + v]);
+            const double prA = logPrior[A], prB = logPrior[B];
+            logLikelihood[A] = LB_TA; logPrior[A] = prB; logPosterior[A] = LB_TA + prB;
+            logLikelihood[B] = LA_TB; logPrior[B] = prA; logPosterior[B] = LA_TB + prA;
+            std::swap(moved[A], moved[B]); std::swap(Pmove[A], Pmove[B]);
+            n_swap_done++;
+        }
+    }
+};
+
+}  // namespace tamcmc

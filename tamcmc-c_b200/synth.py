@@ -88,6 +88,26 @@ def aj_params(rng, Nmax=20, lmax=3, f0=650.0, dnu=85.0, asym=0.0, inc=45.0, a1=1
     return params, plength
 
 
+def ajalm_params(rng, Nmax=11, lmax=2, f0=2100.0, dnu=103.0, asym=0.0, inc=60.0, a1=1.2, trunc_c=30.0, do_amp=0, noise=None,
+                 eta_switch=1.0, epsilon=5e-3, theta0=50.0, delta=20.0, decompose_Alm=1, filter_code=0, wmin=1.0, wmax=5.0):
+    """model_MS_Global_ajAlm_HarveyLike (models.cpp:1411): Nsplit=12 =
+    [a1_0,a1_1, a3_0,a3_1, a5_0,a5_1, eps_0,eps_1, theta0(deg), delta(deg), eta_switch, asym], Ncfg=4 =
+    [trunc_c, do_amp, decompose_Alm, filter_code]."""
+    if noise is None:
+        noise = [0.0, 0.0, 1.0, 1.0, 100.0, 2.0, 0.5, 10.0, 2.0, 0.1]
+    fl = ms_global_modes(rng, Nmax, lmax, f0, dnu)
+    n = np.arange(Nmax)
+    H = rng.uniform(10.0, 20.0, Nmax)
+    W = wmin + (wmax - wmin) * (0.5 - 0.5 * np.cos(np.pi * n / max(Nmax - 1, 1))) + rng.uniform(0, 0.05, Nmax)
+    V = np.array([1.5, 0.53, 0.08])[:lmax]
+    split = np.array([a1, 0.01, rng.uniform(-0.02, 0.02), 0.0, rng.uniform(-0.005, 0.005), 0.0, epsilon, 1e-4, theta0, delta, eta_switch, asym])
+    cfg = [trunc_c, float(do_amp), float(decompose_Alm), float(filter_code)]
+    params = np.concatenate([H, V] + fl + [split, W, np.asarray(noise, float), [inc], cfg])
+    plength = np.array([Nmax, lmax] + [Nmax if l <= lmax else 0 for l in range(4)] + [len(split), Nmax, len(noise), 1, len(cfg)],
+                       dtype=np.int32)
+    return params, plength
+
+
 def make_params_aj_model(rng, lmax, Nfreqs, Dnu, epsilon, d0l, asym_on=None):
     """The reference unit test's input recipe for model_MS_Global_aj_HarveyLike
     (test_build_l_mode.cpp:769-874), seeded.  Note the reference's `el/2` is an

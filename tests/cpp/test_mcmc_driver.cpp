@@ -1,0 +1,113 @@
+// test_mcmc_driver.cpp -- posterior consistency of the fixed-seed adaptive-Metropolis + parallel-tempering driver
+// (tamcmc-c_b200/host/mcmc_driver.hpp, a restatement of MALA.cpp:296-553,623-745) when its likelihood comes from
+//   (a) the GPU hot path through the C ABI, and
+//   (b) the CPU oracle (test infrastructure, linked here only as the checker).
+// Same seed, same proposals: the two runs must give the same posterior summaries (BASELINE.json north_star:
+// "posterior summaries from a fixed-seed run must be statistically consistent with the reference's").
+//
+//   test_mcmc_driver <case.bin> <nsteps>     (case format: tests/test_host_cpp.py)
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/tamcmc_gpu.h"
+#include "../../oracle/tamcmc_oracle.h"
+#include "../../tamcmc-c_b200/host/mcmc_driver.hpp"
+
+static std::vector<double> rd(FILE* f, size_t n) { std::vector<double> v(n); if (fread(v.data(), 8, n, f) != n) { std::puts("short read"); std::exit(2); } return v; }
+
+struct Summary { std::vector<double> mean, sd; double acc0; double swap; double secs; };
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) { std::puts("usage: test_mcmc_driver case.bin nsteps"); return 2; }
+    FILE* f = std::fopen(argv[1], "rb");
+    if (!f) { std::perror(argv[1]); return 2; }
+    const long nsteps = std::atol(argv[2]);
+    const std::vector<double> h = rd(f, 16);
+    const int model_id = (int)h[0], Nmodels = (int)h[2], Nparams = (int)h[3];
+    const long N = (long)h[1];
+    const double p = h[4];
+    int pl[11];
+    for (int k = 0; k < 11; k++) pl[k] = (int)h[5 + k];
+    const std::vector<double> x = rd(f, (size_t)N), y = rd(f, (size_t)N);
+    const std::vector<double> T_in = rd(f, (size_t)Nmodels);
+    const std::vector<double> P = rd(f, (size_t)Nmodels * Nparams);
+    std::fclose(f);
+    const std::vector<double> params0(P.begin(), P.begin() + Nparams);
+
+    // relaxed variables: all heights, all l=0 frequencies, all widths (the fitted quantities of an MS global fit)
+    const int Nmax = pl[0], lmax = pl[1], Nf = pl[2] + pl[3] + pl[4] + pl[5];
+    const int o_width = Nmax + lmax + Nf + pl[6];
+    std::vector<int> relax;
+    std::vector<double> err, lo, hi;
+    for (int n = 0; n < Nmax; n++) { relax.push_back(n); err.push_back(0.05 * std::fabs(params0[n])); }
+    for (int n = 0; n < pl[2]; n++) { relax.push_back(Nmax + lmax + n); err.push_back(0.05); }
+    for (int n = 0; n < pl[7]; n++) { relax.push_back(o_width + n); err.push_back(0.05 * std::fabs(params0[o_width + n])); }
+    for (size_t v = 0; v < relax.size(); v++) {
+        const double c = params0[relax[v]], w = (v >= (size_t)Nmax && v < (size_t)(Nmax + pl[2])) ? 2.0 : 0.6 * std::fabs(c);
+        lo.push_back(c - w); hi.push_back(c + w);
+    }
+    tamcmc::Prior prior = [&](const double* row) -> double {     // uniform box: -inf outside (exercises the prior short-circuit, model_def.cpp:469-480)
+        for (size_t v = 0; v < relax.size(); v++) if (row[relax[v]] < lo[v] || row[relax[v]] > hi[v]) return -(double)INFINITY;
+        return 0.0;
+    };
+
+    tamcmc::DriverConfig cfg;
+    cfg.Nchains = Nmodels; cfg.lambda_temp = T_in.size() > 1 ? T_in[1] / T_in[0] : 1.7; cfg.seed = 20261018;
+    cfg.Nt_learn = {100, nsteps / 2, nsteps / 2 + 1}; cfg.periods_learn = {1, 1};
+    std::vector<double> Tcoefs(Nmodels);
+    for (int m = 0; m < Nmodels; m++) Tcoefs[m] = std::pow(cfg.lambda_temp, m);
+
+    tamcmc_gpu_star s = {};
+    s.model_id = model_id;
+    for (int k = 0; k < 11; k++) s.plength[k] = pl[k];
+    s.Nparams = Nparams; s.x = x.data(); s.y = y.data(); s.N = N;
+    tamcmc_gpu_ctx* ctx = nullptr;
+    int rc = tamcmc_gpu_create(0, 1, &s, Nmodels, Tcoefs.data(), p, TAMCMC_LIKELIHOOD_CHI22P, &ctx);
+    if (rc) { std::printf("tamcmc_gpu_create: %s %s\n", tamcmc_gpu_strerror(rc), tamcmc_gpu_last_error()); return 1; }
+    const int stride = tamcmc_gpu_params_stride(ctx);
+
+    tamcmc::Evaluator ev_gpu = [&](const double* pr, const unsigned char* act, double* L) { return tamcmc_gpu_eval(ctx, pr, act, L, nullptr); };
+    tamcmc::Evaluator ev_cpu = [&](const double* pr, const unsigned char* act, double* L) {
+        std::vector<double> tmp(Nmodels);
+        int r = orc_eval_chains(model_id, pr, stride, pl, x.data(), y.data(), N, Nmodels, Tcoefs.data(), p, tmp.data(), 0);
+        for (int m = 0; m < Nmodels; m++) L[m] = act[m] ? tmp[m] : NAN;
+        return r;
+    };
+
+    auto run = [&](tamcmc::Evaluator ev) {
+        tamcmc::Driver d(cfg, Nparams, stride, params0, relax, err, ev, prior);
+        const int nv = d.n_vars();
+        std::vector<double> s1(nv, 0.0), s2(nv, 0.0);
+        long cnt = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (long i = 0; i < nsteps; i++) {
+            d.step(i);
+            if (i >= nsteps / 2) { for (int v = 0; v < nv; v++) { const double q = d.vars[v]; s1[v] += q; s2[v] += q * q; } cnt++; }
+        }
+        Summary S;
+        S.secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (int v = 0; v < nv; v++) { const double m = s1[v] / cnt; S.mean.push_back(m); S.sd.push_back(std::sqrt(std::fmax(s2[v] / cnt - m * m, 0.0))); }
+        S.acc0 = (double)d.n_accept[0] / nsteps;
+        S.swap = d.n_swap_tried ? (double)d.n_swap_done / d.n_swap_tried : 0.0;
+        return S;
+    };
+    const Summary G = run(ev_gpu), C = run(ev_cpu);
+    tamcmc_gpu_destroy(ctx);
+    std::printf("gpu: %.1f steps/s (%.0f likelihood evals/s), acceptance(chain 0) %.3f, swap rate %.3f\n", nsteps / G.secs, nsteps * Nmodels / G.secs, G.acc0, G.swap);
+    std::printf("cpu: %.1f steps/s, acceptance(chain 0) %.3f, swap rate %.3f\n", nsteps / C.secs, C.acc0, C.swap);
+    int bad = 0;
+    double worst = 0;
+    for (size_t v = 0; v < G.mean.size(); v++) {
+        const double sd = std::fmax(std::fmax(G.sd[v], C.sd[v]), 1e-12);
+        const double dz = std::fabs(G.mean[v] - C.mean[v]) / sd;
+        worst = std::fmax(worst, dz);
+        if (!(dz < 0.35) || !(G.sd[v] > 0) || !(std::fabs(G.sd[v] - C.sd[v]) < 0.5 * sd)) { std::printf("var %zu: gpu %.6g +- %.3g  cpu %.6g +- %.3g\n", v, G.mean[v], G.sd[v], C.mean[v], C.sd[v]); bad++; }
+    }
+    if (!(G.acc0 > 0.05 && G.acc0 < 0.8) || std::fabs(G.acc0 - C.acc0) > 0.05) { std::printf("acceptance rates differ or are degenerate\n"); bad++; }
+    std::printf("%zu variables, worst |mean_gpu - mean_cpu| / sd = %.3f, failures %d\n", G.mean.size(), worst, bad);
+    return bad ? 1 : 0;
+}

@@ -25,6 +25,21 @@ def _build():
     return EXE
 
 
+def _build_driver():
+    exe = os.path.join(HERE, "cpp", "test_mcmc_driver")
+    src = os.path.join(HERE, "cpp", "test_mcmc_driver.cpp")
+    hdr = os.path.join(LIBDIR, "host", "mcmc_driver.hpp")
+    import _oracle
+    _oracle.build()
+    odir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return exe
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, src, "-L" + LIBDIR, "-ltamcmc_gpu", "-L" + odir, "-ltamcmc_oracle",
+                           "-L" + cuda_lib, "-lcudart", "-fopenmp", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath," + odir, "-Wl,-rpath," + cuda_lib])
+    return exe
+
+
 def _have_gpu():
     try:
         import torch
@@ -63,4 +78,32 @@ def test_cpp_mirror_matches_oracle(pkg, oracle, tmp_path):
         for a in (hdr, x, y, T, P.ravel(), logPrior, L, M):
             fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
     r = subprocess.run([exe, str(f)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+
+
+def test_cpp_driver_builds(pkg):
+    pkg.lib()
+    _build_driver()
+
+
+@pytest.mark.gpu
+def test_cpp_driver_posterior_consistent_with_cpu_oracle(pkg, oracle, tmp_path):
+    """Fixed-seed adaptive Metropolis + parallel tempering (host/mcmc_driver.hpp) with the GPU likelihood vs the same
+    driver with the CPU oracle likelihood: same posterior summaries."""
+    exe = _build_driver()
+    Nmodels = 4
+    params, pl, x = _cases.ms_case(pkg.synth, 3, seed=6, N=6000, Nmax=3, lmax=2, trunc_c=10.0)
+    rc, M = oracle.call_model(3, params, pl, x)
+    assert rc == 0
+    rng = np.random.default_rng(12)
+    y = pkg.synth.chi2_2dof_spectrum(rng, M)
+    P = np.tile(params, (Nmodels, 1))
+    T = pkg.synth.tcoefs(Nmodels, 1.7)
+    f = tmp_path / "case.bin"
+    hdr = np.concatenate([[3, len(x), Nmodels, len(params), 1.0], pl.astype(float)])
+    with open(f, "wb") as fh:
+        for a in (hdr, x, y, T, P.ravel()):
+            fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    r = subprocess.run([exe, str(f), "3000"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    print(r.stdout)
     assert r.returncode == 0, r.stdout
