@@ -8,7 +8,7 @@
 """
 import numpy as np
 
-TILE = 1024  # bins per CTA tile (csrc/tamcmc_dev.h); shard boundaries are tile-aligned
+TILE = 1536  # bins per tile of the fused kernel (TAMCMC_TILE, csrc/tamcmc_dev.h); shard boundaries are tile-aligned
 
 
 def star_shard(nstars, rank, world):
