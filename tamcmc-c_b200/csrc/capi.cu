@@ -181,30 +181,29 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum)
     a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
     a.raw_sum = raw_sum; a.trace = c->d_trace;
     a.tl = make_tilelist_args(c); a.ready = c->d_ready; a.epoch = c->d_epoch;
+    a.status = c->d_status(); a.nsc = c->SC();
     return a;
 }
 
-// memset + expand + tile lists + fused kernel + finalize, enqueued on `st`
+// expand + fused kernel (tile lists, model, Whittle sums, per-chain finalisation, queue re-arm), enqueued on `st`
 int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
                      int raw_sum, cudaStream_t st, bool prof)
 {
     ExpandArgs ea = make_expand_args(c, d_params, d_active, d_logL);
     WhittleArgs wa = make_whittle_args(c, d_logL, raw_sum);
-    CK(cudaMemsetAsync(c->d_qctl, 0, sizeof(QueueCtl), st));
     if (prof) CK(cudaEventRecord(c->ev[0], st));
     CK(tamcmc_launch_expand(ea, c->SC(), st));
     if (prof) CK(cudaEventRecord(c->ev[1], st));
     CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, st));
-    CK(tamcmc_launch_finalize(wa, c->d_status(), c->SC(), c->d_epoch, st));
     if (prof) CK(cudaEventRecord(c->ev[2], st));
     return TAMCMC_OK;
 }
 
-// One evaluation on `st`.  Outside profiling the five device operations are replayed as one CUDA graph.
+// One evaluation on `st`.  Outside profiling the two kernels are replayed as one CUDA graph.
 int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
                 int raw_sum, cudaStream_t st)
 {
-    c->launches += 3;
+    c->launches += 2;
     const bool prof = c->profiling && st == c->stream;
     if (prof || !c->use_graphs) return enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof);
     for (int i = 0; i < c->ngraphs; i++) {
@@ -243,6 +242,14 @@ int collect_profile(tamcmc_gpu_ctx* c)
     return TAMCMC_OK;
 }
 
+// after an expand launch that is NOT followed by the fused kernel (debug entries): re-arm the queue like its last CTA does
+int reset_queue(tamcmc_gpu_ctx* c)
+{
+    CK(cudaMemsetAsync(c->d_qctl, 0, sizeof(QueueCtl), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return TAMCMC_OK;
+}
+
 int status_to_rc(const int* st, int n)
 {
     int rc = TAMCMC_OK;
@@ -267,7 +274,6 @@ int expand_single(tamcmc_gpu_ctx* c, int star, const double* row)
     CK(cudaMemcpyAsync(c->d_params, c->h_params, sizeof(double) * (size_t)SC * c->params_stride, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_active, c->h_active, (size_t)SC, cudaMemcpyHostToDevice, c->stream));
     ExpandArgs ea = make_expand_args(c, c->d_params, c->d_active, c->d_logL());
-    CK(cudaMemsetAsync(c->d_qctl, 0, sizeof(QueueCtl), c->stream));
     CK(tamcmc_launch_expand(ea, SC, c->stream));
     c->launches += 1;
     return TAMCMC_OK;
@@ -500,6 +506,7 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char
     std::memcpy(logL_out, c->h_out, sizeof(double) * (size_t)SC);
     if (c->h_qctl->overflow) {
         g_last_error = "component-list pool overflow: raise TAMCMC_GPU_POOL_MB";
+        reset_queue(c);                     // `overflow` is sticky on the device until the host has seen it
         return TAMCMC_ERR_POOL;
     }
     const int* st = reinterpret_cast<const int*>(reinterpret_cast<const double*>(c->h_out) + SC);
@@ -524,8 +531,7 @@ int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, doub
     const StarDesc& sd = c->h_stars[star];
     WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0);
     CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->stream));
-    CK(tamcmc_launch_finalize(wa, c->d_status(), c->SC(), c->d_epoch, c->stream));   // also bumps the ready-flag epoch
-    c->launches += 3;
+    c->launches += 1;
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     const int SC = c->SC();
@@ -550,6 +556,7 @@ int tamcmc_gpu_windows(tamcmc_gpu_ctx* c, int star, const double* params_row, in
     CK(cudaMemcpy(mr.data(), c->d_modes + sc * c->modes_stride, sizeof(ModeRec) * mr.size(), cudaMemcpyDeviceToHost));
     int st = 0;
     CK(cudaMemcpy(&st, c->d_status() + sc, sizeof(int), cudaMemcpyDeviceToHost));
+    { int rc = reset_queue(c); if (rc) return rc; }
     int nlive = sd.nmodes_cap;
     if (sd.model_id == TAMCMC_MODEL_ID_MODE_TABLE && params_row[0] >= 0 && params_row[0] <= sd.nmodes_cap) nlive = (int)params_row[0];
     *nmodes = nlive;
@@ -572,6 +579,7 @@ int tamcmc_gpu_components(tamcmc_gpu_ctx* c, int star, const double* params_row,
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(mr.data(), c->d_modes + sc * c->modes_stride, sizeof(ModeRec) * mr.size(), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(cr.data(), c->d_comps + sc * c->modes_stride * TAMCMC_MAX_COMP_PER_MODE, sizeof(CompRec) * cr.size(), cudaMemcpyDeviceToHost));
+    { int rc = reset_queue(c); if (rc) return rc; }
     int n = 0;
     for (int i = 0; i < sd.nmodes_cap; i++)
         for (int k = 0; k < mr[i].ncomp; k++) {

@@ -100,7 +100,7 @@ __device__ __forceinline__ double ipow(double x, int n)
 // One entry of amplitude_ratio(l, inc) (function_rot.cpp:15-74): V(m=i) = d^l_{i,0}(inc)^2.  Following the four
 // fill loops of function_rot, column l of the matrix holds dmm(l,|i|,0,+-beta) up to a sign, which the square
 // removes; dmm's sum over s (function_rot.cpp:79-83) runs over the host-tabulated integer factors.
-__device__ double d_amplitude_ratio_entry(int l, int i, double beta_deg)
+__device__ __noinline__ double d_amplitude_ratio_entry(int l, int i, double beta_deg)
 {
     const double PI = 3.141592653589793238462643;
     const double angle = PI * beta_deg / 180.;
@@ -119,7 +119,7 @@ __device__ double d_amplitude_ratio_entry(int l, int i, double beta_deg)
 }
 
 // interpol.cpp:13-43
-__device__ double d_lin_interpol(const double* x, const double* y, int Nx, double x_int)
+__device__ __noinline__ double d_lin_interpol(const double* x, const double* y, int Nx, double x_int)
 {
     int i = 0;
     double a = 0, b = 0;
@@ -140,7 +140,7 @@ __device__ double d_lin_interpol(const double* x, const double* y, int Nx, doubl
 }
 
 // linfit.cpp:17-35 with x = 0..n-1 (models.cpp:6065-6071), then models.cpp:6073-6084
-__device__ double d_eta0_fct(const double* fl0, int n_)
+__device__ __noinline__ double d_eta0_fct(const double* fl0, int n_)
 {
     double sx = 0, sy = 0, sty = 0, stt = 0;
     const double n = (double)n_;
@@ -160,7 +160,7 @@ __device__ double d_eta0_fct(const double* fl0, int n_)
 }
 
 // build_lorentzian.cpp:595-649.  Non-exclusive ifs, last one wins.  Returns 0 on success.
-__device__ int d_set_imin_imax(double x0, double xlast, int N, int l, double fc_l, double gamma_l,
+__device__ __noinline__ int d_set_imin_imax(double x0, double xlast, int N, int l, double fc_l, double gamma_l,
                                double f_s, double c, double step, int* i0, int* i1)
 {
     double p0 = nan(""), p1 = nan("");
@@ -224,13 +224,12 @@ struct ModeTmp {
     int n;
 };
 
-__device__ void emit_noise(NoiseRec* out, const double* noise_params, int Nnoise, int Nharvey, int* status)
+__device__ __noinline__ void emit_noise(NoiseRec* out, const double* noise_params, int Nnoise, int Nharvey, int* status)
 {
     // harvey_like(noise_params.array().abs(), ...) -- noise_models.cpp:15-39; models.cpp:2093-2100
-    NoiseRec nr;
+    NoiseRec& nr = *out;                     // filled in place (shared or global memory): no ~1 KB local copy
     int nh = 0;
     if (Nharvey > TAMCMC_MAX_HARVEY) { atomicOr(status, TAMCMC_ST_BADCFG); Nharvey = TAMCMC_MAX_HARVEY; }
-    for (int k = 0; k < TAMCMC_MAX_HARVEY; k++) { nr.H[k] = 0; nr.lnsc[k] = 0; nr.pw[k] = 0; nr.cpi[k] = 0; nr.spi[k] = 0; }
     for (int k = 0; k < Nharvey; k++) {
         const double H = fabs(noise_params[3 * k]);
         const double tau = fabs(noise_params[3 * k + 1]);
@@ -240,19 +239,19 @@ __device__ void emit_noise(NoiseRec* out, const double* noise_params, int Nnoise
             nr.H[nh] = H;
             nr.lnsc[nh] = log((1e-3) * tau);
             nr.pw[nh] = pw;
-            { const double ang = 3.14159265358979323846 / fmax(pw, 1.0); sincos(ang, &nr.spi[nh], &nr.cpi[nh]); }
+            { double sn, cs; const double ang = 3.14159265358979323846 / fmax(pw, 1.0); sincos(ang, &sn, &cs); nr.spi[nh] = sn; nr.cpi[nh] = cs; }
             { double b = 1.0; nr.binom[nh][0] = 1.0; for (int q = 1; q < TAMCMC_BG_TERMS; q++) { b = b * (pw - (double)(q - 1)) / (double)q; nr.binom[nh][q] = b; } }
             nh++;
         }
     }
+    for (int k = nh; k < TAMCMC_MAX_HARVEY; k++) { nr.H[k] = 0; nr.lnsc[k] = 0; nr.pw[k] = 0; nr.cpi[k] = 0; nr.spi[k] = 0; }
     nr.nh = nh; nr.pad = 0;
     nr.N0 = (Nnoise > 0) ? fabs(noise_params[Nnoise - 1]) : 0.0;
     if (!isfinite(nr.N0)) atomicOr(status, TAMCMC_ST_NONFINITE);
-    *out = nr;
 }
 
 // |params[n]/(pi*W)| (models.cpp:2032): long double in the reference, double here (<= 1 ulp apart)
-__device__ __forceinline__ double amp_to_height(double a, double W)
+__device__ __noinline__ double amp_to_height(double a, double W)
 {
     const double PI = 3.141592653589793238462643383279502884;
     return fabs(a / (PI * W));
@@ -268,7 +267,7 @@ __device__ __forceinline__ double nu_a1etaa3(int l, int m, double fc, double f_s
 }
 
 // nu_nlm of build_l_mode_aj (build_lorentzian.cpp:222-226)
-__device__ double nu_aj(int l, int m, double fc, const double* a /*a1..a6*/, double eta0)
+__device__ __noinline__ double nu_aj(int l, int m, double fc, const double* a /*a1..a6*/, double eta0)
 {
     if (l == 0) return fc;
     dd acc = dd_from(fc);
@@ -282,7 +281,7 @@ __device__ double nu_aj(int l, int m, double fc, const double* a /*a1..a6*/, dou
 // Taylor series in u = x - xc of one Harvey-like term H / (1 + (tau' x)^p) (noise_models.cpp:30-31),
 // valid on the tile when |u|/xc is small against the distance to the nearest singularity
 // (x = 0 and (tau' x)^p = -1).  Returns false when the tile must use the per-bin exp() path.
-__device__ bool harvey_series(double H, double lnsc, double pw, double cpi, double spi, const double* binom,
+__device__ __noinline__ bool harvey_series(double H, double lnsc, double pw, double cpi, double spi, const double* binom,
                               double xc, double lnxc, double umax, double* out /*NB, accumulated*/)
 {
     constexpr int NB = TAMCMC_BG_TERMS;
@@ -492,7 +491,8 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         // ---- pass A: one thread per mode: degree, frequency, width, height rule, splittings ----
         {
             const int j = base + tid;
-            ModeTmp t;
+            static_assert(EXP_BATCH == EXP_THREADS, "one scratch slot per thread");
+            ModeTmp& t = mt[tid];          // filled in place in shared memory (no per-thread local copy)
             t.have = 0;
             if (mode_table && tid < EXP_BATCH && j < nmodes_live) {
                 // one optimum_lorentzian_calc_aj call of the host model function (e.g. models.cpp:4937, 4952, 4977, 5001)
@@ -558,7 +558,6 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
                     }
                 }
             }
-            if (tid < EXP_BATCH) mt[tid] = t;
         }
         __syncthreads();
         ETRACE(3);

@@ -17,7 +17,7 @@ struct ExpandArgs {
     TileRec* tilerec;                // [nstars*Nchains][tiles_stride]
     const double* x;                 // concatenated spectra (tile centres / extents)
     const double* lnx;
-    QueueCtl* qctl;                  // zeroed before every expand launch
+    QueueCtl* qctl;                  // all-zero at launch (reset by the previous fused-kernel launch)
     unsigned int qcap;
     int Nchains;
     int params_stride;
@@ -67,7 +67,9 @@ struct WhittleArgs {
     unsigned long long* trace;       // profiling aid (builds with -DTAMCMC_TRACE): [grid][64] globaltimer stamps
     TileListArgs tl;                 // builder warps: inputs of the per-tile list construction
     unsigned int* ready;             // [qcap * NBUCKETS] per queue position: == epoch once the item's lists are built
-    const unsigned int* epoch;       // device launch counter (never 0); bumped by the finalize kernel
+    unsigned int* epoch;             // device launch counter (never 0); bumped by the last CTA of the fused kernel
+    const int* status;               // [nstars*Nchains] per-chain status written by the expand kernel
+    int nsc;                         // nstars*Nchains
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)
 };
 
@@ -77,7 +79,6 @@ cudaError_t tamcmc_expand_configure();
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
 cudaError_t tamcmc_whittle_configure(int* grid_ctas);   // one-time function attributes; returns the persistent grid size
 cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st);
-cudaError_t tamcmc_launch_finalize(const WhittleArgs& a, const int* status, int nsc, unsigned int* epoch, cudaStream_t st);
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st);
 // DFMA throughput microbenchmark: returns achieved FP64 TFLOP/s (2 flops per DFMA)
 cudaError_t tamcmc_fp64_peak(double* tflops, float* ms, int iters);

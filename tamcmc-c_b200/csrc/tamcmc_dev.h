@@ -116,4 +116,6 @@ struct __align__(16) TileRec {
 
 // work queue header: count[k] items in cost bucket k (k = 0 heaviest), head = pop cursor
 #define TAMCMC_NBUCKETS 4            // work-queue cost classes, heaviest first
-struct QueueCtl { unsigned int count[TAMCMC_NBUCKETS]; unsigned int head; unsigned int overflow; unsigned long long pool_cursor; unsigned long long pad; };
+// Zero between evaluations: the last CTA of the fused kernel to finish resets every field but `overflow` (sticky until
+// the host has seen it).
+struct QueueCtl { unsigned int count[TAMCMC_NBUCKETS]; unsigned int head; unsigned int overflow; unsigned long long pool_cursor; unsigned int ctas_done; unsigned int pad; };

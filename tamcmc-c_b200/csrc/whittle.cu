@@ -172,8 +172,20 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
     for (int k = 0; k < TAMCMC_NBUCKETS; k++) cum[k + 1] = cum[k] + A.qctl->count[k];
     const unsigned ntot = cum[TAMCMC_NBUCKETS];
     const unsigned epoch = *A.epoch;
+    // Look-ahead: normally the producer runs up to NBUF-1 segments ahead of the consumers and pops the next queue index
+    // while it still processes the current one.  In the END GAME (the last ~2 items per CTA) it holds at most one tile
+    // in flight beyond the one being consumed and pops late, so that the few remaining (light) items go to the CTAs
+    // that are actually free: that keeps the tail of the persistent grid short.
+    const unsigned endgame_from = (ntot > 2u * gridDim.x) ? ntot - 2u * gridDim.x : 0u;
     unsigned idx = pop_item(A, lane);
+    bool have = true;
+    int h1_b = 0, h2_b = 0;               // buffers of the last and second-to-last fills and their use counts
+    unsigned h1_use = 0, h2_use = 0;
     for (;;) {
+        if (!have) {
+            if (h2_use) mbar_wait(&sm.empty[h2_b], (h2_use - 1) & 1);      // the segment filled two fills ago is released
+            idx = pop_item(A, lane);
+        }
         if (idx >= ntot) {
             if (use[b]) mbar_wait(&sm.empty[b], (use[b] - 1) & 1);
             if (lane == 0) { sm.seg[b].flags = SEG_DONE; mbar_arrive(&sm.full[b]); }
@@ -189,7 +201,8 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
             unsigned r;
             do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(A.ready + idx) : "memory"); if (r != epoch) __nanosleep(64); } while (r != epoch);
         }
-        idx = pop_item(A, lane);                      // next item: the atomic's latency hides behind this tile
+        have = idx < endgame_from;
+        if (have) idx = pop_item(A, lane);            // next item: the atomic's latency hides behind this tile
         const int sc = (int)(item / (unsigned)A.tiles_stride);
         const int tile = (int)(item - (unsigned)sc * (unsigned)A.tiles_stride);
         const StarDesc* sd = A.stars + sc / A.Nchains;
@@ -236,7 +249,9 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
             if (last && lane < NB) sg->bg[lane] = bgk;
             __syncwarp();
             mbar_arrive(&sm.full[b]);
-            use[b]++; b = (b + 1 == NBUF) ? 0 : b + 1;
+            use[b]++;
+            h2_b = h1_b; h2_use = h1_use; h1_b = b; h1_use = use[b];
+            b = (b + 1 == NBUF) ? 0 : b + 1;
         }
     }
 }
@@ -487,6 +502,30 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
     }
 }
 
+// One warp per (star, chain): sum of the per-tile partials in tile order (fixed shape: bitwise reproducible).  Each tile
+// contributes sum(y/M) - ln(prod 1/M) = S - ln(m) - E ln 2;  likelihood_chi22p: f = -p*S_total with p truncated to long
+// (model_def.cpp:399), divided by Tcoefs[m] (model_def.cpp:401).
+__device__ void finalize_chains(const WhittleArgs& A, int warp, int lane, int nwarps)
+{
+    const double LN2 = 0.693147180559945309417232121458;
+    for (int sc = warp; sc < A.nsc; sc += nwarps) {
+        if (A.status[sc] != 0) continue;
+        const int ntiles = A.stars[sc / A.Nchains].ntiles;
+        const double* part = A.partial + 3 * (size_t)sc * A.tiles_stride;
+        double acc = 0.0;
+        for (int t = lane; t < ntiles; t += 32) acc += part[3 * t] - (log(part[3 * t + 1]) + part[3 * t + 2] * LN2);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+        if (lane == 0) {
+            if (A.raw_sum) A.out[sc] = acc;
+            else {
+                const double pl = (double)(long long)A.p;
+                A.out[sc] = (-pl * acc) / A.Tcoefs[sc % A.Nchains];
+            }
+        }
+    }
+}
+
 template <bool WRITE_MODEL>
 __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(WhittleArgs A)
 {
@@ -501,30 +540,22 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
     if (tid >= NC + 32) builder_loop(A, (tid - NC - 32) >> 5, tid & 31);
     else if (tid >= NC) producer_loop(A, sm, tid - NC);
     else consumer_loop<WRITE_MODEL>(A, sm, tid);
-}
 
-// One warp per (star, chain): sum of the per-tile partials in tile order.  Each tile contributes
-// sum(y/M) - ln(prod 1/M) = S - ln(m) - E ln 2;  likelihood_chi22p: f = -p*S_total with p truncated to long
-// (model_def.cpp:399), divided by Tcoefs[m] (model_def.cpp:401).
-__global__ void __launch_bounds__(128) tamcmc_finalize_kernel(WhittleArgs A, const int* __restrict__ status, int nsc, unsigned int* epoch)
-{
-    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned e = *epoch + 1u; *epoch = e ? e : 1u; }   // next launch's ready-flag value
-    const int sc = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (sc >= nsc || status[sc] != 0) return;
-    const int ntiles = A.stars[sc / A.Nchains].ntiles;
-    const double* part = A.partial + 3 * (size_t)sc * A.tiles_stride;
-    const double LN2 = 0.693147180559945309417232121458;
-    double acc = 0.0;
-    for (int t = lane; t < ntiles; t += 32) acc += part[3 * t] - (log(part[3 * t + 1]) + part[3 * t + 2] * LN2);
+    // ---- the LAST CTA to finish turns the per-tile partials into the per-chain results and re-arms the queue ----
+    __shared__ unsigned int s_last;
+    __syncthreads();
+    if (tid == 0) { __threadfence(); s_last = (atomicAdd(&A.qctl->ctas_done, 1u) == gridDim.x - 1u) ? 1u : 0u; }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    finalize_chains(A, tid >> 5, tid & 31, NT / 32);
+    if (tid == 0) {
+        QueueCtl* q = A.qctl;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-    if (lane == 0) {
-        if (A.raw_sum) A.out[sc] = acc;
-        else {
-            const double pl = (double)(long long)A.p;
-            A.out[sc] = (-pl * acc) / A.Tcoefs[sc % A.Nchains];
-        }
+        for (int k = 0; k < TAMCMC_NBUCKETS; k++) q->count[k] = 0u;
+        q->head = 0u; q->pool_cursor = 0ull; q->ctas_done = 0u;
+        const unsigned e = *A.epoch + 1u;
+        *A.epoch = e ? e : 1u;                          // next launch's ready-flag value (never 0)
     }
 }
 
@@ -575,12 +606,6 @@ cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool writ
     const size_t smem = sizeof(Smem);
     if (write_model) tamcmc_whittle_kernel<true><<<grid_ctas, NT, smem, st>>>(a);
     else tamcmc_whittle_kernel<false><<<grid_ctas, NT, smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t tamcmc_launch_finalize(const WhittleArgs& a, const int* status, int nsc, unsigned int* epoch, cudaStream_t st)
-{
-    tamcmc_finalize_kernel<<<(nsc + 3) / 4, 128, 0, st>>>(a, status, nsc, epoch);
     return cudaGetLastError();
 }
 
