@@ -131,6 +131,8 @@ struct tamcmc_gpu_ctx {
     GraphEntry graphs[4] = {};
     int ngraphs = 0;
     bool use_graphs = true;
+    bool use_pdl = false;            // programmatic dependent launch expand -> fused kernel: measured no gain inside a CUDA graph
+                                     // (profiles/r1/NOTES.md); TAMCMC_GPU_PDL=1 enables it
     // measurement
     bool profiling = false;
     long nlaunch_prof = 0;
@@ -194,7 +196,7 @@ int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned c
     if (prof) CK(cudaEventRecord(c->ev[0], st));
     CK(tamcmc_launch_expand(ea, c->SC(), st));
     if (prof) CK(cudaEventRecord(c->ev[1], st));
-    CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, st));
+    CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, st, c->use_pdl && !prof));
     if (prof) CK(cudaEventRecord(c->ev[2], st));
     return TAMCMC_OK;
 }
@@ -321,6 +323,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     tamcmc_gpu_ctx* c = new tamcmc_gpu_ctx();
     c->device = device; c->nstars = nstars; c->Nchains = Nchains; c->p = p;
     if (const char* e = std::getenv("TAMCMC_GPU_NO_GRAPH")) c->use_graphs = !(e[0] == '1');
+    if (const char* e = std::getenv("TAMCMC_GPU_PDL")) c->use_pdl = (e[0] == '1');
     c->h_stars.resize(nstars);
     long long off = 0; int tiles = 0; int maxN = 0;
     for (int s = 0; s < nstars; s++) {
@@ -530,7 +533,7 @@ int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, doub
     { int rc = expand_single(c, star, params_row); if (rc) return rc; }
     const StarDesc& sd = c->h_stars[star];
     WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0);
-    CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->stream));
+    CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->stream, false));
     c->launches += 1;
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -207,7 +207,7 @@ struct Common {
     int status;
 };
 
-constexpr int EXP_THREADS = 128;
+constexpr int EXP_THREADS = 512;                // 16 warps: the (mode, m) slot pass and the queue pass are latency-bound
 constexpr int EXP_BATCH = 128;                 // modes expanded per pass
 constexpr int TILE_BASE_COST = 16;             // per-tile fixed work in (component, bin)-pair units / 1024
 
@@ -224,30 +224,38 @@ struct ModeTmp {
     int n;
 };
 
-__device__ __noinline__ void emit_noise(NoiseRec* out, const double* noise_params, int Nnoise, int Nharvey, int* status)
+// Called by ONE FULL WARP: lane k handles Harvey term k; live terms (tau != 0, noise_models.cpp:29) are compacted in
+// term order with a ballot.  harvey_like(noise_params.array().abs(), ...) -- noise_models.cpp:15-39; models.cpp:2093-2100
+__device__ __noinline__ void emit_noise(NoiseRec* out, const double* noise_params, int Nnoise, int Nharvey, int* status, int lane)
 {
-    // harvey_like(noise_params.array().abs(), ...) -- noise_models.cpp:15-39; models.cpp:2093-2100
-    NoiseRec& nr = *out;                     // filled in place (shared or global memory): no ~1 KB local copy
-    int nh = 0;
-    if (Nharvey > TAMCMC_MAX_HARVEY) { atomicOr(status, TAMCMC_ST_BADCFG); Nharvey = TAMCMC_MAX_HARVEY; }
-    for (int k = 0; k < Nharvey; k++) {
-        const double H = fabs(noise_params[3 * k]);
-        const double tau = fabs(noise_params[3 * k + 1]);
-        const double pw = fabs(noise_params[3 * k + 2]);
+    NoiseRec& nr = *out;                     // filled in place (shared or global memory)
+    if (Nharvey > TAMCMC_MAX_HARVEY) { if (lane == 0) atomicOr(status, TAMCMC_ST_BADCFG); Nharvey = TAMCMC_MAX_HARVEY; }
+    double H = 0, tau = 0, pw = 0;
+    if (lane < Nharvey) {
+        H = fabs(noise_params[3 * lane]); tau = fabs(noise_params[3 * lane + 1]); pw = fabs(noise_params[3 * lane + 2]);
         if (!isfinite(H) || !isfinite(tau) || !isfinite(pw)) atomicOr(status, TAMCMC_ST_NONFINITE);
-        if (tau != 0.0) {                       // noise_models.cpp:29
-            nr.H[nh] = H;
-            nr.lnsc[nh] = log((1e-3) * tau);
-            nr.pw[nh] = pw;
-            { double sn, cs; const double ang = 3.14159265358979323846 / fmax(pw, 1.0); sincos(ang, &sn, &cs); nr.spi[nh] = sn; nr.cpi[nh] = cs; }
-            { double b = 1.0; nr.binom[nh][0] = 1.0; for (int q = 1; q < TAMCMC_BG_TERMS; q++) { b = b * (pw - (double)(q - 1)) / (double)q; nr.binom[nh][q] = b; } }
-            nh++;
-        }
     }
-    for (int k = nh; k < TAMCMC_MAX_HARVEY; k++) { nr.H[k] = 0; nr.lnsc[k] = 0; nr.pw[k] = 0; nr.cpi[k] = 0; nr.spi[k] = 0; }
-    nr.nh = nh; nr.pad = 0;
-    nr.N0 = (Nnoise > 0) ? fabs(noise_params[Nnoise - 1]) : 0.0;
-    if (!isfinite(nr.N0)) atomicOr(status, TAMCMC_ST_NONFINITE);
+    const bool live = (lane < Nharvey) && (tau != 0.0);
+    const unsigned mk = __ballot_sync(0xffffffffu, live);
+    const int nh = __popc(mk);
+    if (live) {
+        const int slot = __popc(mk & ((1u << lane) - 1u));
+        nr.H[slot] = H;
+        nr.lnsc[slot] = log((1e-3) * tau);
+        nr.pw[slot] = pw;
+        { double sn, cs; const double ang = 3.14159265358979323846 / fmax(pw, 1.0); sincos(ang, &sn, &cs); nr.spi[slot] = sn; nr.cpi[slot] = cs; }
+        // generalised binomial coefficients C(p, q) = C(p, q-1) (p - q + 1) / q
+        double b = 1.0;
+        nr.binom[slot][0] = 1.0;
+#pragma unroll
+        for (int q = 1; q < TAMCMC_BG_TERMS; q++) { b = b * (pw - (double)(q - 1)) * (1.0 / (double)q); nr.binom[slot][q] = b; }
+    }
+    if (lane >= nh && lane < TAMCMC_MAX_HARVEY) { nr.H[lane] = 0; nr.lnsc[lane] = 0; nr.pw[lane] = 0; nr.cpi[lane] = 0; nr.spi[lane] = 0; }
+    if (lane == 0) {
+        nr.nh = nh; nr.pad = 0;
+        nr.N0 = (Nnoise > 0) ? fabs(noise_params[Nnoise - 1]) : 0.0;
+        if (!isfinite(nr.N0)) atomicOr(status, TAMCMC_ST_NONFINITE);
+    }
 }
 
 // |params[n]/(pi*W)| (models.cpp:2032): long double in the reference, double here (<= 1 ulp apart)
@@ -319,9 +327,12 @@ __device__ __noinline__ bool harvey_series(double H, double lnsc, double pw, dou
 // expand kernel: grid = nstars*Nchains CTAs, 128 threads.
 // dynamic shared memory: params row [params_stride] doubles, then per-tile cost ints [max_tiles + 1]
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A)
+__global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArgs A)
 {
     extern __shared__ double sp[];             // this chain's parameter row, staged once
+    // let the dependent fused kernel (launched with programmatic stream serialization) be scheduled right away: its
+    // CTAs run their prologue and then block in griddepcontrol.wait until THIS grid has completed and flushed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int sc = blockIdx.x;                 // star*Nchains + chain
     const int star = sc / A.Nchains;
     const StarDesc sd = A.stars[star];
@@ -339,10 +350,10 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         if (A.active && !A.active[sc]) return;
         const int* pl = sd.plength;
         const int o_noise = (sd.model_id == TAMCMC_MODEL_ID_MODE_TABLE) ? TAMCMC_MT_HDR : pl[0] + pl[1] + pl[2] + pl[3] + pl[4] + pl[5] + pl[6] + pl[7];
-        if (threadIdx.x == 0) {
-            s_dummy = 0;
-            emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (sd.model_id == 11) ? 0 : (pl[8] - 1) / 3, &s_dummy);
-        }
+        if (threadIdx.x == 0) s_dummy = 0;
+        __syncthreads();
+        if (threadIdx.x < 32)
+            emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (sd.model_id == 11) ? 0 : (pl[8] - 1) / 3, &s_dummy, threadIdx.x);
         __syncthreads();
         const int tile = (blockIdx.y - 1) * blockDim.x + threadIdx.x;
         if (tile >= sd.ntiles) return;
@@ -372,6 +383,8 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
     __shared__ double slot_nu[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
     __shared__ double slot_A[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
     __shared__ int s_red[EXP_THREADS / 32];
+    __shared__ unsigned int s_bcnt[TAMCMC_NBUCKETS], s_bbase[TAMCMC_NBUCKETS];
+    static_assert(TAMCMC_NBUCKETS == 4, "tile class is packed into 2 bits");
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int* pl = sd.plength;
@@ -475,9 +488,9 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
                 break;
             }
             if (cm.status) atomicOr(&s_status, cm.status);
-        } else if (tid == 64) {
-            // warp 2, lane 0: Harvey-like background parameters
-            emit_noise(noise, params + o_noise, Nnoise, (model == 11) ? 0 : (Nnoise - 1) / 3, &s_status);
+        } else if (tid >= 64 && tid < 96) {
+            // warp 2: Harvey-like background parameters, one lane per term
+            emit_noise(noise, params + o_noise, Nnoise, (model == 11) ? 0 : (Nnoise - 1) / 3, &s_status, tid - 64);
         }
     }
     __syncthreads();
@@ -491,9 +504,9 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         // ---- pass A: one thread per mode: degree, frequency, width, height rule, splittings ----
         {
             const int j = base + tid;
-            static_assert(EXP_BATCH == EXP_THREADS, "one scratch slot per thread");
-            ModeTmp& t = mt[tid];          // filled in place in shared memory (no per-thread local copy)
-            t.have = 0;
+            static_assert(EXP_BATCH <= EXP_THREADS, "one scratch slot per mode of a batch");
+            ModeTmp& t = mt[tid < EXP_BATCH ? tid : 0];      // filled in place in shared memory (threads >= EXP_BATCH idle here)
+            if (tid < EXP_BATCH) t.have = 0;
             if (mode_table && tid < EXP_BATCH && j < nmodes_live) {
                 // one optimum_lorentzian_calc_aj call of the host model function (e.g. models.cpp:4937, 4952, 4977, 5001)
                 const double* r = params + o_modes + TAMCMC_MT_STRIDE * j;
@@ -676,22 +689,28 @@ __global__ void __launch_bounds__(EXP_THREADS) tamcmc_expand_kernel(ExpandArgs A
         __syncthreads();
         mx = 0;
         for (int w = 0; w < EXP_THREADS / 32; w++) mx = max(mx, s_red[w]);
+        // cost class of every tile (quarters of the chain's heaviest tile, heaviest first) and its rank inside the class,
+        // counted in shared memory; then ONE global atomic per class reserves the chain's slots in the queue
+        if (tid < TAMCMC_NBUCKETS) s_bcnt[tid] = 0u;
+        __syncthreads();
         const int rounds = (ntiles + blockDim.x - 1) / blockDim.x;
         for (int r = 0; r < rounds; r++) {
             const int t = r * blockDim.x + tid;
-            const bool valid = t < ntiles;
-            // cost class: quarters of the chain's heaviest tile, heaviest first
-            int cls = TAMCMC_NBUCKETS - 1;
-            if (valid) { const int q = (4 * (tcost[t] - TILE_BASE_COST)) / max(mx - TILE_BASE_COST, 1); cls = min(max(TAMCMC_NBUCKETS - 1 - q, 0), TAMCMC_NBUCKETS - 1); }
-            const unsigned below = (1u << lane) - 1u;
-            const unsigned item = (unsigned)sc * (unsigned)A.tiles_stride + (unsigned)t;
-#pragma unroll
-            for (int k = 0; k < TAMCMC_NBUCKETS; k++) {
-                const unsigned mk = __ballot_sync(0xffffffffu, valid && cls == k);
-                unsigned bk = 0;
-                if (lane == 0 && mk) bk = atomicAdd(&A.qctl->count[k], (unsigned)__popc(mk));
-                bk = __shfl_sync(0xffffffffu, bk, 0);
-                if (valid && cls == k) A.queue[(size_t)k * A.qcap + bk + __popc(mk & below)] = item;
+            if (t < ntiles) {
+                const int q = (4 * (tcost[t] - TILE_BASE_COST)) / max(mx - TILE_BASE_COST, 1);
+                const int cls = min(max(TAMCMC_NBUCKETS - 1 - q, 0), TAMCMC_NBUCKETS - 1);
+                const unsigned rank = atomicAdd(&s_bcnt[cls], 1u);
+                tcost[t] = (int)((rank << 2) | (unsigned)cls);          // ntiles <= 16384: rank fits
+            }
+        }
+        __syncthreads();
+        if (tid < TAMCMC_NBUCKETS) s_bbase[tid] = s_bcnt[tid] ? atomicAdd(&A.qctl->count[tid], s_bcnt[tid]) : 0u;
+        __syncthreads();
+        for (int r = 0; r < rounds; r++) {
+            const int t = r * blockDim.x + tid;
+            if (t < ntiles) {
+                const unsigned v = (unsigned)tcost[t], cls = v & 3u, rank = v >> 2;
+                A.queue[(size_t)cls * A.qcap + s_bbase[cls] + rank] = (unsigned)sc * (unsigned)A.tiles_stride + (unsigned)t;
             }
         }
     }

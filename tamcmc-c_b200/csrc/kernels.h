@@ -78,7 +78,8 @@ cudaError_t tamcmc_upload_dmm_tables(const double* coef, const double* nnum, con
 cudaError_t tamcmc_expand_configure();
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
 cudaError_t tamcmc_whittle_configure(int* grid_ctas);   // one-time function attributes; returns the persistent grid size
-cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st);
+// pdl: programmatic dependent launch behind the expand kernel on the same stream
+cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st, bool pdl);
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st);
 // DFMA throughput microbenchmark: returns achieved FP64 TFLOP/s (2 flops per DFMA)
 cudaError_t tamcmc_fp64_peak(double* tflops, float* ms, int iters);

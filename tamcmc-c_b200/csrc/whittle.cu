@@ -537,6 +537,9 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Programmatic dependent launch: this grid may have been scheduled while the expand kernel was still running (its
+    // prologue above overlaps the expander's tail); everything below reads the expander's output.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid >= NC + 32) builder_loop(A, (tid - NC - 32) >> 5, tid & 31);
     else if (tid >= NC) producer_loop(A, sm, tid - NC);
     else consumer_loop<WRITE_MODEL>(A, sm, tid);
@@ -601,12 +604,21 @@ cudaError_t tamcmc_whittle_configure(int* grid_ctas)
     return cudaSuccess;
 }
 
-cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st)
+cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st, bool pdl)
 {
-    const size_t smem = sizeof(Smem);
-    if (write_model) tamcmc_whittle_kernel<true><<<grid_ctas, NT, smem, st>>>(a);
-    else tamcmc_whittle_kernel<false><<<grid_ctas, NT, smem, st>>>(a);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid_ctas, 1, 1);
+    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = sizeof(Smem);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    WhittleArgs args = a;
+    if (write_model) return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<true>, args);
+    return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<false>, args);
 }
 
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st)
