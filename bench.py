@@ -338,7 +338,7 @@ def main():
             "mcmc_steps_per_s": value / NCHAINS / S if S else None,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(P_host.nbytes),
                     "d2h_bytes_per_step": int(S * NCHAINS * 12), "ms_per_step": t_e2e / args.steps,
-                    "path": "tamcmc_gpu_eval (C ABI, host buffers, pinned staging, H2D+kernels+D2H+sync per step)"},
+                    "path": "tamcmc_gpu_eval (C ABI, host buffers): rows staged in mapped pinned memory and read by the expander over PCIe, results + completion flag written back to mapped pinned memory by the last CTA (TAMCMC_GPU_NO_ZEROCOPY=1: cudaMemcpyAsync H2D/D2H + stream sync)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": traffic, "kernel": "tamcmc_whittle_kernel", "kernel_ms": k_ms, "expand_kernel_ms": expand_ms / max(nprof, 1),

@@ -9,6 +9,7 @@
 #include "host_math.hpp"
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -125,6 +126,13 @@ struct tamcmc_gpu_ctx {
     unsigned char* h_active = nullptr;
     void* h_out = nullptr;
     QueueCtl* h_qctl = nullptr;
+    // zero-copy host path of tamcmc_gpu_eval: parameters are read by the expander straight from mapped pinned memory and
+    // the last CTA of the fused kernel writes results + a completion flag back into mapped pinned memory
+    bool zero_copy = true;           // TAMCMC_GPU_NO_ZEROCOPY=1 selects the DMA path (H2D + D2H copies + stream sync)
+    unsigned char* h_mirror = nullptr;   // [SC] double logL | [SC] int status | pad to 64 | uint overflow | pad to 128 | uint flag
+    double* dm_logL = nullptr; int* dm_status = nullptr; unsigned int* dm_overflow = nullptr; unsigned int* dm_flag = nullptr;
+    double* dh_params = nullptr; unsigned char* dh_active = nullptr;    // device addresses of h_params / h_active
+    unsigned int epoch_host = 1;     // mirrors the device epoch: advanced once per fused-kernel launch
     // CUDA graphs of the device-side sequence (memset, expand, tile lists, fused kernel, finalize), keyed by the
     // buffer pointers of the call
     struct GraphEntry { const double* p; const unsigned char* a; double* o; int raw; cudaGraphExec_t exec; };
@@ -140,6 +148,11 @@ struct tamcmc_gpu_ctx {
     long launches = 0;
     long pairs_last = -1;
 
+    size_t mirror_flag_off() const { return (((size_t)SC() * 12 + 63) / 64) * 64 + 64; }
+    const double* hm_logL() const { return reinterpret_cast<const double*>(h_mirror); }
+    const int* hm_status() const { return reinterpret_cast<const int*>(h_mirror + (size_t)SC() * 8); }
+    volatile unsigned int* hm_overflow() const { return reinterpret_cast<volatile unsigned int*>(h_mirror + mirror_flag_off() - 64); }
+    volatile unsigned int* hm_flag() const { return reinterpret_cast<volatile unsigned int*>(h_mirror + mirror_flag_off()); }
     int SC() const { return nstars * Nchains; }
     double* d_logL() const { return reinterpret_cast<double*>(d_out); }
     int* d_status() const { return reinterpret_cast<int*>(reinterpret_cast<double*>(d_out) + nstars * Nchains); }
@@ -170,7 +183,7 @@ TileListArgs make_tilelist_args(tamcmc_gpu_ctx* c)
     return a;
 }
 
-WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum)
+WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, bool mirror)
 {
     WhittleArgs a;
     a.stars = c->d_stars;
@@ -184,6 +197,9 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum)
     a.raw_sum = raw_sum; a.trace = c->d_trace;
     a.tl = make_tilelist_args(c); a.ready = c->d_ready; a.epoch = c->d_epoch;
     a.status = c->d_status(); a.nsc = c->SC();
+    // the host mirror costs a system-scope fence at the end of the launch: only the host-buffer entry point asks for it
+    a.host_logL = mirror ? c->dm_logL : nullptr; a.host_status = mirror ? c->dm_status : nullptr;
+    a.host_overflow = mirror ? c->dm_overflow : nullptr; a.host_flag = mirror ? c->dm_flag : nullptr;
     return a;
 }
 
@@ -192,7 +208,7 @@ int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned c
                      int raw_sum, cudaStream_t st, bool prof)
 {
     ExpandArgs ea = make_expand_args(c, d_params, d_active, d_logL);
-    WhittleArgs wa = make_whittle_args(c, d_logL, raw_sum);
+    WhittleArgs wa = make_whittle_args(c, d_logL, raw_sum, c->zero_copy && d_params == c->dh_params);
     if (prof) CK(cudaEventRecord(c->ev[0], st));
     CK(tamcmc_launch_expand(ea, c->SC(), st));
     if (prof) CK(cudaEventRecord(c->ev[1], st));
@@ -206,6 +222,7 @@ int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* 
                 int raw_sum, cudaStream_t st)
 {
     c->launches += 2;
+    { const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; }       // what the last CTA will publish
     const bool prof = c->profiling && st == c->stream;
     if (prof || !c->use_graphs) return enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof);
     for (int i = 0; i < c->ngraphs; i++) {
@@ -435,8 +452,22 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     CKC(cudaMalloc(&c->d_out, c->out_bytes()));
     CKC(cudaMemset(c->d_out, 0, c->out_bytes()));
     CKC(cudaMalloc(&c->d_model, sizeof(double) * (size_t)maxN));
-    CKC(cudaMallocHost(&c->h_params, sizeof(double) * (size_t)SC * c->params_stride));
-    CKC(cudaMallocHost(&c->h_active, (size_t)SC));
+    CKC(cudaHostAlloc(&c->h_params, sizeof(double) * (size_t)SC * c->params_stride, cudaHostAllocMapped));
+    CKC(cudaHostAlloc(&c->h_active, (size_t)SC, cudaHostAllocMapped));
+    CKC(cudaHostAlloc(&c->h_mirror, c->mirror_flag_off() + 64, cudaHostAllocMapped));
+    std::memset(c->h_mirror, 0, c->mirror_flag_off() + 64);
+    {
+        void* dp = nullptr;
+        CKC(cudaHostGetDevicePointer(&dp, c->h_params, 0)); c->dh_params = reinterpret_cast<double*>(dp);
+        CKC(cudaHostGetDevicePointer(&dp, c->h_active, 0)); c->dh_active = reinterpret_cast<unsigned char*>(dp);
+        CKC(cudaHostGetDevicePointer(&dp, c->h_mirror, 0));
+        unsigned char* dm = reinterpret_cast<unsigned char*>(dp);
+        c->dm_logL = reinterpret_cast<double*>(dm);
+        c->dm_status = reinterpret_cast<int*>(dm + (size_t)SC * 8);
+        c->dm_overflow = reinterpret_cast<unsigned int*>(dm + c->mirror_flag_off() - 64);
+        c->dm_flag = reinterpret_cast<unsigned int*>(dm + c->mirror_flag_off());
+    }
+    if (const char* e = std::getenv("TAMCMC_GPU_NO_ZEROCOPY")) c->zero_copy = !(e[0] == '1');
     CKC(cudaMallocHost(&c->h_out, c->out_bytes()));
     CKC(cudaMallocHost(&c->h_qctl, sizeof(QueueCtl)));
 
@@ -473,6 +504,7 @@ void tamcmc_gpu_destroy(tamcmc_gpu_ctx* c)
     cudaFree(c->d_model);
     if (c->h_params) cudaFreeHost(c->h_params);
     if (c->h_active) cudaFreeHost(c->h_active);
+    if (c->h_mirror) cudaFreeHost(c->h_mirror);
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_qctl) cudaFreeHost(c->h_qctl);
     for (int i = 0; i < c->ngraphs; i++) cudaGraphExecDestroy(c->graphs[i].exec);
@@ -494,25 +526,53 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char
     const int SC = c->SC();
     const size_t pbytes = sizeof(double) * (size_t)SC * c->params_stride;
     std::memcpy(c->h_params, params, pbytes);
-    CK(cudaMemcpyAsync(c->d_params, c->h_params, pbytes, cudaMemcpyHostToDevice, c->stream));
-    const unsigned char* d_act = nullptr;
-    if (active_mask) {
-        std::memcpy(c->h_active, active_mask, (size_t)SC);
-        CK(cudaMemcpyAsync(c->d_active, c->h_active, (size_t)SC, cudaMemcpyHostToDevice, c->stream));
-        d_act = c->d_active;
+    if (active_mask) std::memcpy(c->h_active, active_mask, (size_t)SC);
+    const int* st = nullptr;
+    unsigned int overflow = 0;
+    if (c->zero_copy) {
+        // ---- zero-copy: no DMA copies, no stream synchronisation.  The expander reads the rows over PCIe; the last CTA
+        // of the fused kernel writes logL/status into the mapped mirror and publishes the launch's epoch in the flag ----
+        { int rc = launch_eval(c, c->dh_params, active_mask ? c->dh_active : nullptr, c->d_logL(), 0, c->stream); if (rc) return rc; }
+        const unsigned int expected = c->epoch_host;
+        volatile unsigned int* flag = c->hm_flag();
+        unsigned long spins = 0;
+        while (*flag != expected) {
+            if ((++spins & 0x3fffu) == 0) {              // every 16k polls make sure the device is still healthy
+                const cudaError_t e = cudaStreamQuery(c->stream);
+                if (e == cudaSuccess) { if (*flag != expected) { g_last_error = "fused kernel finished without publishing its results"; return TAMCMC_ERR_CUDA; } break; }
+                if (e != cudaErrorNotReady) return fail_cuda(e, "cudaStreamQuery (fused kernel)");
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (c->profiling) CK(cudaStreamSynchronize(c->stream));
+        { int rc = collect_profile(c); if (rc) return rc; }
+        std::memcpy(logL_out, c->hm_logL(), sizeof(double) * (size_t)SC);
+        st = c->hm_status();
+        overflow = *c->hm_overflow();
+    } else {
+        CK(cudaMemcpyAsync(c->d_params, c->h_params, pbytes, cudaMemcpyHostToDevice, c->stream));
+        const unsigned char* d_act = nullptr;
+        if (active_mask) {
+            CK(cudaMemcpyAsync(c->d_active, c->h_active, (size_t)SC, cudaMemcpyHostToDevice, c->stream));
+            d_act = c->d_active;
+        }
+        { int rc = launch_eval(c, c->d_params, d_act, c->d_logL(), 0, c->stream); if (rc) return rc; }
+        CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->h_qctl, c->d_qctl, sizeof(QueueCtl), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        { int rc = collect_profile(c); if (rc) return rc; }
+        std::memcpy(logL_out, c->h_out, sizeof(double) * (size_t)SC);
+        st = reinterpret_cast<const int*>(reinterpret_cast<const double*>(c->h_out) + SC);
+        overflow = c->h_qctl->overflow;
     }
-    { int rc = launch_eval(c, c->d_params, d_act, c->d_logL(), 0, c->stream); if (rc) return rc; }
-    CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_qctl, c->d_qctl, sizeof(QueueCtl), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    { int rc = collect_profile(c); if (rc) return rc; }
-    std::memcpy(logL_out, c->h_out, sizeof(double) * (size_t)SC);
-    if (c->h_qctl->overflow) {
+    if (overflow) {
         g_last_error = "component-list pool overflow: raise TAMCMC_GPU_POOL_MB";
         reset_queue(c);                     // `overflow` is sticky on the device until the host has seen it
         return TAMCMC_ERR_POOL;
     }
-    const int* st = reinterpret_cast<const int*>(reinterpret_cast<const double*>(c->h_out) + SC);
     if (status_out) std::memcpy(status_out, st, sizeof(int) * (size_t)SC);
     c->pairs_last = -1;
     return status_to_rc(st, SC);
@@ -532,9 +592,10 @@ int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, doub
     if (!model_out) return TAMCMC_ERR_ARG;
     { int rc = expand_single(c, star, params_row); if (rc) return rc; }
     const StarDesc& sd = c->h_stars[star];
-    WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0);
+    WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0, false);
     CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->stream, false));
     c->launches += 1;
+    { const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; }
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     const int SC = c->SC();

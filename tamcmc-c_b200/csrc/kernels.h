@@ -68,6 +68,9 @@ struct WhittleArgs {
     TileListArgs tl;                 // builder warps: inputs of the per-tile list construction
     unsigned int* ready;             // [qcap * NBUCKETS] per queue position: == epoch once the item's lists are built
     unsigned int* epoch;             // device launch counter (never 0); bumped by the last CTA of the fused kernel
+    // host mirror (mapped pinned memory, device addresses; null = none): the last CTA copies the results there and then
+    // publishes the new epoch value in *host_flag, so the host can pick them up without a D2H copy or a stream sync
+    double* host_logL; int* host_status; unsigned int* host_overflow; unsigned int* host_flag;
     const int* status;               // [nstars*Nchains] per-chain status written by the expand kernel
     int nsc;                         // nstars*Nchains
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)

@@ -552,13 +552,23 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
     if (!s_last) return;
     __threadfence();
     finalize_chains(A, tid >> 5, tid & 31, NT / 32);
+    if (A.host_flag) {
+        // host mirror: every writer fences its own stores at system scope, the barrier orders them before the flag
+        __syncthreads();
+        for (int i = tid; i < A.nsc; i += NT) { A.host_logL[i] = A.out[i]; A.host_status[i] = A.status[i]; }
+        if (tid == 0) *A.host_overflow = A.qctl->overflow;
+        __threadfence_system();
+        __syncthreads();
+    }
     if (tid == 0) {
         QueueCtl* q = A.qctl;
 #pragma unroll
         for (int k = 0; k < TAMCMC_NBUCKETS; k++) q->count[k] = 0u;
         q->head = 0u; q->pool_cursor = 0ull; q->ctas_done = 0u;
-        const unsigned e = *A.epoch + 1u;
-        *A.epoch = e ? e : 1u;                          // next launch's ready-flag value (never 0)
+        unsigned e = *A.epoch + 1u;
+        e = e ? e : 1u;
+        *A.epoch = e;                                   // next launch's ready-flag value (never 0)
+        if (A.host_flag) *reinterpret_cast<volatile unsigned int*>(A.host_flag) = e;      // published last
     }
 }
 
