@@ -93,7 +93,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(synth, seconds=12.0, nthreads=0):
+def cpu_baseline(synth, seconds=12.0, nthreads=None):
     """The oracle port (reference algorithm, OpenMP over chains like MALA.cpp:648) timed on the host
     cores on a bounded sample of the same workload.  Test/benchmark infrastructure only."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -105,6 +105,8 @@ def cpu_baseline(synth, seconds=12.0, nthreads=0):
     P = synth.perturb_chains(rng, params, pl, NCHAINS)
     T = synth.tcoefs(NCHAINS, LAMBDA_T)
     cores = os.cpu_count() or 1
+    if nthreads is None:
+        nthreads = max(1, min(cores, NCHAINS))              # explicit: OMP_NUM_THREADS may be pinned to 1 by a launcher
     O.eval_chains(3, P, pl, x, y, T, nthreads=nthreads)    # warm-up
     n, t0 = 0, time.perf_counter()
     while True:
@@ -113,7 +115,7 @@ def cpu_baseline(synth, seconds=12.0, nthreads=0):
         el = time.perf_counter() - t0
         if el >= seconds and n >= 3:
             break
-    out = {"value": NCHAINS * n / el, "unit": "evals/s", "cores": min(cores, NCHAINS) if nthreads == 0 else nthreads,
+    out = {"value": NCHAINS * n / el, "unit": "evals/s", "cores": nthreads,
            "host_cores": cores, "kind": "port",
            "sample": "%d full 10-chain C2 steps (%.1f s), reference-faithful port: per-mode full-vector copies + multi-pass temporaries, one OpenMP thread per chain" % (n, el)}
     if hasattr(O.L, "orc_eval_chains_fast"):
@@ -153,13 +155,15 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     # two CPU implementations of the reference algorithm exist here; the arm reports the FASTER one (the conservative
     # denominator) and lists the other beside it
+    # torchrun exports OMP_NUM_THREADS=1: ask for the host's threads explicitly (the fan-out is over the 10 chains)
+    nthr = max(1, min(cores, NCHAINS))
     cands = {"port": ("oracle port of the reference algorithm (plain C, reference-faithful: per-mode full-vector copies + "
-                      "multi-pass temporaries), OpenMP over chains as MALA.cpp:648", lambda: O.eval_chains(3, P, pl, x, y, T))}
+                      "multi-pass temporaries), OpenMP over chains as MALA.cpp:648", lambda: O.eval_chains(3, P, pl, x, y, T, nthreads=nthr))}
     if _refshim.available_O3():
         R = _refshim.get_O3()
         cands["reference"] = ("reference sources (tamcmc/sources/models.cpp etc.) compiled -O3 -fopenmp against the eager "
                               "Eigen-API shim (oracle/eigen_shim; real Eigen is absent), OpenMP over chains as MALA.cpp:648",
-                              lambda: R.eval_chains(3, P, pl, x, y, T))
+                              lambda: R.eval_chains(3, P, pl, x, y, T, nthreads=nthr))
     calib = {}
     for k, (_, f) in cands.items():
         f()

@@ -1,0 +1,235 @@
+#!/usr/bin/env python
+"""Throughput of the OTHER BASELINE.json configs (bench.py measures C2, the config the metric is quoted on):
+
+  C1  quick-start red-giant case: the reference's fixture 10722175 (slice 80-128 microHz, ~6100 bins), mixed-mode list
+      resolved by the reference's own ARMM host code (tests/golden/reference_rgb_vectors.npz), 5 chains, lambda = 3.5
+  C3  MS_Global ajAlm (gate filter, decompose_Alm = 1), 33 modes l <= 2, 10^6 bins, 10 chains; bin-sharded over the
+      ranks when launched with torchrun (per-chain partial sums all-reduced with NCCL)
+  C4  dense red-giant mode list: the 78-mode case of the same fixture, 10 chains
+  C5  256 independent C2 stars x 10 chains, star-sharded over the ranks (no collective)
+
+  python profiles/bench_configs.py [--configs c1,c3,c4,c5] [--steps K] [--stars 256]
+  python -m torch.distributed.run --nproc-per-node N profiles/bench_configs.py --configs c3,c5 ...
+
+One JSON line per config on rank 0.  Device-resident timing (CUDA events on the launch stream, max over ranks) and the
+end-to-end C-ABI call with host buffers; every config is first checked against the CPU oracle on a sub-sample."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def timed(torch, ctx, P_host, steps, dist, extra=None):
+    """-> (device ms/step, e2e ms/step) for one context; `extra(d_out)` runs on the stream after each device eval."""
+    stream = torch.cuda.current_stream()
+    d_params = torch.tensor(P_host, device="cuda")
+    n = P_host.shape[0] * P_host.shape[1]
+    d_out = torch.zeros(n, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    raw = extra is not None
+
+    def step():
+        ctx.eval_device(d_params.data_ptr(), d_out.data_ptr(), raw_sum=raw, stream=stream.cuda_stream)
+        if extra:
+            extra(d_out)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(steps):
+        flush.zero_()
+        ev0[i].record(stream)
+        step()
+        ev1[i].record(stream)
+    torch.cuda.synchronize()
+    dev = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)) / steps
+    e2e = None
+    if not raw:
+        ctx.set_profiling(True)                      # CUDA events around each kernel (direct launches, warm L2)
+        for _ in range(10):
+            ctx.eval(P_host)
+        nprof, ems, wms = ctx.kernel_ms()
+        ctx.set_profiling(False)
+        timed.kernel_us = (1e3 * ems / max(nprof, 1), 1e3 * wms / max(nprof, 1))
+        for _ in range(3):
+            ctx.eval(P_host)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.eval(P_host)
+        e2e = (time.perf_counter() - t0) * 1e3 / steps
+    if dist:
+        t = torch.tensor([dev, e2e or 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev, e2e = float(t[0]), (float(t[1]) if e2e is not None else None)
+    return dev, e2e, d_out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c1,c3,c4,c5")
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--stars", type=int, default=256)
+    args = ap.parse_args()
+    import torch
+    import __graft_entry__ as g
+    import _oracle
+    pkg = g.load_package()
+    synth = pkg.synth
+    O = _oracle.get()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lr)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    torch.cuda.set_stream(torch.cuda.Stream())
+    todo = args.configs.split(",")
+
+    def emit(name, workload, evals_per_step, dev, e2e, pairs, extra=None):
+        if rank != 0:
+            return
+        line = {"config": name, "workload": workload, "n_gpus": world, "evals_per_step": evals_per_step,
+                "value": evals_per_step / (dev * 1e-3), "unit": "evals/s", "ms_per_step": dev,
+                "e2e": {"value": evals_per_step / (e2e * 1e-3), "ms_per_step": e2e} if e2e else None,
+                "pairs_per_step": pairs, "alg_tflops": (6.0 * pairs) / (dev * 1e-3) / 1e12 if pairs else None}
+        if extra:
+            line.update(extra)
+        if getattr(timed, "kernel_us", None):
+            line["expand_kernel_us"], line["fused_kernel_us"] = timed.kernel_us
+            timed.kernel_us = None
+        print(json.dumps(line), flush=True)
+
+    # ------------------------------------------------------------------ C1 / C4: red giant, mode table
+    if "c1" in todo or "c4" in todo:
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_rgb_vectors.npz"))
+        x, y = gold["x"], gold["y"]
+        ncases = int(gold["ncases"])
+        cap = max(len(gold["rows%d" % i]) for i in range(ncases)) + 2
+
+        def rows_of(i, scale=1.0):
+            params, pl, rows = gold["params%d" % i], gold["plength%d" % i], gold["rows%d" % i].copy()
+            rows[:, 2] *= scale
+            o = int(pl[:8].sum())
+            nn = int(pl[8])
+            return synth.mode_table_row(cap, abs(params[o + nn]), rows[0, 13], rows[0, 11], params[o:o + nn], rows[:, :11]), nn
+
+        for name, picks, lam in (("c1", [0, 1, 2, 3, 0], 3.5), ("c4", [2] * 10, 1.7)):
+            if name not in todo or rank != 0:
+                continue
+            rng = np.random.default_rng(1)
+            rows = np.stack([rows_of(i, 1.0 + 0.02 * rng.standard_normal())[0] for i in picks])
+            nn = rows_of(0)[1]
+            T = synth.tcoefs(len(picks), lam)
+            rc, L_ref = O.mode_table_eval_chains(rows, nn, 1, x, y, T)
+            star = pkg.Star(synth.MODEL_MODE_TABLE, synth.mode_table_plength(cap, nn, 1), rows.shape[1], x, y)
+            with pkg.Context(star, len(picks), T, device=lr) as ctx:
+                L, st = ctx.eval(rows)
+                err = float(np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)))
+                assert (st == 0).all() and err < 1e-10, err
+                pairs = ctx.pairs_last()
+                dev, e2e, _ = timed(torch, ctx, ctx.pack_params([rows]), args.steps * 4, None)
+            emit(name, "red-giant fixture 10722175, %d bins, %d chains, %d-%d modes/chain (ARMM-resolved mode table)"
+                 % (len(x), len(picks), int(rows[:, 0].min()), int(rows[:, 0].max())), len(picks), dev, e2e, pairs,
+                 {"max_rel_err_vs_oracle": err, "note": "single GPU (replicas only: SURVEY.md 8e); the ARMM host solve is outside the timed region"})
+
+    # ------------------------------------------------------------------ C3: ajAlm, 10^6 bins, bin-sharded
+    if "c3" in todo:
+        from importlib import import_module
+        shard = import_module("tamcmc_c_b200.sharding")
+        rng = np.random.default_rng(3427720)
+        N, Nch = 1000000, 10
+        params, pl = synth.ajalm_params(rng, Nmax=11, lmax=2, f0=2100.0, dnu=103.0, decompose_Alm=1, filter_code=0,
+                                        epsilon=5e-3, theta0=50.0, delta=20.0, trunc_c=30.0)
+        x = synth.freq_axis(N, 100.0)
+        capm = int(pl[2:6].sum())
+        nn = int(pl[8])
+        mpl = synth.mode_table_plength(capm, nn, 0)
+        row0, _ = pkg.expand_ajAlm(params, pl, capm)
+        with pkg.Context(pkg.Star(synth.MODEL_MODE_TABLE, mpl, len(row0), x, np.ones(N)), 1, [1.0], device=lr) as c0:
+            M = c0.model(row0)
+            _, wl, w0, w1 = c0.windows(row0)
+        y = synth.chi2_2dof_spectrum(rng, M)
+        P = synth.perturb_chains(rng, params, pl, Nch)
+        rows = np.stack([pkg.expand_ajAlm(P[c], pl, capm)[0] for c in range(Nch)])
+        T = synth.tcoefs(Nch, 1.7)
+        rc, Mo = O.mode_table_model(rows[1], nn, 0, x)              # oracle check of one chain at full size
+        L1_ref = O.call_likelihood(y, Mo, 1.0, T[1])
+        lo, hi = shard.bin_shards(N, world, shard.bin_work(N, wl, w0, w1))[rank]
+        star = pkg.Star.shard(synth.MODEL_MODE_TABLE, mpl, rows.shape[1], x, y, lo, hi) if world > 1 else \
+            pkg.Star(synth.MODEL_MODE_TABLE, mpl, rows.shape[1], x, y)
+        with pkg.Context(star, Nch, T, device=lr) as ctx:
+            if world > 1:
+                def allreduce(d_S):
+                    dist.all_reduce(d_S, op=dist.ReduceOp.SUM)      # 80 bytes: the path's one exchange step
+                dev, e2e, d_S = timed(torch, ctx, ctx.pack_params([rows]), args.steps, dist, extra=allreduce)
+                # d_S was all-reduced in place after the last evaluation
+                L = shard.finalize_logL(d_S.cpu().numpy(), 1.0, T)
+            else:
+                dev, e2e, d_L = timed(torch, ctx, ctx.pack_params([rows]), args.steps, None)
+                L = d_L.cpu().numpy()
+            pairs = ctx.pairs_last()
+        if dist:
+            pt = torch.tensor([float(pairs)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(pt)
+            pairs = int(pt[0])
+        err = abs(L[1] - L1_ref) / abs(L1_ref)
+        assert err < 1e-10, err
+        emit("c3", "MS_Global ajAlm (gate, decompose_Alm=1) via host expander, 33 modes l<=2, 10^6 bins, 10 chains", Nch, dev, e2e, pairs,
+             {"max_rel_err_vs_oracle": float(err), "sharding": "bins, balanced by per-bin work, tile-aligned; NCCL sum-allreduce of 10 partial sums" if world > 1 else "none",
+              "note": "host expander (tamcmc_host_expand_ajAlm) outside the timed region"})
+
+    # ------------------------------------------------------------------ C5: 256 stars x 10 chains, star-sharded
+    if "c5" in todo:
+        from importlib import import_module
+        shard = import_module("tamcmc_c_b200.sharding")
+        import bench
+        mine = shard.star_shard(args.stars, rank, world)
+        T = synth.tcoefs(10, 1.7)
+        stars, Ps = [], []
+        p0, pl0 = synth.classic_params(np.random.default_rng(0))
+        with pkg.Context(pkg.Star(3, pl0, len(p0), synth.freq_axis(bench.NBINS, 500.0), np.ones(bench.NBINS)), 1, [1.0], device=lr) as c0:
+            for s in mine:
+                rng = np.random.default_rng(12345 + s)
+                # Dnu ~ U(60, 95): 20 radial orders stay inside the 500-2480 microHz spectrum (SURVEY.md 8d says U(60,130),
+                # which pushes the upper orders of a 20-order comb past the last bin)
+                params, pl = synth.classic_params(rng, dnu=rng.uniform(60.0, 95.0), f0=rng.uniform(560.0, 620.0))
+                x = synth.freq_axis(bench.NBINS, 500.0)
+                M = c0.model(params)
+                y = synth.chi2_2dof_spectrum(rng, M)
+                stars.append(pkg.Star(3, pl, len(params), x, y))
+                Ps.append(synth.perturb_chains(rng, params, pl, 10))
+        rc, L_ref = O.eval_chains(3, Ps[0], stars[0].plength, stars[0].x, stars[0].y, T)
+        with pkg.Context(stars, 10, T, device=lr) as ctx:
+            P_host = ctx.pack_params(Ps)
+            L, st = ctx.eval(P_host)
+            err = float(np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)))
+            assert (st == 0).all() and err < 1e-10, err
+            pairs = ctx.pairs_last()
+            dev, e2e, _ = timed(torch, ctx, P_host, max(args.steps // 5, 5), dist)
+        if dist:
+            pt = torch.tensor([float(pairs)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(pt)
+            pairs = int(pt[0])
+        emit("c5", "%d independent C2-like stars (Dnu 60-95 microHz) x 10 chains, 250k bins each, star-sharded" % args.stars,
+             args.stars * 10, dev, e2e, pairs, {"max_rel_err_vs_oracle": err, "stars_per_gpu": len(mine)})
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

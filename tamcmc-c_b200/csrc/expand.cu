@@ -624,6 +624,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             CompRec* out = comps + (size_t)j * TAMCMC_MAX_COMP_PER_MODE;
             int nf = 0, ns = 0;
             unsigned fastmask = 0, livemask = 0;
+            int wide = 0;
             for (int k = 0; k <= 2 * l; k++) {
                 const double Ah = slot_A[tid * TAMCMC_MAX_COMP_PER_MODE + k];
                 const double v = slot_nu[tid * TAMCMC_MAX_COMP_PER_MODE + k];
@@ -633,8 +634,11 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 if (!(emax < 1e100)) { atomicOr(&s_status, TAMCMC_ST_NONFINITE); continue; }
                 livemask |= 1u << k;
                 // FAST: t' = (1+e^2)/A stays inside [1e-8, 1e16] over the whole window, so 16 merges between
-                // two exponent renormalisations cannot leave the FP64 range
+                // two exponent renormalisations cannot leave the FP64 range.  WIDE (very narrow modes, e.g. red-giant
+                // mixed modes far narrower than a bin): t' inside [1e-16, 1e32], same scaled form, but the segments
+                // that hold such a mode renormalise every 4 merges.
                 if (Ah >= 1e-8 && Ah <= 1e8 && emax < 1e4) fastmask |= 1u << k;
+                else if (Ah >= 1e-16 && Ah <= 1e16 && emax < 1e8) { fastmask |= 1u << k; wide = 1; }
             }
             for (int pass = 0; pass < 2; pass++)
                 for (int k = 0; k <= 2 * l; k++) {
@@ -648,7 +652,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                     else { cr.flags = TAMCMC_CF_SLOW; cr.s = sg; cr.a = Ah; ns++; }
                     out[nf + ns - 1] = cr;
                 }
-            mr.nfast = nf; mr.ncomp = nf + ns;
+            mr.nfast = nf | (wide << 16); mr.ncomp = nf + ns;      // bit 16: the mode has WIDE fast components
             modes[j] = mr;
             // per-tile cost: difference array over the LOCAL tiles this window touches
             if (!bad && mr.ncomp > 0) {

@@ -46,7 +46,8 @@ struct __align__(16) ModeRec {
     // first 16 bytes = everything the tile classification needs (one 128-bit load)
     int i0, i1;          // GLOBAL bin window [i0, i1)  (set_imin_imax, bit-exact)
     int ncomp;           // number of live components (height != 0); FAST ones are stored first
-    int nfast;           // leading components in the scaled FAST form
+    int nfast;           // bits 0-15: leading components in the scaled FAST form; bit 16: some of them are WIDE-range
+                         // (the segments that list this mode renormalise every 4 merges instead of every 16)
     int l;               // degree
     int pad;
     double fc;           // central frequency fc_l
@@ -98,7 +99,7 @@ struct StarDesc {
 struct __align__(16) FastEntry { double s, c, a, pad; };                 // e' = fma(u, s, c); t' = fma(e', e', a)
 struct __align__(16) ModeHdr { double qa, qb, qc; int begin, count; };   // asym fast path: q(u) and its fast entries
 struct __align__(16) GenEntry { double s, c, aadd, num, qa, qb, qc; int lo, hi; };
-struct __align__(16) SegDesc { int f0, nf, h0, nh, g0, ng, pad0, pad1; }; // slices of the tile's three arrays
+struct __align__(16) SegDesc { int f0, nf, h0, nh, g0, ng, wide, pad1; }; // slices of the tile's three arrays; wide: see ModeRec.nfast
 
 // per (star, chain, tile) record: background series from the background CTAs of the expand launch, list
 // descriptor from the tile-list kernel.  The tile's lists live in the pool at pool_off:
@@ -112,6 +113,7 @@ struct __align__(16) TileRec {
     int nseg;                     // segments (1 unless a list exceeds the shared-memory capacities)
     int TF, TH, TG;               // total entries of the three arrays
     int s0_nf, s0_nh, s0_ng;      // first segment (f0 = h0 = g0 = 0)
+    int s0_wide;
 };
 
 // work queue header: count[k] items in cost bucket k (k = 0 heaviest), head = pop cursor

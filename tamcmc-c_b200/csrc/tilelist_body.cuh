@@ -46,7 +46,7 @@ __device__ void build_tile_lists(const TileListArgs& A, unsigned int item, int l
         if (mi < nmodes) {
             const int4 h = *reinterpret_cast<const int4*>(modes + mi);     // {i0, i1, ncomp, nfast}
             if (h.z > 0 && h.x < gend && h.y > g0) {
-                nf = (h.x <= g0 && h.y >= gend) ? h.w : 0;
+                nf = (h.x <= g0 && h.y >= gend) ? (h.w & 0xffff) : 0;
                 ng = h.z - nf;
             }
         }
@@ -59,7 +59,7 @@ __device__ void build_tile_lists(const TileListArgs& A, unsigned int item, int l
     if (lane == 0) off = atomicAdd(&A.qctl->pool_cursor, (bytes + 127ull) & ~127ull);
     off = __shfl_sync(0xffffffffu, off, 0);
     if (off + bytes > A.pool_bytes) {
-        if (lane == 0) { atomicExch(&A.qctl->overflow, 1u); tr->nseg = 0; tr->TF = tr->TG = tr->TH = 0; tr->s0_nf = tr->s0_nh = tr->s0_ng = 0; tr->pool_off = 0; }
+        if (lane == 0) { atomicExch(&A.qctl->overflow, 1u); tr->nseg = 0; tr->TF = tr->TG = tr->TH = 0; tr->s0_nf = tr->s0_nh = tr->s0_ng = 0; tr->s0_wide = 0; tr->pool_off = 0; }
         return;
     }
     FastEntry* fast = reinterpret_cast<FastEntry*>(A.pool + off);
@@ -69,15 +69,16 @@ __device__ void build_tile_lists(const TileListArgs& A, unsigned int item, int l
 
     // ---- sweep 2: emit.  (cf, cg, ch) = entries written so far; (f0, g0s, h0) = start of the open segment ----
     int cf = 0, cg = 0, ch = 0, f0 = 0, g0s = 0, h0 = 0, nseg = 0;
-    int s0nf = 0, s0nh = 0, s0ng = 0;
+    int s0nf = 0, s0nh = 0, s0ng = 0, s0wide = 0, seg_wide = 0;
     for (int base = 0; base < nmodes; base += 32) {
         const int mi = base + lane;
-        int ncomp = 0, nfast = 0, ngen = 0, i0 = 0, i1 = 0, nfast_rec = 0;
+        int ncomp = 0, nfast = 0, ngen = 0, i0 = 0, i1 = 0, nfast_rec = 0, mwide = 0;
         if (mi < nmodes) {
             const int4 h = *reinterpret_cast<const int4*>(modes + mi);
             if (h.z > 0 && h.x < gend && h.y > g0) {
-                ncomp = h.z; nfast_rec = h.w; i0 = h.x; i1 = h.y;
-                nfast = (h.x <= g0 && h.y >= gend) ? h.w : 0;
+                ncomp = h.z; nfast_rec = h.w & 0xffff; i0 = h.x; i1 = h.y;
+                nfast = (h.x <= g0 && h.y >= gend) ? nfast_rec : 0;
+                mwide = (nfast > 0) ? (h.w >> 16) & 1 : 0;
                 ngen = ncomp - nfast;
             }
         }
@@ -95,10 +96,11 @@ __device__ void build_tile_lists(const TileListArgs& A, unsigned int item, int l
             }
             if ((cf - f0) + tf > TAMCMC_CAPF || (cg - g0s) + tg > TAMCMC_CAPG || (ch - h0) + th > TAMCMC_CAPH) {
                 // close the open segment
-                if (lane == 0) { SegDesc d; d.f0 = f0; d.nf = cf - f0; d.h0 = h0; d.nh = ch - h0; d.g0 = g0s; d.ng = cg - g0s; d.pad0 = d.pad1 = 0; segs[nseg] = d; }
-                if (nseg == 0) { s0nf = cf - f0; s0nh = ch - h0; s0ng = cg - g0s; }
-                nseg++; f0 = cf; g0s = cg; h0 = ch;
+                if (lane == 0) { SegDesc d; d.f0 = f0; d.nf = cf - f0; d.h0 = h0; d.nh = ch - h0; d.g0 = g0s; d.ng = cg - g0s; d.wide = seg_wide; d.pad1 = 0; segs[nseg] = d; }
+                if (nseg == 0) { s0nf = cf - f0; s0nh = ch - h0; s0ng = cg - g0s; s0wide = seg_wide; }
+                nseg++; f0 = cf; g0s = cg; h0 = ch; seg_wide = 0;
             }
+            seg_wide |= __any_sync(0xffffffffu, mine && mwide) ? 1 : 0;
             const int mf = mine ? nfast : 0, mg = mine ? ngen : 0, mh = mine ? hh : 0;
             const int of = cf + warp_excl_scan(mf, lane), og = cg + warp_excl_scan(mg, lane), oh = ch + warp_excl_scan(mh, lane);
             if (mine && ncomp > 0) {
@@ -134,12 +136,12 @@ __device__ void build_tile_lists(const TileListArgs& A, unsigned int item, int l
         }
     }
     // last segment (possibly empty: a tile no mode touches still has its background and Whittle terms)
-    if (lane == 0) { SegDesc d; d.f0 = f0; d.nf = cf - f0; d.h0 = h0; d.nh = ch - h0; d.g0 = g0s; d.ng = cg - g0s; d.pad0 = d.pad1 = 0; segs[nseg] = d; }
-    if (nseg == 0) { s0nf = cf - f0; s0nh = ch - h0; s0ng = cg - g0s; }
+    if (lane == 0) { SegDesc d; d.f0 = f0; d.nf = cf - f0; d.h0 = h0; d.nh = ch - h0; d.g0 = g0s; d.ng = cg - g0s; d.wide = seg_wide; d.pad1 = 0; segs[nseg] = d; }
+    if (nseg == 0) { s0nf = cf - f0; s0nh = ch - h0; s0ng = cg - g0s; s0wide = seg_wide; }
     nseg++;
     if (lane == 0) {
         tr->pool_off = off; tr->nseg = nseg; tr->TF = TF; tr->TH = TH; tr->TG = TG;
-        tr->s0_nf = s0nf; tr->s0_nh = s0nh; tr->s0_ng = s0ng;
+        tr->s0_nf = s0nf; tr->s0_nh = s0nh; tr->s0_ng = s0ng; tr->s0_wide = s0wide;
     }
 }
 

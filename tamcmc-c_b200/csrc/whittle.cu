@@ -34,13 +34,14 @@ constexpr int NT = TAMCMC_THREADS;                         // + producer warp
 constexpr int BPT = TAMCMC_BINS_PER_THREAD;
 constexpr int TILE = TAMCMC_TILE;
 constexpr int GROUP = 16;                                  // fast components merged between two renormalisations
+constexpr int GROUP_WIDE = 4;                              // ... in segments that hold WIDE-range components
 constexpr int NB = TAMCMC_BG_TERMS;
 constexpr int CAPF = TAMCMC_CAPF;                          // fast entries per segment
 constexpr int CAPG = TAMCMC_CAPG;                          // general entries per segment
 constexpr int CAPH = TAMCMC_CAPH;                          // mode headers per segment (asym fast path)
 constexpr int NBUF = 4;                                    // segment ring depth
 
-enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_POISON = 32 };
+enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_POISON = 32, SEG_WIDE = 64 };
 
 struct __align__(16) Segment {
     double x[TILE];          // TMA destinations: spectrum tile (first segment of a tile) ...
@@ -215,7 +216,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
         const int nseg = tr->nseg;
         const unsigned long long poff = tr->pool_off;
         const int TF = tr->TF, TH = tr->TH;
-        int nf = tr->s0_nf, nh = tr->s0_nh, ng = tr->s0_ng, f0 = 0, h0 = 0, g0 = 0;
+        int nf = tr->s0_nf, nh = tr->s0_nh, ng = tr->s0_ng, f0 = 0, h0 = 0, g0 = 0, wide = tr->s0_wide;
         const double bgk = (lane < NB) ? tr->bg[lane] : 0.0;
         const bool asym = A.asym_flag[sc] != 0;
         const double N0 = A.noise[sc].N0;
@@ -228,7 +229,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
 
         const int nsegs = (nseg > 0) ? nseg : 1;      // nseg == 0: list pool overflow -> poisoned tile (NaN)
         for (int j = 0; j < nsegs; j++) {
-            if (j > 0) { const SegDesc d = segs[j]; f0 = d.f0; nf = d.nf; h0 = d.h0; nh = d.nh; g0 = d.g0; ng = d.ng; }
+            if (j > 0) { const SegDesc d = segs[j]; f0 = d.f0; nf = d.nf; h0 = d.h0; nh = d.nh; g0 = d.g0; ng = d.ng; wide = d.wide; }
             if (use[b]) mbar_wait(&sm.empty[b], (use[b] - 1) & 1);
             Segment* sg = &sm.seg[b];
             const bool first = (j == 0), last = (j == nsegs - 1);
@@ -243,7 +244,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
                 if (nh) tma_load_1d(sg->hdr, lists + 32ull * TF + 32ull * h0, 32u * (unsigned)nh, &sm.full[b]);
                 if (ng) tma_load_1d(sg->gen, lists + 32ull * TF + 32ull * TH + 64ull * g0, 64u * (unsigned)ng, &sm.full[b]);
                 sg->nfast = nf; sg->ngen = ng; sg->nhdr = nh;
-                sg->flags = (first ? SEG_FIRST : 0) | (last ? SEG_LAST : 0) | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (nseg > 0 ? 0 : SEG_POISON);
+                sg->flags = (first ? SEG_FIRST : 0) | (last ? SEG_LAST : 0) | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (nseg > 0 ? 0 : SEG_POISON) | (wide ? SEG_WIDE : 0);
                 sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
             }
             if (last && lane < NB) sg->bg[lane] = bgk;
@@ -306,11 +307,27 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
         const int tot_fast = sg.nfast;
         if (!asym) {
             int k = 0;
-            for (; k + GROUP <= tot_fast; k += GROUP) {
+            if (!(flags & SEG_WIDE)) {
+                for (; k + GROUP <= tot_fast; k += GROUP) {
 #pragma unroll
-                for (int kk = 0; kk < GROUP; kk++) {
-                    const double2 p = *reinterpret_cast<const double2*>(&sg.fast[k + kk].s);
-                    const double a = sg.fast[k + kk].a;
+                    for (int kk = 0; kk < GROUP; kk++) {
+                        const double2 p = *reinterpret_cast<const double2*>(&sg.fast[k + kk].s);
+                        const double a = sg.fast[k + kk].a;
+#pragma unroll
+                        for (int j = 0; j < BPT; j++) {
+                            const double e = fma(u[j], p.x, p.y);
+                            const double t = fma(e, e, a);
+                            N[j] = fma(N[j], t, D[j]);
+                            D[j] *= t;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < BPT; j++) renorm(N[j], D[j]);
+                }
+#pragma unroll 4
+                for (; k < tot_fast; k++) {
+                    const double2 p = *reinterpret_cast<const double2*>(&sg.fast[k].s);
+                    const double a = sg.fast[k].a;
 #pragma unroll
                     for (int j = 0; j < BPT; j++) {
                         const double e = fma(u[j], p.x, p.y);
@@ -319,19 +336,25 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
                         D[j] *= t;
                     }
                 }
+            } else {
+                // WIDE-range components in this segment: renormalise every GROUP_WIDE merges
+                for (; k < tot_fast; k += GROUP_WIDE) {
 #pragma unroll
-                for (int j = 0; j < BPT; j++) renorm(N[j], D[j]);
-            }
-#pragma unroll 4
-            for (; k < tot_fast; k++) {
-                const double2 p = *reinterpret_cast<const double2*>(&sg.fast[k].s);
-                const double a = sg.fast[k].a;
+                    for (int kk = 0; kk < GROUP_WIDE; kk++) {
+                        if (k + kk < tot_fast) {
+                            const double2 p = *reinterpret_cast<const double2*>(&sg.fast[k + kk].s);
+                            const double a = sg.fast[k + kk].a;
 #pragma unroll
-                for (int j = 0; j < BPT; j++) {
-                    const double e = fma(u[j], p.x, p.y);
-                    const double t = fma(e, e, a);
-                    N[j] = fma(N[j], t, D[j]);
-                    D[j] *= t;
+                            for (int j = 0; j < BPT; j++) {
+                                const double e = fma(u[j], p.x, p.y);
+                                const double t = fma(e, e, a);
+                                N[j] = fma(N[j], t, D[j]);
+                                D[j] *= t;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < BPT; j++) renorm(N[j], D[j]);
                 }
             }
 #pragma unroll
@@ -358,7 +381,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
                     }
                 }
                 since += h.count;
-                if (since + TAMCMC_MAX_COMP_PER_MODE > GROUP) {
+                if (since + TAMCMC_MAX_COMP_PER_MODE > ((flags & SEG_WIDE) ? TAMCMC_MAX_COMP_PER_MODE : GROUP)) {
                     since = 0;
 #pragma unroll
                     for (int j = 0; j < BPT; j++) renorm(N[j], D[j]);
