@@ -72,13 +72,14 @@ __device__ void build_tile_lists(const TileListArgs& A, unsigned int item, int l
     int s0nf = 0, s0nh = 0, s0ng = 0, s0wide = 0, seg_wide = 0;
     for (int base = 0; base < nmodes; base += 32) {
         const int mi = base + lane;
-        int ncomp = 0, nfast = 0, ngen = 0, i0 = 0, i1 = 0, nfast_rec = 0, mwide = 0;
+        int ncomp = 0, nfast = 0, ngen = 0, i0 = 0, i1 = 0, nfast_rec = 0, mwide = 0, wbit = 0;
         if (mi < nmodes) {
             const int4 h = *reinterpret_cast<const int4*>(modes + mi);
             if (h.z > 0 && h.x < gend && h.y > g0) {
                 ncomp = h.z; nfast_rec = h.w & 0xffff; i0 = h.x; i1 = h.y;
                 nfast = (h.x <= g0 && h.y >= gend) ? nfast_rec : 0;
-                mwide = (nfast > 0) ? (h.w >> 16) & 1 : 0;
+                wbit = (h.w >> 16) & 1;
+                mwide = (nfast > 0) ? wbit : 0;
                 ngen = ncomp - nfast;
             }
         }
@@ -124,7 +125,10 @@ __device__ void build_tile_lists(const TileListArgs& A, unsigned int item, int l
                                 const bool ff = k < nfast_rec;
                                 GenEntry ge;
                                 ge.s = cs[kk]; ge.c = cc; ge.aadd = ff ? ca[kk] : 1.0; ge.num = ff ? 1.0 : ca[kk];
-                                ge.qa = qa; ge.qb = qb; ge.qc = qc; ge.lo = i0 - g0; ge.hi = i1 - g0;
+                                // window in tile-local bins, clamped to the tile; bit 30 of hi: the entry needs an exponent
+                                // renormalisation after every merge (general form, or a WIDE-range mode)
+                                ge.qa = qa; ge.qb = qb; ge.qc = qc; ge.lo = max(i0 - g0, 0);
+                                ge.hi = min(i1 - g0, TAMCMC_TILE) | ((!ff || wbit) ? (1 << 30) : 0);
                                 gen[og + (k - nfast)] = ge;
                             }
                         }

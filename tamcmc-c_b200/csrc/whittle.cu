@@ -101,12 +101,12 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #endif
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
 
-// 1/x to ~1 ulp: hardware approximation (rel. error 2^-23) + two Newton steps.  x = 0 -> inf, NaN -> NaN.
+// 1/x for the Whittle terms: hardware approximation (rel. error <= 2^-23) + ONE Newton step -> rel. error <= 2^-46 = 1.4e-14,
+// four orders of magnitude inside the 1e-10 bar on logL (the model-spectrum entry uses a true division).  x = 0 -> inf.
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
     r = fma(fma(-x, r, 1.0), r, r);
     return r;
 }
@@ -395,28 +395,53 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
         // contiguous run of 64 bins per register pair (bins 2*tid + 2*NC*pj + r): a run the window covers is merged unmasked, a run holding
         // a window edge under a per-bin mask, the others are skipped; the three-way decision is warp-uniform. ----------
         const int tot_gen = sg.ngen;
+        int gsince[BPT / 2];                       // plain merges of each register pair since its last renormalisation
+#pragma unroll
+        for (int pj = 0; pj < BPT / 2; pj++) gsince[pj] = 0;
         for (int g = 0; g < tot_gen; g++) {
             const GenEntry ge = sg.gen[g];
+            const int ghi = ge.hi & 0xffff;
+            const bool heavy = (ge.hi >> 30) & 1;
 #pragma unroll
             for (int pj = 0; pj < BPT / 2; pj++) {
                 const int w0 = 2 * NC * pj + 64 * warp, w1 = w0 + 64;
-                if (ge.hi <= w0 || ge.lo >= w1) continue;
-                const bool whole = (ge.lo <= w0 && ge.hi >= w1);
+                if (ghi <= w0 || ge.lo >= w1) continue;
+                const bool whole = (ge.lo <= w0 && ghi >= w1);
+                if (whole && !heavy) {
+                    // the window covers this run and the component is in the FAST range: a plain merge
 #pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    const int j = 2 * pj + r;
-                    const int bb = 2 * tid + 2 * NC * pj + r;
-                    const bool in = whole || ((bb >= ge.lo) && (bb < ge.hi));
-                    const double e = fma(u[j], ge.s, ge.c);
-                    const double t = fma(e, e, ge.aadd);
-                    double nd = ge.num * D[j];
-                    if (asym) { const double w = fma(u[j], ge.qa, ge.qb); nd *= fma(w, w, ge.qc); }
-                    const double Nn = fma(N[j], t, nd);
-                    const double Dn = D[j] * t;
-                    if (in) { N[j] = Nn; D[j] = Dn; }
-                    renorm(N[j], D[j]);
+                    for (int r = 0; r < 2; r++) {
+                        const int j = 2 * pj + r;
+                        const double e = fma(u[j], ge.s, ge.c);
+                        const double t = fma(e, e, ge.aadd);
+                        double nd = D[j];                       // FAST form: num == 1
+                        if (asym) { const double w = fma(u[j], ge.qa, ge.qb); nd *= fma(w, w, ge.qc); }
+                        N[j] = fma(N[j], t, nd);
+                        D[j] *= t;
+                    }
+                    if (++gsince[pj] >= GROUP - 1) { gsince[pj] = 0; renorm(N[2 * pj], D[2 * pj]); renorm(N[2 * pj + 1], D[2 * pj + 1]); }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int j = 2 * pj + r;
+                        const int bb = 2 * tid + 2 * NC * pj + r;
+                        const bool in = whole || ((bb >= ge.lo) && (bb < ghi));
+                        const double e = fma(u[j], ge.s, ge.c);
+                        const double t = fma(e, e, ge.aadd);
+                        double nd = ge.num * D[j];
+                        if (asym) { const double w = fma(u[j], ge.qa, ge.qb); nd *= fma(w, w, ge.qc); }
+                        const double Nn = fma(N[j], t, nd);
+                        const double Dn = D[j] * t;
+                        if (in) { N[j] = Nn; D[j] = Dn; }
+                        renorm(N[j], D[j]);
+                    }
+                    gsince[pj] = 0;
                 }
             }
+        }
+        if (tot_gen) {
+#pragma unroll
+            for (int j = 0; j < BPT; j++) renorm(N[j], D[j]);
         }
 
         if (flags & SEG_LAST) {
