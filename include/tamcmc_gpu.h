@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define TAMCMC_GPU_ABI_VERSION 1
+#define TAMCMC_GPU_ABI_VERSION 2
 
 typedef enum {
     TAMCMC_OK = 0,
@@ -71,6 +71,7 @@ typedef enum {
 
 /* likelihood ids = Config/default/likelihoods_ctrl.list (model_def.cpp:396-403) */
 #define TAMCMC_LIKELIHOOD_CHI22P 0      /* likelihood_chi22p, likelihoods.cpp:17-28 */
+#define TAMCMC_LIKELIHOOD_CHI_SQUARE 1  /* likelihood_chi_square, likelihoods.cpp:31-40: -sum((y-M)^2/sigma_y^2)/2, /Tcoefs[m] */
 
 typedef struct tamcmc_gpu_ctx tamcmc_gpu_ctx;
 
@@ -89,6 +90,9 @@ typedef struct {
     long N_global;
     long bin_offset;
     double x_first, x_second, x_last;
+    /* chi_square likelihood only: uncertainties of y, length N (Data.sigma_y); NULL = all ones, which is what the
+     * reference substitutes when the data file has no such column (config.cpp:367-374) */
+    const double *sigma_y;
 } tamcmc_gpu_star;
 
 /* Replaces: the data/model set-up of Model_def::Model_def (model_def.cpp:28-160) for the hot path.

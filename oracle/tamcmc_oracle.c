@@ -1294,6 +1294,31 @@ int orc_eval_chains(int model_id, const double *params, int Nparams, const int *
     return rc_all;
 }
 
+/* call_model + call_likelihood case 1 (chi_square, model_def.cpp:403-406): likelihood_chi_square(y, model, sigma_y) / Tcoefs[m] */
+int orc_eval_chains_chi_square(int model_id, const double *params, int Nparams, const int *plength, const double *x,
+                               const double *y, const double *sigma, long N, int Nchains, const double *Tcoefs,
+                               double *logL_out, int nthreads)
+{
+    int rc_all = 0, c;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (c = 0; c < Nchains; c++) {
+        double *model = (double *)malloc(sizeof(double) * (size_t)N);
+        int rc = orc_call_model(model_id, params + (size_t)c * Nparams, plength, x, N, model, 0, 0);
+        if (rc) {
+            logL_out[c] = NAN;
+#pragma omp critical
+            rc_all = rc;
+        } else logL_out[c] = (double)(orc_likelihood_chi_square(y, model, sigma, N) / Tcoefs[c]);
+        free(model);
+    }
+    return rc_all;
+}
+
 /* ------------------------------------------------------------------------- */
 /* generic mode table (include/tamcmc_gpu.h: TAMCMC_MODEL_MODE_TABLE)         */
 /* ------------------------------------------------------------------------- */

@@ -140,6 +140,10 @@ int orc_eval_chains_fast(int model_id, const double *params, int Nparams, const 
                          const double *x, const double *y, long N, int Nchains, const double *Tcoefs, double p,
                          double *logL_out, int nthreads);
 
+int orc_eval_chains_chi_square(int model_id, const double *params, int Nparams, const int *plength, const double *x,
+                               const double *y, const double *sigma, long N, int Nchains, const double *Tcoefs,
+                               double *logL_out, int nthreads);
+
 /* generic mode table (TAMCMC_MODEL_MODE_TABLE of include/tamcmc_gpu.h): what the aj-family model functions do after
  * resolving their mode list (models.cpp:4931-5017) */
 int orc_mode_table_model(const double *row, int Nnoise, int step_mode, const double *x, long N, double *out);

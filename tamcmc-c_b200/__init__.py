@@ -53,6 +53,7 @@ class StarStruct(C.Structure):
         ("x_first", C.c_double),
         ("x_second", C.c_double),
         ("x_last", C.c_double),
+        ("sigma_y", _dp),
     ]
 
 
@@ -132,7 +133,7 @@ def _d(a):
 class Star:
     """Host-side description of one star/slice (reference: Data{x,y,Nx} + model selection)."""
 
-    def __init__(self, model_id, plength, Nparams, x, y, N_global=0, bin_offset=0, x_first=0.0, x_second=0.0, x_last=0.0):
+    def __init__(self, model_id, plength, Nparams, x, y, N_global=0, bin_offset=0, x_first=0.0, x_second=0.0, x_last=0.0, sigma_y=None):
         self.model_id = int(model_id)
         self.plength = np.ascontiguousarray(plength, dtype=np.int32)
         self.Nparams = int(Nparams)
@@ -140,13 +141,14 @@ class Star:
         self.y = _d(y)
         self.N_global, self.bin_offset = int(N_global), int(bin_offset)
         self.x_first, self.x_second, self.x_last = float(x_first), float(x_second), float(x_last)
+        self.sigma_y = None if sigma_y is None else _d(sigma_y)     # chi_square likelihood only
 
     @classmethod
-    def shard(cls, model_id, plength, Nparams, x, y, lo, hi):
+    def shard(cls, model_id, plength, Nparams, x, y, lo, hi, sigma_y=None):
         """Bins [lo,hi) of a spectrum (bin-sharding over GPUs)."""
         x = _d(x)
         return cls(model_id, plength, Nparams, x[lo:hi], _d(y)[lo:hi], N_global=len(x), bin_offset=lo,
-                   x_first=x[0], x_second=x[1], x_last=x[-1])
+                   x_first=x[0], x_second=x[1], x_last=x[-1], sigma_y=None if sigma_y is None else _d(sigma_y)[lo:hi])
 
     def struct(self):
         s = StarStruct()
@@ -159,6 +161,7 @@ class Star:
         s.N = len(self.x)
         s.N_global, s.bin_offset = self.N_global, self.bin_offset
         s.x_first, s.x_second, s.x_last = self.x_first, self.x_second, self.x_last
+        s.sigma_y = self.sigma_y.ctypes.data_as(_dp) if self.sigma_y is not None else None
         return s
 
 

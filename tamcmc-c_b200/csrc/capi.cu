@@ -110,7 +110,8 @@ struct tamcmc_gpu_ctx {
     unsigned int qcap = 0;
     int grid_ctas = 0;
     int max_tiles = 0;
-    double *d_x = nullptr, *d_y = nullptr, *d_lnx = nullptr;
+    double *d_x = nullptr, *d_y = nullptr, *d_lnx = nullptr, *d_wsig = nullptr;
+    int likelihood = 0;
     double* d_params = nullptr;
     unsigned char* d_active = nullptr;
     ModeRec* d_modes = nullptr;
@@ -187,7 +188,7 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, boo
 {
     WhittleArgs a;
     a.stars = c->d_stars;
-    a.x = c->d_x; a.y = c->d_y; a.lnx = c->d_lnx;
+    a.x = c->d_x; a.y = c->d_y; a.lnx = c->d_lnx; a.wsig = c->d_wsig; a.likelihood = c->likelihood;
     a.modes = c->d_modes; a.comps = c->d_comps; a.noise = c->d_noise;
     a.asym_flag = c->d_asym; a.Tcoefs = c->d_Tcoefs;
     a.queue = c->d_queue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec; a.pool = c->d_pool;
@@ -315,7 +316,7 @@ const char* tamcmc_gpu_strerror(int s)
     case TAMCMC_ERR_CUDA: return "CUDA error (no CPU fallback exists)";
     case TAMCMC_ERR_WINDOW: return "set_imin_imax: imax - imin <= 0 for some chain";
     case TAMCMC_ERR_NONFINITE: return "non-finite mode quantity for some chain";
-    case TAMCMC_ERR_LIKELIHOOD: return "likelihood id not on the GPU path";
+    case TAMCMC_ERR_LIKELIHOOD: return "likelihood id unknown (model_def.cpp:405-416)";
     case TAMCMC_ERR_POOL: return "component-list pool too small (TAMCMC_GPU_POOL_MB)";
     }
     return "unknown status";
@@ -327,7 +328,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     if (!out) return TAMCMC_ERR_ARG;
     *out = nullptr;
     if (nstars <= 0 || !stars || Nchains <= 0 || !Tcoefs) return TAMCMC_ERR_ARG;
-    if (likelihood_id != TAMCMC_LIKELIHOOD_CHI22P) return TAMCMC_ERR_LIKELIHOOD;
+    if (likelihood_id != TAMCMC_LIKELIHOOD_CHI22P && likelihood_id != TAMCMC_LIKELIHOOD_CHI_SQUARE) return TAMCMC_ERR_LIKELIHOOD;
     int ndev = 0;
     {
         cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -338,7 +339,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     { int rc = upload_tables(device); if (rc) return rc; }
 
     tamcmc_gpu_ctx* c = new tamcmc_gpu_ctx();
-    c->device = device; c->nstars = nstars; c->Nchains = Nchains; c->p = p;
+    c->device = device; c->nstars = nstars; c->Nchains = Nchains; c->p = p; c->likelihood = likelihood_id;
     if (const char* e = std::getenv("TAMCMC_GPU_NO_GRAPH")) c->use_graphs = !(e[0] == '1');
     if (const char* e = std::getenv("TAMCMC_GPU_PDL")) c->use_pdl = (e[0] == '1');
     c->h_stars.resize(nstars);
@@ -486,6 +487,16 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         CKC(cudaMemcpy(c->d_Tcoefs, Tcoefs, sizeof(double) * Nchains, cudaMemcpyHostToDevice));
         CKC(tamcmc_launch_lnx(c->d_x, c->d_lnx, off, c->stream));
         c->launches += 1;
+        if (likelihood_id == TAMCMC_LIKELIHOOD_CHI_SQUARE) {
+            // weights 1/sigma_y^2 (pad: 1); a missing sigma_y column means sigma = 1 (config.cpp:367-374)
+            std::vector<double> hs((size_t)off, 1.0);
+            for (int s = 0; s < nstars; s++)
+                if (stars[s].sigma_y) std::memcpy(&hs[(size_t)c->h_stars[s].off], stars[s].sigma_y, sizeof(double) * (size_t)c->h_stars[s].Nloc);
+            CKC(cudaMalloc(&c->d_wsig, sizeof(double) * off));
+            CKC(cudaMemcpy(c->d_wsig, hs.data(), sizeof(double) * off, cudaMemcpyHostToDevice));
+            CKC(tamcmc_launch_wsig(c->d_wsig, off, c->stream));
+            c->launches += 1;
+        }
         CKC(cudaStreamSynchronize(c->stream));
     }
 #undef CKC
@@ -498,7 +509,7 @@ void tamcmc_gpu_destroy(tamcmc_gpu_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_ready); cudaFree(c->d_epoch); cudaFree(c->d_tilerec); cudaFree(c->d_pool); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx);
+    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_ready); cudaFree(c->d_epoch); cudaFree(c->d_tilerec); cudaFree(c->d_pool); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx); cudaFree(c->d_wsig);
     cudaFree(c->d_params); cudaFree(c->d_active); cudaFree(c->d_modes); cudaFree(c->d_comps); cudaFree(c->d_noise);
     cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_out);
     cudaFree(c->d_model);

@@ -47,6 +47,7 @@ struct WhittleArgs {
     const double* x;                 // concatenated local bins, tile-padded
     const double* y;
     const double* lnx;
+    const double* wsig;              // chi_square likelihood: 1/sigma_y^2 per bin (same layout as x); nullptr for chi(2,2p)
     const ModeRec* modes;
     const CompRec* comps;
     const NoiseRec* noise;
@@ -73,6 +74,7 @@ struct WhittleArgs {
     double* host_logL; int* host_status; unsigned int* host_overflow; unsigned int* host_flag;
     const int* status;               // [nstars*Nchains] per-chain status written by the expand kernel
     int nsc;                         // nstars*Nchains
+    int likelihood;                  // 0: chi(2,2p)  S = sum(ln M + y/M);  1: chi_square  S = sum((y-M)^2/sigma^2)
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)
 };
 
@@ -83,6 +85,7 @@ cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t 
 cudaError_t tamcmc_whittle_configure(int* grid_ctas);   // one-time function attributes; returns the persistent grid size
 // pdl: programmatic dependent launch behind the expand kernel on the same stream
 cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st, bool pdl);
+cudaError_t tamcmc_launch_wsig(double* sigma_in_weights_out, long long n, cudaStream_t st);   // in place: w = 1/sigma^2
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st);
 // DFMA throughput microbenchmark: returns achieved FP64 TFLOP/s (2 flops per DFMA)
 cudaError_t tamcmc_fp64_peak(double* tflops, float* ms, int iters);

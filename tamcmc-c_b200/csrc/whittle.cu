@@ -491,6 +491,23 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
             // the finalize kernel takes one log per tile). ----------
             double s1 = 0.0, pm = 1.0;
             int pe = 0;
+            if (A.likelihood == 1) {
+                // chi_square (likelihoods.cpp:31-40): sum of (y - M)^2 / sigma_y^2; the weights 1/sigma^2 were formed once at create
+                const double* wg = A.wsig + sg.off;
+#pragma unroll
+                for (int pj = 0; pj < BPT / 2; pj++) {
+                    const double2 w = *reinterpret_cast<const double2*>(wg + 2 * tid + 2 * NC * pj);
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int j = 2 * pj + r;
+                        const int bb = 2 * tid + 2 * NC * pj + r;
+                        const double num = fma(bgv[j], D[j], N[j]);
+                        const double M = num / D[j];
+                        if (WRITE_MODEL) { if (bb < nvalid) A.model_out[lb0 + bb] = M; }
+                        if (bb < nvalid) { const double d = yv[j] - M; s1 = fma(d * d, r ? w.y : w.x, s1); }
+                    }
+                }
+            } else
 #pragma unroll
             for (int j = 0; j < BPT; j++) {
                 const int bb = 2 * tid + 2 * NC * (j >> 1) + (j & 1);
@@ -566,6 +583,7 @@ __device__ void finalize_chains(const WhittleArgs& A, int warp, int lane, int nw
         for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
         if (lane == 0) {
             if (A.raw_sum) A.out[sc] = acc;
+            else if (A.likelihood == 1) A.out[sc] = ((-acc) / 2) / A.Tcoefs[sc % A.Nchains];        // likelihoods.cpp:36-37, model_def.cpp:405
             else {
                 const double pl = (double)(long long)A.p;
                 A.out[sc] = (-pl * acc) / A.Tcoefs[sc % A.Nchains];
@@ -626,6 +644,12 @@ __global__ void tamcmc_lnx_kernel(const double* __restrict__ x, double* __restri
     if (i < n) lnx[i] = log(x[i]);
 }
 
+__global__ void tamcmc_wsig_kernel(const double* __restrict__ sig, double* __restrict__ w, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = 1.0 / (sig[i] * sig[i]);          // sigma.array().square().cwiseInverse(), likelihoods.cpp:36
+}
+
 // ---- DFMA roofline microbenchmark: 8 independent FMA chains per thread ----
 __global__ void __launch_bounds__(256) tamcmc_dfma_kernel(double* out, int iters, double seed)
 {
@@ -683,6 +707,13 @@ cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStr
 {
     if (n <= 0) return cudaSuccess;
     tamcmc_lnx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, lnx, n);
+    return cudaGetLastError();
+}
+
+cudaError_t tamcmc_launch_wsig(double* w_inout, long long n, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    tamcmc_wsig_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w_inout, w_inout, n);
     return cudaGetLastError();
 }
 

@@ -44,6 +44,7 @@ struct StarData {
     std::vector<int> plength;           // 11 entries (io_ms_global.cpp:1315-1325)
     int Nparams;
     std::vector<double> x, y;
+    std::vector<double> sigma_y;        // Data.sigma_y, only read by the chi_square likelihood; empty = ones (config.cpp:367-374)
 };
 
 class ModelDefGPU {
@@ -70,6 +71,7 @@ public:
             for (int k = 0; k < 11; k++) s[i].plength[k] = stars[i].plength[k];
             s[i].Nparams = stars[i].Nparams;
             s[i].x = stars[i].x.data(); s[i].y = stars[i].y.data(); s[i].N = (long)stars[i].x.size();
+            s[i].sigma_y = (stars[i].sigma_y.size() == stars[i].x.size()) ? stars[i].sigma_y.data() : nullptr;
             Nx.push_back((long)stars[i].x.size());
             Nparams_of.push_back(stars[i].Nparams);
         }

@@ -77,6 +77,8 @@ class Oracle:
         L.orc_call_model.argtypes = [C.c_int, _dp, _ip, _dp, C.c_long, _dp, self._alm_t, C.c_void_p]
         L.orc_eval_chains.restype = C.c_int
         L.orc_eval_chains.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _dp, C.c_long, C.c_int, _dp, C.c_double, _dp, C.c_int]
+        L.orc_eval_chains_chi_square.restype = C.c_int
+        L.orc_eval_chains_chi_square.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _dp, _dp, C.c_long, C.c_int, _dp, _dp, C.c_int]
         L.orc_mode_table_model.restype = C.c_int
         L.orc_mode_table_model.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_long, _dp]
         L.orc_mode_table_eval_chains.restype = C.c_int
@@ -129,6 +131,16 @@ class Oracle:
         if trace:
             n = self.L.orc_trace_end()
             return rc, out, (tl[:n].copy(), t0[:n].copy(), t1[:n].copy())
+        return rc, out
+
+    def eval_chains_chi_square(self, model_id, params, plength, x, y, sigma, Tcoefs, nthreads=0):
+        params = _as_d(params)
+        Nchains, Nparams = params.shape
+        x, y, sigma, T = _as_d(x), _as_d(y), _as_d(sigma), _as_d(Tcoefs)
+        pl = np.ascontiguousarray(plength, dtype=np.int32)
+        out = np.zeros(Nchains)
+        rc = self.L.orc_eval_chains_chi_square(model_id, _p(params), Nparams, pl.ctypes.data_as(_ip), _p(x), _p(y), _p(sigma), len(x),
+                                               Nchains, _p(T), _p(out), int(nthreads))
         return rc, out
 
     def mode_table_model(self, row, Nnoise, step_mode, x, trace=False):

@@ -29,14 +29,14 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_abi_version_and_strerror(pkg):
     L = pkg.lib()
-    assert L.tamcmc_gpu_abi_version() == 1
+    assert L.tamcmc_gpu_abi_version() == 2
     for rc in range(7):
         assert len(L.tamcmc_gpu_strerror(rc)) > 0
 
 
 def test_struct_layout_matches_header(pkg):
-    # tamcmc_gpu_star: int, int[11], int, 2 pointers, 3 longs, 3 doubles (LP64)
-    assert C.sizeof(pkg.StarStruct) == 4 + 44 + 4 + 4 + 8 * 2 + 8 * 3 + 8 * 3
+    # tamcmc_gpu_star: int, int[11], int, 2 pointers, 3 longs, 3 doubles, 1 pointer (LP64)
+    assert C.sizeof(pkg.StarStruct) == 4 + 44 + 4 + 4 + 8 * 2 + 8 * 3 + 8 * 3 + 8
 
 
 def test_argument_validation_without_device(pkg):

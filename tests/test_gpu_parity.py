@@ -165,7 +165,7 @@ def test_unknown_model_and_bad_sizes(pkg):
         pkg.Context(pkg.Star(3, pl, len(params) - 5, x, np.ones_like(x)), 1, [1.0])
     assert ei.value.status == pkg.ERR_ARG
     with pytest.raises(pkg.TamcmcError) as ei:
-        pkg.Context(pkg.Star(3, pl, len(params), x, np.ones_like(x)), 1, [1.0], likelihood_id=1)
+        pkg.Context(pkg.Star(3, pl, len(params), x, np.ones_like(x)), 1, [1.0], likelihood_id=2)
     assert ei.value.status == pkg.ERR_LIKELIHOOD
 
 
@@ -280,3 +280,27 @@ def test_full_size_properties(pkg):
             cs.sync()
             S += dS.cpu().numpy()
     assert np.allclose(-S / T, L[0], rtol=1e-13, atol=0)
+
+
+def test_chi_square_likelihood(pkg, oracle):
+    """likelihood_chi_square (likelihoods.cpp:31-40, likelihoods_ctrl.list id 1): -sum((y-M)^2/sigma_y^2)/2, tempered like
+    model_def.cpp:405; a missing sigma_y means ones (config.cpp:367-374)."""
+    for model_id, seed in ((3, 21), (23, 22)):
+        params, pl, x = _cases.ms_case(pkg.synth, model_id, seed=seed, N=25000, asym=0.0 if seed % 2 else 8.0)
+        rc, M = oracle.call_model(model_id, params, pl, x)
+        assert rc == 0
+        rng = np.random.default_rng(seed)
+        sigma = rng.uniform(0.3, 2.0, len(x)) * np.sqrt(M)
+        y = M + sigma * rng.standard_normal(len(x))
+        P = pkg.synth.perturb_chains(rng, params, pl, 3)
+        T = pkg.synth.tcoefs(3, 1.7)
+        for sig in (sigma, None):
+            rc, L_ref = oracle.eval_chains_chi_square(model_id, P, pl, x, y, sigma if sig is not None else np.ones(len(x)), T)
+            assert rc == 0
+            star = pkg.Star(model_id, pl, len(params), x, y, sigma_y=sig)
+            with pkg.Context(star, 3, T, likelihood_id=1) as ctx:
+                L, st = ctx.eval(P)
+                assert (st == 0).all()
+                assert np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)) < RTOL
+                L2, _ = ctx.eval(P)
+                assert np.array_equal(L, L2)

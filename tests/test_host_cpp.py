@@ -17,7 +17,8 @@ LIBDIR = os.path.join(ROOT, "tamcmc-c_b200")
 def _build():
     src = os.path.join(HERE, "cpp", "test_model_def_gpu.cpp")
     hdr = os.path.join(LIBDIR, "host", "model_def_gpu.hpp")
-    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    abi = os.path.join(ROOT, "include", "tamcmc_gpu.h")
+    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(abi)):
         return EXE
     cuda_lib = "/usr/local/cuda/lib64"
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", EXE, src, "-L" + LIBDIR, "-ltamcmc_gpu",
@@ -32,7 +33,8 @@ def _build_driver():
     import _oracle
     _oracle.build()
     odir = os.path.join(ROOT, "oracle", "_ref")
-    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    abi = os.path.join(ROOT, "include", "tamcmc_gpu.h")
+    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(abi)):
         return exe
     cuda_lib = "/usr/local/cuda/lib64"
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, src, "-L" + LIBDIR, "-ltamcmc_gpu", "-L" + odir, "-ltamcmc_oracle",
