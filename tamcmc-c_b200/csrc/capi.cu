@@ -101,10 +101,7 @@ struct tamcmc_gpu_ctx {
     StarDesc* d_stars = nullptr;
     unsigned int* d_queue = nullptr;
     TileRec* d_tilerec = nullptr;
-    unsigned int* d_ready = nullptr;
     unsigned int* d_epoch = nullptr;
-    unsigned char* d_pool = nullptr;
-    unsigned long long pool_bytes = 0;
     unsigned long long* d_trace = nullptr;   // profiling aid (TAMCMC_TRACE builds)
     QueueCtl* d_qctl = nullptr;
     unsigned int qcap = 0;
@@ -139,6 +136,7 @@ struct tamcmc_gpu_ctx {
     struct GraphEntry { const double* p; const unsigned char* a; double* o; int raw; cudaGraphExec_t exec; };
     GraphEntry graphs[4] = {};
     int ngraphs = 0;
+    int look = 2, look_end = 1;       // producer look-ahead (TAMCMC_GPU_LOOK / TAMCMC_GPU_LOOK_END = 1 or 2; tuning aid)
     bool use_graphs = true;
     bool use_pdl = false;            // programmatic dependent launch expand -> fused kernel: measured no gain inside a CUDA graph
                                      // (profiles/r1/NOTES.md); TAMCMC_GPU_PDL=1 enables it
@@ -175,15 +173,6 @@ ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const uns
     return a;
 }
 
-TileListArgs make_tilelist_args(tamcmc_gpu_ctx* c)
-{
-    TileListArgs a;
-    a.stars = c->d_stars; a.modes = c->d_modes; a.comps = c->d_comps; a.asym_flag = c->d_asym;
-    a.queue = c->d_queue; a.qctl = c->d_qctl; a.tilerec = c->d_tilerec; a.pool = c->d_pool; a.pool_bytes = c->pool_bytes;
-    a.qcap = c->qcap; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
-    return a;
-}
-
 WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, bool mirror)
 {
     WhittleArgs a;
@@ -191,12 +180,13 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, boo
     a.x = c->d_x; a.y = c->d_y; a.lnx = c->d_lnx; a.wsig = c->d_wsig; a.likelihood = c->likelihood;
     a.modes = c->d_modes; a.comps = c->d_comps; a.noise = c->d_noise;
     a.asym_flag = c->d_asym; a.Tcoefs = c->d_Tcoefs;
-    a.queue = c->d_queue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec; a.pool = c->d_pool;
+    a.queue = c->d_queue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec;
     a.partial = c->d_partial;
     a.out = d_out; a.model_out = c->d_model;
     a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
     a.raw_sum = raw_sum; a.trace = c->d_trace;
-    a.tl = make_tilelist_args(c); a.ready = c->d_ready; a.epoch = c->d_epoch;
+    a.epoch = c->d_epoch;
+    a.look = c->look; a.look_end = c->look_end;
     a.status = c->d_status(); a.nsc = c->SC();
     // the host mirror costs a system-scope fence at the end of the launch: only the host-buffer entry point asks for it
     a.host_logL = mirror ? c->dm_logL : nullptr; a.host_status = mirror ? c->dm_status : nullptr;
@@ -342,6 +332,8 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     c->device = device; c->nstars = nstars; c->Nchains = Nchains; c->p = p; c->likelihood = likelihood_id;
     if (const char* e = std::getenv("TAMCMC_GPU_NO_GRAPH")) c->use_graphs = !(e[0] == '1');
     if (const char* e = std::getenv("TAMCMC_GPU_PDL")) c->use_pdl = (e[0] == '1');
+    if (const char* e = std::getenv("TAMCMC_GPU_LOOK")) c->look = (e[0] == '1') ? 1 : 2;
+    if (const char* e = std::getenv("TAMCMC_GPU_LOOK_END")) c->look_end = (e[0] == '1') ? 1 : 2;
     c->h_stars.resize(nstars);
     long long off = 0; int tiles = 0; int maxN = 0;
     for (int s = 0; s < nstars; s++) {
@@ -411,27 +403,9 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     c->qcap = (unsigned int)((size_t)SC * (size_t)c->tiles_stride);
     CKC(cudaMalloc(&c->d_queue, sizeof(unsigned int) * TAMCMC_NBUCKETS * (size_t)c->qcap));
     CKC(cudaMalloc(&c->d_qctl, sizeof(QueueCtl)));
-    CKC(cudaMalloc(&c->d_ready, sizeof(unsigned int) * TAMCMC_NBUCKETS * (size_t)c->qcap));
-    CKC(cudaMemset(c->d_ready, 0, sizeof(unsigned int) * TAMCMC_NBUCKETS * (size_t)c->qcap));
     CKC(cudaMalloc(&c->d_epoch, sizeof(unsigned int)));
     { const unsigned int one = 1u; CKC(cudaMemcpy(c->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice)); }
     CKC(cudaMalloc(&c->d_tilerec, sizeof(TileRec) * (size_t)c->qcap));
-    {
-        // list pool: worst case = every component of every mode listed (as a general entry) in every tile;
-        // capped, because typical lists are ~50x smaller.  TAMCMC_GPU_POOL_MB overrides the size.
-        unsigned long long worst = 0;
-        for (int s = 0; s < nstars; s++) {
-            const StarDesc& sd = c->h_stars[s];
-            const unsigned long long per_tile = (unsigned long long)sd.nmodes_cap * (TAMCMC_MAX_COMP_PER_MODE * 64ull + 32ull + 16ull) + 256ull;
-            worst += (unsigned long long)Nchains * (unsigned long long)sd.ntiles * per_tile;
-        }
-        unsigned long long cap = 64ull << 20;
-        const unsigned long long typical = 12288ull * (unsigned long long)c->qcap;
-        if (typical > cap) cap = typical;
-        if (const char* e = std::getenv("TAMCMC_GPU_POOL_MB")) { const long mb = std::atol(e); if (mb > 0) cap = (unsigned long long)mb << 20; }
-        c->pool_bytes = worst < cap ? worst : cap;
-        CKC(cudaMalloc(&c->d_pool, c->pool_bytes));
-    }
 #ifdef TAMCMC_TRACE
     CKC(cudaMalloc(&c->d_trace, sizeof(unsigned long long) * 64 * 4096));
     CKC(cudaMemset(c->d_trace, 0, sizeof(unsigned long long) * 64 * 4096));
@@ -509,7 +483,7 @@ void tamcmc_gpu_destroy(tamcmc_gpu_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_ready); cudaFree(c->d_epoch); cudaFree(c->d_tilerec); cudaFree(c->d_pool); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx); cudaFree(c->d_wsig);
+    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_epoch); cudaFree(c->d_tilerec); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx); cudaFree(c->d_wsig);
     cudaFree(c->d_params); cudaFree(c->d_active); cudaFree(c->d_modes); cudaFree(c->d_comps); cudaFree(c->d_noise);
     cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_out);
     cudaFree(c->d_model);
@@ -572,18 +546,12 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char
         }
         { int rc = launch_eval(c, c->d_params, d_act, c->d_logL(), 0, c->stream); if (rc) return rc; }
         CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(c->h_qctl, c->d_qctl, sizeof(QueueCtl), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         { int rc = collect_profile(c); if (rc) return rc; }
         std::memcpy(logL_out, c->h_out, sizeof(double) * (size_t)SC);
         st = reinterpret_cast<const int*>(reinterpret_cast<const double*>(c->h_out) + SC);
-        overflow = c->h_qctl->overflow;
     }
-    if (overflow) {
-        g_last_error = "component-list pool overflow: raise TAMCMC_GPU_POOL_MB";
-        reset_queue(c);                     // `overflow` is sticky on the device until the host has seen it
-        return TAMCMC_ERR_POOL;
-    }
+    (void)overflow;
     if (status_out) std::memcpy(status_out, st, sizeof(int) * (size_t)SC);
     c->pairs_last = -1;
     return status_to_rc(st, SC);

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     __shared__ double slot_A[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
     __shared__ int s_red[EXP_THREADS / 32];
     __shared__ unsigned int s_bcnt[TAMCMC_NBUCKETS], s_bbase[TAMCMC_NBUCKETS];
-    static_assert(TAMCMC_NBUCKETS == 4, "tile class is packed into 2 bits");
+    static_assert(TAMCMC_NBUCKETS == (1 << TAMCMC_NBUCKETS_LOG2), "tile class is packed into the low bits");
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int* pl = sd.plength;
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         __syncthreads();
         mx = 0;
         for (int w = 0; w < EXP_THREADS / 32; w++) mx = max(mx, s_red[w]);
-        // cost class of every tile (quarters of the chain's heaviest tile, heaviest first) and its rank inside the class,
+        // cost class of every tile (sixteenths of the chain's heaviest tile, heaviest first) and its rank inside the class,
         // counted in shared memory; then ONE global atomic per class reserves the chain's slots in the queue
         if (tid < TAMCMC_NBUCKETS) s_bcnt[tid] = 0u;
         __syncthreads();
@@ -701,10 +701,10 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         for (int r = 0; r < rounds; r++) {
             const int t = r * blockDim.x + tid;
             if (t < ntiles) {
-                const int q = (4 * (tcost[t] - TILE_BASE_COST)) / max(mx - TILE_BASE_COST, 1);
+                const int q = (TAMCMC_NBUCKETS * (tcost[t] - TILE_BASE_COST)) / max(mx - TILE_BASE_COST, 1);
                 const int cls = min(max(TAMCMC_NBUCKETS - 1 - q, 0), TAMCMC_NBUCKETS - 1);
                 const unsigned rank = atomicAdd(&s_bcnt[cls], 1u);
-                tcost[t] = (int)((rank << 2) | (unsigned)cls);          // ntiles <= 16384: rank fits
+                tcost[t] = (int)((rank << TAMCMC_NBUCKETS_LOG2) | (unsigned)cls);          // ntiles <= 16384: rank fits
             }
         }
         __syncthreads();
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         for (int r = 0; r < rounds; r++) {
             const int t = r * blockDim.x + tid;
             if (t < ntiles) {
-                const unsigned v = (unsigned)tcost[t], cls = v & 3u, rank = v >> 2;
+                const unsigned v = (unsigned)tcost[t], cls = v & (TAMCMC_NBUCKETS - 1u), rank = v >> TAMCMC_NBUCKETS_LOG2;
                 A.queue[(size_t)cls * A.qcap + s_bbase[cls] + rank] = (unsigned)sc * (unsigned)A.tiles_stride + (unsigned)t;
             }
         }

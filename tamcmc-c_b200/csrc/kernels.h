@@ -27,21 +27,6 @@ struct ExpandArgs {
     unsigned long long* trace;       // profiling aid (TAMCMC_TRACE builds)
 };
 
-struct TileListArgs {
-    const StarDesc* stars;
-    const ModeRec* modes;
-    const CompRec* comps;
-    const int* asym_flag;
-    const unsigned int* queue;
-    QueueCtl* qctl;
-    TileRec* tilerec;
-    unsigned char* pool;
-    unsigned long long pool_bytes;
-    unsigned int qcap;
-    int Nchains;
-    int modes_stride;
-    int tiles_stride;
-};
 struct WhittleArgs {
     const StarDesc* stars;
     const double* x;                 // concatenated local bins, tile-padded
@@ -55,7 +40,6 @@ struct WhittleArgs {
     const double* Tcoefs;            // [Nchains]
     const unsigned int* queue;
     const TileRec* tilerec;
-    const unsigned char* pool;
     QueueCtl* qctl;
     unsigned int qcap;
     double* partial;                 // [nstars*Nchains][tiles_stride][3]: sum y/M, mantissa and exponent of prod 1/M
@@ -66,14 +50,14 @@ struct WhittleArgs {
     int modes_stride;
     int tiles_stride;
     unsigned long long* trace;       // profiling aid (builds with -DTAMCMC_TRACE): [grid][64] globaltimer stamps
-    TileListArgs tl;                 // builder warps: inputs of the per-tile list construction
-    unsigned int* ready;             // [qcap * NBUCKETS] per queue position: == epoch once the item's lists are built
-    unsigned int* epoch;             // device launch counter (never 0); bumped by the last CTA of the fused kernel
+    unsigned int* epoch;             // device launch counter (never 0), bumped by the last CTA of the fused kernel: the value
+                                     // the host-mirror flag publishes
     // host mirror (mapped pinned memory, device addresses; null = none): the last CTA copies the results there and then
     // publishes the new epoch value in *host_flag, so the host can pick them up without a D2H copy or a stream sync
     double* host_logL; int* host_status; unsigned int* host_overflow; unsigned int* host_flag;
     const int* status;               // [nstars*Nchains] per-chain status written by the expand kernel
     int nsc;                         // nstars*Nchains
+    int look, look_end;              // producer look-ahead in tiles (1 or 2): steady state / last ~4 items per CTA
     int likelihood;                  // 0: chi(2,2p)  S = sum(ln M + y/M);  1: chi_square  S = sum((y-M)^2/sigma^2)
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)
 };

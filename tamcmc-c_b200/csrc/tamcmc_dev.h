@@ -6,7 +6,7 @@
 //   params           : [nstars][Nchains][Nparams_max] FP64, row-major (uploaded every step)
 //   modes / comps    : [nstars][Nchains][max_modes] ModeRec, [..][max_modes*7] CompRec
 //   noise            : [nstars][Nchains] NoiseRec
-//   queue            : [2][nstars*Nchains*max_tiles] uint32 work items (heavy tiles, light tiles)
+//   queue            : [16][nstars*Nchains*max_tiles] uint32 work items in 16 cost classes, heaviest first
 //   partial          : [nstars][Nchains][max_tiles] FP64 per-tile partial sums
 //   out              : [nstars*Nchains] FP64 logL followed by [nstars*Nchains] int32 status
 #pragma once
@@ -17,8 +17,8 @@
 #define TAMCMC_BG_TERMS 10           // Taylor coefficients of the Harvey background per tile
 #define TAMCMC_TILE 1536             // bins per tile
 #define TAMCMC_CONSUMERS 384         // consumer threads per CTA (4 bins per thread); ONE persistent CTA per SM
-#define TAMCMC_BUILDERS 3            // list-builder warps per CTA of the fused kernel
-#define TAMCMC_THREADS (TAMCMC_CONSUMERS + 32 + 32 * TAMCMC_BUILDERS)   // + one TMA producer warp + builders
+#define TAMCMC_PRODUCERS 4           // producer warps per CTA = slots of the shared-memory ring
+#define TAMCMC_THREADS (TAMCMC_CONSUMERS + 32 * TAMCMC_PRODUCERS)
 #define TAMCMC_BINS_PER_THREAD (TAMCMC_TILE / TAMCMC_CONSUMERS)
 #define TAMCMC_MAX_TILES 16384       // tiles per star the expander's cost scan supports (16.7M bins)
 #ifndef TAMCMC_MIN_CTAS
@@ -91,7 +91,7 @@ struct StarDesc {
     double step;         // x[1]-x[0] (MS models, models.cpp:1952) or x[2]-x[1] (RGB v4, models.cpp:4714)
 };
 
-// ---- per-tile component lists (built by the tile-list kernel, streamed by TMA into the fused kernel) ----
+// ---- per-tile component lists (built by the producer warps of the fused kernel in their ring slots) ----
 #define TAMCMC_CAPF 352              // fast entries per shared-memory segment
 #define TAMCMC_CAPH 64               // mode headers per segment (asymmetric profiles)
 #define TAMCMC_CAPG 24               // general entries per segment
@@ -99,25 +99,18 @@ struct StarDesc {
 struct __align__(16) FastEntry { double s, c, a, pad; };                 // e' = fma(u, s, c); t' = fma(e', e', a)
 struct __align__(16) ModeHdr { double qa, qb, qc; int begin, count; };   // asym fast path: q(u) and its fast entries
 struct __align__(16) GenEntry { double s, c, aadd, num, qa, qb, qc; int lo, hi; };
-struct __align__(16) SegDesc { int f0, nf, h0, nh, g0, ng, wide, pad1; }; // slices of the tile's three arrays; wide: see ModeRec.nfast
 
-// per (star, chain, tile) record: background series from the background CTAs of the expand launch, list
-// descriptor from the tile-list kernel.  The tile's lists live in the pool at pool_off:
-//   FastEntry fast[TF] | ModeHdr hdr[TH] | GenEntry gen[TG] | SegDesc seg[nseg_cap]
+// per (star, chain, tile) record, written by the background CTAs of the expand launch
 struct __align__(16) TileRec {
     double bg[TAMCMC_BG_TERMS];   // Taylor coefficients in u = x - xc of sum_h H_h/(1+(tau_h x)^p_h)
     double xc;                    // tile-local origin x[tile centre]
     double umax;                  // max |x - xc| over the tile
-    unsigned long long pool_off;  // byte offset of the tile's lists in the pool
     int series_ok;                // 0: the tile must evaluate the background exactly per bin
-    int nseg;                     // segments (1 unless a list exceeds the shared-memory capacities)
-    int TF, TH, TG;               // total entries of the three arrays
-    int s0_nf, s0_nh, s0_ng;      // first segment (f0 = h0 = g0 = 0)
-    int s0_wide;
+    int pad[3];
 };
 
 // work queue header: count[k] items in cost bucket k (k = 0 heaviest), head = pop cursor
-#define TAMCMC_NBUCKETS 4            // work-queue cost classes, heaviest first
-// Zero between evaluations: the last CTA of the fused kernel to finish resets every field but `overflow` (sticky until
-// the host has seen it).
-struct QueueCtl { unsigned int count[TAMCMC_NBUCKETS]; unsigned int head; unsigned int overflow; unsigned long long pool_cursor; unsigned int ctas_done; unsigned int pad; };
+#define TAMCMC_NBUCKETS 16           // work-queue cost classes, heaviest first (fine classes = near-sorted pops = short tail)
+#define TAMCMC_NBUCKETS_LOG2 4
+// Zero between evaluations: the last CTA of the fused kernel to finish resets it.
+struct QueueCtl { unsigned int count[TAMCMC_NBUCKETS]; unsigned int head; unsigned int ctas_done; unsigned int pad[2]; };

@@ -1,29 +1,27 @@
 // whittle.cu -- fused power-spectrum model + Whittle chi^2(2 dof) log-likelihood (sm_100a, FP64).
 //
-// Persistent, warp-specialised kernel.  Each CTA has one PRODUCER warp and 8 CONSUMER warps:
+// Persistent, warp-specialised kernel.  Each CTA has 4 PRODUCER warps and 12 CONSUMER warps:
 //
-//  * the producer pops (star, chain, tile) work items from the heavy-first queue the expander built,
-//    classifies the chain's modes against the tile, writes the tile-local component list into one of two
-//    shared-memory segments, builds the Taylor series of the Harvey background for the tile, and fetches the
-//    tile's x and y (2 x 8 KB) with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) -- all one tile
-//    ahead of the consumers, synchronised with full/empty mbarriers;
-//  * the 256 consumer threads own 4 bins each.  The model spectrum M never exists in HBM: every thread keeps
-//    the running Lorentzian sum of a bin as ONE fraction N/D,
+//  * every producer warp owns ONE slot of the shared-memory ring.  It pops a (star, chain, tile) work item from the
+//    heaviest-first queue the expander built, classifies the chain's modes against the tile (bit-exact windows from
+//    the expander) and writes the tile-local component list straight into its slot: window covers the tile ->
+//    mask-free FastEntry, window edge or extreme dynamic range -> GenEntry with [lo,hi); it fetches the tile's x and
+//    y (2 x 12 KB) with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) and publishes the slot on its
+//    `full` mbarrier.  Four producers overlap the global-memory latency of four tiles; a list that exceeds the
+//    slot's capacities is streamed through the same slot as several segments;
+//  * the 384 consumer threads own 4 bins each and take the slots round-robin, one tile at a time.  The model
+//    spectrum M never exists in HBM: every thread keeps the running Lorentzian sum of a bin as ONE fraction N/D,
 //        sum_k A_k / (1 + 4 (x - nu_k)^2 / Gamma_k^2)  =  N / D ,
 //    merging a component with 2 FMAs for its scaled denominator t' = (1 + e^2)/A_k and 1 FMA + 1 MUL for
 //    (N, D) <- (N t' + D, D t').  That replaces the reference's FP64 divide per (component, bin)
-//    (build_lorentzian.cpp:151: cwiseInverse) by 4 FP64-pipe instructions, with one divide per bin at the
+//    (build_lorentzian.cpp:151: cwiseInverse) by 4 FP64-pipe instructions, with one reciprocal per bin at the
 //    end.  Exponents of (N, D) are renormalised with 4 integer ops per bin every 16 components.  The background
 //    (noise_models.cpp:15-39) is a 9th-degree polynomial per tile (or exact exp() per bin near x = 0), the
 //    Whittle terms y/M + ln M (likelihoods.cpp:23) are reduced in registers, by warp shuffles and a
-//    fixed-shape block tree; the last CTA to finish a chain sums its per-tile partials in index order, so
-//    results are bitwise reproducible run to run whatever the scheduling.
-//
-// Mode windows (ModeRec.i0/i1) come bit-exact from the expander; a mode whose window covers the whole tile
-// takes the mask-free fast path, a mode that only partly overlaps it takes the masked general path.
+//    fixed-shape block tree into one partial per tile; the last CTA to finish sums the per-tile partials of every
+//    chain in tile order, so results are bitwise reproducible run to run whatever the scheduling.
 #include "tamcmc_dev.h"
 #include "kernels.h"
-#include "tilelist_body.cuh"
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -39,9 +37,10 @@ constexpr int NB = TAMCMC_BG_TERMS;
 constexpr int CAPF = TAMCMC_CAPF;                          // fast entries per segment
 constexpr int CAPG = TAMCMC_CAPG;                          // general entries per segment
 constexpr int CAPH = TAMCMC_CAPH;                          // mode headers per segment (asym fast path)
-constexpr int NBUF = 4;                                    // segment ring depth
+constexpr int NBUF = 4;                                    // ring slots = producer warps
+constexpr int NPROD = NBUF;
 
-enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_POISON = 32, SEG_WIDE = 64 };
+enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_WIDE = 64 };
 
 struct __align__(16) Segment {
     double x[TILE];          // TMA destinations: spectrum tile (first segment of a tile) ...
@@ -63,6 +62,8 @@ struct Smem {
     double red_m[NBUF][NC / 32];
     int red_e[NBUF][NC / 32];
     unsigned int cnt[NBUF];
+    volatile int cons_cur;            // slot the consumers are working on (-1 before the first tile)
+    unsigned int done_mask;           // producers that have drained the queue
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -121,41 +122,23 @@ __device__ __forceinline__ void renorm(double& N, double& D)
     N = __hiloint2double(__double2hiint(N) - k, __double2loint(N));
 }
 
-// Pop order -> position in the (heaviest-first) queue.  The first gridDim.x pops take the LIGHTEST items (from the
-// end of the queue): their lists are the quickest to build, so every CTA's consumers have work while the
-// builders prepare the heavy tiles; afterwards items go heaviest-first, which keeps the tail short.
-__device__ __forceinline__ unsigned pop_to_pos(unsigned idx, unsigned ntot)
+// ------------------------------------------------------------------------------------------------
+// producer warps
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_sum(int v)
 {
-    const unsigned g = min((unsigned)gridDim.x, ntot);
-    return (idx < g) ? (ntot - 1u - idx) : (idx - g);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ int warp_excl_scan(int v, int lane)
+{
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += o; }
+    return x - v;
 }
 
-// ------------------------------------------------------------------------------------------------
-// builder warps: the lists of queue position q are built by builder (q mod total builders); heaviest tiles
-// first, so consumers start after one list-build latency and the rest hides behind the arithmetic.  Builders
-// never wait; the producer spins on ready[q] (all CTAs of the persistent grid are co-resident).
-// ------------------------------------------------------------------------------------------------
-__device__ void builder_loop(const WhittleArgs& A, int builder, int lane)
-{
-    unsigned cum[TAMCMC_NBUCKETS + 1];
-    cum[0] = 0;
-    for (int k = 0; k < TAMCMC_NBUCKETS; k++) cum[k + 1] = cum[k] + A.qctl->count[k];
-    const unsigned ntot = cum[TAMCMC_NBUCKETS];
-    const unsigned stride = gridDim.x * TAMCMC_BUILDERS;
-    const unsigned epoch = *A.epoch;
-    for (unsigned q = blockIdx.x * TAMCMC_BUILDERS + builder; q < ntot; q += stride) {
-        const unsigned pos = pop_to_pos(q, ntot);
-        int bucket = 0;
-        while (pos >= cum[bucket + 1]) bucket++;
-        tamcmc_tl::build_tile_lists(A.tl, A.queue[(size_t)bucket * A.qcap + (pos - cum[bucket])], lane);
-        __syncwarp();
-        if (lane == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.ready + q), "r"(epoch) : "memory"); }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// producer warp: pops work items and streams their data into the segment ring with TMA bulk copies
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned pop_item(const WhittleArgs& A, int lane)
 {
     unsigned idx = 0;
@@ -163,97 +146,183 @@ __device__ __forceinline__ unsigned pop_item(const WhittleArgs& A, int lane)
     return __shfl_sync(0xffffffffu, idx, 0);
 }
 
-__device__ void producer_loop(const WhittleArgs& A, Smem& sm, int lane)
+// first slot after `c` (cyclically) whose producer has not drained the queue; `w` itself is never in the mask
+__device__ __forceinline__ int next_live(int c, unsigned done_mask)
 {
-    unsigned use[NBUF];               // how many times each segment buffer has been filled
-    for (int i = 0; i < NBUF; i++) use[i] = 0;
-    int b = 0;
-    unsigned cum[TAMCMC_NBUCKETS + 1];
-    cum[0] = 0;
-    for (int k = 0; k < TAMCMC_NBUCKETS; k++) cum[k + 1] = cum[k] + A.qctl->count[k];
-    const unsigned ntot = cum[TAMCMC_NBUCKETS];
-    const unsigned epoch = *A.epoch;
-    // Look-ahead: normally the producer runs up to NBUF-1 segments ahead of the consumers and pops the next queue index
-    // while it still processes the current one.  In the END GAME (the last ~2 items per CTA) it holds at most one tile
-    // in flight beyond the one being consumed and pops late, so that the few remaining (light) items go to the CTAs
-    // that are actually free: that keeps the tail of the persistent grid short.
-    const unsigned endgame_from = (ntot > 2u * gridDim.x) ? ntot - 2u * gridDim.x : 0u;
-    unsigned idx = pop_item(A, lane);
-    bool have = true;
-    int h1_b = 0, h2_b = 0;               // buffers of the last and second-to-last fills and their use counts
-    unsigned h1_use = 0, h2_use = 0;
+    int n = (c + 1) % NBUF;
+#pragma unroll
+    for (int k = 0; k < NBUF; k++) { if (!((done_mask >> n) & 1u)) break; n = (n + 1) % NBUF; }
+    return n;
+}
+
+__device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
+{
+    // lane k < NBUCKETS keeps the inclusive prefix sum of the cost-class counts: item idx lives in the class whose
+    // prefix first exceeds it
+    static_assert(TAMCMC_NBUCKETS <= 32, "one lane per cost class");
+    unsigned cum_inc = (lane < TAMCMC_NBUCKETS) ? A.qctl->count[lane] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, cum_inc, d); if (lane >= d) cum_inc += o; }
+    const unsigned ntot = __shfl_sync(0xffffffffu, cum_inc, 31);
+    // Work distribution.  The queue is sorted heaviest-first (16 cost classes).
+    //  * first item of every producer: STATIC, in snake order over the 4 x gridDim heaviest items (producer w of CTA k
+    //    takes w*grid + k for even w, w*grid + grid-1-k for odd w), so every CTA starts with the same total weight;
+    //  * afterwards: dynamic pops, but a producer pops only while its slot is among the next LOOK live slots after the
+    //    one the consumers work on (LOOK = 2, 1 for the last ~4 items per CTA): items are claimed late, by the CTAs
+    //    that are actually ahead, which is what keeps the tail of the persistent grid short.
+    const unsigned G = gridDim.x;
+    const unsigned nstatic = (unsigned)NPROD * G;
+    const unsigned endgame_from = (ntot > 4u * G) ? ntot - 4u * G : 0u;
+    Segment* const sg = &sm.seg[w];
+    unsigned long long* const full = &sm.full[w];
+    unsigned long long* const empty = &sm.empty[w];
+    unsigned use = 0;                 // segments published in this slot so far
+    bool first_item = true;
+    unsigned last_idx = 0;
     for (;;) {
-        if (!have) {
-            if (h2_use) mbar_wait(&sm.empty[h2_b], (h2_use - 1) & 1);      // the segment filled two fills ago is released
-            idx = pop_item(A, lane);
+        unsigned idx;
+        if (first_item) {
+            idx = (unsigned)w * G + ((w & 1) ? (G - 1u - blockIdx.x) : blockIdx.x);
+            first_item = false;
+        } else {
+            if (use) mbar_wait(empty, (use - 1) & 1);          // claim nothing while this slot still holds a tile
+            const int look = (last_idx + nstatic >= endgame_from) ? A.look_end : A.look;
+            for (;;) {
+                const int cur = sm.cons_cur;
+                const unsigned dm = *reinterpret_cast<volatile unsigned int*>(&sm.done_mask);
+                const int n1 = next_live(cur, dm);
+                if (n1 == w || (look > 1 && next_live(n1, dm) == w)) break;
+                __nanosleep(64);
+            }
+            idx = nstatic + pop_item(A, lane);
         }
+        last_idx = idx;
         if (idx >= ntot) {
-            if (use[b]) mbar_wait(&sm.empty[b], (use[b] - 1) & 1);
-            if (lane == 0) { sm.seg[b].flags = SEG_DONE; mbar_arrive(&sm.full[b]); }
+            if (use) mbar_wait(empty, (use - 1) & 1);
+            if (lane == 0) { sg->flags = SEG_DONE; atomicOr(&sm.done_mask, 1u << w); mbar_arrive(full); }
             __syncwarp();
-            mbar_arrive(&sm.full[b]);
+            mbar_arrive(full);
             return;
         }
-        const unsigned pos = pop_to_pos(idx, ntot);
-        int bucket = 0;
-        while (pos >= cum[bucket + 1]) bucket++;
-        const unsigned item = A.queue[(size_t)bucket * A.qcap + (pos - cum[bucket])];
-        {   // wait until a builder warp (of any CTA) has published this item's lists
-            unsigned r;
-            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(A.ready + idx) : "memory"); if (r != epoch) __nanosleep(64); } while (r != epoch);
-        }
-        have = idx < endgame_from;
-        if (have) idx = pop_item(A, lane);            // next item: the atomic's latency hides behind this tile
+        const int bucket = __popc(__ballot_sync(0xffffffffu, lane < TAMCMC_NBUCKETS && idx >= cum_inc));
+        const unsigned cbase = __shfl_sync(0xffffffffu, cum_inc, (bucket + 31) & 31);      // prefix of the class before
+        const unsigned item = A.queue[(size_t)bucket * A.qcap + (idx - (bucket ? cbase : 0u))];
         const int sc = (int)(item / (unsigned)A.tiles_stride);
         const int tile = (int)(item - (unsigned)sc * (unsigned)A.tiles_stride);
         const StarDesc* sd = A.stars + sc / A.Nchains;
         const TileRec* tr = A.tilerec + item;
         // one round trip: star fields, tile record, chain flags
         const long long soff = sd->off;
-        const int Nloc = sd->Nloc;
+        const int Nloc = sd->Nloc, bin0 = sd->bin0, nmodes = sd->nmodes_cap;
         const double xc = tr->xc;
         const int series_ok = tr->series_ok;
-        const int nseg = tr->nseg;
-        const unsigned long long poff = tr->pool_off;
-        const int TF = tr->TF, TH = tr->TH;
-        int nf = tr->s0_nf, nh = tr->s0_nh, ng = tr->s0_ng, f0 = 0, h0 = 0, g0 = 0, wide = tr->s0_wide;
         const double bgk = (lane < NB) ? tr->bg[lane] : 0.0;
         const bool asym = A.asym_flag[sc] != 0;
         const double N0 = A.noise[sc].N0;
-
         const int lb0 = tile * TILE;
         const int nvalid = min(TILE, Nloc - lb0);
         const long long off = soff + lb0;
-        const unsigned char* lists = A.pool + poff;
-        const SegDesc* segs = reinterpret_cast<const SegDesc*>(lists + 32ull * TF + 32ull * TH + 64ull * tr->TG);
+        const int g0 = bin0 + lb0, gend = g0 + nvalid;
+        const ModeRec* modes = A.modes + (size_t)sc * A.modes_stride;
+        const CompRec* comps = A.comps + (size_t)sc * A.modes_stride * TAMCMC_MAX_COMP_PER_MODE;
 
-        const int nsegs = (nseg > 0) ? nseg : 1;      // nseg == 0: list pool overflow -> poisoned tile (NaN)
-        for (int j = 0; j < nsegs; j++) {
-            if (j > 0) { const SegDesc d = segs[j]; f0 = d.f0; nf = d.nf; h0 = d.h0; nh = d.nh; g0 = d.g0; ng = d.ng; wide = d.wide; }
-            if (use[b]) mbar_wait(&sm.empty[b], (use[b] - 1) & 1);
-            Segment* sg = &sm.seg[b];
-            const bool first = (j == 0), last = (j == nsegs - 1);
-            if (lane == 0) {
-                const unsigned bytes = (first ? 2u * TILE * (unsigned)sizeof(double) : 0u) + 32u * (unsigned)nf + 32u * (unsigned)nh + 64u * (unsigned)ng;
-                if (bytes) mbar_arrive_expect_tx(&sm.full[b], bytes); else mbar_arrive(&sm.full[b]);
-                if (first) {
-                    tma_load_1d(sg->x, A.x + off, TILE * sizeof(double), &sm.full[b]);
-                    tma_load_1d(sg->y, A.y + off, TILE * sizeof(double), &sm.full[b]);
-                }
-                if (nf) tma_load_1d(sg->fast, lists + 32ull * f0, 32u * (unsigned)nf, &sm.full[b]);
-                if (nh) tma_load_1d(sg->hdr, lists + 32ull * TF + 32ull * h0, 32u * (unsigned)nh, &sm.full[b]);
-                if (ng) tma_load_1d(sg->gen, lists + 32ull * TF + 32ull * TH + 64ull * g0, 64u * (unsigned)ng, &sm.full[b]);
-                sg->nfast = nf; sg->ngen = ng; sg->nhdr = nh;
-                sg->flags = (first ? SEG_FIRST : 0) | (last ? SEG_LAST : 0) | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (nseg > 0 ? 0 : SEG_POISON) | (wide ? SEG_WIDE : 0);
-                sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
-            }
-            if (last && lane < NB) sg->bg[lane] = bgk;
-            __syncwarp();
-            mbar_arrive(&sm.full[b]);
-            use[b]++;
-            h2_b = h1_b; h2_use = h1_use; h1_b = b; h1_use = use[b];
-            b = (b + 1 == NBUF) ? 0 : b + 1;
+        bool first = true;
+        int cf = 0, cg = 0, ch = 0, seg_wide = 0;
+        // ---- open the first segment: the slot must have been released; x and y start streaming in ----
+        if (use) mbar_wait(empty, (use - 1) & 1);
+        if (lane == 0) {
+            mbar_arrive_expect_tx(full, 2u * TILE * (unsigned)sizeof(double));
+            tma_load_1d(sg->x, A.x + off, TILE * sizeof(double), full);
+            tma_load_1d(sg->y, A.y + off, TILE * sizeof(double), full);
         }
+        for (int base = 0; base < nmodes; base += 32) {
+            const int mi = base + lane;
+            int ncomp = 0, nfast = 0, ngen = 0, i0 = 0, i1 = 0, nfast_rec = 0, mwide = 0, wbit = 0;
+            if (mi < nmodes) {
+                const int4 h = *reinterpret_cast<const int4*>(modes + mi);     // {i0, i1, ncomp, nfast | wide << 16}
+                if (h.z > 0 && h.x < gend && h.y > g0) {
+                    ncomp = h.z; nfast_rec = h.w & 0xffff; i0 = h.x; i1 = h.y;
+                    nfast = (h.x <= g0 && h.y >= gend) ? nfast_rec : 0;
+                    ngen = ncomp - nfast;
+                    wbit = (h.w >> 16) & 1;
+                    mwide = (nfast > 0) ? wbit : 0;
+                }
+            }
+            if (!__any_sync(0xffffffffu, ncomp > 0)) continue;
+            const int hh = (asym && nfast > 0) ? 1 : 0;
+            int sub_lo = 0;
+            while (sub_lo < 32) {
+                int sub_hi = 32;
+                bool mine = lane >= sub_lo;
+                int tf = warp_sum(mine ? nfast : 0), tg = warp_sum(mine ? ngen : 0), th = warp_sum(mine ? hh : 0);
+                if (tg > CAPG) {
+                    // too many general entries for one segment: 3 modes at a time (3 x 7 <= CAPG)
+                    sub_hi = sub_lo + 3;
+                    mine = lane >= sub_lo && lane < sub_hi;
+                    tf = warp_sum(mine ? nfast : 0); tg = warp_sum(mine ? ngen : 0); th = warp_sum(mine ? hh : 0);
+                }
+                if (cf + tf > CAPF || cg + tg > CAPG || ch + th > CAPH) {
+                    // ---- the slot is full: publish this segment, wait for the consumers to release the slot, go on ----
+                    if (lane == 0) {
+                        sg->nfast = cf; sg->ngen = cg; sg->nhdr = ch;
+                        sg->flags = (first ? SEG_FIRST : 0) | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (seg_wide ? SEG_WIDE : 0);
+                        sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
+                    }
+                    __syncwarp();
+                    mbar_arrive(full);
+                    use++;
+                    first = false; cf = cg = ch = 0; seg_wide = 0;
+                    mbar_wait(empty, (use - 1) & 1);
+                    if (lane == 0) mbar_arrive(full);          // this segment carries no TMA bytes
+                }
+                seg_wide |= __any_sync(0xffffffffu, mine && mwide) ? 1 : 0;
+                const int mf = mine ? nfast : 0, mg = mine ? ngen : 0, mh = mine ? hh : 0;
+                const int of = cf + warp_excl_scan(mf, lane), og = cg + warp_excl_scan(mg, lane), oh = ch + warp_excl_scan(mh, lane);
+                if (mine && ncomp > 0) {
+                    const CompRec* cp = comps + (size_t)mi * TAMCMC_MAX_COMP_PER_MODE;
+                    double qa = 0.0, qb = 1.0, qc = 0.0;
+                    if (asym || ngen > 0) { const ModeRec* mr = modes + mi; qa = mr->qa; qb = mr->qb0 + xc * qa; qc = mr->qc; }
+                    if (hh) { ModeHdr m; m.qa = qa; m.qb = qb; m.qc = qc; m.begin = of; m.count = nfast; sg->hdr[oh] = m; }
+#pragma unroll
+                    for (int k0 = 0; k0 < 8; k0 += 4) {
+                        double cnu[4], cs[4], ca[4];
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) { const int k = k0 + kk; if (k < ncomp) { cnu[kk] = cp[k].nu; cs[kk] = cp[k].s; ca[kk] = cp[k].a; } }
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            const int k = k0 + kk;
+                            if (k < ncomp) {
+                                const double cc = -(cnu[kk] - xc) * cs[kk];
+                                if (k < nfast) { FastEntry fe; fe.s = cs[kk]; fe.c = cc; fe.a = ca[kk]; fe.pad = 0.0; sg->fast[of + k] = fe; }
+                                else {
+                                    // components are stored FAST-first; a FAST one lands here only on a window edge
+                                    const bool ff = k < nfast_rec;
+                                    GenEntry ge;
+                                    ge.s = cs[kk]; ge.c = cc; ge.aadd = ff ? ca[kk] : 1.0; ge.num = ff ? 1.0 : ca[kk];
+                                    // window in tile-local bins, clamped to the tile; bit 30 of hi: the entry needs an exponent
+                                    // renormalisation after every merge (general form, or a WIDE-range mode)
+                                    ge.qa = qa; ge.qb = qb; ge.qc = qc; ge.lo = max(i0 - g0, 0);
+                                    ge.hi = min(i1 - g0, TILE) | ((!ff || wbit) ? (1 << 30) : 0);
+                                    sg->gen[og + (k - nfast)] = ge;
+                                }
+                            }
+                        }
+                    }
+                }
+                cf += tf; cg += tg; ch += th;
+                sub_lo = sub_hi;
+            }
+        }
+        // ---- last segment of the tile (possibly empty: a tile no mode touches still has its background and Whittle terms)
+        if (lane == 0) {
+            sg->nfast = cf; sg->ngen = cg; sg->nhdr = ch;
+            sg->flags = (first ? SEG_FIRST : 0) | SEG_LAST | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (seg_wide ? SEG_WIDE : 0);
+            sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
+        }
+        if (lane < NB) sg->bg[lane] = bgk;
+        __syncwarp();
+        mbar_arrive(full);
+        use++;
     }
 }
 
@@ -267,6 +336,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
     unsigned use[NBUF];
     for (int i = 0; i < NBUF; i++) use[i] = 0;
     int b = 0;
+    unsigned done = 0;                  // producers (slots) that have delivered SEG_DONE
     double u[BPT], N[BPT], D[BPT], yv[BPT];
 #pragma unroll
     for (int j = 0; j < BPT; j++) { u[j] = 0; N[j] = 0; D[j] = 1; yv[j] = 0; }
@@ -286,8 +356,15 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
 #ifdef TAMCMC_TRACE
         if (tid == 0) { TRACE(tslot + 1, gtime()); tslot += 2; if (flags & SEG_DONE) TRACE(1, gtime()); }
 #endif
-        if (flags & SEG_DONE) return;
+        if (flags & SEG_DONE) {
+            // this producer has drained the queue: drop its slot from the round-robin
+            done |= 1u << b;
+            if (done == (1u << NBUF) - 1u) return;
+            do { b = (b + 1 == NBUF) ? 0 : b + 1; } while ((done >> b) & 1u);
+            continue;
+        }
         const bool asym = (flags & SEG_ASYM) != 0;
+        if ((flags & SEG_FIRST) && tid == 0) sm.cons_cur = b;
 
         if (flags & SEG_FIRST) {
             // this thread's 4 bins: b(j) = 2*tid + 512*(j>>1) + (j&1), read as 128-bit pairs
@@ -522,7 +599,6 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
                     pe += k >> 20;
                 }
             }
-            if (flags & SEG_POISON) s1 = nan("");       // the tile's lists did not fit the pool
             // ---------- barrier-free tile completion.  Every warp deposits its (shuffle-tree) sums in the slots of
             // this segment buffer; the LAST warp to do so combines the slots in warp order (deterministic whatever
             // the arrival order) and stores the tile's partial (sum y/M, mantissa and exponent of prod 1/M).  Nobody
@@ -560,10 +636,10 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
             }
             __syncwarp();
             mbar_arrive(&sm.empty[b]);                    // the slot array of this buffer is free again
+            do { b = (b + 1 == NBUF) ? 0 : b + 1; } while ((done >> b) & 1u);      // next tile: next live slot
         } else {
-            mbar_arrive(&sm.empty[b]);
+            mbar_arrive(&sm.empty[b]);                    // more segments of this tile follow in the SAME slot
         }
-        b = (b + 1 == NBUF) ? 0 : b + 1;
     }
 }
 
@@ -600,14 +676,14 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < NBUF; i++) { mbar_init(&sm.full[i], 33); mbar_init(&sm.empty[i], NC); sm.cnt[i] = 0u; }
+        sm.cons_cur = -1; sm.done_mask = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     // Programmatic dependent launch: this grid may have been scheduled while the expand kernel was still running (its
     // prologue above overlaps the expander's tail); everything below reads the expander's output.
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (tid >= NC + 32) builder_loop(A, (tid - NC - 32) >> 5, tid & 31);
-    else if (tid >= NC) producer_loop(A, sm, tid - NC);
+    if (tid >= NC) producer_loop(A, sm, (tid - NC) >> 5, tid & 31);
     else consumer_loop<WRITE_MODEL>(A, sm, tid);
 
     // ---- the LAST CTA to finish turns the per-tile partials into the per-chain results and re-arms the queue ----
@@ -622,7 +698,7 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
         // host mirror: every writer fences its own stores at system scope, the barrier orders them before the flag
         __syncthreads();
         for (int i = tid; i < A.nsc; i += NT) { A.host_logL[i] = A.out[i]; A.host_status[i] = A.status[i]; }
-        if (tid == 0) *A.host_overflow = A.qctl->overflow;
+        if (tid == 0) *A.host_overflow = 0u;
         __threadfence_system();
         __syncthreads();
     }
@@ -630,7 +706,7 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
         QueueCtl* q = A.qctl;
 #pragma unroll
         for (int k = 0; k < TAMCMC_NBUCKETS; k++) q->count[k] = 0u;
-        q->head = 0u; q->pool_cursor = 0ull; q->ctas_done = 0u;
+        q->head = 0u; q->ctas_done = 0u;
         unsigned e = *A.epoch + 1u;
         e = e ? e : 1u;
         *A.epoch = e;                                   // next launch's ready-flag value (never 0)
