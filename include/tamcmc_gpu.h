@@ -32,8 +32,8 @@ typedef enum {
                                     status_out[] tells which chain */
     TAMCMC_ERR_NONFINITE = 5,    /* some chain produced a non-finite mode quantity; its logL is NaN */
     TAMCMC_ERR_LIKELIHOOD = 6,   /* likelihood id not on this path (model_def.cpp:405-416) */
-    TAMCMC_ERR_POOL = 7          /* the device pool for per-tile component lists is too small for these
-                                    parameters; affected chains are NaN; enlarge with TAMCMC_GPU_POOL_MB */
+    TAMCMC_ERR_POOL = 7          /* reserved (ABI v1 reported an exhausted device list pool; tile lists now live in shared
+                                    memory only and the code is never returned) */
 } tamcmc_status;
 
 /* per-chain status bits written to status_out[] (0 = evaluated normally) */

@@ -127,7 +127,7 @@ struct tamcmc_gpu_ctx {
     // zero-copy host path of tamcmc_gpu_eval: parameters are read by the expander straight from mapped pinned memory and
     // the last CTA of the fused kernel writes results + a completion flag back into mapped pinned memory
     bool zero_copy = true;           // TAMCMC_GPU_NO_ZEROCOPY=1 selects the DMA path (H2D + D2H copies + stream sync)
-    unsigned char* h_mirror = nullptr;   // [SC] double logL | [SC] int status | pad to 64 | uint overflow | pad to 128 | uint flag
+    unsigned char* h_mirror = nullptr;   // [SC] double logL | [SC] int status | pad to 64 | (reserved word) | pad to 128 | uint flag
     double* dm_logL = nullptr; int* dm_status = nullptr; unsigned int* dm_overflow = nullptr; unsigned int* dm_flag = nullptr;
     double* dh_params = nullptr; unsigned char* dh_active = nullptr;    // device addresses of h_params / h_active
     unsigned int epoch_host = 1;     // mirrors the device epoch: advanced once per fused-kernel launch
@@ -136,6 +136,7 @@ struct tamcmc_gpu_ctx {
     struct GraphEntry { const double* p; const unsigned char* a; double* o; int raw; cudaGraphExec_t exec; };
     GraphEntry graphs[4] = {};
     int ngraphs = 0;
+    int stagger_ns = 0;               // TAMCMC_GPU_STAGGER_NS (tuning aid)
     int look = 2, look_end = 1;       // producer look-ahead (TAMCMC_GPU_LOOK / TAMCMC_GPU_LOOK_END = 1 or 2; tuning aid)
     bool use_graphs = true;
     bool use_pdl = false;            // programmatic dependent launch expand -> fused kernel: measured no gain inside a CUDA graph
@@ -186,7 +187,7 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, boo
     a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
     a.raw_sum = raw_sum; a.trace = c->d_trace;
     a.epoch = c->d_epoch;
-    a.look = c->look; a.look_end = c->look_end;
+    a.look = c->look; a.look_end = c->look_end; a.stagger_ns = c->stagger_ns;
     a.status = c->d_status(); a.nsc = c->SC();
     // the host mirror costs a system-scope fence at the end of the launch: only the host-buffer entry point asks for it
     a.host_logL = mirror ? c->dm_logL : nullptr; a.host_status = mirror ? c->dm_status : nullptr;
@@ -307,7 +308,7 @@ const char* tamcmc_gpu_strerror(int s)
     case TAMCMC_ERR_WINDOW: return "set_imin_imax: imax - imin <= 0 for some chain";
     case TAMCMC_ERR_NONFINITE: return "non-finite mode quantity for some chain";
     case TAMCMC_ERR_LIKELIHOOD: return "likelihood id unknown (model_def.cpp:405-416)";
-    case TAMCMC_ERR_POOL: return "component-list pool too small (TAMCMC_GPU_POOL_MB)";
+    case TAMCMC_ERR_POOL: return "reserved";
     }
     return "unknown status";
 }
@@ -332,6 +333,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     c->device = device; c->nstars = nstars; c->Nchains = Nchains; c->p = p; c->likelihood = likelihood_id;
     if (const char* e = std::getenv("TAMCMC_GPU_NO_GRAPH")) c->use_graphs = !(e[0] == '1');
     if (const char* e = std::getenv("TAMCMC_GPU_PDL")) c->use_pdl = (e[0] == '1');
+    if (const char* e = std::getenv("TAMCMC_GPU_STAGGER_NS")) c->stagger_ns = std::atoi(e);
     if (const char* e = std::getenv("TAMCMC_GPU_LOOK")) c->look = (e[0] == '1') ? 1 : 2;
     if (const char* e = std::getenv("TAMCMC_GPU_LOOK_END")) c->look_end = (e[0] == '1') ? 1 : 2;
     c->h_stars.resize(nstars);
@@ -513,7 +515,6 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char
     std::memcpy(c->h_params, params, pbytes);
     if (active_mask) std::memcpy(c->h_active, active_mask, (size_t)SC);
     const int* st = nullptr;
-    unsigned int overflow = 0;
     if (c->zero_copy) {
         // ---- zero-copy: no DMA copies, no stream synchronisation.  The expander reads the rows over PCIe; the last CTA
         // of the fused kernel writes logL/status into the mapped mirror and publishes the launch's epoch in the flag ----
@@ -536,7 +537,6 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char
         { int rc = collect_profile(c); if (rc) return rc; }
         std::memcpy(logL_out, c->hm_logL(), sizeof(double) * (size_t)SC);
         st = c->hm_status();
-        overflow = *c->hm_overflow();
     } else {
         CK(cudaMemcpyAsync(c->d_params, c->h_params, pbytes, cudaMemcpyHostToDevice, c->stream));
         const unsigned char* d_act = nullptr;
@@ -551,7 +551,6 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char
         std::memcpy(logL_out, c->h_out, sizeof(double) * (size_t)SC);
         st = reinterpret_cast<const int*>(reinterpret_cast<const double*>(c->h_out) + SC);
     }
-    (void)overflow;
     if (status_out) std::memcpy(status_out, st, sizeof(int) * (size_t)SC);
     c->pairs_last = -1;
     return status_to_rc(st, SC);

@@ -57,6 +57,7 @@ struct WhittleArgs {
     double* host_logL; int* host_status; unsigned int* host_overflow; unsigned int* host_flag;
     const int* status;               // [nstars*Nchains] per-chain status written by the expand kernel
     int nsc;                         // nstars*Nchains
+    int stagger_ns;                  // start offset between the consumer warps of one SM sub-partition (de-phasing)
     int look, look_end;              // producer look-ahead in tiles (1 or 2): steady state / last ~4 items per CTA
     int likelihood;                  // 0: chi(2,2p)  S = sum(ln M + y/M);  1: chi_square  S = sum((y-M)^2/sigma^2)
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)

@@ -16,7 +16,9 @@
 #define TAMCMC_MAX_HARVEY 8
 #define TAMCMC_BG_TERMS 10           // Taylor coefficients of the Harvey background per tile
 #define TAMCMC_TILE 1536             // bins per tile
+#ifndef TAMCMC_CONSUMERS
 #define TAMCMC_CONSUMERS 384         // consumer threads per CTA (4 bins per thread); ONE persistent CTA per SM
+#endif
 #define TAMCMC_PRODUCERS 4           // producer warps per CTA = slots of the shared-memory ring
 #define TAMCMC_THREADS (TAMCMC_CONSUMERS + 32 * TAMCMC_PRODUCERS)
 #define TAMCMC_BINS_PER_THREAD (TAMCMC_TILE / TAMCMC_CONSUMERS)

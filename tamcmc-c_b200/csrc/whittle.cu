@@ -79,13 +79,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Blocks in hardware for up to `MBAR_SUSPEND_NS` per try (suspendTimeHint): a waiting warp issues one instruction group
+// every few microseconds instead of spinning and taking issue slots from the FP64 loops of the consumer warps.
+constexpr unsigned MBAR_SUSPEND_NS = 4000;
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
     unsigned ok = 0;
     const unsigned addr = smem_u32(bar);
     while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
     }
 }
 // TMA 1-D bulk copy global -> shared, completion counted on an mbarrier
@@ -192,7 +195,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
                 const unsigned dm = *reinterpret_cast<volatile unsigned int*>(&sm.done_mask);
                 const int n1 = next_live(cur, dm);
                 if (n1 == w || (look > 1 && next_live(n1, dm) == w)) break;
-                __nanosleep(64);
+                __nanosleep(256);
             }
             idx = nstatic + pop_item(A, lane);
         }
@@ -345,6 +348,11 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
     int tslot = 2;
     if (tid == 0) { TRACE(0, gtime()); unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); TRACE(63, (unsigned long long)smid + 1); }
 #endif
+    // De-phasing: the 12 consumer warps do the same work on every tile, so left alone they run in lock step and the FP64
+    // pipe idles while ALL of them are in the latency-bound epilogue.  The three warps of each SM sub-partition start
+    // `stagger_ns` apart; the offset persists (bounded by the ring depth), so one warp's epilogue overlaps the others'
+    // main loops.
+    if (A.stagger_ns > 0 && warp >= 4) __nanosleep((unsigned)A.stagger_ns * (unsigned)(warp >> 2));
     for (;;) {
 #ifdef TAMCMC_TRACE
         if (tid == 0) TRACE(tslot, gtime());        // begin waiting for a segment

@@ -116,3 +116,51 @@ def test_gpu_mode_table_extra_shifts_and_errors(pkg, oracle):
     with pytest.raises(pkg.TamcmcError):
         pl_bad = pl.copy(); pl_bad[3] = 2
         pkg.Context(pkg.Star(pkg.synth.MODEL_MODE_TABLE, pl_bad, len(row), x, M), 1, [1.0])
+
+
+@pytest.mark.gpu
+def test_gpu_dense_lists_stream_through_one_slot_in_segments(pkg, oracle):
+    """Tile lists far larger than one ring slot (352 mask-free / 24 general entries): 220 modes (l up to 3 -> ~1100
+    components) whose windows all cover a 2-tile spectrum, plus 70 narrow-window modes whose edges fall inside the tiles
+    (several hundred general entries).  The producer streams such a list through its slot as many segments."""
+    rng = np.random.default_rng(77)
+    N = 2500
+    x = pkg.synth.freq_axis(N, 1000.0, 0.01)            # 25 microHz wide: 2 tiles
+    noise = [0.5, 200.0, 2.0, 0.2]
+    nwide, nedge = 220, 70
+    modes = np.zeros((nwide + nedge, 11))
+    modes[:, 0] = rng.integers(0, 4, nwide + nedge)
+    modes[:nwide, 1] = rng.uniform(1001, 1024, nwide)
+    modes[:nwide, 3] = rng.uniform(0.2, 1.5, nwide)      # trunc_c * (l + Gamma) >> 25 microHz: every window covers both tiles
+    modes[nwide:, 1] = rng.uniform(1002, 1023, nedge)
+    modes[nwide:, 3] = rng.uniform(0.01, 0.05, nedge)
+    modes[:, 2] = rng.uniform(0.5, 30, nwide + nedge)
+    modes[:, 4] = rng.uniform(0.05, 0.4, nwide + nedge)  # a1 < 1: window half-width = c*(l+1) for narrow modes
+    cap = nwide + nedge
+    for asym, trunc_wide in ((0.0, 40.0), (25.0, 40.0)):
+        # two chains: one with wide windows for everything, one where the narrow modes get c = 1.5 (edges inside the tiles)
+        rows = np.stack([pkg.synth.mode_table_row(cap, 37.0, trunc_wide, asym, noise, modes),
+                         pkg.synth.mode_table_row(cap, 37.0, 1.5, asym, noise, modes)])
+        T = [1.0, 1.7]
+        refs = []
+        for r in rows:
+            rc, M, tr = oracle.mode_table_model(r, len(noise), 0, x, trace=True)
+            assert rc == 0
+            refs.append((M, tr))
+        w0 = refs[1][1][1]; w1 = refs[1][1][2]
+        assert np.sum((w0 > 0) & (w0 < N)) + np.sum((w1 > 0) & (w1 < N)) > 100      # many window edges inside the spectrum
+        rng2 = np.random.default_rng(5)
+        y = pkg.synth.chi2_2dof_spectrum(rng2, refs[0][0])
+        rc, L_ref = oracle.mode_table_eval_chains(rows, len(noise), 0, x, y, T)
+        pl = pkg.synth.mode_table_plength(cap, len(noise), 0)
+        with pkg.Context(pkg.Star(pkg.synth.MODEL_MODE_TABLE, pl, rows.shape[1], x, y), 2, T) as ctx:
+            for r, (M, tr) in zip(rows, refs):
+                rcw, wl, a, b = ctx.windows(r)
+                assert np.array_equal(wl, tr[0]) and np.array_equal(a, tr[1]) and np.array_equal(b, tr[2])
+                Mg = ctx.model(r)
+                assert np.max(np.abs(Mg - M) / np.abs(M)) < RTOL
+            L, st = ctx.eval(rows)
+            assert (st == 0).all()
+            assert np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)) < RTOL
+            L2, _ = ctx.eval(rows)
+            assert np.array_equal(L, L2)
