@@ -46,9 +46,13 @@ typedef enum {
  * Config/default/models_ctrl.list */
 #define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC     3   /* models.cpp:1943 */
 #define TAMCMC_MODEL_MS_GLOBAL_A1L_ETAA3_HARVEYLIKE           6   /* models.cpp:25   */
+#define TAMCMC_MODEL_MS_GLOBAL_A1N_ETAA3_HARVEYLIKE            7   /* models.cpp:217  */
+#define TAMCMC_MODEL_MS_GLOBAL_A1NL_ETAA3_HARVEYLIKE           8   /* models.cpp:1003 */
 #define TAMCMC_MODEL_MS_LOCAL_BASIC                          11   /* models.cpp:3012 */
 #define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC_V2 12   /* models.cpp:2128 */
 #define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC_V3 13   /* models.cpp:2338 */
+/* ids 18 / 19 (model_MS_Global_a1n_a2a3 / a1nl_a2a3_HarveyLike) print "not tested yet" and exit in the reference
+ * (models.cpp:599-603, 993-997): TAMCMC_ERR_MODEL */
 #define TAMCMC_MODEL_MS_GLOBAL_AJ_HARVEYLIKE                 23   /* models.cpp:1195 */
 
 /* Generic MODE TABLE (not a reference model id): the entry for model functions whose mode list is resolved by host

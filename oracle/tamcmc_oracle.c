@@ -1004,6 +1004,58 @@ static int model_MS_Global_a1l_etaa3_HarveyLike(const double *params, const int 
     return rc;
 }
 
+/* model_MS_Global_a1n_etaa3_HarveyLike (models.cpp:217-407, id 7), model_MS_Global_a1nl_etaa3_HarveyLike (:1003-1193, id 8),
+ * model_MS_Global_a1n_a2a3_HarveyLike (:409-607, id 18), model_MS_Global_a1nl_a2a3_HarveyLike (:805-1001, id 19): the loop of
+ * model_MS_Global_a1l_etaa3_HarveyLike with the splittings read per radial order:
+ *   a11[n] = |params[split+6+n]|;  a12[n] = a11[n] (a1n) or |params[split+6+Nmax+n]| (a1nl);
+ *   a2a3 variants: no eta term, a2[n] = params[split+6+Nmax+n] (a1n) / params[split+6+2Nmax+n] (a1nl), build_l_mode_a1l_a2a3 */
+static int model_MS_Global_a1x_HarveyLike(const double *params, const int *pl, const double *x, long N, double *out, int id)
+{
+    const double step = x[1] - x[0];
+    const long double pi = PI_L;
+    const int Nmax = pl[0], lmax = pl[1], Nfl0 = pl[2], Nfl1 = pl[3], Nfl2 = pl[4], Nfl3 = pl[5];
+    const int Nsplit = pl[6], Nwidth = pl[7], Nnoise = pl[8], Ninc = pl[9];
+    const int Nf = Nfl0 + Nfl1 + Nfl2 + Nfl3;
+    const int o_split = Nmax + lmax + Nf;
+    const int do_amp = (params[o_split + Nsplit + Nwidth + Nnoise + Ninc + 1] != 0);
+    const int a2a3 = (id == 18 || id == 19), nl = (id == 8 || id == 19);
+    const double trunc_c = params[o_split + Nsplit + Nwidth + Nnoise + Ninc];
+    const double inclination = params[o_split + Nsplit + Nwidth + Nnoise];
+    double ratios[4][7], Vl[4] = {1, 0, 0, 0};
+    const double *fl0_all = params + Nmax + lmax;
+    const double *Wl0_all = params + o_split + Nsplit;
+    const double eta0 = a2a3 ? 0.0 : orc_eta0_fct(fl0_all, Nfl0);
+    const double a3 = params[o_split + 2], asym = params[o_split + 5];
+    double *model = zeros(N), *noise_abs; long n; int rc = 0, Nharvey, l;
+    ratios[0][0] = 1;
+    for (l = 1; l <= lmax && l <= 3; l++) { Vl[l] = fabs(params[Nmax + l - 1]); orc_amplitude_ratio(l, inclination, ratios[l]); }
+    for (n = 0; n < Nmax && !rc; n++) {
+        const double a11 = fabs(params[o_split + 6 + n]);
+        const double a12 = nl ? fabs(params[o_split + 6 + Nmax + n]) : a11;
+        const double a2 = a2a3 ? params[o_split + 6 + (nl ? 2 : 1) * Nmax + n] : 0.0;
+        for (l = 0; l <= lmax && l <= 3 && !rc; l++) {
+            const int off = Nmax + lmax + (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0);
+            const double fl = params[off + n];
+            const double Wl = (l == 0) ? fabs(Wl0_all[n]) : fabs(orc_lin_interpol(fl0_all, Wl0_all, Nmax, fl));
+            double Hl;
+            if (l == 0) Hl = do_amp ? (double)fabsl(params[n] / (pi * Wl)) : fabs(params[n]);
+            else Hl = do_amp ? (double)(fabsl(params[n] / (pi * Wl)) * Vl[l]) : fabs(params[n] * Vl[l]);
+            if (a2a3) rc = orc_optimum_lorentzian_calc_a1l_a2a3(x, N, &model, Hl, fl, a11, a12, (l == 0) ? 0.0 : a2, (l == 0) ? 0.0 : a3, asym, Wl, l, ratios[l], step, trunc_c);
+            else rc = orc_optimum_lorentzian_calc_a1l_etaa3(x, N, &model, Hl, fl, a11, a12, eta0, a3, asym, Wl, l, ratios[l], step, trunc_c);
+        }
+    }
+    if (!rc) {
+        noise_abs = (double *)malloc(sizeof(double) * (size_t)(Nnoise > 0 ? Nnoise : 1));
+        abs_copy(params + o_split + Nsplit + Nwidth, Nnoise, noise_abs);
+        Nharvey = (Nnoise - 1) / 3;
+        orc_harvey_like(noise_abs, Nnoise, x, N, &model, Nharvey);
+        free(noise_abs);
+        memcpy(out, model, sizeof(double) * (size_t)N);
+    }
+    free(model);
+    return rc;
+}
+
 /* tamcmc/sources/models.cpp:3012-3196 */
 static int model_MS_local_basic(const double *params, const int *pl, const double *x, long N, double *out)
 {
@@ -1259,6 +1311,10 @@ int orc_call_model(int model_id, const double *params, const int *plength, const
     case ORC_MODEL_MS_GLOBAL_CLASSIC_V2: return model_MS_Global_a1etaa3_HarveyLike_Classic_v2(params, plength, x, N, model_out);
     case ORC_MODEL_MS_GLOBAL_CLASSIC_V3: return model_MS_Global_a1etaa3_HarveyLike_Classic_v3(params, plength, x, N, model_out);
     case ORC_MODEL_MS_GLOBAL_A1L_ETAA3:  return model_MS_Global_a1l_etaa3_HarveyLike(params, plength, x, N, model_out);
+    case ORC_MODEL_MS_GLOBAL_A1N_ETAA3: case ORC_MODEL_MS_GLOBAL_A1NL_ETAA3:
+        return model_MS_Global_a1x_HarveyLike(params, plength, x, N, model_out, model_id);
+    /* ORC_MODEL_MS_GLOBAL_A1N_A2A3 (18) and ORC_MODEL_MS_GLOBAL_A1NL_A2A3 (19) compute a model and then print "not tested yet"
+     * and exit in the reference (models.cpp:599-603, 993-997): unusable there, ORC_ERR_MODEL here */
     case ORC_MODEL_MS_LOCAL_BASIC:       return model_MS_local_basic(params, plength, x, N, model_out);
     case ORC_MODEL_MS_GLOBAL_AJ:         return model_MS_Global_aj_HarveyLike(params, plength, x, N, model_out);
     case ORC_MODEL_MS_GLOBAL_AJALM:      return model_MS_Global_ajAlm_HarveyLike(params, plength, x, N, model_out, alm, alm_user);

@@ -79,7 +79,8 @@ int upload_tables(int device)
 int modes_of(int model_id, const int* pl)
 {
     switch (model_id) {
-    case 3: case 6: case 12: case 13: return pl[0] * (pl[1] + 1);
+    case 3: case 6: case 7: case 8: case 12: case 13: return pl[0] * (pl[1] + 1);
+    // 18 / 19 (a1n / a1nl a2a3) print "not tested yet" and exit in the reference (models.cpp:599-603, 993-997): ERR_MODEL
     case 11: case 23: return pl[2] + pl[3] + pl[4] + pl[5];
     case TAMCMC_MODEL_ID_MODE_TABLE: return pl[0];
     }
@@ -354,11 +355,14 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
             if (in.plength[1] == 1 && (in.N < 3 || in.N_global > 0)) { delete c; return TAMCMC_ERR_ARG; }
         }
         if (!in.x || !in.y || in.N < 2 || in.N > 2000000000L || in.Nparams < need || nm == 0) { delete c; return TAMCMC_ERR_ARG; }
-        if (in.model_id == 3 || in.model_id == 6 || in.model_id == 12 || in.model_id == 13) {
+        if (in.model_id == 3 || in.model_id == 6 || in.model_id == 7 || in.model_id == 8 || in.model_id == 12 || in.model_id == 13) {
             // the reference indexes fl_l[n] for n < Nmax and l <= lmax (models.cpp:2026-2075)
             for (int l = 0; l <= in.plength[1] && l <= 3; l++)
                 if (in.plength[2 + l] < in.plength[0]) { delete c; return TAMCMC_ERR_ARG; }
             if (in.plength[1] > 3 || in.plength[0] < 2) { delete c; return TAMCMC_ERR_ARG; }
+            // per-radial-order splittings live in the splitting block (models.cpp:229, 421, 817, 1015)
+            const int per_n = (in.model_id == 7) ? 1 : (in.model_id == 8) ? 2 : 0;
+            if (in.plength[6] < 6 + per_n * in.plength[0]) { delete c; return TAMCMC_ERR_ARG; }
         }
         if ((in.model_id == 23) && (in.plength[0] < 2 || in.plength[2] < 2)) { delete c; return TAMCMC_ERR_ARG; }
         sd.off = off;

@@ -466,6 +466,11 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 cm.a3 = params[o_split + 2];
                 cm.asym = params[o_split + 5];
                 break;
+            case 7: case 8:              // a1n / a1nl etaa3: models.cpp:290-296, 1075-1081 (splittings per radial order: pass A)
+                cm.eta0 = d_eta0_fct(fl0_all, Nfl0);
+                cm.a3 = params[o_split + 2];
+                cm.asym = params[o_split + 5];
+                break;
             case 11:                     // models.cpp:3059-3075 (Nvis plays the role of lmax)
                 cm.a1 = params[o_split + 3] * params[o_split + 3] + params[o_split + 4] * params[o_split + 4];
                 cm.eta0 = params[o_split + 1];
@@ -520,7 +525,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 }
             } else if (!mode_table && tid < EXP_BATCH && j < nmodes) {
                 int l, n;
-                if (model == 3 || model == 12 || model == 13 || model == 6) {
+                if (model == 3 || model == 12 || model == 13 || model == 6 || model == 7 || model == 8) {
                     l = j % (lmax + 1); n = j / (lmax + 1);          // n-major, l interleaved (models.cpp:2026-2085)
                 } else {
                     // l-major: all l=0, then l=1, ... (models.cpp:1287-1376, 3082-3134)
@@ -559,6 +564,11 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                     t.W = (l == 0) ? fabs(Wl0_all[n]) : fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
                     if (model == 6) {                     // build_lorentzian.cpp:58-66, 383-396
                         t.f_s = (l == 0) ? 0.0 : (l == 1) ? cm.a11 : (l == 2) ? cm.a12 : (cm.a11 + cm.a12) / 2.;
+                    } else if (model == 7 || model == 8) {
+                        // splittings per radial order (models.cpp:290-291, 317-318; 1075-1076, 1099-1100)
+                        const double a11 = fabs(params[o_split + 6 + n]);
+                        const double a12 = (model == 8) ? fabs(params[o_split + 6 + Nmax + n]) : a11;
+                        t.f_s = (l == 0) ? 0.0 : (l == 1) ? a11 : (l == 2) ? a12 : (a11 + a12) / 2.;
                     } else t.f_s = cm.a1;
                     t.fsw = t.f_s;
                     if (model == 13) {

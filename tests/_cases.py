@@ -24,7 +24,7 @@ def ms_case(synth, model_id, seed, N=20000, x0=900.0, step=None, Nmax=6, lmax=3,
     inc = rng.uniform(0.0, 90.0) if inc is None else inc
     a1 = rng.uniform(0.2, 3.0) if a1 is None else a1
     noise = _noise_variants(rng, seed)
-    if model_id in (3, 12, 13, 6):
+    if model_id in (3, 12, 13, 6, 7, 8, 18, 19):
         params, pl = synth.classic_params(rng, Nmax=Nmax, lmax=lmax, f0=f0, dnu=dnu, asym=asym, inc=inc, a1=a1,
                                           a3=rng.uniform(-0.05, 0.05), trunc_c=trunc_c, do_amp=do_amp, noise=noise,
                                           wmin=wmin, wmax=wmax)
@@ -35,6 +35,18 @@ def ms_case(synth, model_id, seed, N=20000, x0=900.0, step=None, Nmax=6, lmax=3,
             split = np.concatenate([params[o_split:o_split + 6], [rng.uniform(0.2, 3.0)]])
             params = np.concatenate([params[:o_split], split, params[o_split + 6:]])
             pl = pl.copy(); pl[6] = 7
+        if model_id in (7, 8, 18, 19):
+            # splittings per radial order appended to the 6 global splitting parameters:
+            #   7 (a1n_etaa3): a1[n]            8 (a1nl_etaa3): a1(l=1)[n], a1(l=2)[n]          (models.cpp:290, 1075-1076)
+            #  18 (a1n_a2a3):  a1[n], a2[n]    19 (a1nl_a2a3):  a1(l=1)[n], a1(l=2)[n], a2[n]  (models.cpp:481-483, 876-878)
+            extra = [rng.uniform(0.2, 3.0, Nmax)]
+            if model_id in (8, 19):
+                extra.append(rng.uniform(0.2, 3.0, Nmax))
+            if model_id in (18, 19):
+                extra.append(rng.uniform(-0.15, 0.15, Nmax))
+            split = np.concatenate([params[o_split:o_split + 6]] + extra)
+            params = np.concatenate([params[:o_split], split, params[o_split + 6:]])
+            pl = pl.copy(); pl[6] = len(split)
         if model_id == 12:
             # Ninc=9 m-height ratios [l=1: m0,m1 | l=2: m0,m1,m2 | l=3: m0..m3] (models.cpp:2196-2214)
             o_inc = len(params) - 3
@@ -71,4 +83,6 @@ def ms_case(synth, model_id, seed, N=20000, x0=900.0, step=None, Nmax=6, lmax=3,
     raise ValueError(model_id)
 
 
-ALL_MODELS = (3, 6, 11, 12, 13, 23)
+ALL_MODELS = (3, 6, 7, 8, 11, 12, 13, 23)
+# ids 18/19 (a1n/a1nl_a2a3) and a1l_a2a3 print "not tested yet" and exit in the reference (models.cpp:599-603, 798-800, 993-997):
+# they are rejected with ERR_MODEL here; ms_case can still build their parameter vectors for that test

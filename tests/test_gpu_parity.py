@@ -157,7 +157,7 @@ def test_window_error_is_reported_not_fatal(pkg, oracle):
 def test_unknown_model_and_bad_sizes(pkg):
     x = pkg.synth.freq_axis(2048, 900.0, 0.1)
     params, pl = pkg.synth.classic_params(np.random.default_rng(0), Nmax=4, lmax=2, f0=950.0, dnu=40.0)
-    for mid in (2, 4, 5, 9, 99):     # obsolete / unknown ids exit in the reference (model_def.cpp:231-384)
+    for mid in (2, 4, 5, 18, 19, 99):     # obsolete / unknown / self-terminating ids exit in the reference (model_def.cpp:231-384, models.cpp:599-603)
         with pytest.raises(pkg.TamcmcError) as ei:
             pkg.Context(pkg.Star(mid, pl, len(params), x, np.ones_like(x)), 1, [1.0])
         assert ei.value.status == pkg.ERR_MODEL
