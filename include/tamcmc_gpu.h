@@ -51,6 +51,7 @@ typedef enum {
 #define TAMCMC_MODEL_MS_LOCAL_BASIC                          11   /* models.cpp:3012 */
 #define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC_V2 12   /* models.cpp:2128 */
 #define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC_V3 13   /* models.cpp:2338 */
+#define TAMCMC_MODEL_MS_LOCAL_HNLM                           14   /* models.cpp:3198 */
 /* ids 18 / 19 (model_MS_Global_a1n_a2a3 / a1nl_a2a3_HarveyLike) print "not tested yet" and exit in the reference
  * (models.cpp:599-603, 993-997): TAMCMC_ERR_MODEL */
 #define TAMCMC_MODEL_MS_GLOBAL_AJ_HARVEYLIKE                 23   /* models.cpp:1195 */

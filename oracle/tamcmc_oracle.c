@@ -1115,6 +1115,50 @@ static int model_MS_local_basic(const double *params, const int *pl, const doubl
     return rc;
 }
 
+/* tamcmc/sources/models.cpp:3198-3343: model_MS_local_Hnlm.  Heights are H(n,l,|m|), symmetric in m, stored
+ * (l+1) per mode at params[base_l + (l+1) n + |m|] with base_l = Nfl0, Nfl0+Nfl1, Nfl0+Nfl1+Nfl2 for l = 1, 2, 3 exactly as the
+ * reference indexes them (models.cpp:3270-3272, 3285-3289, 3303-3309); white noise only (Nharvey = 0). */
+static int model_MS_local_Hnlm(const double *params, const int *pl, const double *x, long N, double *out)
+{
+    const double step = x[1] - x[0];
+    const long double pi = PI_L;
+    const int Nmax = pl[0], Nvis = pl[1], Nfl0 = pl[2], Nfl1 = pl[3], Nfl2 = pl[4], Nfl3 = pl[5];
+    const int Nsplit = pl[6], Nwidth = pl[7], Nnoise = pl[8], Ninc = pl[9];
+    const int Nf = Nfl0 + Nfl1 + Nfl2 + Nfl3;
+    const double trunc_c = params[Nmax + Nvis + Nf + Nsplit + Nwidth + Nnoise + Ninc];
+    const int do_amp = (params[Nmax + Nvis + Nf + Nsplit + Nwidth + Nnoise + Ninc + 1] != 0);
+    const double a1 = fabs(params[Nmax + Nvis + Nf]);
+    const double eta0 = params[Nmax + Nvis + Nf + 1], a3 = params[Nmax + Nvis + Nf + 2], asym = params[Nmax + Nvis + Nf + 5];
+    double *model = zeros(N), *noise_abs; long n; int rc = 0, l, m;
+    const int Nfl[4] = {Nfl0, Nfl1, Nfl2, Nfl3};
+    int f_off = 0, h_off = 0;
+    for (l = 0; l <= 3 && !rc; l++) {
+        for (n = 0; n < Nfl[l] && !rc; n++) {
+            const double fl = params[Nmax + Nvis + f_off + n];
+            const double Wl = fabs(params[Nmax + Nvis + Nf + Nsplit + f_off + n]);
+            const int pos0 = (l + 1) * (int)n;
+            double Hlm[7];
+            for (m = -l; m <= l; m++) {
+                double h = params[h_off + pos0 + (m < 0 ? -m : m)];
+                if (do_amp) h = (l == 0) ? (double)(h / (pi * Wl)) : (double)(h / (pi * Wl));
+                Hlm[m + l] = fabs(h);
+            }
+            rc = orc_optimum_lorentzian_calc_a1etaa3_v2(x, N, &model, Hlm, fl, a1, eta0, a3, asym, Wl, l, step, trunc_c);
+        }
+        f_off += Nfl[l];
+        h_off += Nfl[l];      /* the reference indexes the l>=2 heights from Nfl0+Nfl1(+Nfl2), not from Nfl0+2*Nfl1(+3*Nfl2): models.cpp:3285-3289, 3303-3309 */
+    }
+    if (!rc) {
+        noise_abs = (double *)malloc(sizeof(double) * (size_t)(Nnoise > 0 ? Nnoise : 1));
+        abs_copy(params + Nmax + Nvis + Nf + Nsplit + Nwidth, Nnoise, noise_abs);
+        orc_harvey_like(noise_abs, Nnoise, x, N, &model, 0);   /* Nharvey = 0 (models.cpp:3329) */
+        free(noise_abs);
+        memcpy(out, model, sizeof(double) * (size_t)N);
+    }
+    free(model);
+    return rc;
+}
+
 /* tamcmc/sources/models.cpp:1195-1408.  The four omp-parallel loops (l=0, then 1, 2, 3)
  * are run serially in index order. */
 static int model_MS_Global_aj_HarveyLike(const double *params, const int *pl, const double *x, long N, double *out)
@@ -1316,6 +1360,7 @@ int orc_call_model(int model_id, const double *params, const int *plength, const
     /* ORC_MODEL_MS_GLOBAL_A1N_A2A3 (18) and ORC_MODEL_MS_GLOBAL_A1NL_A2A3 (19) compute a model and then print "not tested yet"
      * and exit in the reference (models.cpp:599-603, 993-997): unusable there, ORC_ERR_MODEL here */
     case ORC_MODEL_MS_LOCAL_BASIC:       return model_MS_local_basic(params, plength, x, N, model_out);
+    case ORC_MODEL_MS_LOCAL_HNLM:        return model_MS_local_Hnlm(params, plength, x, N, model_out);
     case ORC_MODEL_MS_GLOBAL_AJ:         return model_MS_Global_aj_HarveyLike(params, plength, x, N, model_out);
     case ORC_MODEL_MS_GLOBAL_AJALM:      return model_MS_Global_ajAlm_HarveyLike(params, plength, x, N, model_out, alm, alm_user);
     default: return ORC_ERR_MODEL;

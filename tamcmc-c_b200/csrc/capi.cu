@@ -81,7 +81,7 @@ int modes_of(int model_id, const int* pl)
     switch (model_id) {
     case 3: case 6: case 7: case 8: case 12: case 13: return pl[0] * (pl[1] + 1);
     // 18 / 19 (a1n / a1nl a2a3) print "not tested yet" and exit in the reference (models.cpp:599-603, 993-997): ERR_MODEL
-    case 11: case 23: return pl[2] + pl[3] + pl[4] + pl[5];
+    case 11: case 14: case 23: return pl[2] + pl[3] + pl[4] + pl[5];
     case TAMCMC_MODEL_ID_MODE_TABLE: return pl[0];
     }
     return -1;

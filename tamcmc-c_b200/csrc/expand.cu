@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         if (threadIdx.x == 0) s_dummy = 0;
         __syncthreads();
         if (threadIdx.x < 32)
-            emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (sd.model_id == 11) ? 0 : (pl[8] - 1) / 3, &s_dummy, threadIdx.x);
+            emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (sd.model_id == 11 || sd.model_id == 14) ? 0 : (pl[8] - 1) / 3, &s_dummy, threadIdx.x);
         __syncthreads();
         const int tile = (blockIdx.y - 1) * blockDim.x + threadIdx.x;
         if (tile >= sd.ntiles) return;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             // warp 0, lanes 0..14: the 3+5+7 entries of amplitude_ratio(l, inc), l = 1..3 (or the ratio parameters)
             const int l = (tid < 3) ? 1 : (tid < 8) ? 2 : 3;
             const int i = tid - ((l == 1) ? 0 : (l == 2) ? 3 : 8) - l;       // m = -l..l
-            const bool have = mode_table ? true : (model == 11) ? (pl[2 + l] >= 1) : (lmax >= l);
+            const bool have = mode_table ? true : (model == 11) ? (pl[2 + l] >= 1) : (model == 14) ? false : (lmax >= l);
             if (have) {
                 if (mode_table) {
                     cm.ratios[l][i + l] = d_amplitude_ratio_entry(l, i, params[1]);
@@ -442,8 +442,8 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             }
         } else if (tid >= 16 && tid <= 18) {
             const int l = tid - 15;
-            const bool have = mode_table ? false : (model == 11) ? (pl[2 + l] >= 1) : (lmax >= l);
-            cm.Vl[l] = (have && model != 11) ? fabs(params[Nmax + l - 1]) : 1.0;
+            const bool have = mode_table ? false : (model == 11 || model == 14) ? false : (lmax >= l);
+            cm.Vl[l] = have ? fabs(params[Nmax + l - 1]) : 1.0;
         } else if (tid == 32) {
             // warp 1, lane 0: scalar parameters and eta0
             cm.trunc_c = mode_table ? params[2] : params[o_cfg];
@@ -471,6 +471,12 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 cm.a3 = params[o_split + 2];
                 cm.asym = params[o_split + 5];
                 break;
+            case 14:                     // model_MS_local_Hnlm: models.cpp:3242-3245
+                cm.a1 = fabs(params[o_split]);
+                cm.eta0 = params[o_split + 1];
+                cm.a3 = params[o_split + 2];
+                cm.asym = params[o_split + 5];
+                break;
             case 11:                     // models.cpp:3059-3075 (Nvis plays the role of lmax)
                 cm.a1 = params[o_split + 3] * params[o_split + 3] + params[o_split + 4] * params[o_split + 4];
                 cm.eta0 = params[o_split + 1];
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             if (cm.status) atomicOr(&s_status, cm.status);
         } else if (tid >= 64 && tid < 96) {
             // warp 2: Harvey-like background parameters, one lane per term
-            emit_noise(noise, params + o_noise, Nnoise, (model == 11) ? 0 : (Nnoise - 1) / 3, &s_status, tid - 64);
+            emit_noise(noise, params + o_noise, Nnoise, (model == 11 || model == 14) ? 0 : (Nnoise - 1) / 3, &s_status, tid - 64);
         }
     }
     __syncthreads();
@@ -537,7 +543,15 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 const double fc = params[o_fl + n];
                 t.have = 1; t.l = l; t.n = n; t.fc = fc; t.hoff = -1; t.eta0 = cm.eta0;
                 for (int k = 0; k < 6; k++) t.a[k] = 0.0;
-                if (model == 11) {
+                if (model == 14) {
+                    // models.cpp:3256-3318: individual widths; heights H(n,l,|m|) at params[base_l + (l+1) n + |m|] with
+                    // base_l = Nfl0, Nfl0+Nfl1, Nfl0+Nfl1+Nfl2 exactly as the reference indexes them (:3270, 3285, 3303)
+                    const int idx = (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0) + n;
+                    t.W = fabs(params[o_width + idx]);
+                    t.H = -1.0;
+                    t.hoff = idx - n + (l + 1) * n;
+                    t.f_s = cm.a1; t.fsw = cm.a1;
+                } else if (model == 11) {
                     // models.cpp:3082-3134: individual heights and widths per mode
                     const int idx = (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0) + n;
                     t.W = fabs(params[o_width + idx]);

@@ -80,9 +80,22 @@ def ms_case(synth, model_id, seed, N=20000, x0=900.0, step=None, Nmax=6, lmax=3,
         params = np.concatenate([H, np.zeros(lmax), fl, split, W, noise, [0.0], [trunc_c, float(do_amp)]])
         pl = np.array([Nf, lmax] + [int(v) for v in Nfl] + [6, Nf, 7, 1, 2], dtype=np.int32)
         return params, pl, x
+    if model_id == 14:
+        # model_MS_local_Hnlm (models.cpp:3198): per-mode widths, heights H(n,l,|m|) ((l+1) per mode), Nsplit=6
+        # [a1, eta0, a3, magb, magalfa, asym], white noise only
+        Nfl = [int(rng.integers(1, 3)) if l <= lmax else 0 for l in range(4)]
+        Nf = int(sum(Nfl))
+        fl = np.sort(rng.uniform(x[0] + 0.15 * span, x[-1] - 0.15 * span, Nf))
+        H = rng.uniform(0.5, 20.0, sum((l + 1) * Nfl[l] for l in range(4)))
+        W = rng.uniform(wmin, wmax, Nf)
+        split = np.array([a1, rng.uniform(0, 1.5e8), rng.uniform(-0.05, 0.05), 0.0, 0.0, asym])
+        noise = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.25])
+        params = np.concatenate([H, np.zeros(lmax), fl, split, W, noise, [0.0], [trunc_c, float(do_amp)]])
+        pl = np.array([len(H), lmax] + [int(v) for v in Nfl] + [6, Nf, 7, 1, 2], dtype=np.int32)
+        return params, pl, x
     raise ValueError(model_id)
 
 
-ALL_MODELS = (3, 6, 7, 8, 11, 12, 13, 23)
+ALL_MODELS = (3, 6, 7, 8, 11, 12, 13, 14, 23)
 # ids 18/19 (a1n/a1nl_a2a3) and a1l_a2a3 print "not tested yet" and exit in the reference (models.cpp:599-603, 798-800, 993-997):
 # they are rejected with ERR_MODEL here; ms_case can still build their parameter vectors for that test
