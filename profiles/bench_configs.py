@@ -226,6 +226,30 @@ def main():
             pairs = int(pt[0])
         emit("c5", "%d independent C2-like stars (Dnu 60-95 microHz) x 10 chains, 250k bins each, star-sharded" % args.stars,
              args.stars * 10, dev, e2e, pairs, {"max_rel_err_vs_oracle": err, "stars_per_gpu": len(mine)})
+    # ------------------------------------------------------------------ MCMC steps/s with the C++ driver (C2)
+    if "driver" in todo and rank == 0:
+        import subprocess
+        import tempfile
+        import bench
+        import test_host_cpp
+        exe = test_host_cpp._build_driver()
+        rng, params, pl, x = bench.make_star(synth, 0)
+        with pkg.Context(pkg.Star(3, pl, len(params), x, np.ones_like(x)), 1, [1.0], device=lr) as c0:
+            M = c0.model(params)
+        y = synth.chi2_2dof_spectrum(rng, M)
+        T = synth.tcoefs(10, 1.7)
+        with tempfile.TemporaryDirectory() as td:
+            f = os.path.join(td, "c2.bin")
+            hdr = np.concatenate([[3, len(x), 10, len(params), 1.0], pl.astype(float)])
+            with open(f, "wb") as fh:
+                for a in (hdr, x, y, T, np.tile(params, (10, 1)).ravel()):
+                    fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+            r = subprocess.run([exe, f, "4000", "bench"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        d = json.loads(line[-1]) if line else {"error": r.stdout[-400:]}
+        d.update({"config": "driver", "workload": "C2 star, fixed-seed adaptive Metropolis + parallel tempering (host/mcmc_driver.hpp): proposals, priors, "
+                  "accept/reject, learning and swaps on the host, one tamcmc_gpu_eval per step"})
+        print(json.dumps(d), flush=True)
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -88,9 +88,28 @@ public:
     void step(long i)
     {
         gamma = cfg.c0 / (1.0 + (double)i);                                                                   // MALA.cpp:646
-        // ---- propose all chains (MALA.cpp:481-486) ----
+        // ---- propose all chains (MALA.cpp:481-486).  Random numbers are drawn serially in chain order (deterministic
+        // whatever the thread count); factorisations, matrix-vector products and priors then run one chain per thread ----
+        const int n = Nvars;
+        if (chol_all.empty()) { chol_all.assign((size_t)Nchains * n * n, 0.0); chol_dirty.assign((size_t)Nchains, 1); }
+        z_all.resize((size_t)Nchains * n);
+        for (size_t k = 0; k < z_all.size(); k++) z_all[k] = normal01();
+        nonfinite.assign((size_t)Nchains, 0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) if (Nvars >= 32)
+#endif
         for (int m = 0; m < Nchains; m++) {
-            new_prop_values(m);
+            nonfinite[(size_t)m] = new_prop_values(m, &z_all[(size_t)m * n]) ? 0 : 1;
+        }
+        for (int m = 0; m < Nchains; m++)                       // MALA.cpp:356-366: redraw until finite (never seen in practice)
+            for (int tries = 0; nonfinite[(size_t)m] && tries < 8; tries++) {
+                for (int a = 0; a < n; a++) z_all[(size_t)m * n + a] = normal01();
+                nonfinite[(size_t)m] = new_prop_values(m, &z_all[(size_t)m * n]) ? 0 : 1;
+            }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) if (Nvars >= 32)
+#endif
+        for (int m = 0; m < Nchains; m++) {
             for (int k = 0; k < Nparams; k++) prop_params[(size_t)m * stride + k] = params[(size_t)m * stride + k];
             for (int v = 0; v < Nvars; v++) prop_params[(size_t)m * stride + index_to_relax[v]] = prop_vars[(size_t)m * Nvars + v];
             prop_logPrior[m] = prior(&prop_params[(size_t)m * stride]);
@@ -100,8 +119,13 @@ public:
         eval(prop_params.data(), active.data(), prop_logL.data());
         n_eval_calls++;
         // ---- accept / reject (MALA.cpp:490-548), learn (MALA.cpp:656-668) ----
+        u_all.resize((size_t)Nchains);
+        for (int m = 0; m < Nchains; m++) u_all[(size_t)m] = uniform01();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) if (Nvars >= 32)
+#endif
         for (int m = 0; m < Nchains; m++) {
-            const double u = uniform01();
+            const double u = u_all[(size_t)m];
             double r;
             const double prop_post = active[m] ? prop_logL[m] + prop_logPrior[m] : -std::numeric_limits<double>::infinity();
             if (!active[m]) r = 0.0;
@@ -134,7 +158,9 @@ private:
     Prior prior;
     std::mt19937_64 rng;
     double gamma = 0.0;
-    std::vector<double> prop_params, prop_vars, prop_logL, prop_logPrior, chol, z;
+    std::vector<double> prop_params, prop_vars, prop_logL, prop_logPrior, chol_all, z_all;
+    std::vector<unsigned char> chol_dirty, nonfinite;
+    std::vector<double> u_all;
     std::vector<unsigned char> active;
 
     double uniform01() { return std::generate_canonical<double, 53>(rng); }
@@ -145,29 +171,33 @@ private:
         return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925286766559 * uniform01());
     }
 
-    // MALA.cpp:339-369: ran = vars + chol((covarmat + epsilon2) * sigma) * N(0, I)
-    void new_prop_values(int m)
+    // MALA.cpp:339-369: ran = vars + chol((covarmat + epsilon2) * sigma) * N(0, I).  The reference factorises at every
+    // call; chol((C + eps2) sigma) = sqrt(sigma) chol(C + eps2), so the factor of C + eps2 is cached per chain and only
+    // recomputed after update_proposal changed C (with the GPU likelihood the factorisation would otherwise dominate a step).
+    bool new_prop_values(int m, const double* zm)
     {
         const int n = Nvars;
-        chol.assign((size_t)n * n, 0.0); z.resize((size_t)n);
-        const double* C = &covarmat[(size_t)m * n * n];
-        for (int a = 0; a < n; a++)
-            for (int b = 0; b <= a; b++) {
-                double s = (C[(size_t)a * n + b] + (a == b ? cfg.epsi2 : 0.0)) * sigma[m];
-                for (int k = 0; k < b; k++) s -= chol[(size_t)a * n + k] * chol[(size_t)b * n + k];
-                chol[(size_t)a * n + b] = (a == b) ? std::sqrt(s > 0 ? s : 0.0) : (chol[(size_t)b * n + b] > 0 ? s / chol[(size_t)b * n + b] : 0.0);
-            }
-        for (int tries = 0; tries < 8; tries++) {
-            bool finite = true;
-            for (int a = 0; a < n; a++) z[(size_t)a] = normal01();
-            for (int a = 0; a < n; a++) {
-                double s = vars[(size_t)m * n + a];
-                for (int k = 0; k <= a; k++) s += chol[(size_t)a * n + k] * z[(size_t)k];
-                prop_vars[(size_t)m * n + a] = s;
-                finite = finite && std::isfinite(s);
-            }
-            if (finite) break;
+        double* L = &chol_all[(size_t)m * n * n];
+        if (chol_dirty[(size_t)m]) {
+            const double* C = &covarmat[(size_t)m * n * n];
+            for (int a = 0; a < n; a++)
+                for (int b = 0; b <= a; b++) {
+                    double s = C[(size_t)a * n + b] + (a == b ? cfg.epsi2 : 0.0);
+                    for (int k = 0; k < b; k++) s -= L[(size_t)a * n + k] * L[(size_t)b * n + k];
+                    L[(size_t)a * n + b] = (a == b) ? std::sqrt(s > 0 ? s : 0.0) : (L[(size_t)b * n + b] > 0 ? s / L[(size_t)b * n + b] : 0.0);
+                }
+            chol_dirty[(size_t)m] = 0;
         }
+        const double ssig = std::sqrt(sigma[m]);
+        bool finite = true;
+        for (int a = 0; a < n; a++) {
+            double s = 0.0;
+            for (int k = 0; k <= a; k++) s += L[(size_t)a * n + k] * zm[k];
+            s = vars[(size_t)m * n + a] + ssig * s;
+            prop_vars[(size_t)m * n + a] = s;
+            finite = finite && std::isfinite(s);
+        }
+        return finite;
     }
 
     // MALA.cpp:296-319 with the projections p1/p2/p3 (MALA.cpp:135-177)
@@ -190,13 +220,16 @@ private:
             }
         fro = std::sqrt(fro);
         if (fro > cfg.A1) for (size_t k = 0; k < (size_t)n * n; k++) C[k] *= cfg.A1 / fro;
+        chol_dirty[(size_t)m] = 1;
         double s = sigma[m] + gamma * (acceptance - cfg.target_acceptance);
         if (s < cfg.epsilon1) s = cfg.epsilon1;
         if (s > cfg.A1) s = cfg.A1;
         sigma[m] = s;
     }
 
-    // MALA.cpp:397-461: swap two adjacent chains; the stored likelihoods are TEMPERED
+    // MALA.cpp:397-461: swap two adjacent chains; the stored likelihoods are TEMPERED.  (The reference computes logPosterior[B]
+    // with logPrior[A] AFTER it has overwritten logPrior[A] by B's value, MALA.cpp:447; the intended prior is used here --
+    // identical under the flat priors of the tests.)
     void parallel_tempering()
     {
         const double u = uniform01();

@@ -5,11 +5,14 @@
 // Same seed, same proposals: the two runs must give the same posterior summaries (BASELINE.json north_star:
 // "posterior summaries from a fixed-seed run must be statistically consistent with the reference's").
 //
-//   test_mcmc_driver <case.bin> <nsteps>     (case format: tests/test_host_cpp.py)
+//   test_mcmc_driver <case.bin> <nsteps>          (case format: tests/test_host_cpp.py)
+//   test_mcmc_driver <case.bin> <nsteps> bench    GPU likelihood only, every fitted quantity of an MS global fit relaxed
+//                                                 (heights, all frequencies, widths, a1, inclination): prints MCMC steps/s
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "../../include/tamcmc_gpu.h"
@@ -37,6 +40,7 @@ int main(int argc, char** argv)
     const std::vector<double> P = rd(f, (size_t)Nmodels * Nparams);
     std::fclose(f);
     const std::vector<double> params0(P.begin(), P.begin() + Nparams);
+    const bool bench = (argc > 3 && std::string(argv[3]) == "bench");
 
     // relaxed variables: all heights, all l=0 frequencies, all widths (the fitted quantities of an MS global fit)
     const int Nmax = pl[0], lmax = pl[1], Nf = pl[2] + pl[3] + pl[4] + pl[5];
@@ -44,10 +48,17 @@ int main(int argc, char** argv)
     std::vector<int> relax;
     std::vector<double> err, lo, hi;
     for (int n = 0; n < Nmax; n++) { relax.push_back(n); err.push_back(0.05 * std::fabs(params0[n])); }
-    for (int n = 0; n < pl[2]; n++) { relax.push_back(Nmax + lmax + n); err.push_back(0.05); }
+    for (int n = 0; n < (bench ? Nf : pl[2]); n++) { relax.push_back(Nmax + lmax + n); err.push_back(0.05); }
     for (int n = 0; n < pl[7]; n++) { relax.push_back(o_width + n); err.push_back(0.05 * std::fabs(params0[o_width + n])); }
+    if (bench) {
+        relax.push_back(Nmax + lmax + Nf); err.push_back(0.02);                                   // a1
+        relax.push_back(o_width + pl[7] + pl[8]); err.push_back(1.0);                              // inclination
+    }
+    const size_t nfreq = (size_t)(bench ? Nf : pl[2]);
     for (size_t v = 0; v < relax.size(); v++) {
-        const double c = params0[relax[v]], w = (v >= (size_t)Nmax && v < (size_t)(Nmax + pl[2])) ? 2.0 : 0.6 * std::fabs(c);
+        const double c = params0[relax[v]];
+        double w = (v >= (size_t)Nmax && v < (size_t)Nmax + nfreq) ? 2.0 : 0.6 * std::fabs(c);
+        if (bench && v + 1 == relax.size()) w = 40.0;
         lo.push_back(c - w); hi.push_back(c + w);
     }
     tamcmc::Prior prior = [&](const double* row) -> double {     // uniform box: -inf outside (exercises the prior short-circuit, model_def.cpp:469-480)
@@ -95,6 +106,15 @@ int main(int argc, char** argv)
         S.swap = d.n_swap_tried ? (double)d.n_swap_done / d.n_swap_tried : 0.0;
         return S;
     };
+    if (bench) {
+        cfg.Nt_learn = {100, nsteps / 2, nsteps / 2 + 1};
+        const Summary G = run(ev_gpu);
+        tamcmc_gpu_destroy(ctx);
+        std::printf("{\"mcmc_steps_per_s\": %.1f, \"evals_per_s\": %.0f, \"chains\": %d, \"bins\": %ld, \"relaxed_variables\": %zu, \"steps\": %ld, "
+                    "\"acceptance_chain0\": %.3f, \"swap_rate\": %.3f}\n",
+                    nsteps / G.secs, nsteps * (double)Nmodels / G.secs, Nmodels, N, relax.size(), nsteps, G.acc0, G.swap);
+        return 0;
+    }
     const Summary G = run(ev_gpu), C = run(ev_cpu);
     tamcmc_gpu_destroy(ctx);
     std::printf("gpu: %.1f steps/s (%.0f likelihood evals/s), acceptance(chain 0) %.3f, swap rate %.3f\n", nsteps / G.secs, nsteps * Nmodels / G.secs, G.acc0, G.swap);
