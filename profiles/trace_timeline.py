@@ -7,16 +7,31 @@ import __graft_entry__ as g
 pkg = g.load_package(); synth = pkg.synth
 import bench
 rng = np.random.default_rng(12345)
-trunc = float(sys.argv[1]) if len(sys.argv) > 1 else 30.0
-params, pl = synth.classic_params(rng, trunc_c=trunc)
-if len(sys.argv) > 2 and int(sys.argv[2]): params[:20] = 0.0
-x = synth.freq_axis(bench.NBINS, 500.0)
-with pkg.Context(pkg.Star(3, pl, len(params), x, np.ones_like(x)), 1, [1.0]) as c0:
-    M = c0.model(params)
-y = synth.chi2_2dof_spectrum(rng, M)
-T = synth.tcoefs(10, 1.7)
-ctx = pkg.Context(pkg.Star(3, pl, len(params), x, y), 10, T)
-P = ctx.pack_params([synth.perturb_chains(rng, params, pl, 10)])
+trunc = float(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1] != "c1" else 30.0
+if len(sys.argv) > 1 and sys.argv[1] == "c1":
+    # red-giant fixture (BASELINE config C1): mode table, 5 chains, ~6100 bins
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_rgb_vectors.npz"))
+    x, y = gold["x"], gold["y"]
+    cap = max(len(gold["rows%d" % i]) for i in range(4)) + 2
+    rows = []
+    for i in (0, 1, 2, 3, 0):
+        params, pl, r = gold["params%d" % i], gold["plength%d" % i], gold["rows%d" % i]
+        o = int(pl[:8].sum()); nn = int(pl[8])
+        rows.append(synth.mode_table_row(cap, abs(params[o + nn]), r[0, 13], r[0, 11], params[o:o + nn], r[:, :11]))
+    rows = np.stack(rows)
+    T = synth.tcoefs(5, 3.5)
+    ctx = pkg.Context(pkg.Star(synth.MODEL_MODE_TABLE, synth.mode_table_plength(cap, nn, 1), rows.shape[1], x, y), 5, T)
+    P = ctx.pack_params([rows])
+else:
+    params, pl = synth.classic_params(rng, trunc_c=trunc)
+    if len(sys.argv) > 2 and int(sys.argv[2]): params[:20] = 0.0
+    x = synth.freq_axis(bench.NBINS, 500.0)
+    with pkg.Context(pkg.Star(3, pl, len(params), x, np.ones_like(x)), 1, [1.0]) as c0:
+        M = c0.model(params)
+    y = synth.chi2_2dof_spectrum(rng, M)
+    T = synth.tcoefs(10, 1.7)
+    ctx = pkg.Context(pkg.Star(3, pl, len(params), x, y), 10, T)
+    P = ctx.pack_params([synth.perturb_chains(rng, params, pl, 10)])
 for _ in range(5): ctx.eval(P)
 n = 148
 buf = np.zeros((n, 64), dtype=np.uint64)

@@ -304,3 +304,35 @@ def test_chi_square_likelihood(pkg, oracle):
                 assert np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)) < RTOL
                 L2, _ = ctx.eval(P)
                 assert np.array_equal(L, L2)
+
+
+def test_tiny_and_large_spectra(pkg, oracle):
+    """Size extremes: the smallest spectra the ABI accepts (2 and 3 bins) and a 3-million-bin spectrum (1954 tiles per chain)."""
+    rng = np.random.default_rng(31)
+    params, pl = pkg.synth.classic_params(rng, Nmax=3, lmax=2, f0=1000.0, dnu=60.0, trunc_c=10.0)
+    for N in (2, 3, 5):
+        x = pkg.synth.freq_axis(N, 1059.0, 0.25)
+        rc, M = oracle.call_model(3, params, pl, x)
+        assert rc == 0
+        y = M * np.linspace(0.5, 1.5, N)
+        rc, L_ref = oracle.eval_chains(3, params[None, :], pl, x, y, [1.0])
+        with _ctx(pkg, 3, params, pl, x, y) as ctx:
+            Mg = ctx.model(params)
+            assert np.max(np.abs(Mg - M) / np.abs(M)) < RTOL
+            L, st = ctx.eval(params[None, :])
+            assert st[0, 0] == 0 and abs(L[0, 0] - L_ref[0]) / abs(L_ref[0]) < RTOL
+    N = 3000000
+    x = pkg.synth.freq_axis(N, 5.0, 0.003)
+    params, pl = pkg.synth.classic_params(rng, Nmax=4, lmax=2, f0=3000.0, dnu=110.0, trunc_c=30.0)
+    rc, M, tr = oracle.call_model(3, params, pl, x, trace=True)
+    assert rc == 0
+    y = pkg.synth.chi2_2dof_spectrum(rng, M)
+    P = pkg.synth.perturb_chains(rng, params, pl, 2)
+    T = [1.0, 1.7]
+    rc, L_ref = oracle.eval_chains(3, P, pl, x, y, T)
+    with _ctx(pkg, 3, params, pl, x, y, 2, T) as ctx:
+        rcw, wl, w0, w1 = ctx.windows(params)
+        assert np.array_equal(w0, tr[1]) and np.array_equal(w1, tr[2])
+        L, st = ctx.eval(P)
+        assert (st == 0).all()
+        assert np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)) < RTOL
