@@ -279,15 +279,20 @@ def main():
     dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
     launches = ctx.launch_count() - launches0
 
-    # ---- timed region 2 (e2e): the C-ABI call with HOST buffers, H2D + D2H inside ----
+    # ---- timed region 2 (e2e): the C-ABI call tamcmc_gpu_eval with HOST buffers (caller-owned numpy arrays, pointers
+    # bound once like a C caller's loop), host->device and device->host transfers inside the call ----
+    L_e2e = np.empty((S, NCHAINS))
+    st_e2e = np.empty((S, NCHAINS), dtype=np.int32)
+    call_e2e = ctx.bind_host_buffers(P_host, L_e2e, st_e2e)
     for _ in range(3):
-        ctx.eval(P_host)
+        assert call_e2e() == 0
+    assert np.array_equal(L_e2e, L_host)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.eval(P_host)
+        call_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist:

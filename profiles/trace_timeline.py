@@ -82,3 +82,13 @@ e = eb[0].astype(np.int64)
 names = ["start", "params staged", "phase1 done", "passA done", "passB done", "passC done", "queue done"]
 print("expand mode-CTA phases (ns since start):", [(names[i], int(e[i] - e[0])) for i in range(1, 7) if e[i]])
 print("expand background CTA: %d ns (starts %d ns after the mode CTA)" % (e[33] - e[32], e[32] - e[0]))
+
+# per-phase cycle accounting of consumer warp 0 (trace slots 48..57), summed over the CTA's tiles
+names = ["wait full", "load x,y", "fast loop", "gen loop", "background", "whittle terms", "shuffle tree", "publish partial", "combine+release", "loop top"]
+ph = b[:, 48:58].astype(np.float64)
+if ph.sum() > 0:
+    live = ph.sum(1) > 0
+    tot = ph[live].sum(1).mean()
+    print("consumer warp 0, cycles per CTA (mean over %d CTAs, total %.0f = %.1f us at 1.93 GHz):" % (live.sum(), tot, tot / 1930.0))
+    for k, nm in enumerate(names):
+        print("  %-16s %9.0f  %5.1f %%" % (nm, ph[live, k].mean(), 100 * ph[live, k].mean() / tot))

@@ -232,6 +232,24 @@ class Context:
         self.last_rc = rc
         return out, st
 
+    def bind_host_buffers(self, params, logL_out, status_out=None, active=None):
+        """Pre-convert caller-owned contiguous host arrays to C pointers for repeated evaluations: returns a zero-argument
+        callable that runs tamcmc_gpu_eval on them and returns its status code (what a C/C++ caller's loop does; skips the
+        per-call numpy/ctypes conversions of eval())."""
+        assert params.dtype == np.float64 and params.flags.c_contiguous and params.size == self.nstars * self.Nchains * self.params_stride
+        assert logL_out.dtype == np.float64 and logL_out.flags.c_contiguous and logL_out.size == self.nstars * self.Nchains
+        fn = lib().tamcmc_gpu_eval
+        h = self.h
+        pp = params.ctypes.data_as(_dp)
+        po = logL_out.ctypes.data_as(_dp)
+        ps = status_out.ctypes.data_as(_ip) if status_out is not None else None
+        pa = active.ctypes.data_as(_ucp) if active is not None else None
+        keep = (params, logL_out, status_out, active)
+
+        def call(_keep=keep):
+            return fn(h, pp, pa, po, ps)
+        return call
+
     def eval_device(self, d_params_ptr, d_logL_ptr, d_active_ptr=None, raw_sum=False, stream=None):
         rc = lib().tamcmc_gpu_eval_device(self.h, C.c_void_p(d_params_ptr), C.c_void_p(d_active_ptr) if d_active_ptr else None,
                                           C.c_void_p(d_logL_ptr), 1 if raw_sum else 0, C.c_void_p(stream) if stream else None)

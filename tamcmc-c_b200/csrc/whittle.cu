@@ -100,8 +100,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
 #ifdef TAMCMC_TRACE
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TRACE(slot, val) do { if (A.trace && (slot) < 64) A.trace[(size_t)blockIdx.x * 64 + (slot)] = (val); } while (0)
+// per-phase cycle accounting of consumer warp 0 (slots 48..57 of the CTA's trace row)
+#define PHASE_DECL long long ph_t = clock64(); long long ph_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PHASE(k) do { if (tid == 0) { const long long now_ = clock64(); ph_acc[k] += now_ - ph_t; ph_t = now_; } } while (0)
+#define PHASE_FLUSH do { if (tid == 0) for (int k_ = 0; k_ < 10; k_++) TRACE(48 + k_, (unsigned long long)ph_acc[k_]); } while (0)
 #else
 #define TRACE(slot, val) do { } while (0)
+#define PHASE_DECL
+#define PHASE(k) do { } while (0)
+#define PHASE_FLUSH do { } while (0)
 #endif
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
 
@@ -353,21 +360,24 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
     // `stagger_ns` apart; the offset persists (bounded by the ring depth), so one warp's epilogue overlaps the others'
     // main loops.
     if (A.stagger_ns > 0 && warp >= 4) __nanosleep((unsigned)A.stagger_ns * (unsigned)(warp >> 2));
+    PHASE_DECL
     for (;;) {
 #ifdef TAMCMC_TRACE
         if (tid == 0) TRACE(tslot, gtime());        // begin waiting for a segment
 #endif
+        PHASE(9);
         mbar_wait(&sm.full[b], use[b] & 1);
         use[b]++;
         const Segment& sg = sm.seg[b];
         const int flags = sg.flags;
+        PHASE(0);
 #ifdef TAMCMC_TRACE
         if (tid == 0) { TRACE(tslot + 1, gtime()); tslot += 2; if (flags & SEG_DONE) TRACE(1, gtime()); }
 #endif
         if (flags & SEG_DONE) {
             // this producer has drained the queue: drop its slot from the round-robin
             done |= 1u << b;
-            if (done == (1u << NBUF) - 1u) return;
+            if (done == (1u << NBUF) - 1u) { PHASE_FLUSH; return; }
             do { b = (b + 1 == NBUF) ? 0 : b + 1; } while ((done >> b) & 1u);
             continue;
         }
@@ -388,6 +398,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
             for (int j = 0; j < BPT; j++) { N[j] = 0.0; D[j] = 1.0; }
         }
 
+        PHASE(1);
         // ---------- fast path: windows cover the whole tile, no masks ----------
         const int tot_fast = sg.nfast;
         if (!asym) {
@@ -479,6 +490,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
         // ---------- general path: window edges and extreme-dynamic-range components.  Every warp owns a
         // contiguous run of 64 bins per register pair (bins 2*tid + 2*NC*pj + r): a run the window covers is merged unmasked, a run holding
         // a window edge under a per-bin mask, the others are skipped; the three-way decision is warp-uniform. ----------
+        PHASE(2);
         const int tot_gen = sg.ngen;
         int gsince[BPT / 2];                       // plain merges of each register pair since its last renormalisation
 #pragma unroll
@@ -529,6 +541,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
             for (int j = 0; j < BPT; j++) renorm(N[j], D[j]);
         }
 
+        PHASE(3);
         if (flags & SEG_LAST) {
             const int sc = sg.sc_index, tile = sg.tile, nvalid = sg.nvalid, lb0 = sg.lb0;
             const double N0 = sg.N0;
@@ -540,9 +553,13 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
                 for (int k = 0; k < NB; k++) cf[k] = sg.bg[k];
 #pragma unroll
                 for (int j = 0; j < BPT; j++) {
+#ifdef TAMCMC_EXP_NO_POLY
+                    double acc = cf[0];
+#else
                     double acc = cf[NB - 1];
 #pragma unroll
                     for (int k = NB - 2; k >= 0; k--) acc = fma(acc, u[j], cf[k]);
+#endif
                     bgv[j] = acc + N0;
                 }
             } else {
@@ -574,6 +591,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
             // ---------- M = N/D + background; Whittle terms.  y_i/M_i is summed; ln M_i is carried as the
             // product of the 1/M_i split exactly into mantissa and integer exponent (no log in this kernel:
             // the finalize kernel takes one log per tile). ----------
+            PHASE(4);
             double s1 = 0.0, pm = 1.0;
             int pe = 0;
             if (A.likelihood == 1) {
@@ -611,12 +629,16 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
             // this segment buffer; the LAST warp to do so combines the slots in warp order (deterministic whatever
             // the arrival order) and stores the tile's partial (sum y/M, mantissa and exponent of prod 1/M).  Nobody
             // waits for anybody: warps that finish early go on to the next segment. ----------
+            PHASE(5);
+#ifndef TAMCMC_EXP_NO_TREE
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
                 s1 += __shfl_down_sync(0xffffffffu, s1, d);
                 pm *= __shfl_down_sync(0xffffffffu, pm, d);     // mantissas in [1,2): 128 of them stay below 2^128
                 pe += __shfl_down_sync(0xffffffffu, pe, d);
             }
+#endif
+            PHASE(6);
             unsigned int prev = 0;
             if (lane == 0) {
                 sm.red_s[b][warp] = s1; sm.red_m[b][warp] = pm; sm.red_e[b][warp] = pe;
@@ -624,6 +646,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
                 prev = atomicAdd(&sm.cnt[b], 1u);
             }
             prev = __shfl_sync(0xffffffffu, prev, 0);
+            PHASE(7);
             if (prev == (unsigned int)(NC / 32 - 1) && lane == 0) {
                 __threadfence_block();
                 sm.cnt[b] = 0u;
@@ -644,6 +667,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
             }
             __syncwarp();
             mbar_arrive(&sm.empty[b]);                    // the slot array of this buffer is free again
+            PHASE(8);
             do { b = (b + 1 == NBUF) ? 0 : b + 1; } while ((done >> b) & 1u);      // next tile: next live slot
         } else {
             mbar_arrive(&sm.empty[b]);                    // more segments of this tile follow in the SAME slot
