@@ -39,6 +39,11 @@ constexpr int CAPG = TAMCMC_CAPG;                          // general entries pe
 constexpr int CAPH = TAMCMC_CAPH;                          // mode headers per segment (asym fast path)
 constexpr int NBUF = 4;                                    // ring slots = producer warps
 constexpr int NPROD = NBUF;
+#ifdef TAMCMC_WARP_ARRIVE
+constexpr int EMPTY_COUNT = NC / 32;                       // one arrival per consumer warp (lane 0): measured 1.3 % SLOWER on C2
+#else
+constexpr int EMPTY_COUNT = NC;                            // every consumer thread arrives on the slot's `empty` barrier
+#endif
 
 enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_WIDE = 64 };
 
@@ -209,9 +214,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
         last_idx = idx;
         if (idx >= ntot) {
             if (use) mbar_wait(empty, (use - 1) & 1);
-            if (lane == 0) { sg->flags = SEG_DONE; atomicOr(&sm.done_mask, 1u << w); mbar_arrive(full); }
-            __syncwarp();
-            mbar_arrive(full);
+            if (lane == 0) { sg->flags = SEG_DONE; atomicOr(&sm.done_mask, 1u << w); mbar_arrive(full); mbar_arrive(full); }
             return;
         }
         const int bucket = __popc(__ballot_sync(0xffffffffu, lane < TAMCMC_NBUCKETS && idx >= cum_inc));
@@ -279,7 +282,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
                         sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
                     }
                     __syncwarp();
-                    mbar_arrive(full);
+                    if (lane == 0) mbar_arrive(full);
                     use++;
                     first = false; cf = cg = ch = 0; seg_wide = 0;
                     mbar_wait(empty, (use - 1) & 1);
@@ -331,7 +334,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
         }
         if (lane < NB) sg->bg[lane] = bgk;
         __syncwarp();
-        mbar_arrive(full);
+        if (lane == 0) mbar_arrive(full);             // 2 arrivals per phase: the opening one (with the TMA byte count) and this
         use++;
     }
 }
@@ -553,13 +556,10 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
                 for (int k = 0; k < NB; k++) cf[k] = sg.bg[k];
 #pragma unroll
                 for (int j = 0; j < BPT; j++) {
-#ifdef TAMCMC_EXP_NO_POLY
-                    double acc = cf[0];
-#else
                     double acc = cf[NB - 1];
 #pragma unroll
-                    for (int k = NB - 2; k >= 0; k--) acc = fma(acc, u[j], cf[k]);
-#endif
+                    for (int k = NB - 2; k >= 0; k--) acc = fma(acc, u[j], cf[k]);      // Horner (Estrin's scheme measured slower:
+                                                                                        // the epilogue is FP64-issue bound, not latency bound)
                     bgv[j] = acc + N0;
                 }
             } else {
@@ -666,11 +666,12 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
                 part[0] = S; part[1] = Mm; part[2] = (double)E;
             }
             __syncwarp();
-            mbar_arrive(&sm.empty[b]);                    // the slot array of this buffer is free again
+            if (EMPTY_COUNT == NC || lane == 0) mbar_arrive(&sm.empty[b]);     // the slot (and its reduction scratch) is free again
             PHASE(8);
             do { b = (b + 1 == NBUF) ? 0 : b + 1; } while ((done >> b) & 1u);      // next tile: next live slot
         } else {
-            mbar_arrive(&sm.empty[b]);                    // more segments of this tile follow in the SAME slot
+            __syncwarp();
+            if (EMPTY_COUNT == NC || lane == 0) mbar_arrive(&sm.empty[b]);     // more segments of this tile follow in the SAME slot
         }
     }
 }
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int i = 0; i < NBUF; i++) { mbar_init(&sm.full[i], 33); mbar_init(&sm.empty[i], NC); sm.cnt[i] = 0u; }
+        for (int i = 0; i < NBUF; i++) { mbar_init(&sm.full[i], 2); mbar_init(&sm.empty[i], EMPTY_COUNT); sm.cnt[i] = 0u; }
         sm.cons_cur = -1; sm.done_mask = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
