@@ -108,6 +108,7 @@ struct tamcmc_gpu_ctx {
     unsigned int qcap = 0;
     int grid_ctas = 0;
     int max_tiles = 0;
+    int tile_bins = TAMCMC_TILE;     // TAMCMC_TILE, or half of it when the full-size tiles would leave most SMs idle
     double *d_x = nullptr, *d_y = nullptr, *d_lnx = nullptr, *d_wsig = nullptr;
     int likelihood = 0;
     double* d_params = nullptr;
@@ -205,7 +206,7 @@ int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned c
     if (prof) CK(cudaEventRecord(c->ev[0], st));
     CK(tamcmc_launch_expand(ea, c->SC(), st));
     if (prof) CK(cudaEventRecord(c->ev[1], st));
-    CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, st, c->use_pdl && !prof));
+    CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, c->tile_bins, st, c->use_pdl && !prof));
     if (prof) CK(cudaEventRecord(c->ev[2], st));
     return TAMCMC_OK;
 }
@@ -338,6 +339,17 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     if (const char* e = std::getenv("TAMCMC_GPU_LOOK")) c->look = (e[0] == '1') ? 1 : 2;
     if (const char* e = std::getenv("TAMCMC_GPU_LOOK_END")) c->look_end = (e[0] == '1') ? 1 : 2;
     c->h_stars.resize(nstars);
+    {
+        // tile size: full-size tiles unless they would give fewer than ~2 work items per SM (spectra of a few thousand
+        // bins: the red-giant slices of BASELINE configs C1/C4); TAMCMC_GPU_TILE overrides
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        long long items = 0;
+        for (int s = 0; s < nstars; s++) items += (long long)Nchains * ((stars[s].N + TAMCMC_TILE - 1) / TAMCMC_TILE);
+        c->tile_bins = (items >= 2LL * sms) ? TAMCMC_TILE : TAMCMC_TILE / 2;
+        if (const char* e = std::getenv("TAMCMC_GPU_TILE")) { const int t = std::atoi(e); if (t == TAMCMC_TILE || t == TAMCMC_TILE / 2) c->tile_bins = t; }
+    }
+    const int TB = c->tile_bins;
     long long off = 0; int tiles = 0; int maxN = 0;
     for (int s = 0; s < nstars; s++) {
         const tamcmc_gpu_star& in = stars[s];
@@ -375,14 +387,15 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         sd.step = sharded ? (in.x_second - in.x_first) : (in.x[1] - in.x[0]);
         if (mode_table && in.plength[1] == 1) sd.step = in.x[2] - in.x[1];      // RGB v4 models: models.cpp:4714
         if (sharded && (in.bin_offset < 0 || in.bin_offset + in.N > in.N_global)) { delete c; return TAMCMC_ERR_ARG; }
-        sd.ntiles = (sd.Nloc + TAMCMC_TILE - 1) / TAMCMC_TILE;
+        sd.ntiles = (sd.Nloc + TB - 1) / TB;
+        sd.tile_bins = TB;
         sd.tile0 = tiles;
         sd.model_id = in.model_id;
         sd.Nparams = in.Nparams;
         sd.nmodes_cap = nm;
         for (int k = 0; k < 11; k++) sd.plength[k] = in.plength[k];
         tiles += sd.ntiles;
-        off += (long long)sd.ntiles * TAMCMC_TILE;
+        off += (long long)sd.ntiles * TB;
         if (in.Nparams > c->params_stride) c->params_stride = in.Nparams;
         if (nm > c->modes_stride) c->modes_stride = nm;
         if (sd.ntiles > c->tiles_stride) c->tiles_stride = sd.ntiles;
@@ -459,7 +472,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
             const StarDesc& sd = c->h_stars[s];
             std::memcpy(&hx[(size_t)sd.off], stars[s].x, sizeof(double) * (size_t)sd.Nloc);
             std::memcpy(&hy[(size_t)sd.off], stars[s].y, sizeof(double) * (size_t)sd.Nloc);
-            for (long long i = sd.Nloc; i < (long long)sd.ntiles * TAMCMC_TILE; i++) hx[(size_t)(sd.off + i)] = stars[s].x[sd.Nloc - 1];
+            for (long long i = sd.Nloc; i < (long long)sd.ntiles * TB; i++) hx[(size_t)(sd.off + i)] = stars[s].x[sd.Nloc - 1];
         }
         CKC(cudaMemcpy(c->d_x, hx.data(), sizeof(double) * off, cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_y, hy.data(), sizeof(double) * off, cudaMemcpyHostToDevice));
@@ -575,7 +588,7 @@ int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, doub
     { int rc = expand_single(c, star, params_row); if (rc) return rc; }
     const StarDesc& sd = c->h_stars[star];
     WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0, false);
-    CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->stream, false));
+    CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->tile_bins, c->stream, false));
     c->launches += 1;
     { const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; }
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));

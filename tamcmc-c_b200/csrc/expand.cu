@@ -357,12 +357,12 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         __syncthreads();
         const int tile = (blockIdx.y - 1) * blockDim.x + threadIdx.x;
         if (tile >= sd.ntiles) return;
-        const int lb0 = tile * TAMCMC_TILE;
-        const int nvalid = min(TAMCMC_TILE, sd.Nloc - lb0);
+        const int lb0 = tile * sd.tile_bins;
+        const int nvalid = min(sd.tile_bins, sd.Nloc - lb0);
         const double* xs = A.x + sd.off + lb0;
         TileRec tr;
         tr.xc = xs[nvalid >> 1];
-        tr.umax = fmax(fabs(xs[0] - tr.xc), fabs(xs[TAMCMC_TILE - 1] - tr.xc));
+        tr.umax = fmax(fabs(xs[0] - tr.xc), fabs(xs[sd.tile_bins - 1] - tr.xc));
         const double lnxc = A.lnx[sd.off + lb0 + (nvalid >> 1)];
         for (int k = 0; k < TAMCMC_BG_TERMS; k++) tr.bg[k] = 0.0;
         bool ok = true;
@@ -682,8 +682,8 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             if (!bad && mr.ncomp > 0) {
                 const int lo = max(i0, sd.bin0) - sd.bin0, hi = min(i1, sd.bin0 + sd.Nloc) - sd.bin0;
                 if (hi > lo) {
-                    atomicAdd(&tcost[lo / TAMCMC_TILE], mr.ncomp);
-                    atomicAdd(&tcost[(hi - 1) / TAMCMC_TILE + 1], -mr.ncomp);
+                    atomicAdd(&tcost[lo / sd.tile_bins], mr.ncomp);
+                    atomicAdd(&tcost[(hi - 1) / sd.tile_bins + 1], -mr.ncomp);
                 }
             }
         }

@@ -69,7 +69,8 @@ cudaError_t tamcmc_expand_configure();
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
 cudaError_t tamcmc_whittle_configure(int* grid_ctas);   // one-time function attributes; returns the persistent grid size
 // pdl: programmatic dependent launch behind the expand kernel on the same stream
-cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st, bool pdl);
+// tile_bins: TAMCMC_TILE or TAMCMC_TILE / 2 (the context's tile size, StarDesc.tile_bins)
+cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, int tile_bins, cudaStream_t st, bool pdl);
 cudaError_t tamcmc_launch_wsig(double* sigma_in_weights_out, long long n, cudaStream_t st);   // in place: w = 1/sigma^2
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st);
 // DFMA throughput microbenchmark: returns achieved FP64 TFLOP/s (2 flops per DFMA)

@@ -15,7 +15,9 @@
 #define TAMCMC_MAX_COMP_PER_MODE 7   // l <= 3 -> 2l+1 <= 7 (reference: acoefs.cpp supports l<=3)
 #define TAMCMC_MAX_HARVEY 8
 #define TAMCMC_BG_TERMS 10           // Taylor coefficients of the Harvey background per tile
+#ifndef TAMCMC_TILE
 #define TAMCMC_TILE 1536             // bins per tile
+#endif
 #ifndef TAMCMC_CONSUMERS
 #define TAMCMC_CONSUMERS 384         // consumer threads per CTA (4 bins per thread); ONE persistent CTA per SM
 #endif
@@ -85,6 +87,7 @@ struct StarDesc {
     int bin0;            // global index of local bin 0
     int tile0;           // first flat tile index
     int ntiles;
+    int tile_bins;       // bins per tile of this context: TAMCMC_TILE, or TAMCMC_TILE / 2 for small problems
     int model_id;
     int Nparams;
     int nmodes_cap;      // modes per chain (capacity == exact count for the MS families)

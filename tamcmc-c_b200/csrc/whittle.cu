@@ -29,8 +29,9 @@ namespace {
 
 constexpr int NC = TAMCMC_CONSUMERS;                       // consumer threads
 constexpr int NT = TAMCMC_THREADS;                         // + producer warp
-constexpr int BPT = TAMCMC_BINS_PER_THREAD;
-constexpr int TILE = TAMCMC_TILE;
+constexpr int BPT_MAX = TAMCMC_BINS_PER_THREAD;            // bins per consumer thread of a full-size tile
+constexpr int TILE_MAX = TAMCMC_TILE;                      // the kernel is instantiated for tiles of TILE_MAX and TILE_MAX / 2 bins
+                                                           // (BPT = 4 and 2): small spectra use the smaller tile so that more SMs get work
 constexpr int GROUP = 16;                                  // fast components merged between two renormalisations
 constexpr int GROUP_WIDE = 4;                              // ... in segments that hold WIDE-range components
 constexpr int NB = TAMCMC_BG_TERMS;
@@ -48,8 +49,8 @@ constexpr int EMPTY_COUNT = NC;                            // every consumer thr
 enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_WIDE = 64 };
 
 struct __align__(16) Segment {
-    double x[TILE];          // TMA destinations: spectrum tile (first segment of a tile) ...
-    double y[TILE];
+    double x[TILE_MAX];      // TMA destinations: spectrum tile (first segment of a tile) ...
+    double y[TILE_MAX];
     FastEntry fast[CAPF];    // ... and the slices of the tile's lists built by the tile-list kernel
     ModeHdr hdr[CAPH];
     GenEntry gen[CAPG];
@@ -170,6 +171,7 @@ __device__ __forceinline__ int next_live(int c, unsigned done_mask)
     return n;
 }
 
+template <int TILE>
 __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
 {
     // lane k < NBUCKETS keeps the inclusive prefix sum of the cost-class counts: item idx lives in the class whose
@@ -342,7 +344,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
 // ------------------------------------------------------------------------------------------------
 // consumer warps
 // ------------------------------------------------------------------------------------------------
-template <bool WRITE_MODEL>
+template <bool WRITE_MODEL, int BPT>
 __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
@@ -499,7 +501,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
 #pragma unroll
         for (int pj = 0; pj < BPT / 2; pj++) gsince[pj] = 0;
         for (int g = 0; g < tot_gen; g++) {
-            const GenEntry ge = sg.gen[g];
+            const GenEntry ge = sg.gen[g];          // (prefetching the next entry measured slower)
             const int ghi = ge.hi & 0xffff;
             const bool heavy = (ge.hi >> 30) & 1;
 #pragma unroll
@@ -701,7 +703,7 @@ __device__ void finalize_chains(const WhittleArgs& A, int warp, int lane, int nw
     }
 }
 
-template <bool WRITE_MODEL>
+template <bool WRITE_MODEL, int BPT>
 __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(WhittleArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -716,8 +718,8 @@ __global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(Whi
     // Programmatic dependent launch: this grid may have been scheduled while the expand kernel was still running (its
     // prologue above overlaps the expander's tail); everything below reads the expander's output.
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (tid >= NC) producer_loop(A, sm, (tid - NC) >> 5, tid & 31);
-    else consumer_loop<WRITE_MODEL>(A, sm, tid);
+    if (tid >= NC) producer_loop<NC * BPT>(A, sm, (tid - NC) >> 5, tid & 31);
+    else consumer_loop<WRITE_MODEL, BPT>(A, sm, tid);
 
     // ---- the LAST CTA to finish turns the per-tile partials into the per-chain results and re-arms the queue ----
     __shared__ unsigned int s_last;
@@ -779,23 +781,27 @@ __global__ void __launch_bounds__(256) tamcmc_dfma_kernel(double* out, int iters
 cudaError_t tamcmc_whittle_configure(int* grid_ctas)
 {
     const int smem = (int)sizeof(Smem);
-    cudaError_t e = cudaFuncSetAttribute(tamcmc_whittle_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tamcmc_whittle_kernel<false, BPT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tamcmc_whittle_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(tamcmc_whittle_kernel<true, BPT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tamcmc_whittle_kernel<false, BPT_MAX / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tamcmc_whittle_kernel<true, BPT_MAX / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, per_sm = 0;
     e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tamcmc_whittle_kernel<false>, NT, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tamcmc_whittle_kernel<false, BPT_MAX>, NT, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     *grid_ctas = sms * per_sm;      // persistent: one CTA per resident slot
     return cudaSuccess;
 }
 
-cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, cudaStream_t st, bool pdl)
+cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, int tile_bins, cudaStream_t st, bool pdl)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid_ctas, 1, 1);
@@ -808,8 +814,15 @@ cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool writ
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     WhittleArgs args = a;
-    if (write_model) return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<true>, args);
-    return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<false>, args);
+    if (tile_bins == TILE_MAX) {
+        if (write_model) return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<true, BPT_MAX>, args);
+        return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<false, BPT_MAX>, args);
+    }
+    if (tile_bins == TILE_MAX / 2) {
+        if (write_model) return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<true, BPT_MAX / 2>, args);
+        return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<false, BPT_MAX / 2>, args);
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st)
