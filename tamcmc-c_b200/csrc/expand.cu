@@ -159,6 +159,31 @@ __device__ __noinline__ double d_eta0_fct(const double* fl0, int n_)
     return 3. * PI / (rho * G);
 }
 
+// The same linear fit and density scaling with the four sums formed by a full warp (lane-strided partial sums, shuffle
+// tree): the result differs from the serial order by rounding only (eta0 feeds nu_nlm, never a bin window).
+__device__ __noinline__ double d_eta0_fct_warp(const double* fl0, int n_, int lane)
+{
+    double sx = 0, sy = 0;
+    for (int i = lane; i < n_; i += 32) { sx += (double)i; sy += fl0[i]; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, d); sy += __shfl_xor_sync(0xffffffffu, sy, d); }
+    const double n = (double)n_;
+    const double mean_x = sx / n;
+    double sty = 0, stt = 0;
+    for (int i = lane; i < n_; i += 32) { const double t = (double)i - mean_x; sty += t * fl0[i]; stt += t * t; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { sty += __shfl_xor_sync(0xffffffffu, sty, d); stt += __shfl_xor_sync(0xffffffffu, stt, d); }
+    (void)sy;
+    const double Dnu_obs = sty / stt;
+    const double G = 6.667e-8, Dnu_sun = 135.1, R_sun = 6.96342e5, M_sun = 1.98855e30;
+    const double PI = 3.14159265358979323846;
+    const double r5 = R_sun * 1e5;
+    const double rho_sun = M_sun * 1e3 / (4 * PI * (r5 * r5 * r5) / 3);
+    const double q = Dnu_obs / Dnu_sun;
+    const double rho = (q * q) * rho_sun;
+    return 3. * PI / (rho * G);
+}
+
 // build_lorentzian.cpp:595-649.  Non-exclusive ifs, last one wins.  Returns 0 on success.
 __device__ __noinline__ int d_set_imin_imax(double x0, double xlast, int N, int l, double fc_l, double gamma_l,
                                double f_s, double c, double step, int* i0, int* i1)
@@ -209,6 +234,7 @@ struct Common {
 
 constexpr int EXP_THREADS = 512;                // 16 warps: the (mode, m) slot pass and the queue pass are latency-bound
 constexpr int EXP_BATCH = 128;                 // modes expanded per pass
+enum : unsigned char { SLOT_DEAD = 0, SLOT_FAST = 1, SLOT_WIDE = 2, SLOT_SLOW = 3, SLOT_NONFINITE = 4 };   // per (mode, m) slot
 constexpr int TILE_BASE_COST = 16;             // per-tile fixed work in (component, bin)-pair units / 1024
 
 // per-mode scratch between the three passes of a batch
@@ -222,6 +248,7 @@ struct ModeTmp {
     double eta0;           // eta0 seen by this mode
     int hoff;              // model 13: offset of the per-m heights in the parameter vector
     int n;
+    int i0, i1, bad;       // bit-exact window of set_imin_imax (pass A), bad != 0: imax - imin <= 0
 };
 
 // Called by ONE FULL WARP: lane k handles Harvey term k; live terms (tau != 0, noise_models.cpp:29) are compacted in
@@ -382,6 +409,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     __shared__ double slot_ia[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
     __shared__ double slot_nu[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
     __shared__ double slot_A[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
+    __shared__ unsigned char slot_cls[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
     __shared__ int s_red[EXP_THREADS / 32];
     __shared__ unsigned int s_bcnt[TAMCMC_NBUCKETS], s_bbase[TAMCMC_NBUCKETS];
     static_assert(TAMCMC_NBUCKETS == (1 << TAMCMC_NBUCKETS_LOG2), "tile class is packed into the low bits");
@@ -444,8 +472,12 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             const int l = tid - 15;
             const bool have = mode_table ? false : (model == 11 || model == 14) ? false : (lmax >= l);
             cm.Vl[l] = have ? fabs(params[Nmax + l - 1]) : 1.0;
-        } else if (tid == 32) {
-            // warp 1, lane 0: scalar parameters and eta0
+        } else if (tid >= 32 && tid < 64) {
+            // warp 1: eta0 by the whole warp (models that use it), then lane 0 files the scalar parameters
+            const bool need_eta = (model == 3 || model == 12 || model == 13 || model == 6 || model == 7 || model == 8) ||
+                                  (model == 23 && params[o_split + 12] == 1);
+            const double eta_w = need_eta ? d_eta0_fct_warp(fl0_all, Nfl0, tid - 32) : 0.0;
+            if (tid == 32) {
             cm.trunc_c = mode_table ? params[2] : params[o_cfg];
             cm.do_amp = mode_table ? 0 : (params[o_cfg + 1] != 0.0);
             cm.ratios[0][0] = 1.0;
@@ -455,19 +487,19 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             switch (model) {
             case 3: case 12: case 13:    // models.cpp:2011-2016, 2219-2222, 2396-2399
                 cm.a1 = fabs(params[o_split]);
-                cm.eta0 = d_eta0_fct(fl0_all, Nfl0);
+                cm.eta0 = eta_w;
                 cm.a3 = params[o_split + 2];
                 cm.asym = params[o_split + 5];
                 break;
             case 6:                      // models.cpp:87-91
                 cm.a11 = fabs(params[o_split]);
                 cm.a12 = fabs(params[o_split + 6]);
-                cm.eta0 = d_eta0_fct(fl0_all, Nfl0);
+                cm.eta0 = eta_w;
                 cm.a3 = params[o_split + 2];
                 cm.asym = params[o_split + 5];
                 break;
             case 7: case 8:              // a1n / a1nl etaa3: models.cpp:290-296, 1075-1081 (splittings per radial order: pass A)
-                cm.eta0 = d_eta0_fct(fl0_all, Nfl0);
+                cm.eta0 = eta_w;
                 cm.a3 = params[o_split + 2];
                 cm.asym = params[o_split + 5];
                 break;
@@ -486,7 +518,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             case 23:                     // models.cpp:1257-1270
                 for (int k = 0; k < 12; k++) cm.aterm[k] = params[o_split + k];
                 cm.asym = params[o_split + 13];
-                cm.eta0 = (params[o_split + 12] == 1) ? d_eta0_fct(fl0_all, Nfl0) : 0.0;
+                cm.eta0 = (params[o_split + 12] == 1) ? eta_w : 0.0;
                 break;
             case TAMCMC_MODEL_ID_MODE_TABLE:   // modes already resolved by a host expander (e.g. models.cpp:4788-4911)
                 cm.asym = params[3];
@@ -499,6 +531,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 break;
             }
             if (cm.status) atomicOr(&s_status, cm.status);
+            }
         } else if (tid >= 64 && tid < 96) {
             // warp 2: Harvey-like background parameters, one lane per term
             emit_noise(noise, params + o_noise, Nnoise, (model == 11 || model == 14) ? 0 : (Nnoise - 1) / 3, &s_status, tid - 64);
@@ -595,6 +628,9 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                     }
                 }
             }
+            // bit-exact window (build_lorentzian.cpp:595-649), one thread per mode
+            if (tid < EXP_BATCH && t.have)
+                t.bad = d_set_imin_imax(sd.x0, sd.xlast, sd.Nglob, t.l, t.fc, t.W, t.fsw, cm.trunc_c, sd.step, &t.i0, &t.i1);
         }
         __syncthreads();
         ETRACE(3);
@@ -617,6 +653,21 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             }
             slot_nu[sl] = nu; slot_A[sl] = h;
             slot_s[sl] = (2.0 / t.W) / sqrt(h); slot_ia[sl] = 1.0 / h;     // scaled FAST form (used if the slot qualifies)
+            // classification against the mode's window.  FAST: t' = (1+e^2)/A stays inside [1e-8, 1e16] over the whole
+            // window, so 16 merges between two exponent renormalisations cannot leave the FP64 range.  WIDE (very narrow
+            // modes, e.g. red-giant mixed modes far narrower than a bin): t' inside [1e-16, 1e32], same scaled form, but the
+            // segments that hold such a mode renormalise every 4 merges.  Everything else live: general (SLOW) form.
+            unsigned char cls = SLOT_DEAD;
+            if (!isfinite(h) || !isfinite(nu)) cls = SLOT_NONFINITE;
+            else if (h != 0.0 && t.W > 0.0) {               // else: contributes exactly 0 (gamma == 0: DESIGN.md deviations)
+                const double xlo = sd.x0 + (double)t.i0 * sd.step, xhi = sd.x0 + (double)t.i1 * sd.step;
+                const double emax = (2.0 / t.W) * fmax(fabs(xlo - nu), fabs(xhi - nu));
+                if (!(emax < 1e100)) cls = SLOT_NONFINITE;
+                else if (h >= 1e-8 && h <= 1e8 && emax < 1e4) cls = SLOT_FAST;
+                else if (h >= 1e-16 && h <= 1e16 && emax < 1e8) cls = SLOT_WIDE;
+                else cls = SLOT_SLOW;
+            }
+            slot_cls[sl] = cls;
         }
         __syncthreads();
         ETRACE(4);
@@ -633,8 +684,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             const int j = base + tid;
             const int l = t.l;
             ModeRec mr;
-            int i0, i1;
-            const int bad = d_set_imin_imax(sd.x0, sd.xlast, sd.Nglob, l, t.fc, t.W, t.fsw, cm.trunc_c, sd.step, &i0, &i1);
+            const int i0 = t.i0, i1 = t.i1, bad = t.bad;
             if (bad) atomicOr(&s_status, TAMCMC_ST_WINDOW);
             mr.i0 = i0; mr.i1 = i1; mr.l = l; mr.fc = t.fc; mr.gamma = t.W;
             mr.qa = cm.asym / t.fc;
@@ -644,36 +694,21 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             if (!isfinite(t.fc) || !isfinite(t.W) || (cm.asym != 0.0 && (!isfinite(mr.qa) || !isfinite(mr.qc))))
                 atomicOr(&s_status, TAMCMC_ST_NONFINITE);
             const double sg = 2.0 / t.W;
-            const double xlo = sd.x0 + (double)i0 * sd.step, xhi = sd.x0 + (double)i1 * sd.step;
             CompRec* out = comps + (size_t)j * TAMCMC_MAX_COMP_PER_MODE;
-            int nf = 0, ns = 0;
-            unsigned fastmask = 0, livemask = 0;
-            int wide = 0;
-            for (int k = 0; k <= 2 * l; k++) {
-                const double Ah = slot_A[tid * TAMCMC_MAX_COMP_PER_MODE + k];
-                const double v = slot_nu[tid * TAMCMC_MAX_COMP_PER_MODE + k];
-                if (!isfinite(Ah) || !isfinite(v)) { atomicOr(&s_status, TAMCMC_ST_NONFINITE); continue; }
-                if (Ah == 0.0 || !(t.W > 0.0)) continue;     // contributes exactly 0 (gamma == 0: DESIGN.md deviations)
-                const double emax = sg * fmax(fabs(xlo - v), fabs(xhi - v));
-                if (!(emax < 1e100)) { atomicOr(&s_status, TAMCMC_ST_NONFINITE); continue; }
-                livemask |= 1u << k;
-                // FAST: t' = (1+e^2)/A stays inside [1e-8, 1e16] over the whole window, so 16 merges between
-                // two exponent renormalisations cannot leave the FP64 range.  WIDE (very narrow modes, e.g. red-giant
-                // mixed modes far narrower than a bin): t' inside [1e-16, 1e32], same scaled form, but the segments
-                // that hold such a mode renormalise every 4 merges.
-                if (Ah >= 1e-8 && Ah <= 1e8 && emax < 1e4) fastmask |= 1u << k;
-                else if (Ah >= 1e-16 && Ah <= 1e16 && emax < 1e8) { fastmask |= 1u << k; wide = 1; }
-            }
+            int nf = 0, ns = 0, wide = 0;
+            // FAST/WIDE components first, then the SLOW ones (classes from pass B)
             for (int pass = 0; pass < 2; pass++)
                 for (int k = 0; k <= 2 * l; k++) {
-                    if (!(livemask & (1u << k))) continue;
-                    const bool fast = (fastmask >> k) & 1u;
+                    const int sl = tid * TAMCMC_MAX_COMP_PER_MODE + k;
+                    const unsigned char cls = slot_cls[sl];
+                    if (cls == SLOT_NONFINITE) { if (pass == 0) atomicOr(&s_status, TAMCMC_ST_NONFINITE); continue; }
+                    if (cls == SLOT_DEAD) continue;
+                    const bool fast = (cls == SLOT_FAST || cls == SLOT_WIDE);
                     if (fast != (pass == 0)) continue;
-                    const double Ah = slot_A[tid * TAMCMC_MAX_COMP_PER_MODE + k];
                     CompRec cr;
-                    cr.nu = slot_nu[tid * TAMCMC_MAX_COMP_PER_MODE + k]; cr.m = k - l;
-                    if (fast) { cr.flags = TAMCMC_CF_FAST; cr.s = slot_s[tid * TAMCMC_MAX_COMP_PER_MODE + k]; cr.a = slot_ia[tid * TAMCMC_MAX_COMP_PER_MODE + k]; nf++; }
-                    else { cr.flags = TAMCMC_CF_SLOW; cr.s = sg; cr.a = Ah; ns++; }
+                    cr.nu = slot_nu[sl]; cr.m = k - l;
+                    if (fast) { cr.flags = TAMCMC_CF_FAST; cr.s = slot_s[sl]; cr.a = slot_ia[sl]; nf++; wide |= (cls == SLOT_WIDE); }
+                    else { cr.flags = TAMCMC_CF_SLOW; cr.s = sg; cr.a = slot_A[sl]; ns++; }
                     out[nf + ns - 1] = cr;
                 }
             mr.nfast = nf | (wide << 16); mr.ncomp = nf + ns;      // bit 16: the mode has WIDE fast components
