@@ -336,3 +336,28 @@ def test_tiny_and_large_spectra(pkg, oracle):
         L, st = ctx.eval(P)
         assert (st == 0).all()
         assert np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)) < RTOL
+
+
+@pytest.mark.parametrize("asym", [0.0, 10.0])
+def test_c2_fullsize_against_reference_golden(pkg, oracle, asym):
+    """BASELINE config C2 at FULL size (250k bins, 80 modes, 10 chains) against the log-likelihoods of the reference's own
+    model + likelihood functions for the same seeded inputs (tests/golden/reference_c2_fullsize.json)."""
+    import importlib.util
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_c2_fullsize", os.path.join(gdir, "make_golden_c2_fullsize.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = json.load(open(os.path.join(gdir, "reference_c2_fullsize.json")))["asym_%g" % asym]
+    params, pl, x, y, P, T = mod.c2_inputs(pkg.synth, oracle, asym)
+    assert abs(y.sum() - gold["y_sum"]) <= 1e-13 * abs(gold["y_sum"])
+    with _ctx(pkg, 3, params, pl, x, y, 10, T) as ctx:
+        L, st = ctx.eval(P)
+        assert (st == 0).all()
+        Lr = np.array(gold["logL_reference"])
+        assert np.max(np.abs(L[0] - Lr) / np.abs(Lr)) < RTOL
+        M0 = ctx.model(P[0])
+        assert abs(M0.sum() - gold["model0_sum"]) <= 1e-11 * abs(gold["model0_sum"])
+        for i, v in gold["model0_at"].items():
+            assert abs(M0[int(i)] - v) <= RTOL * abs(v)

@@ -126,3 +126,21 @@ def test_golden_fixtures_from_reference_cpp(oracle):
         l, fc, gam, fs, c = row
         rc, a, b = oracle.set_imin_imax(wx, int(l), fc, gam, fs, c, step)
         assert rc == 0 and (a, b) == (int(exp[0]), int(exp[1]))
+
+
+def test_c2_fullsize_golden_from_reference(oracle, pkg):
+    """BASELINE config C2 at full size (250k bins, 80 modes, 10 chains): the oracle against the log-likelihoods the REFERENCE's
+    own functions gave for the same seeded inputs (tests/golden/make_golden_c2_fullsize.py)."""
+    import json
+    sys_path_golden = os.path.join(HERE, "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_c2_fullsize", os.path.join(sys_path_golden, "make_golden_c2_fullsize.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = json.load(open(os.path.join(sys_path_golden, "reference_c2_fullsize.json")))
+    params, pl, x, y, P, T = mod.c2_inputs(pkg.synth, oracle, 0.0)
+    gd = gold["asym_0"]
+    assert y.sum() == pytest.approx(gd["y_sum"], rel=1e-13)          # the regenerated inputs are the ones the reference saw
+    rc, L = oracle.eval_chains(3, P[:3], pl, x, y, T[:3])
+    assert rc == 0
+    assert np.max(np.abs(L - np.array(gd["logL_reference"][:3])) / np.abs(L)) < 1e-12
