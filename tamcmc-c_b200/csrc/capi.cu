@@ -38,7 +38,7 @@ using tamcmc_host::fact_i;
 using tamcmc_host::combi_i;
 
 bool g_tables_uploaded[64] = {false};
-int g_grid_ctas[64] = {0};
+int g_grid_ctas[64] = {0}, g_grid_ctas_half[64] = {0};
 
 int upload_tables(int device)
 {
@@ -71,7 +71,7 @@ int upload_tables(int device)
         CK(tamcmc_upload_dmm_tables(&coef[0][0][0], &nnum[0][0], &nden[0]));
     }
     CK(tamcmc_expand_configure());
-    { int g = 0; CK(tamcmc_whittle_configure(&g)); g_grid_ctas[device < 64 && device >= 0 ? device : 0] = g; }
+    { int g = 0, gh = 0; CK(tamcmc_whittle_configure(&g, &gh)); const int d = (device < 64 && device >= 0) ? device : 0; g_grid_ctas[d] = g; g_grid_ctas_half[d] = gh; }
     if (device >= 0 && device < 64) g_tables_uploaded[device] = true;
     return TAMCMC_OK;
 }
@@ -430,7 +430,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     CKC(cudaMemset(c->d_trace, 0, sizeof(unsigned long long) * 64 * 4096));
 #endif
     CKC(cudaMemset(c->d_qctl, 0, sizeof(QueueCtl)));
-    c->grid_ctas = g_grid_ctas[device < 64 ? device : 0];
+    c->grid_ctas = (c->tile_bins == TAMCMC_TILE) ? g_grid_ctas[device < 64 ? device : 0] : g_grid_ctas_half[device < 64 ? device : 0];
     CKC(cudaMalloc(&c->d_x, sizeof(double) * off));
     CKC(cudaMalloc(&c->d_y, sizeof(double) * off));
     CKC(cudaMalloc(&c->d_lnx, sizeof(double) * off));

@@ -67,7 +67,7 @@ cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const d
 cudaError_t tamcmc_upload_dmm_tables(const double* coef, const double* nnum, const double* nden);
 cudaError_t tamcmc_expand_configure();
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
-cudaError_t tamcmc_whittle_configure(int* grid_ctas);   // one-time function attributes; returns the persistent grid size
+cudaError_t tamcmc_whittle_configure(int* grid_full, int* grid_half);   // one-time function attributes; persistent grid sizes for the two tile sizes
 // pdl: programmatic dependent launch behind the expand kernel on the same stream
 // tile_bins: TAMCMC_TILE or TAMCMC_TILE / 2 (the context's tile size, StarDesc.tile_bins)
 cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, int tile_bins, cudaStream_t st, bool pdl);

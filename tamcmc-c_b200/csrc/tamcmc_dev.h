@@ -21,12 +21,17 @@
 #ifndef TAMCMC_CONSUMERS
 #define TAMCMC_CONSUMERS 384         // consumer threads per CTA (4 bins per thread); ONE persistent CTA per SM
 #endif
+#ifndef TAMCMC_PRODUCERS
 #define TAMCMC_PRODUCERS 4           // producer warps per CTA = slots of the shared-memory ring
+#endif
 #define TAMCMC_THREADS (TAMCMC_CONSUMERS + 32 * TAMCMC_PRODUCERS)
 #define TAMCMC_BINS_PER_THREAD (TAMCMC_TILE / TAMCMC_CONSUMERS)
 #define TAMCMC_MAX_TILES 16384       // tiles per star the expander's cost scan supports (16.7M bins)
 #ifndef TAMCMC_MIN_CTAS
-#define TAMCMC_MIN_CTAS 1            // resident CTAs per SM the fused kernel is compiled for
+#define TAMCMC_MIN_CTAS 1            // resident CTAs per SM the fused kernel is compiled for (full-size tiles)
+#endif
+#ifndef TAMCMC_MIN_CTAS_HALF
+#define TAMCMC_MIN_CTAS_HALF 1       // ... half-size tiles (2 was measured: the 64-register cap spills in the main loop, 20 % slower)
 #endif
 
 // generic mode table (public id TAMCMC_MODEL_MODE_TABLE, include/tamcmc_gpu.h): a parameter row is

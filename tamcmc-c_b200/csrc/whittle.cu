@@ -38,7 +38,7 @@ constexpr int NB = TAMCMC_BG_TERMS;
 constexpr int CAPF = TAMCMC_CAPF;                          // fast entries per segment
 constexpr int CAPG = TAMCMC_CAPG;                          // general entries per segment
 constexpr int CAPH = TAMCMC_CAPH;                          // mode headers per segment (asym fast path)
-constexpr int NBUF = 4;                                    // ring slots = producer warps
+constexpr int NBUF = TAMCMC_PRODUCERS;                     // ring slots = producer warps
 constexpr int NPROD = NBUF;
 #ifdef TAMCMC_WARP_ARRIVE
 constexpr int EMPTY_COUNT = NC / 32;                       // one arrival per consumer warp (lane 0): measured 1.3 % SLOWER on C2
@@ -48,9 +48,10 @@ constexpr int EMPTY_COUNT = NC;                            // every consumer thr
 
 enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_WIDE = 64 };
 
+template <int TILE>
 struct __align__(16) Segment {
-    double x[TILE_MAX];      // TMA destinations: spectrum tile (first segment of a tile) ...
-    double y[TILE_MAX];
+    double x[TILE];          // TMA destinations: spectrum tile (first segment of a tile) ...
+    double y[TILE];
     FastEntry fast[CAPF];    // ... and the slices of the tile's lists built by the tile-list kernel
     ModeHdr hdr[CAPH];
     GenEntry gen[CAPG];
@@ -61,8 +62,9 @@ struct __align__(16) Segment {
     long long off;           // offset of the tile in the concatenated arrays
 };
 
+template <int TILE>
 struct Smem {
-    Segment seg[NBUF];
+    Segment<TILE> seg[NBUF];
     unsigned long long full[NBUF], empty[NBUF];
     double red_s[NBUF][NC / 32];
     double red_m[NBUF][NC / 32];
@@ -172,7 +174,7 @@ __device__ __forceinline__ int next_live(int c, unsigned done_mask)
 }
 
 template <int TILE>
-__device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
+__device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int lane)
 {
     // lane k < NBUCKETS keeps the inclusive prefix sum of the cost-class counts: item idx lives in the class whose
     // prefix first exceeds it
@@ -190,7 +192,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
     const unsigned G = gridDim.x;
     const unsigned nstatic = (unsigned)NPROD * G;
     const unsigned endgame_from = (ntot > 4u * G) ? ntot - 4u * G : 0u;
-    Segment* const sg = &sm.seg[w];
+    Segment<TILE>* const sg = &sm.seg[w];
     unsigned long long* const full = &sm.full[w];
     unsigned long long* const empty = &sm.empty[w];
     unsigned use = 0;                 // segments published in this slot so far
@@ -345,7 +347,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem& sm, int w, int lane)
 // consumer warps
 // ------------------------------------------------------------------------------------------------
 template <bool WRITE_MODEL, int BPT>
-__device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
+__device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
     unsigned use[NBUF];
@@ -373,7 +375,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem& sm, int tid)
         PHASE(9);
         mbar_wait(&sm.full[b], use[b] & 1);
         use[b]++;
-        const Segment& sg = sm.seg[b];
+        const Segment<NC * BPT>& sg = sm.seg[b];
         const int flags = sg.flags;
         PHASE(0);
 #ifdef TAMCMC_TRACE
@@ -703,11 +705,18 @@ __device__ void finalize_chains(const WhittleArgs& A, int warp, int lane, int nw
     }
 }
 
+// Full-size tiles: one CTA per SM.  Half-size tiles: compiled for TWO resident CTAs per SM (64 registers per thread, 2 x 107 KB
+// of shared memory): the two CTAs work on different tiles, so one CTA's latency-bound phases (tile epilogue, window edges,
+// start-up) overlap the other's FP64 main loop.
 template <bool WRITE_MODEL, int BPT>
-__global__ void __launch_bounds__(NT, TAMCMC_MIN_CTAS) tamcmc_whittle_kernel(WhittleArgs A)
+#ifdef TAMCMC_MAXNREG
+__global__ void __maxnreg__(TAMCMC_MAXNREG) tamcmc_whittle_kernel(WhittleArgs A)
+#else
+__global__ void __launch_bounds__(NT, (BPT == BPT_MAX) ? TAMCMC_MIN_CTAS : TAMCMC_MIN_CTAS_HALF) tamcmc_whittle_kernel(WhittleArgs A)
+#endif
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    Smem<NC * BPT>& sm = *reinterpret_cast<Smem<NC * BPT>*>(smem_raw);
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < NBUF; i++) { mbar_init(&sm.full[i], 2); mbar_init(&sm.empty[i], EMPTY_COUNT); sm.cnt[i] = 0u; }
@@ -778,27 +787,31 @@ __global__ void __launch_bounds__(256) tamcmc_dfma_kernel(double* out, int iters
 
 }  // namespace
 
-cudaError_t tamcmc_whittle_configure(int* grid_ctas)
+template <bool WM, int BPT>
+static cudaError_t configure_one(int sms, int* grid)
 {
-    const int smem = (int)sizeof(Smem);
-    cudaError_t e = cudaFuncSetAttribute(tamcmc_whittle_kernel<false, BPT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = (int)sizeof(Smem<NC * BPT>);
+    cudaError_t e = cudaFuncSetAttribute(tamcmc_whittle_kernel<WM, BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tamcmc_whittle_kernel<true, BPT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tamcmc_whittle_kernel<WM, BPT>, NT, smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tamcmc_whittle_kernel<false, BPT_MAX / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tamcmc_whittle_kernel<true, BPT_MAX / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0, sms = 0, per_sm = 0;
-    e = cudaGetDevice(&dev);
+    if (per_sm < 1) per_sm = 1;
+    if (grid) *grid = sms * per_sm;      // persistent: one CTA per resident slot
+    return cudaSuccess;
+}
+
+cudaError_t tamcmc_whittle_configure(int* grid_full, int* grid_half)
+{
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tamcmc_whittle_kernel<false, BPT_MAX>, NT, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    *grid_ctas = sms * per_sm;      // persistent: one CTA per resident slot
-    return cudaSuccess;
+    if ((e = configure_one<false, BPT_MAX>(sms, grid_full)) != cudaSuccess) return e;
+    if ((e = configure_one<true, BPT_MAX>(sms, nullptr)) != cudaSuccess) return e;
+    if ((e = configure_one<false, BPT_MAX / 2>(sms, grid_half)) != cudaSuccess) return e;
+    return configure_one<true, BPT_MAX / 2>(sms, nullptr);
 }
 
 cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, int tile_bins, cudaStream_t st, bool pdl)
@@ -806,7 +819,6 @@ cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool writ
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid_ctas, 1, 1);
     cfg.blockDim = dim3(NT, 1, 1);
-    cfg.dynamicSmemBytes = sizeof(Smem);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -815,10 +827,12 @@ cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool writ
     cfg.numAttrs = pdl ? 1 : 0;
     WhittleArgs args = a;
     if (tile_bins == TILE_MAX) {
+        cfg.dynamicSmemBytes = sizeof(Smem<TILE_MAX>);
         if (write_model) return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<true, BPT_MAX>, args);
         return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<false, BPT_MAX>, args);
     }
     if (tile_bins == TILE_MAX / 2) {
+        cfg.dynamicSmemBytes = sizeof(Smem<TILE_MAX / 2>);
         if (write_model) return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<true, BPT_MAX / 2>, args);
         return cudaLaunchKernelEx(&cfg, tamcmc_whittle_kernel<false, BPT_MAX / 2>, args);
     }
