@@ -139,27 +139,8 @@ __device__ __noinline__ double d_lin_interpol(const double* x, const double* y, 
     return a * x_int + b;
 }
 
-// linfit.cpp:17-35 with x = 0..n-1 (models.cpp:6065-6071), then models.cpp:6073-6084
-__device__ __noinline__ double d_eta0_fct(const double* fl0, int n_)
-{
-    double sx = 0, sy = 0, sty = 0, stt = 0;
-    const double n = (double)n_;
-    for (int i = 0; i < n_; i++) sx += (double)i;
-    for (int i = 0; i < n_; i++) sy += fl0[i];
-    const double mean_x = sx / n;
-    for (int i = 0; i < n_; i++) { double t = (double)i - mean_x; sty += t * fl0[i]; }
-    for (int i = 0; i < n_; i++) { double t = (double)i - mean_x; stt += t * t; }
-    const double Dnu_obs = sty / stt;
-    const double G = 6.667e-8, Dnu_sun = 135.1, R_sun = 6.96342e5, M_sun = 1.98855e30;
-    const double PI = 3.14159265358979323846;
-    const double r5 = R_sun * 1e5;
-    const double rho_sun = M_sun * 1e3 / (4 * PI * (r5 * r5 * r5) / 3);
-    const double q = Dnu_obs / Dnu_sun;
-    const double rho = (q * q) * rho_sun;
-    return 3. * PI / (rho * G);
-}
-
-// The same linear fit and density scaling with the four sums formed by a full warp (lane-strided partial sums, shuffle
+// linfit.cpp:17-35 with x = 0..n-1 (models.cpp:6065-6071), then eta0 = 3 pi / (rho G), rho = (Dnu/135.1)^2 rho_sun (models.cpp:6073-6084),
+// with the four sums formed by a full warp (lane-strided partial sums, shuffle
 // tree): the result differs from the serial order by rounding only (eta0 feeds nu_nlm, never a bin window).
 __device__ __noinline__ double d_eta0_fct_warp(const double* fl0, int n_, int lane)
 {
@@ -395,7 +376,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         bool ok = true;
         for (int h = 0; h < s_nz.nh && ok; h++)
             ok = harvey_series(s_nz.H[h], s_nz.lnsc[h], s_nz.pw[h], s_nz.cpi[h], s_nz.spi[h], s_nz.binom[h], tr.xc, lnxc, tr.umax, tr.bg);
-        TileRec* dst = A.tilerec + (size_t)sc * A.tiles_stride + tile;     // list descriptor fields: tile-list kernel
+        TileRec* dst = A.tilerec + (size_t)sc * A.tiles_stride + tile;
         for (int k = 0; k < TAMCMC_BG_TERMS; k++) dst->bg[k] = tr.bg[k];
         dst->xc = tr.xc; dst->umax = tr.umax; dst->series_ok = ok ? 1 : 0;
         ETRACE(1);

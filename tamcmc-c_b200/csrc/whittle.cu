@@ -52,7 +52,7 @@ template <int TILE>
 struct __align__(16) Segment {
     double x[TILE];          // TMA destinations: spectrum tile (first segment of a tile) ...
     double y[TILE];
-    FastEntry fast[CAPF];    // ... and the slices of the tile's lists built by the tile-list kernel
+    FastEntry fast[CAPF];    // ... and the tile's component lists, written by the slot's producer warp
     ModeHdr hdr[CAPH];
     GenEntry gen[CAPG];
     double bg[NB];           // background Taylor coefficients in u
@@ -594,7 +594,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
 
             // ---------- M = N/D + background; Whittle terms.  y_i/M_i is summed; ln M_i is carried as the
             // product of the 1/M_i split exactly into mantissa and integer exponent (no log in this kernel:
-            // the finalize kernel takes one log per tile). ----------
+            // the per-chain finalisation takes one log per tile). ----------
             PHASE(4);
             double s1 = 0.0, pm = 1.0;
             int pe = 0;

@@ -361,3 +361,32 @@ def test_c2_fullsize_against_reference_golden(pkg, oracle, asym):
         assert abs(M0.sum() - gold["model0_sum"]) <= 1e-11 * abs(gold["model0_sum"])
         for i, v in gold["model0_at"].items():
             assert abs(M0[int(i)] - v) <= RTOL * abs(v)
+
+
+def test_device_entry_graph_cache_rotation(pkg, oracle):
+    """tamcmc_gpu_eval_device keeps one CUDA graph per (params, active, out) pointer set (4 entries): rotating through more
+    buffer sets than that must evict and re-capture without changing results; a caller stream is honoured."""
+    import torch
+    params, pl, x = _cases.ms_case(pkg.synth, 3, seed=17, N=9000)
+    rc, M = oracle.call_model(3, params, pl, x)
+    rng = np.random.default_rng(2)
+    y = pkg.synth.chi2_2dof_spectrum(rng, M)
+    T = pkg.synth.tcoefs(3, 1.7)
+    sets = [pkg.synth.perturb_chains(rng, params, pl, 3) for _ in range(6)]
+    refs = [oracle.eval_chains(3, P, pl, x, y, T)[1] for P in sets]
+    stream = torch.cuda.Stream()
+    with _ctx(pkg, 3, params, pl, x, y, 3, T) as ctx:
+        dP = [torch.tensor(ctx.pack_params(P), device="cuda") for P in sets]
+        dL = [torch.zeros(3, dtype=torch.float64, device="cuda") for _ in sets]
+        for rnd in range(3):
+            for k in range(6):
+                with torch.cuda.stream(stream):
+                    ctx.eval_device(dP[k].data_ptr(), dL[k].data_ptr(), stream=stream.cuda_stream)
+            stream.synchronize()
+            for k in range(6):
+                got = dL[k].cpu().numpy()
+                assert np.max(np.abs(got - refs[k]) / np.abs(refs[k])) < RTOL
+                dL[k].zero_()
+        # host entry interleaved with the device entry on the same context
+        L, st = ctx.eval(sets[2])
+        assert np.max(np.abs(L[0] - refs[2]) / np.abs(refs[2])) < RTOL
