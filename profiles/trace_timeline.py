@@ -81,6 +81,8 @@ rc = pkg.lib().tamcmc_gpu_debug_trace(ctx.h, eb.ctypes.data_as(C.POINTER(C.c_ulo
 e = eb[0].astype(np.int64)
 names = ["start", "params staged", "phase1 done", "passA done", "passB done", "passC done", "queue done"]
 print("expand mode-CTA phases (ns since start):", [(names[i], int(e[i] - e[0])) for i in range(1, 7) if e[i]])
+sub = [("ratios (warp 0)", 8), ("eta0 + scalars (warp 1)", 9), ("noise record (warp 2)", 10), ("pass A before windows (thread 5)", 11)]
+print("expand sub-phases (ns since start):", [(nm, int(e[k] - e[0])) for nm, k in sub if e[k]])
 print("expand background CTA: %d ns (starts %d ns after the mode CTA)" % (e[33] - e[32], e[32] - e[0]))
 
 # per-phase cycle accounting of consumer warp 0 (trace slots 48..57), summed over the CTA's tiles

@@ -57,8 +57,11 @@ namespace {
 #ifdef TAMCMC_TRACE
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define ETRACE(slot) do { if (A.trace && threadIdx.x == 0 && blockIdx.x == 0) A.trace[(blockIdx.y ? 32 : 0) + (slot)] = gtime(); } while (0)
+// stamp written by an arbitrary thread of CTA (0, 0) (sub-phases of one warp)
+#define ETRACE_T(slot, thread) do { if (A.trace && threadIdx.x == (thread) && blockIdx.x == 0 && blockIdx.y == 0) A.trace[(slot)] = gtime(); } while (0)
 #else
 #define ETRACE(slot) do { } while (0)
+#define ETRACE_T(slot, thread) do { } while (0)
 #endif
 
 __device__ __forceinline__ double Phi(int s, int l, int m) { return c_Pslm_hi[s][l][m + 3]; }
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                     cm.ratios[l][i + l] = d_amplitude_ratio_entry(l, i, inc);
                 }
             }
+            ETRACE_T(8, 14);
         } else if (tid >= 16 && tid <= 18) {
             const int l = tid - 15;
             const bool have = mode_table ? false : (model == 11 || model == 14) ? false : (lmax >= l);
@@ -513,9 +517,11 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             }
             if (cm.status) atomicOr(&s_status, cm.status);
             }
+            ETRACE_T(9, 32);
         } else if (tid >= 64 && tid < 96) {
             // warp 2: Harvey-like background parameters, one lane per term
             emit_noise(noise, params + o_noise, Nnoise, (model == 11 || model == 14) ? 0 : (Nnoise - 1) / 3, &s_status, tid - 64);
+            ETRACE_T(10, 64);
         }
     }
     __syncthreads();
@@ -609,6 +615,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                     }
                 }
             }
+            ETRACE_T(11, 5);
             // bit-exact window (build_lorentzian.cpp:595-649), one thread per mode
             if (tid < EXP_BATCH && t.have)
                 t.bad = d_set_imin_imax(sd.x0, sd.xlast, sd.Nglob, t.l, t.fc, t.W, t.fsw, cm.trunc_c, sd.step, &t.i0, &t.i1);
