@@ -245,10 +245,16 @@ def main():
                 for a in (hdr, x, y, T, np.tile(params, (10, 1)).ravel()):
                     fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
             r = subprocess.run([exe, f, "4000", "bench"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            r2 = subprocess.run([exe, f, "600", "batch", "32"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         line = [l for l in r.stdout.splitlines() if l.startswith("{")]
         d = json.loads(line[-1]) if line else {"error": r.stdout[-400:]}
         d.update({"config": "driver", "workload": "C2 star, fixed-seed adaptive Metropolis + parallel tempering (host/mcmc_driver.hpp): proposals, priors, "
                   "accept/reject, learning and swaps on the host, one tamcmc_gpu_eval per step"})
+        print(json.dumps(d), flush=True)
+        line = [l for l in r2.stdout.splitlines() if l.startswith("{")]
+        d = json.loads(line[-1]) if line else {"error": r2.stdout[-400:]}
+        d.update({"config": "driver_batch", "workload": "32 independent C2 stars driven by BatchDriver: one tamcmc_gpu_eval of 320 chains per step, "
+                  "host halves one star per OpenMP thread"})
         print(json.dumps(d), flush=True)
     if dist:
         dist.barrier()

@@ -22,7 +22,9 @@
 #include <cstddef>
 #include <cstdint>
 #include <functional>
+#include <algorithm>
 #include <limits>
+#include <memory>
 #include <random>
 #include <vector>
 
@@ -55,8 +57,10 @@ public:
     long n_swap_tried = 0, n_swap_done = 0, n_eval_calls = 0;
     std::vector<long> n_accept;
 
+    // defer_initial_eval: the caller evaluates `params` itself (BatchDriver: one launch for all stars) and reports the result
+    // through set_initial_logL()
     Driver(const DriverConfig& cfg_, int Nparams_, int stride_, const std::vector<double>& params0, const std::vector<int>& relax_index,
-           const std::vector<double>& errors, Evaluator ev, Prior pr)
+           const std::vector<double>& errors, Evaluator ev, Prior pr, bool defer_initial_eval = false)
         : cfg(cfg_), Nchains(cfg_.Nchains), Nparams(Nparams_), stride(stride_), Nvars((int)relax_index.size()), index_to_relax(relax_index),
           eval(std::move(ev)), prior(std::move(pr)), rng(cfg_.seed)
     {
@@ -79,13 +83,39 @@ public:
         prop_params = params; prop_vars = vars; prop_logL = logLikelihood; prop_logPrior = logLikelihood; active.assign(Nchains, 1);
         // initial model (Model_def constructor, model_def.cpp:142-147)
         for (int m = 0; m < Nchains; m++) { logPrior[m] = prior(&params[(size_t)m * stride]); active[m] = std::isinf(logPrior[m]) ? 0 : 1; }
-        eval(params.data(), active.data(), logLikelihood.data());
-        n_eval_calls++;
-        for (int m = 0; m < Nchains; m++) logPosterior[m] = active[m] ? logLikelihood[m] + logPrior[m] : -std::numeric_limits<double>::infinity();
+        if (!defer_initial_eval) {
+            eval(params.data(), active.data(), logLikelihood.data());
+            n_eval_calls++;
+            set_initial_logL(logLikelihood.data());
+        }
     }
+
+    void set_initial_logL(const double* logL)
+    {
+        for (int m = 0; m < Nchains; m++) {
+            logLikelihood[m] = logL[m];
+            logPosterior[m] = active[m] ? logLikelihood[m] + logPrior[m] : -std::numeric_limits<double>::infinity();
+        }
+    }
+
+    // buffers of the two-phase interface (propose -> caller evaluates -> finish)
+    const double* proposal_params() const { return prop_params.data(); }
+    const unsigned char* active_mask() const { return active.data(); }
+    double* proposal_logL() { return prop_logL.data(); }
+    int row_stride() const { return stride; }
 
     // one iteration i of MALA::execute (MALA.cpp:646-700)
     void step(long i)
+    {
+        propose(i);
+        // ---- ONE batched evaluation (was: generate_model per chain inside the OpenMP loop) ----
+        eval(prop_params.data(), active.data(), prop_logL.data());
+        n_eval_calls++;
+        finish(i);
+    }
+
+    // first half of an iteration: new positions and their priors for every chain
+    void propose(long i)
     {
         gamma = cfg.c0 / (1.0 + (double)i);                                                                   // MALA.cpp:646
         // ---- propose all chains (MALA.cpp:481-486).  Random numbers are drawn serially in chain order (deterministic
@@ -115,9 +145,11 @@ public:
             prop_logPrior[m] = prior(&prop_params[(size_t)m * stride]);
             active[m] = (prop_logPrior[m] == -std::numeric_limits<double>::infinity()) ? 0 : 1;               // model_def.cpp:469
         }
-        // ---- ONE batched evaluation (was: generate_model per chain inside the OpenMP loop) ----
-        eval(prop_params.data(), active.data(), prop_logL.data());
-        n_eval_calls++;
+    }
+
+    // second half: proposal_logL() holds the tempered log-likelihoods of proposal_params()
+    void finish(long i)
+    {
         // ---- accept / reject (MALA.cpp:490-548), learn (MALA.cpp:656-668) ----
         u_all.resize((size_t)Nchains);
         for (int m = 0; m < Nchains; m++) u_all[(size_t)m] = uniform01();
@@ -249,6 +281,54 @@ private:
             n_swap_done++;
         }
     }
+};
+
+// Many independent stars (BASELINE config C5; the reference runs one process per star, scripts/slurm/job.sh): one Driver per
+// star, all proposals of all stars evaluated by ONE batched call per step.  Stars are independent, so their host halves run one
+// star per OpenMP thread; every Driver owns its seeded generator, so results do not depend on the thread count.
+using BatchEvaluator = std::function<int(const double* /*[nstars][Nchains][stride]*/, const unsigned char* /*[nstars][Nchains]*/,
+                                         double* /*[nstars][Nchains]*/)>;
+class BatchDriver {
+public:
+    std::vector<std::unique_ptr<Driver>> stars;
+    BatchDriver(std::vector<std::unique_ptr<Driver>> d, BatchEvaluator ev) : stars(std::move(d)), eval(std::move(ev))
+    {
+        const size_t S = stars.size();
+        Nchains = stars[0]->n_chains(); stride = stars[0]->row_stride();
+        P.assign(S * Nchains * stride, 0.0); act.assign(S * Nchains, 1); L.assign(S * Nchains, 0.0);
+        // initial models of all stars in one launch (Model_def constructor, model_def.cpp:142-147)
+        for (size_t s = 0; s < S; s++) {
+            std::copy(stars[s]->params.begin(), stars[s]->params.end(), P.begin() + s * Nchains * stride);
+            std::copy(stars[s]->active_mask(), stars[s]->active_mask() + Nchains, act.begin() + s * Nchains);
+        }
+        eval(P.data(), act.data(), L.data());
+        for (size_t s = 0; s < S; s++) stars[s]->set_initial_logL(&L[s * Nchains]);
+    }
+    void step(long i)
+    {
+        const long S = (long)stars.size();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+        for (long s = 0; s < S; s++) {
+            stars[(size_t)s]->propose(i);
+            std::copy(stars[(size_t)s]->proposal_params(), stars[(size_t)s]->proposal_params() + (size_t)Nchains * stride, P.begin() + (size_t)s * Nchains * stride);
+            std::copy(stars[(size_t)s]->active_mask(), stars[(size_t)s]->active_mask() + Nchains, act.begin() + (size_t)s * Nchains);
+        }
+        eval(P.data(), act.data(), L.data());
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+        for (long s = 0; s < S; s++) {
+            std::copy(L.begin() + (size_t)s * Nchains, L.begin() + (size_t)(s + 1) * Nchains, stars[(size_t)s]->proposal_logL());
+            stars[(size_t)s]->finish(i);
+        }
+    }
+private:
+    BatchEvaluator eval;
+    int Nchains = 0, stride = 0;
+    std::vector<double> P, L;
+    std::vector<unsigned char> act;
 };
 
 }  // namespace tamcmc

@@ -6,12 +6,16 @@
 // "posterior summaries from a fixed-seed run must be statistically consistent with the reference's").
 //
 //   test_mcmc_driver <case.bin> <nsteps>          (case format: tests/test_host_cpp.py)
+//   test_mcmc_driver <case.bin> <nsteps> batch <nstars>   nstars independent copies of the star (different seeds) driven by
+//                                                 BatchDriver: one tamcmc_gpu_eval per step for all stars; checks that star 0
+//                                                 reproduces the single-star run bit for bit, prints aggregate star-steps/s
 //   test_mcmc_driver <case.bin> <nsteps> bench    GPU likelihood only, every fitted quantity of an MS global fit relaxed
 //                                                 (heights, all frequencies, widths, a1, inclination): prints MCMC steps/s
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -40,7 +44,9 @@ int main(int argc, char** argv)
     const std::vector<double> P = rd(f, (size_t)Nmodels * Nparams);
     std::fclose(f);
     const std::vector<double> params0(P.begin(), P.begin() + Nparams);
-    const bool bench = (argc > 3 && std::string(argv[3]) == "bench");
+    const bool batch = (argc > 4 && std::string(argv[3]) == "batch");
+    const int nbatch = batch ? std::atoi(argv[4]) : 0;
+    const bool bench = (argc > 3 && std::string(argv[3]) == "bench") || batch;
 
     // relaxed variables: all heights, all l=0 frequencies, all widths (the fitted quantities of an MS global fit)
     const int Nmax = pl[0], lmax = pl[1], Nf = pl[2] + pl[3] + pl[4] + pl[5];
@@ -106,6 +112,39 @@ int main(int argc, char** argv)
         S.swap = d.n_swap_tried ? (double)d.n_swap_done / d.n_swap_tried : 0.0;
         return S;
     };
+    if (batch) {
+        // ---- C5-style: nbatch independent stars, one batched evaluation per step ----
+        cfg.Nt_learn = {100, nsteps / 2, nsteps / 2 + 1};
+        const Summary single = run(ev_gpu);                    // reference: star 0 alone
+        tamcmc_gpu_destroy(ctx);
+        std::vector<tamcmc_gpu_star> ss((size_t)nbatch, s);
+        tamcmc_gpu_ctx* bctx = nullptr;
+        rc = tamcmc_gpu_create(0, nbatch, ss.data(), Nmodels, Tcoefs.data(), p, TAMCMC_LIKELIHOOD_CHI22P, &bctx);
+        if (rc) { std::printf("tamcmc_gpu_create(batch): %s %s\n", tamcmc_gpu_strerror(rc), tamcmc_gpu_last_error()); return 1; }
+        std::vector<std::unique_ptr<tamcmc::Driver>> ds;
+        for (int k = 0; k < nbatch; k++) {
+            tamcmc::DriverConfig c = cfg;
+            c.seed = cfg.seed + (std::uint64_t)k;               // star 0 keeps the seed of the single-star run
+            ds.emplace_back(new tamcmc::Driver(c, Nparams, stride, params0, relax, err, tamcmc::Evaluator(), prior, true));
+        }
+        tamcmc::BatchDriver bd(std::move(ds), [&](const double* pr, const unsigned char* act, double* L) { return tamcmc_gpu_eval(bctx, pr, act, L, nullptr); });
+        const int nv = bd.stars[0]->n_vars();
+        std::vector<double> s1(nv, 0.0);
+        long cnt = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (long i = 0; i < nsteps; i++) {
+            bd.step(i);
+            if (i >= nsteps / 2) { for (int v = 0; v < nv; v++) s1[v] += bd.stars[0]->vars[v]; cnt++; }
+        }
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        tamcmc_gpu_destroy(bctx);
+        int bad = 0;
+        for (int v = 0; v < nv; v++) if (s1[v] / cnt != single.mean[(size_t)v]) bad++;       // same seed, same data: identical chain
+        std::printf("{\"stars\": %d, \"chains\": %d, \"bins\": %ld, \"relaxed_variables\": %d, \"steps\": %ld, \"star_steps_per_s\": %.1f, "
+                    "\"evals_per_s\": %.0f, \"ms_per_batched_step\": %.3f, \"star0_matches_single_run\": %s}\n",
+                    nbatch, Nmodels, N, nv, nsteps, nbatch * nsteps / secs, nbatch * (double)Nmodels * nsteps / secs, 1e3 * secs / nsteps, bad ? "false" : "true");
+        return bad ? 1 : 0;
+    }
     if (bench) {
         cfg.Nt_learn = {100, nsteps / 2, nsteps / 2 + 1};
         const Summary G = run(ev_gpu);

@@ -109,3 +109,24 @@ def test_cpp_driver_posterior_consistent_with_cpu_oracle(pkg, oracle, tmp_path):
     r = subprocess.run([exe, str(f), "3000"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     print(r.stdout)
     assert r.returncode == 0, r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_batch_driver_reproduces_single_star_chain(pkg, oracle, tmp_path):
+    """BatchDriver (many independent stars, one batched tamcmc_gpu_eval per step): star 0 of a 5-star batch reproduces the
+    single-star run bit for bit (same seed, same data), whatever the OpenMP thread count."""
+    exe = _build_driver()
+    Nmodels = 3
+    params, pl, x = _cases.ms_case(pkg.synth, 3, seed=8, N=5000, Nmax=3, lmax=2, trunc_c=10.0)
+    rc, M = oracle.call_model(3, params, pl, x)
+    assert rc == 0
+    y = pkg.synth.chi2_2dof_spectrum(np.random.default_rng(3), M)
+    T = pkg.synth.tcoefs(Nmodels, 1.7)
+    f = tmp_path / "case.bin"
+    hdr = np.concatenate([[3, len(x), Nmodels, len(params), 1.0], pl.astype(float)])
+    with open(f, "wb") as fh:
+        for a in (hdr, x, y, T, np.tile(params, (Nmodels, 1)).ravel()):
+            fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    r = subprocess.run([exe, str(f), "800", "batch", "5"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    print(r.stdout)
+    assert r.returncode == 0 and '"star0_matches_single_run": true' in r.stdout, r.stdout
