@@ -44,6 +44,12 @@ typedef enum {
 
 /* model ids = case labels of Model_def::call_model (model_def.cpp:220-388) =
  * Config/default/models_ctrl.list */
+/* Gaussian-envelope models (no Lorentzians; plength is not read, parameters sit at fixed positions):
+ *   0: [k_a, s_a, k_b0, s_b0, c0, a1, a2, k1, s1, c1, k2, s2, c2, N0, Amax, numax, sigma, mu_numax] (Nparams >= 18); the
+ *      super-Lorentzian normalisations ksi_k integrate over the whole spectrum (noise_models.cpp:65-84): no bin-range slices
+ *   1: [H1, tc1, p1, H2, tc2, p2, B0, Hgauss, nu_gauss, sigma] (Nparams >= 10) */
+#define TAMCMC_MODEL_KALLINGER2014_GAUSSIAN                   0   /* models.cpp:5728 */
+#define TAMCMC_MODEL_HARVEY_GAUSSIAN                          1   /* models.cpp:5674 */
 #define TAMCMC_MODEL_MS_GLOBAL_A1ETAA3_HARVEYLIKE_CLASSIC     3   /* models.cpp:1943 */
 #define TAMCMC_MODEL_MS_GLOBAL_A1L_ETAA3_HARVEYLIKE           6   /* models.cpp:25   */
 #define TAMCMC_MODEL_MS_GLOBAL_A1N_ETAA3_HARVEYLIKE            7   /* models.cpp:217  */

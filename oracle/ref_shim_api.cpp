@@ -123,6 +123,8 @@ int ref_call_model(int model_id, const double* params, int nparams, const int* p
     VectorXi pl(11);
     for (int i = 0; i < 11; i++) pl[i] = plength[i];
     switch (model_id) {
+    case 0: m = model_Kallinger2014_Gaussian(p, pl, xv, false); break;      // NB: rewrites ./params.model on every call (models.cpp:5764)
+    case 1: m = model_Harvey_Gaussian(p, pl, xv, false); break;
     case 3: m = model_MS_Global_a1etaa3_HarveyLike_Classic(p, pl, xv, false); break;
     case 6: m = model_MS_Global_a1l_etaa3_HarveyLike(p, pl, xv, false); break;
     case 7: m = model_MS_Global_a1n_etaa3_HarveyLike(p, pl, xv, false); break;

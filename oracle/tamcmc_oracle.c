@@ -1346,11 +1346,94 @@ static int model_MS_Global_ajAlm_HarveyLike(const double *params, const int *pl,
 }
 
 /* Model_def::call_model switch, tamcmc/sources/model_def.cpp:220-388 */
+/* ------------------------------------------------------------------------------------------------
+ * Gaussian-envelope models (no Lorentzians)
+ * ------------------------------------------------------------------------------------------------ */
+/* tamcmc/sources/models.cpp:5674-5725: model_Harvey_Gaussian.  params = [H1, tc1, p1, H2, tc2, p2, B0, Hgauss, nu, sigma];
+ * Gaussian first (:5693-5694), then harvey_like on |params[0..6]| with Nharvey = 2 (:5698-5700). */
+static int model_Harvey_Gaussian(const double *params, const double *x, long N, double *out)
+{
+    double *model = (double *)malloc(sizeof(double) * (size_t)N), noise_abs[7];
+    const double sig2 = pow(fabs(params[9]), 2);
+    long i; int k;
+    for (i = 0; i < N; i++) { const double d = x[i] - params[8]; model[i] = -0.5 * (d * d) / sig2; }
+    for (i = 0; i < N; i++) model[i] = fabs(params[7]) * exp(model[i]);
+    for (k = 0; k < 7; k++) noise_abs[k] = fabs(params[k]);
+    orc_harvey_like(noise_abs, 7, x, N, &model, 2);
+    memcpy(out, model, sizeof(double) * (size_t)N);
+    free(model);
+    return 0;
+}
+
+/* tamcmc/sources/noise_models.cpp:65-84: get_ksinorm, trapezoid rule over the whole (equally spaced) x */
+static double get_ksinorm(double b, double c, const double *x, long N)
+{
+    double integral = 0.0;
+    const double h = x[1] - x[0];
+    long i;
+    for (i = 0; i < N; i++) {
+        const double term = 1.0 / (1.0 + pow(x[i] / b, c));
+        if (i == 0 || i == N - 1) integral += 0.5 * term;
+        else integral += term;
+    }
+    integral *= h;
+    return b / integral;
+}
+
+/* tamcmc/sources/models.cpp:5728-5797 + noise_models.cpp:87-150: model_Kallinger2014_Gaussian.
+ * params = [k_a, s_a, k_b0, s_b0, c0, a1, a2, k1, s1, c1, k2, s2, c2, N0, Amax, numax, sigma, mu_numax].
+ * Gaussian times the sinc^2 leakage (:5768-5772); white noise and three normalised super-Lorentzians (noise_models.cpp:128-146).
+ * The last statement of Kallinger2014 (`Power.cwiseProduct(eta_squared);`, noise_models.cpp:148) discards its result: the noise
+ * is NOT attenuated.  (The reference also forces outparams and rewrites params.model on every call, :5764 -- a file side effect
+ * outside this path.) */
+static int model_Kallinger2014_Gaussian(const double *params, const double *x, long N, double *out)
+{
+    const double Amax = fabs(params[14]), numax = fabs(params[15]), sig_numax = fabs(params[16]), mu_numax = params[17];
+    const double *np = params;
+    double x_nyquist = x[0];
+    double a0, b0, c0, a1, a2, b1, b2, c1, c2, N0, ksi0, ksi1, ksi2, sig2, f0, f1, f2;
+    long i;
+    for (i = 1; i < N; i++) if (x[i] > x_nyquist) x_nyquist = x[i];
+    sig2 = pow(fabs(sig_numax), 2);
+    for (i = 0; i < N; i++) {
+        /* eta_squared_Kallinger2014, noise_models.cpp:87-97 */
+        double eta = sin(0.5 * M_PI * x[i] / x_nyquist) / (0.5 * M_PI * x[i] / x_nyquist);
+        double g;
+        if (i == 0 && x[0] == 0) eta = 1;
+        g = -0.5 * ((x[i] - numax) * (x[i] - numax)) / sig2;
+        out[i] = fabs(Amax) * (eta * eta) * exp(g);
+    }
+    a0 = fabs(np[0] * pow(fabs(numax), np[1]));
+    b0 = fabs(np[2] * pow(fabs(numax + mu_numax), np[3]));
+    c0 = fabs(np[4]);
+    a1 = np[5];
+    a2 = np[6];
+    b1 = fabs(np[7] * pow(fabs(numax + mu_numax), np[8]));
+    b2 = fabs(np[10] * pow(fabs(numax + mu_numax), np[11]));
+    c1 = fabs(np[9]);
+    c2 = fabs(np[12]);
+    N0 = fabs(np[13]);
+    ksi0 = get_ksinorm(b0, c0, x, N);
+    ksi1 = get_ksinorm(b1, c1, x, N);
+    ksi2 = get_ksinorm(b2, c2, x, N);
+    f0 = ksi0 * pow(a0, 2) / b0; f1 = ksi1 * pow(a1, 2) / b1; f2 = ksi2 * pow(a2, 2) / b2;
+    for (i = 0; i < N; i++) {
+        double P = out[i] + N0;
+        P = P + f0 * (1.0 / (pow(x[i] / b0, c0) + 1.0));
+        P = P + f1 * (1.0 / (pow(x[i] / b1, c1) + 1.0));
+        P = P + f2 * (1.0 / (pow(x[i] / b2, c2) + 1.0));
+        out[i] = P;
+    }
+    return 0;
+}
+
 int orc_call_model(int model_id, const double *params, const int *plength, const double *x, long N,
                    double *model_out, orc_alm_fn alm, void *alm_user)
 {
     if (N < 2) return ORC_ERR_ARG;
     switch (model_id) {
+    case ORC_MODEL_KALLINGER2014_GAUSSIAN: return N < 3 ? ORC_ERR_ARG : model_Kallinger2014_Gaussian(params, x, N, model_out);
+    case ORC_MODEL_HARVEY_GAUSSIAN:      return model_Harvey_Gaussian(params, x, N, model_out);
     case ORC_MODEL_MS_GLOBAL_CLASSIC:    return model_MS_Global_a1etaa3_HarveyLike_Classic(params, plength, x, N, model_out);
     case ORC_MODEL_MS_GLOBAL_CLASSIC_V2: return model_MS_Global_a1etaa3_HarveyLike_Classic_v2(params, plength, x, N, model_out);
     case ORC_MODEL_MS_GLOBAL_CLASSIC_V3: return model_MS_Global_a1etaa3_HarveyLike_Classic_v3(params, plength, x, N, model_out);

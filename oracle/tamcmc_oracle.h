@@ -28,6 +28,8 @@ extern "C" {
 
 /* ---- model ids: Config/default/models_ctrl.list ---- */
 enum {
+    ORC_MODEL_KALLINGER2014_GAUSSIAN = 0,   /* models.cpp:5728 */
+    ORC_MODEL_HARVEY_GAUSSIAN        = 1,   /* models.cpp:5674 */
     ORC_MODEL_MS_GLOBAL_A1L_ETAA3   = 6,
     ORC_MODEL_MS_GLOBAL_A1N_ETAA3   = 7,
     ORC_MODEL_MS_GLOBAL_A1NL_ETAA3  = 8,

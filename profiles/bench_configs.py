@@ -8,7 +8,7 @@
   C4  dense red-giant mode list: the 78-mode case of the same fixture, 10 chains
   C5  256 independent C2 stars x 10 chains, star-sharded over the ranks (no collective)
 
-  python profiles/bench_configs.py [--configs c1,c3,c4,c5] [--steps K] [--stars 256]
+  python profiles/bench_configs.py [--configs c1,c3,c4,c5,env,driver] [--steps K] [--stars 256]
   python -m torch.distributed.run --nproc-per-node N profiles/bench_configs.py --configs c3,c5 ...
 
 One JSON line per config on rank 0.  Device-resident timing (CUDA events on the launch stream, max over ranks) and the
@@ -226,6 +226,28 @@ def main():
             pairs = int(pt[0])
         emit("c5", "%d independent C2-like stars (Dnu 60-95 microHz) x 10 chains, 250k bins each, star-sharded" % args.stars,
              args.stars * 10, dev, e2e, pairs, {"max_rel_err_vs_oracle": err, "stars_per_gpu": len(mine)})
+    # ------------------------------------------------------------------ envelope models (ids 0, 1): no Lorentzians
+    if "env" in todo and rank == 0:
+        import bench
+        N = bench.NBINS
+        T = synth.tcoefs(10, 1.7)
+        x = np.arange(N) * (283.2 / N)
+        for mid, make, name in ((0, synth.kallinger_gaussian_params, "model_Kallinger2014_Gaussian"), (1, synth.harvey_gaussian_params, "model_Harvey_Gaussian")):
+            rng = np.random.default_rng(7 + mid)
+            rows = np.stack([make(rng, jitter=0.02) for _ in range(10)])
+            rc, M0 = O.call_model(mid, rows[0], synth.ENVELOPE_PLENGTH, x)
+            y = M0 * rng.exponential(1.0, N)
+            t0 = time.perf_counter()
+            rc, L_ref = O.eval_chains(mid, rows, synth.ENVELOPE_PLENGTH, x, y, T, nthreads=os.cpu_count())
+            cpu_s = time.perf_counter() - t0
+            with pkg.Context(pkg.Star(mid, synth.ENVELOPE_PLENGTH, rows.shape[1], x, y), 10, T, device=lr) as ctx:
+                P_host = ctx.pack_params(rows)
+                L, st = ctx.eval(P_host)
+                err = float(np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)))
+                assert (st == 0).all() and err < 1e-10, err
+                dev, e2e, _ = timed(torch, ctx, P_host, args.steps, None)
+            emit("env%d" % mid, "%s, %d bins from 0 microHz, 10 chains" % (name, N), 10, dev, e2e, 0,
+                 {"max_rel_err_vs_oracle": err, "cpu_port_evals_per_s": 10 / cpu_s, "cpu_threads": os.cpu_count()})
     # ------------------------------------------------------------------ MCMC steps/s with the C++ driver (C2)
     if "driver" in todo and rank == 0:
         import subprocess

@@ -9,6 +9,7 @@
 #include "host_math.hpp"
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -83,6 +84,7 @@ int modes_of(int model_id, const int* pl)
     // 18 / 19 (a1n / a1nl a2a3) print "not tested yet" and exit in the reference (models.cpp:599-603, 993-997): ERR_MODEL
     case 11: case 14: case 23: return pl[2] + pl[3] + pl[4] + pl[5];
     case TAMCMC_MODEL_ID_MODE_TABLE: return pl[0];
+    case TAMCMC_MODEL_ID_KALLINGER_GAUSS: case TAMCMC_MODEL_ID_HARVEY_GAUSS: return 0;      // background + Gaussian envelope only
     }
     return -1;
 }
@@ -119,6 +121,8 @@ struct tamcmc_gpu_ctx {
     int* d_asym = nullptr;
     double* d_Tcoefs = nullptr;
     double* d_partial = nullptr;
+    double* d_ksi = nullptr;                 // get_ksinorm slice sums (Kallinger2014 model), [SC][ksi_slices][3]
+    int ksi_slices = 0;
     void* d_out = nullptr;          // [SC] double logL then [SC] int status
     double* d_model = nullptr;      // max Nloc
     // pinned host staging
@@ -173,6 +177,7 @@ ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const uns
     a.tilerec = c->d_tilerec; a.x = c->d_x; a.lnx = c->d_lnx;
     a.Nchains = c->Nchains; a.params_stride = c->params_stride; a.modes_stride = c->modes_stride;
     a.tiles_stride = c->tiles_stride; a.max_tiles = c->max_tiles; a.trace = c->d_trace ? c->d_trace + 64 * 2048 : nullptr;
+    a.ksi_part = c->d_ksi; a.ksi_slices = c->ksi_slices;
     return a;
 }
 
@@ -215,7 +220,7 @@ int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned c
 int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
                 int raw_sum, cudaStream_t st)
 {
-    c->launches += 2;
+    c->launches += c->d_ksi ? 3 : 2;
     { const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; }       // what the last CTA will publish
     const bool prof = c->profiling && st == c->stream;
     if (prof || !c->use_graphs) return enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof);
@@ -366,7 +371,14 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
             for (int k = 2; k < 11; k++) if (k != 8 && in.plength[k] != 0) { delete c; return TAMCMC_ERR_ARG; }
             if (in.plength[1] == 1 && (in.N < 3 || in.N_global > 0)) { delete c; return TAMCMC_ERR_ARG; }
         }
-        if (!in.x || !in.y || in.N < 2 || in.N > 2000000000L || in.Nparams < need || nm == 0) { delete c; return TAMCMC_ERR_ARG; }
+        const bool envelope = in.model_id == TAMCMC_MODEL_ID_KALLINGER_GAUSS || in.model_id == TAMCMC_MODEL_ID_HARVEY_GAUSS;
+        if (envelope) {
+            // fixed parameter positions, plength is not read (models.cpp:5693-5701, 5741-5745); the Kallinger normalisation
+            // integrates over the WHOLE spectrum (noise_models.cpp:65-84), so that model does not take a bin-range slice
+            need = (in.model_id == TAMCMC_MODEL_ID_KALLINGER_GAUSS) ? 18 : 10;
+            if (in.model_id == TAMCMC_MODEL_ID_KALLINGER_GAUSS && in.N_global > 0) { delete c; return TAMCMC_ERR_ARG; }
+        }
+        if (!in.x || !in.y || in.N < 2 || in.N > 2000000000L || in.Nparams < need || (nm == 0 && !envelope)) { delete c; return TAMCMC_ERR_ARG; }
         if (in.model_id == 3 || in.model_id == 6 || in.model_id == 7 || in.model_id == 8 || in.model_id == 12 || in.model_id == 13) {
             // the reference indexes fl_l[n] for n < Nmax and l <= lmax (models.cpp:2026-2075)
             for (int l = 0; l <= in.plength[1] && l <= 3; l++)
@@ -393,7 +405,8 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         sd.model_id = in.model_id;
         sd.Nparams = in.Nparams;
         sd.nmodes_cap = nm;
-        for (int k = 0; k < 11; k++) sd.plength[k] = in.plength[k];
+        for (int k = 0; k < 11; k++) sd.plength[k] = envelope ? 0 : in.plength[k];
+        if (in.model_id == TAMCMC_MODEL_ID_KALLINGER_GAUSS) c->ksi_slices = std::max(c->ksi_slices, (sd.Nloc + TAMCMC_KSI_SLICE - 1) / TAMCMC_KSI_SLICE);
         tiles += sd.ntiles;
         off += (long long)sd.ntiles * TB;
         if (in.Nparams > c->params_stride) c->params_stride = in.Nparams;
@@ -403,6 +416,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         if (sd.Nloc > maxN) maxN = sd.Nloc;
     }
     c->total_tiles = tiles;
+    if (c->modes_stride < 1) c->modes_stride = 1;       // envelope models only: keep the mode tables non-empty
     c->max_tiles = c->tiles_stride;
     // the expander stages one parameter row + the per-tile cost array in (at most 96 KB of) shared memory
     if (sizeof(double) * (size_t)c->params_stride + sizeof(int) * (size_t)(c->max_tiles + 2) > 96u * 1024u) { delete c; return TAMCMC_ERR_ARG; }
@@ -443,6 +457,10 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     CKC(cudaMalloc(&c->d_asym, sizeof(int) * (size_t)SC));
     CKC(cudaMalloc(&c->d_Tcoefs, sizeof(double) * Nchains));
     CKC(cudaMalloc(&c->d_partial, sizeof(double) * 3 * (size_t)SC * c->tiles_stride));
+    if (c->ksi_slices > 0) {
+        CKC(cudaMalloc(&c->d_ksi, sizeof(double) * 3 * (size_t)SC * c->ksi_slices));
+        CKC(cudaMemset(c->d_ksi, 0, sizeof(double) * 3 * (size_t)SC * c->ksi_slices));
+    }
     CKC(cudaMalloc(&c->d_out, c->out_bytes()));
     CKC(cudaMemset(c->d_out, 0, c->out_bytes()));
     CKC(cudaMalloc(&c->d_model, sizeof(double) * (size_t)maxN));
@@ -504,7 +522,7 @@ void tamcmc_gpu_destroy(tamcmc_gpu_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_epoch); cudaFree(c->d_tilerec); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx); cudaFree(c->d_wsig);
     cudaFree(c->d_params); cudaFree(c->d_active); cudaFree(c->d_modes); cudaFree(c->d_comps); cudaFree(c->d_noise);
-    cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_out);
+    cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_ksi); cudaFree(c->d_out);
     cudaFree(c->d_model);
     if (c->h_params) cudaFreeHost(c->h_params);
     if (c->h_active) cudaFreeHost(c->h_active);

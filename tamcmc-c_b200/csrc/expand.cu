@@ -263,9 +263,122 @@ __device__ __noinline__ void emit_noise(NoiseRec* out, const double* noise_param
     }
     if (lane >= nh && lane < TAMCMC_MAX_HARVEY) { nr.H[lane] = 0; nr.lnsc[lane] = 0; nr.pw[lane] = 0; nr.cpi[lane] = 0; nr.spi[lane] = 0; }
     if (lane == 0) {
-        nr.nh = nh; nr.pad = 0;
+        nr.nh = nh; nr.gauss = 0;
         nr.N0 = (Nnoise > 0) ? fabs(noise_params[Nnoise - 1]) : 0.0;
         if (!isfinite(nr.N0)) atomicOr(status, TAMCMC_ST_NONFINITE);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian-envelope models (no Lorentzians): model_Harvey_Gaussian (models.cpp:5674-5725) and
+// model_Kallinger2014_Gaussian (models.cpp:5728-5797).  Their background terms all have the shape H / (1 + (x/b)^c), so
+// they ride the exact per-bin background path of the fused kernel; the Gaussian bump is one more per-bin term.
+// ------------------------------------------------------------------------------------------------
+// Kallinger+2014 super-Lorentzians of one chain (noise_models.cpp:115-126): amplitudes a_k, corner frequencies b_k, slopes c_k
+struct KallingerPar { double a[3], b[3], c[3], N0; };
+
+__device__ __noinline__ void kallinger_params(const double* p, KallingerPar& k)
+{
+    const double numax = fabs(p[15]), mu_numax = p[17];          // models.cpp:5742-5745
+    k.a[0] = fabs(p[0] * pow(fabs(numax), p[1]));
+    k.b[0] = fabs(p[2] * pow(fabs(numax + mu_numax), p[3]));
+    k.c[0] = fabs(p[4]);
+    k.a[1] = p[5];
+    k.a[2] = p[6];
+    k.b[1] = fabs(p[7] * pow(fabs(numax + mu_numax), p[8]));
+    k.c[1] = fabs(p[9]);
+    k.b[2] = fabs(p[10] * pow(fabs(numax + mu_numax), p[11]));
+    k.c[2] = fabs(p[12]);
+    k.N0 = fabs(p[13]);
+}
+
+// get_ksinorm (noise_models.cpp:65-84), first half: trapezoid sums of 1 / (1 + (x/b_k)^c_k) over the whole spectrum, one
+// CTA per slice of TAMCMC_KSI_SLICE bins and chain, fixed reduction shape; the expander adds the slices in slice order.
+// (x/b)^c = exp(c (ln x - ln b)) with ln x tabulated at create; x = 0 gives exp(-inf) = 0 like pow(0, c), c = 0 gives 1.
+__global__ void __launch_bounds__(256) tamcmc_ksi_kernel(ExpandArgs A)
+{
+    const int sc = blockIdx.x, slice = blockIdx.y;
+    const StarDesc& sd = A.stars[sc / A.Nchains];
+    if (sd.model_id != TAMCMC_MODEL_ID_KALLINGER_GAUSS) return;
+    if (A.active && !A.active[sc]) return;
+    const int b0 = slice * TAMCMC_KSI_SLICE;
+    if (b0 >= sd.Nloc) return;
+    __shared__ double s_lnb[3], s_c[3];
+    __shared__ double s_red[8][3];
+    if (threadIdx.x == 0) {
+        KallingerPar k;
+        kallinger_params(A.params + (size_t)sc * A.params_stride, k);
+        for (int j = 0; j < 3; j++) { s_lnb[j] = log(k.b[j]); s_c[j] = k.c[j]; }
+    }
+    __syncthreads();
+    const double* lx = A.lnx + sd.off;
+    const int b1 = min(b0 + TAMCMC_KSI_SLICE, sd.Nloc);
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int i = b0 + (int)threadIdx.x; i < b1; i += 256) {
+        const double w = (i == 0 || i == sd.Nloc - 1) ? 0.5 : 1.0;
+        const double l = lx[i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const double z = (s_c[j] == 0.0) ? 1.0 : exp(s_c[j] * (l - s_lnb[j]));
+            acc[j] += w / (1.0 + z);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], d);
+    if ((threadIdx.x & 31) == 0) for (int j = 0; j < 3; j++) s_red[threadIdx.x >> 5][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += s_red[w][threadIdx.x];
+        A.ksi_part[((size_t)sc * A.ksi_slices + slice) * 3 + threadIdx.x] = t;
+    }
+}
+
+// NoiseRec of the Kallinger2014 + Gaussian model (one warp; lanes 0..2 own one super-Lorentzian each):
+//   ksi_k = b_k / (h * trapezoid sum)                      noise_models.cpp:80-82
+//   term  = (ksi_k a_k^2 / b_k) / (1 + (x/b_k)^c_k)        noise_models.cpp:135-146
+//   Gaussian |Amax| eta^2(x) exp(-0.5 (x - numax)^2 / sigma^2), eta = sinc leakage   models.cpp:5768-5772
+// (the reference multiplies the noise by eta^2 into a discarded temporary, noise_models.cpp:148: only the Gaussian is attenuated)
+__device__ __noinline__ void emit_kallinger(NoiseRec* out, const double* p, const double* ksi_part, int nslices, double h, double xnyq,
+                                            int* status, int lane)
+{
+    NoiseRec& nr = *out;
+    KallingerPar k;
+    kallinger_params(p, k);
+    if (lane < 3) {
+        double sum = 0.0;
+        for (int s = 0; s < nslices; s++) sum += ksi_part[3 * s + lane];
+        const double ksi = k.b[lane] / (sum * h);
+        const double H = (ksi * (k.a[lane] * k.a[lane])) / k.b[lane];
+        nr.H[lane] = H;
+        nr.lnsc[lane] = -log(k.b[lane]);
+        nr.pw[lane] = k.c[lane];
+        nr.cpi[lane] = 0; nr.spi[lane] = 0;
+        if (!isfinite(H) || !isfinite(nr.lnsc[lane]) || !isfinite(k.c[lane])) atomicOr(status, TAMCMC_ST_NONFINITE);
+    } else if (lane < TAMCMC_MAX_HARVEY) { nr.H[lane] = 0; nr.lnsc[lane] = 0; nr.pw[lane] = 0; nr.cpi[lane] = 0; nr.spi[lane] = 0; }
+    if (lane == 0) {
+        const double sig = fabs(p[16]);
+        nr.nh = 3; nr.gauss = 2;
+        nr.N0 = k.N0;
+        nr.gH = fabs(p[14]); nr.gnu = fabs(p[15]); nr.gk = 0.5 / (sig * sig);
+        nr.xnyq = xnyq;
+        if (!isfinite(nr.N0) || !isfinite(nr.gH) || !isfinite(nr.gnu) || !isfinite(nr.gk)) atomicOr(status, TAMCMC_ST_NONFINITE);
+    }
+}
+
+// NoiseRec of the Harvey + Gaussian model: params = [H1, tc1, p1, H2, tc2, p2, B0, Hgauss, nu_gauss, sigma] (models.cpp:5693-5701)
+__device__ __noinline__ void emit_harvey_gauss(NoiseRec* out, const double* p, int* status, int lane)
+{
+    emit_noise(out, p, 7, 2, status, lane);
+    if (lane == 0) {
+        NoiseRec& nr = *out;
+        const double sig = fabs(p[9]);
+        nr.gauss = 1;
+        nr.gH = fabs(p[7]); nr.gnu = p[8]; nr.gk = 0.5 / (sig * sig);
+        nr.xnyq = 1.0;
+        if (!isfinite(nr.gH) || !isfinite(nr.gnu) || !isfinite(nr.gk)) atomicOr(status, TAMCMC_ST_NONFINITE);
     }
 }
 
@@ -363,8 +476,11 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         const int o_noise = (sd.model_id == TAMCMC_MODEL_ID_MODE_TABLE) ? TAMCMC_MT_HDR : pl[0] + pl[1] + pl[2] + pl[3] + pl[4] + pl[5] + pl[6] + pl[7];
         if (threadIdx.x == 0) s_dummy = 0;
         __syncthreads();
-        if (threadIdx.x < 32)
-            emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (sd.model_id == 11 || sd.model_id == 14) ? 0 : (pl[8] - 1) / 3, &s_dummy, threadIdx.x);
+        const bool kallinger = sd.model_id == TAMCMC_MODEL_ID_KALLINGER_GAUSS;      // always the exact per-bin background
+        if (threadIdx.x < 32 && !kallinger) {
+            if (sd.model_id == TAMCMC_MODEL_ID_HARVEY_GAUSS) emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride, 7, 2, &s_dummy, threadIdx.x);
+            else emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (sd.model_id == 11 || sd.model_id == 14) ? 0 : (pl[8] - 1) / 3, &s_dummy, threadIdx.x);
+        }
         __syncthreads();
         const int tile = (blockIdx.y - 1) * blockDim.x + threadIdx.x;
         if (tile >= sd.ntiles) return;
@@ -376,8 +492,8 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         tr.umax = fmax(fabs(xs[0] - tr.xc), fabs(xs[sd.tile_bins - 1] - tr.xc));
         const double lnxc = A.lnx[sd.off + lb0 + (nvalid >> 1)];
         for (int k = 0; k < TAMCMC_BG_TERMS; k++) tr.bg[k] = 0.0;
-        bool ok = true;
-        for (int h = 0; h < s_nz.nh && ok; h++)
+        bool ok = !kallinger;
+        for (int h = 0; ok && h < s_nz.nh; h++)
             ok = harvey_series(s_nz.H[h], s_nz.lnsc[h], s_nz.pw[h], s_nz.cpi[h], s_nz.spi[h], s_nz.binom[h], tr.xc, lnxc, tr.umax, tr.bg);
         TileRec* dst = A.tilerec + (size_t)sc * A.tiles_stride + tile;
         for (int k = 0; k < TAMCMC_BG_TERMS; k++) dst->bg[k] = tr.bg[k];
@@ -505,6 +621,10 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 cm.asym = params[o_split + 13];
                 cm.eta0 = (params[o_split + 12] == 1) ? eta_w : 0.0;
                 break;
+            case TAMCMC_MODEL_ID_KALLINGER_GAUSS: case TAMCMC_MODEL_ID_HARVEY_GAUSS:   // no modes: background + Gaussian envelope
+                cm.asym = 0.0;
+                cm.eta0 = 0.0;
+                break;
             case TAMCMC_MODEL_ID_MODE_TABLE:   // modes already resolved by a host expander (e.g. models.cpp:4788-4911)
                 cm.asym = params[3];
                 cm.eta0 = 0.0;
@@ -520,7 +640,11 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             ETRACE_T(9, 32);
         } else if (tid >= 64 && tid < 96) {
             // warp 2: Harvey-like background parameters, one lane per term
-            emit_noise(noise, params + o_noise, Nnoise, (model == 11 || model == 14) ? 0 : (Nnoise - 1) / 3, &s_status, tid - 64);
+            if (model == TAMCMC_MODEL_ID_KALLINGER_GAUSS)
+                emit_kallinger(noise, params, A.ksi_part + (size_t)sc * A.ksi_slices * 3, (sd.Nloc + TAMCMC_KSI_SLICE - 1) / TAMCMC_KSI_SLICE,
+                               sd.step, sd.xlast, &s_status, tid - 64);
+            else if (model == TAMCMC_MODEL_ID_HARVEY_GAUSS) emit_harvey_gauss(noise, params, &s_status, tid - 64);
+            else emit_noise(noise, params + o_noise, Nnoise, (model == 11 || model == 14) ? 0 : (Nnoise - 1) / 3, &s_status, tid - 64);
             ETRACE_T(10, 64);
         }
     }
@@ -783,6 +907,10 @@ cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t 
 {
     const size_t smem = sizeof(double) * (size_t)a.params_stride + sizeof(int) * (size_t)(a.max_tiles + 2);
     dim3 grid((unsigned)nblocks, 1u + (unsigned)((a.max_tiles + EXP_THREADS - 1) / EXP_THREADS), 1u);
+    if (a.ksi_part) {       // some star runs the Kallinger2014 model: its normalisation sums come first
+        dim3 kgrid((unsigned)nblocks, (unsigned)a.ksi_slices, 1u);
+        tamcmc_ksi_kernel<<<kgrid, 256, 0, st>>>(a);
+    }
     tamcmc_expand_kernel<<<grid, EXP_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }

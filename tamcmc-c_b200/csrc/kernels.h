@@ -25,6 +25,8 @@ struct ExpandArgs {
     int tiles_stride;
     int max_tiles;                   // largest ntiles of any star (sizes the dynamic shared memory)
     unsigned long long* trace;       // profiling aid (TAMCMC_TRACE builds)
+    double* ksi_part;                // [nstars*Nchains][ksi_slices][3] partial sums of get_ksinorm (Kallinger2014 model only), or nullptr
+    int ksi_slices;
 };
 
 struct WhittleArgs {

@@ -37,6 +37,10 @@
 // generic mode table (public id TAMCMC_MODEL_MODE_TABLE, include/tamcmc_gpu.h): a parameter row is
 //   [nmodes, inclination, trunc_c, asym, noise[Nnoise], nmodes x {l, fc, H, W, a1..a6, eta0, extra[-3..3], 0, 0}]
 #define TAMCMC_MODEL_ID_MODE_TABLE 1000
+// Gaussian-envelope models (no Lorentzians): models.cpp:5728-5797 and 5674-5725
+#define TAMCMC_MODEL_ID_KALLINGER_GAUSS 0
+#define TAMCMC_MODEL_ID_HARVEY_GAUSS 1
+#define TAMCMC_KSI_SLICE 2048        // bins per CTA of the normalisation pre-pass (get_ksinorm, noise_models.cpp:65-84)
 #define TAMCMC_MT_HDR 4
 #define TAMCMC_MT_STRIDE 20
 
@@ -75,8 +79,10 @@ struct __align__(8) CompRec {
 
 struct NoiseRec {
     int nh;                              // live Harvey terms (tau != 0)
-    int pad;
+    int gauss;                           // envelope models: 0 none, 1 Gaussian, 2 Gaussian times the sinc^2 leakage (Kallinger+2014 eq. 1)
     double N0;                           // white noise
+    double gH, gnu, gk;                  // Gaussian envelope gH * exp(-(x - gnu)^2 * gk), gk = 0.5 / sigma^2 (models.cpp:5693-5694, 5771-5772)
+    double xnyq;                         // leakage: eta = sin(a)/a, a = 0.5 pi x / x_nyquist (noise_models.cpp:89-97)
     double H[TAMCMC_MAX_HARVEY];         // heights
     double lnsc[TAMCMC_MAX_HARVEY];      // ln(1e-3 * tau)
     double pw[TAMCMC_MAX_HARVEY];        // exponents

@@ -46,7 +46,7 @@ constexpr int EMPTY_COUNT = NC / 32;                       // one arrival per co
 constexpr int EMPTY_COUNT = NC;                            // every consumer thread arrives on the slot's `empty` barrier
 #endif
 
-enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_WIDE = 64 };
+enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_GAUSS = 32, SEG_WIDE = 64 };
 
 template <int TILE>
 struct __align__(16) Segment {
@@ -236,6 +236,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         const double bgk = (lane < NB) ? tr->bg[lane] : 0.0;
         const bool asym = A.asym_flag[sc] != 0;
         const double N0 = A.noise[sc].N0;
+        const int gauss = A.noise[sc].gauss ? SEG_GAUSS : 0;      // Gaussian-envelope models (ids 0, 1)
         const int lb0 = tile * TILE;
         const int nvalid = min(TILE, Nloc - lb0);
         const long long off = soff + lb0;
@@ -282,7 +283,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                     // ---- the slot is full: publish this segment, wait for the consumers to release the slot, go on ----
                     if (lane == 0) {
                         sg->nfast = cf; sg->ngen = cg; sg->nhdr = ch;
-                        sg->flags = (first ? SEG_FIRST : 0) | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (seg_wide ? SEG_WIDE : 0);
+                        sg->flags = (first ? SEG_FIRST : 0) | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (seg_wide ? SEG_WIDE : 0) | gauss;
                         sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
                     }
                     __syncwarp();
@@ -333,7 +334,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         // ---- last segment of the tile (possibly empty: a tile no mode touches still has its background and Whittle terms)
         if (lane == 0) {
             sg->nfast = cf; sg->ngen = cg; sg->nhdr = ch;
-            sg->flags = (first ? SEG_FIRST : 0) | SEG_LAST | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (seg_wide ? SEG_WIDE : 0);
+            sg->flags = (first ? SEG_FIRST : 0) | SEG_LAST | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (seg_wide ? SEG_WIDE : 0) | gauss;
             sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
         }
         if (lane < NB) sg->bg[lane] = bgk;
@@ -341,6 +342,21 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         if (lane == 0) mbar_arrive(full);             // 2 arrivals per phase: the opening one (with the TMA byte count) and this
         use++;
     }
+}
+
+// Gaussian envelope of the models without Lorentzians (ids 0, 1): |H| exp(-0.5 (x - nu)^2 / sigma^2), times the sinc^2
+// leakage of Kallinger+2014 eq. 1 for model 0 (models.cpp:5693-5694, 5768-5772; noise_models.cpp:89-97).  Kept out of
+// line: it is off the path of the Lorentzian models and must not cost them registers.
+__device__ __noinline__ double gauss_envelope(const NoiseRec* nz, double x)
+{
+    const double d = x - nz->gnu;
+    double g = nz->gH * exp(-(d * d) * nz->gk);
+    if (nz->gauss == 2) {
+        const double a = (0.5 * 3.14159265358979323846 * x) / nz->xnyq;
+        const double eta = (x == 0.0) ? 1.0 : sin(a) / a;
+        g *= eta * eta;
+    }
+    return g;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -590,6 +606,12 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
                 }
 #pragma unroll
                 for (int j = 0; j < BPT; j++) bgv[j] = N0;
+            }
+
+            if (flags & SEG_GAUSS) {
+                const double xc = sg.xc;
+#pragma unroll
+                for (int j = 0; j < BPT; j++) bgv[j] += gauss_envelope(nz, u[j] + xc);
             }
 
             // ---------- M = N/D + background; Whittle terms.  y_i/M_i is summed; ln M_i is carried as the

@@ -195,3 +195,25 @@ def mode_table_row(capacity, inclination, trunc_c, asym, noise, modes, extra=Non
         rec[:n, 11:18] = np.asarray(extra, dtype=np.float64)
     row[4 + len(noise):] = rec.ravel()
     return row
+
+
+# ---- Gaussian-envelope models (ids 0 and 1; models.cpp:5728-5797, 5674-5725): fixed parameter positions, no plength ----
+ENVELOPE_PLENGTH = [0] * 11
+
+
+def kallinger_gaussian_params(rng=None, numax=100.0, jitter=0.0):
+    """[k_a, s_a, k_b0, s_b0, c0, a1, a2, k1, s1, c1, k2, s2, c2, N0, Amax, numax, sigma, mu_numax] with the scaling
+    relations of Kallinger+2014 Table 2 (amplitudes in ppm, frequencies in microHz)."""
+    p = np.array([3335.0, -0.564, 0.317, 0.970, 4.0, 3382.0 * numax ** -0.609, 3382.0 * numax ** -0.609,
+                  0.317, 0.970, 4.0, 0.948, 0.992, 4.0, 5.0, 800.0, numax, 0.12 * numax, 0.5])
+    if rng is not None and jitter > 0:
+        p = p * (1.0 + jitter * rng.standard_normal(p.size))
+    return p
+
+
+def harvey_gaussian_params(rng=None, numax=120.0, jitter=0.0):
+    """[H1, tc1, p1, H2, tc2, p2, B0, Hgauss, nu_gauss, sigma]"""
+    p = np.array([50.0, 30.0, 2.0, 10.0, 5.0, 3.0, 2.0, 30.0, numax, 0.12 * numax])
+    if rng is not None and jitter > 0:
+        p = p * (1.0 + jitter * rng.standard_normal(p.size))
+    return p
