@@ -66,10 +66,10 @@ template <int TILE>
 struct Smem {
     Segment<TILE> seg[NBUF];
     unsigned long long full[NBUF], empty[NBUF];
-    double red_s[NBUF][NC / 32];
-    double red_m[NBUF][NC / 32];
-    int red_e[NBUF][NC / 32];
-    unsigned int cnt[NBUF];
+    // per-thread Whittle sums of the slot's tile, left by the consumers for the slot's producer warp (tile_reduce)
+    double red_s[NBUF][NC];
+    double red_m[NBUF][NC];
+    int red_e[NBUF][NC];
     volatile int cons_cur;            // slot the consumers are working on (-1 before the first tile)
     unsigned int done_mask;           // producers that have drained the queue
 };
@@ -109,9 +109,21 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TRACE(slot, val) do { if (A.trace && (slot) < 64) A.trace[(size_t)blockIdx.x * 64 + (slot)] = (val); } while (0)
 // per-phase cycle accounting of consumer warp 0 (slots 48..57 of the CTA's trace row)
-#define PHASE_DECL long long ph_t = clock64(); long long ph_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#define PHASE(k) do { if (tid == 0) { const long long now_ = clock64(); ph_acc[k] += now_ - ph_t; ph_t = now_; } } while (0)
-#define PHASE_FLUSH do { if (tid == 0) for (int k_ = 0; k_ < 10; k_++) TRACE(48 + k_, (unsigned long long)ph_acc[k_]); } while (0)
+#ifndef TAMCMC_TRACE_TID
+#define TAMCMC_TRACE_TID 0      // consumer thread whose phases are accounted (e.g. 256 = warp 8)
+#endif
+// -DTAMCMC_TRACE_GANTT: lane 0 of EVERY consumer warp of CTA 0 also logs (clock64 << 4 | phase) at each phase boundary
+// (trace words 65536 + 512 warp + event): profiles/trace_gantt.py draws which warps overlap which phases
+#ifdef TAMCMC_TRACE_GANTT
+#define GANTT(k) do { if (blockIdx.x == 0 && (tid & 31) == 0 && A.trace && gantt_n < 512) A.trace[65536 + 512 * (tid >> 5) + gantt_n++] = ((unsigned long long)clock64() << 4) | (unsigned)(k); } while (0)
+#define GANTT_DECL int gantt_n = 0;
+#else
+#define GANTT(k) do { } while (0)
+#define GANTT_DECL
+#endif
+#define PHASE_DECL GANTT_DECL long long ph_t = clock64(); long long ph_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PHASE(k) do { GANTT(k); if (tid == TAMCMC_TRACE_TID) { const long long now_ = clock64(); ph_acc[k] += now_ - ph_t; ph_t = now_; } } while (0)
+#define PHASE_FLUSH do { if (tid == TAMCMC_TRACE_TID) for (int k_ = 0; k_ < 10; k_++) TRACE(48 + k_, (unsigned long long)ph_acc[k_]); } while (0)
 #else
 #define TRACE(slot, val) do { } while (0)
 #define PHASE_DECL
@@ -173,6 +185,45 @@ __device__ __forceinline__ int next_live(int c, unsigned done_mask)
     return n;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tile reduction, run by the slot's PRODUCER warp once the consumers have released the slot: the 384 per-thread sums
+// (sum y/M, mantissa product and exponent sum of prod 1/M) become the tile's partial.  The consumers only store their
+// three values and go on to the next tile -- no shuffle tree, no atomics, no combine on the FP64-bound warps.  Fixed
+// shape (lane l takes threads l, l+32, ...; then a shuffle tree): bitwise reproducible whatever the scheduling.
+// ------------------------------------------------------------------------------------------------
+template <int TILE>
+__device__ __forceinline__ void tile_reduce(const WhittleArgs& A, Smem<TILE>& sm, int w, int lane)
+{
+    const Segment<TILE>& sg = sm.seg[w];
+    double s1 = 0.0, pm = 1.0;
+    int pe = 0;
+#pragma unroll
+    for (int i = 0; i < NC / 32; i++) {
+        s1 += sm.red_s[w][lane + 32 * i];
+        pm *= sm.red_m[w][lane + 32 * i];          // each is a product of <= 4 mantissas in [1,2): 12 of them stay below 2^48
+        pe += sm.red_e[w][lane + 32 * i];
+    }
+    {
+        const int hi = __double2hiint(pm);
+        const int k = (hi & 0x7ff00000) - 0x3ff00000;
+        pm = __hiloint2double(hi - k, __double2loint(pm));
+        pe += k >> 20;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        s1 += __shfl_down_sync(0xffffffffu, s1, d);
+        pm *= __shfl_down_sync(0xffffffffu, pm, d);     // 32 mantissas in [1,2) stay below 2^32
+        pe += __shfl_down_sync(0xffffffffu, pe, d);
+    }
+    if (lane == 0) {
+        const int hi = __double2hiint(pm);
+        const int k = (hi & 0x7ff00000) - 0x3ff00000;
+        double* part = A.partial + 3 * ((size_t)sg.sc_index * A.tiles_stride + sg.tile);
+        part[0] = s1; part[1] = __hiloint2double(hi - k, __double2loint(pm)); part[2] = (double)(pe + (k >> 20));
+    }
+    __syncwarp();
+}
+
 template <int TILE>
 __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int lane)
 {
@@ -197,6 +248,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
     unsigned long long* const empty = &sm.empty[w];
     unsigned use = 0;                 // segments published in this slot so far
     bool first_item = true;
+    bool pending = false;             // the slot holds a finished tile whose per-thread sums are still to be reduced
     unsigned last_idx = 0;
     for (;;) {
         unsigned idx;
@@ -205,6 +257,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
             first_item = false;
         } else {
             if (use) mbar_wait(empty, (use - 1) & 1);          // claim nothing while this slot still holds a tile
+            if (pending) { tile_reduce<TILE>(A, sm, w, lane); pending = false; }
             const int look = (last_idx + nstatic >= endgame_from) ? A.look_end : A.look;
             for (;;) {
                 const int cur = sm.cons_cur;
@@ -341,6 +394,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         __syncwarp();
         if (lane == 0) mbar_arrive(full);             // 2 arrivals per phase: the opening one (with the TMA byte count) and this
         use++;
+        pending = true;
     }
 }
 
@@ -651,48 +705,15 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
                     pe += k >> 20;
                 }
             }
-            // ---------- barrier-free tile completion.  Every warp deposits its (shuffle-tree) sums in the slots of
-            // this segment buffer; the LAST warp to do so combines the slots in warp order (deterministic whatever
-            // the arrival order) and stores the tile's partial (sum y/M, mantissa and exponent of prod 1/M).  Nobody
-            // waits for anybody: warps that finish early go on to the next segment. ----------
+            // ---------- tile completion: every thread leaves its three sums in the slot's scratch; the slot's producer
+            // warp reduces them (tile_reduce) after the empty barrier has handed the slot back.  Nobody waits for
+            // anybody: this warp goes straight on to the next tile. ----------
             PHASE(5);
-#ifndef TAMCMC_EXP_NO_TREE
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                s1 += __shfl_down_sync(0xffffffffu, s1, d);
-                pm *= __shfl_down_sync(0xffffffffu, pm, d);     // mantissas in [1,2): 128 of them stay below 2^128
-                pe += __shfl_down_sync(0xffffffffu, pe, d);
-            }
-#endif
+            sm.red_s[b][tid] = s1; sm.red_m[b][tid] = pm; sm.red_e[b][tid] = pe;
             PHASE(6);
-            unsigned int prev = 0;
-            if (lane == 0) {
-                sm.red_s[b][warp] = s1; sm.red_m[b][warp] = pm; sm.red_e[b][warp] = pe;
-                __threadfence_block();
-                prev = atomicAdd(&sm.cnt[b], 1u);
-            }
-            prev = __shfl_sync(0xffffffffu, prev, 0);
             PHASE(7);
-            if (prev == (unsigned int)(NC / 32 - 1) && lane == 0) {
-                __threadfence_block();
-                sm.cnt[b] = 0u;
-                double S = sm.red_s[b][0], Mm = sm.red_m[b][0];
-                int E = sm.red_e[b][0];
-                for (int w = 1; w < NC / 32; w++) {
-                    S += sm.red_s[b][w];
-                    Mm *= sm.red_m[b][w];
-                    E += sm.red_e[b][w];
-                    // keep the running mantissa product in range
-                    const int hi = __double2hiint(Mm);
-                    const int k = (hi & 0x7ff00000) - 0x3ff00000;
-                    Mm = __hiloint2double(hi - k, __double2loint(Mm));
-                    E += k >> 20;
-                }
-                double* part = A.partial + 3 * ((size_t)sc * A.tiles_stride + tile);
-                part[0] = S; part[1] = Mm; part[2] = (double)E;
-            }
             __syncwarp();
-            if (EMPTY_COUNT == NC || lane == 0) mbar_arrive(&sm.empty[b]);     // the slot (and its reduction scratch) is free again
+            if (EMPTY_COUNT == NC || lane == 0) mbar_arrive(&sm.empty[b]);     // release: the slot and the sums go back to its producer warp
             PHASE(8);
             do { b = (b + 1 == NBUF) ? 0 : b + 1; } while ((done >> b) & 1u);      // next tile: next live slot
         } else {
@@ -741,7 +762,7 @@ __global__ void __launch_bounds__(NT, (BPT == BPT_MAX) ? TAMCMC_MIN_CTAS : TAMCM
     Smem<NC * BPT>& sm = *reinterpret_cast<Smem<NC * BPT>*>(smem_raw);
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int i = 0; i < NBUF; i++) { mbar_init(&sm.full[i], 2); mbar_init(&sm.empty[i], EMPTY_COUNT); sm.cnt[i] = 0u; }
+        for (int i = 0; i < NBUF; i++) { mbar_init(&sm.full[i], 2); mbar_init(&sm.empty[i], EMPTY_COUNT); }
         sm.cons_cur = -1; sm.done_mask = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
