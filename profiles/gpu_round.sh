@@ -20,7 +20,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "ncu launches rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:tamcmc_whittle_kernel -s 4 -c 2 -f -o $OUT/${TAG}_whittle $BCMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
-python profiles/bench_configs.py --configs c1,c4,c3,c5 --steps 50 > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err
+python profiles/bench_configs.py --configs c1,c4,c3,c5,env --steps 50 > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err
 cat $OUT/${TAG}_configs.jsonl | cut -c1-200
 python __graft_entry__.py smoke 2>&1 | tail -2
 ls -la $OUT | tail -14

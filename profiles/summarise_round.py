@@ -37,11 +37,11 @@ if os.path.exists(p):
             agg.setdefault(k, [0, 0.0])
             agg[k][0] += 1
             agg[k][1] += float(r[iv])
-    step = {k: v for k, v in agg.items() if "expand" in k or ("whittle_kernel<0>" in k) or "whittle_kernel<(bool)0>" in k}
+    step = {k: v for k, v in agg.items() if "expand" in k or "ksi_kernel" in k or ("whittle_kernel<0" in k) or "whittle_kernel<(bool)0" in k}
     tot = sum(v[1] / v[0] for v in step.values()) or 1.0
     with open(os.path.join(dst, "launch_shares.txt"), "w") as f:
         f.write("ncu --metrics gpu__time_duration.sum --clock-control none, command: python bench.py --steps 5 --warmup 3 --no-cpu-baseline\n")
-        f.write("per-launch times are cold-cache and serialised; one evaluation (step) = tamcmc_expand_kernel + tamcmc_whittle_kernel<0>\n\n")
+        f.write("per-launch times are cold-cache and serialised; one evaluation (step) = tamcmc_expand_kernel + tamcmc_whittle_kernel<0, bins per thread>\n\n")
         for k, v in agg.items():
             f.write("%-50s launches %4d  avg %9.2f us\n" % (k, v[0], v[1] / v[0] / 1e3))
         f.write("\nshare of one step:\n")
