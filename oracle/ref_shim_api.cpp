@@ -15,6 +15,8 @@
 #include "noise_models.h"       // harvey_like
 #include "likelihoods.h"        // likelihood_chi22p, likelihood_chi_square
 #include "models.h"             // model_MS_Global_*, model_MS_local_*, model_RGB_asympt_* (tamcmc/sources/models.cpp)
+#include "stats_dictionary.h"   // logP_* primitive priors
+#include "priors_calc.h"        // apply_generic_priors, priors_Harvey_Gaussian, priors_Kallinger2014_Gaussian
 
 using Eigen::VectorXd;
 using Eigen::VectorXi;
@@ -56,6 +58,10 @@ Optim_L optimum_lorentzian_calc_aj(const VectorXd& x, const double H_l, const do
 
 static VectorXd vec(const double* p, long n) { VectorXd v(n); for (long i = 0; i < n; i++) v[i] = p[i]; return v; }
 static void out(const VectorXd& v, double* p) { for (long i = 0; i < (long)v.size(); i++) p[i] = v[i]; }
+
+// logP_tabulated_2d (stats_dictionary.cpp:293) reaches the GSL-backed Alm interpolator, which cannot be built here (no GSL):
+// never called through this shim
+double interpolate_core(gsl_interp2d*, const GridData4gsl&, double, double) { std::abort(); }
 
 extern "C" {
 
@@ -195,5 +201,37 @@ int ref_call_model_recorded(int model_id, const double* params, int nparams, con
 }
 
 double ref_eta0_fct(const double* fl0, long n) { return eta0_fct(vec(fl0, n)); }
+
+// primitive priors by their switch value (Config/default/primepriors_ctrl.list), stats_dictionary.cpp
+double ref_logP(int kind, double a, double b, double c, double d, double x)
+{
+    switch (kind) {
+    case 1: return (double)logP_uniform(a, b, x);
+    case 2: return (double)logP_gaussian(a, b, x);
+    case 4: return (double)logP_jeffrey(a, b, x);
+    case 5: return (double)logP_uniform_gaussian(a, b, c, x);
+    case 6: return (double)logP_gaussian_uniform(a, b, c, x);
+    case 7: return (double)logP_gaussian_uniform_gaussian(a, b, c, d, x);
+    case 8: return (double)logP_uniform_abs(a, b, x);
+    case 9: return (double)logP_uniform_cos(a, b, x);
+    case 10: return (double)logP_jeffrey_abs(a, b, x);
+    }
+    return 0.0;
+}
+
+// which = -1: apply_generic_priors; 0 / 1: priors_Kallinger2014_Gaussian / priors_Harvey_Gaussian (priors_calc.cpp:725, 649, 631).
+// pri = [4][n] row-major (the reference's MatrixXd priors_params(4, n)), kinds = priors_names_switch.
+double ref_priors(int which, const double* params, int n, const double* pri, const int* kinds)
+{
+    VectorXd p = vec(params, n);
+    MatrixXd P(4, n);
+    VectorXi k(n), pl(11);
+    for (int i = 0; i < n; i++) { k[i] = kinds[i]; for (int r = 0; r < 4; r++) P(r, i) = pri[(size_t)r * n + i]; }
+    for (int i = 0; i < 11; i++) pl[i] = 0;
+    tabpriors none;
+    if (which == 0) return (double)priors_Kallinger2014_Gaussian(p, pl, P, k, none);
+    if (which == 1) return (double)priors_Harvey_Gaussian(p, pl, P, k, none);
+    return (double)apply_generic_priors(p, P, k, none);
+}
 
 }  // extern "C"

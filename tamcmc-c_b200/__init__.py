@@ -15,6 +15,7 @@ import os
 import numpy as np
 
 from . import synth  # noqa: F401  (synthetic inputs; numpy only)
+from . import formats  # noqa: F401  (readers for the reference's simplest on-disk inputs; numpy only)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TAMCMC_GPU_LIB selects another build of the SAME CUDA library (e.g. the -DTAMCMC_TRACE profiling build)

@@ -1,0 +1,139 @@
+"""Either side of the hot path for the simplest model family (first slice): the reference's generic priors
+restated for the C++ driver (tamcmc-c_b200/host/priors.hpp) against values from the REFERENCE's own stats_dictionary.cpp /
+priors_calc.cpp, the readers of its `.data` / simple-matrix `.model` files, and its real fixture 10280410_Gaussfit run on the
+GPU (tests/golden/make_golden_priors_and_gaussfit.py generated the vectors)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD_P = os.path.join(HERE, "golden", "reference_priors.json")
+GOLD_G = os.path.join(HERE, "golden", "reference_gaussfit_10280410.npz")
+
+
+def _build():
+    exe = os.path.join(HERE, "cpp", "test_priors")
+    src = os.path.join(HERE, "cpp", "test_priors.cpp")
+    hdr = os.path.join(ROOT, "tamcmc-c_b200", "host", "priors.hpp")
+    if not (os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", exe, src])
+    return exe
+
+
+def _same(a, b):
+    if np.isinf(b) or np.isnan(b):
+        return (np.isinf(a) and np.isinf(b) and (a < 0) == (b < 0)) or (np.isnan(a) and np.isnan(b))
+    return abs(a - b) <= 1e-13 * max(1.0, abs(b))
+
+
+def test_generic_priors_match_reference():
+    g = json.load(open(GOLD_P))
+    lines, want = [], []
+    for kind, a, b, c, d, x, v in g["primitive"]:
+        lines.append("P %d %r %r %r %r %r" % (kind, a, b, c, d, x)); want.append(v)
+    for s in g["sets"]:
+        tag = {-1: "G", 1: "H", 0: "K"}[s["which"]]
+        flat = " ".join(repr(float(v)) for row in s["pri"] for v in row)
+        lines.append("%s %d %s %s %s" % (tag, len(s["params"]), " ".join(repr(float(v)) for v in s["params"]),
+                                         " ".join(str(int(k)) for k in s["kinds"]), flat))
+        want.append(s["value"])
+    r = subprocess.run([_build()], input="\n".join(lines) + "\n", stdout=subprocess.PIPE, text=True, check=True)
+    got = [float(t) for t in r.stdout.split()]
+    assert len(got) == len(want)
+    bad = [(l, a, b) for l, a, b in zip(lines, got, want) if not _same(a, b)]
+    assert not bad, bad[:3]
+    assert sum(1 for v in want if np.isinf(v)) > 10 and sum(1 for v in want if np.isfinite(v)) > 100     # both branches exercised
+
+
+def test_simple_matrix_model_and_data_readers(pkg, tmp_path):
+    g = np.load(GOLD_G)
+    f = tmp_path / "star.model"
+    f.write_text(str(g["model_text"]))
+    m = pkg.formats.read_simple_matrix_model(str(f))
+    assert m["names"] == ["H1", "tc1", "p1", "H2", "tc2", "p2", "B0", "Amax", "numax", "Gauss_sigma"]
+    assert np.array_equal(m["inputs"], g["rows"][0])
+    assert list(m["relax"]) == [1, 1, 0, 1, 1, 1, 1, 1, 1, 1]
+    assert m["prior_names"][2] == "Fix" and m["prior_kinds"][2] == 0 and m["prior_kinds"][9] == 7        # GUG on the envelope width
+    assert m["priors"].shape == (4, 10) and m["priors"][2, 0] == -9999.0 and m["priors"][3, 9] == 42.544956
+    assert m["xrange"] == [0.000079, 256.875763]
+    d = tmp_path / "star.data"
+    d.write_text("# comment\n! frequency power\n* (microHz) (ppm^2/microHz)\n 1.0 5.0\n 2.0 6.0\n 3.5 7.0\n")
+    x, y = pkg.formats.read_data(str(d), xrange=(1.5, 10))
+    assert list(x) == [2.0, 3.5] and list(y) == [6.0, 7.0]
+
+
+def test_oracle_on_reference_gaussfit_fixture(pkg, oracle):
+    g = np.load(GOLD_G)
+    for r, M_ref, L_ref in zip(g["rows"], g["model"], g["logL"]):
+        rc, M = oracle.call_model(1, r, pkg.synth.ENVELOPE_PLENGTH, g["x"])
+        assert rc == 0 and np.max(np.abs(M - M_ref) / M_ref) < 1e-13
+        assert abs(oracle.chi22p(g["y"], M, 1) - L_ref) <= 1e-12 * abs(L_ref)
+
+
+@pytest.mark.gpu
+def test_gpu_on_reference_gaussfit_fixture(pkg):
+    """Real Kepler spectrum of KIC 10280410 + the reference's own .model initial values -> GPU model and logL against the
+    REFERENCE's model_Harvey_Gaussian / likelihood_chi22p."""
+    g = np.load(GOLD_G)
+    x, y, rows = g["x"], g["y"], g["rows"]
+    T = pkg.synth.tcoefs(len(rows), 1.7)
+    with pkg.Context(pkg.Star(1, pkg.synth.ENVELOPE_PLENGTH, rows.shape[1], x, y), len(rows), T) as ctx:
+        for r, M_ref in zip(rows, g["model"]):
+            assert np.max(np.abs(ctx.model(r) - M_ref) / M_ref) < 1e-10
+        L, st = ctx.eval(rows)
+        assert (st == 0).all()
+        assert np.max(np.abs(L[0] * T - g["logL"]) / np.abs(g["logL"])) < 1e-10
+
+
+def _build_gaussfit():
+    exe = os.path.join(HERE, "cpp", "test_gaussfit")
+    src = os.path.join(HERE, "cpp", "test_gaussfit.cpp")
+    libdir = os.path.join(ROOT, "tamcmc-c_b200")
+    deps = [src, os.path.join(libdir, "host", "priors.hpp"), os.path.join(libdir, "host", "mcmc_driver.hpp"), os.path.join(ROOT, "include", "tamcmc_gpu.h")]
+    if not (os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(d) for d in deps)):
+        cuda_lib = "/usr/local/cuda/lib64"
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fopenmp", "-o", exe, src, "-L" + libdir, "-ltamcmc_gpu", "-L" + cuda_lib, "-lcudart",
+                               "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda_lib])
+    return exe
+
+
+def test_gaussfit_example_builds(pkg):
+    pkg.lib()
+    assert os.path.exists(_build_gaussfit())
+
+
+@pytest.mark.gpu
+def test_gaussfit_mcmc_on_reference_fixture(pkg, tmp_path):
+    """The whole first-stage analysis of the reference on its own fixture: read .model/.data, sample the posterior of the
+    Harvey + Gaussian model under the .model's priors with the GPU likelihood.  The chain leaves the .model's rough guess
+    (log posterior +5000), stays inside the priors, is reproducible for a fixed seed, and mixes (measured: 28k MCMC steps/s
+    of 6 chains x 32k bins on one B200; 6000 and 30000 steps give the same posterior means)."""
+    g = np.load(GOLD_G)
+    f = tmp_path / "star.model"
+    f.write_text(str(g["model_text"]))
+    m = pkg.formats.read_simple_matrix_model(str(f))
+    x, y = g["x"], g["y"]
+    errors = 0.03 * np.abs(m["inputs"])
+    case = tmp_path / "case.bin"
+    with open(case, "wb") as fh:
+        for a in ([len(x), len(m["inputs"]), 6, 20261018], x, y, m["inputs"], m["relax"], m["prior_kinds"], m["priors"].ravel(), errors):
+            fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    exe = _build_gaussfit()
+    outs = []
+    for _ in range(2):
+        r = subprocess.run([exe, str(case), "6000"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
+        outs.append(json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1]))
+    a, b = outs
+    assert a["final"] == b["final"]                                  # same seed, same chain
+    assert a["mean"][2] == 4.0 and a["sd"][2] == 0.0                 # p1 is fixed in the .model (relax 0)
+    lo, hi = m["priors"][0, 8], m["priors"][1, 8]                    # uniform prior on numax
+    assert lo < a["mean"][8] < hi and a["sd"][8] < 15.0
+    assert a["mean"][9] > 0.5 * 0.263 * a["mean"][8] ** 0.77         # the Stello+2009 width condition of priors_Harvey_Gaussian held
+    assert a["logpost_final"] > a["logpost_initial"] + 1000.0        # the .model's initial guess is far from the posterior mode
+    assert 0.03 < a["acceptance_cold"] < 0.8 and a["swap_rate"] > 0.05
+    print(a)
