@@ -214,6 +214,7 @@ struct Common {
     double aterm[12];      // aj: [a1_0,a1_1,...,a6_0,a6_1]
     int do_amp;
     int status;
+    int eta_from_fit;      // eta0 comes from the large-separation fit of warp 1 (phase 1b)
 };
 
 constexpr int EXP_THREADS = 512;                // 16 warps: the (mode, m) slot pass and the queue pass are latency-bound
@@ -229,7 +230,8 @@ struct ModeTmp {
     double f_s;            // splitting used by nu (a1etaa3 family)
     double H;              // common height (multiplied by the m-ratios), or < 0 when per-m heights are used
     double a[6];           // a1..a6 of this mode (aj family)
-    double eta0;           // eta0 seen by this mode
+    double eta0;           // eta0 seen by this mode (eta_cm: take the chain's eta0, which warp 1 computes while pass A runs)
+    int eta_cm;
     int hoff;              // model 13: offset of the per-m heights in the parameter vector
     int n;
     int i0, i1, bad;       // bit-exact window of set_imin_imax (pass A), bad != 0: imax - imin <= 0
@@ -545,7 +547,78 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     const double* fl0_all = params + Nmax + lmax;
     const double* Wl0_all = params + o_width;
 
-    // ---------------- phase 1: per-chain common quantities, spread over three warps ----------------
+    // ---------------- phase 1a: the scalars pass A needs (one thread; everything here is a parameter read) ----------------
+    if (!inactive) {
+        if (tid >= 97 && tid <= 99) {
+            const int l = tid - 96;
+            const bool have = mode_table ? false : (model == 11 || model == 14) ? false : (lmax >= l);
+            cm.Vl[l] = have ? fabs(params[Nmax + l - 1]) : 1.0;
+        } else if (tid == 96) {
+            cm.eta_from_fit = 0; cm.eta0 = 0.0;
+            cm.trunc_c = mode_table ? params[2] : params[o_cfg];
+            cm.do_amp = mode_table ? 0 : (params[o_cfg + 1] != 0.0);
+            cm.ratios[0][0] = 1.0;
+            cm.Vl[0] = 1.0;
+            cm.status = 0;
+            cm.a1 = cm.a3 = cm.a11 = cm.a12 = 0.0;
+            switch (model) {
+            case 3: case 12: case 13:    // models.cpp:2011-2016, 2219-2222, 2396-2399
+                cm.a1 = fabs(params[o_split]);
+                cm.eta_from_fit = 1;
+                cm.a3 = params[o_split + 2];
+                cm.asym = params[o_split + 5];
+                break;
+            case 6:                      // models.cpp:87-91
+                cm.a11 = fabs(params[o_split]);
+                cm.a12 = fabs(params[o_split + 6]);
+                cm.eta_from_fit = 1;
+                cm.a3 = params[o_split + 2];
+                cm.asym = params[o_split + 5];
+                break;
+            case 7: case 8:              // a1n / a1nl etaa3: models.cpp:290-296, 1075-1081 (splittings per radial order: pass A)
+                cm.eta_from_fit = 1;
+                cm.a3 = params[o_split + 2];
+                cm.asym = params[o_split + 5];
+                break;
+            case 14:                     // model_MS_local_Hnlm: models.cpp:3242-3245
+                cm.a1 = fabs(params[o_split]);
+                cm.eta0 = params[o_split + 1];
+                cm.a3 = params[o_split + 2];
+                cm.asym = params[o_split + 5];
+                break;
+            case 11:                     // models.cpp:3059-3075 (Nvis plays the role of lmax)
+                cm.a1 = params[o_split + 3] * params[o_split + 3] + params[o_split + 4] * params[o_split + 4];
+                cm.eta0 = params[o_split + 1];
+                cm.a3 = params[o_split + 2];
+                cm.asym = params[o_split + 5];
+                break;
+            case 23:                     // models.cpp:1257-1270
+                for (int k = 0; k < 12; k++) cm.aterm[k] = params[o_split + k];
+                cm.asym = params[o_split + 13];
+                cm.eta_from_fit = (params[o_split + 12] == 1) ? 1 : 0; cm.eta0 = 0.0;
+                break;
+            case TAMCMC_MODEL_ID_KALLINGER_GAUSS: case TAMCMC_MODEL_ID_HARVEY_GAUSS:   // no modes: background + Gaussian envelope
+                cm.asym = 0.0;
+                cm.eta0 = 0.0;
+                break;
+            case TAMCMC_MODEL_ID_MODE_TABLE:   // modes already resolved by a host expander (e.g. models.cpp:4788-4911)
+                cm.asym = params[3];
+                cm.eta0 = 0.0;
+                if (!(params[0] >= 0.0 && params[0] <= (double)sd.nmodes_cap)) cm.status = TAMCMC_ST_BADCFG;
+                break;
+            default:
+                cm.status = TAMCMC_ST_BADCFG;
+                cm.eta0 = 0; cm.asym = 0;
+                break;
+            }
+            if (cm.status) atomicOr(&s_status, cm.status);
+        }
+    }
+    __syncthreads();
+    const bool run = !inactive && !(s_status & TAMCMC_ST_BADCFG);
+
+    // ---------------- phase 1b (warps 0-2) beside pass A of the first batch (warps 4-7): the m-height ratios, eta0 and the
+    // noise record are long dependent FP64 chains that pass A does not read ----------------
     if (!inactive) {
         if (tid < 15) {
             // warp 0, lanes 0..14: the 3+5+7 entries of amplitude_ratio(l, inc), l = 1..3 (or the ratio parameters)
@@ -569,74 +642,12 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 }
             }
             ETRACE_T(8, 14);
-        } else if (tid >= 16 && tid <= 18) {
-            const int l = tid - 15;
-            const bool have = mode_table ? false : (model == 11 || model == 14) ? false : (lmax >= l);
-            cm.Vl[l] = have ? fabs(params[Nmax + l - 1]) : 1.0;
         } else if (tid >= 32 && tid < 64) {
             // warp 1: eta0 by the whole warp (models that use it), then lane 0 files the scalar parameters
             const bool need_eta = (model == 3 || model == 12 || model == 13 || model == 6 || model == 7 || model == 8) ||
                                   (model == 23 && params[o_split + 12] == 1);
             const double eta_w = need_eta ? d_eta0_fct_warp(fl0_all, Nfl0, tid - 32) : 0.0;
-            if (tid == 32) {
-            cm.trunc_c = mode_table ? params[2] : params[o_cfg];
-            cm.do_amp = mode_table ? 0 : (params[o_cfg + 1] != 0.0);
-            cm.ratios[0][0] = 1.0;
-            cm.Vl[0] = 1.0;
-            cm.status = 0;
-            cm.a1 = cm.a3 = cm.a11 = cm.a12 = 0.0;
-            switch (model) {
-            case 3: case 12: case 13:    // models.cpp:2011-2016, 2219-2222, 2396-2399
-                cm.a1 = fabs(params[o_split]);
-                cm.eta0 = eta_w;
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 6:                      // models.cpp:87-91
-                cm.a11 = fabs(params[o_split]);
-                cm.a12 = fabs(params[o_split + 6]);
-                cm.eta0 = eta_w;
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 7: case 8:              // a1n / a1nl etaa3: models.cpp:290-296, 1075-1081 (splittings per radial order: pass A)
-                cm.eta0 = eta_w;
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 14:                     // model_MS_local_Hnlm: models.cpp:3242-3245
-                cm.a1 = fabs(params[o_split]);
-                cm.eta0 = params[o_split + 1];
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 11:                     // models.cpp:3059-3075 (Nvis plays the role of lmax)
-                cm.a1 = params[o_split + 3] * params[o_split + 3] + params[o_split + 4] * params[o_split + 4];
-                cm.eta0 = params[o_split + 1];
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 23:                     // models.cpp:1257-1270
-                for (int k = 0; k < 12; k++) cm.aterm[k] = params[o_split + k];
-                cm.asym = params[o_split + 13];
-                cm.eta0 = (params[o_split + 12] == 1) ? eta_w : 0.0;
-                break;
-            case TAMCMC_MODEL_ID_KALLINGER_GAUSS: case TAMCMC_MODEL_ID_HARVEY_GAUSS:   // no modes: background + Gaussian envelope
-                cm.asym = 0.0;
-                cm.eta0 = 0.0;
-                break;
-            case TAMCMC_MODEL_ID_MODE_TABLE:   // modes already resolved by a host expander (e.g. models.cpp:4788-4911)
-                cm.asym = params[3];
-                cm.eta0 = 0.0;
-                if (!(params[0] >= 0.0 && params[0] <= (double)sd.nmodes_cap)) cm.status = TAMCMC_ST_BADCFG;
-                break;
-            default:
-                cm.status = TAMCMC_ST_BADCFG;
-                cm.eta0 = 0; cm.asym = 0;
-                break;
-            }
-            if (cm.status) atomicOr(&s_status, cm.status);
-            }
+            if (tid == 32 && cm.eta_from_fit) cm.eta0 = eta_w;
             ETRACE_T(9, 32);
         } else if (tid >= 64 && tid < 96) {
             // warp 2: Harvey-like background parameters, one lane per term
@@ -648,21 +659,22 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             ETRACE_T(10, 64);
         }
     }
-    __syncthreads();
 
     ETRACE(2);
     // ---------------- phase 2: modes in batches of 128; three passes per batch ----------------
     const int nmodes = sd.nmodes_cap;
-    const bool run = !inactive && !(s_status & TAMCMC_ST_BADCFG);
     const int nmodes_live = (mode_table && run) ? (int)params[0] : nmodes;     // mode table: per-chain mode count
     for (int base = 0; run && base < nmodes; base += EXP_BATCH) {
         // ---- pass A: one thread per mode: degree, frequency, width, height rule, splittings ----
         {
-            const int j = base + tid;
-            static_assert(EXP_BATCH <= EXP_THREADS, "one scratch slot per mode of a batch");
-            ModeTmp& t = mt[tid < EXP_BATCH ? tid : 0];      // filled in place in shared memory (threads >= EXP_BATCH idle here)
-            if (tid < EXP_BATCH) t.have = 0;
-            if (mode_table && tid < EXP_BATCH && j < nmodes_live) {
+            // threads 128..255 (warps 4-7): warps 0-2 are still busy with phase 1b during the first batch
+            const int ta = tid - EXP_BATCH;
+            const bool mine = ta >= 0 && ta < EXP_BATCH;
+            const int j = base + ta;
+            static_assert(2 * EXP_BATCH <= EXP_THREADS, "one scratch slot per mode of a batch, on warps 4..7");
+            ModeTmp& t = mt[mine ? ta : 0];      // filled in place in shared memory (the other threads idle here)
+            if (mine) t.have = 0;
+            if (mode_table && mine && j < nmodes_live) {
                 // one optimum_lorentzian_calc_aj call of the host model function (e.g. models.cpp:4937, 4952, 4977, 5001)
                 const double* r = params + o_modes + TAMCMC_MT_STRIDE * j;
                 const int l = (int)r[0];
@@ -670,10 +682,10 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 else {
                     t.have = 1; t.l = l; t.n = j; t.fc = r[1]; t.H = r[2]; t.W = r[3];
                     for (int k = 0; k < 6; k++) t.a[k] = r[4 + k];
-                    t.eta0 = r[10]; t.fsw = r[4]; t.f_s = 0.0;
+                    t.eta0 = r[10]; t.eta_cm = 0; t.fsw = r[4]; t.f_s = 0.0;
                     t.hoff = o_modes + TAMCMC_MT_STRIDE * j + 11 + 3;     // extra[m] = params[hoff + m]
                 }
-            } else if (!mode_table && tid < EXP_BATCH && j < nmodes) {
+            } else if (!mode_table && mine && j < nmodes) {
                 int l, n;
                 if (model == 3 || model == 12 || model == 13 || model == 6 || model == 7 || model == 8) {
                     l = j % (lmax + 1); n = j / (lmax + 1);          // n-major, l interleaved (models.cpp:2026-2085)
@@ -685,7 +697,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 }
                 const int o_fl = Nmax + lmax + (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0);
                 const double fc = params[o_fl + n];
-                t.have = 1; t.l = l; t.n = n; t.fc = fc; t.hoff = -1; t.eta0 = cm.eta0;
+                t.have = 1; t.l = l; t.n = n; t.fc = fc; t.hoff = -1; t.eta0 = 0.0; t.eta_cm = 1;     // cm.eta0 is read in pass B
                 for (int k = 0; k < 6; k++) t.a[k] = 0.0;
                 if (model == 14) {
                     // models.cpp:3256-3318: individual widths; heights H(n,l,|m|) at params[base_l + (l+1) n + |m|] with
@@ -706,7 +718,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                     if (l == 0) {
                         t.W = fabs(Wl0_all[n]);
                         t.H = cm.do_amp ? amp_to_height(params[n], t.W) : fabs(params[n]);
-                        t.eta0 = 0.0;
+                        t.eta0 = 0.0; t.eta_cm = 0;
                     } else {
                         t.W = fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
                         const double Hi = d_lin_interpol(fl0_all, params, Nmax, fc);
@@ -739,9 +751,9 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                     }
                 }
             }
-            ETRACE_T(11, 5);
+            ETRACE_T(11, EXP_BATCH + 5);
             // bit-exact window (build_lorentzian.cpp:595-649), one thread per mode
-            if (tid < EXP_BATCH && t.have)
+            if (mine && t.have)
                 t.bad = d_set_imin_imax(sd.x0, sd.xlast, sd.Nglob, t.l, t.fc, t.W, t.fsw, cm.trunc_c, sd.step, &t.i0, &t.i1);
         }
         __syncthreads();
@@ -753,9 +765,10 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             if (!t.have || k > 2 * t.l) continue;
             const int l = t.l, m = k - l;
             double nu, h;
-            if (model == 23) nu = nu_aj(l, m, t.fc, t.a, t.eta0);
-            else if (mode_table) { nu = nu_aj(l, m, t.fc, t.a, t.eta0); if (l != 0) nu = nu + params[t.hoff + m]; }   // build_lorentzian.cpp:182-190
-            else nu = nu_a1etaa3(l, m, t.fc, t.f_s, t.eta0, cm.a3);
+            const double eta0 = t.eta_cm ? cm.eta0 : t.eta0;
+            if (model == 23) nu = nu_aj(l, m, t.fc, t.a, eta0);
+            else if (mode_table) { nu = nu_aj(l, m, t.fc, t.a, eta0); if (l != 0) nu = nu + params[t.hoff + m]; }   // build_lorentzian.cpp:182-190
+            else nu = nu_a1etaa3(l, m, t.fc, t.f_s, eta0, cm.a3);
             if (t.H >= 0.0) h = t.H * cm.ratios[l][k];
             else {
                 const double PI = 3.141592653589793238462643383279502884;
@@ -837,6 +850,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         __syncthreads();
     }
 
+    __syncthreads();       // phase 1b has no barrier of its own when no batch ran (envelope models, masked chains)
     ETRACE(5);
     // ---------------- phase 3: tile costs -> heavy-first work queue ----------------
     const bool enqueue = run && (s_status == 0);
