@@ -235,6 +235,8 @@ def main():
         for mid, make, name in ((0, synth.kallinger_gaussian_params, "model_Kallinger2014_Gaussian"), (1, synth.harvey_gaussian_params, "model_Harvey_Gaussian")):
             rng = np.random.default_rng(7 + mid)
             rows = np.stack([make(rng, jitter=0.02) for _ in range(10)])
+            if mid == 0:
+                rows[:, [4, 9, 12]] = 4.0          # super-Lorentzian slopes fixed at 4 as in the reference's .model files
             rc, M0 = O.call_model(mid, rows[0], synth.ENVELOPE_PLENGTH, x)
             y = M0 * rng.exponential(1.0, N)
             t0 = time.perf_counter()

@@ -122,7 +122,7 @@ struct tamcmc_gpu_ctx {
     double* d_Tcoefs = nullptr;
     double* d_partial = nullptr;
     double* d_ksi = nullptr;                 // get_ksinorm slice sums (Kallinger2014 model), [SC][ksi_slices][3]
-    int ksi_slices = 0;
+    int ksi_slices = 0, ksi_slice_bins = TAMCMC_KSI_SLICE, ksi_maxN = 0;
     void* d_out = nullptr;          // [SC] double logL then [SC] int status
     double* d_model = nullptr;      // max Nloc
     // pinned host staging
@@ -177,7 +177,7 @@ ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const uns
     a.tilerec = c->d_tilerec; a.x = c->d_x; a.lnx = c->d_lnx;
     a.Nchains = c->Nchains; a.params_stride = c->params_stride; a.modes_stride = c->modes_stride;
     a.tiles_stride = c->tiles_stride; a.max_tiles = c->max_tiles; a.trace = c->d_trace ? c->d_trace + 64 * 2048 : nullptr;
-    a.ksi_part = c->d_ksi; a.ksi_slices = c->ksi_slices;
+    a.ksi_part = c->d_ksi; a.ksi_slices = c->ksi_slices; a.ksi_slice_bins = c->ksi_slice_bins;
     return a;
 }
 
@@ -406,7 +406,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         sd.Nparams = in.Nparams;
         sd.nmodes_cap = nm;
         for (int k = 0; k < 11; k++) sd.plength[k] = envelope ? 0 : in.plength[k];
-        if (in.model_id == TAMCMC_MODEL_ID_KALLINGER_GAUSS) c->ksi_slices = std::max(c->ksi_slices, (sd.Nloc + TAMCMC_KSI_SLICE - 1) / TAMCMC_KSI_SLICE);
+        if (in.model_id == TAMCMC_MODEL_ID_KALLINGER_GAUSS) c->ksi_maxN = std::max(c->ksi_maxN, sd.Nloc);
         tiles += sd.ntiles;
         off += (long long)sd.ntiles * TB;
         if (in.Nparams > c->params_stride) c->params_stride = in.Nparams;
@@ -457,6 +457,14 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     CKC(cudaMalloc(&c->d_asym, sizeof(int) * (size_t)SC));
     CKC(cudaMalloc(&c->d_Tcoefs, sizeof(double) * Nchains));
     CKC(cudaMalloc(&c->d_partial, sizeof(double) * 3 * (size_t)SC * c->tiles_stride));
+    if (c->ksi_maxN > 0) {
+        // at most ~2 waves of pre-pass CTAs (4 x 256 threads per SM resident); measured flat between 2048 and 4096 bins per CTA, slower at 8192 when the batch allows it: their prologue, not their bins, is the cost
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        while ((long long)SC * ((c->ksi_maxN + c->ksi_slice_bins - 1) / c->ksi_slice_bins) > 8LL * sms && c->ksi_slice_bins < (1 << 20)) c->ksi_slice_bins *= 2;
+        if (const char* e = std::getenv("TAMCMC_GPU_KSI_SLICE")) { const int v = std::atoi(e); if (v >= 256 && v <= (1 << 20)) c->ksi_slice_bins = v; }
+        c->ksi_slices = (c->ksi_maxN + c->ksi_slice_bins - 1) / c->ksi_slice_bins;
+    }
     if (c->ksi_slices > 0) {
         CKC(cudaMalloc(&c->d_ksi, sizeof(double) * 3 * (size_t)SC * c->ksi_slices));
         CKC(cudaMemset(c->d_ksi, 0, sizeof(double) * 3 * (size_t)SC * c->ksi_slices));

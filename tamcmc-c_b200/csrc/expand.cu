@@ -255,6 +255,7 @@ __device__ __noinline__ void emit_noise(NoiseRec* out, const double* noise_param
         const int slot = __popc(mk & ((1u << lane) - 1u));
         nr.H[slot] = H;
         nr.lnsc[slot] = log((1e-3) * tau);
+        nr.isc[slot] = (1e-3) * tau;
         nr.pw[slot] = pw;
         { double sn, cs; const double ang = 3.14159265358979323846 / fmax(pw, 1.0); sincos(ang, &sn, &cs); nr.spi[slot] = sn; nr.cpi[slot] = cs; }
         // generalised binomial coefficients C(p, q) = C(p, q-1) (p - q + 1) / q
@@ -263,7 +264,7 @@ __device__ __noinline__ void emit_noise(NoiseRec* out, const double* noise_param
 #pragma unroll
         for (int q = 1; q < TAMCMC_BG_TERMS; q++) { b = b * (pw - (double)(q - 1)) * (1.0 / (double)q); nr.binom[slot][q] = b; }
     }
-    if (lane >= nh && lane < TAMCMC_MAX_HARVEY) { nr.H[lane] = 0; nr.lnsc[lane] = 0; nr.pw[lane] = 0; nr.cpi[lane] = 0; nr.spi[lane] = 0; }
+    if (lane >= nh && lane < TAMCMC_MAX_HARVEY) { nr.H[lane] = 0; nr.lnsc[lane] = 0; nr.isc[lane] = 0; nr.pw[lane] = 0; nr.cpi[lane] = 0; nr.spi[lane] = 0; }
     if (lane == 0) {
         nr.nh = nh; nr.gauss = 0;
         nr.N0 = (Nnoise > 0) ? fabs(noise_params[Nnoise - 1]) : 0.0;
@@ -297,32 +298,63 @@ __device__ __noinline__ void kallinger_params(const double* p, KallingerPar& k)
 // get_ksinorm (noise_models.cpp:65-84), first half: trapezoid sums of 1 / (1 + (x/b_k)^c_k) over the whole spectrum, one
 // CTA per slice of TAMCMC_KSI_SLICE bins and chain, fixed reduction shape; the expander adds the slices in slice order.
 // (x/b)^c = exp(c (ln x - ln b)) with ln x tabulated at create; x = 0 gives exp(-inf) = 0 like pow(0, c), c = 0 gives 1.
+// 1/x to ~1 ulp: hardware approximation + two Newton steps (explicit FMAs: this file is compiled with -fmad=false)
+__device__ __forceinline__ double rcp_newton(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 __global__ void __launch_bounds__(256) tamcmc_ksi_kernel(ExpandArgs A)
 {
     const int sc = blockIdx.x, slice = blockIdx.y;
     const StarDesc& sd = A.stars[sc / A.Nchains];
     if (sd.model_id != TAMCMC_MODEL_ID_KALLINGER_GAUSS) return;
     if (A.active && !A.active[sc]) return;
-    const int b0 = slice * TAMCMC_KSI_SLICE;
+    const int b0 = slice * A.ksi_slice_bins;
     if (b0 >= sd.Nloc) return;
-    __shared__ double s_lnb[3], s_c[3];
+    __shared__ double s_lnb[3], s_c[3], s_ib[3];
     __shared__ double s_red[8][3];
-    if (threadIdx.x == 0) {
-        KallingerPar k;
-        kallinger_params(A.params + (size_t)sc * A.params_stride, k);
-        for (int j = 0; j < 3; j++) { s_lnb[j] = log(k.b[j]); s_c[j] = k.c[j]; }
+    if (threadIdx.x < 3) {
+        // b_j = |k_j |numax + mu_numax|^s_j| (noise_models.cpp:117-121) through logarithms, one lane per term: the CTA waits for
+        // this prologue, and three pow() + log() + divide in a row on one thread cost more than the slice's bins
+        const double* p = A.params + (size_t)sc * A.params_stride;
+        const int j = threadIdx.x, ik = (j == 0) ? 2 : (j == 1) ? 7 : 10;
+        const double lnb = log(fabs(p[ik])) + p[ik + 1] * log(fabs(fabs(p[15]) + p[17]));
+        s_lnb[j] = lnb; s_c[j] = fabs(p[ik + 2]); s_ib[j] = exp(-lnb);
     }
     __syncthreads();
     const double* lx = A.lnx + sd.off;
-    const int b1 = min(b0 + TAMCMC_KSI_SLICE, sd.Nloc);
+    const double* xs = A.x + sd.off;
+    const int b1 = min(b0 + A.ksi_slice_bins, sd.Nloc);
     double acc[3] = {0.0, 0.0, 0.0};
-    for (int i = b0 + (int)threadIdx.x; i < b1; i += 256) {
-        const double w = (i == 0 || i == sd.Nloc - 1) ? 0.5 : 1.0;
-        const double l = lx[i];
+    const bool ipow0 = (s_c[0] == 4.0 || s_c[0] == 2.0), ipow1 = (s_c[1] == 4.0 || s_c[1] == 2.0), ipow2 = (s_c[2] == 4.0 || s_c[2] == 2.0);
+    const bool need_ln = !(ipow0 && ipow1 && ipow2);         // ln x is only read for non-integer slopes
+    constexpr int U = 8;                                     // bins per thread in flight: the loads of a chunk are issued together
+    for (int i0 = b0 + (int)threadIdx.x; i0 < b1; i0 += 256 * U) {
+        double xv[U], lv[U];
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const double z = (s_c[j] == 0.0) ? 1.0 : exp(s_c[j] * (l - s_lnb[j]));
-            acc[j] += w / (1.0 + z);
+        for (int q = 0; q < U; q++) {
+            const int i = i0 + 256 * q;
+            xv[q] = (i < b1) ? xs[i] : 0.0;
+            lv[q] = (need_ln && i < b1) ? lx[i] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < U; q++) {
+            const int i = i0 + 256 * q;
+            const double w = (i >= b1) ? 0.0 : (i == 0 || i == sd.Nloc - 1) ? 0.5 : 1.0;      // no early exit: the 8 x 3 chains interleave
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                double z;
+                if (s_c[j] == 4.0 || s_c[j] == 2.0) {          // the usual fixed slopes: plain products instead of exp
+                    const double r = xv[q] * s_ib[j], r2 = r * r;
+                    z = (s_c[j] == 4.0) ? r2 * r2 : r2;
+                } else z = (s_c[j] == 0.0) ? 1.0 : exp(s_c[j] * (lv[q] - s_lnb[j]));
+                acc[j] += (z < 1e300) ? w * rcp_newton(1.0 + z) : w / (1.0 + z);      // 1 + z in [1, 1e300]: the Newton form is exact enough; inf / NaN keep IEEE semantics
+            }
         }
     }
 #pragma unroll
@@ -356,10 +388,11 @@ __device__ __noinline__ void emit_kallinger(NoiseRec* out, const double* p, cons
         const double H = (ksi * (k.a[lane] * k.a[lane])) / k.b[lane];
         nr.H[lane] = H;
         nr.lnsc[lane] = -log(k.b[lane]);
+        nr.isc[lane] = 1.0 / k.b[lane];
         nr.pw[lane] = k.c[lane];
         nr.cpi[lane] = 0; nr.spi[lane] = 0;
         if (!isfinite(H) || !isfinite(nr.lnsc[lane]) || !isfinite(k.c[lane])) atomicOr(status, TAMCMC_ST_NONFINITE);
-    } else if (lane < TAMCMC_MAX_HARVEY) { nr.H[lane] = 0; nr.lnsc[lane] = 0; nr.pw[lane] = 0; nr.cpi[lane] = 0; nr.spi[lane] = 0; }
+    } else if (lane < TAMCMC_MAX_HARVEY) { nr.H[lane] = 0; nr.lnsc[lane] = 0; nr.isc[lane] = 0; nr.pw[lane] = 0; nr.cpi[lane] = 0; nr.spi[lane] = 0; }
     if (lane == 0) {
         const double sig = fabs(p[16]);
         nr.nh = 3; nr.gauss = 2;
@@ -652,7 +685,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         } else if (tid >= 64 && tid < 96) {
             // warp 2: Harvey-like background parameters, one lane per term
             if (model == TAMCMC_MODEL_ID_KALLINGER_GAUSS)
-                emit_kallinger(noise, params, A.ksi_part + (size_t)sc * A.ksi_slices * 3, (sd.Nloc + TAMCMC_KSI_SLICE - 1) / TAMCMC_KSI_SLICE,
+                emit_kallinger(noise, params, A.ksi_part + (size_t)sc * A.ksi_slices * 3, (sd.Nloc + A.ksi_slice_bins - 1) / A.ksi_slice_bins,
                                sd.step, sd.xlast, &s_status, tid - 64);
             else if (model == TAMCMC_MODEL_ID_HARVEY_GAUSS) emit_harvey_gauss(noise, params, &s_status, tid - 64);
             else emit_noise(noise, params + o_noise, Nnoise, (model == 11 || model == 14) ? 0 : (Nnoise - 1) / 3, &s_status, tid - 64);

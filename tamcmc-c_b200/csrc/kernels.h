@@ -27,6 +27,7 @@ struct ExpandArgs {
     unsigned long long* trace;       // profiling aid (TAMCMC_TRACE builds)
     double* ksi_part;                // [nstars*Nchains][ksi_slices][3] partial sums of get_ksinorm (Kallinger2014 model only), or nullptr
     int ksi_slices;
+    int ksi_slice_bins;              // bins per pre-pass CTA: the smallest power-of-two multiple of TAMCMC_KSI_SLICE that fits the grid in one wave
 };
 
 struct WhittleArgs {

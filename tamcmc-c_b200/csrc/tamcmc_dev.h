@@ -85,6 +85,7 @@ struct NoiseRec {
     double xnyq;                         // leakage: eta = sin(a)/a, a = 0.5 pi x / x_nyquist (noise_models.cpp:89-97)
     double H[TAMCMC_MAX_HARVEY];         // heights
     double lnsc[TAMCMC_MAX_HARVEY];      // ln(1e-3 * tau)
+    double isc[TAMCMC_MAX_HARVEY];       // 1e-3 * tau itself: integer exponents (2, 4) are evaluated as plain products
     double pw[TAMCMC_MAX_HARVEY];        // exponents
     double cpi[TAMCMC_MAX_HARVEY];       // cos(pi/p), sin(pi/p): direction of the nearest pole of 1/(1+z^p)
     double spi[TAMCMC_MAX_HARVEY];

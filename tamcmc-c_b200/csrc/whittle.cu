@@ -647,12 +647,20 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
                     const double2 v = *reinterpret_cast<const double2*>(lx + 2 * tid + 2 * NC * pj);
                     lnx[2 * pj] = v.x; lnx[2 * pj + 1] = v.y;
                 }
+                const double xc = sg.xc;
                 for (int h = 0; h < nh; h++) {
-                    const double H = nz->H[h], ls = nz->lnsc[h], pw = nz->pw[h];
+                    const double H = nz->H[h], ls = nz->lnsc[h], pw = nz->pw[h], isc = nz->isc[h];
+                    const bool p4 = (pw == 4.0), p2 = (pw == 2.0);     // the usual fixed slopes: plain products instead of exp
 #pragma unroll
                     for (int j = 0; j < BPT; j++) {
-                        const double arg = fmin(pw * (ls + lnx[j]), 70.0);
-                        const double z = (pw == 0.0) ? 1.0 : exp(arg);
+                        double z;
+                        if (p4 || p2) {
+                            const double r = (u[j] + xc) * isc, r2 = r * r;
+                            z = fmin(p4 ? r2 * r2 : r2, 2.5e30);
+                        } else {
+                            const double arg = fmin(pw * (ls + lnx[j]), 70.0);
+                            z = (pw == 0.0) ? 1.0 : exp(arg);
+                        }
                         const double t = 1.0 + z;
                         N[j] = fma(N[j], t, H * D[j]);
                         D[j] *= t;

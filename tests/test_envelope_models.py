@@ -98,3 +98,30 @@ def test_gpu_envelope_argument_checks(pkg):
     with pkg.Context(pkg.Star(1, pkg.synth.ENVELOPE_PLENGTH, 10, x, y), 2, T) as whole, \
             pkg.Context(pkg.Star.shard(1, pkg.synth.ENVELOPE_PLENGTH, 10, x, y, 1000, 3000), 2, T) as part:
         assert np.allclose(part.model(r[0]), whole.model(r[0])[1000:3000], rtol=1e-13, atol=0)
+
+
+@pytest.mark.gpu
+def test_gpu_envelope_integer_slopes(pkg, oracle):
+    """Slopes fixed at exactly 4 or 2 (the usual .model choice) take the product path instead of exp(c ln(x/b))."""
+    rng = np.random.default_rng(9)
+    x = np.arange(20000) * (283.2 / 20000)          # from 0: the first tiles of model 1 are on the exact background path
+    T = pkg.synth.tcoefs(3, 1.7)
+    for mid in (0, 1):
+        rows = []
+        for _ in range(3):
+            if mid == 0:
+                p = pkg.synth.kallinger_gaussian_params(rng, jitter=0.03)
+                p[4], p[9], p[12] = 4.0, 4.0, 2.0
+            else:
+                p = pkg.synth.harvey_gaussian_params(rng, jitter=0.03)
+                p[2], p[5] = 4.0, 2.0
+            rows.append(p)
+        rows = np.stack(rows)
+        rc, M0 = oracle.call_model(mid, rows[0], pkg.synth.ENVELOPE_PLENGTH, x)
+        y = M0 * rng.exponential(1.0, len(x))
+        rc, L_ref = oracle.eval_chains(mid, rows, pkg.synth.ENVELOPE_PLENGTH, x, y, T)
+        assert rc == 0
+        with pkg.Context(pkg.Star(mid, pkg.synth.ENVELOPE_PLENGTH, rows.shape[1], x, y), 3, T) as ctx:
+            assert _rel(ctx.model(rows[0]), M0) < RTOL
+            L, st = ctx.eval(rows)
+            assert (st == 0).all() and _rel(L[0], L_ref) < RTOL
