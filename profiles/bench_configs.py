@@ -57,7 +57,7 @@ def timed(torch, ctx, P_host, steps, dist, extra=None):
     dev = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)) / steps
     e2e = None
     if not raw:
-        ctx.set_profiling(True)                      # CUDA events around each kernel (direct launches, warm L2)
+        ctx.set_profiling(True)                      # CUDA event-record nodes between the kernels of the replayed graph (warm L2)
         for _ in range(10):
             ctx.eval(P_host)
         nprof, ems, wms = ctx.kernel_ms()

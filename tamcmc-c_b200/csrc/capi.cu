@@ -139,7 +139,7 @@ struct tamcmc_gpu_ctx {
     unsigned int epoch_host = 1;     // mirrors the device epoch: advanced once per fused-kernel launch
     // CUDA graphs of the device-side sequence (memset, expand, tile lists, fused kernel, finalize), keyed by the
     // buffer pointers of the call
-    struct GraphEntry { const double* p; const unsigned char* a; double* o; int raw; cudaGraphExec_t exec; };
+    struct GraphEntry { const double* p; const unsigned char* a; double* o; int raw; bool prof; cudaGraphExec_t exec; };
     GraphEntry graphs[4] = {};
     int ngraphs = 0;
     int stagger_ns = 0;               // TAMCMC_GPU_STAGGER_NS (tuning aid)
@@ -204,29 +204,34 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, boo
 
 // expand + fused kernel (tile lists, model, Whittle sums, per-chain finalisation, queue re-arm), enqueued on `st`
 int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
-                     int raw_sum, cudaStream_t st, bool prof)
+                     int raw_sum, cudaStream_t st, bool prof, bool capturing)
 {
     ExpandArgs ea = make_expand_args(c, d_params, d_active, d_logL);
     WhittleArgs wa = make_whittle_args(c, d_logL, raw_sum, c->zero_copy && d_params == c->dh_params);
-    if (prof) CK(cudaEventRecord(c->ev[0], st));
+    // profiling: CUDA events between the kernels.  Inside a captured graph they become event-record NODES
+    // (cudaEventRecordExternal), so the durations are those of the replayed graph -- the configuration that is benchmarked --
+    // without the host launch latency a per-kernel cudaEventRecord pair on a stream adds to a kernel this short.
+#define REC(k) (capturing ? cudaEventRecordWithFlags(c->ev[k], st, cudaEventRecordExternal) : cudaEventRecord(c->ev[k], st))
+    if (prof) CK(REC(0));
     CK(tamcmc_launch_expand(ea, c->SC(), st));
-    if (prof) CK(cudaEventRecord(c->ev[1], st));
+    if (prof) CK(REC(1));
     CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, c->tile_bins, st, c->use_pdl && !prof));
-    if (prof) CK(cudaEventRecord(c->ev[2], st));
+    if (prof) CK(REC(2));
+#undef REC
     return TAMCMC_OK;
 }
 
-// One evaluation on `st`.  Outside profiling the two kernels are replayed as one CUDA graph.
+// One evaluation on `st`: the kernels are replayed as one CUDA graph (with event-record nodes between them while profiling).
 int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
                 int raw_sum, cudaStream_t st)
 {
     c->launches += c->d_ksi ? 3 : 2;
     { const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; }       // what the last CTA will publish
     const bool prof = c->profiling && st == c->stream;
-    if (prof || !c->use_graphs) return enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof);
+    if (!c->use_graphs) return enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof, false);
     for (int i = 0; i < c->ngraphs; i++) {
         const tamcmc_gpu_ctx::GraphEntry& g = c->graphs[i];
-        if (g.p == d_params && g.a == d_active && g.o == d_logL && g.raw == raw_sum) { CK(cudaGraphLaunch(g.exec, st)); return TAMCMC_OK; }
+        if (g.p == d_params && g.a == d_active && g.o == d_logL && g.raw == raw_sum && g.prof == prof) { CK(cudaGraphLaunch(g.exec, st)); return TAMCMC_OK; }
     }
     if (c->ngraphs == 4) {           // evict the oldest
         cudaGraphExecDestroy(c->graphs[0].exec);
@@ -236,12 +241,12 @@ int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* 
     cudaGraph_t graph = nullptr;
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, c->stream, false);
+    const int rc = enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, c->stream, prof, true);
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture");
     tamcmc_gpu_ctx::GraphEntry g;
-    g.p = d_params; g.a = d_active; g.o = d_logL; g.raw = raw_sum; g.exec = nullptr;
+    g.p = d_params; g.a = d_active; g.o = d_logL; g.raw = raw_sum; g.prof = prof; g.exec = nullptr;
     e = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail_cuda(e, "cudaGraphInstantiate");
