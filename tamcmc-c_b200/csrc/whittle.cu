@@ -17,9 +17,11 @@
 //    (build_lorentzian.cpp:151: cwiseInverse) by 4 FP64-pipe instructions, with one reciprocal per bin at the
 //    end.  Exponents of (N, D) are renormalised with 4 integer ops per bin every 16 components.  The background
 //    (noise_models.cpp:15-39) is a 9th-degree polynomial per tile (or exact exp() per bin near x = 0), the
-//    Whittle terms y/M + ln M (likelihoods.cpp:23) are reduced in registers, by warp shuffles and a
-//    fixed-shape block tree into one partial per tile; the last CTA to finish sums the per-tile partials of every
-//    chain in tile order, so results are bitwise reproducible run to run whatever the scheduling.
+//    Whittle terms y/M + ln M (likelihoods.cpp:23) are summed per thread; the thread stores its three sums in the
+//    slot's scratch and releases the slot, and the slot's PRODUCER warp reduces the 384 triples (fixed shape) into
+//    one partial per tile once the empty barrier has handed the slot back.  The last CTA to finish sums the per-tile
+//    partials of every chain in tile order, so results are bitwise reproducible run to run whatever the scheduling.
+//    The Gaussian-envelope models (ids 0, 1: no Lorentzians) ride the same path with empty component lists.
 #include "tamcmc_dev.h"
 #include "kernels.h"
 #include <cuda_runtime.h>
