@@ -308,11 +308,16 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
             tma_load_1d(sg->x, A.x + off, TILE * sizeof(double), full);
             tma_load_1d(sg->y, A.y + off, TILE * sizeof(double), full);
         }
+        // mode headers are fetched one batch ahead: the header round trip of batch k+1 overlaps the component-record round
+        // trip of batch k (a tile-list build is a chain of dependent loads, and the first one is every CTA's start-up)
+        int4 hnext = make_int4(0, 0, 0, 0);
+        if (lane < nmodes) hnext = *reinterpret_cast<const int4*>(modes + lane);     // {i0, i1, ncomp, nfast | wide << 16}
         for (int base = 0; base < nmodes; base += 32) {
             const int mi = base + lane;
             int ncomp = 0, nfast = 0, ngen = 0, i0 = 0, i1 = 0, nfast_rec = 0, mwide = 0, wbit = 0;
+            const int4 h = hnext;
+            if (mi + 32 < nmodes) hnext = *reinterpret_cast<const int4*>(modes + mi + 32);
             if (mi < nmodes) {
-                const int4 h = *reinterpret_cast<const int4*>(modes + mi);     // {i0, i1, ncomp, nfast | wide << 16}
                 if (h.z > 0 && h.x < gend && h.y > g0) {
                     ncomp = h.z; nfast_rec = h.w & 0xffff; i0 = h.x; i1 = h.y;
                     nfast = (h.x <= g0 && h.y >= gend) ? nfast_rec : 0;
