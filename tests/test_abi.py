@@ -74,3 +74,25 @@ def test_product_never_references_the_oracle():
                     if "oracle/" in txt or "tamcmc_oracle" in txt or "_oracle" in txt:
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_links_from_c(pkg, tmp_path):
+    """The boundary is a C ABI: the header compiles as strict C99 and a C program links against the library
+    (no C++ runtime, no torch types in any signature)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "tamcmc_gpu.h"\n#include <stdio.h>\n'
+                   "int main(void) {\n"
+                   "  tamcmc_gpu_star s; tamcmc_gpu_ctx *c = 0; (void)s;\n"
+                   "  if (tamcmc_gpu_create(0, 0, 0, 1, 0, 1.0, TAMCMC_LIKELIHOOD_CHI22P, &c) != TAMCMC_ERR_ARG) return 1;\n"
+                   '  printf("%d %s\\n", tamcmc_gpu_abi_version(), tamcmc_gpu_strerror(TAMCMC_ERR_WINDOW));\n'
+                   "  return sizeof(s) == 128 ? 0 : 2;\n}\n")
+    libdir = os.path.join(root, "tamcmc-c_b200")
+    exe = tmp_path / "abi_check"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), "-o", str(exe), str(src),
+                           "-L" + libdir, "-ltamcmc_gpu", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir,
+                           "-Wl,-rpath,/usr/local/cuda/lib64"])
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.split()[0] == "2"
