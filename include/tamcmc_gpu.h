@@ -134,6 +134,16 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx *ctx, const double *params, const unsigned ch
 int tamcmc_gpu_eval_device(tamcmc_gpu_ctx *ctx, const double *d_params, const unsigned char *d_active,
                            double *d_logL, int raw_sum, void *stream);
 
+/* Replaces: MALA::parallel_tempering (MALA.cpp:397-461) for callers that keep chains on the device (e.g. a bin-sharded run
+ * whose ranks all hold the all-reduced log-likelihoods): swap of the adjacent chains A and A+1 of star `star`, decided and
+ * applied on the device, asynchronously on `stream` (NULL = the context's stream).  d_logL holds TEMPERED log-likelihoods
+ * (layout of tamcmc_gpu_eval_device): with LA' = logL[A] T[A]/T[A+1] and LB' = logL[A+1] T[A+1]/T[A], the swap is accepted when
+ * u <= min(1, exp(LA' + LB' - logL[A] - logL[A+1])) (NaN never accepts); then the parameter rows A and A+1 of d_params and, if
+ * given, the entries of d_logPrior are exchanged and logL[A] = LB', logL[A+1] = LA'.  `u` is the caller's uniform draw in [0, 1)
+ * (every rank of a sharded run passes the same one); d_swapped (device int, may be NULL) receives 1 or 0. */
+int tamcmc_gpu_pt_swap_device(tamcmc_gpu_ctx *ctx, int star, int A, double u, double *d_params, double *d_logL,
+                              double *d_logPrior, int *d_swapped, void *stream);
+
 /* Waits for the context's own stream (after tamcmc_gpu_eval_device with stream == NULL) and, when
  * profiling is on, accumulates the CUDA-event durations of that evaluation's kernels. */
 int tamcmc_gpu_sync(tamcmc_gpu_ctx *ctx);

@@ -30,7 +30,7 @@ CHAIN_WINDOW, CHAIN_NONFINITE, CHAIN_BADCFG, CHAIN_INACTIVE = 1, 2, 4, 8
 
 # every symbol include/tamcmc_gpu.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "tamcmc_gpu_create", "tamcmc_gpu_destroy", "tamcmc_gpu_eval", "tamcmc_gpu_eval_device",
+    "tamcmc_gpu_create", "tamcmc_gpu_destroy", "tamcmc_gpu_eval", "tamcmc_gpu_eval_device", "tamcmc_gpu_pt_swap_device",
     "tamcmc_gpu_sync", "tamcmc_gpu_model", "tamcmc_gpu_windows", "tamcmc_gpu_components",
     "tamcmc_gpu_params_stride", "tamcmc_gpu_nstars", "tamcmc_gpu_nchains", "tamcmc_gpu_pairs_last",
     "tamcmc_gpu_set_profiling", "tamcmc_gpu_get_kernel_ms", "tamcmc_gpu_launch_count",
@@ -82,6 +82,8 @@ def lib():
     L.tamcmc_gpu_destroy.argtypes = [vp]
     L.tamcmc_gpu_eval.restype = C.c_int
     L.tamcmc_gpu_eval.argtypes = [vp, _dp, _ucp, _dp, _ip]
+    L.tamcmc_gpu_pt_swap_device.restype = C.c_int
+    L.tamcmc_gpu_pt_swap_device.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp, vp]
     L.tamcmc_gpu_eval_device.restype = C.c_int
     L.tamcmc_gpu_eval_device.argtypes = [vp, vp, vp, vp, C.c_int, vp]
     L.tamcmc_gpu_sync.restype = C.c_int
@@ -250,6 +252,14 @@ class Context:
         def call(_keep=keep):
             return fn(h, pp, pa, po, ps)
         return call
+
+    def pt_swap_device(self, A, u, d_params_ptr, d_logL_ptr, d_logPrior_ptr=None, d_swapped_ptr=None, star=0, stream=None):
+        """Parallel-tempering swap of chains A, A+1 decided and applied on the device (MALA.cpp:397-461)."""
+        rc = lib().tamcmc_gpu_pt_swap_device(self.h, int(star), int(A), float(u), C.c_void_p(d_params_ptr), C.c_void_p(d_logL_ptr),
+                                             C.c_void_p(d_logPrior_ptr) if d_logPrior_ptr else None,
+                                             C.c_void_p(d_swapped_ptr) if d_swapped_ptr else None, C.c_void_p(stream) if stream else None)
+        if rc != OK:
+            _raise(rc)
 
     def eval_device(self, d_params_ptr, d_logL_ptr, d_active_ptr=None, raw_sum=False, stream=None):
         rc = lib().tamcmc_gpu_eval_device(self.h, C.c_void_p(d_params_ptr), C.c_void_p(d_active_ptr) if d_active_ptr else None,

@@ -740,6 +740,19 @@ int tamcmc_gpu_debug_trace(tamcmc_gpu_ctx* c, unsigned long long* out, int nctas
     return TAMCMC_OK;
 }
 
+int tamcmc_gpu_pt_swap_device(tamcmc_gpu_ctx* c, int star, int A, double u, double* d_params, double* d_logL, double* d_logPrior,
+                              int* d_swapped, void* stream)
+{
+    if (!c || !d_params || !d_logL || star < 0 || star >= c->nstars || A < 0 || A + 1 >= c->Nchains) return TAMCMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    const size_t row0 = (size_t)star * c->Nchains;
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c->stream;
+    CK(tamcmc_launch_pt_swap(d_params + row0 * c->params_stride, d_logL + row0, d_logPrior ? d_logPrior + row0 : nullptr, c->d_Tcoefs,
+                             c->params_stride, A, u, d_swapped, st));
+    c->launches += 1;
+    return TAMCMC_OK;
+}
+
 int tamcmc_gpu_sync(tamcmc_gpu_ctx* c)
 {
     if (!c) return TAMCMC_ERR_ARG;

@@ -945,6 +945,39 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     }
 }
 
+// Parallel-tempering swap of two adjacent chains on the device (MALA.cpp:397-461): one CTA; thread 0 decides, all threads
+// exchange the two parameter rows.
+__global__ void __launch_bounds__(256) tamcmc_pt_swap_kernel(double* params, double* logL, double* logPrior, const double* T, int stride,
+                                                             int A, double u, int* swapped)
+{
+    __shared__ int s_do;
+    const int B = A + 1;
+    if (threadIdx.x == 0) {
+        const double LA = logL[A], LB = logL[B];
+        const double LA_TB = LA * T[A] / T[B], LB_TA = LB * T[B] / T[A];
+        double r = exp(LA_TB + LB_TA - LA - LB);
+        if (r > 1.0) r = 1.0;
+        s_do = (u <= r) ? 1 : 0;                      // NaN: the comparison is false
+        if (s_do) {
+            logL[A] = LB_TA; logL[B] = LA_TB;
+            if (logPrior) { const double t = logPrior[A]; logPrior[A] = logPrior[B]; logPrior[B] = t; }
+        }
+        if (swapped) *swapped = s_do;
+    }
+    __syncthreads();
+    if (!s_do) return;
+    double* a = params + (size_t)A * stride;
+    double* b = params + (size_t)B * stride;
+    for (int k = threadIdx.x; k < stride; k += blockDim.x) { const double t = a[k]; a[k] = b[k]; b[k] = t; }
+}
+
+cudaError_t tamcmc_launch_pt_swap(double* d_params_star, double* d_logL_star, double* d_logPrior_star, const double* d_Tcoefs, int stride,
+                                  int A, double u, int* d_swapped, cudaStream_t st)
+{
+    tamcmc_pt_swap_kernel<<<1, 256, 0, st>>>(d_params_star, d_logL_star, d_logPrior_star, d_Tcoefs, stride, A, u, d_swapped);
+    return cudaGetLastError();
+}
+
 cudaError_t tamcmc_expand_configure()
 {
     return cudaFuncSetAttribute(tamcmc_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

@@ -68,6 +68,8 @@ struct WhittleArgs {
 
 cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const double* Q);
 cudaError_t tamcmc_upload_dmm_tables(const double* coef, const double* nnum, const double* nden);
+cudaError_t tamcmc_launch_pt_swap(double* d_params_star, double* d_logL_star, double* d_logPrior_star, const double* d_Tcoefs, int stride,
+                                 int A, double u, int* d_swapped, cudaStream_t st);
 cudaError_t tamcmc_expand_configure();
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st);
 cudaError_t tamcmc_whittle_configure(int* grid_full, int* grid_half);   // one-time function attributes; persistent grid sizes for the two tile sizes

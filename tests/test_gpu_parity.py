@@ -390,3 +390,44 @@ def test_device_entry_graph_cache_rotation(pkg, oracle):
         # host entry interleaved with the device entry on the same context
         L, st = ctx.eval(sets[2])
         assert np.max(np.abs(L[0] - refs[2]) / np.abs(refs[2])) < RTOL
+
+
+def test_device_parallel_tempering_swap(pkg):
+    """tamcmc_gpu_pt_swap_device against the host rule of MALA::parallel_tempering (MALA.cpp:397-461) as restated in
+    host/mcmc_driver.hpp: tempered log-likelihoods, adjacent chains, rows and priors exchanged only when accepted."""
+    import torch
+    params, pl, x = _cases.ms_case(pkg.synth, 3, seed=5, N=6000)
+    rng = np.random.default_rng(8)
+    Nch = 5
+    T = pkg.synth.tcoefs(Nch, 1.7)
+    stars = [pkg.Star(3, pl, len(params), x, np.ones_like(x)) for _ in range(2)]
+    with pkg.Context(stars, Nch, T) as ctx:
+        stride = ctx.params_stride
+        P = rng.standard_normal((2, Nch, stride))
+        for trial in range(40):
+            L = -1e4 * (1 + 0.001 * rng.standard_normal((2, Nch))) / T          # tempered values close enough for both outcomes
+            if trial == 7:
+                L[1, 2] = np.nan
+            pr = rng.standard_normal((2, Nch))
+            star, A, u = int(rng.integers(0, 2)), int(rng.integers(0, Nch - 1)), float(rng.random())
+            dP, dL, dpr = torch.tensor(P, device="cuda"), torch.tensor(L, device="cuda"), torch.tensor(pr, device="cuda")
+            flag = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+            ctx.pt_swap_device(A, u, dP.data_ptr(), dL.data_ptr(), dpr.data_ptr(), flag.data_ptr(), star=star)
+            ctx.sync()
+            B = A + 1
+            LA, LB = L[star, A], L[star, B]
+            LA_TB, LB_TA = LA * T[A] / T[B], LB * T[B] / T[A]
+            with np.errstate(over="ignore", invalid="ignore"):
+                r = min(1.0, np.exp(LA_TB + LB_TA - LA - LB)) if np.isfinite(LA + LB) else np.nan
+            want = bool(u <= r)
+            assert int(flag[0]) == int(want)
+            P2, L2, pr2 = P.copy(), L.copy(), pr.copy()
+            if want:
+                P2[star, [A, B]] = P[star, [B, A]]
+                pr2[star, [A, B]] = pr[star, [B, A]]
+                L2[star, A], L2[star, B] = LB_TA, LA_TB
+            assert np.array_equal(dP.cpu().numpy(), P2)
+            assert np.array_equal(dpr.cpu().numpy(), pr2)
+            assert np.allclose(dL.cpu().numpy(), L2, rtol=1e-15, atol=0, equal_nan=True)
+        with pytest.raises(pkg.TamcmcError):
+            ctx.pt_swap_device(Nch - 1, 0.5, dP.data_ptr(), dL.data_ptr())      # no chain A+1
