@@ -126,6 +126,13 @@ void tamcmc_gpu_destroy(tamcmc_gpu_ctx *ctx);
 int tamcmc_gpu_eval(tamcmc_gpu_ctx *ctx, const double *params, const unsigned char *active_mask,
                     double *logL_out, int *status_out);
 
+/* The same evaluation in two halves, for callers with host work that does not depend on the result (e.g. drawing the next
+ * proposal's random numbers while the GPU evaluates this one): _begin stages `params` / `active_mask` (the caller's buffers are
+ * free again on return) and launches; _end waits, fills logL_out / status_out and returns what tamcmc_gpu_eval returns.
+ * tamcmc_gpu_eval == _begin + _end.  One evaluation in flight per context: a second _begin before _end is TAMCMC_ERR_ARG. */
+int tamcmc_gpu_eval_begin(tamcmc_gpu_ctx *ctx, const double *params, const unsigned char *active_mask);
+int tamcmc_gpu_eval_end(tamcmc_gpu_ctx *ctx, double *logL_out, int *status_out);
+
 /* Same evaluation with DEVICE-resident inputs/outputs on the caller's CUDA stream (cudaStream_t
  * passed as void*; NULL = the context's own stream).  d_params has the layout of `params` above,
  * d_logL is [nstars][Nchains].  Asynchronous: the caller synchronises the stream.

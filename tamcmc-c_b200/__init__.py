@@ -30,7 +30,7 @@ CHAIN_WINDOW, CHAIN_NONFINITE, CHAIN_BADCFG, CHAIN_INACTIVE = 1, 2, 4, 8
 
 # every symbol include/tamcmc_gpu.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "tamcmc_gpu_create", "tamcmc_gpu_destroy", "tamcmc_gpu_eval", "tamcmc_gpu_eval_device", "tamcmc_gpu_pt_swap_device",
+    "tamcmc_gpu_create", "tamcmc_gpu_destroy", "tamcmc_gpu_eval", "tamcmc_gpu_eval_begin", "tamcmc_gpu_eval_end", "tamcmc_gpu_eval_device", "tamcmc_gpu_pt_swap_device",
     "tamcmc_gpu_sync", "tamcmc_gpu_model", "tamcmc_gpu_windows", "tamcmc_gpu_components",
     "tamcmc_gpu_params_stride", "tamcmc_gpu_nstars", "tamcmc_gpu_nchains", "tamcmc_gpu_pairs_last",
     "tamcmc_gpu_set_profiling", "tamcmc_gpu_get_kernel_ms", "tamcmc_gpu_launch_count",
@@ -82,6 +82,10 @@ def lib():
     L.tamcmc_gpu_destroy.argtypes = [vp]
     L.tamcmc_gpu_eval.restype = C.c_int
     L.tamcmc_gpu_eval.argtypes = [vp, _dp, _ucp, _dp, _ip]
+    L.tamcmc_gpu_eval_begin.restype = C.c_int
+    L.tamcmc_gpu_eval_begin.argtypes = [vp, _dp, _ucp]
+    L.tamcmc_gpu_eval_end.restype = C.c_int
+    L.tamcmc_gpu_eval_end.argtypes = [vp, _dp, _ip]
     L.tamcmc_gpu_pt_swap_device.restype = C.c_int
     L.tamcmc_gpu_pt_swap_device.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, vp, vp, vp, vp]
     L.tamcmc_gpu_eval_device.restype = C.c_int

@@ -121,6 +121,7 @@ struct tamcmc_gpu_ctx {
     int* d_asym = nullptr;
     double* d_Tcoefs = nullptr;
     double* d_partial = nullptr;
+    int pending = 0;                         // tamcmc_gpu_eval_begin issued, tamcmc_gpu_eval_end not yet: 1 zero-copy, 2 copy engine
     double* d_ksi = nullptr;                 // get_ksinorm slice sums (Kallinger2014 model), [SC][ksi_slices][3]
     int ksi_slices = 0, ksi_slice_bins = TAMCMC_KSI_SLICE, ksi_maxN = 0;
     void* d_out = nullptr;          // [SC] double logL then [SC] int status
@@ -287,7 +288,7 @@ int status_to_rc(const int* st, int n)
 // evaluate one parameter row as chain 0 of `star` (all other chains masked); used by the debug entries
 int expand_single(tamcmc_gpu_ctx* c, int star, const double* row)
 {
-    if (!c || !row || star < 0 || star >= c->nstars) return TAMCMC_ERR_ARG;
+    if (!c || !row || star < 0 || star >= c->nstars || c->pending) return TAMCMC_ERR_ARG;      // not re-entrant: one evaluation in flight
     const int SC = c->SC();
     std::memset(c->h_params, 0, sizeof(double) * (size_t)SC * c->params_stride);
     std::memset(c->h_active, 0, (size_t)SC);
@@ -553,20 +554,42 @@ int tamcmc_gpu_nstars(const tamcmc_gpu_ctx* c) { return c ? c->nstars : 0; }
 int tamcmc_gpu_nchains(const tamcmc_gpu_ctx* c) { return c ? c->Nchains : 0; }
 long tamcmc_gpu_launch_count(const tamcmc_gpu_ctx* c) { return c ? c->launches : 0; }
 
-int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char* active_mask,
-                    double* logL_out, int* status_out)
+int tamcmc_gpu_eval_begin(tamcmc_gpu_ctx* c, const double* params, const unsigned char* active_mask)
 {
-    if (!c || !params || !logL_out) return TAMCMC_ERR_ARG;
+    if (!c || !params || c->pending) return TAMCMC_ERR_ARG;
     CK(cudaSetDevice(c->device));
     const int SC = c->SC();
     const size_t pbytes = sizeof(double) * (size_t)SC * c->params_stride;
     std::memcpy(c->h_params, params, pbytes);
     if (active_mask) std::memcpy(c->h_active, active_mask, (size_t)SC);
-    const int* st = nullptr;
     if (c->zero_copy) {
         // ---- zero-copy: no DMA copies, no stream synchronisation.  The expander reads the rows over PCIe; the last CTA
         // of the fused kernel writes logL/status into the mapped mirror and publishes the launch's epoch in the flag ----
         { int rc = launch_eval(c, c->dh_params, active_mask ? c->dh_active : nullptr, c->d_logL(), 0, c->stream); if (rc) return rc; }
+        c->pending = 1;
+    } else {
+        CK(cudaMemcpyAsync(c->d_params, c->h_params, pbytes, cudaMemcpyHostToDevice, c->stream));
+        const unsigned char* d_act = nullptr;
+        if (active_mask) {
+            CK(cudaMemcpyAsync(c->d_active, c->h_active, (size_t)SC, cudaMemcpyHostToDevice, c->stream));
+            d_act = c->d_active;
+        }
+        { int rc = launch_eval(c, c->d_params, d_act, c->d_logL(), 0, c->stream); if (rc) return rc; }
+        CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
+        c->pending = 2;
+    }
+    return TAMCMC_OK;
+}
+
+int tamcmc_gpu_eval_end(tamcmc_gpu_ctx* c, double* logL_out, int* status_out)
+{
+    if (!c || !logL_out || !c->pending) return TAMCMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    const int SC = c->SC();
+    const int mode = c->pending;
+    c->pending = 0;
+    const int* st = nullptr;
+    if (mode == 1) {
         const unsigned int expected = c->epoch_host;
         volatile unsigned int* flag = c->hm_flag();
         unsigned long spins = 0;
@@ -586,14 +609,6 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char
         std::memcpy(logL_out, c->hm_logL(), sizeof(double) * (size_t)SC);
         st = c->hm_status();
     } else {
-        CK(cudaMemcpyAsync(c->d_params, c->h_params, pbytes, cudaMemcpyHostToDevice, c->stream));
-        const unsigned char* d_act = nullptr;
-        if (active_mask) {
-            CK(cudaMemcpyAsync(c->d_active, c->h_active, (size_t)SC, cudaMemcpyHostToDevice, c->stream));
-            d_act = c->d_active;
-        }
-        { int rc = launch_eval(c, c->d_params, d_act, c->d_logL(), 0, c->stream); if (rc) return rc; }
-        CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         { int rc = collect_profile(c); if (rc) return rc; }
         std::memcpy(logL_out, c->h_out, sizeof(double) * (size_t)SC);
@@ -604,10 +619,18 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char
     return status_to_rc(st, SC);
 }
 
+int tamcmc_gpu_eval(tamcmc_gpu_ctx* c, const double* params, const unsigned char* active_mask,
+                    double* logL_out, int* status_out)
+{
+    if (!c || !params || !logL_out) return TAMCMC_ERR_ARG;
+    { int rc = tamcmc_gpu_eval_begin(c, params, active_mask); if (rc) return rc; }
+    return tamcmc_gpu_eval_end(c, logL_out, status_out);
+}
+
 int tamcmc_gpu_eval_device(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active,
                            double* d_logL, int raw_sum, void* stream)
 {
-    if (!c || !d_params || !d_logL) return TAMCMC_ERR_ARG;
+    if (!c || !d_params || !d_logL || c->pending) return TAMCMC_ERR_ARG;
     CK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : c->stream;
     return launch_eval(c, d_params, d_active, d_logL, raw_sum, st);

@@ -15,8 +15,11 @@
 //   * propose-all -> one evaluation of all chains -> accept-all (chains are independent within a step);
 //   * one seeded std::mt19937_64 drives every draw on the calling thread (the reference seeds from time(NULL) and
 //     races on the shared generator inside its OpenMP loop, MALA.cpp:62,648);
-//   * priors are a user callback (priors_calc.cpp stays in the reference); -inf prior -> the chain is masked out
-//     exactly like model_def.cpp:469-480.
+//   * priors are a user callback (priors_calc.cpp stays in the reference; host/priors.hpp restates the generic ones);
+//     -inf prior -> the chain is masked out exactly like model_def.cpp:469-480;
+//   * the normal draws of step i+1 and their products with the proposal's Cholesky factors are prepared WHILE the GPU evaluates
+//     step i (they do not depend on its outcome; a factor that the learning update of step i changes is re-applied to the same
+//     draws), so outside the learning windows the host half of a step hides behind the evaluation.
 #pragma once
 #include <cmath>
 #include <cstddef>
@@ -44,6 +47,11 @@ struct DriverConfig {
 //            returns 0, or a status; NaN logL is data (MALA.cpp:490,522).
 using Evaluator = std::function<int(const double*, const unsigned char*, double*)>;
 using Prior = std::function<double(const double* params_row)>;      // log prior of one full parameter vector
+// the same evaluation in two halves (tamcmc_gpu_eval_begin / _end): the driver prepares the next proposal in between
+struct AsyncEvaluator {
+    std::function<int(const double*, const unsigned char*)> begin;
+    std::function<int(double*)> end;
+};
 
 class Driver {
 public:
@@ -108,10 +116,38 @@ public:
     void step(long i)
     {
         propose(i);
-        // ---- ONE batched evaluation (was: generate_model per chain inside the OpenMP loop) ----
-        eval(prop_params.data(), active.data(), prop_logL.data());
+        // ---- ONE batched evaluation (was: generate_model per chain inside the OpenMP loop); the draws of the next step are
+        // prepared while it runs (same order of random numbers with and without an asynchronous evaluator) ----
+        if (async.begin) {
+            async.begin(prop_params.data(), active.data());
+            prepare_next();
+            async.end(prop_logL.data());
+        } else {
+            eval(prop_params.data(), active.data(), prop_logL.data());
+            prepare_next();
+        }
         n_eval_calls++;
         finish(i);
+    }
+
+    void set_async_evaluator(AsyncEvaluator a) { async = std::move(a); }
+
+    // Between the two halves of an iteration: the N(0, I) draws of the NEXT proposal (serially, in chain order) and L z for
+    // every chain whose factor is current.  propose() re-applies a factor that finish() changes in between.
+    void prepare_next()
+    {
+        const int n = Nvars;
+        if (chol_all.empty()) { chol_all.assign((size_t)Nchains * n * n, 0.0); chol_dirty.assign((size_t)Nchains, 1); }
+        z_next.resize((size_t)Nchains * n);
+        lz_next.resize((size_t)Nchains * n);
+        lz_valid.assign((size_t)Nchains, 0);
+        for (size_t k = 0; k < z_next.size(); k++) z_next[k] = normal01();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) if (Nvars >= 32)
+#endif
+        for (int m = 0; m < Nchains; m++)
+            if (!chol_dirty[(size_t)m]) { apply_factor(m, &z_next[(size_t)m * n], &lz_next[(size_t)m * n]); lz_valid[(size_t)m] = 1; }
+        have_next = true;
     }
 
     // first half of an iteration: new positions and their priors for every chain
@@ -121,20 +157,23 @@ public:
         // ---- propose all chains (MALA.cpp:481-486).  Random numbers are drawn serially in chain order (deterministic
         // whatever the thread count); factorisations, matrix-vector products and priors then run one chain per thread ----
         const int n = Nvars;
-        if (chol_all.empty()) { chol_all.assign((size_t)Nchains * n * n, 0.0); chol_dirty.assign((size_t)Nchains, 1); }
-        z_all.resize((size_t)Nchains * n);
-        for (size_t k = 0; k < z_all.size(); k++) z_all[k] = normal01();
+        if (!have_next) prepare_next();                        // first iteration (or a caller that drives propose()/finish() itself)
+        z_all.swap(z_next); lz_all.swap(lz_next); lz_ok.swap(lz_valid);
+        have_next = false;
         nonfinite.assign((size_t)Nchains, 0);
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static, 1) if (Nvars >= 32)
 #endif
         for (int m = 0; m < Nchains; m++) {
-            nonfinite[(size_t)m] = new_prop_values(m, &z_all[(size_t)m * n]) ? 0 : 1;
+            // a factor that changed since the draws were prepared (learning update of the previous step) is applied now
+            if (!lz_ok[(size_t)m] || chol_dirty[(size_t)m]) apply_factor(m, &z_all[(size_t)m * n], &lz_all[(size_t)m * n]);
+            nonfinite[(size_t)m] = move_from(m, &lz_all[(size_t)m * n]) ? 0 : 1;
         }
         for (int m = 0; m < Nchains; m++)                       // MALA.cpp:356-366: redraw until finite (never seen in practice)
             for (int tries = 0; nonfinite[(size_t)m] && tries < 8; tries++) {
                 for (int a = 0; a < n; a++) z_all[(size_t)m * n + a] = normal01();
-                nonfinite[(size_t)m] = new_prop_values(m, &z_all[(size_t)m * n]) ? 0 : 1;
+                apply_factor(m, &z_all[(size_t)m * n], &lz_all[(size_t)m * n]);
+                nonfinite[(size_t)m] = move_from(m, &lz_all[(size_t)m * n]) ? 0 : 1;
             }
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static, 1) if (Nvars >= 32)
@@ -190,7 +229,10 @@ private:
     Prior prior;
     std::mt19937_64 rng;
     double gamma = 0.0;
-    std::vector<double> prop_params, prop_vars, prop_logL, prop_logPrior, chol_all, z_all;
+    std::vector<double> prop_params, prop_vars, prop_logL, prop_logPrior, chol_all, z_all, lz_all, z_next, lz_next;
+    std::vector<unsigned char> lz_ok, lz_valid;
+    bool have_next = false;
+    AsyncEvaluator async;
     std::vector<unsigned char> chol_dirty, nonfinite;
     std::vector<double> u_all;
     std::vector<unsigned char> active;
@@ -206,7 +248,8 @@ private:
     // MALA.cpp:339-369: ran = vars + chol((covarmat + epsilon2) * sigma) * N(0, I).  The reference factorises at every
     // call; chol((C + eps2) sigma) = sqrt(sigma) chol(C + eps2), so the factor of C + eps2 is cached per chain and only
     // recomputed after update_proposal changed C (with the GPU likelihood the factorisation would otherwise dominate a step).
-    bool new_prop_values(int m, const double* zm)
+    // apply_factor: out = L z (refreshing L first if C changed); move_from: prop_vars = vars + sqrt(sigma) (L z).
+    void apply_factor(int m, const double* zm, double* out)
     {
         const int n = Nvars;
         double* L = &chol_all[(size_t)m * n * n];
@@ -214,18 +257,35 @@ private:
             const double* C = &covarmat[(size_t)m * n * n];
             for (int a = 0; a < n; a++)
                 for (int b = 0; b <= a; b++) {
-                    double s = C[(size_t)a * n + b] + (a == b ? cfg.epsi2 : 0.0);
-                    for (int k = 0; k < b; k++) s -= L[(size_t)a * n + k] * L[(size_t)b * n + k];
+                    const double* La = &L[(size_t)a * n];
+                    const double* Lb = &L[(size_t)b * n];
+                    double dot = 0.0;                       // rows of L are contiguous: a vectorised dot product (fixed lane
+#ifdef _OPENMP                                              // order for a given build, so runs stay reproducible)
+#pragma omp simd reduction(+ : dot)
+#endif
+                    for (int k = 0; k < b; k++) dot += La[k] * Lb[k];
+                    const double s = C[(size_t)a * n + b] + (a == b ? cfg.epsi2 : 0.0) - dot;
                     L[(size_t)a * n + b] = (a == b) ? std::sqrt(s > 0 ? s : 0.0) : (L[(size_t)b * n + b] > 0 ? s / L[(size_t)b * n + b] : 0.0);
                 }
             chol_dirty[(size_t)m] = 0;
         }
+        for (int a = 0; a < n; a++) {
+            const double* La = &L[(size_t)a * n];
+            double s = 0.0;
+#ifdef _OPENMP
+#pragma omp simd reduction(+ : s)
+#endif
+            for (int k = 0; k <= a; k++) s += La[k] * zm[k];
+            out[a] = s;
+        }
+    }
+    bool move_from(int m, const double* lz)
+    {
+        const int n = Nvars;
         const double ssig = std::sqrt(sigma[m]);
         bool finite = true;
         for (int a = 0; a < n; a++) {
-            double s = 0.0;
-            for (int k = 0; k <= a; k++) s += L[(size_t)a * n + k] * zm[k];
-            s = vars[(size_t)m * n + a] + ssig * s;
+            const double s = vars[(size_t)m * n + a] + ssig * lz[a];
             prop_vars[(size_t)m * n + a] = s;
             finite = finite && std::isfinite(s);
         }
@@ -315,7 +375,14 @@ public:
             std::copy(stars[(size_t)s]->proposal_params(), stars[(size_t)s]->proposal_params() + (size_t)Nchains * stride, P.begin() + (size_t)s * Nchains * stride);
             std::copy(stars[(size_t)s]->active_mask(), stars[(size_t)s]->active_mask() + Nchains, act.begin() + (size_t)s * Nchains);
         }
-        eval(P.data(), act.data(), L.data());
+        if (async.begin) async.begin(P.data(), act.data());
+        else eval(P.data(), act.data(), L.data());
+        // the next step's draws of every star, while the batched evaluation runs (same order with a synchronous evaluator)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+        for (long s = 0; s < S; s++) stars[(size_t)s]->prepare_next();
+        if (async.begin) async.end(L.data());
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1)
 #endif
@@ -324,8 +391,10 @@ public:
             stars[(size_t)s]->finish(i);
         }
     }
+    void set_async_evaluator(AsyncEvaluator a) { async = std::move(a); }
 private:
     BatchEvaluator eval;
+    AsyncEvaluator async;
     int Nchains = 0, stride = 0;
     std::vector<double> P, L;
     std::vector<unsigned char> act;

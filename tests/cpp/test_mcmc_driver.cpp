@@ -25,7 +25,7 @@
 
 static std::vector<double> rd(FILE* f, size_t n) { std::vector<double> v(n); if (fread(v.data(), 8, n, f) != n) { std::puts("short read"); std::exit(2); } return v; }
 
-struct Summary { std::vector<double> mean, sd; double acc0; double swap; double secs; };
+struct Summary { std::vector<double> mean, sd; double acc0; double swap; double secs; double secs_sampling; };
 
 int main(int argc, char** argv)
 {
@@ -95,18 +95,27 @@ int main(int argc, char** argv)
         return r;
     };
 
-    auto run = [&](tamcmc::Evaluator ev) {
+    // the GPU evaluation in two halves: the driver prepares the next proposal's draws while the kernels run
+    tamcmc::AsyncEvaluator async_gpu;
+    async_gpu.begin = [&](const double* pr, const unsigned char* act) { return tamcmc_gpu_eval_begin(ctx, pr, act); };
+    async_gpu.end = [&](double* L) { return tamcmc_gpu_eval_end(ctx, L, nullptr); };
+
+    auto run = [&](tamcmc::Evaluator ev, bool use_async = false) {
         tamcmc::Driver d(cfg, Nparams, stride, params0, relax, err, ev, prior);
+        if (use_async) d.set_async_evaluator(async_gpu);
         const int nv = d.n_vars();
         std::vector<double> s1(nv, 0.0), s2(nv, 0.0);
         long cnt = 0;
         const auto t0 = std::chrono::steady_clock::now();
+        auto thalf = t0;
         for (long i = 0; i < nsteps; i++) {
+            if (i == nsteps / 2 + 1) thalf = std::chrono::steady_clock::now();        // the learning windows end at nsteps / 2
             d.step(i);
             if (i >= nsteps / 2) { for (int v = 0; v < nv; v++) { const double q = d.vars[v]; s1[v] += q; s2[v] += q * q; } cnt++; }
         }
         Summary S;
         S.secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        S.secs_sampling = std::chrono::duration<double>(std::chrono::steady_clock::now() - thalf).count();
         for (int v = 0; v < nv; v++) { const double m = s1[v] / cnt; S.mean.push_back(m); S.sd.push_back(std::sqrt(std::fmax(s2[v] / cnt - m * m, 0.0))); }
         S.acc0 = (double)d.n_accept[0] / nsteps;
         S.swap = d.n_swap_tried ? (double)d.n_swap_done / d.n_swap_tried : 0.0;
@@ -128,6 +137,12 @@ int main(int argc, char** argv)
             ds.emplace_back(new tamcmc::Driver(c, Nparams, stride, params0, relax, err, tamcmc::Evaluator(), prior, true));
         }
         tamcmc::BatchDriver bd(std::move(ds), [&](const double* pr, const unsigned char* act, double* L) { return tamcmc_gpu_eval(bctx, pr, act, L, nullptr); });
+        {
+            tamcmc::AsyncEvaluator ab;
+            ab.begin = [&](const double* pr, const unsigned char* act) { return tamcmc_gpu_eval_begin(bctx, pr, act); };
+            ab.end = [&](double* L) { return tamcmc_gpu_eval_end(bctx, L, nullptr); };
+            bd.set_async_evaluator(ab);
+        }
         const int nv = bd.stars[0]->n_vars();
         std::vector<double> s1(nv, 0.0);
         long cnt = 0;
@@ -147,15 +162,21 @@ int main(int argc, char** argv)
     }
     if (bench) {
         cfg.Nt_learn = {100, nsteps / 2, nsteps / 2 + 1};
-        const Summary G = run(ev_gpu);
+        const Summary G = run(ev_gpu, true);
         tamcmc_gpu_destroy(ctx);
-        std::printf("{\"mcmc_steps_per_s\": %.1f, \"evals_per_s\": %.0f, \"chains\": %d, \"bins\": %ld, \"relaxed_variables\": %zu, \"steps\": %ld, "
-                    "\"acceptance_chain0\": %.3f, \"swap_rate\": %.3f}\n",
-                    nsteps / G.secs, nsteps * (double)Nmodels / G.secs, Nmodels, N, relax.size(), nsteps, G.acc0, G.swap);
+        const long nsamp = nsteps - (nsteps / 2 + 1);
+        std::printf("{\"mcmc_steps_per_s\": %.1f, \"evals_per_s\": %.0f, \"mcmc_steps_per_s_sampling_phase\": %.1f, \"mcmc_steps_per_s_learning_phase\": %.1f, "
+                    "\"chains\": %d, \"bins\": %ld, \"relaxed_variables\": %zu, \"steps\": %ld, \"acceptance_chain0\": %.3f, \"swap_rate\": %.3f}\n",
+                    nsteps / G.secs, nsteps * (double)Nmodels / G.secs, nsamp / G.secs_sampling, (nsteps - nsamp) / (G.secs - G.secs_sampling),
+                    Nmodels, N, relax.size(), nsteps, G.acc0, G.swap);
         return 0;
     }
-    const Summary G = run(ev_gpu), C = run(ev_cpu);
+    const Summary G = run(ev_gpu), C = run(ev_cpu), GA = run(ev_gpu, true);
     tamcmc_gpu_destroy(ctx);
+    // the two-halves evaluation only moves host work under the kernels: same draws, same chain
+    for (size_t v = 0; v < G.mean.size(); v++)
+        if (G.mean[v] != GA.mean[v] || G.sd[v] != GA.sd[v]) { std::printf("asynchronous evaluation changed the chain (variable %zu)\n", v); return 1; }
+    std::printf("gpu (begin/end): %.1f steps/s, identical chain\n", nsteps / GA.secs);
     std::printf("gpu: %.1f steps/s (%.0f likelihood evals/s), acceptance(chain 0) %.3f, swap rate %.3f\n", nsteps / G.secs, nsteps * Nmodels / G.secs, G.acc0, G.swap);
     std::printf("cpu: %.1f steps/s, acceptance(chain 0) %.3f, swap rate %.3f\n", nsteps / C.secs, C.acc0, C.swap);
     int bad = 0;

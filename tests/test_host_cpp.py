@@ -37,7 +37,7 @@ def _build_driver():
     if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(abi)):
         return exe
     cuda_lib = "/usr/local/cuda/lib64"
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, src, "-L" + LIBDIR, "-ltamcmc_gpu", "-L" + odir, "-ltamcmc_oracle",
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-mavx2", "-Wall", "-o", exe, src, "-L" + LIBDIR, "-ltamcmc_gpu", "-L" + odir, "-ltamcmc_oracle",
                            "-L" + cuda_lib, "-lcudart", "-fopenmp", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath," + odir, "-Wl,-rpath," + cuda_lib])
     return exe
 
