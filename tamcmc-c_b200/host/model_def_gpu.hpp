@@ -113,6 +113,26 @@ public:
         return rc;
     }
 
+    // generate_models() in two halves (tamcmc_gpu_eval_begin / _end): the caller does host work that does not depend on the
+    // likelihoods in between (e.g. the random numbers of the next proposal).  Same results as generate_models().
+    void generate_models_begin()
+    {
+        const size_t n = (size_t)nstars * Nmodels;
+        for (size_t i = 0; i < n; i++) active[i] = (logPrior[i] != -std::numeric_limits<double>::infinity()) ? 1 : 0;
+        check(tamcmc_gpu_eval_begin(ctx, params.data(), active.data()), "tamcmc_gpu_eval_begin");
+    }
+    int generate_models_end()
+    {
+        const size_t n = (size_t)nstars * Nmodels;
+        const int rc = tamcmc_gpu_eval_end(ctx, logLikelihood.data(), status.data());
+        if (rc != TAMCMC_OK && rc != TAMCMC_ERR_WINDOW && rc != TAMCMC_ERR_NONFINITE) check(rc, "tamcmc_gpu_eval_end");
+        for (size_t i = 0; i < n; i++) {
+            if (active[i]) logPosterior[i] = logLikelihood[i] + logPrior[i];
+            else { logLikelihood[i] = init_logLikelihood[i]; logPosterior[i] = -std::numeric_limits<double>::infinity(); }
+        }
+        return rc;
+    }
+
     // call_model_explicit (model_def.cpp:209-218): the model spectrum of one parameter vector
     std::vector<double> call_model_explicit(const std::vector<double>& params0, int star = 0)
     {

@@ -72,6 +72,14 @@ int main(int argc, char** argv)
         const double post = md.logLikelihood[m] + logPrior[m];
         if (!(rel < 1e-10) || md.logPosterior[m] != post) { std::printf("chain %d: logL %.17g ref %.17g rel %.3e\n", m, md.logLikelihood[m], L_ref[m], rel); bad++; }
     }
+    {   // the two-halves call gives the same numbers; a second begin before end is refused
+        const std::vector<double> L1 = md.logLikelihood;
+        md.generate_models_begin();
+        bool refused = false;
+        try { md.generate_models_begin(); } catch (const tamcmc::tamcmc_error& e) { refused = (e.status == TAMCMC_ERR_ARG); }
+        const int rc2 = md.generate_models_end();
+        if (rc2 != TAMCMC_OK || !refused || md.logLikelihood != L1) { std::printf("begin/end: rc %d refused %d same %d\n", rc2, (int)refused, (int)(md.logLikelihood == L1)); bad++; }
+    }
     const std::vector<double> M = md.call_model_explicit(std::vector<double>(P.begin(), P.begin() + Nparams));
     double worst = 0;
     for (long i = 0; i < N; i++) worst = std::fmax(worst, std::fabs(M[i] - M_ref[i]) / std::fabs(M_ref[i]));
