@@ -144,7 +144,8 @@ struct tamcmc_gpu_ctx {
     GraphEntry graphs[4] = {};
     int ngraphs = 0;
     int stagger_ns = 0;               // TAMCMC_GPU_STAGGER_NS (tuning aid)
-    int look = 2, look_end = 1;       // producer look-ahead (TAMCMC_GPU_LOOK / TAMCMC_GPU_LOOK_END = 1 or 2; tuning aid)
+    int look = 3, look_end = 3;       // producer look-ahead in tiles (TAMCMC_GPU_LOOK / TAMCMC_GPU_LOOK_END = 1 .. producers - 1; tuning aid)
+    double far_ratio = TAMCMC_FAR_RATIO_DEFAULT;   // far-field folding (TAMCMC_GPU_FAR_RATIO; 0 = off)
     bool use_graphs = true;
     bool use_pdl = false;            // programmatic dependent launch expand -> fused kernel: measured no gain inside a CUDA graph
                                      // (profiles/r1/NOTES.md); TAMCMC_GPU_PDL=1 enables it
@@ -179,6 +180,7 @@ ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const uns
     a.Nchains = c->Nchains; a.params_stride = c->params_stride; a.modes_stride = c->modes_stride;
     a.tiles_stride = c->tiles_stride; a.max_tiles = c->max_tiles; a.trace = c->d_trace ? c->d_trace + 64 * 2048 : nullptr;
     a.ksi_part = c->d_ksi; a.ksi_slices = c->ksi_slices; a.ksi_slice_bins = c->ksi_slice_bins;
+    a.far_ratio = c->far_ratio;
     return a;
 }
 
@@ -195,7 +197,7 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, boo
     a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
     a.raw_sum = raw_sum; a.trace = c->d_trace;
     a.epoch = c->d_epoch;
-    a.look = c->look; a.look_end = c->look_end; a.stagger_ns = c->stagger_ns;
+    a.look = c->look; a.look_end = c->look_end; a.stagger_ns = c->stagger_ns; a.far_ratio = c->far_ratio;
     a.status = c->d_status(); a.nsc = c->SC();
     // the host mirror costs a system-scope fence at the end of the launch: only the host-buffer entry point asks for it
     a.host_logL = mirror ? c->dm_logL : nullptr; a.host_status = mirror ? c->dm_status : nullptr;
@@ -347,8 +349,9 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     if (const char* e = std::getenv("TAMCMC_GPU_NO_GRAPH")) c->use_graphs = !(e[0] == '1');
     if (const char* e = std::getenv("TAMCMC_GPU_PDL")) c->use_pdl = (e[0] == '1');
     if (const char* e = std::getenv("TAMCMC_GPU_STAGGER_NS")) c->stagger_ns = std::atoi(e);
-    if (const char* e = std::getenv("TAMCMC_GPU_LOOK")) c->look = (e[0] == '1') ? 1 : 2;
-    if (const char* e = std::getenv("TAMCMC_GPU_LOOK_END")) c->look_end = (e[0] == '1') ? 1 : 2;
+    if (const char* e = std::getenv("TAMCMC_GPU_LOOK")) { const int v = std::atoi(e); if (v >= 1 && v < TAMCMC_PRODUCERS) c->look = v; }
+    if (const char* e = std::getenv("TAMCMC_GPU_LOOK_END")) { const int v = std::atoi(e); if (v >= 1 && v < TAMCMC_PRODUCERS) c->look_end = v; }
+    if (const char* e = std::getenv("TAMCMC_GPU_FAR_RATIO")) { const double v = std::atof(e); c->far_ratio = (v >= 4.0 && v <= 1e6) ? v : 0.0; }
     c->h_stars.resize(nstars);
     {
         // tile size: full-size tiles unless they would give fewer than ~2 work items per SM (spectra of a few thousand

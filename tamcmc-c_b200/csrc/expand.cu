@@ -834,6 +834,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             // unused slot of a mode table (or a rejected record): an empty record, so stale data is never listed
             ModeRec mr;
             mr.i0 = 0; mr.i1 = 0; mr.ncomp = 0; mr.nfast = 0; mr.l = 0; mr.pad = 0;
+            mr.numin = 1.0; mr.numax = 0.0;
             mr.fc = 0; mr.gamma = 0; mr.qa = 0; mr.qb0 = 1; mr.qc = 0;
             modes[base + tid] = mr;
         }
@@ -854,6 +855,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
             const double sg = 2.0 / t.W;
             CompRec* out = comps + (size_t)j * TAMCMC_MAX_COMP_PER_MODE;
             int nf = 0, ns = 0, wide = 0;
+            double numin = 1e300, numax = -1e300;        // extent of the FAST components' centres (far-field test of the fused kernel)
             // FAST/WIDE components first, then the SLOW ones (classes from pass B)
             for (int pass = 0; pass < 2; pass++)
                 for (int k = 0; k <= 2 * l; k++) {
@@ -865,18 +867,37 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                     if (fast != (pass == 0)) continue;
                     CompRec cr;
                     cr.nu = slot_nu[sl]; cr.m = k - l;
-                    if (fast) { cr.flags = TAMCMC_CF_FAST; cr.s = slot_s[sl]; cr.a = slot_ia[sl]; nf++; wide |= (cls == SLOT_WIDE); }
+                    if (fast) {
+                        cr.flags = TAMCMC_CF_FAST; cr.s = slot_s[sl]; cr.a = slot_ia[sl]; nf++; wide |= (cls == SLOT_WIDE);
+                        numin = fmin(numin, cr.nu); numax = fmax(numax, cr.nu);
+                    }
                     else { cr.flags = TAMCMC_CF_SLOW; cr.s = sg; cr.a = slot_A[sl]; ns++; }
                     out[nf + ns - 1] = cr;
                 }
             mr.nfast = nf | (wide << 16); mr.ncomp = nf + ns;      // bit 16: the mode has WIDE fast components
+            // numin > numax: the mode is never folded into a tile's far-field polynomial (no FAST components, WIDE dynamic
+            // range, or an asymmetric profile)
+            const bool far_capable = nf > 0 && !wide && cm.asym == 0.0;
+            mr.numin = far_capable ? numin : 1.0; mr.numax = far_capable ? numax : 0.0;
             modes[j] = mr;
             // per-tile cost: difference array over the LOCAL tiles this window touches
             if (!bad && mr.ncomp > 0) {
                 const int lo = max(i0, sd.bin0) - sd.bin0, hi = min(i1, sd.bin0 + sd.Nloc) - sd.bin0;
                 if (hi > lo) {
-                    atomicAdd(&tcost[lo / sd.tile_bins], mr.ncomp);
-                    atomicAdd(&tcost[(hi - 1) / sd.tile_bins + 1], -mr.ncomp);
+                    int t0 = lo / sd.tile_bins, t1 = (hi - 1) / sd.tile_bins + 1;
+                    if (far_capable && A.far_ratio > 0.0 && ns == 0) {
+                        // the fused kernel merges this mode per bin only in the tiles whose centre lies within far_ratio half
+                        // tiles of its components; elsewhere it costs nothing per bin (a scheduling weight, not a result)
+                        const double T = (double)sd.tile_bins, Rb = A.far_ratio * 0.5 * T + 0.5 * T;
+                        const double bmin = (numin - sd.x0) / sd.step - (double)sd.bin0, bmax = (numax - sd.x0) / sd.step - (double)sd.bin0;
+                        const double tl = floor((bmin - Rb) / T), th = ceil((bmax + Rb) / T) + 1.0;
+                        if (tl > (double)t0) t0 = (int)fmin(tl, (double)t1);
+                        if (th < (double)t1) t1 = (int)fmax(th, (double)t0);
+                    }
+                    if (t1 > t0) {
+                        atomicAdd(&tcost[t0], mr.ncomp);
+                        atomicAdd(&tcost[t1], -mr.ncomp);
+                    }
                 }
             }
         }

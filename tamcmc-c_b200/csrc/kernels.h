@@ -28,6 +28,7 @@ struct ExpandArgs {
     double* ksi_part;                // [nstars*Nchains][ksi_slices][3] partial sums of get_ksinorm (Kallinger2014 model only), or nullptr
     int ksi_slices;
     int ksi_slice_bins;              // bins per pre-pass CTA: the smallest power-of-two multiple of TAMCMC_KSI_SLICE that fits the grid in one wave
+    double far_ratio;                // far-field folding of the fused kernel (0 = off): only used to weigh the tiles of the work queue
 };
 
 struct WhittleArgs {
@@ -64,6 +65,8 @@ struct WhittleArgs {
     int look, look_end;              // producer look-ahead in tiles (1 or 2): steady state / last ~4 items per CTA
     int likelihood;                  // 0: chi(2,2p)  S = sum(ln M + y/M);  1: chi_square  S = sum((y-M)^2/sigma^2)
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)
+    double far_ratio;                // > 0: modes whose components all lie >= far_ratio * umax from a tile's centre are folded into
+                                     // the tile's polynomial instead of being merged per bin (whittle.cu); 0 = every component per bin
 };
 
 cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const double* Q);

@@ -15,6 +15,10 @@
 #define TAMCMC_MAX_COMP_PER_MODE 7   // l <= 3 -> 2l+1 <= 7 (reference: acoefs.cpp supports l<=3)
 #define TAMCMC_MAX_HARVEY 8
 #define TAMCMC_BG_TERMS 10           // Taylor coefficients of the Harvey background per tile
+#ifndef TAMCMC_FAR_TERMS
+#define TAMCMC_FAR_TERMS 16          // coefficients of the per-tile polynomial once FAR Lorentzians are folded into it (whittle.cu)
+#endif
+#define TAMCMC_FAR_RATIO_DEFAULT 8.0 // a mode is FAR from a tile when every component centre is >= ratio * (tile half-width) away from the tile centre
 #ifndef TAMCMC_TILE
 #define TAMCMC_TILE 1536             // bins per tile
 #endif
@@ -61,6 +65,8 @@ struct __align__(16) ModeRec {
     int ncomp;           // number of live components (height != 0); FAST ones are stored first
     int nfast;           // bits 0-15: leading components in the scaled FAST form; bit 16: some of them are WIDE-range
                          // (the segments that list this mode renormalise every 4 merges instead of every 16)
+    // next 16 bytes: what the far-field test of a tile needs (second 128-bit load, issued with the first)
+    double numin, numax; // smallest / largest nu_nlm of the FAST components (+inf / -inf ... see expand.cu: never FAR when numin > numax)
     int l;               // degree
     int pad;
     double fc;           // central frequency fc_l

@@ -37,6 +37,8 @@ constexpr int TILE_MAX = TAMCMC_TILE;                      // the kernel is inst
 constexpr int GROUP = 16;                                  // fast components merged between two renormalisations
 constexpr int GROUP_WIDE = 4;                              // ... in segments that hold WIDE-range components
 constexpr int NB = TAMCMC_BG_TERMS;
+constexpr int NFAR = TAMCMC_FAR_TERMS;                     // terms of the tile polynomial when far Lorentzians are folded into it
+static_assert(NFAR >= NB && NFAR <= 32, "one producer lane per coefficient");
 constexpr int CAPF = TAMCMC_CAPF;                          // fast entries per segment
 constexpr int CAPG = TAMCMC_CAPG;                          // general entries per segment
 constexpr int CAPH = TAMCMC_CAPH;                          // mode headers per segment (asym fast path)
@@ -48,7 +50,7 @@ constexpr int EMPTY_COUNT = NC / 32;                       // one arrival per co
 constexpr int EMPTY_COUNT = NC;                            // every consumer thread arrives on the slot's `empty` barrier
 #endif
 
-enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_GAUSS = 32, SEG_WIDE = 64 };
+enum { SEG_FIRST = 1, SEG_LAST = 2, SEG_DONE = 4, SEG_BGSERIES = 8, SEG_ASYM = 16, SEG_GAUSS = 32, SEG_WIDE = 64, SEG_FAR = 128 };
 
 template <int TILE>
 struct __align__(16) Segment {
@@ -57,7 +59,7 @@ struct __align__(16) Segment {
     FastEntry fast[CAPF];    // ... and the tile's component lists, written by the slot's producer warp
     ModeHdr hdr[CAPH];
     GenEntry gen[CAPG];
-    double bg[NB];           // background Taylor coefficients in u
+    double bg[NFAR];         // tile polynomial in u = x - xc: Harvey background series (NB terms) + far Lorentzians (NFAR terms)
     double xc, N0;
     int nfast, ngen, nhdr, flags;
     int sc_index, tile, nvalid, lb0;
@@ -72,9 +74,13 @@ struct Smem {
     double red_s[NBUF][NC];
     double red_m[NBUF][NC];
     int red_e[NBUF][NC];
+    double far_acc[NBUF][NFAR][33];   // per-lane partial sums of the far-field coefficients of the tile a producer is listing
+    int far_list[NBUF][32 * TAMCMC_MAX_COMP_PER_MODE];   // far components of the mode batch being listed (indices into the chain's CompRec table)
     volatile int cons_cur;            // slot the consumers are working on (-1 before the first tile)
     unsigned int done_mask;           // producers that have drained the queue
 };
+
+static_assert(sizeof(Smem<TILE_MAX>) <= 232448, "the ring must fit the 227 KB of shared memory a CTA can opt into");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
@@ -226,6 +232,27 @@ __device__ __forceinline__ void tile_reduce(const WhittleArgs& A, Smem<TILE>& sm
     __syncwarp();
 }
 
+// Taylor coefficients in u of one far component 1 / ((s u + c)^2 + a), added to this lane's partial sums (stride 33 doubles):
+// f_0 = h, f_1 = p h, f_{k+1} = p f_k - q f_{k-1} with h = 1/(c^2 + a), p = -2 s c h, q = s^2 h (see producer_loop).
+__device__ __forceinline__ void far_series(double* facc, double s, double c, double a)
+{
+    const double w2 = fma(c, c, a);
+    double h;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(h) : "d"(w2));
+    h = fma(fma(-w2, h, 1.0), h, h);
+    h = fma(fma(-w2, h, 1.0), h, h);          // two Newton steps: relative error ~1e-16
+    const double sh = s * h;
+    const double p = -2.0 * c * sh, q = s * sh;
+    double f0 = h, f1 = p * h;
+    facc[0] += f0; facc[33] += f1;
+#pragma unroll
+    for (int t = 2; t < NFAR; t++) {
+        const double f2 = fma(p, f1, -(q * f0));
+        facc[33 * t] += f2;
+        f0 = f1; f1 = f2;
+    }
+}
+
 template <int TILE>
 __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int lane)
 {
@@ -264,8 +291,9 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
             for (;;) {
                 const int cur = sm.cons_cur;
                 const unsigned dm = *reinterpret_cast<volatile unsigned int*>(&sm.done_mask);
-                const int n1 = next_live(cur, dm);
-                if (n1 == w || (look > 1 && next_live(n1, dm) == w)) break;
+                int n = next_live(cur, dm), hops = 1;
+                while (n != w && hops < look) { n = next_live(n, dm); hops++; }
+                if (n == w) break;
                 __nanosleep(256);
             }
             idx = nstatic + pop_item(A, lane);
@@ -288,7 +316,8 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         const int Nloc = sd->Nloc, bin0 = sd->bin0, nmodes = sd->nmodes_cap;
         const double xc = tr->xc;
         const int series_ok = tr->series_ok;
-        const double bgk = (lane < NB) ? tr->bg[lane] : 0.0;
+        const double umax = tr->umax;
+        const double bgk = (lane < NB && series_ok) ? tr->bg[lane] : 0.0;
         const bool asym = A.asym_flag[sc] != 0;
         const double N0 = A.noise[sc].N0;
         const int gauss = A.noise[sc].gauss ? SEG_GAUSS : 0;      // Gaussian-envelope models (ids 0, 1)
@@ -299,6 +328,23 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         const ModeRec* modes = A.modes + (size_t)sc * A.modes_stride;
         const CompRec* comps = A.comps + (size_t)sc * A.modes_stride * TAMCMC_MAX_COMP_PER_MODE;
 
+        // Far field.  A symmetric Lorentzian in the scaled FAST form, 1 / ((s u + c)^2 + a), is analytic in u with poles at
+        // distance |w|/s, w = c - i sqrt(a), from the tile centre.  When every component of a mode lies >= far_ratio * umax
+        // from the centre (and the window covers the tile), its Taylor series in u converges like far_ratio^-k on the tile:
+        //     f_k = (-s/|w|)^k U_k(c/|w|) / |w|^2        (U_k: Chebyshev polynomials of the second kind),
+        // i.e. f_0 = h, f_1 = p h, f_{k+1} = p f_k - q f_{k-1} with h = 1/(c^2 + a), p = -2 s c h, q = s^2 h.  Truncated
+        // after NFAR terms the relative error of the component is <= (NFAR+1) ratio^-NFAR ((1+1/ratio)/(1-1/ratio))^2
+        // (1e-13 for 16 terms at ratio 8).  Such a mode costs NFAR producer-side steps per component instead of 4 FP64
+        // instructions per component AND BIN; its coefficients join the background polynomial of the tile.
+        // (a partial last tile qualifies too: its padding repeats the last x, so umax bounds |u| of every bin)
+        const bool far_on = A.far_ratio > 0.0 && !asym;
+        const double farR = A.far_ratio * umax;
+        double* const facc = &sm.far_acc[w][0][lane];
+        if (far_on) {
+#pragma unroll
+            for (int k = 0; k < NFAR; k++) facc[33 * k] = 0.0;
+        }
+        int any_far = 0;
         bool first = true;
         int cf = 0, cg = 0, ch = 0, seg_wide = 0;
         // ---- open the first segment: the slot must have been released; x and y start streaming in ----
@@ -311,19 +357,44 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         // mode headers are fetched one batch ahead: the header round trip of batch k+1 overlaps the component-record round
         // trip of batch k (a tile-list build is a chain of dependent loads, and the first one is every CTA's start-up)
         int4 hnext = make_int4(0, 0, 0, 0);
-        if (lane < nmodes) hnext = *reinterpret_cast<const int4*>(modes + lane);     // {i0, i1, ncomp, nfast | wide << 16}
+        double2 fnext = make_double2(1.0, 0.0);
+        if (lane < nmodes) {
+            hnext = *reinterpret_cast<const int4*>(modes + lane);     // {i0, i1, ncomp, nfast | wide << 16}
+            if (far_on) fnext = *reinterpret_cast<const double2*>(&modes[lane].numin);
+        }
         for (int base = 0; base < nmodes; base += 32) {
             const int mi = base + lane;
-            int ncomp = 0, nfast = 0, ngen = 0, i0 = 0, i1 = 0, nfast_rec = 0, mwide = 0, wbit = 0;
+            int ncomp = 0, nfast = 0, ngen = 0, i0 = 0, i1 = 0, nfast_rec = 0, mwide = 0, wbit = 0, nfar = 0;
             const int4 h = hnext;
-            if (mi + 32 < nmodes) hnext = *reinterpret_cast<const int4*>(modes + mi + 32);
+            const double2 fz = fnext;
+            if (mi + 32 < nmodes) {
+                hnext = *reinterpret_cast<const int4*>(modes + mi + 32);
+                if (far_on) fnext = *reinterpret_cast<const double2*>(&modes[mi + 32].numin);
+            }
             if (mi < nmodes) {
                 if (h.z > 0 && h.x < gend && h.y > g0) {
                     ncomp = h.z; nfast_rec = h.w & 0xffff; i0 = h.x; i1 = h.y;
                     nfast = (h.x <= g0 && h.y >= gend) ? nfast_rec : 0;
                     ngen = ncomp - nfast;
                     wbit = (h.w >> 16) & 1;
+                    if (far_on && nfast > 0 && fz.x <= fz.y && ((fz.x - xc) >= farR || (xc - fz.y) >= farR)) { nfar = nfast; nfast = 0; }
                     mwide = (nfast > 0) ? wbit : 0;
+                }
+            }
+            // far components of this batch: spread evenly over the lanes (a mode's 2l+1 components would otherwise run
+            // serially on its lane); their records are fetched now and turned into series after the entries below
+            const int tfar = far_on ? warp_sum(nfar) : 0;
+            constexpr int FR = 1;       // far records fetched ahead per lane (2 spills at the 128-register cap)
+            double fr_nu[FR], fr_s[FR], fr_a[FR];
+            if (tfar) {
+                any_far = 1;
+                const int ofar = warp_excl_scan(nfar, lane);
+                for (int k = 0; k < nfar; k++) sm.far_list[w][ofar + k] = mi * TAMCMC_MAX_COMP_PER_MODE + k;
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < FR; r++) {
+                    const int e = lane + 32 * r;
+                    if (e < tfar) { const CompRec* c = comps + sm.far_list[w][e]; fr_nu[r] = c->nu; fr_s[r] = c->s; fr_a[r] = c->a; }
                 }
             }
             if (!__any_sync(0xffffffffu, ncomp > 0)) continue;
@@ -362,14 +433,15 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                     if (asym || ngen > 0) { const ModeRec* mr = modes + mi; qa = mr->qa; qb = mr->qb0 + xc * qa; qc = mr->qc; }
                     if (hh) { ModeHdr m; m.qa = qa; m.qb = qb; m.qc = qc; m.begin = of; m.count = nfast; sg->hdr[oh] = m; }
 #pragma unroll
+                    const int nlead = nfast + nfar;          // leading components that are not general entries in this tile
                     for (int k0 = 0; k0 < 8; k0 += 4) {
                         double cnu[4], cs[4], ca[4];
 #pragma unroll
-                        for (int kk = 0; kk < 4; kk++) { const int k = k0 + kk; if (k < ncomp) { cnu[kk] = cp[k].nu; cs[kk] = cp[k].s; ca[kk] = cp[k].a; } }
+                        for (int kk = 0; kk < 4; kk++) { const int k = k0 + kk; if (k >= nfar && k < ncomp) { cnu[kk] = cp[k].nu; cs[kk] = cp[k].s; ca[kk] = cp[k].a; } }
 #pragma unroll
                         for (int kk = 0; kk < 4; kk++) {
                             const int k = k0 + kk;
-                            if (k < ncomp) {
+                            if (k >= nfar && k < ncomp) {
                                 const double cc = -(cnu[kk] - xc) * cs[kk];
                                 if (k < nfast) { FastEntry fe; fe.s = cs[kk]; fe.c = cc; fe.a = ca[kk]; fe.pad = 0.0; sg->fast[of + k] = fe; }
                                 else {
@@ -381,7 +453,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                                     // renormalisation after every merge (general form, or a WIDE-range mode)
                                     ge.qa = qa; ge.qb = qb; ge.qc = qc; ge.lo = max(i0 - g0, 0);
                                     ge.hi = min(i1 - g0, TILE) | ((!ff || wbit) ? (1 << 30) : 0);
-                                    sg->gen[og + (k - nfast)] = ge;
+                                    sg->gen[og + (k - nlead)] = ge;
                                 }
                             }
                         }
@@ -390,14 +462,40 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                 cf += tf; cg += tg; ch += th;
                 sub_lo = sub_hi;
             }
+            if (tfar) {
+#pragma unroll
+                for (int r = 0; r < FR; r++)
+                    if (lane + 32 * r < tfar) far_series(facc, fr_s[r], -(fr_nu[r] - xc) * fr_s[r], fr_a[r]);
+                for (int e = lane + 32 * FR; e < tfar; e += 32) {
+                    const CompRec* c = comps + sm.far_list[w][e];
+                    const double cs_ = c->s;
+                    far_series(facc, cs_, -(c->nu - xc) * cs_, c->a);
+                }
+                __syncwarp();          // the list is rewritten by the next batch
+            }
         }
         // ---- last segment of the tile (possibly empty: a tile no mode touches still has its background and Whittle terms)
         if (lane == 0) {
             sg->nfast = cf; sg->ngen = cg; sg->nhdr = ch;
-            sg->flags = (first ? SEG_FIRST : 0) | SEG_LAST | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (seg_wide ? SEG_WIDE : 0) | gauss;
+            sg->flags = (first ? SEG_FIRST : 0) | SEG_LAST | (asym ? SEG_ASYM : 0) | (series_ok ? SEG_BGSERIES : 0) | (seg_wide ? SEG_WIDE : 0) | gauss
+                      | (any_far ? SEG_FAR : 0);
             sg->sc_index = sc; sg->tile = tile; sg->nvalid = nvalid; sg->lb0 = lb0; sg->off = off; sg->xc = xc; sg->N0 = N0;
         }
-        if (lane < NB) sg->bg[lane] = bgk;
+        {
+            // coefficient k of the tile polynomial: background series + the 32 per-lane far-field sums, in lane order (fixed shape)
+            double ck = bgk;
+            if (any_far) {
+                __syncwarp();
+                if (lane < NFAR) {
+                    const double* row = &sm.far_acc[w][lane][0];
+                    double fs = 0.0;
+#pragma unroll 8
+                    for (int j = 0; j < 32; j++) fs += row[j];
+                    ck += fs;
+                }
+            }
+            if (lane < NFAR) sg->bg[lane] = ck;
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(full);             // 2 arrivals per phase: the opening one (with the TMA byte count) and this
         use++;
@@ -631,7 +729,20 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
             const double N0 = sg.N0;
             const NoiseRec* nz = A.noise + sc;
             double bgv[BPT];
-            if (flags & SEG_BGSERIES) {
+            if (flags & SEG_FAR) {
+                // background series + far Lorentzians: NFAR terms
+                double acc[BPT];
+#pragma unroll
+                for (int j = 0; j < BPT; j++) acc[j] = sg.bg[NFAR - 1];
+#pragma unroll
+                for (int k = NFAR - 2; k >= 0; k--) {
+                    const double ck = sg.bg[k];
+#pragma unroll
+                    for (int j = 0; j < BPT; j++) acc[j] = fma(acc[j], u[j], ck);
+                }
+#pragma unroll
+                for (int j = 0; j < BPT; j++) bgv[j] = acc[j] + N0;
+            } else if (flags & SEG_BGSERIES) {
                 double cf[NB];
 #pragma unroll
                 for (int k = 0; k < NB; k++) cf[k] = sg.bg[k];
@@ -644,6 +755,10 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
                     bgv[j] = acc + N0;
                 }
             } else {
+#pragma unroll
+                for (int j = 0; j < BPT; j++) bgv[j] = N0;
+            }
+            if (!(flags & SEG_BGSERIES)) {
                 // near x = 0 / near a singularity of a term: evaluate every bin exactly and merge the terms into
                 // the same fraction: (1e-3 tau x)^p = exp(p (ln(1e-3 tau) + ln x)); the clamp keeps D finite
                 const double* lx = A.lnx + sg.off;
@@ -673,8 +788,6 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
                         D[j] *= t;
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < BPT; j++) bgv[j] = N0;
             }
 
             if (flags & SEG_GAUSS) {
