@@ -875,9 +875,8 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                     out[nf + ns - 1] = cr;
                 }
             mr.nfast = nf | (wide << 16); mr.ncomp = nf + ns;      // bit 16: the mode has WIDE fast components
-            // numin > numax: the mode is never folded into a tile's far-field polynomial (no FAST components, WIDE dynamic
-            // range, or an asymmetric profile)
-            const bool far_capable = nf > 0 && !wide && cm.asym == 0.0;
+            // numin > numax: the mode is never folded into a tile's far-field polynomial (no FAST components or WIDE dynamic range)
+            const bool far_capable = nf > 0 && !wide;
             mr.numin = far_capable ? numin : 1.0; mr.numax = far_capable ? numax : 0.0;
             modes[j] = mr;
             // per-tile cost: difference array over the LOCAL tiles this window touches

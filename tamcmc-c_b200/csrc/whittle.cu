@@ -76,6 +76,7 @@ struct Smem {
     int red_e[NBUF][NC];
     double far_acc[NBUF][NFAR][33];   // per-lane partial sums of the far-field coefficients of the tile a producer is listing
     int far_list[NBUF][32 * TAMCMC_MAX_COMP_PER_MODE];   // far components of the mode batch being listed (indices into the chain's CompRec table)
+    double far_q[NBUF][32][3];        // asymmetric profiles: q(u) = Q0 + Q1 u + Q2 u^2 of the batch's far modes (one per lane)
     volatile int cons_cur;            // slot the consumers are working on (-1 before the first tile)
     unsigned int done_mask;           // producers that have drained the queue
 };
@@ -234,7 +235,8 @@ __device__ __forceinline__ void tile_reduce(const WhittleArgs& A, Smem<TILE>& sm
 
 // Taylor coefficients in u of one far component 1 / ((s u + c)^2 + a), added to this lane's partial sums (stride 33 doubles):
 // f_0 = h, f_1 = p h, f_{k+1} = p f_k - q f_{k-1} with h = 1/(c^2 + a), p = -2 s c h, q = s^2 h (see producer_loop).
-__device__ __forceinline__ void far_series(double* facc, double s, double c, double a)
+template <bool ASYM>
+__device__ __forceinline__ void far_series(double* facc, double s, double c, double a, double Q0 = 1.0, double Q1 = 0.0, double Q2 = 0.0)
 {
     const double w2 = fma(c, c, a);
     double h;
@@ -244,11 +246,15 @@ __device__ __forceinline__ void far_series(double* facc, double s, double c, dou
     const double sh = s * h;
     const double p = -2.0 * c * sh, q = s * sh;
     double f0 = h, f1 = p * h;
-    facc[0] += f0; facc[33] += f1;
+    if (ASYM) {
+        // times the asymmetry factor of the mode (build_lorentzian.cpp:153-157), a quadratic in u: the Cauchy product, truncated alike
+        facc[0] += Q0 * f0; facc[33] += fma(Q0, f1, Q1 * f0);
+    } else { facc[0] += f0; facc[33] += f1; }
 #pragma unroll
     for (int t = 2; t < NFAR; t++) {
         const double f2 = fma(p, f1, -(q * f0));
-        facc[33 * t] += f2;
+        if (ASYM) facc[33 * t] += fma(Q0, f2, fma(Q1, f1, Q2 * f0));
+        else facc[33 * t] += f2;
         f0 = f1; f1 = f2;
     }
 }
@@ -337,7 +343,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         // (1e-13 for 16 terms at ratio 8).  Such a mode costs NFAR producer-side steps per component instead of 4 FP64
         // instructions per component AND BIN; its coefficients join the background polynomial of the tile.
         // (a partial last tile qualifies too: its padding repeats the last x, so umax bounds |u| of every bin)
-        const bool far_on = A.far_ratio > 0.0 && !asym;
+        const bool far_on = A.far_ratio > 0.0;
         const double farR = A.far_ratio * umax;
         double* const facc = &sm.far_acc[w][0][lane];
         if (far_on) {
@@ -390,6 +396,11 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                 any_far = 1;
                 const int ofar = warp_excl_scan(nfar, lane);
                 for (int k = 0; k < nfar; k++) sm.far_list[w][ofar + k] = mi * TAMCMC_MAX_COMP_PER_MODE + k;
+                if (asym && nfar > 0) {
+                    const ModeRec* mr = modes + mi;
+                    const double qa = mr->qa, qb = mr->qb0 + xc * qa;
+                    sm.far_q[w][lane][0] = fma(qb, qb, mr->qc); sm.far_q[w][lane][1] = 2.0 * qa * qb; sm.far_q[w][lane][2] = qa * qa;
+                }
                 __syncwarp();
 #pragma unroll
                 for (int r = 0; r < FR; r++) {
@@ -463,13 +474,25 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                 sub_lo = sub_hi;
             }
             if (tfar) {
+                if (!asym) {
 #pragma unroll
-                for (int r = 0; r < FR; r++)
-                    if (lane + 32 * r < tfar) far_series(facc, fr_s[r], -(fr_nu[r] - xc) * fr_s[r], fr_a[r]);
-                for (int e = lane + 32 * FR; e < tfar; e += 32) {
-                    const CompRec* c = comps + sm.far_list[w][e];
-                    const double cs_ = c->s;
-                    far_series(facc, cs_, -(c->nu - xc) * cs_, c->a);
+                    for (int r = 0; r < FR; r++)
+                        if (lane + 32 * r < tfar) far_series<false>(facc, fr_s[r], -(fr_nu[r] - xc) * fr_s[r], fr_a[r]);
+                    for (int e = lane + 32 * FR; e < tfar; e += 32) {
+                        const CompRec* c = comps + sm.far_list[w][e];
+                        const double cs_ = c->s;
+                        far_series<false>(facc, cs_, -(c->nu - xc) * cs_, c->a);
+                    }
+                } else {
+                    for (int e = lane; e < tfar; e += 32) {
+                        const int idx = sm.far_list[w][e];
+                        const CompRec* c = comps + idx;
+                        const double* Q = sm.far_q[w][idx / TAMCMC_MAX_COMP_PER_MODE - base];
+                        double cnu_, cs_, ca_;
+                        static_assert(FR == 1, "the first round reads the one record fetched ahead");
+                        if (e < 32 * FR) { cnu_ = fr_nu[0]; cs_ = fr_s[0]; ca_ = fr_a[0]; } else { cnu_ = c->nu; cs_ = c->s; ca_ = c->a; }
+                        far_series<true>(facc, cs_, -(cnu_ - xc) * cs_, ca_, Q[0], Q[1], Q[2]);
+                    }
                 }
                 __syncwarp();          // the list is rewritten by the next batch
             }
