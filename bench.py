@@ -352,6 +352,11 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": traffic, "kernel": "tamcmc_whittle_kernel", "kernel_ms": k_ms, "expand_kernel_ms": expand_ms / max(nprof, 1),
                          "algorithmic_flops_per_launch": F, "pairs_per_launch": pairs,
+                         "note": "achieved = ALGORITHMIC flops (SURVEY 8(d): 6 per (component, bin) pair of the reference's windows + 20 per bin) / "
+                                 "kernel time. The kernel executes fewer: modes >= far_ratio tile half-widths from a tile are folded into the "
+                                 "tile's polynomial (DESIGN.md 3, far-field folding; TAMCMC_GPU_FAR_RATIO=0 merges every pair per bin), so frac is "
+                                 "not FP64-pipe utilisation -- that is the ncu figure in profiles/",
+                         "far_ratio": float(os.environ.get("TAMCMC_GPU_FAR_RATIO", "8")),
                          "peak_source": "DFMA microbenchmark run in this process (tamcmc_gpu_fp64_peak); FP64 is not in MEASURED_PEAKS.json",
                          "hbm": {"achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "algorithmic_bytes_per_launch": alg_bytes}},

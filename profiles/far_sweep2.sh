@@ -1,9 +1,14 @@
-run() { tag=$1; shift; env "$@" python bench.py --no-cpu-baseline --steps 500 2>/dev/null | python -c "
+# A/B on the bench workload (C2) and on 32 stars per launch: number of far-field terms, tile cost model of the work queue
+run() { tag=$1; shift; env "$@" python bench.py --no-cpu-baseline --steps ${STEPS:-500} $ARGS 2>/dev/null | python -c "
 import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
 print('$tag', round(d['value']), 'evals/s', round(d['ms_per_step']*1e3,1),'us/step kernel',round(r['kernel_ms']*1e3,1),'expand',round(r['expand_kernel_ms']*1e3,1),'frac',round(r['frac'],3),'e2e',round(d['e2e']['value']))"; }
-run stag300 TAMCMC_GPU_STAGGER_NS=300
-run stag1000 TAMCMC_GPU_STAGGER_NS=1000
-run stag2000 TAMCMC_GPU_STAGGER_NS=2000
-run pdl TAMCMC_GPU_PDL=1
-run tile768 TAMCMC_GPU_TILE=768
+L=$PWD/tamcmc-c_b200
+for a in "" "--stars-per-gpu 32"; do
+ARGS=$a; STEPS=500; [ -n "$a" ] && STEPS=60
+echo "== $a"
+run default X=1
+run far20_ratio5 TAMCMC_GPU_LIB=$L/libtamcmc_gpu_far20.so TAMCMC_GPU_FAR_RATIO=5
+run edgecost TAMCMC_GPU_LIB=$L/libtamcmc_gpu_farcost.so
+run ratio6 TAMCMC_GPU_FAR_RATIO=6
+done

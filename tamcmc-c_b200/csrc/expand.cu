@@ -220,7 +220,10 @@ struct Common {
 constexpr int EXP_THREADS = 512;                // 16 warps: the (mode, m) slot pass and the queue pass are latency-bound
 constexpr int EXP_BATCH = 128;                 // modes expanded per pass
 enum : unsigned char { SLOT_DEAD = 0, SLOT_FAST = 1, SLOT_WIDE = 2, SLOT_SLOW = 3, SLOT_NONFINITE = 4 };   // per (mode, m) slot
-constexpr int TILE_BASE_COST = 16;             // per-tile fixed work in (component, bin)-pair units / 1024
+#ifndef TAMCMC_TILE_BASE_COST
+#define TAMCMC_TILE_BASE_COST 16
+#endif
+constexpr int TILE_BASE_COST = TAMCMC_TILE_BASE_COST;             // per-tile fixed work in (component, bin)-pair units / 1024
 
 // per-mode scratch between the three passes of a batch
 struct ModeTmp {
@@ -897,6 +900,14 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                         atomicAdd(&tcost[t0], mr.ncomp);
                         atomicAdd(&tcost[t1], -mr.ncomp);
                     }
+#ifdef TAMCMC_EDGE_COST
+                    // a tile that holds a window edge merges the mode under masks (general entries): about twice a plain merge
+                    {
+                        const int e0 = lo / sd.tile_bins, e1 = (hi - 1) / sd.tile_bins;
+                        if (lo % sd.tile_bins) { atomicAdd(&tcost[e0], TAMCMC_EDGE_COST * mr.ncomp); atomicAdd(&tcost[e0 + 1], -TAMCMC_EDGE_COST * mr.ncomp); }
+                        if (hi % sd.tile_bins) { atomicAdd(&tcost[e1], TAMCMC_EDGE_COST * mr.ncomp); atomicAdd(&tcost[e1 + 1], -TAMCMC_EDGE_COST * mr.ncomp); }
+                    }
+#endif
                 }
             }
         }

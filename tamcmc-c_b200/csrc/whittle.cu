@@ -364,9 +364,11 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         // trip of batch k (a tile-list build is a chain of dependent loads, and the first one is every CTA's start-up)
         int4 hnext = make_int4(0, 0, 0, 0);
         double2 fnext = make_double2(1.0, 0.0);
-        if (lane < nmodes) {
+        // (the first batch is fetched for every lane below the table's stride, not below nmodes: the header round trip then
+        // starts with the star / tile-record round trip instead of after it; lanes >= nmodes are ignored below)
+        if (lane < A.modes_stride) {
             hnext = *reinterpret_cast<const int4*>(modes + lane);     // {i0, i1, ncomp, nfast | wide << 16}
-            if (far_on) fnext = *reinterpret_cast<const double2*>(&modes[lane].numin);
+            if (A.far_ratio > 0.0) fnext = *reinterpret_cast<const double2*>(&modes[lane].numin);
         }
         for (int base = 0; base < nmodes; base += 32) {
             const int mi = base + lane;
@@ -564,7 +566,8 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
     // pipe idles while ALL of them are in the latency-bound epilogue.  The three warps of each SM sub-partition start
     // `stagger_ns` apart; the offset persists (bounded by the ring depth), so one warp's epilogue overlaps the others'
     // main loops.
-    if (A.stagger_ns > 0 && warp >= 4) __nanosleep((unsigned)A.stagger_ns * (unsigned)(warp >> 2));
+    // (applied after the FIRST tile has arrived: every warp waits for that one, an offset taken earlier would be lost there)
+    bool staggered = !(A.stagger_ns > 0 && warp >= 4);
     PHASE_DECL
     for (;;) {
 #ifdef TAMCMC_TRACE
@@ -588,6 +591,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
         }
         const bool asym = (flags & SEG_ASYM) != 0;
         if ((flags & SEG_FIRST) && tid == 0) sm.cons_cur = b;
+        if (!staggered) { staggered = true; __nanosleep((unsigned)A.stagger_ns * (unsigned)(warp >> 2)); }
 
         if (flags & SEG_FIRST) {
             // this thread's 4 bins: b(j) = 2*tid + 512*(j>>1) + (j&1), read as 128-bit pairs

@@ -431,3 +431,37 @@ def test_device_parallel_tempering_swap(pkg):
             assert np.allclose(dL.cpu().numpy(), L2, rtol=1e-15, atol=0, equal_nan=True)
         with pytest.raises(pkg.TamcmcError):
             ctx.pt_swap_device(Nch - 1, 0.5, dP.data_ptr(), dL.data_ptr())      # no chain A+1
+
+
+@pytest.mark.parametrize("asym", [0.0, 25.0])
+def test_far_field_folding_against_per_bin_merge(pkg, oracle, monkeypatch, asym):
+    """Modes far from a tile are folded into the tile's polynomial (whittle.cu, producer_loop).  The same library with
+    TAMCMC_GPU_FAR_RATIO=0 merges every component per bin like the reference sums them (build_lorentzian.cpp:131-161):
+    both must agree with the oracle to 1e-10 and with each other to 1e-12, at a ratio below the default as well."""
+    params, pl, x = _cases.ms_case(pkg.synth, 3, seed=11, N=61000, asym=asym)
+    rc, M = oracle.call_model(3, params, pl, x)[:2]
+    assert rc == 0
+    rng = np.random.default_rng(5)
+    y = pkg.synth.chi2_2dof_spectrum(rng, M)
+    P = pkg.synth.perturb_chains(rng, params, pl, 3)
+    T = pkg.synth.tcoefs(3, 1.7)
+    rc, L_ref = oracle.eval_chains(3, P, pl, x, y, T)
+    assert rc == 0
+    res = {}
+    for ratio in ("0", None, "6"):
+        if ratio is None:
+            monkeypatch.delenv("TAMCMC_GPU_FAR_RATIO", raising=False)
+        else:
+            monkeypatch.setenv("TAMCMC_GPU_FAR_RATIO", ratio)
+        with _ctx(pkg, 3, params, pl, x, y, 3, T) as ctx:
+            Mg = ctx.model(params)
+            L, st = ctx.eval(P)
+            assert (st == 0).all()
+        assert np.max(np.abs(Mg - M) / np.abs(M)) < RTOL
+        assert np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)) < RTOL
+        res[ratio] = (Mg, L[0])
+    for ratio in (None, "6"):
+        assert np.max(np.abs(res[ratio][0] - res["0"][0]) / np.abs(res["0"][0])) < 1e-11
+        assert np.max(np.abs(res[ratio][1] - res["0"][1]) / np.abs(res["0"][1])) < 1e-12
+    # the folding is not a no-op on this case: the two paths round differently somewhere
+    assert not np.array_equal(res[None][0], res["0"][0])
