@@ -356,7 +356,7 @@ def main():
                                  "kernel time. The kernel executes fewer: modes >= far_ratio tile half-widths from a tile are folded into the "
                                  "tile's polynomial (DESIGN.md 3, far-field folding; TAMCMC_GPU_FAR_RATIO=0 merges every pair per bin), so frac is "
                                  "not FP64-pipe utilisation -- that is the ncu figure in profiles/",
-                         "far_ratio": float(os.environ.get("TAMCMC_GPU_FAR_RATIO", "8")),
+                         "far_ratio": float(os.environ.get("TAMCMC_GPU_FAR_RATIO", "5")),
                          "peak_source": "DFMA microbenchmark run in this process (tamcmc_gpu_fp64_peak); FP64 is not in MEASURED_PEAKS.json",
                          "hbm": {"achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "algorithmic_bytes_per_launch": alg_bytes}},

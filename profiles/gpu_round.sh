@@ -22,5 +22,7 @@ ncu --set full --clock-control none --import-source on -k regex:tamcmc_whittle_k
 echo "ncu full rc=$?"
 python profiles/bench_configs.py --configs c1,c4,c3,c5,env --steps 50 > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err
 cat $OUT/${TAG}_configs.jsonl | cut -c1-200
+python profiles/far_accuracy.py > $OUT/${TAG}_far_accuracy.json 2> $OUT/${TAG}_far_accuracy.err; head -c 600 $OUT/${TAG}_far_accuracy.json
+TAMCMC_GPU_LIB=$PWD/tamcmc-c_b200/libtamcmc_gpu_trace.so timeout 120 python profiles/trace_timeline.py > $OUT/${TAG}_trace.txt 2>&1; tail -14 $OUT/${TAG}_trace.txt | cut -c1-160
 python __graft_entry__.py smoke 2>&1 | tail -2
 ls -la $OUT | tail -14

@@ -221,7 +221,10 @@ constexpr int EXP_THREADS = 512;                // 16 warps: the (mode, m) slot 
 constexpr int EXP_BATCH = 128;                 // modes expanded per pass
 enum : unsigned char { SLOT_DEAD = 0, SLOT_FAST = 1, SLOT_WIDE = 2, SLOT_SLOW = 3, SLOT_NONFINITE = 4 };   // per (mode, m) slot
 #ifndef TAMCMC_TILE_BASE_COST
-#define TAMCMC_TILE_BASE_COST 16
+#define TAMCMC_TILE_BASE_COST 26     // measured with the far-field folding on (trace build, C2): fixed phases of a tile / cost of one listed component
+#endif
+#ifndef TAMCMC_EDGE_COST
+#define TAMCMC_EDGE_COST 1
 #endif
 constexpr int TILE_BASE_COST = TAMCMC_TILE_BASE_COST;             // per-tile fixed work in (component, bin)-pair units / 1024
 
@@ -900,7 +903,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                         atomicAdd(&tcost[t0], mr.ncomp);
                         atomicAdd(&tcost[t1], -mr.ncomp);
                     }
-#ifdef TAMCMC_EDGE_COST
+#if TAMCMC_EDGE_COST > 0
                     // a tile that holds a window edge merges the mode under masks (general entries): about twice a plain merge
                     {
                         const int e0 = lo / sd.tile_bins, e1 = (hi - 1) / sd.tile_bins;

@@ -16,9 +16,9 @@
 #define TAMCMC_MAX_HARVEY 8
 #define TAMCMC_BG_TERMS 10           // Taylor coefficients of the Harvey background per tile
 #ifndef TAMCMC_FAR_TERMS
-#define TAMCMC_FAR_TERMS 16          // coefficients of the per-tile polynomial once FAR Lorentzians are folded into it (whittle.cu)
+#define TAMCMC_FAR_TERMS 20          // coefficients of the per-tile polynomial once FAR Lorentzians are folded into it (whittle.cu)
 #endif
-#define TAMCMC_FAR_RATIO_DEFAULT 8.0 // a mode is FAR from a tile when every component centre is >= ratio * (tile half-width) away from the tile centre
+#define TAMCMC_FAR_RATIO_DEFAULT 5.0 // a mode is FAR from a tile when every component centre is >= ratio * (tile half-width) away from the tile centre
 #ifndef TAMCMC_TILE
 #define TAMCMC_TILE 1536             // bins per tile
 #endif
