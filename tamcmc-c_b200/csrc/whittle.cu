@@ -343,7 +343,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         // (1e-13 for 16 terms at ratio 8).  Such a mode costs NFAR producer-side steps per component instead of 4 FP64
         // instructions per component AND BIN; its coefficients join the background polynomial of the tile.
         // (a partial last tile qualifies too: its padding repeats the last x, so umax bounds |u| of every bin)
-        const bool far_on = A.far_ratio > 0.0;
+        const bool far_on = A.far_ratio > 0.0 && nmodes > 0;
         const double farR = A.far_ratio * umax;
         double* const facc = &sm.far_acc[w][0][lane];
         if (far_on) {
