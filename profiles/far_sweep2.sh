@@ -1,4 +1,4 @@
-# A/B on the bench workload (C2) and on 32 stars per launch: number of far-field terms, tile cost model of the work queue
+# quick A/B harness on the bench workload (C2) and on 32 stars per launch; edit the `run` lines
 run() { tag=$1; shift; env "$@" python bench.py --no-cpu-baseline --steps ${STEPS:-500} $ARGS 2>/dev/null | python -c "
 import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
@@ -7,8 +7,6 @@ L=$PWD/tamcmc-c_b200
 for a in "" "--stars-per-gpu 32"; do
 ARGS=$a; STEPS=500; [ -n "$a" ] && STEPS=60
 echo "== $a"
-run default X=1
-run far20_ratio5 TAMCMC_GPU_LIB=$L/libtamcmc_gpu_far20.so TAMCMC_GPU_FAR_RATIO=5
-run edgecost TAMCMC_GPU_LIB=$L/libtamcmc_gpu_farcost.so
-run ratio6 TAMCMC_GPU_FAR_RATIO=6
+run packed_scan+prefetch X=1
+run packed_scan_only TAMCMC_GPU_LIB=$L/libtamcmc_gpu_nopf.so
 done

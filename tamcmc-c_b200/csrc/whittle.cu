@@ -292,7 +292,8 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
             first_item = false;
         } else {
             if (use) mbar_wait(empty, (use - 1) & 1);          // claim nothing while this slot still holds a tile
-            if (pending) { tile_reduce<TILE>(A, sm, w, lane); pending = false; }
+            // (the finished tile's sums are reduced further down, under the header round trip of the next tile: the consumers
+            // rewrite the slot's scratch only at the end of the tile this producer is about to list)
             const int look = (last_idx + nstatic >= endgame_from) ? A.look_end : A.look;
             for (;;) {
                 const int cur = sm.cons_cur;
@@ -307,6 +308,7 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
         last_idx = idx;
         if (idx >= ntot) {
             if (use) mbar_wait(empty, (use - 1) & 1);
+            if (pending) { tile_reduce<TILE>(A, sm, w, lane); pending = false; }
             if (lane == 0) { sg->flags = SEG_DONE; atomicOr(&sm.done_mask, 1u << w); mbar_arrive(full); mbar_arrive(full); }
             return;
         }
@@ -370,6 +372,9 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
             hnext = *reinterpret_cast<const int4*>(modes + lane);     // {i0, i1, ncomp, nfast | wide << 16}
             if (A.far_ratio > 0.0) fnext = *reinterpret_cast<const double2*>(&modes[lane].numin);
         }
+        // the previous tile of this slot: its per-thread sums become the tile partial while the loads above are in flight
+        // (tile_reduce reads the slot's sc_index / tile fields: nothing above has rewritten them yet)
+        if (pending) { tile_reduce<TILE>(A, sm, w, lane); pending = false; }
         for (int base = 0; base < nmodes; base += 32) {
             const int mi = base + lane;
             int ncomp = 0, nfast = 0, ngen = 0, i0 = 0, i1 = 0, nfast_rec = 0, mwide = 0, wbit = 0, nfar = 0;
@@ -389,14 +394,34 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                     mwide = (nfast > 0) ? wbit : 0;
                 }
             }
+#ifdef TAMCMC_COMP_PREFETCH
+            // (measured 3 % SLOWER on C2 and on 32 stars per launch: left out of the default build)
+            // the component records this lane's mode will need (general/fast entries below, far series via the list) start
+            // their way into L1 now: the scans, the list and the barrier below then overlap the L2 round trip
+            if (ncomp > 0) {
+                const char* p0 = reinterpret_cast<const char*>(comps + (size_t)mi * TAMCMC_MAX_COMP_PER_MODE);
+                const char* p1 = p0 + ncomp * (int)sizeof(CompRec) - 1;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p0));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p1));
+                if (ncomp > 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + 128));
+            }
+#endif
+            // ONE inclusive scan of the four per-lane counts packed in 8-bit fields (each total <= 32 x 7 = 224): offsets and
+            // totals of the fast entries, general entries, asym headers and far components of the batch
+            const int hh = (asym && nfast > 0) ? 1 : 0;
+            const unsigned packed = (unsigned)nfast | ((unsigned)ngen << 8) | ((unsigned)hh << 16) | ((unsigned)nfar << 24);
+            unsigned incl = packed;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+            const unsigned tot = __shfl_sync(0xffffffffu, incl, 31), excl = incl - packed;
             // far components of this batch: spread evenly over the lanes (a mode's 2l+1 components would otherwise run
             // serially on its lane); their records are fetched now and turned into series after the entries below
-            const int tfar = far_on ? warp_sum(nfar) : 0;
+            const int tfar = (int)(tot >> 24);
             constexpr int FR = 1;       // far records fetched ahead per lane (2 spills at the 128-register cap)
             double fr_nu[FR], fr_s[FR], fr_a[FR];
             if (tfar) {
                 any_far = 1;
-                const int ofar = warp_excl_scan(nfar, lane);
+                const int ofar = (int)(excl >> 24);
                 for (int k = 0; k < nfar; k++) sm.far_list[w][ofar + k] = mi * TAMCMC_MAX_COMP_PER_MODE + k;
                 if (asym && nfar > 0) {
                     const ModeRec* mr = modes + mi;
@@ -411,17 +436,18 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                 }
             }
             if (!__any_sync(0xffffffffu, ncomp > 0)) continue;
-            const int hh = (asym && nfast > 0) ? 1 : 0;
+            const bool whole_batch = (int)((tot >> 8) & 255u) <= CAPG;     // the usual case: the batch is listed in one go
             int sub_lo = 0;
             while (sub_lo < 32) {
                 int sub_hi = 32;
                 bool mine = lane >= sub_lo;
-                int tf = warp_sum(mine ? nfast : 0), tg = warp_sum(mine ? ngen : 0), th = warp_sum(mine ? hh : 0);
-                if (tg > CAPG) {
+                int tf, tg, th;
+                if (whole_batch) { tf = (int)(tot & 255u); tg = (int)((tot >> 8) & 255u); th = (int)((tot >> 16) & 255u); }
+                else {
                     // too many general entries for one segment: 3 modes at a time (3 x 7 <= CAPG)
-                    sub_hi = sub_lo + 3;
-                    mine = lane >= sub_lo && lane < sub_hi;
-                    tf = warp_sum(mine ? nfast : 0); tg = warp_sum(mine ? ngen : 0); th = warp_sum(mine ? hh : 0);
+                    tg = warp_sum(mine ? ngen : 0);
+                    if (tg > CAPG) { sub_hi = sub_lo + 3; mine = lane >= sub_lo && lane < sub_hi; tg = warp_sum(mine ? ngen : 0); }
+                    tf = warp_sum(mine ? nfast : 0); th = warp_sum(mine ? hh : 0);
                 }
                 if (cf + tf > CAPF || cg + tg > CAPG || ch + th > CAPH) {
                     // ---- the slot is full: publish this segment, wait for the consumers to release the slot, go on ----
@@ -439,14 +465,16 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                 }
                 seg_wide |= __any_sync(0xffffffffu, mine && mwide) ? 1 : 0;
                 const int mf = mine ? nfast : 0, mg = mine ? ngen : 0, mh = mine ? hh : 0;
-                const int of = cf + warp_excl_scan(mf, lane), og = cg + warp_excl_scan(mg, lane), oh = ch + warp_excl_scan(mh, lane);
+                int of, og, oh;
+                if (whole_batch) { of = cf + (int)(excl & 255u); og = cg + (int)((excl >> 8) & 255u); oh = ch + (int)((excl >> 16) & 255u); }
+                else { of = cf + warp_excl_scan(mf, lane); og = cg + warp_excl_scan(mg, lane); oh = ch + warp_excl_scan(mh, lane); }
                 if (mine && ncomp > 0) {
                     const CompRec* cp = comps + (size_t)mi * TAMCMC_MAX_COMP_PER_MODE;
                     double qa = 0.0, qb = 1.0, qc = 0.0;
                     if (asym || ngen > 0) { const ModeRec* mr = modes + mi; qa = mr->qa; qb = mr->qb0 + xc * qa; qc = mr->qc; }
                     if (hh) { ModeHdr m; m.qa = qa; m.qb = qb; m.qc = qc; m.begin = of; m.count = nfast; sg->hdr[oh] = m; }
-#pragma unroll
                     const int nlead = nfast + nfar;          // leading components that are not general entries in this tile
+#pragma unroll
                     for (int k0 = 0; k0 < 8; k0 += 4) {
                         double cnu[4], cs[4], ca[4];
 #pragma unroll
@@ -513,10 +541,10 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
                 __syncwarp();
                 if (lane < NFAR) {
                     const double* row = &sm.far_acc[w][lane][0];
-                    double fs = 0.0;
-#pragma unroll 8
-                    for (int j = 0; j < 32; j++) fs += row[j];
-                    ck += fs;
+                    double fa = 0.0, fb = 0.0, fc = 0.0, fd = 0.0;     // four interleaved chains, fixed association
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) { fa += row[j]; fb += row[j + 1]; fc += row[j + 2]; fd += row[j + 3]; }
+                    ck += (fa + fb) + (fc + fd);
                 }
             }
             if (lane < NFAR) sg->bg[lane] = ck;
