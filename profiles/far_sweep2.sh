@@ -7,6 +7,6 @@ L=$PWD/tamcmc-c_b200
 for a in "" "--stars-per-gpu 32"; do
 ARGS=$a; STEPS=500; [ -n "$a" ] && STEPS=60
 echo "== $a"
-run packed_scan+prefetch X=1
-run packed_scan_only TAMCMC_GPU_LIB=$L/libtamcmc_gpu_nopf.so
+run claim_early X=1
+run claim_after_release TAMCMC_GPU_LIB=$L/libtamcmc_gpu_prev.so
 done

@@ -291,9 +291,14 @@ __device__ void producer_loop(const WhittleArgs& A, Smem<TILE>& sm, int w, int l
             idx = (unsigned)w * G + ((w & 1) ? (G - 1u - blockIdx.x) : blockIdx.x);
             first_item = false;
         } else {
+            // The next item is claimed as soon as the look-ahead rule allows, BEFORE the slot has been handed back: the pop, the
+            // queue entry and the tile / star records (three dependent round trips) are then in flight while the consumers finish
+            // the slot's tile; the wait for the slot comes where the slot is first written (below).  The finished tile's sums are
+            // reduced further down, under the header round trip of the next tile: the consumers rewrite the slot's scratch only at
+            // the end of the tile this producer is about to list.
+#ifdef TAMCMC_CLAIM_AFTER_RELEASE
             if (use) mbar_wait(empty, (use - 1) & 1);          // claim nothing while this slot still holds a tile
-            // (the finished tile's sums are reduced further down, under the header round trip of the next tile: the consumers
-            // rewrite the slot's scratch only at the end of the tile this producer is about to list)
+#endif
             const int look = (last_idx + nstatic >= endgame_from) ? A.look_end : A.look;
             for (;;) {
                 const int cur = sm.cons_cur;
