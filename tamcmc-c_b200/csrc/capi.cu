@@ -508,6 +508,11 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
             std::memcpy(&hx[(size_t)sd.off], stars[s].x, sizeof(double) * (size_t)sd.Nloc);
             std::memcpy(&hy[(size_t)sd.off], stars[s].y, sizeof(double) * (size_t)sd.Nloc);
             for (long long i = sd.Nloc; i < (long long)sd.ntiles * TB; i++) hx[(size_t)(sd.off + i)] = stars[s].x[sd.Nloc - 1];
+            // the far-field folding bounds |x - xc| inside a tile by the tile's end points: a frequency axis that is not
+            // monotone (the reference's windows assume x0 + i*step, build_lorentzian.cpp:645-646) turns the folding off
+            bool up = true, down = true;
+            for (int i = 1; i < sd.Nloc; i++) { up = up && stars[s].x[i] >= stars[s].x[i - 1]; down = down && stars[s].x[i] <= stars[s].x[i - 1]; }
+            if (!up && !down) c->far_ratio = 0.0;
         }
         CKC(cudaMemcpy(c->d_x, hx.data(), sizeof(double) * off, cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_y, hy.data(), sizeof(double) * off, cudaMemcpyHostToDevice));
