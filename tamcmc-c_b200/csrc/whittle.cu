@@ -8,7 +8,11 @@
 //    mask-free FastEntry, window edge or extreme dynamic range -> GenEntry with [lo,hi); it fetches the tile's x and
 //    y (2 x 12 KB) with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) and publishes the slot on its
 //    `full` mbarrier.  Four producers overlap the global-memory latency of four tiles; a list that exceeds the
-//    slot's capacities is streamed through the same slot as several segments;
+//    slot's capacities is streamed through the same slot as several segments.  FAR-FIELD FOLDING: a mode whose components
+//    all lie >= far_ratio tile half-widths from the tile centre (and whose window covers the tile) is not listed: the
+//    producer expands its components in Taylor series about the tile centre (Chebyshev-U recurrence, far_series) and adds
+//    the coefficients to the tile's background polynomial, so the consumers pay one longer Horner evaluation per bin
+//    instead of 4 FP64 instructions per far component and bin (truncation <= 5e-13 of a folded component);
 //  * the 384 consumer threads own 4 bins each and take the slots round-robin, one tile at a time.  The model
 //    spectrum M never exists in HBM: every thread keeps the running Lorentzian sum of a bin as ONE fraction N/D,
 //        sum_k A_k / (1 + 4 (x - nu_k)^2 / Gamma_k^2)  =  N / D ,
@@ -16,7 +20,8 @@
 //    (N, D) <- (N t' + D, D t').  That replaces the reference's FP64 divide per (component, bin)
 //    (build_lorentzian.cpp:151: cwiseInverse) by 4 FP64-pipe instructions, with one reciprocal per bin at the
 //    end.  Exponents of (N, D) are renormalised with 4 integer ops per bin every 16 components.  The background
-//    (noise_models.cpp:15-39) is a 9th-degree polynomial per tile (or exact exp() per bin near x = 0), the
+//    (noise_models.cpp:15-39) is a 9th-degree polynomial per tile (or exact exp() per bin near x = 0; 19th degree once far
+//    modes are folded into it), the
 //    Whittle terms y/M + ln M (likelihoods.cpp:23) are summed per thread; the thread stores its three sums in the
 //    slot's scratch and releases the slot, and the slot's PRODUCER warp reduces the 384 triples (fixed shape) into
 //    one partial per tile once the empty barrier has handed the slot back.  The last CTA to finish sums the per-tile
