@@ -1,4 +1,4 @@
-"""Readers for the reference's simplest on-disk inputs (first slice): the ASCII `.data` spectrum and
+"""Readers for the reference's simplest on-disk inputs and reader/writer of its binary chain outputs (first slice): the ASCII `.data` spectrum and
 the "simple matrix" `.model` file of the Gaussian-envelope fits (model_Harvey_Gaussian / model_Kallinger2014_Gaussian).
 
   .data  : '#' comments, '!' column labels, '*' units, then whitespace-separated columns (frequency, power[, ...])
@@ -6,6 +6,8 @@ the "simple matrix" `.model` file of the Gaussian-envelope fits (model_Harvey_Ga
   .model : '#' comments, '* fmin fmax' the fitted range, '! names', the initial values, '! relax' + one 0/1 flag per
            parameter, '! prior names', then up to four rows of prior parameters (-9999 = unused slot)
            -- Config::read_inputs_prior_Simple_Matrix (config.cpp:560-660)
+
+  outputs: <prefix>.hdr + <prefix>_chain-<k>.bin, the binary chain files of Outputs::write_bin_params (outputs.cpp:1231-1334)
 
 Host-side I/O only: nothing here is on the GPU path."""
 import numpy as np
@@ -63,3 +65,82 @@ def read_simple_matrix_model(path):
         raise ValueError("%s: %d names, %d values, %d relax flags, %d priors" % (path, len(names), len(inputs), len(relax), n))
     kinds = np.array([PRIOR_KINDS.get(p, -1) for p in prior_names], dtype=np.int32)
     return dict(xrange=xrange, names=names, inputs=inputs, relax=relax, prior_names=prior_names, prior_kinds=kinds, priors=priors)
+
+
+# ------------------------------------------------------------------------------------------------
+# Binary chain outputs of the reference (Outputs::write_bin_params, tamcmc/sources/outputs.cpp:1231-1334):
+#   <prefix>.hdr            ASCII metadata, '#' comments and '! key= values' lines
+#   <prefix>_chain-<k>.bin  raw little-endian float64, one row of Nvars values per kept sample, one file per chain
+# so that a run of the GPU driver leaves files the reference's own post-processing tools (bin2txt, getstats) read.
+# ------------------------------------------------------------------------------------------------
+def _eigen_row(values, integers):
+    """A row vector the way Eigen's operator<< prints `v.transpose()`: default stream precision (6 significant digits),
+    every coefficient right-aligned to the widest one, single-space separators."""
+    txt = [("%d" % int(v)) if integers else ("%g" % float(v)) for v in values]
+    w = max((len(t) for t in txt), default=0)
+    return " ".join(t.rjust(w) for t in txt)
+
+
+def params_header_text(Nsamples, Nchains, Nsamples_done, relax, plength, cons_names, cons_values, var_names):
+    """The text of <prefix>.hdr (outputs.cpp:1259-1303).  `relax` has one flag per parameter (variables and constants),
+    `cons_names == ['None']` stands for "no constant" (the reference then writes -1 as the value)."""
+    Nvars, Ncons = len(var_names), len(cons_names)
+    out = ["# This is the header file of the BINARY output file for the model parameters ",
+           "# This file contains values for vars[0:Nchains-1][ 0:Nvars-1]. Each matrix is in a different file, indexed by the chain number",
+           "! Nsamples= %d" % Nsamples, "! Nchains= %d" % Nchains, "! Nsamples_done=%d" % Nsamples_done, "! Nvars= %d" % Nvars,
+           "! Ncons= %d" % Ncons, "! relax= " + _eigen_row(relax, True), "! plength= " + _eigen_row(plength, True),
+           "! constant_names= " + "".join("%s   " % n for n in cons_names),
+           "! constant_values= " + ("-1" if list(cons_names)[:1] == ["None"] else _eigen_row(cons_values, False)),
+           "! variable_names=" + "".join("%s   " % n for n in var_names)]
+    return "\n".join(out) + "\n"
+
+
+def write_params_outputs(prefix, samples, relax, plength, cons_names, cons_values, var_names, Nsamples=None, append=False, file_ext="bin"):
+    """samples[Nkept, Nchains, Nvars] -> <prefix>.hdr and <prefix>_chain-<k>.<file_ext>.  append=True adds rows to existing
+    chain files and leaves the header alone, like the reference's buffered writes after the first one."""
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    if samples.ndim != 3 or samples.shape[2] != len(var_names):
+        raise ValueError("samples must be [Nkept, Nchains, Nvars]")
+    Nkept, Nchains, _ = samples.shape
+    if not append:
+        with open(prefix + ".hdr", "w") as f:
+            f.write(params_header_text(Nkept if Nsamples is None else Nsamples, Nchains, Nkept, relax, plength, cons_names, cons_values, var_names))
+    for k in range(Nchains):
+        with open("%s_chain-%d.%s" % (prefix, k, file_ext), "ab" if append else "wb") as f:
+            f.write(np.ascontiguousarray(samples[:, k, :]).astype("<f8").tobytes())
+
+
+def parse_params_header(text):
+    """-> dict(Nsamples, Nchains, Nsamples_done, Nvars, Ncons, relax, plength, constant_names, constant_values, variable_names)"""
+    h = {}
+    for line in text.splitlines():
+        s = line.strip()
+        if not s.startswith("!"):
+            continue
+        key, _, val = s[1:].partition("=")
+        key, toks = key.strip(), val.split()
+        if key in ("Nsamples", "Nchains", "Nsamples_done", "Nvars", "Ncons"):
+            h[key] = int(toks[0])
+        elif key in ("relax", "plength"):
+            h[key] = np.array([int(float(t)) for t in toks], dtype=np.int64)
+        elif key == "constant_values":
+            h[key] = np.array([float(t) for t in toks], dtype=np.float64)
+        else:
+            h[key] = toks
+    return h
+
+
+def read_params_outputs(prefix, chains=None, file_ext="bin"):
+    """-> (header dict, samples[Nrows, Nchains_read, Nvars]); Nrows is what the chain files hold (the reference appends whole
+    buffers, so it can be ahead of or behind the header's Nsamples_done)."""
+    with open(prefix + ".hdr") as f:
+        h = parse_params_header(f.read())
+    ks = range(h["Nchains"]) if chains is None else chains
+    cols = []
+    for k in ks:
+        a = np.fromfile("%s_chain-%d.%s" % (prefix, k, file_ext), dtype="<f8")
+        if a.size % h["Nvars"]:
+            raise ValueError("chain file %d does not hold whole rows of Nvars=%d values" % (k, h["Nvars"]))
+        cols.append(a.reshape(-1, h["Nvars"]))
+    n = min(c.shape[0] for c in cols)
+    return h, np.stack([c[:n] for c in cols], axis=1)

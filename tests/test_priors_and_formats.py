@@ -137,3 +137,43 @@ def test_gaussfit_mcmc_on_reference_fixture(pkg, tmp_path):
     assert a["logpost_final"] > a["logpost_initial"] + 1000.0        # the .model's initial guess is far from the posterior mode
     assert 0.03 < a["acceptance_cold"] < 0.8 and a["swap_rate"] > 0.05
     print(a)
+
+
+def test_params_output_header_matches_the_reference_byte_for_byte(pkg):
+    """Outputs::write_bin_params (outputs.cpp:1231-1334): the header the reference wrote for its own Gaussian-envelope run
+    (tests/golden/reference_params_hdr.json, made by make_golden_params_hdr.py) is parsed to its values, and the writer
+    regenerates the same bytes from them."""
+    fmt = pkg.formats
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_params_hdr.json")))
+    h = fmt.parse_params_header(gold["text"])
+    tok = gold["tokens"]
+    for k in ("Nsamples", "Nchains", "Nsamples_done", "Nvars", "Ncons"):
+        assert h[k] == int(tok[k][0])
+    assert h["relax"].tolist() == [int(t) for t in tok["relax"]] and h["plength"].tolist() == [int(t) for t in tok["plength"]]
+    assert h["constant_names"] == tok["constant_names"] and h["variable_names"] == tok["variable_names"]
+    assert h["constant_values"].tolist() == [float(t) for t in tok["constant_values"]]
+    assert len(h["variable_names"]) == h["Nvars"] and len(h["relax"]) == h["Nvars"] + h["Ncons"]
+    text = fmt.params_header_text(h["Nsamples"], h["Nchains"], h["Nsamples_done"], h["relax"], h["plength"], h["constant_names"],
+                                  h["constant_values"], h["variable_names"])
+    assert text == gold["text"]
+    # Eigen pads every coefficient of a printed row to the widest one
+    assert fmt._eigen_row([20, 3, 20, 6], True) == "20  3 20  6" and fmt._eigen_row([0.5, 12.25], False) == "  0.5 12.25"
+    assert "! constant_values= -1\n" in fmt.params_header_text(10, 1, 10, [1], [1], ["None"], [], ["a"])
+
+
+def test_params_outputs_round_trip(pkg, tmp_path):
+    fmt = pkg.formats
+    rng = np.random.default_rng(0)
+    names = ["H1", "tc1", "B0"]
+    s1, s2 = rng.normal(size=(7, 3, 3)), rng.normal(size=(5, 3, 3))
+    prefix = str(tmp_path / "star_A_params")
+    fmt.write_params_outputs(prefix, s1, [1, 1, 0, 1], [1, 1, 1, 1], ["p1"], [4.0], names, Nsamples=12)
+    fmt.write_params_outputs(prefix, s2, [1, 1, 0, 1], [1, 1, 1, 1], ["p1"], [4.0], names, append=True)      # second buffer
+    h, got = fmt.read_params_outputs(prefix)
+    assert h["Nsamples"] == 12 and h["Nchains"] == 3 and h["Nvars"] == 3 and h["variable_names"] == names
+    assert got.shape == (12, 3, 3) and np.array_equal(got, np.concatenate([s1, s2]))         # bit-exact: raw float64
+    assert os.path.getsize(prefix + "_chain-2.bin") == 12 * 3 * 8
+    _, one = fmt.read_params_outputs(prefix, chains=[1])
+    assert np.array_equal(one[:, 0, :], got[:, 1, :])
+    with pytest.raises(ValueError):
+        fmt.write_params_outputs(prefix, s1[:, :, :2], [1], [1], ["None"], [], names)
