@@ -1,0 +1,93 @@
+// outputs.hpp -- the reference's binary chain outputs, written by the C++ driver side (host only, header only).
+//
+//   <prefix>.hdr            ASCII metadata: '#' comments and '! key= values' lines
+//   <prefix>_chain-<k>.bin  raw float64, one row of Nvars values per kept sample, one file per chain
+//
+// Same files as Outputs::write_bin_params (tamcmc/sources/outputs.cpp:1231-1334), so the reference's post-processing tools
+// (bin2txt, getstats) read a run of mcmc_driver.hpp unchanged; tamcmc-c_b200/formats.py holds the Python reader/writer of the
+// same format.  Errors are returned, never fatal (the reference exits when a file cannot be opened, outputs.cpp:1322-1327).
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <fstream>
+#include <string>
+#include <vector>
+
+namespace tamcmc {
+namespace outputs {
+
+// A row vector the way Eigen's operator<< prints `v.transpose()` (outputs.cpp:1270, 1274, 1289): stream default precision
+// (6 significant digits), every coefficient right-aligned to the widest one, single-space separators.
+template <class T>
+inline std::string eigen_row(const std::vector<T>& v, bool integers)
+{
+    std::vector<std::string> txt;
+    size_t w = 0;
+    for (const T& x : v) {
+        char buf[64];
+        if (integers) std::snprintf(buf, sizeof buf, "%ld", (long)x);
+        else std::snprintf(buf, sizeof buf, "%g", (double)x);
+        txt.emplace_back(buf);
+        w = std::max(w, txt.back().size());
+    }
+    std::string out;
+    for (size_t i = 0; i < txt.size(); i++) { if (i) out += " "; out += std::string(w - txt[i].size(), ' ') + txt[i]; }
+    return out;
+}
+
+struct ParamsMeta {
+    long Nsamples = 0;                       // samples the run was asked for
+    int Nchains = 0;
+    std::vector<int> relax, plength;         // one relax flag per parameter (variables and constants)
+    std::vector<std::string> cons_names;     // {"None"}: no constant (the reference then writes -1 as the value)
+    std::vector<double> cons_values;
+    std::vector<std::string> var_names;
+};
+
+inline std::string params_header_text(const ParamsMeta& m, long Nsamples_done)
+{
+    std::string s;
+    s += "# This is the header file of the BINARY output file for the model parameters \n";
+    s += "# This file contains values for vars[0:Nchains-1][ 0:Nvars-1]. Each matrix is in a different file, indexed by the chain number\n";
+    s += "! Nsamples= " + std::to_string(m.Nsamples) + "\n";
+    s += "! Nchains= " + std::to_string(m.Nchains) + "\n";
+    s += "! Nsamples_done=" + std::to_string(Nsamples_done) + "\n";
+    s += "! Nvars= " + std::to_string(m.var_names.size()) + "\n";
+    s += "! Ncons= " + std::to_string(m.cons_names.size()) + "\n";
+    s += "! relax= " + eigen_row(m.relax, true) + "\n";
+    s += "! plength= " + eigen_row(m.plength, true) + "\n";
+    s += "! constant_names= ";
+    for (const auto& n : m.cons_names) s += n + "   ";
+    s += "\n! constant_values= ";
+    s += (!m.cons_names.empty() && m.cons_names[0] == "None") ? std::string("-1") : eigen_row(m.cons_values, false);
+    s += "\n! variable_names=";
+    for (const auto& n : m.var_names) s += n + "   ";
+    s += "\n";
+    return s;
+}
+
+// Writes (first == true: header + fresh chain files) or appends (first == false: chain files only, like the reference's
+// buffered writes after the first) `nrows` samples held as vars[row][chain][var] (row-major, contiguous).  0 on success.
+inline int write_params(const std::string& prefix, const ParamsMeta& m, const double* vars, long nrows, long Nsamples_done, bool first)
+{
+    const size_t nv = m.var_names.size();
+    if (first) {
+        std::ofstream h((prefix + ".hdr").c_str());
+        if (!h.is_open()) return -1;
+        h << params_header_text(m, Nsamples_done);
+    }
+    std::vector<double> row(nv);
+    for (int c = 0; c < m.Nchains; c++) {
+        std::ofstream f((prefix + "_chain-" + std::to_string(c) + ".bin").c_str(),
+                        first ? (std::ofstream::binary | std::ofstream::trunc) : (std::ofstream::binary | std::ofstream::app));
+        if (!f.is_open()) return -2;
+        for (long i = 0; i < nrows; i++)
+            f.write(reinterpret_cast<const char*>(vars + ((size_t)i * m.Nchains + c) * nv), (std::streamsize)(nv * sizeof(double)));
+        f.flush();
+        if (!f.good()) return -3;
+    }
+    return 0;
+}
+
+}  // namespace outputs
+}  // namespace tamcmc

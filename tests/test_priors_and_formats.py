@@ -177,3 +177,21 @@ def test_params_outputs_round_trip(pkg, tmp_path):
     assert np.array_equal(one[:, 0, :], got[:, 1, :])
     with pytest.raises(ValueError):
         fmt.write_params_outputs(prefix, s1[:, :, :2], [1], [1], ["None"], [], names)
+
+
+def test_cpp_outputs_writer_matches_reference_header_and_python_reader(pkg, tmp_path):
+    """host/outputs.hpp (the C++ driver side of Outputs::write_bin_params): same header bytes as the reference's fixture, chain
+    files the Python reader takes back bit for bit."""
+    exe, src = os.path.join(HERE, "cpp", "test_outputs"), os.path.join(HERE, "cpp", "test_outputs.cpp")
+    hdr = os.path.join(HERE, "..", "tamcmc-c_b200", "host", "outputs.hpp")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", exe, src])
+    prefix = str(tmp_path / "10280410_Gaussfit_A_params")
+    r = subprocess.run([exe, prefix], stdout=subprocess.PIPE, text=True, check=True)
+    assert r.stdout == "  0.5 12.25"
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_params_hdr.json")))
+    assert open(prefix + ".hdr").read() == gold["text"]
+    h, s = pkg.formats.read_params_outputs(prefix)
+    assert s.shape == (10, 4, 9)
+    i, c, v = np.meshgrid(np.arange(10), np.arange(4), np.arange(9), indexing="ij")
+    assert np.array_equal(s, 1000.0 * i + 10.0 * c + v + 0.125)
