@@ -144,3 +144,89 @@ def read_params_outputs(prefix, chains=None, file_ext="bin"):
         cols.append(a.reshape(-1, h["Nvars"]))
     n = min(c.shape[0] for c in cols)
     return h, np.stack([c[:n] for c in cols], axis=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# Acceptance-rate log (Outputs::write_txt_acceptance, outputs.cpp:747-789) and restore files
+# (Outputs::write_buffer_restore, outputs.cpp:863-1027; read back by Config::restore at start-up when do_restore=1)
+# ------------------------------------------------------------------------------------------------
+ACCEPTANCE_HEADER = ("# This is an output file for the acceptance rate. \n"
+                     "# This file contains values for the acceptance_rate[0:Nchains-1] in function of the average sample position\n"
+                     "# Averaging is done over Nbuffer \n")
+
+
+def acceptance_text(xaxis, rates, with_header=True):
+    """Rows `xaxis rate_0 .. rate_{Nchains-1}` the way the reference appends them (one Eigen-printed row per buffer)."""
+    rates = np.atleast_2d(np.asarray(rates, dtype=np.float64))
+    out = (ACCEPTANCE_HEADER + "! Nchains= %d\n" % rates.shape[1]) if with_header else ""
+    for x, r in zip(np.atleast_1d(xaxis), rates):
+        out += "%g %s\n" % (x, _eigen_row(r, False))
+    return out
+
+
+def read_acceptance(path):
+    """-> (xaxis[Nrows], rates[Nrows, Nchains])"""
+    rows = [[float(t) for t in l.split()] for l in open(path) if l.strip() and l.lstrip()[0] not in "#!"]
+    a = np.asarray(rows, dtype=np.float64)
+    return a[:, 0].copy(), a[:, 1:].copy()
+
+
+def parse_restore_text(text):
+    """One restore file -> dict.  Scalars (`Nchains`, `Nvars`, `iteration`), `variable_names`, and every `! key=` block as an
+    array: values on the key's own line give a vector (sigmas), following rows a matrix [Nchains, Nvars] (vars, mus, ...),
+    `*k` sub-blocks a stack [Nchains, Nvars, Nvars] (covarmats).  Values carry the 6 significant digits the reference prints."""
+    out, key, rows, blocks = {}, None, [], None
+
+    def close():
+        nonlocal key, rows, blocks
+        if key is not None:
+            if blocks is not None:
+                if rows:
+                    blocks.append(rows)
+                out[key] = np.asarray(blocks, dtype=np.float64)
+            elif rows:
+                out[key] = np.asarray(rows, dtype=np.float64)
+        key, rows, blocks = None, [], None
+
+    for line in text.splitlines():
+        s = line.strip()
+        if not s or s[0] == "#":
+            continue
+        if s[0] == "!":
+            close()
+            k, _, v = s[1:].partition("=")
+            k, toks = k.strip(), v.split()
+            if k in ("Nchains", "Nvars", "iteration"):
+                out[k] = int(toks[0])
+            elif k == "variable_names":
+                out[k] = toks
+            elif toks:
+                out[k] = np.asarray([float(t) for t in toks], dtype=np.float64)
+            else:
+                key = k
+        elif s[0] == "*":
+            if blocks is None:
+                blocks = []
+            elif rows:
+                blocks.append(rows)
+            rows = []
+        else:
+            rows.append([float(t) for t in s.split()])
+    close()
+    return out
+
+
+def read_restore(directory, star_id, phase="A"):
+    """The three files `<star_id>_restore_<phase>_{1,2,3}.dat` of a run -> one dict: vars, vars_mean (file 1), sigmas, mus and
+    their means (file 2), covarmats, covarmats_mean (file 3) -- what a restarted run needs (position, proposal scale, proposal
+    mean and covariance of every chain)."""
+    import os
+    merged = {}
+    for n in (1, 2, 3):
+        with open(os.path.join(directory, "%s_restore_%s_%d.dat" % (star_id, phase, n))) as f:
+            d = parse_restore_text(f.read())
+        for k in ("Nchains", "Nvars", "iteration"):
+            if k in merged and k in d and merged[k] != d[k]:
+                raise ValueError("restore files disagree on %s" % k)
+        merged.update(d)
+    return merged

@@ -195,3 +195,30 @@ def test_cpp_outputs_writer_matches_reference_header_and_python_reader(pkg, tmp_
     assert s.shape == (10, 4, 9)
     i, c, v = np.meshgrid(np.arange(10), np.arange(4), np.arange(9), indexing="ij")
     assert np.array_equal(s, 1000.0 * i + 10.0 * c + v + 0.125)
+
+
+def test_acceptance_log_and_restore_files_of_the_reference(pkg, tmp_path):
+    """The acceptance log regenerates byte for byte from its parsed values (Outputs::write_txt_acceptance, outputs.cpp:747-789);
+    the three restore files the reference wrote (write_buffer_restore, outputs.cpp:863-1027) parse into the state a restart
+    needs.  Texts: tests/golden/reference_outputs_10280410.json (make_golden_params_hdr.py)."""
+    fmt = pkg.formats
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_outputs_10280410.json")))
+    p = tmp_path / "acc.txt"
+    p.write_text(gold["acceptance"])
+    x, r = fmt.read_acceptance(str(p))
+    assert r.shape[1] == 4 and x[0] == 2500 and r[0].tolist() == [0.237, 0.2316, 0.2764, 0.2348] and np.all(np.diff(x) == 5000)
+    assert fmt.acceptance_text(x, r) == gold["acceptance"]
+    for n in (1, 2, 3):
+        (tmp_path / ("10280410_Gaussfit_restore_A_%d.dat" % n)).write_text(gold["restore"][str(n)])
+    st = fmt.read_restore(str(tmp_path), "10280410_Gaussfit")
+    assert st["Nchains"] == 4 and st["Nvars"] == 9 and st["iteration"] == 99999 and st["variable_names"][-1] == "Gauss_sigma"
+    for k in ("vars", "vars_mean", "mus", "mus_mean"):
+        assert st[k].shape == (4, 9)
+    assert st["vars"][0, 0] == 1110.3 and st["vars"][3, 8] == 11.8951 and st["mus"][3, 2] == 345.202
+    assert st["sigmas"].tolist() == [0.00234744, 0.00110771, 0.0414778, 0.00270788] and np.array_equal(st["sigmas"], st["sigmas_mean"])
+    for k in ("covarmats", "covarmats_mean"):
+        C = st[k]
+        assert C.shape == (4, 9, 9)
+        assert np.allclose(C, np.transpose(C, (0, 2, 1)), rtol=1e-5, atol=0)          # symmetric to the printed digits
+        assert np.all(np.linalg.eigvalsh(0.5 * (C + np.transpose(C, (0, 2, 1)))) > 0)       # proposal covariances
+    assert st["covarmats"][0, 0, 0] == 4.20452 and st["covarmats"][0, 1, 0] == 1.11062
