@@ -230,3 +230,45 @@ def read_restore(directory, star_id, phase="A"):
                 raise ValueError("restore files disagree on %s" % k)
         merged.update(d)
     return merged
+
+
+_RESTORE_WHAT = {
+    1: ("# Contains the last values for the variables vars[0:Nchain-1]. vars_mean denotes averaged values of Nbuffer \n", "do_restore_[X]=1", "do_restore_proposal=1"),
+    2: ("# Contains the last values of (a) sigmas[0:Nchains-1] and (b) mus[0:Nchains-1, 0:Nvars-1].  sigmas_mean and mus_mean denotes averaged values of Nbuffer\n", "do_restore=1", "do_restore=1"),
+    3: ("# Contains the last value of the covariance matrix covarmats[0:Nchains-1, 0:Nvars-1, 0:Nvars-1]. covarmats_mean denotes the averaged values over Nbuffer\n", "do_restore=1", "do_restore=1"),
+}
+
+
+def restore_texts(state):
+    """state (the dict read_restore returns) -> {1: text, 2: text, 3: text} in the layout of Outputs::write_buffer_restore
+    (outputs.cpp:863-1027): every matrix row printed on its own (`.row(i)`: aligned per row), 6 significant digits."""
+    names = "! variable_names=" + "".join("%s   " % n for n in state["variable_names"]) + "\n"
+
+    def head(n):
+        what, a, b = _RESTORE_WHAT[n]
+        return ("# This is an output file containing what is required to restore a run to its last saved position \n"
+                "# File number: %d \n" % n + what + "# Use this if you wish to: \n"
+                "#       (1) complete a finished job that requires more samples ==> set erase_old_file=0 and %s \n" % a +
+                "#       (2) restart a finished job by ignoring old samples (e.g. ignoring a Burn-in) ==> set erase_old_file=1 and %s \n" % b +
+                "#       (3) terminate an unfinished job which failed to finished (e.g. due to computer unexpected shutdown) ==> set erase_old_file=0 and %s \n" % a +
+                "! Nchains= %d\n! Nvars= %d\n! iteration=%d\n" % (state["Nchains"], state["Nvars"], state["iteration"]) + names)
+
+    def rows(M):
+        return "".join(_eigen_row(r, False) + "\n" for r in np.atleast_2d(M))
+
+    t1 = head(1) + "! vars= \n" + rows(state["vars"]) + "! vars_mean= \n" + rows(state["vars_mean"])
+    t2 = (head(2) + "! sigmas= " + _eigen_row(state["sigmas"], False) + "\n! mus= \n" + rows(state["mus"]) +
+          "! sigmas_mean= " + _eigen_row(state["sigmas_mean"], False) + "\n! mus_mean= \n" + rows(state["mus_mean"]))
+    t3 = head(3)
+    for key in ("covarmats", "covarmats_mean"):
+        t3 += "! %s= \n" % key
+        for k, C in enumerate(state[key]):
+            t3 += "*%d\n" % k + rows(C)
+    return {1: t1, 2: t2, 3: t3}
+
+
+def write_restore(directory, star_id, state, phase="A"):
+    import os
+    for n, text in restore_texts(state).items():
+        with open(os.path.join(directory, "%s_restore_%s_%d.dat" % (star_id, phase, n)), "w") as f:
+            f.write(text)

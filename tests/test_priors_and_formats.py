@@ -222,3 +222,24 @@ def test_acceptance_log_and_restore_files_of_the_reference(pkg, tmp_path):
         assert np.allclose(C, np.transpose(C, (0, 2, 1)), rtol=1e-5, atol=0)          # symmetric to the printed digits
         assert np.all(np.linalg.eigvalsh(0.5 * (C + np.transpose(C, (0, 2, 1)))) > 0)       # proposal covariances
     assert st["covarmats"][0, 0, 0] == 4.20452 and st["covarmats"][0, 1, 0] == 1.11062
+
+
+def test_restore_writer_reproduces_the_reference_data_lines(pkg, tmp_path):
+    """write_restore: every non-comment line of the three files the reference wrote comes back byte for byte from the parsed
+    state (the comment lines of file 1 differ between versions of the reference: `do_restore=1` vs `do_restore_[X]=1`)."""
+    fmt = pkg.formats
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_outputs_10280410.json")))
+    for n in (1, 2, 3):
+        (tmp_path / ("10280410_Gaussfit_restore_A_%d.dat" % n)).write_text(gold["restore"][str(n)])
+    st = fmt.read_restore(str(tmp_path), "10280410_Gaussfit")
+    texts = fmt.restore_texts(st)
+    data = lambda t: [l for l in t.splitlines() if not l.startswith("#")]
+    for n in (1, 2, 3):
+        assert data(texts[n]) == data(gold["restore"][str(n)]), n
+        assert len([l for l in texts[n].splitlines() if l.startswith("#")]) == len([l for l in gold["restore"][str(n)].splitlines() if l.startswith("#")])
+    assert texts[3] == gold["restore"]["3"] and texts[2] == gold["restore"]["2"]
+    out = tmp_path / "again"
+    out.mkdir()
+    fmt.write_restore(str(out), "star", st, phase="L")
+    st2 = fmt.read_restore(str(out), "star", phase="L")
+    assert all(np.array_equal(st[k], st2[k]) for k in ("vars", "vars_mean", "sigmas", "mus", "covarmats", "covarmats_mean"))
