@@ -106,6 +106,33 @@ public:
         }
     }
 
+    // Restart from a previous run (the reference's do_restore_proposal / do_restore_variables switches; the values come from
+    // its three restore files, tamcmc-c_b200/formats.py:read_restore).
+    // MALA::restore_proposal (MALA.cpp:191-246): scale, mean and covariance of every chain's proposal law.
+    void restore_proposal(const double* sigma_in /*[Nchains]*/, const double* mu_in /*[Nchains][Nvars]*/,
+                          const double* covarmat_in /*[Nchains][Nvars][Nvars]*/)
+    {
+        std::copy(sigma_in, sigma_in + Nchains, sigma.begin());
+        std::copy(mu_in, mu_in + (size_t)Nchains * Nvars, mu.begin());
+        std::copy(covarmat_in, covarmat_in + (size_t)Nchains * Nvars * Nvars, covarmat.begin());
+        if (!chol_dirty.empty()) chol_dirty.assign((size_t)Nchains, 1);       // every factor is stale; prepared draws get it re-applied
+    }
+    // Chain positions of a previous run (Model_def constructed on the restored vars, model_def.cpp:142-147): priors and
+    // likelihoods are evaluated again at the restored position.
+    void restore_variables(const double* vars_in /*[Nchains][Nvars]*/)
+    {
+        std::copy(vars_in, vars_in + (size_t)Nchains * Nvars, vars.begin());
+        for (int m = 0; m < Nchains; m++) {
+            for (int v = 0; v < Nvars; v++) params[(size_t)m * stride + index_to_relax[v]] = vars[(size_t)m * Nvars + v];
+            logPrior[m] = prior(&params[(size_t)m * stride]);
+            active[m] = std::isinf(logPrior[m]) ? 0 : 1;
+        }
+        prop_params = params; prop_vars = vars;
+        eval(params.data(), active.data(), logLikelihood.data());
+        n_eval_calls++;
+        set_initial_logL(logLikelihood.data());
+    }
+
     // buffers of the two-phase interface (propose -> caller evaluates -> finish)
     const double* proposal_params() const { return prop_params.data(); }
     const unsigned char* active_mask() const { return active.data(); }
