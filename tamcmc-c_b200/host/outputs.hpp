@@ -9,6 +9,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <string>
 #include <vector>
@@ -85,6 +86,79 @@ inline int write_params(const std::string& prefix, const ParamsMeta& m, const do
             f.write(reinterpret_cast<const char*>(vars + ((size_t)i * m.Nchains + c) * nv), (std::streamsize)(nv * sizeof(double)));
         f.flush();
         if (!f.good()) return -3;
+    }
+    return 0;
+}
+
+// ---- restore files (Outputs::write_buffer_restore, outputs.cpp:863-1027): <dir>/<id>_restore_<phase>_{1,2,3}.dat ----
+// What Driver::restore_variables / restore_proposal need, with the reference's names.  `*_mean` are the averages over the last
+// buffer (do_restore_proposal_mean, MALA.cpp:206-224).
+struct RestoreState {
+    int Nchains = 0, Nvars = 0;
+    long iteration = 0;
+    std::vector<std::string> variable_names;
+    std::vector<double> vars, vars_mean;             // [Nchains][Nvars]
+    std::vector<double> sigmas, sigmas_mean;         // [Nchains]
+    std::vector<double> mus, mus_mean;               // [Nchains][Nvars]
+    std::vector<double> covarmats, covarmats_mean;   // [Nchains][Nvars][Nvars]
+};
+
+// Parses ONE restore file into `st` (keys it does not hold are left alone).  0 on success, <0 when the file cannot be opened or
+// a block does not have the size the header announces.
+inline int read_restore_file(const std::string& path, RestoreState& st)
+{
+    std::ifstream f(path.c_str());
+    if (!f.is_open()) return -1;
+    auto numbers = [](const std::string& s, std::vector<double>& out) {
+        const char* p = s.c_str();
+        char* e = nullptr;
+        for (;;) { const double v = std::strtod(p, &e); if (e == p) break; out.push_back(v); p = e; }
+    };
+    std::vector<double>* cur = nullptr;
+    std::string line;
+    while (std::getline(f, line)) {
+        const size_t b = line.find_first_not_of(" \t\r");
+        if (b == std::string::npos || line[b] == '#') continue;
+        if (line[b] == '!') {
+            const size_t eq = line.find('=', b);
+            if (eq == std::string::npos) continue;
+            std::string key = line.substr(b + 1, eq - b - 1);
+            key.erase(0, key.find_first_not_of(' ')); key.erase(key.find_last_not_of(' ') + 1);
+            const std::string val = line.substr(eq + 1);
+            cur = nullptr;
+            if (key == "Nchains") st.Nchains = std::atoi(val.c_str());
+            else if (key == "Nvars") st.Nvars = std::atoi(val.c_str());
+            else if (key == "iteration") st.iteration = std::atol(val.c_str());
+            else if (key == "variable_names") {
+                st.variable_names.clear();
+                size_t p = 0;
+                while ((p = val.find_first_not_of(' ', p)) != std::string::npos) { const size_t q = val.find(' ', p); st.variable_names.push_back(val.substr(p, q - p)); if (q == std::string::npos) break; p = q; }
+            }
+            else if (key == "vars") cur = &st.vars;
+            else if (key == "vars_mean") cur = &st.vars_mean;
+            else if (key == "sigmas") cur = &st.sigmas;
+            else if (key == "sigmas_mean") cur = &st.sigmas_mean;
+            else if (key == "mus") cur = &st.mus;
+            else if (key == "mus_mean") cur = &st.mus_mean;
+            else if (key == "covarmats") cur = &st.covarmats;
+            else if (key == "covarmats_mean") cur = &st.covarmats_mean;
+            if (cur) { cur->clear(); numbers(val, *cur); }
+        } else if (line[b] == '*') {
+            continue;                                      // chain marker of a covariance block: the rows follow in chain order
+        } else if (cur) numbers(line, *cur);
+    }
+    const size_t nc = (size_t)st.Nchains, nv = (size_t)st.Nvars;
+    auto ok = [](const std::vector<double>& v, size_t n) { return v.empty() || v.size() == n; };
+    if (!ok(st.vars, nc * nv) || !ok(st.vars_mean, nc * nv) || !ok(st.sigmas, nc) || !ok(st.sigmas_mean, nc) || !ok(st.mus, nc * nv) ||
+        !ok(st.mus_mean, nc * nv) || !ok(st.covarmats, nc * nv * nv) || !ok(st.covarmats_mean, nc * nv * nv)) return -2;
+    return 0;
+}
+
+inline int read_restore(const std::string& dir, const std::string& star_id, const std::string& phase, RestoreState& st)
+{
+    for (int n = 1; n <= 3; n++) {
+        const int rc = read_restore_file(dir + "/" + star_id + "_restore_" + phase + "_" + std::to_string(n) + ".dat", st);
+        if (rc) return rc;
     }
     return 0;
 }

@@ -2,6 +2,7 @@
 // Gaussian-envelope run (metadata on the command line side is fixed here) and two buffers of synthetic samples.
 //   usage: test_outputs <prefix>
 #include <cstdio>
+#include <string>
 #include <vector>
 
 #include "../../tamcmc-c_b200/host/outputs.hpp"
@@ -9,6 +10,16 @@
 int main(int argc, char** argv)
 {
     if (argc < 2) return 2;
+    if (argc >= 5 && std::string(argv[1]) == "restore") {
+        // test_outputs restore <dir> <star_id> <phase>: prints what read_restore found, 17 significant digits per value
+        tamcmc::outputs::RestoreState st;
+        const int rc = tamcmc::outputs::read_restore(argv[2], argv[3], argv[4], st);
+        std::printf("rc %d Nchains %d Nvars %d iteration %ld names %zu last %s\n", rc, st.Nchains, st.Nvars, st.iteration, st.variable_names.size(),
+                    st.variable_names.empty() ? "" : st.variable_names.back().c_str());
+        const std::vector<double>* all[8] = {&st.vars, &st.vars_mean, &st.sigmas, &st.sigmas_mean, &st.mus, &st.mus_mean, &st.covarmats, &st.covarmats_mean};
+        for (const auto* v : all) { std::printf("%zu", v->size()); for (double x : *v) std::printf(" %.17g", x); std::printf("\n"); }
+        return rc ? 1 : 0;
+    }
     tamcmc::outputs::ParamsMeta m;
     m.Nsamples = 100000; m.Nchains = 4;
     m.relax = {1, 1, 0, 1, 1, 1, 1, 1, 1, 1};

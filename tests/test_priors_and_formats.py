@@ -243,3 +243,22 @@ def test_restore_writer_reproduces_the_reference_data_lines(pkg, tmp_path):
     fmt.write_restore(str(out), "star", st, phase="L")
     st2 = fmt.read_restore(str(out), "star", phase="L")
     assert all(np.array_equal(st[k], st2[k]) for k in ("vars", "vars_mean", "sigmas", "mus", "covarmats", "covarmats_mean"))
+
+
+def test_cpp_restore_reader_agrees_with_python(pkg, tmp_path):
+    """host/outputs.hpp:read_restore on the reference's own restore files: same state as formats.read_restore, value for value."""
+    exe, src = os.path.join(HERE, "cpp", "test_outputs"), os.path.join(HERE, "cpp", "test_outputs.cpp")
+    hdr = os.path.join(HERE, "..", "tamcmc-c_b200", "host", "outputs.hpp")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", exe, src])
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_outputs_10280410.json")))
+    for n in (1, 2, 3):
+        (tmp_path / ("10280410_Gaussfit_restore_A_%d.dat" % n)).write_text(gold["restore"][str(n)])
+    st = pkg.formats.read_restore(str(tmp_path), "10280410_Gaussfit")
+    r = subprocess.run([exe, "restore", str(tmp_path), "10280410_Gaussfit", "A"], stdout=subprocess.PIPE, text=True, check=True)
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "rc 0 Nchains 4 Nvars 9 iteration 99999 names 9 last Gauss_sigma"
+    for line, key in zip(lines[1:], ("vars", "vars_mean", "sigmas", "sigmas_mean", "mus", "mus_mean", "covarmats", "covarmats_mean")):
+        vals = np.array([float(t) for t in line.split()[1:]])
+        assert int(line.split()[0]) == st[key].size and np.array_equal(vals, st[key].ravel()), key
+    assert subprocess.run([exe, "restore", str(tmp_path), "missing", "A"], stdout=subprocess.PIPE).returncode == 1
