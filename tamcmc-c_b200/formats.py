@@ -7,6 +7,7 @@ the "simple matrix" `.model` file of the Gaussian-envelope fits (model_Harvey_Ga
            parameter, '! prior names', then up to four rows of prior parameters (-9999 = unused slot)
            -- Config::read_inputs_prior_Simple_Matrix (config.cpp:560-660)
 
+  .cfg   : '!Group:' headers, `key=value; free text` lines (Config::read_cfg_file / format_line, config.cpp:1062-1110, 1223-1500)
   outputs: <prefix>.hdr + <prefix>_chain-<k>.bin, the binary chain files of Outputs::write_bin_params (outputs.cpp:1231-1334)
 
 Host-side I/O only: nothing here is on the GPU path."""
@@ -272,3 +273,62 @@ def write_restore(directory, star_id, state, phase="A"):
     for n, text in restore_texts(state).items():
         with open(os.path.join(directory, "%s_restore_%s_%d.dat" % (star_id, phase, n)), "w") as f:
             f.write(text)
+
+
+# ------------------------------------------------------------------------------------------------
+# The .cfg control file (Config::read_cfg_file / format_line, tamcmc/sources/config.cpp:1062-1110, 1223-1500):
+#   '!Group:' opens a group, '#' starts a comment line, every other line is `key=value; free text` -- the value ends at the
+#   FIRST ';' (a line without one is an error in the reference), numbers are read with strtod semantics (leading number,
+#   trailing text ignored: `lambda_temp=3.50 #1.70;` is 3.5), lists are comma separated.
+# ------------------------------------------------------------------------------------------------
+import re as _re
+
+_NUM = _re.compile(r"\s*([-+]?(?:\d+\.?\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?))")
+
+
+def cfg_number(raw):
+    m = _NUM.match(raw)
+    if not m:
+        raise ValueError("no number at the start of %r" % raw)
+    return float(m.group(1))
+
+
+def cfg_list(raw):
+    return [cfg_number(t) for t in raw.split(",") if t.strip()]
+
+
+def read_cfg(path):
+    """-> {group: {key: raw value string}} with the reference's line rules; later duplicates of a key win, as they do when the
+    reference assigns keyword after keyword."""
+    groups, cur = {}, None
+    with open(path) as f:
+        for n, line in enumerate(f, 1):
+            s = line.strip()
+            if not s or s[0] == "#":
+                continue
+            if s[0] == "!":
+                cur = groups.setdefault(s[1:].split(":")[0].strip(), {})
+                continue
+            if s == "/END":
+                break
+            if ";" not in s:
+                raise ValueError("%s:%d: no ';' terminates the value (config.cpp:1090-1096)" % (path, n))
+            body = s[: s.index(";")].strip()
+            if "=" not in body or cur is None:
+                continue
+            key, _, val = body.partition("=")
+            cur[key.strip()] = val.strip()
+    return groups
+
+
+def mala_config(groups):
+    """The !MALA group with the field names of tamcmc::DriverConfig (host/mcmc_driver.hpp); `epsilon2` is the reference's
+    MALA.epsi2 (config.cpp:1276-1279)."""
+    g = groups["MALA"]
+    out = {"Nchains": int(cfg_number(g["Nchains"])), "lambda_temp": cfg_number(g["lambda_temp"]), "c0": cfg_number(g["c0"]),
+           "epsilon1": cfg_number(g["epsilon1"]), "epsi2": cfg_number(g["epsilon2"]), "A1": cfg_number(g["A1"]),
+           "target_acceptance": cfg_number(g["target_acceptance"]), "dN_mixing": int(cfg_number(g["dN_mixing"])),
+           "Nt_learn": [int(v) for v in cfg_list(g["Nt_learn"])], "periods_learn": [int(v) for v in cfg_list(g["periods_learn"])]}
+    if len(out["periods_learn"]) != len(out["Nt_learn"]) - 1:
+        raise ValueError("periods_learn must have one entry fewer than Nt_learn (config_default.cfg:18)")
+    return out

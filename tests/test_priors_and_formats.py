@@ -262,3 +262,40 @@ def test_cpp_restore_reader_agrees_with_python(pkg, tmp_path):
         vals = np.array([float(t) for t in line.split()[1:]])
         assert int(line.split()[0]) == st[key].size and np.array_equal(vals, st[key].ravel()), key
     assert subprocess.run([exe, "restore", str(tmp_path), "missing", "A"], stdout=subprocess.PIPE).returncode == 1
+
+
+def test_cfg_reader(pkg, tmp_path):
+    """read_cfg / mala_config follow Config::format_line and read_cfg_file (config.cpp:1062-1110, 1223-1300): value up to the
+    first ';', strtod-style numbers, comma lists, '#' comment lines, '!Group:' headers.  The values of the reference's shipped
+    config_default.cfg as read by the same code are in tests/golden/reference_cfg_default.json (make_golden_cfg.py)."""
+    fmt = pkg.formats
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_cfg_default.json")))
+    assert gold["MALA"] == {"Nchains": 5, "lambda_temp": 3.5, "c0": 10.0, "epsilon1": 1e-12, "epsi2": 1e-12, "A1": 1e14,
+                            "target_acceptance": 0.234, "dN_mixing": 1, "Nt_learn": [1000, 1500, 100000], "periods_learn": [1, 1]}
+    assert gold["Modeling"]["likelihood_fct_name"] == "chi(2,2p)" and gold["groups"] == ["Data", "Diagnostics", "MALA", "Modeling", "Outputs"]
+    sample = """# a control file in the reference's syntax
+!MALA:
+\ttarget_acceptance=0.234;
+\tc0=10;  Relaxation constrain. Important: adjust; empirically
+\tepsilon1=1e-12;  free text
+\tepsilon2=1e-10;
+\tA1=1e14;
+\tNt_learn=200, 400, 5000;   text
+\tperiods_learn=1, 2;
+ \t#Nchains=10;   commented out
+\tNchains=4;
+\tdN_mixing=1.;  trailing dot
+ \tlambda_temp=1.70 #3.50; the number ends where strtod stops
+!Data:
+\tysig_col=-1 //-1;  // text
+"""
+    p = tmp_path / "c.cfg"
+    p.write_text(sample)
+    g = fmt.read_cfg(str(p))
+    m = fmt.mala_config(g)
+    assert m == {"Nchains": 4, "lambda_temp": 1.7, "c0": 10.0, "epsilon1": 1e-12, "epsi2": 1e-10, "A1": 1e14, "target_acceptance": 0.234,
+                 "dN_mixing": 1, "Nt_learn": [200, 400, 5000], "periods_learn": [1, 2]}
+    assert fmt.cfg_number(g["Data"]["ysig_col"]) == -1
+    p.write_text("!MALA:\n\tc0=10\n")
+    with pytest.raises(ValueError):
+        fmt.read_cfg(str(p))
