@@ -36,7 +36,8 @@ namespace tamcmc {
 struct DriverConfig {
     int Nchains = 10;
     double lambda_temp = 1.7;                 // Tcoefs[m] = lambda^m
-    double c0 = 10.0, epsilon1 = 1e-12, epsi2 = 1e-10, A1 = 1e14, target_acceptance = 0.234;   // config_default.cfg:11-16
+    double c0 = 10.0, epsilon1 = 1e-12, epsi2 = 1e-10, A1 = 1e14, target_acceptance = 0.234;   // config_default.cfg:11-16 (the shipped
+                                              // file has epsilon2 = 1e-12; formats.py:mala_config reads a run's own values)
     std::vector<long> Nt_learn = {1000, 1500, 100000};       // config_default.cfg:17
     std::vector<long> periods_learn = {1, 1};                 // config_default.cfg:18
     long dN_mixing = 1;                                       // config_default.cfg:28
