@@ -296,6 +296,20 @@ def test_cfg_reader(pkg, tmp_path):
     assert m == {"Nchains": 4, "lambda_temp": 1.7, "c0": 10.0, "epsilon1": 1e-12, "epsi2": 1e-10, "A1": 1e14, "target_acceptance": 0.234,
                  "dN_mixing": 1, "Nt_learn": [200, 400, 5000], "periods_learn": [1, 2]}
     assert fmt.cfg_number(g["Data"]["ysig_col"]) == -1
+    # the C++ reader of the driver side (host/config.hpp) on the same file
+    exe, src = os.path.join(HERE, "cpp", "test_config"), os.path.join(HERE, "cpp", "test_config.cpp")
+    hdrs = [os.path.join(HERE, "..", "tamcmc-c_b200", "host", h) for h in ("config.hpp", "mcmc_driver.hpp")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-fopenmp", "-o", exe, src])
+    r = subprocess.run([exe, str(p)], stdout=subprocess.PIPE, text=True, check=True)
+    t = r.stdout.split()
+    got = {t[i]: t[i + 1] for i in range(0, t.index("Nt_learn"), 2)}
+    assert got["ok"] == "1" and got["groups"] == "2" and int(got["Nchains"]) == m["Nchains"] and int(got["dN_mixing"]) == m["dN_mixing"]
+    for k in ("lambda_temp", "c0", "epsilon1", "epsi2", "A1", "target_acceptance"):
+        assert float(got[k]) == m[k], k
+    assert [int(v) for v in t[t.index("Nt_learn") + 1:t.index("periods_learn")]] == m["Nt_learn"]
+    assert [int(v) for v in t[t.index("periods_learn") + 1:]] == m["periods_learn"]
     p.write_text("!MALA:\n\tc0=10\n")
     with pytest.raises(ValueError):
         fmt.read_cfg(str(p))
+    assert subprocess.run([exe, str(p)], stdout=subprocess.PIPE, text=True).stdout.strip() == "rc 2"
