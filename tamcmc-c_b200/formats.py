@@ -332,3 +332,92 @@ def mala_config(groups):
     if len(out["periods_learn"]) != len(out["Nt_learn"]) - 1:
         raise ValueError("periods_learn must have one entry fewer than Nt_learn (config_default.cfg:18)")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# The MS_Global `.model` file, PARSE STAGE ONLY (read_MCMC_file_MS_Global, tamcmc/sources/io_ms_global.cpp:27-360): the file
+# into the fields of the reference's MCMC_files structure.  Turning those into the parameter vector / plength / priors
+# (build_init_MS_Global, io_ms_global.cpp:362-1400) stays in the reference.
+# The reference walks the file by counting lines that start with '#':
+#   up to the 3rd '#'   header ('#KIC=' id, '! Dnu', '!! C_l', '!n numax [err]', '* fmin fmax') and the mode table
+#                       `p|g|co  l  frequency  [relax_f relax_H relax_W]` (missing flags default to 1)
+#   to the next '#'     hyper priors (the line right after the 3rd '#' is skipped unread -- in the shipped files that is the
+#                       '# Extra parameters (obselete)' label, so the "extra parameters" column lands in hyper_priors)
+#   then, '#' to '#':   eigen-solution table [n, 6], noise parameters (flattened, right-aligned in 10 slots, -1 fill),
+#                       noise_s2 [<=10, 3] (right-aligned in 10 rows, -1 fill), and to the end of the file the common
+#                       parameters `name  prior_or_switch  values...` (up to 5 values, -9999 fill)
+# ------------------------------------------------------------------------------------------------
+def read_ms_global_model(path):
+    with open(path) as f:
+        lines = [l.strip() for l in f.read().splitlines()]
+    out = {"ID": None, "Dnu": None, "C_l": None, "numax": -9999.0, "err_numax": -9999.0, "freq_range": None,
+           "param_type": [], "els": [], "freqs_ref": [], "relax_freq": [], "relax_H": [], "relax_gamma": []}
+    i, nhash = 0, 0
+    while nhash < 3 and i < len(lines):
+        s = lines[i]
+        i += 1
+        if not s:
+            continue
+        if s[0] == "#":
+            nhash += 1
+            if s[1:2] == "K":
+                out["ID"] = s.replace("=", " ").split()[1]
+        elif s[0] == "!":
+            w = s.split()
+            if s[1:2] == "!":
+                out["C_l"] = float(w[1])
+            elif s[1:2] == "n":
+                out["numax"] = float(w[1])
+                if len(w) == 3:
+                    out["err_numax"] = float(w[2])
+            else:
+                out["Dnu"] = float(w[1])
+        elif s[0] == "*":
+            if out["freq_range"] is not None:
+                raise ValueError("two frequency ranges (io_ms_global.cpp: only one '*' line is allowed)")
+            w = s.split()
+            out["freq_range"] = (float(w[1]), float(w[2]))
+        else:
+            w = s.split()
+            if w[0] not in ("p", "g", "co"):
+                raise ValueError("mode line must start with p, g or co: %r" % s)
+            out["param_type"].append(w[0]); out["els"].append(int(w[1])); out["freqs_ref"].append(float(w[2]))
+            flags = [bool(int(float(t))) for t in w[3:6]] + [True] * (3 - len(w[3:6]))
+            out["relax_freq"].append(flags[0]); out["relax_H"].append(flags[1]); out["relax_gamma"].append(flags[2])
+    i += 1                                         # the reference's second loop reads a line before it looks at one
+
+    def block(i):
+        rows = []
+        while i < len(lines):
+            s = lines[i]
+            i += 1
+            if s and s[0] == "#":
+                break
+            if s:
+                rows.append(s.split())
+        return rows, i
+
+    rows, i = block(i)
+    out["hyper_priors"] = np.array([[float(r[0])] + [float(t) for t in r[2:]] for r in rows], dtype=np.float64) if rows else np.zeros((0, 1))
+    rows, i = block(i)
+    out["eigen_params"] = np.array([[float(t) for t in r] for r in rows], dtype=np.float64).reshape(-1, 6)
+    rows, i = block(i)
+    flat = [float(t) for r in rows for t in r]
+    out["noise_params"] = np.array([-1.0] * (10 - len(flat)) + flat, dtype=np.float64)
+    rows, i = block(i)
+    s2 = np.full((10, 3), -1.0)
+    if rows:
+        s2[10 - len(rows):] = [[float(t) for t in r] for r in rows]
+    out["noise_s2"] = s2
+    rows, i = block(i)
+    out["common_names"] = [r[0] for r in rows]
+    out["common_names_priors"] = [r[1] for r in rows]
+    mc = np.full((len(rows), 5), -9999.0)
+    for k, r in enumerate(rows):
+        vals = [float(t) for t in r[2:7]]
+        mc[k, :len(vals)] = vals
+    out["modes_common"] = mc
+    for k in ("els",):
+        out[k] = np.array(out[k], dtype=np.int64)
+    out["freqs_ref"] = np.array(out["freqs_ref"], dtype=np.float64)
+    return out

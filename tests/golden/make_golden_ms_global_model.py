@@ -1,0 +1,29 @@
+"""Golden vector for formats.read_ms_global_model: the reference's own ajAlm test input (a 118-line .model data file) and the
+facts a reader must get out of it, asserted here against the file.  Run in the build container (needs /root/reference):
+    python tests/golden/make_golden_ms_global_model.py"""
+import importlib.util
+import json
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = "/root/reference/test/inputs/kplr003427720_kasoc-psd_slc_v1_ajAlm_gate.model"
+spec = importlib.util.spec_from_file_location("formats", os.path.join(HERE, "..", "..", "tamcmc-c_b200", "formats.py"))
+fmt = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(fmt)
+m = fmt.read_ms_global_model(SRC)
+text = open(SRC).read()
+# facts read off the file by eye ("33 modes l<=2", mode list at .model:6-38)
+assert m["ID"] == "003427720" and m["Dnu"] == 119.557 and m["C_l"] == 55.0616 and m["freq_range"] == (1434.684, 3706.267)
+assert len(m["els"]) == 33 and [int((m["els"] == l).sum()) for l in (0, 1, 2)] == [11, 11, 11]
+assert m["freqs_ref"][0] == 1969.8199 and m["freqs_ref"][-1] == 3157.25 and all(m["relax_freq"]) and set(m["param_type"]) == {"p"}
+assert m["hyper_priors"].shape == (5, 1) and not m["hyper_priors"].any()
+assert m["eigen_params"].shape == (33, 6) and m["eigen_params"][0].tolist() == [0, 1969.81995, 1965.20764, 1972.13269, 1.24707, 0.36161]
+assert m["noise_params"].tolist() == [0, 0, 1, 5.446283e-31, 420.20987, 4, 24.214348, 9.9205704, 2, 1.2831577]
+assert m["noise_s2"].shape == (10, 3) and m["noise_s2"][3, 2] == float("inf") and m["noise_s2"][9].tolist() == [1.2831577, 0.0059365905, 0.0059641842]
+assert m["common_names"][0] == "model_fullname" and m["common_names_priors"][0] == "model_MS_Global_ajAlm_HarveyLike"
+assert m["common_names"][-1] == "trunc_c" and m["modes_common"][-1].tolist() == [30.0, -9999, -9999, -9999, -9999]
+k = m["common_names"].index("epsilon_0")
+assert m["common_names_priors"][k] == "Jeffreys" and m["modes_common"][k].tolist() == [0.005, 0.001, 0.01, -9999, -9999]
+json.dump({"source": SRC.replace("/root/reference/", ""), "text": text, "n_common": len(m["common_names"])},
+          open(os.path.join(HERE, "reference_ms_global_model.json"), "w"), indent=1)
+print("ok", len(m["common_names"]), m["common_names"])

@@ -313,3 +313,35 @@ def test_cfg_reader(pkg, tmp_path):
     with pytest.raises(ValueError):
         fmt.read_cfg(str(p))
     assert subprocess.run([exe, str(p)], stdout=subprocess.PIPE, text=True).stdout.strip() == "rc 2"
+
+
+def test_ms_global_model_parse_stage(pkg, tmp_path):
+    """read_ms_global_model follows read_MCMC_file_MS_Global (io_ms_global.cpp:27-360) into the fields of MCMC_files, on the
+    reference's own ajAlm test input (tests/golden/reference_ms_global_model.json, make_golden_ms_global_model.py)."""
+    fmt = pkg.formats
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_ms_global_model.json")))
+    p = tmp_path / "star.model"
+    p.write_text(gold["text"])
+    m = fmt.read_ms_global_model(str(p))
+    assert m["ID"] == "003427720" and m["Dnu"] == 119.557 and m["C_l"] == 55.0616 and m["freq_range"] == (1434.684, 3706.267)
+    assert m["numax"] == -9999.0 and len(m["els"]) == 33 and [int((m["els"] == l).sum()) for l in (0, 1, 2)] == [11, 11, 11]
+    assert m["freqs_ref"][0] == 1969.8199 and m["freqs_ref"][-1] == 3157.25 and all(m["relax_H"]) and all(m["relax_gamma"])
+    assert m["hyper_priors"].shape == (5, 1)                      # the "extra parameters" column (the label line is skipped unread)
+    assert m["eigen_params"].shape == (33, 6) and np.array_equal(m["eigen_params"][:, 0], m["els"])
+    assert np.allclose(m["eigen_params"][:, 1], m["freqs_ref"], rtol=0, atol=2e-4)
+    assert m["noise_params"].tolist() == [0, 0, 1, 5.446283e-31, 420.20987, 4, 24.214348, 9.9205704, 2, 1.2831577]
+    assert np.array_equal(m["noise_s2"][:, 0], m["noise_params"]) and np.isinf(m["noise_s2"][3, 2])
+    assert len(m["common_names"]) == gold["n_common"] == 22 and m["common_names_priors"][0] == "model_MS_Global_ajAlm_HarveyLike"
+    k = m["common_names"].index("Visibility_l2")
+    assert m["common_names_priors"][k] == "Gaussian" and m["modes_common"][k].tolist() == [0.53, 0.53, 0.03, -9999, -9999]
+    assert m["modes_common"][m["common_names"].index("trunc_c"), 0] == 30.0
+    # a short file: numax line, missing relax flags, fewer noise rows (right-aligned, -1 fill), a second '*' line is an error
+    short = "#KIC =1\n!n 100.5 2.5\n! 10.0\n!! 1.5\n* 50 150\n# type\np 0 90.0\ng 1 95.5 0\n# hyper priors\n# extra\n# eigen\n 0 90 89 91 0.1 1\n# noise\n 1 2 3\n 0.5\n# s2\n 1 0 0\n# common\n trunc_c Fix 20\n"
+    p.write_text(short)
+    m = fmt.read_ms_global_model(str(p))
+    assert m["numax"] == 100.5 and m["err_numax"] == 2.5 and m["param_type"] == ["p", "g"] and m["relax_freq"] == [True, False] and m["relax_H"] == [True, True]
+    assert m["noise_params"].tolist() == [-1] * 6 + [1, 2, 3, 0.5] and m["noise_s2"][9].tolist() == [1, 0, 0] and m["noise_s2"][8, 0] == -1
+    assert m["hyper_priors"].shape[0] == 0 and m["common_names"] == ["trunc_c"]
+    p.write_text(short.replace("# type", "* 1 2\n# type"))
+    with pytest.raises(ValueError):
+        fmt.read_ms_global_model(str(p))
