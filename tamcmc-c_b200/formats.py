@@ -336,7 +336,9 @@ def mala_config(groups):
 
 # ------------------------------------------------------------------------------------------------
 # The MS_Global `.model` file, PARSE STAGE ONLY (read_MCMC_file_MS_Global, tamcmc/sources/io_ms_global.cpp:27-360): the file
-# into the fields of the reference's MCMC_files structure.  Turning those into the parameter vector / plength / priors
+# into the fields of the reference's MCMC_files structure.  The red-giant (asymptotic) dialect goes through the same reader
+# (read_MCMC_file_asymptotic, io_asymptotic.cpp:27-29); there the hyper-prior rows `value  prior  params...` hold the l=1
+# frequency priors of model_RGB_asympt_aj_AppWidth_HarveyLike_v4.  Turning those into the parameter vector / plength / priors
 # (build_init_MS_Global, io_ms_global.cpp:362-1400) stays in the reference.
 # The reference walks the file by counting lines that start with '#':
 #   up to the 3rd '#'   header ('#KIC=' id, '! Dnu', '!! C_l', '!n numax [err]', '* fmin fmax') and the mode table
@@ -399,6 +401,7 @@ def read_ms_global_model(path):
 
     rows, i = block(i)
     out["hyper_priors"] = np.array([[float(r[0])] + [float(t) for t in r[2:]] for r in rows], dtype=np.float64) if rows else np.zeros((0, 1))
+    out["hyper_priors_names"] = [r[1] for r in rows if len(r) > 1]       # io_ms_global.cpp:191-193
     rows, i = block(i)
     out["eigen_params"] = np.array([[float(t) for t in r] for r in rows], dtype=np.float64).reshape(-1, 6)
     rows, i = block(i)

@@ -27,3 +27,14 @@ assert m["common_names_priors"][k] == "Jeffreys" and m["modes_common"][k].tolist
 json.dump({"source": SRC.replace("/root/reference/", ""), "text": text, "n_common": len(m["common_names"])},
           open(os.path.join(HERE, "reference_ms_global_model.json"), "w"), indent=1)
 print("ok", len(m["common_names"]), m["common_names"])
+
+# ---- the red-giant dialect: same reader (read_MCMC_file_asymptotic -> read_MCMC_file_MS_Global), the reference's fixture 10722175
+SRC2 = "/root/reference/test/inputs/RGB/v1.86.0/10722175_nobias.model"
+r = fmt.read_ms_global_model(SRC2)
+assert r["ID"] == "010722175" and r["numax"] == 113.784460254 and r["err_numax"] == 0.220633701471 and r["Dnu"] == 9.54 and r["C_l"] == 1.2867
+assert r["freq_range"] == (80.0, 128.0) and r["els"].tolist() == [0] * 5 + [1] + [2] * 5 + [3] * 2
+assert r["hyper_priors"].shape == (16, 4) and r["hyper_priors"][0].tolist() == [92.2, 0, 0, 0.1] and set(r["hyper_priors_names"]) == {"Fix"}
+assert r["eigen_params"].shape == (12, 6) and r["eigen_params"][5].tolist() == [1, 100.0, -1, -1, -1, -1]
+json.dump({"source": SRC2.replace("/root/reference/", ""), "text": open(SRC2).read(), "n_common": len(r["common_names"]),
+           "common_names": r["common_names"]}, open(os.path.join(HERE, "reference_rgb_model.json"), "w"), indent=1)
+print("rgb ok", r["hyper_priors"].shape, r["eigen_params"].shape, len(r["common_names"]), r["common_names"][:6], r["noise_params"].tolist())

@@ -345,3 +345,25 @@ def test_ms_global_model_parse_stage(pkg, tmp_path):
     p.write_text(short.replace("# type", "* 1 2\n# type"))
     with pytest.raises(ValueError):
         fmt.read_ms_global_model(str(p))
+
+
+def test_rgb_model_file_goes_through_the_same_reader(pkg, tmp_path):
+    """read_MCMC_file_asymptotic is read_MCMC_file_MS_Global (io_asymptotic.cpp:27-29): the reference's red-giant fixture
+    10722175_nobias.model (tests/golden/reference_rgb_model.json) -- numax line, 16 hyper-prior rows `value prior params...`
+    for the l=1 frequencies, the l=1 placeholder row of the eigen table -- and the noise values agree with the parameter vector
+    the kernel-parity vectors of the same fixture were built with (reference_rgb_vectors.npz)."""
+    fmt = pkg.formats
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_rgb_model.json")))
+    p = tmp_path / "rgb.model"
+    p.write_text(gold["text"])
+    r = fmt.read_ms_global_model(str(p))
+    assert r["ID"] == "010722175" and r["numax"] == 113.784460254 and r["err_numax"] == 0.220633701471 and r["Dnu"] == 9.54
+    assert r["freq_range"] == (80.0, 128.0) and r["els"].tolist() == [0] * 5 + [1] + [2] * 5 + [3] * 2
+    assert r["hyper_priors"].shape == (16, 4) and r["hyper_priors"][0].tolist() == [92.2, 0, 0, 0.1] and r["hyper_priors_names"] == ["Fix"] * 16
+    assert np.all(np.diff(r["hyper_priors"][:, 0]) > 0)
+    assert r["eigen_params"].shape == (12, 6) and r["eigen_params"][5].tolist() == [1, 100.0, -1, -1, -1, -1]
+    assert r["common_names"] == gold["common_names"] and len(r["common_names"]) == gold["n_common"]
+    g = np.load(os.path.join(HERE, "golden", "reference_rgb_vectors.npz"))
+    pl, params = g["plength0"], g["params0"]
+    o, nn = int(pl[:8].sum()), int(pl[8])
+    assert nn == 10 and np.array_equal(r["noise_params"], params[o:o + nn])
