@@ -424,3 +424,35 @@ def read_ms_global_model(path):
         out[k] = np.array(out[k], dtype=np.int64)
     out["freqs_ref"] = np.array(out["freqs_ref"], dtype=np.float64)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Custom tabulated priors, `<input root>_<k>.priors` beside the .model file (Config::setup, config.cpp:196-260; read with the
+# same column reader as the spectra, read_data_ascii_Ncols): '#' comments, '!' labels, '*' units, then either two columns
+# (x, PDF: a 1-D table for the `Tabulated(p)` prior) or a grid whose first row holds the x values after a corner token
+# ('NA') and whose first column holds the y values (a 2-D table for `Tabulated_2d(p1,p2)`).
+# ------------------------------------------------------------------------------------------------
+def read_tabulated_prior(path):
+    """-> dict(labels, units, ndim, and for ndim == 1: x, pdf; for ndim == 2: x (first row), y (first column), pdf[len(y), len(x)])"""
+    labels, units, rows = [], [], []
+    with open(path) as f:
+        for line in f:
+            s = line.strip()
+            if not s or s[0] == "#":
+                continue
+            if s[0] == "!":
+                labels = s[1:].split()
+            elif s[0] == "*":
+                units = s[1:].split()
+            else:
+                rows.append(s.split())
+    if not rows:
+        raise ValueError("no table in %s" % path)
+    if len(rows[0]) == 2:
+        a = np.array([[float(t) for t in r] for r in rows], dtype=np.float64)
+        return {"labels": labels, "units": units, "ndim": 1, "x": a[:, 0].copy(), "pdf": a[:, 1].copy()}
+    x = np.array([float(t) for t in rows[0][1:]], dtype=np.float64)
+    body = np.array([[float(t) for t in r] for r in rows[1:]], dtype=np.float64)
+    if body.shape[1] != x.size + 1:
+        raise ValueError("2-D table: every row must hold the y value and one PDF value per x")
+    return {"labels": labels, "units": units, "ndim": 2, "x": x, "y": body[:, 0].copy(), "pdf": body[:, 1:].copy()}

@@ -38,3 +38,15 @@ assert r["eigen_params"].shape == (12, 6) and r["eigen_params"][5].tolist() == [
 json.dump({"source": SRC2.replace("/root/reference/", ""), "text": open(SRC2).read(), "n_common": len(r["common_names"]),
            "common_names": r["common_names"]}, open(os.path.join(HERE, "reference_rgb_model.json"), "w"), indent=1)
 print("rgb ok", r["hyper_priors"].shape, r["eigen_params"].shape, len(r["common_names"]), r["common_names"][:6], r["noise_params"].tolist())
+
+# ---- the two tabulated-prior tables shipped beside the ajAlm .model (tiny data files)
+tabs = {}
+for k in (0, 1):
+    pth = "/root/reference/test/inputs/kplr003427720_kasoc-psd_slc_v1_ajAlm_gate_%d.priors" % k
+    tabs[str(k)] = open(pth).read()
+t0, t1 = [fmt.read_tabulated_prior("/root/reference/test/inputs/kplr003427720_kasoc-psd_slc_v1_ajAlm_gate_%d.priors" % k) for k in (0, 1)]
+assert t0["ndim"] == 1 and t0["labels"] == ["a1", "PDF"] and t0["x"].tolist() == [0, .1, .2, .3, .4, .5, .6, .7] and t0["pdf"].tolist() == [.001, .1, .2, .4, .2, .1, .05, 0]
+assert t1["ndim"] == 2 and t1["labels"] == ["a1", "Inclination", "PDF"] and t1["y"].tolist() == [0, 20, 40, 50, 60, 70, 80, 90]
+assert t1["x"].size == 10 and t1["pdf"].shape == (8, 10) and t1["pdf"][3, 2] == 0.511 and t1["pdf"][7, 4] == 0.03
+json.dump(tabs, open(os.path.join(HERE, "reference_tabulated_priors.json"), "w"), indent=1)
+print("tabulated ok")

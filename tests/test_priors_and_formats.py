@@ -367,3 +367,20 @@ def test_rgb_model_file_goes_through_the_same_reader(pkg, tmp_path):
     pl, params = g["plength0"], g["params0"]
     o, nn = int(pl[:8].sum()), int(pl[8])
     assert nn == 10 and np.array_equal(r["noise_params"], params[o:o + nn])
+
+
+def test_tabulated_prior_tables(pkg, tmp_path):
+    """The `.priors` tables the reference ships beside its ajAlm .model (config.cpp:196-260): a 1-D PDF of a1 and a 2-D PDF of
+    (a1, inclination).  Texts in tests/golden/reference_tabulated_priors.json (make_golden_ms_global_model.py)."""
+    fmt = pkg.formats
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_tabulated_priors.json")))
+    for k in ("0", "1"):
+        (tmp_path / (k + ".priors")).write_text(gold[k])
+    t0, t1 = fmt.read_tabulated_prior(str(tmp_path / "0.priors")), fmt.read_tabulated_prior(str(tmp_path / "1.priors"))
+    assert t0["ndim"] == 1 and t0["labels"] == ["a1", "PDF"] and t0["units"] == ["(microHz)", "(no_unit)"]
+    assert t0["x"].tolist() == [0, .1, .2, .3, .4, .5, .6, .7] and t0["pdf"].tolist() == [.001, .1, .2, .4, .2, .1, .05, 0]
+    assert t1["ndim"] == 2 and t1["labels"] == ["a1", "Inclination", "PDF"] and t1["y"].tolist() == [0, 20, 40, 50, 60, 70, 80, 90]
+    assert np.allclose(t1["x"], np.arange(10) / 10) and t1["pdf"].shape == (8, 10) and t1["pdf"][3, 2] == 0.511 and t1["pdf"][7, 4] == 0.03
+    (tmp_path / "bad.priors").write_text("! a b c\nNA 1 2\n10 0.1\n")
+    with pytest.raises(ValueError):
+        fmt.read_tabulated_prior(str(tmp_path / "bad.priors"))
