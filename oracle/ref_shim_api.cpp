@@ -219,6 +219,12 @@ double ref_logP(int kind, double a, double b, double c, double d, double x)
     return 0.0;
 }
 
+// 1-D tabulated prior (switch value 11), stats_dictionary.cpp:252-291
+double ref_logP_tabulated(const double* tab_x, const double* tab_y, int n, double x, int normalise)
+{
+    return (double)logP_tabulated(vec(tab_x, n), vec(tab_y, n), x, normalise != 0);
+}
+
 // which = -1: apply_generic_priors; 0 / 1: priors_Kallinger2014_Gaussian / priors_Harvey_Gaussian (priors_calc.cpp:725, 649, 631).
 // pri = [4][n] row-major (the reference's MatrixXd priors_params(4, n)), kinds = priors_names_switch.
 double ref_priors(int which, const double* params, int n, const double* pri, const int* kinds)

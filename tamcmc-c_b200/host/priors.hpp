@@ -159,5 +159,34 @@ inline long double priors_Kallinger2014_Gaussian(const double* params, const Gen
     return f;
 }
 
+// 1-D tabulated prior (switch value 11), logP_tabulated (stats_dictionary.cpp:252-291) on a table read by
+// formats.read_tabulated_prior / the reference's `.priors` files: linear interpolation of the PDF (interpol.cpp:13-43), a
+// negative interpolated value counts as 0, outside the table the reference returns numeric_limits<double>::lowest().  The flag
+// keeps the reference's meaning: normalise == false divides by the trapezoid area of the table, normalise == true divides by
+// C = 0 exactly as the reference does (log(P) - log(0) = +inf: the caller is expected to pass false).
+inline long double logP_tabulated(const double* tab_x, const double* tab_y, int n, long double x, bool normalise)
+{
+    double mn = tab_x[0], mx = tab_x[0];
+    for (int i = 1; i < n; i++) { mn = tab_x[i] < mn ? tab_x[i] : mn; mx = tab_x[i] > mx ? tab_x[i] : mx; }
+    if (x < mn || x > mx) return std::numeric_limits<double>::lowest();
+    // lin_interpol(tab_x, tab_y, x): the reference's function takes the abscissa as a double
+    const double xi = (double)x;
+    int i = 0;
+    double a = 0, b = 0;
+    if (xi >= tab_x[0] && xi <= tab_x[n - 1]) {
+        while ((xi < tab_x[i] || xi > tab_x[i + 1]) && i < n - 2) i = i + 1;
+        a = (tab_y[i + 1] - tab_y[i]) / (tab_x[i + 1] - tab_x[i]);
+        b = tab_y[i] - a * tab_x[i];
+    }
+    if (xi < tab_x[0]) { a = (tab_y[1] - tab_y[0]) / (tab_x[1] - tab_x[0]); b = tab_y[0] - a * tab_x[0]; }
+    if (xi > tab_x[n - 1]) { a = (tab_y[n - 1] - tab_y[n - 2]) / (tab_x[n - 1] - tab_x[n - 2]); b = tab_y[n - 2] - a * tab_x[n - 2]; }
+    long double P = a * xi + b;
+    if (P < 0) P = 0;
+    long double C = 0;
+    if (!normalise)
+        for (int k = 0; k + 1 < n; k++) { const double dy = (tab_y[k] + tab_y[k + 1]) / 2; const double dx = tab_x[k + 1] - tab_x[k]; C = C + dx * dy; }
+    return std::log(P) - std::log(C);
+}
+
 }  // namespace priors
 }  // namespace tamcmc

@@ -16,7 +16,16 @@ int main()
     std::string tag;
     while (std::cin >> tag) {
         long double r = 0;
-        if (tag == "P") {
+        if (tag == "T") {
+            // T n tab_x[n] tab_y[n] x normalise  -> logP_tabulated
+            int n, nrm; double x;
+            std::cin >> n;
+            std::vector<double> tx(n), ty(n);
+            for (auto& v : tx) std::cin >> v;
+            for (auto& v : ty) std::cin >> v;
+            std::cin >> x >> nrm;
+            r = logP_tabulated(tx.data(), ty.data(), n, x, nrm != 0);
+        } else if (tag == "P") {
             int kind; double a, b, c, d, x;
             std::cin >> kind >> a >> b >> c >> d >> x;
             GenericPriors g({kind}, {a}, {b}, {c}, {d});

@@ -384,3 +384,20 @@ def test_tabulated_prior_tables(pkg, tmp_path):
     (tmp_path / "bad.priors").write_text("! a b c\nNA 1 2\n10 0.1\n")
     with pytest.raises(ValueError):
         fmt.read_tabulated_prior(str(tmp_path / "bad.priors"))
+
+
+def test_tabulated_prior_matches_reference():
+    """priors.hpp:logP_tabulated against the reference's own logP_tabulated (stats_dictionary.cpp:252-291) on its shipped table and
+    an irregular one: in range, on the nodes, out of range (numeric_limits<double>::lowest()), negative interpolated values
+    (log 0 = -inf) and the normalise flag as the reference treats it (tests/golden/reference_tabulated_logp.json)."""
+    cases = json.load(open(os.path.join(HERE, "golden", "reference_tabulated_logp.json")))
+    lines = ["T %d %s %s %r %d" % (len(c["tab_x"]), " ".join(repr(v) for v in c["tab_x"]), " ".join(repr(v) for v in c["tab_y"]), c["x"], c["normalise"])
+             for c in cases]
+    r = subprocess.run([_build()], input="\n".join(lines) + "\n", stdout=subprocess.PIPE, text=True, check=True)
+    got = [float(t) for t in r.stdout.split()]
+    want = [float(c["value"]) for c in cases]
+    assert len(got) == len(want) > 200
+    bad = [(c["x"], c["normalise"], a, b) for c, a, b in zip(cases, got, want) if not (a == b or _same(a, b))]
+    assert not bad, bad[:3]
+    lowest = -1.7976931348623157e308
+    assert sum(1 for v in want if v == lowest) > 8 and sum(1 for v in want if np.isfinite(v) and v != lowest) > 80 and any(np.isinf(v) for v in want)
