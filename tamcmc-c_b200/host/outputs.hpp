@@ -154,6 +154,43 @@ inline int read_restore_file(const std::string& path, RestoreState& st)
     return 0;
 }
 
+// Writes the three restore files of `st` in the reference's layout (outputs.cpp:863-1027): every matrix row printed on its own
+// (Eigen's `.row(i)`: aligned per row, 6 significant digits).  0 on success, -1 when a file cannot be opened.
+inline int write_restore(const std::string& dir, const std::string& star_id, const std::string& phase, const RestoreState& st)
+{
+    const size_t nc = (size_t)st.Nchains, nv = (size_t)st.Nvars;
+    auto row = [&](const std::vector<double>& v, size_t off, size_t n) { return eigen_row(std::vector<double>(v.begin() + (long)off, v.begin() + (long)(off + n)), false) + "\n"; };
+    auto rows = [&](const std::vector<double>& v, size_t first, size_t nrows) { std::string t; for (size_t r = 0; r < nrows; r++) t += row(v, (first + r) * nv, nv); return t; };
+    auto head = [&](int n, const char* what, const char* a, const char* b) {
+        std::string t = "# This is an output file containing what is required to restore a run to its last saved position \n";
+        t += "# File number: " + std::to_string(n) + " \n" + what + "# Use this if you wish to: \n";
+        t += std::string("#       (1) complete a finished job that requires more samples ==> set erase_old_file=0 and ") + a + " \n";
+        t += std::string("#       (2) restart a finished job by ignoring old samples (e.g. ignoring a Burn-in) ==> set erase_old_file=1 and ") + b + " \n";
+        t += std::string("#       (3) terminate an unfinished job which failed to finished (e.g. due to computer unexpected shutdown) ==> set erase_old_file=0 and ") + a + " \n";
+        t += "! Nchains= " + std::to_string(st.Nchains) + "\n! Nvars= " + std::to_string(st.Nvars) + "\n! iteration=" + std::to_string(st.iteration) + "\n! variable_names=";
+        for (const auto& nm : st.variable_names) t += nm + "   ";
+        return t + "\n";
+    };
+    std::string t[3];
+    t[0] = head(1, "# Contains the last values for the variables vars[0:Nchain-1]. vars_mean denotes averaged values of Nbuffer \n", "do_restore_[X]=1", "do_restore_proposal=1")
+         + "! vars= \n" + rows(st.vars, 0, nc) + "! vars_mean= \n" + rows(st.vars_mean, 0, nc);
+    t[1] = head(2, "# Contains the last values of (a) sigmas[0:Nchains-1] and (b) mus[0:Nchains-1, 0:Nvars-1].  sigmas_mean and mus_mean denotes averaged values of Nbuffer\n", "do_restore=1", "do_restore=1")
+         + "! sigmas= " + eigen_row(st.sigmas, false) + "\n! mus= \n" + rows(st.mus, 0, nc)
+         + "! sigmas_mean= " + eigen_row(st.sigmas_mean, false) + "\n! mus_mean= \n" + rows(st.mus_mean, 0, nc);
+    t[2] = head(3, "# Contains the last value of the covariance matrix covarmats[0:Nchains-1, 0:Nvars-1, 0:Nvars-1]. covarmats_mean denotes the averaged values over Nbuffer\n", "do_restore=1", "do_restore=1");
+    for (int pass = 0; pass < 2; pass++) {
+        const std::vector<double>& C = pass ? st.covarmats_mean : st.covarmats;
+        t[2] += pass ? "! covarmats_mean= \n" : "! covarmats= \n";
+        for (size_t c = 0; c < nc; c++) t[2] += "*" + std::to_string(c) + "\n" + rows(C, c * nv, nv);
+    }
+    for (int n = 0; n < 3; n++) {
+        std::ofstream f((dir + "/" + star_id + "_restore_" + phase + "_" + std::to_string(n + 1) + ".dat").c_str());
+        if (!f.is_open()) return -1;
+        f << t[n];
+    }
+    return 0;
+}
+
 inline int read_restore(const std::string& dir, const std::string& star_id, const std::string& phase, RestoreState& st)
 {
     for (int n = 1; n <= 3; n++) {

@@ -6,8 +6,9 @@
 #include <vector>
 
 #include "../../tamcmc-c_b200/host/mcmc_driver.hpp"
+#include "../../tamcmc-c_b200/host/outputs.hpp"
 
-int main()
+int main(int argc, char** argv)
 {
     const int Nparams = 4, Nchains = 3;
     const std::vector<double> centre = {1.0, -2.0, 0.5, 3.0}, width = {0.5, 0.2, 1.0, 0.1};
@@ -53,5 +54,29 @@ int main()
     const double acc = (double)B.n_accept[0] / N;
     if (!(acc > 0.05 && acc < 0.7)) { std::printf("acceptance %.3f\n", acc); return 1; }
     std::printf("restored: identical state, acceptance(chain 0) %.3f\n", acc);
+    if (argc >= 2) {
+        // through the reference's restore files (6 significant digits): A's state -> write_restore -> read_restore -> driver C
+        namespace out = tamcmc::outputs;
+        out::RestoreState st;
+        st.Nchains = Nchains; st.Nvars = 3; st.iteration = 800; st.variable_names = {"p0", "p1", "p3"};
+        st.vars = st.vars_mean = A.vars; st.sigmas = st.sigmas_mean = A.sigma; st.mus = st.mus_mean = A.mu; st.covarmats = st.covarmats_mean = A.covarmat;
+        if (out::write_restore(argv[1], "star", "A", st)) { std::printf("write_restore failed\n"); return 1; }
+        out::RestoreState rd;
+        if (out::read_restore(argv[1], "star", "A", rd)) { std::printf("read_restore failed\n"); return 1; }
+        tamcmc::Driver Cd(cfgB, Nparams, Nparams, p0, relax, err, ev, flat);
+        Cd.restore_proposal(rd.sigmas.data(), rd.mus.data(), rd.covarmats.data());
+        Cd.restore_variables(rd.vars.data());
+        auto close = [](const std::vector<double>& a, const std::vector<double>& b) {
+            if (a.size() != b.size()) return false;
+            for (size_t i = 0; i < a.size(); i++) if (std::fabs(a[i] - b[i]) > 5e-6 * std::fabs(b[i]) + 1e-300) return false;      // %g keeps 6 digits
+            return true;
+        };
+        if (rd.iteration != 800 || rd.variable_names.size() != 3 || !close(Cd.vars, A.vars) || !close(Cd.sigma, A.sigma) || !close(Cd.mu, A.mu) || !close(Cd.covarmat, A.covarmat)) {
+            std::printf("state read back from the restore files differs\n"); return 1;
+        }
+        for (long i = 0; i < 500; i++) Cd.step(200000 + i);
+        for (int m = 0; m < Nchains; m++) if (!std::isfinite(Cd.logLikelihood[m])) { std::printf("non-finite likelihood after the restart\n"); return 1; }
+        std::printf("restart through the restore files: ok\n");
+    }
     return 0;
 }

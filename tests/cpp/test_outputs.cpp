@@ -18,6 +18,10 @@ int main(int argc, char** argv)
                     st.variable_names.empty() ? "" : st.variable_names.back().c_str());
         const std::vector<double>* all[8] = {&st.vars, &st.vars_mean, &st.sigmas, &st.sigmas_mean, &st.mus, &st.mus_mean, &st.covarmats, &st.covarmats_mean};
         for (const auto* v : all) { std::printf("%zu", v->size()); for (double x : *v) std::printf(" %.17g", x); std::printf("\n"); }
+        if (argc >= 6 && !rc) {
+            // ... and writes it back under <outdir> = argv[5] (round trip of write_restore)
+            if (tamcmc::outputs::write_restore(argv[5], argv[3], argv[4], st)) return 1;
+        }
         return rc ? 1 : 0;
     }
     tamcmc::outputs::ParamsMeta m;

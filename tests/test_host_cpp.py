@@ -132,11 +132,12 @@ def test_cpp_batch_driver_reproduces_single_star_chain(pkg, oracle, tmp_path):
     assert r.returncode == 0 and '"star0_matches_single_run": true' in r.stdout, r.stdout
 
 
-def test_cpp_driver_restores_a_previous_run():
+def test_cpp_driver_restores_a_previous_run(tmp_path):
     """Driver::restore_proposal / restore_variables (MALA.cpp:191-246, do_restore): CPU-only, analytic Gaussian likelihood."""
     exe, src = os.path.join(HERE, "cpp", "test_driver_restore"), os.path.join(HERE, "cpp", "test_driver_restore.cpp")
-    hdr = os.path.join(HERE, "..", "tamcmc-c_b200", "host", "mcmc_driver.hpp")
-    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "tamcmc-c_b200", "host", h) for h in ("mcmc_driver.hpp", "outputs.hpp")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fopenmp", "-o", exe, src])
-    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert r.returncode == 0 and "identical state" in r.stdout, r.stdout
+    r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "identical state" in r.stdout and "restart through the restore files: ok" in r.stdout, r.stdout
+    assert sorted(os.listdir(tmp_path)) == ["star_restore_A_%d.dat" % n for n in (1, 2, 3)]

@@ -262,6 +262,17 @@ def test_cpp_restore_reader_agrees_with_python(pkg, tmp_path):
         vals = np.array([float(t) for t in line.split()[1:]])
         assert int(line.split()[0]) == st[key].size and np.array_equal(vals, st[key].ravel()), key
     assert subprocess.run([exe, "restore", str(tmp_path), "missing", "A"], stdout=subprocess.PIPE).returncode == 1
+    # write_restore (C++): files 2 and 3 come back byte for byte, file 1 on every data line (as with the Python writer)
+    out = tmp_path / "again"
+    out.mkdir()
+    subprocess.run([exe, "restore", str(tmp_path), "10280410_Gaussfit", "A", str(out)], stdout=subprocess.PIPE, check=True)
+    data = lambda t: [l for l in t.splitlines() if not l.startswith("#")]
+    for n in (1, 2, 3):
+        again = (out / ("10280410_Gaussfit_restore_A_%d.dat" % n)).read_text()
+        assert data(again) == data(gold["restore"][str(n)]), n
+        if n > 1:
+            assert again == gold["restore"][str(n)]
+        assert again == pkg.formats.restore_texts(st)[n]
 
 
 def test_cfg_reader(pkg, tmp_path):
