@@ -199,6 +199,29 @@ double tamcmc_host_alm(int l, int m, double theta0, double delta, int filter_cod
 int tamcmc_host_expand_ajAlm(const double *params, const int *plength, tamcmc_alm_fn alm, void *alm_user, int capacity,
                              double *row_out, int *nmodes_out);
 
+/* ---- Alm from the precomputed grids (what the reference's ajAlm model actually uses) ----
+ * Replaces: loadAllData + flatten_grid + init_2dgrid as run once by Config::Config (config.cpp:77-147;
+ * external/Alm/Alm_cpp/Alm_interpol.cpp:11-79, bilinear_interpol.cpp:27-124): reads <grid_dir>/{gate,triangle}/A<l><m+l>.gz
+ * (l = 1..3, m = 0..l; gzip'ed text "x=.." / "y=.." / "z=" / rows) and prepares the bicubic interpolators.  grid_dir is the
+ * reference's external/Alm/data/Alm_grids_CPP/1deg_grids (or any directory written by tamcmc_alm_grids_make). */
+typedef struct tamcmc_alm_grids tamcmc_alm_grids;
+int tamcmc_alm_grids_load(const char *grid_dir, tamcmc_alm_grids **out);
+void tamcmc_alm_grids_free(tamcmc_alm_grids *grids);
+/* Replaces: Alm_interp_iter_preinitialised (Alm_interpol.cpp:188-348) -> interpolate_core -> gsl_interp2d_eval_e with
+ * gsl_interp2d_bicubic (bilinear_interpol.cpp:115-135).  Has the tamcmc_alm_fn signature: pass it with `grids` as the user
+ * pointer to tamcmc_host_expand_ajAlm.  theta0, delta in radians; outside the grid GSL raises GSL_EDOM (the reference's
+ * process aborts): NaN here; l outside 1..3 or |m| > l: -9998 like the reference. */
+double tamcmc_alm_grids_eval(int l, int m, double theta0, double delta, int filter_code, void *grids);
+/* grid introspection (parity tests): axes and node values of grid (filter_code, l, |m|); z is [ny][nx] row-major */
+int tamcmc_alm_grids_shape(const tamcmc_alm_grids *grids, int filter_code, int l, int m, int *nx, int *ny);
+int tamcmc_alm_grids_nodes(const tamcmc_alm_grids *grids, int filter_code, int l, int m, double *x, double *y, double *z);
+/* Replaces: the reference's GridMaker (external/Alm/Alm_cpp/do_grids.cpp:63-76, make_grids.cpp:17-131, gzip_compress.cpp:41-70):
+ * writes <out_dir>/<gate|triangle>/A<l><m+l>.gz for l = 1..lmax, m = -l..l in the reference's text format (6 significant digits).
+ * The shipped 1-degree grids are resol = pi/180, theta0 in [0, pi/2], delta in [0, pi/4]. */
+int tamcmc_alm_grids_make(const char *out_dir, int filter_code, int lmax, double resol, double theta_min, double theta_max,
+                          double delta_min, double delta_max);
+const char *tamcmc_alm_grids_last_error(void);
+
 const char *tamcmc_gpu_strerror(int status);
 const char *tamcmc_gpu_last_error(void);
 int tamcmc_gpu_abi_version(void);

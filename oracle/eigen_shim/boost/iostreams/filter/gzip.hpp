@@ -1,1 +1,3 @@
-// stub: Boost is not available in the build container; nothing of it is needed by the hot-path pin
+// see ../filtering_stream.hpp (the stand-in lives there)
+#pragma once
+#include "../filtering_stream.hpp"

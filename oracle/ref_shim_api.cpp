@@ -17,13 +17,22 @@
 #include "models.h"             // model_MS_Global_*, model_MS_local_*, model_RGB_asympt_* (tamcmc/sources/models.cpp)
 #include "stats_dictionary.h"   // logP_* primitive priors
 #include "priors_calc.h"        // apply_generic_priors, priors_Harvey_Gaussian, priors_Kallinger2014_Gaussian
+#include <cmath>
 
 using Eigen::VectorXd;
 using Eigen::VectorXi;
 
-// The Alm activity term needs GSL and Boost (absent here); the pin never takes that branch.
-long double Alm(const int, const int, const long double, const long double, std::string) { std::abort(); }
-double Alm_interp_iter_preinitialised(const int, const int, const long double, const long double, const std::string, gsl_funcs) { std::abort(); }
+// The Alm activity term: the reference's own external/Alm/Alm_cpp/{activity,Alm_interpol,bilinear_interpol}.cpp are compiled
+// in (oracle/Makefile) against stand-ins for the three absent libraries: Boost's spherical harmonics
+// (eigen_shim/boost/math/special_functions/spherical_harmonic.hpp), Boost.Iostreams' gzip filter (zlib underneath) and
+// GSL's interp2d (eigen_shim/gsl/gsl_interp2d.h: GSL's published bicubic algorithm, NOT GSL itself).
+long double Alm(const int, const int, const long double, const long double, std::string);
+double Alm_interp_iter_preinitialised(const int, const int, const long double, const long double, const std::string, gsl_funcs);
+GridData_Alm_fast loadAllData(const std::string grid_dir, const std::string ftype);
+GridData4gsl flatten_grid(const GridData& data);
+gsl_interp2d* init_2dgrid(const GridData4gsl& data_flatten);
+static external_data g_extra;          // what Config::Config builds once (config.cpp:77-147)
+static bool g_extra_ok = false;
 
 // ---- recording wrapper around the reference's optimum_lorentzian_calc_aj (build_lorentzian.cpp:502-522) ----
 // build_lorentzian.cpp is compiled with that symbol renamed to refreal_optimum_lorentzian_calc_aj (oracle/Makefile);
@@ -58,10 +67,6 @@ Optim_L optimum_lorentzian_calc_aj(const VectorXd& x, const double H_l, const do
 
 static VectorXd vec(const double* p, long n) { VectorXd v(n); for (long i = 0; i < n; i++) v[i] = p[i]; return v; }
 static void out(const VectorXd& v, double* p) { for (long i = 0; i < (long)v.size(); i++) p[i] = v[i]; }
-
-// logP_tabulated_2d (stats_dictionary.cpp:293) reaches the GSL-backed Alm interpolator, which cannot be built here (no GSL):
-// never called through this shim
-double interpolate_core(gsl_interp2d*, const GridData4gsl&, double, double) { std::abort(); }
 
 extern "C" {
 
@@ -141,6 +146,10 @@ int ref_call_model(int model_id, const double* params, int nparams, const int* p
     case 14: m = model_MS_local_Hnlm(p, pl, xv, false); break;
     case 18: m = model_MS_Global_a1n_a2a3_HarveyLike(p, pl, xv, false); break;
     case 19: m = model_MS_Global_a1nl_a2a3_HarveyLike(p, pl, xv, false); break;
+    case 21:                                                               // needs ref_alm_grids_load() first (model_def.cpp:322-324)
+        if (!g_extra_ok) return 3;
+        m = model_MS_Global_ajAlm_HarveyLike(p, pl, xv, false, g_extra);
+        break;
     case 23: m = model_MS_Global_aj_HarveyLike(p, pl, xv, false); break;
     case 25: m = model_RGB_asympt_aj_AppWidth_HarveyLike_v4(p, pl, xv, false); break;
     case 27: m = model_RGB_asympt_aj_CteWidth_HarveyLike_v4(p, pl, xv, false); break;
@@ -148,6 +157,41 @@ int ref_call_model(int model_id, const double* params, int nparams, const int* p
     }
     out(m, model_out);
     return 0;
+}
+
+// ---- the Alm activity term through the reference's own sources ----
+static const char* ftype_of(int filter_code) { return filter_code == 0 ? "gate" : filter_code == 1 ? "gauss" : "triangle"; }
+
+// Alm() direct integral, activity.cpp:221-246 (theta0, delta in radians)
+double ref_Alm(int l, int m, double theta0, double delta, int filter_code) { return (double)Alm(l, m, theta0, delta, ftype_of(filter_code)); }
+
+// the grid set-up of Config::Config (config.cpp:77-147) with the reference's own loadAllData / flatten_grid / init_2dgrid
+static bool fill_funcs(const std::string& dir, const char* ftype, gsl_funcs& f)
+{
+    GridData_Alm_fast g = loadAllData(dir, ftype);
+    if (g.error) return false;
+    f.flat_grid_A10 = flatten_grid(g.A10); f.flat_grid_A11 = flatten_grid(g.A11);
+    f.flat_grid_A20 = flatten_grid(g.A20); f.flat_grid_A21 = flatten_grid(g.A21); f.flat_grid_A22 = flatten_grid(g.A22);
+    f.flat_grid_A30 = flatten_grid(g.A30); f.flat_grid_A31 = flatten_grid(g.A31); f.flat_grid_A32 = flatten_grid(g.A32);
+    f.flat_grid_A33 = flatten_grid(g.A33);
+    f.interp_A10 = init_2dgrid(f.flat_grid_A10); f.interp_A11 = init_2dgrid(f.flat_grid_A11);
+    f.interp_A20 = init_2dgrid(f.flat_grid_A20); f.interp_A21 = init_2dgrid(f.flat_grid_A21); f.interp_A22 = init_2dgrid(f.flat_grid_A22);
+    f.interp_A30 = init_2dgrid(f.flat_grid_A30); f.interp_A31 = init_2dgrid(f.flat_grid_A31); f.interp_A32 = init_2dgrid(f.flat_grid_A32);
+    f.interp_A33 = init_2dgrid(f.flat_grid_A33);
+    f.valid = true;
+    return true;
+}
+int ref_alm_grids_load(const char* grid_dir)
+{
+    g_extra_ok = fill_funcs(grid_dir, "gate", g_extra.Alm_interp_gate) && fill_funcs(grid_dir, "triangle", g_extra.Alm_interp_triangle);
+    return g_extra_ok ? 0 : 1;
+}
+// Alm_interp_iter_preinitialised, Alm_interpol.cpp:188-348
+double ref_Alm_interp(int l, int m, double theta0, double delta, int filter_code)
+{
+    if (!g_extra_ok) return std::nan("");
+    return Alm_interp_iter_preinitialised(l, m, theta0, delta, ftype_of(filter_code),
+                                          filter_code == 0 ? g_extra.Alm_interp_gate : g_extra.Alm_interp_triangle);
 }
 
 // One MCMC step's worth of likelihood work with the reference's own functions: the per-chain OpenMP fan-out of

@@ -36,6 +36,8 @@ ABI_SYMBOLS = [
     "tamcmc_gpu_set_profiling", "tamcmc_gpu_get_kernel_ms", "tamcmc_gpu_launch_count",
     "tamcmc_gpu_debug_trace", "tamcmc_gpu_fp64_peak", "tamcmc_gpu_strerror", "tamcmc_gpu_last_error", "tamcmc_gpu_abi_version",
     "tamcmc_host_alm", "tamcmc_host_expand_ajAlm",
+    "tamcmc_alm_grids_load", "tamcmc_alm_grids_free", "tamcmc_alm_grids_eval", "tamcmc_alm_grids_shape", "tamcmc_alm_grids_nodes",
+    "tamcmc_alm_grids_make", "tamcmc_alm_grids_last_error",
 ]
 
 ALM_FN = C.CFUNCTYPE(C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p)
@@ -121,6 +123,19 @@ def lib():
     L.tamcmc_host_alm.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
     L.tamcmc_host_expand_ajAlm.restype = C.c_int
     L.tamcmc_host_expand_ajAlm.argtypes = [_dp, _ip, ALM_FN, vp, C.c_int, _dp, _ip]
+    L.tamcmc_alm_grids_load.restype = C.c_int
+    L.tamcmc_alm_grids_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.tamcmc_alm_grids_free.restype = None
+    L.tamcmc_alm_grids_free.argtypes = [vp]
+    L.tamcmc_alm_grids_eval.restype = C.c_double
+    L.tamcmc_alm_grids_eval.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, vp]
+    L.tamcmc_alm_grids_shape.restype = C.c_int
+    L.tamcmc_alm_grids_shape.argtypes = [vp, C.c_int, C.c_int, C.c_int, _ip, _ip]
+    L.tamcmc_alm_grids_nodes.restype = C.c_int
+    L.tamcmc_alm_grids_nodes.argtypes = [vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]
+    L.tamcmc_alm_grids_make.restype = C.c_int
+    L.tamcmc_alm_grids_make.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.tamcmc_alm_grids_last_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -334,14 +349,63 @@ def host_alm(l, m, theta0, delta, filter_code=0):
     return lib().tamcmc_host_alm(int(l), int(m), float(theta0), float(delta), int(filter_code))
 
 
+class AlmGrids:
+    """The reference's precomputed Alm grids + GSL-style bicubic interpolation (Config::Config, config.cpp:77-147;
+    Alm_interp_iter_preinitialised, Alm_interpol.cpp:188-348)."""
+
+    def __init__(self, grid_dir):
+        h = C.c_void_p()
+        rc = lib().tamcmc_alm_grids_load(os.fsencode(grid_dir), C.byref(h))
+        if rc != OK:
+            raise TamcmcError(rc, lib().tamcmc_alm_grids_last_error().decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tamcmc_alm_grids_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, l, m, theta0, delta, filter_code=0):
+        return lib().tamcmc_alm_grids_eval(int(l), int(m), float(theta0), float(delta), int(filter_code), self.h)
+
+    def nodes(self, l, m, filter_code=0):
+        nx, ny = C.c_int(0), C.c_int(0)
+        rc = lib().tamcmc_alm_grids_shape(self.h, int(filter_code), int(l), int(m), C.byref(nx), C.byref(ny))
+        if rc != OK:
+            _raise(rc)
+        x, y, z = np.zeros(nx.value), np.zeros(ny.value), np.zeros((ny.value, nx.value))
+        lib().tamcmc_alm_grids_nodes(self.h, int(filter_code), int(l), int(m), x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), z.ctypes.data_as(_dp))
+        return x, y, z
+
+    @staticmethod
+    def make(out_dir, filter_code, lmax=3, resol=np.pi / 180., theta=(0.0, np.pi / 2), delta=(0.0, np.pi / 4)):
+        """GridMaker (do_grids.cpp, make_grids.cpp): defaults = the ranges of the reference's shipped 1-degree grids."""
+        rc = lib().tamcmc_alm_grids_make(os.fsencode(out_dir), int(filter_code), int(lmax), float(resol), float(theta[0]), float(theta[1]),
+                                         float(delta[0]), float(delta[1]))
+        if rc != OK:
+            raise TamcmcError(rc, lib().tamcmc_alm_grids_last_error().decode())
+
+
 def expand_ajAlm(params, plength, capacity, alm=None):
-    """Host expander of model_MS_Global_ajAlm_HarveyLike (models.cpp:1411-1746): -> (mode-table row, nmodes)."""
+    """Host expander of model_MS_Global_ajAlm_HarveyLike (models.cpp:1411-1746): -> (mode-table row, nmodes).
+    alm: None (direct integral tamcmc_host_alm), an AlmGrids (the reference's grid interpolation), or a Python callable."""
     p = _d(params)
     pl = np.ascontiguousarray(plength, dtype=np.int32)
     row = np.zeros(synth.mode_table_nparams(capacity, int(pl[8])))
     n = C.c_int(0)
-    cb = ALM_FN(alm) if alm is not None else C.cast(None, ALM_FN)
-    rc = lib().tamcmc_host_expand_ajAlm(p.ctypes.data_as(_dp), pl.ctypes.data_as(_ip), cb, None, int(capacity), row.ctypes.data_as(_dp), C.byref(n))
+    user = None
+    if isinstance(alm, AlmGrids):
+        cb = C.cast(lib().tamcmc_alm_grids_eval, ALM_FN)
+        user = alm.h
+    else:
+        cb = ALM_FN(alm) if alm is not None else C.cast(None, ALM_FN)
+    rc = lib().tamcmc_host_expand_ajAlm(p.ctypes.data_as(_dp), pl.ctypes.data_as(_ip), cb, user, int(capacity), row.ctypes.data_as(_dp), C.byref(n))
     if rc != OK:
         _raise(rc)
     return row, n.value

@@ -789,6 +789,12 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
         }
 
         PHASE(3);
+#ifdef TAMCMC_TRACE
+        // per-tile record of CTA row 1024 + blockIdx.x: list sizes of the segment whose wait ended at stamp tslot - 1
+        if (tid == 0 && A.trace && (tslot >> 1) - 2 < 64 && (tslot >> 1) >= 2)
+            A.trace[(size_t)(1024 + blockIdx.x) * 64 + (tslot >> 1) - 2] = (unsigned long long)sg.nfast | ((unsigned long long)sg.ngen << 16)
+                | ((unsigned long long)sg.nhdr << 32) | ((unsigned long long)(flags & 0xff) << 48) | ((unsigned long long)(sg.tile & 0xff) << 56);
+#endif
         if (flags & SEG_LAST) {
             const int sc = sg.sc_index, tile = sg.tile, nvalid = sg.nvalid, lb0 = sg.lb0;
             const double N0 = sg.N0;

@@ -57,6 +57,15 @@ class Ref:
         L.ref_eval_chains.restype = C.c_int
         L.ref_eval_chains.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _dp, C.c_long, C.c_int, _dp, C.c_double, _dp, C.c_int]
         L.ref_max_threads.restype = C.c_int
+        L.ref_likelihood_chi_square.restype = C.c_longdouble
+        L.ref_likelihood_chi_square.argtypes = [_dp, _dp, _dp, C.c_long]
+        if hasattr(L, "ref_Alm"):
+            L.ref_Alm.restype = C.c_double
+            L.ref_Alm.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+            L.ref_alm_grids_load.restype = C.c_int
+            L.ref_alm_grids_load.argtypes = [C.c_char_p]
+            L.ref_Alm_interp.restype = C.c_double
+            L.ref_Alm_interp.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
 
     def Pslm(self, s, l, m):
         return float(self.L.ref_Pslm(s, l, m))
@@ -104,6 +113,22 @@ class Ref:
     def chi22p(self, y, model, p=1):
         y, model = _d(y), _d(model)
         return float(self.L.ref_likelihood_chi22p(_p(y), _p(model), len(y), int(p)))
+
+    def chi_square(self, y, model, sigma):
+        y, model, sigma = _d(y), _d(model), _d(sigma)
+        return float(self.L.ref_likelihood_chi_square(_p(y), _p(model), _p(sigma), len(y)))
+
+    def Alm(self, l, m, theta0, delta, filter_code=0):
+        """The reference's direct integral Alm() (activity.cpp:221-246); radians."""
+        return self.L.ref_Alm(int(l), int(m), float(theta0), float(delta), int(filter_code))
+
+    def alm_grids_load(self, grid_dir):
+        """Config::Config's grid set-up (config.cpp:77-147) with the reference's own loadAllData / init_2dgrid."""
+        return self.L.ref_alm_grids_load(os.fsencode(grid_dir))
+
+    def Alm_interp(self, l, m, theta0, delta, filter_code=0):
+        """Alm_interp_iter_preinitialised (Alm_interpol.cpp:188-348) on the grids loaded by alm_grids_load."""
+        return self.L.ref_Alm_interp(int(l), int(m), float(theta0), float(delta), int(filter_code))
 
     def call_model(self, model_id, params, plength, x):
         params, x = _d(params), _d(x)

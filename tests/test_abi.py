@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_functions():
     src = open(os.path.join(ROOT, "include", "tamcmc_gpu.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(tamcmc_(?:gpu|host)_[a-zA-Z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(tamcmc_(?:gpu|host|alm)_[a-zA-Z0-9_]+)\s*\(", src)))
 
 
 def test_header_functions_match_binding_list(pkg):

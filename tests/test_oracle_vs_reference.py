@@ -109,6 +109,59 @@ def test_models_vs_reference(oracle, pkg, model_id):
         assert np.max(np.abs(M - Mr) / np.abs(Mr)) < MODEL_TOL
 
 
+@needs_ref
+def test_chi_square_likelihood_vs_reference(oracle):
+    """likelihood_chi_square (likelihoods.cpp:31-40) -- the second likelihood of call_likelihood (model_def.cpp:402-406)."""
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    R = _refshim.get()
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 777, 20000):
+        model = rng.uniform(0.1, 50.0, n)
+        y = model + rng.normal(0, 1, n) * rng.uniform(0.5, 2.0, n)
+        sigma = rng.uniform(0.3, 3.0, n)
+        mine = float(oracle.L.orc_likelihood_chi_square(y.ctypes.data_as(dp), model.ctypes.data_as(dp), sigma.ctypes.data_as(dp), n))
+        assert mine == pytest.approx(R.chi_square(y, model, sigma), rel=1e-14)
+        ones = np.ones(n)                      # a data file without a sigma column (config.cpp:367-374)
+        mine1 = float(oracle.L.orc_likelihood_chi_square(y.ctypes.data_as(dp), model.ctypes.data_as(dp), ones.ctypes.data_as(dp), n))
+        assert mine1 == pytest.approx(R.chi_square(y, model, ones), rel=1e-14)
+
+
+REF_GRIDS = "/root/reference/external/Alm/data/Alm_grids_CPP/1deg_grids"
+needs_alm = pytest.mark.skipif(not (_refshim.available() and hasattr(_refshim.get().L, "ref_Alm") and os.path.isdir(REF_GRIDS)),
+                               reason="reference Alm sources / shipped grids not available here")
+
+
+@needs_alm
+@pytest.mark.parametrize("filter_code", [0, 2])
+@pytest.mark.parametrize("decompose", [-1, 0, 1, 2])
+def test_ajalm_model_vs_reference(oracle, pkg, decompose, filter_code):
+    """Oracle model 21 against the reference's own model_MS_Global_ajAlm_HarveyLike (models.cpp:1411-1746) with the grid set-up
+    of Config::Config (config.cpp:77-147) on the shipped 1-degree grids.  The oracle is fed the Alm values of the reference's
+    own interpolation chain (so the pin is on the model function: unpacking, decompose_Alm paths, eval_acoefs, windows)."""
+    R = _refshim.get()
+    assert R.alm_grids_load(REF_GRIDS) == 0
+    alm = lambda l, m, t0, de, fc, user: R.Alm_interp(l, m, t0, de, fc)
+    for seed in range(3):
+        rng = np.random.default_rng(100 * seed + 10 * filter_code + decompose + 1)
+        params, pl = pkg.synth.ajalm_params(rng, Nmax=7, lmax=(3 if seed != 1 else 2), f0=1200.0, dnu=75.0, decompose_Alm=decompose,
+                                            filter_code=filter_code, asym=(0.0 if seed == 0 else 21.0), do_amp=seed & 1, trunc_c=25.0,
+                                            theta0=rng.uniform(5, 85), delta=rng.uniform(1, 44), eta_switch=float(seed != 2),
+                                            epsilon=rng.uniform(1e-4, 8e-3))
+        x = pkg.synth.freq_axis(16000 + 11 * seed, 1100.0, 0.05)
+        rc, M, tr = oracle.call_model(21, params, pl, x, alm=alm, trace=True)
+        assert rc == 0
+        rcr, Mr = R.call_model(21, params, pl, x)
+        assert rcr == 0
+        assert np.max(np.abs(M - Mr) / np.abs(Mr)) < MODEL_TOL
+        # and the product's host expander, fed the product's own grid interpolation, lands on the reference's spectrum
+        G = pkg.AlmGrids(REF_GRIDS)
+        row, nm = pkg.expand_ajAlm(params, pl, int(pl[2:6].sum()), alm=G)
+        rc, M2 = oracle.mode_table_model(row, int(pl[8]), 0, x)
+        assert rc == 0
+        assert np.max(np.abs(M2 - Mr) / np.abs(Mr)) < 1e-12
+
+
 def test_golden_fixtures_from_reference_cpp(oracle):
     """Holds everywhere: fixtures generated from the reference-compiled library in the build container."""
     g = np.load(GOLD, allow_pickle=False)
