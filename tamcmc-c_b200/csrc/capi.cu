@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -224,17 +225,27 @@ int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned c
     return TAMCMC_OK;
 }
 
+// after a launch that failed part-way (e.g. the expander went out, the fused kernel did not): read the device's launch
+// epoch back so that the next zero-copy evaluation waits for the right flag value
+void resync_epoch(tamcmc_gpu_ctx* c)
+{
+    unsigned int e = 0;
+    if (cudaStreamSynchronize(c->stream) == cudaSuccess && cudaMemcpy(&e, c->d_epoch, sizeof(e), cudaMemcpyDeviceToHost) == cudaSuccess && e) c->epoch_host = e;
+    cudaMemsetAsync(c->d_qctl, 0, sizeof(QueueCtl), c->stream);      // an expander without its fused kernel leaves the queue armed
+}
+
 // One evaluation on `st`: the kernels are replayed as one CUDA graph (with event-record nodes between them while profiling).
 int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
                 int raw_sum, cudaStream_t st)
 {
-    c->launches += c->d_ksi ? 3 : 2;
-    { const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; }       // what the last CTA will publish
+    // the host's copy of the launch epoch (what the last CTA of THIS launch will publish) advances only once the launch has
+    // been accepted: a failed capture / instantiate / launch leaves host and device counters in step
+    auto launched_ok = [c]() { c->launches += c->d_ksi ? 3 : 2; const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; };
     const bool prof = c->profiling && st == c->stream;
-    if (!c->use_graphs) return enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof, false);
+    if (!c->use_graphs) { const int rc = enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof, false); if (rc == TAMCMC_OK) launched_ok(); else resync_epoch(c); return rc; }
     for (int i = 0; i < c->ngraphs; i++) {
         const tamcmc_gpu_ctx::GraphEntry& g = c->graphs[i];
-        if (g.p == d_params && g.a == d_active && g.o == d_logL && g.raw == raw_sum && g.prof == prof) { CK(cudaGraphLaunch(g.exec, st)); return TAMCMC_OK; }
+        if (g.p == d_params && g.a == d_active && g.o == d_logL && g.raw == raw_sum && g.prof == prof) { CK(cudaGraphLaunch(g.exec, st)); launched_ok(); return TAMCMC_OK; }
     }
     if (c->ngraphs == 4) {           // evict the oldest
         cudaGraphExecDestroy(c->graphs[0].exec);
@@ -255,6 +266,7 @@ int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* 
     if (e != cudaSuccess) return fail_cuda(e, "cudaGraphInstantiate");
     c->graphs[c->ngraphs++] = g;
     CK(cudaGraphLaunch(g.exec, st));
+    launched_ok();
     return TAMCMC_OK;
 }
 
@@ -607,9 +619,13 @@ int tamcmc_gpu_eval_end(tamcmc_gpu_ctx* c, double* logL_out, int* status_out)
                 if (e == cudaSuccess) { if (*flag != expected) { g_last_error = "fused kernel finished without publishing its results"; return TAMCMC_ERR_CUDA; } break; }
                 if (e != cudaErrorNotReady) return fail_cuda(e, "cudaStreamQuery (fused kernel)");
             }
+            // back-off: a few thousand pause-spins cover the usual 50-100 us evaluation; after that the core is yielded between
+            // polls, so a long batched evaluation (or many contexts polled from an OpenMP team) does not burn a host core each
+            if (spins < 4096u) {
 #if defined(__x86_64__)
-            __builtin_ia32_pause();
+                __builtin_ia32_pause();
 #endif
+            } else std::this_thread::yield();
         }
         std::atomic_thread_fence(std::memory_order_acquire);
         if (c->profiling) CK(cudaStreamSynchronize(c->stream));
@@ -650,9 +666,9 @@ int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, doub
     { int rc = expand_single(c, star, params_row); if (rc) return rc; }
     const StarDesc& sd = c->h_stars[star];
     WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0, false);
-    CK(tamcmc_launch_whittle(wa, c->grid_ctas, true, c->tile_bins, c->stream, false));
+    { const cudaError_t e = tamcmc_launch_whittle(wa, c->grid_ctas, true, c->tile_bins, c->stream, false); if (e != cudaSuccess) { resync_epoch(c); return fail_cuda(e, "tamcmc_launch_whittle"); } }
     c->launches += 1;
-    { const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; }
+    { const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; }       // only after the launch was accepted
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     const int SC = c->SC();

@@ -873,6 +873,7 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
             PHASE(4);
             double s1 = 0.0, pm = 1.0;
             int pe = 0;
+            int bad = 0;                     // sign / NaN watch of 1/M_i: OR of the high words (see below)
             if (A.likelihood == 1) {
                 // chi_square (likelihoods.cpp:31-40): sum of (y - M)^2 / sigma_y^2; the weights 1/sigma^2 were formed once at create
                 const double* wg = A.wsig + sg.off;
@@ -902,8 +903,14 @@ __device__ void consumer_loop(const WhittleArgs& A, Smem<NC * BPT>& sm, int tid)
                     const int k = (hi & 0x7ff00000) - 0x3ff00000;
                     pm *= __hiloint2double(hi - k, __double2loint(minv));
                     pe += k >> 20;
+                    bad |= hi;
                 }
             }
+            // The reference takes log() of every model bin (likelihoods.cpp:23): ONE non-positive M_i makes its logL NaN and
+            // the proposal is rejected (MALA.cpp:522).  The product of the 1/M_i would hide an even number of negative factors,
+            // so the sign bit of any of them poisons the tile (one integer OR per bin; heights and noise terms are abs()
+            // values, so this only triggers on caller-supplied mode tables or data that defeat that).
+            if (bad < 0) pm = nan("");
             // ---------- tile completion: every thread leaves its three sums in the slot's scratch; the slot's producer
             // warp reduces them (tile_reduce) after the empty barrier has handed the slot back.  Nobody waits for
             // anybody: this warp goes straight on to the next tile. ----------

@@ -29,6 +29,8 @@
 #include <limits>
 #include <memory>
 #include <random>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace tamcmc {
@@ -54,6 +56,11 @@ struct AsyncEvaluator {
     std::function<int(double*)> end;
 };
 
+// Evaluator status codes that are DATA (some chain's logL is NaN and its proposal is rejected, MALA.cpp:490,522): TAMCMC_OK,
+// TAMCMC_ERR_WINDOW, TAMCMC_ERR_NONFINITE (include/tamcmc_gpu.h).  Anything else (bad argument, unknown model, CUDA error)
+// means the output buffer may not have been written at all.
+inline bool eval_status_is_fatal(int rc) { return !(rc == 0 || rc == 4 || rc == 5); }
+
 class Driver {
 public:
     // state with the reference's names (model_def.h:54-66, MALA.h)
@@ -65,6 +72,7 @@ public:
     std::vector<int> moved;
     long n_swap_tried = 0, n_swap_done = 0, n_eval_calls = 0;
     std::vector<long> n_accept;
+    int last_eval_status = 0;                              // what the evaluator returned for the last step (0 = OK)
 
     // defer_initial_eval: the caller evaluates `params` itself (BatchDriver: one launch for all stars) and reports the result
     // through set_initial_logL()
@@ -93,8 +101,7 @@ public:
         // initial model (Model_def constructor, model_def.cpp:142-147)
         for (int m = 0; m < Nchains; m++) { logPrior[m] = prior(&params[(size_t)m * stride]); active[m] = std::isinf(logPrior[m]) ? 0 : 1; }
         if (!defer_initial_eval) {
-            eval(params.data(), active.data(), logLikelihood.data());
-            n_eval_calls++;
+            evaluate_current("initial model");
             set_initial_logL(logLikelihood.data());
         }
     }
@@ -129,8 +136,7 @@ public:
             active[m] = std::isinf(logPrior[m]) ? 0 : 1;
         }
         prop_params = params; prop_vars = vars;
-        eval(params.data(), active.data(), logLikelihood.data());
-        n_eval_calls++;
+        evaluate_current("restored position");
         set_initial_logL(logLikelihood.data());
     }
 
@@ -140,22 +146,30 @@ public:
     double* proposal_logL() { return prop_logL.data(); }
     int row_stride() const { return stride; }
 
-    // one iteration i of MALA::execute (MALA.cpp:646-700)
-    void step(long i)
+    // one iteration i of MALA::execute (MALA.cpp:646-700).  Returns the evaluator's status.  The proposal's log-likelihoods
+    // are preset to NaN, so a chain the evaluator did not write (a failed call) is rejected like any NaN likelihood
+    // (MALA.cpp:522-524) instead of being judged on the previous step's values; a fatal status (eval_status_is_fatal) is
+    // returned to the caller, who decides whether to go on.
+    int step(long i)
     {
         propose(i);
         // ---- ONE batched evaluation (was: generate_model per chain inside the OpenMP loop); the draws of the next step are
         // prepared while it runs (same order of random numbers with and without an asynchronous evaluator) ----
+        std::fill(prop_logL.begin(), prop_logL.end(), std::numeric_limits<double>::quiet_NaN());
+        int rc;
         if (async.begin) {
-            async.begin(prop_params.data(), active.data());
+            rc = async.begin(prop_params.data(), active.data());
             prepare_next();
-            async.end(prop_logL.data());
+            if (!eval_status_is_fatal(rc)) rc = async.end(prop_logL.data());
         } else {
-            eval(prop_params.data(), active.data(), prop_logL.data());
+            rc = eval(prop_params.data(), active.data(), prop_logL.data());
             prepare_next();
         }
         n_eval_calls++;
+        last_eval_status = rc;
+        if (eval_status_is_fatal(rc)) std::fill(prop_logL.begin(), prop_logL.end(), std::numeric_limits<double>::quiet_NaN());
         finish(i);
+        return rc;
     }
 
     void set_async_evaluator(AsyncEvaluator a) { async = std::move(a); }
@@ -250,6 +264,16 @@ public:
     int n_chains() const { return Nchains; }
 
 private:
+    // likelihoods of the CURRENT positions (constructor, restore): there is nothing to fall back on if this fails
+    void evaluate_current(const char* what)
+    {
+        std::fill(logLikelihood.begin(), logLikelihood.end(), std::numeric_limits<double>::quiet_NaN());
+        const int rc = eval(params.data(), active.data(), logLikelihood.data());
+        n_eval_calls++;
+        last_eval_status = rc;
+        if (eval_status_is_fatal(rc)) throw std::runtime_error(std::string("tamcmc::Driver: evaluation of the ") + what + " failed with status " + std::to_string(rc));
+    }
+
     DriverConfig cfg;
     int Nchains, Nparams, stride, Nvars;
     std::vector<int> index_to_relax;
@@ -389,10 +413,15 @@ public:
             std::copy(stars[s]->params.begin(), stars[s]->params.end(), P.begin() + s * Nchains * stride);
             std::copy(stars[s]->active_mask(), stars[s]->active_mask() + Nchains, act.begin() + s * Nchains);
         }
-        eval(P.data(), act.data(), L.data());
+        std::fill(L.begin(), L.end(), std::numeric_limits<double>::quiet_NaN());
+        last_eval_status = eval(P.data(), act.data(), L.data());
+        if (eval_status_is_fatal(last_eval_status))
+            throw std::runtime_error("tamcmc::BatchDriver: evaluation of the initial models failed with status " + std::to_string(last_eval_status));
         for (size_t s = 0; s < S; s++) stars[s]->set_initial_logL(&L[s * Nchains]);
     }
-    void step(long i)
+    int last_eval_status = 0;
+    // returns the evaluator's status; unwritten / failed evaluations reject every proposal (NaN), see Driver::step
+    int step(long i)
     {
         const long S = (long)stars.size();
 #ifdef _OPENMP
@@ -403,14 +432,16 @@ public:
             std::copy(stars[(size_t)s]->proposal_params(), stars[(size_t)s]->proposal_params() + (size_t)Nchains * stride, P.begin() + (size_t)s * Nchains * stride);
             std::copy(stars[(size_t)s]->active_mask(), stars[(size_t)s]->active_mask() + Nchains, act.begin() + (size_t)s * Nchains);
         }
-        if (async.begin) async.begin(P.data(), act.data());
-        else eval(P.data(), act.data(), L.data());
+        std::fill(L.begin(), L.end(), std::numeric_limits<double>::quiet_NaN());
+        int rc = async.begin ? async.begin(P.data(), act.data()) : eval(P.data(), act.data(), L.data());
         // the next step's draws of every star, while the batched evaluation runs (same order with a synchronous evaluator)
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1)
 #endif
         for (long s = 0; s < S; s++) stars[(size_t)s]->prepare_next();
-        if (async.begin) async.end(L.data());
+        if (async.begin && !eval_status_is_fatal(rc)) rc = async.end(L.data());
+        last_eval_status = rc;
+        if (eval_status_is_fatal(rc)) std::fill(L.begin(), L.end(), std::numeric_limits<double>::quiet_NaN());
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1)
 #endif
@@ -418,6 +449,7 @@ public:
             std::copy(L.begin() + (size_t)s * Nchains, L.begin() + (size_t)(s + 1) * Nchains, stars[(size_t)s]->proposal_logL());
             stars[(size_t)s]->finish(i);
         }
+        return rc;
     }
     void set_async_evaluator(AsyncEvaluator a) { async = std::move(a); }
 private:

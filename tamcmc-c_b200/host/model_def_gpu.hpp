@@ -14,6 +14,7 @@
 //
 // There is no CPU path here: every method forwards to libtamcmc_gpu.so and throws if it fails.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <limits>
@@ -100,8 +101,25 @@ public:
     // take init_logLikelihood / logPosterior = -inf exactly like the reference; the others get the tempered logL.
     // Returns the C-ABI status (TAMCMC_OK, or ERR_WINDOW / ERR_NONFINITE when some chain was flagged: NaN logL is data,
     // MALA.cpp:490,522).  Throws on CUDA / argument errors.
+    // What the reference's constructor does with the initial parameters (model_def.cpp:142-153): model + likelihood of EVERY
+    // chain "whatever the situation" (no prior short-circuit), kept as init_logLikelihood -- the value generate_model hands
+    // back for a chain whose prior is -inf (model_def.cpp:476-480).  Call it once `params` holds the initial vectors;
+    // generate_models() / generate_models_begin() run it on their first call otherwise.
+    int initialise()
+    {
+        const size_t n = (size_t)nstars * Nmodels;
+        std::fill(active.begin(), active.end(), (unsigned char)1);
+        const int rc = tamcmc_gpu_eval(ctx, params.data(), active.data(), logLikelihood.data(), status.data());
+        if (rc != TAMCMC_OK && rc != TAMCMC_ERR_WINDOW && rc != TAMCMC_ERR_NONFINITE) check(rc, "tamcmc_gpu_eval (initial models)");
+        init_logLikelihood = logLikelihood;
+        for (size_t i = 0; i < n; i++) logPosterior[i] = logLikelihood[i] + logPrior[i];
+        initialised = true;
+        return rc;
+    }
+
     int generate_models()
     {
+        if (!initialised) initialise();
         const size_t n = (size_t)nstars * Nmodels;
         for (size_t i = 0; i < n; i++) active[i] = (logPrior[i] != -std::numeric_limits<double>::infinity()) ? 1 : 0;
         const int rc = tamcmc_gpu_eval(ctx, params.data(), active.data(), logLikelihood.data(), status.data());
@@ -117,6 +135,7 @@ public:
     // likelihoods in between (e.g. the random numbers of the next proposal).  Same results as generate_models().
     void generate_models_begin()
     {
+        if (!initialised) initialise();
         const size_t n = (size_t)nstars * Nmodels;
         for (size_t i = 0; i < n; i++) active[i] = (logPrior[i] != -std::numeric_limits<double>::infinity()) ? 1 : 0;
         check(tamcmc_gpu_eval_begin(ctx, params.data(), active.data()), "tamcmc_gpu_eval_begin");
@@ -150,6 +169,7 @@ private:
     std::vector<long> Nx;
     std::vector<int> Nparams_of;
     std::vector<unsigned char> active;
+    bool initialised = false;          // initialise() has filled init_logLikelihood
 };
 
 }  // namespace tamcmc

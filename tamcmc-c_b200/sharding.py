@@ -26,7 +26,14 @@ def bin_work(N, l, i0, i1, base=1.0):
 
 
 def bin_shards(N, world, work=None, align=TILE):
-    """Contiguous [lo,hi) per rank with ~equal total work; boundaries multiples of `align`."""
+    """Contiguous [lo,hi) per rank with ~equal total work; inner boundaries are multiples of `align` (the full tile: also a
+    multiple of the half-size tile the library picks for small contexts, csrc/capi.cu).  Every rank gets at least `align` bins
+    (tamcmc_gpu_create refuses fewer than 2): a spectrum too short for that raises instead of handing some rank an empty
+    shard while the others enter the exchange."""
+    if world < 1 or N < 2:
+        raise ValueError("bin_shards: need world >= 1 and N >= 2")
+    if world > 1 and N < world * align:
+        raise ValueError("bin_shards: %d bins cannot give %d ranks at least %d bins each; use fewer ranks" % (N, world, align))
     if work is None:
         work = np.ones(N)
     cs = np.concatenate([[0.0], np.cumsum(work)])
@@ -35,13 +42,23 @@ def bin_shards(N, world, work=None, align=TILE):
         target = cs[-1] * r / world
         b = int(np.searchsorted(cs, target))
         b = int(round(b / align) * align)
-        b = min(max(b, bounds[-1]), N)
+        lo = bounds[-1] + align                          # this rank's shard is at least `align` bins ...
+        hi = ((N - (world - r) * align) // align) * align  # ... and so is every later one
+        b = min(max(b, lo), hi)
         bounds.append(b)
     bounds.append(N)
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
-def finalize_logL(S, p, Tcoefs):
-    """Tempered chi^2(2,2p) log-likelihood from the all-reduced sum S (likelihoods.cpp:23-25; p truncated
-    to long and the division by Tcoefs[m] as model_def.cpp:399-401)."""
-    return (-float(int(p)) * np.asarray(S, dtype=np.float64)) / np.asarray(Tcoefs, dtype=np.float64)
+def finalize_logL(S, p, Tcoefs, likelihood_id=0):
+    """Tempered log-likelihood from the all-reduced raw sum S of the shards (tamcmc_gpu_eval_device with raw_sum = 1).
+    likelihood_id 0, chi^2(2,2p): -p S / T with S = sum(ln M + y/M), p truncated to long (likelihoods.cpp:23-25,
+    model_def.cpp:399-401); likelihood_id 1, chi_square: -(S / 2) / T with S = sum((y - M)^2 / sigma^2) (likelihoods.cpp:36-37,
+    model_def.cpp:405)."""
+    S = np.asarray(S, dtype=np.float64)
+    T = np.asarray(Tcoefs, dtype=np.float64)
+    if likelihood_id == 1:
+        return ((-S) / 2) / T
+    if likelihood_id != 0:
+        raise ValueError("unknown likelihood id %r" % (likelihood_id,))
+    return (-float(int(p)) * S) / T

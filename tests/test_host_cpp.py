@@ -141,3 +141,16 @@ def test_cpp_driver_restores_a_previous_run(tmp_path):
     r = subprocess.run([exe, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "identical state" in r.stdout and "restart through the restore files: ok" in r.stdout, r.stdout
     assert sorted(os.listdir(tmp_path)) == ["star_restore_A_%d.dat" % n for n in (1, 2, 3)]
+
+
+def test_cpp_driver_samples_the_right_law():
+    """Adaptive Metropolis + parallel tempering (MALA.cpp:296-319, 397-461, 463-553) on a correlated Gaussian with known
+    covariance: chain 0 mean/covariance, chain m covariance = T_m x that, acceptance at the Robbins-Monro target, PT swap rate
+    against its expectation; and a failing evaluator rejects every proposal and reports its status (CPU only)."""
+    exe, src = os.path.join(HERE, "cpp", "test_driver_law"), os.path.join(HERE, "cpp", "test_driver_law.cpp")
+    hdr = os.path.join(HERE, "..", "tamcmc-c_b200", "host", "mcmc_driver.hpp")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fopenmp", "-o", exe, src])
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    print(r.stdout)
+    assert r.returncode == 0 and "driver law: ok" in r.stdout, r.stdout

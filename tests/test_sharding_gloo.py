@@ -99,3 +99,20 @@ def test_bin_shards_balance_work(pkg):
         tot = [work[lo:hi].sum() for lo, hi in r]
         assert max(tot) / (sum(tot) / world) < 1.15          # within 15% of perfect balance
         assert all(lo % shard.TILE == 0 for lo, _ in r)
+
+
+def test_bin_shards_never_hand_out_an_empty_shard(pkg):
+    """Peaked work or a short spectrum: every rank still gets at least one full tile (tamcmc_gpu_create refuses N < 2), or the
+    call raises before any rank enters the exchange; the chi_square finaliser (likelihoods.cpp:36-37, model_def.cpp:405)."""
+    from importlib import import_module
+    shard = import_module("tamcmc_c_b200.sharding")
+    w = np.ones(100000)
+    w[:2000] += 1e6                                    # all the work in the first two tiles
+    r = shard.bin_shards(100000, 8, w)
+    assert all(hi - lo >= shard.TILE for lo, hi in r) and r[0][0] == 0 and r[-1][1] == 100000
+    assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(lo % shard.TILE == 0 for lo, _ in r)
+    assert shard.bin_shards(3 * shard.TILE + 5, 3) == [(0, 1536), (1536, 3072), (3072, 4613)]
+    with pytest.raises(ValueError):
+        shard.bin_shards(3000, 4)
+    assert np.array_equal(shard.finalize_logL([2.0, 4.0], 1.0, [1.0, 2.0], likelihood_id=1), [-1.0, -1.0])
+    assert np.array_equal(shard.finalize_logL([2.0, 4.0], 2.9, [1.0, 2.0]), [-4.0, -4.0])      # p truncated to long
