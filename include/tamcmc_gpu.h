@@ -199,6 +199,30 @@ double tamcmc_host_alm(int l, int m, double theta0, double delta, int filter_cod
 int tamcmc_host_expand_ajAlm(const double *params, const int *plength, tamcmc_alm_fn alm, void *alm_user, int capacity,
                              double *row_out, int *nmodes_out);
 
+/* ---- red-giant models: mixed-mode host expander (BASELINE configs C1 / C4) ----
+ * Replaces: the host half of model_RGB_asympt_aj_AppWidth_HarveyLike_v4 (model_id 25, models.cpp:4684-4927) and of
+ * model_RGB_asympt_aj_CteWidth_HarveyLike_v4 (model_id 27, models.cpp:4334-4556): params / plength in those models' own layout ->
+ * ONE mode-table row of `capacity` modes (row_out: TAMCMC_MT_HEADER + Nnoise + TAMCMC_MT_STRIDE * capacity doubles) for a context
+ * created with plength = [capacity, 1 (step = x[2]-x[1]), 0,...,0, Nnoise, 0, 0].  step = x[2] - x[1] of the spectrum
+ * (models.cpp:4714): the grid resolution of the ARMM solver.  *nmodes_out = number of modes (the number of l=1 mixed modes varies
+ * from chain to chain); TAMCMC_ERR_ARG with *nmodes_out set when it exceeds `capacity`; TAMCMC_ERR_NONFINITE where the reference
+ * exits (fmin - Dnu < 0, negative p-mode frequency) or finds no mixed mode. */
+int tamcmc_host_expand_rgb_v4(int model_id, const double *params, const int *plength, double step, int capacity, double *row_out,
+                              int *nmodes_out);
+/* Replaces: solve_mm_asymptotic_O2from_l0 / solve_mm_asymptotic_O2p (external/ARMM/solver_mm.cpp:624-746, 470-604) with sigma_p = 0
+ * and returns_pg_freqs = true: mixed-mode frequencies nu_m[*n_m] (sorted, duplicates within 2 resol removed), the pure p modes
+ * nu_p[*n_p] with their local large separations dnup[*n_p], the pure g modes nu_g[*n_g].  Arrays of capacity `cap` (nu_p, dnup,
+ * nu_g and the counts may be NULL). */
+int tamcmc_host_armm_solve_from_l0(const double *nu_l0, int n_l0, int el, double delta0l, double DPl, double alpha, double q, double resol,
+                                   double freq_min, double freq_max, int cap, double *nu_m, int *n_m, double *nu_p, double *dnup, int *n_p,
+                                   double *nu_g, int *n_g);
+int tamcmc_host_armm_solve_O2p(double Dnu_p, double epsilon, int el, double delta0l, double alpha_p, double nmax, double DPl, double alpha,
+                               double q, double fmin, double fmax, double resol, int cap, double *nu_m, int *n_m, double *nu_p, double *dnup,
+                               int *n_p, double *nu_g, int *n_g);
+/* Replaces: tk::spline with second-derivative-zero boundaries (external/spline/src/spline.h), the bias of the l=1 mixed modes
+ * (models.cpp:4834-4843): type 1 = cspline, 2 = cspline_hermite; out[i] = spline(xq[i]) (linear extrapolation outside). */
+int tamcmc_host_spline_eval(const double *x, const double *y, int n, int type, const double *xq, int nq, double *out);
+
 /* ---- Alm from the precomputed grids (what the reference's ajAlm model actually uses) ----
  * Replaces: loadAllData + flatten_grid + init_2dgrid as run once by Config::Config (config.cpp:77-147;
  * external/Alm/Alm_cpp/Alm_interpol.cpp:11-79, bilinear_interpol.cpp:27-124): reads <grid_dir>/{gate,triangle}/A<l><m+l>.gz

@@ -18,6 +18,9 @@
 #include "stats_dictionary.h"   // logP_* primitive priors
 #include "priors_calc.h"        // apply_generic_priors, priors_Harvey_Gaussian, priors_Kallinger2014_Gaussian
 #include <cmath>
+#include "solver_mm.h"            // external/ARMM: solve_mm_asymptotic_O2p, solve_mm_asymptotic_O2from_l0
+#include "bump_DP.h"              // external/ARMM: ksi_fct2, h_l_rgb, gamma_l_fct2, dnu_rot_2zones
+#include "../../external/spline/src/spline.h"   // tk::spline (resolved against -I$(REFERENCE)/tamcmc/headers)
 
 using Eigen::VectorXd;
 using Eigen::VectorXi;
@@ -157,6 +160,33 @@ int ref_call_model(int model_id, const double* params, int nparams, const int* p
     }
     out(m, model_out);
     return 0;
+}
+
+// ---- the ARMM mixed-mode solver and its helpers (external/ARMM), as the red-giant models call them ----
+static int put(const VectorXd& v, double* dst, int cap) { if ((int)v.size() > cap) return -1; for (long i = 0; i < (long)v.size(); i++) dst[i] = v[i]; return (int)v.size(); }
+int ref_solve_mm_from_l0(const double* nu_l0, int n, int el, double delta0l, double DPl, double alpha, double q, double resol, double fmin, double fmax,
+                         int cap, double* nu_m, int* n_m, double* nu_p, double* dnup, int* n_p, double* nu_g, int* n_g)
+{
+    Data_eigensols r = solve_mm_asymptotic_O2from_l0(vec(nu_l0, n), el, delta0l, DPl, alpha, q, 0, resol, true, false, fmin, fmax);
+    *n_m = put(r.nu_m, nu_m, cap); *n_p = put(r.nu_p, nu_p, cap); put(r.dnup, dnup, cap); *n_g = put(r.nu_g, nu_g, cap);
+    return (*n_m < 0 || *n_p < 0 || *n_g < 0) ? 1 : 0;
+}
+int ref_solve_mm_O2p(double Dnu_p, double epsilon, int el, double delta0l, double alpha_p, double nmax, double DPl, double alpha, double q, double fmin,
+                     double fmax, double resol, int cap, double* nu_m, int* n_m, double* nu_p, double* dnup, int* n_p, double* nu_g, int* n_g)
+{
+    Data_eigensols r = solve_mm_asymptotic_O2p(Dnu_p, epsilon, el, delta0l, alpha_p, nmax, DPl, alpha, q, 0, fmin, fmax, resol, true, false);
+    *n_m = put(r.nu_m, nu_m, cap); *n_p = put(r.nu_p, nu_p, cap); put(r.dnup, dnup, cap); *n_g = put(r.nu_g, nu_g, cap);
+    return (*n_m < 0 || *n_p < 0 || *n_g < 0) ? 1 : 0;
+}
+void ref_ksi_fct2(const double* nu, int n, const double* nu_p, const double* dnup, int n_p, const double* nu_g, const double* dPg, int n_g, double q, double* ksi)
+{ out(ksi_fct2(vec(nu, n), vec(nu_p, n_p), vec(nu_g, n_g), vec(dnup, n_p), vec(dPg, n_g), q, "precise"), ksi); }
+// tk::spline exactly as the models set it up (models.cpp:4834-4843): type 1 cspline, 2 cspline_hermite
+void ref_spline_eval(const double* x, const double* y, int n, int type, const double* xq, int nq, double* o)
+{
+    tk::spline s;
+    s.set_boundary(tk::spline::second_deriv, 0.0, tk::spline::second_deriv, 0.0);
+    s.set_points(std::vector<double>(x, x + n), std::vector<double>(y, y + n), type == 1 ? tk::spline::cspline : tk::spline::cspline_hermite);
+    for (int i = 0; i < nq; i++) o[i] = s(xq[i]);
 }
 
 // ---- the Alm activity term through the reference's own sources ----

@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "tamcmc_gpu_set_profiling", "tamcmc_gpu_get_kernel_ms", "tamcmc_gpu_launch_count",
     "tamcmc_gpu_debug_trace", "tamcmc_gpu_fp64_peak", "tamcmc_gpu_strerror", "tamcmc_gpu_last_error", "tamcmc_gpu_abi_version",
     "tamcmc_host_alm", "tamcmc_host_expand_ajAlm",
+    "tamcmc_host_expand_rgb_v4", "tamcmc_host_armm_solve_from_l0", "tamcmc_host_armm_solve_O2p", "tamcmc_host_spline_eval",
     "tamcmc_alm_grids_load", "tamcmc_alm_grids_free", "tamcmc_alm_grids_eval", "tamcmc_alm_grids_shape", "tamcmc_alm_grids_nodes",
     "tamcmc_alm_grids_make", "tamcmc_alm_grids_last_error",
 ]
@@ -123,6 +124,14 @@ def lib():
     L.tamcmc_host_alm.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
     L.tamcmc_host_expand_ajAlm.restype = C.c_int
     L.tamcmc_host_expand_ajAlm.argtypes = [_dp, _ip, ALM_FN, vp, C.c_int, _dp, _ip]
+    L.tamcmc_host_expand_rgb_v4.restype = C.c_int
+    L.tamcmc_host_expand_rgb_v4.argtypes = [C.c_int, _dp, _ip, C.c_double, C.c_int, _dp, _ip]
+    L.tamcmc_host_armm_solve_from_l0.restype = C.c_int
+    L.tamcmc_host_armm_solve_from_l0.argtypes = [_dp, C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_int, _dp, _ip, _dp, _dp, _ip, _dp, _ip]
+    L.tamcmc_host_armm_solve_O2p.restype = C.c_int
+    L.tamcmc_host_armm_solve_O2p.argtypes = [C.c_double, C.c_double, C.c_int] + [C.c_double] * 9 + [C.c_int, _dp, _ip, _dp, _dp, _ip, _dp, _ip]
+    L.tamcmc_host_spline_eval.restype = C.c_int
+    L.tamcmc_host_spline_eval.argtypes = [_dp, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp]
     L.tamcmc_alm_grids_load.restype = C.c_int
     L.tamcmc_alm_grids_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.tamcmc_alm_grids_free.restype = None
@@ -409,6 +418,55 @@ def expand_ajAlm(params, plength, capacity, alm=None):
     if rc != OK:
         _raise(rc)
     return row, n.value
+
+
+def expand_rgb_v4(model_id, params, plength, step, capacity):
+    """Host expander of model_RGB_asympt_aj_{AppWidth (25), CteWidth (27)}_HarveyLike_v4 (models.cpp:4684-5079, 4334-4682):
+    -> (mode-table row, nmodes).  step = x[2] - x[1]."""
+    p = _d(params)
+    pl = np.ascontiguousarray(plength, dtype=np.int32)
+    row = np.zeros(synth.mode_table_nparams(capacity, int(pl[8])))
+    n = C.c_int(0)
+    rc = lib().tamcmc_host_expand_rgb_v4(int(model_id), p.ctypes.data_as(_dp), pl.ctypes.data_as(_ip), float(step), int(capacity),
+                                         row.ctypes.data_as(_dp), C.byref(n))
+    if rc != OK:
+        _raise(rc)
+    return row, n.value
+
+
+def armm_solve_from_l0(nu_l0, el, delta0l, DPl, alpha, q, resol, freq_min, freq_max, cap=4096):
+    """solve_mm_asymptotic_O2from_l0 (solver_mm.cpp:624-746): -> nu_m, nu_p, dnup, nu_g."""
+    f = _d(nu_l0)
+    out = [np.zeros(cap) for _ in range(4)]
+    n = [C.c_int(0) for _ in range(3)]
+    rc = lib().tamcmc_host_armm_solve_from_l0(f.ctypes.data_as(_dp), len(f), int(el), float(delta0l), float(DPl), float(alpha), float(q), float(resol),
+                                              float(freq_min), float(freq_max), cap, out[0].ctypes.data_as(_dp), C.byref(n[0]), out[1].ctypes.data_as(_dp),
+                                              out[2].ctypes.data_as(_dp), C.byref(n[1]), out[3].ctypes.data_as(_dp), C.byref(n[2]))
+    if rc != OK:
+        _raise(rc)
+    return out[0][:n[0].value].copy(), out[1][:n[1].value].copy(), out[2][:n[1].value].copy(), out[3][:n[2].value].copy()
+
+
+def armm_solve_O2p(Dnu_p, epsilon, el, delta0l, alpha_p, nmax, DPl, alpha, q, fmin, fmax, resol, cap=4096):
+    """solve_mm_asymptotic_O2p (solver_mm.cpp:470-604): -> nu_m, nu_p, dnup, nu_g."""
+    out = [np.zeros(cap) for _ in range(4)]
+    n = [C.c_int(0) for _ in range(3)]
+    rc = lib().tamcmc_host_armm_solve_O2p(float(Dnu_p), float(epsilon), int(el), float(delta0l), float(alpha_p), float(nmax), float(DPl), float(alpha),
+                                          float(q), float(fmin), float(fmax), float(resol), cap, out[0].ctypes.data_as(_dp), C.byref(n[0]),
+                                          out[1].ctypes.data_as(_dp), out[2].ctypes.data_as(_dp), C.byref(n[1]), out[3].ctypes.data_as(_dp), C.byref(n[2]))
+    if rc != OK:
+        _raise(rc)
+    return out[0][:n[0].value].copy(), out[1][:n[1].value].copy(), out[2][:n[1].value].copy(), out[3][:n[2].value].copy()
+
+
+def spline_eval(x, y, xq, kind=1):
+    """tk::spline with zero second derivatives at the ends (spline.h): kind 1 cubic, 2 Hermite."""
+    x, y, xq = _d(x), _d(y), _d(np.atleast_1d(xq))
+    out = np.zeros(len(xq))
+    rc = lib().tamcmc_host_spline_eval(x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), len(x), int(kind), xq.ctypes.data_as(_dp), len(xq), out.ctypes.data_as(_dp))
+    if rc != OK:
+        _raise(rc)
+    return out
 
 
 def fp64_peak(device=0):

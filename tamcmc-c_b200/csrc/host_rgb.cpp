@@ -1,0 +1,639 @@
+// host_rgb.cpp -- host expander of the red-giant models (BASELINE configs C1 / C4): the host half of
+//   model_RGB_asympt_aj_AppWidth_HarveyLike_v4   tamcmc/sources/models.cpp:4684-5079   (models_ctrl.list id 25)
+//   model_RGB_asympt_aj_CteWidth_HarveyLike_v4   tamcmc/sources/models.cpp:4334-4682   (id 27)
+// i.e. everything those functions do BEFORE their optimum_lorentzian_calc_aj loops: Appourchaux / constant l=0 widths, the
+// asymptotic mixed-mode solver for the l=1 frequencies (ARMM), the bias spline, the zeta function, heights, widths and
+// two-zone splittings of the mixed modes.  The result is one MODE TABLE row (include/tamcmc_gpu.h): exactly the arguments the
+// reference passes to optimum_lorentzian_calc_aj (models.cpp:4931-5006); windows, profiles, noise and likelihood run on the GPU.
+// Part of libtamcmc_gpu.so; plain host C++ (no CUDA calls), compiled with -ffp-contract=off.
+//
+// Reference pieces restated here (new code; same operations in the same order and in the same floating-point types, because
+// a mixed mode can be narrower than 1e-3 microHz: its frequency has to agree to ~1e-15 relative for 1e-10 on the spectrum):
+//   sign_change, pnu_fct, gnu_fct, asympt_nu_p, asympt_nu_p_from_l0_Xd, asympt_nu_g, solver_mm,
+//   solve_mm_asymptotic_O2p, solve_mm_asymptotic_O2from_l0        external/ARMM/solver_mm.cpp:71-740
+//   Frstder_adaptive_reggrid                                       external/ARMM/derivatives_handler.cpp:425-444
+//   where_in_range, where_dbl                                      external/ARMM/string_handler.cpp:135-237
+//   ksi_fct1, ksi_fct2 ("precise"), gamma_l_fct2, h_l_rgb, dnu_rot_2zones   external/ARMM/bump_DP.cpp:46-240, 531-537
+//   tk::spline (cspline / cspline_hermite, second-derivative boundaries)    external/spline/src/spline.h:219-405, 480-503, 685-761
+//   linfit, lin_interpol, eta0_fct                                 tamcmc/sources/linfit.cpp:16-33, interpol.cpp:13-43, models.cpp:6065-6084
+// Eigen is not used: a `VectorXd op long double` expression of the reference converts the scalar to double and applies the
+// operation element by element, which is what the loops below do (the casts are where the reference's conversions are).
+// The reference runs the (p mode, g mode) pairs and the zeta sums under OpenMP with critical sections (solver_mm.cpp:561,
+// bump_DP.cpp:137,153): its own summation order depends on the thread schedule.  Here pairs are independent and their
+// solutions are sorted afterwards, and the zeta sums are taken per frequency in (np, ng) order -- the single-thread order of
+// the reference -- so results do not depend on the thread count.
+#include "../../include/tamcmc_gpu.h"
+#include "host_math.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+typedef long double ld;
+typedef std::vector<double> vec;
+
+// Eigen::VectorXd::LinSpaced(n, lo, hi): lo + i * (hi - lo) / (n - 1), last element = hi
+vec linspaced(long n, double lo, double hi)
+{
+    vec r((size_t)(n > 0 ? n : 0));
+    if (n <= 0) return r;
+    if (n == 1) { r[0] = hi; return r; }
+    const double step = (hi - lo) / (double)(n - 1);
+    for (long i = 0; i < n; i++) r[(size_t)i] = lo + (double)i * step;
+    r[(size_t)n - 1] = hi;
+    return r;
+}
+
+// linfit (tamcmc/sources/linfit.cpp:16-33): out[0] slope, out[1] intercept
+void linfit(const vec& x, const vec& y, double out[2])
+{
+    double sx = 0, sy = 0;
+    for (double v : x) sx += v;
+    for (double v : y) sy += v;
+    const double n = (double)x.size();
+    const double mean_x = sx / n;
+    double sty = 0, stt = 0;
+    for (size_t i = 0; i < x.size(); i++) { const double t = x[i] - mean_x; sty += t * y[i]; }
+    for (size_t i = 0; i < x.size(); i++) { const double t = x[i] - mean_x; stt += t * t; }
+    out[0] = sty / stt;
+    out[1] = (sy - sx * out[0]) / n;
+}
+
+double vmin(const vec& v) { double m = v[0]; for (double a : v) if (a < m) m = a; return m; }
+double vmax(const vec& v) { double m = v[0]; for (double a : v) if (a > m) m = a; return m; }
+
+// ---------------------------------------------------------------------------------------------- solver_mm.cpp
+// sign_change (solver_mm.cpp:71-106): positions i where x[i] -> x[i+1] crosses (or touches) zero
+void sign_change(const vec& x, std::vector<long>& pos)
+{
+    pos.clear();
+    for (size_t i = 0; i + 1 < x.size(); i++) {
+        if ((x[i + 1] >= 0 && x[i] < 0) || (x[i + 1] > 0 && x[i] <= 0)) pos.push_back((long)i);       // - to +
+        if ((x[i + 1] <= 0 && x[i] > 0) || (x[i + 1] <= 0 && x[i] >= 0)) pos.push_back((long)i);      // + to -
+    }
+}
+
+// p(nu) - g(nu): pnu_fct (solver_mm.cpp:114-127) minus gnu_fct (solver_mm.cpp:150-161) as their VectorXd versions compute one
+// element (double arithmetic, the long double scalars converted first)
+struct PminusG {
+    double nu_p_d, inv_g, pi_d, DPl_d, q_d, Dnu_d;
+    PminusG(ld nu_p, ld nu_g, ld Dnu_p, ld DPl, ld q)
+        : nu_p_d((double)nu_p), inv_g(1.0 / (double)nu_g), pi_d((double)3.141592653589793238L), DPl_d((double)DPl), q_d((double)q), Dnu_d((double)Dnu_p) {}
+    double operator()(double nu) const
+    {
+        const double pnu = nu - nu_p_d;
+        const double X = ((pi_d * (1.0 / nu - inv_g)) * 1e6) / DPl_d;
+        const double t = q_d * std::tan(X);
+        const double gnu = (Dnu_d * std::atan(t)) / pi_d;
+        return pnu - gnu;
+    }
+};
+
+// lin_interpol(f(nu_local), nu_local, 0) (tamcmc/sources/interpol.cpp:13-43) with f evaluated ON DEMAND: the function reads
+// both end values, then either walks from the left until it brackets zero (an increasing crossing) or -- when f runs from + to
+// -, which is what the jump of g at a pole of the tangent looks like -- only the first and the last two values.  Same
+// comparisons and arithmetic as lin_interpol on the full vector; a fraction of the tan / atan calls.
+double interp_zero_lazy(const vec& y /*nu_local*/, const PminusG& F, vec& val, std::vector<unsigned char>& have)
+{
+    const int Nx = (int)y.size();
+    val.assign((size_t)Nx, 0.0); have.assign((size_t)Nx, 0);
+    auto X = [&](int i) { if (!have[(size_t)i]) { val[(size_t)i] = F(y[(size_t)i]); have[(size_t)i] = 1; } return val[(size_t)i]; };
+    const double x_int = 0.0;
+    int i = 0;
+    double a = 0, b = 0;
+    if (x_int >= X(0) && x_int <= X(Nx - 1)) {
+        while ((x_int < X(i) || x_int > X(i + 1)) && i < Nx - 2) i = i + 1;
+        a = (y[(size_t)i + 1] - y[(size_t)i]) / (X(i + 1) - X(i));
+        b = y[(size_t)i] - a * X(i);
+    }
+    if (x_int < X(0)) { a = (y[1] - y[0]) / (X(1) - X(0)); b = y[0] - a * X(0); }
+    if (x_int > X(Nx - 1)) { a = (y[(size_t)Nx - 1] - y[(size_t)Nx - 2]) / (X(Nx - 1) - X(Nx - 2)); b = y[(size_t)Nx - 2] - a * X(Nx - 2); }
+    return a * x_int + b;
+}
+
+// gnu_fct for one frequency (solver_mm.cpp:172-180), long double throughout
+ld gnu_scalar(ld nu, ld nu_g, ld Dnu_p, ld DPl, ld q)
+{
+    const ld pi = 3.141592653589793238L;
+    const ld X = pi * (1. / nu - 1. / nu_g) * 1e6 / DPl;
+    return Dnu_p * atanl(q * tanl(X)) / pi;
+}
+
+// solver_mm (solver_mm.cpp:326-449): intersections of p(nu) = nu - nu_p and g(nu) for ONE (p mode, g mode) pair.
+// The reference evaluates p - g on the whole grid [numin, numax] (3.5 large separations at the spectrum's resolution) and keeps
+// the sign changes.  |g(nu)| = |Dnu atan(.)/pi| <= Dnu/2, so outside |nu - nu_p| <= Dnu/2 the difference has the sign of nu - nu_p
+// and cannot change sign: only the grid points of that band (plus a margin of a few points) are evaluated -- the same grid
+// values, hence the same sign-change indices and the same solutions, for less than a third of the tan / atan calls.
+void solver_mm(ld nu_p, ld nu_g, ld Dnu_p, ld DPl, ld q, ld numin, ld numax, ld resol, ld factor, vec& nu_m)
+{
+    nu_m.clear();
+    if (!(nu_g >= numin && nu_g <= numax)) return;
+    const long n = (numin >= 0) ? (long)((numax - numin) / resol) : (long)((numax) / resol);
+    const double lo = (numin >= 0) ? (double)numin : 0.0, hi = (double)numax;
+    if (n < 2) return;
+    const double gstep = (hi - lo) / (double)(n - 1);
+    auto grid = [&](long i) { return (i == n - 1) ? hi : lo + (double)i * gstep; };      // Eigen::VectorXd::LinSpaced(n, lo, hi)[i]
+    long i_lo = 0, i_hi = n - 1;
+    {
+        const double half = 0.5 * std::fabs((double)Dnu_p) * (1.0 + 1e-9) + 4.0 * std::fabs(gstep);
+        const double a = ((double)nu_p - half - lo) / gstep, b = ((double)nu_p + half - lo) / gstep;
+        if (std::isfinite(a) && std::isfinite(b) && gstep > 0) {
+            i_lo = std::max(0L, (long)std::floor(a) - 2);
+            i_hi = std::min(n - 1, (long)std::ceil(b) + 2);
+        }
+        if (i_hi < i_lo + 1) return;                                                     // the band lies outside the grid: no sign change
+    }
+    vec nu((size_t)(i_hi - i_lo + 1));
+    for (long i = i_lo; i <= i_hi; i++) nu[(size_t)(i - i_lo)] = grid(i);
+    vec f(nu.size()), nu_local, f_local;
+    std::vector<unsigned char> have;
+    std::vector<long> idx;
+    const PminusG F(nu_p, nu_g, Dnu_p, DPl, q);
+    for (size_t i = 0; i < nu.size(); i++) f[i] = F(nu[i]);
+    sign_change(f, idx);
+    for (size_t k = 0; k < idx.size(); k++) {
+        const ld range_min = nu[(size_t)idx[k]] - 2 * resol, range_max = nu[(size_t)idx[k]] + 2 * resol;
+        nu_local = linspaced((long)((range_max - range_min) / (resol * factor)), (double)range_min, (double)range_max);
+        if (nu_local.size() < 2) continue;
+        const ld nu_m_proposed = interp_zero_lazy(nu_local, F, f_local, have);
+        const ld ysol_gnu = gnu_scalar(nu_m_proposed, nu_g, Dnu_p, DPl, q);
+        const ld ysol_pnu = nu_m_proposed - nu_p;
+        const ld ratio = ysol_gnu / ysol_pnu;
+        // only intersections that really satisfy p = g (to 0.1 %) are kept: the arctan branch cuts produce spurious sign changes
+        if ((ratio >= 0.999) && (ratio <= 1.001)) nu_m.push_back((double)nu_m_proposed);
+    }
+}
+
+struct Eigensols { vec nu_m, nu_p, nu_g, dnup, dPg; bool ok = false; };
+
+// Frstder_adaptive_reggrid(y) (derivatives_handler.cpp:425-444): one-sided differences at the ends, centred inside
+vec first_derivative(const vec& y)
+{
+    const size_t n = y.size();
+    vec d(n, 0.0);
+    if (n < 2) return d;
+    d[0] = y[1] - y[0];
+    d[n - 1] = y[n - 1] - y[n - 2];
+    for (size_t i = 0; i + 2 < n; i++) d[i + 1] = (y[i + 2] - y[i]) / 2.;
+    return d;
+}
+
+// the pair loop shared by the two entry points + sort + std::unique with tolerance (solver_mm.cpp:558-590, 706-740)
+// dnu_local[np]: the local large separation handed to solver_mm; centre +- zone[np] is the search range
+void solve_pairs(const vec& nu_p_all, const vec& nu_g_all, const vec& dnu_local, const std::vector<ld>& lo, const std::vector<ld>& hi, ld DPl, ld q,
+                 ld resol, double fact, ld keep_min, ld keep_max, vec& nu_m_all)
+{
+    const long Np = (long)nu_p_all.size(), Ng = (long)nu_g_all.size();
+    std::vector<vec> found((size_t)(Np * Ng));
+#ifdef _OPENMP
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
+#endif
+    for (long np = 0; np < Np; np++)
+        for (long ng = 0; ng < Ng; ng++)
+            solver_mm(nu_p_all[(size_t)np], nu_g_all[(size_t)ng], dnu_local[(size_t)np], DPl, q, lo[(size_t)np], hi[(size_t)np], resol, fact,
+                      found[(size_t)(np * Ng + ng)]);
+    vec all;
+    for (const vec& v : found)
+        for (double s : v)
+            if ((ld)s >= keep_min && (ld)s <= keep_max) all.push_back(s);
+    std::sort(all.begin(), all.end());
+    const double tol = (double)(2 * resol);
+    nu_m_all.clear();
+    for (double s : all)                                            // std::unique: compare with the last element KEPT
+        if (nu_m_all.empty() || !(std::abs(nu_m_all.back() - s) <= tol)) nu_m_all.push_back(s);
+}
+
+// ng range and search parameters common to both entry points (solver_mm.cpp:497-533, 649-683)
+bool g_mode_setup(ld fmin, ld fmax, ld DPl, ld alpha, int& ng_min, int& ng_max, double& fact)
+{
+    ng_min = (int)floorl(1e6 / (fmax * DPl) - alpha);
+    ng_max = (int)ceill(1e6 / (fmin * DPl) - alpha);
+    if (ng_min <= 0 && ng_max < 1) return false;                    // "You requested an impossible star": the reference returns nothing
+    if (ng_min <= 0 && ng_max >= 1) ng_min = 1;
+    fact = 0.04;
+    if (fmin <= 150) fact = 0.01;
+    if (fmin <= 50) fact = 0.005;
+    return true;
+}
+
+// solve_mm_asymptotic_O2from_l0 (solver_mm.cpp:624-746), sigma_p = 0
+void solve_from_l0(const vec& nu_l0_in, int el, ld delta0l, ld DPl, ld alpha, ld q, ld resol, ld freq_min, ld freq_max, Eigensols& S)
+{
+    S = Eigensols();
+    const size_t n0 = nu_l0_in.size();
+    double fit[2];
+    linfit(linspaced((long)n0, 0.0, (double)(n0 - 1)), nu_l0_in, fit);
+    const double Dnu_p = fit[0];
+    double fmin = vmin(nu_l0_in) - Dnu_p, fmax = vmax(nu_l0_in) + Dnu_p;
+    if (fmin < 0) fmin = 0;
+    int ng_min, ng_max; double fact;
+    if (!g_mode_setup(fmin, fmax, DPl, alpha, ng_min, ng_max, fact)) return;
+    const double Coeff = (ng_max - ng_min < 6) ? 20 : 1.75;
+    // asympt_nu_p_from_l0_Xd (solver_mm.cpp:263-304): the l=0 comb extended by three orders on each side, shifted to degree el
+    {
+        const ld Dnu = Dnu_p;
+        vec l0_long(n0 + 6);
+        l0_long[0] = (double)(vmin(nu_l0_in) - 3 * Dnu); l0_long[1] = (double)(vmin(nu_l0_in) - 2 * Dnu); l0_long[2] = (double)(vmin(nu_l0_in) - Dnu);
+        for (size_t k = 0; k < n0; k++) l0_long[k + 3] = nu_l0_in[k];
+        l0_long[n0 + 3] = (double)(vmax(nu_l0_in) + Dnu); l0_long[n0 + 4] = (double)(vmax(nu_l0_in) + 2 * Dnu); l0_long[n0 + 5] = (double)(vmax(nu_l0_in) + 3 * Dnu);
+        const double shift = (double)(el / 2. * Dnu + delta0l);
+        const double lo = (double)(ld)fmin, hi = (double)(ld)fmax;               // (fmin == -1 / fmax == -1 defaults do not occur: both are >= 0 here)
+        for (double v : l0_long) { const double s = v + shift; if (s >= lo && s <= hi) S.nu_p.push_back(s); }
+        if (S.nu_p.empty()) return;                                             // the reference exits: "No frequency found in the specified range"
+    }
+    for (int ng = ng_min; ng < ng_max; ng++) S.nu_g.push_back((double)(1e6 / ((ng + alpha) * DPl + 0)));     // asympt_nu_g, solver_mm.cpp:314-318
+    S.dnup = first_derivative(S.nu_p);
+    S.dPg.assign(S.nu_g.size(), (double)DPl);
+    std::vector<ld> lo(S.nu_p.size()), hi(S.nu_p.size());
+    for (size_t np = 0; np < S.nu_p.size(); np++) { lo[np] = S.nu_p[np] - Coeff * Dnu_p; hi[np] = S.nu_p[np] + Coeff * Dnu_p; }     // double arithmetic
+    solve_pairs(S.nu_p, S.nu_g, S.dnup, lo, hi, DPl, q, resol, fact, freq_min, freq_max, S.nu_m);
+    S.ok = true;
+}
+
+// solve_mm_asymptotic_O2p (solver_mm.cpp:470-604), sigma_p = 0
+int solve_O2p(ld Dnu_p, ld epsilon, int el, ld delta0l, ld alpha_p, ld nmax, ld DPl, ld alpha, ld q, ld fmin, ld fmax, ld resol, Eigensols& S)
+{
+    S = Eigensols();
+    int np_min = (int)floorl(fmin / Dnu_p - epsilon - el / 2 - delta0l);         // el / 2: integer division like the reference
+    int np_max = (int)ceill(fmax / Dnu_p - epsilon - el / 2 - delta0l);
+    np_min = (int)floorl(np_min - alpha_p * powl(np_min - nmax, 2) / 2.);
+    np_max = (int)ceill(np_max + alpha_p * powl(np_max - nmax, 2) / 2.);
+    int ng_min, ng_max; double fact;
+    if (!g_mode_setup(fmin, fmax, DPl, alpha, ng_min, ng_max, fact)) return TAMCMC_OK;
+    const double Coeff = (ng_max - ng_min < 6) ? (double)np_max : 1.75;
+    if (np_min <= 0) np_min = 1;
+    for (int np = np_min; np < np_max; np++) {
+        const ld nu_p = (np + epsilon + el / 2. + delta0l + alpha_p * powl(np - nmax, 2) / 2) * Dnu_p;     // asympt_nu_p, solver_mm.cpp:201-215
+        if (nu_p < 0.0) return TAMCMC_ERR_NONFINITE;                                                       // the reference exits
+        S.nu_p.push_back((double)(nu_p + 0));
+    }
+    for (int ng = ng_min; ng < ng_max; ng++) S.nu_g.push_back((double)(1e6 / ((ng + alpha) * DPl + 0)));
+    if (S.nu_p.empty()) { S.ok = true; return TAMCMC_OK; }
+    S.dnup = first_derivative(S.nu_p);
+    S.dPg.assign(S.nu_g.size(), (double)DPl);
+    vec dnu_local(S.nu_p.size());
+    std::vector<ld> lo(S.nu_p.size()), hi(S.nu_p.size());
+    for (size_t np = 0; np < S.nu_p.size(); np++) {
+        dnu_local[np] = (double)(Dnu_p * (1.0 + alpha_p * (np + np_min - nmax)));
+        lo[np] = S.nu_p[np] - Coeff * Dnu_p; hi[np] = S.nu_p[np] + Coeff * Dnu_p;                           // long double arithmetic (Dnu_p is)
+    }
+    solve_pairs(S.nu_p, S.nu_g, dnu_local, lo, hi, DPl, q, resol, fact, fmin, fmax, S.nu_m);
+    S.ok = true;
+    return TAMCMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- bump_DP.cpp
+// Sum over (np, ng) of ksi_fct1 (bump_DP.cpp:46-64) at every frequency of `nu`, in the reference's single-thread order: for each
+// np a local sum over ng, then added to the total (bump_DP.cpp:137-151).  One term is
+//     1 / (1 + front * cos^2(up) / cos^2(down)),   up = (pi 1e6 (1/nu - 1/nu_g)) / DPl,  down = (pi (nu - nu_p)) / Dnu_p,
+//     front = ((1e-6 nu^2) DPl) / (q Dnu_p):
+// `up` depends on (nu, ng) only and `down` on (nu, np) only, so the Lp + Lg cosines of a frequency are taken once instead of
+// 2 Lp Lg times -- the same arguments give the same cosines, every other operation is unchanged.
+void ksi_sum(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, const vec& DPl, ld q, vec& out)
+{
+    const ld pi = M_PI;
+    const size_t Lp = nu_p.size(), Lg = nu_g.size();
+    const double c_up = (double)(pi * 1e6), pi_d = (double)pi;
+    std::vector<double> inv_g(Lg), qD(Lp);
+    for (size_t g = 0; g < Lg; g++) inv_g[g] = (double)(1. / (ld)nu_g[g]);
+    for (size_t p = 0; p < Lp; p++) qD[p] = (double)(q * (ld)Dnu_p[p]);
+    out.assign(nu.size(), 0.0);
+    const long N = (long)nu.size();
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        std::vector<double> cu2(Lg), cd2(Lp), nd(Lg);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (long i = 0; i < N; i++) {
+            const double v = nu[(size_t)i];
+            const double inv = 1.0 / v, sq = 1e-6 * (v * v);
+            for (size_t g = 0; g < Lg; g++) { const double c = std::cos((c_up * (inv - inv_g[g])) / DPl[g]); cu2[g] = c * c; nd[g] = sq * DPl[g]; }
+            for (size_t p = 0; p < Lp; p++) { const double c = std::cos((pi_d * (v - nu_p[p])) / Dnu_p[p]); cd2[p] = c * c; }
+            double tot = 0.0;
+            for (size_t p = 0; p < Lp; p++) {
+                double loc = 0.0;
+                for (size_t g = 0; g < Lg; g++) loc += 1.0 / (1.0 + (nd[g] / qD[p]) * (cu2[g] / cd2[p]));
+                tot += loc;
+            }
+            out[(size_t)i] = tot;
+        }
+    }
+}
+
+// ksi_fct2(..., "precise") = ksi_fct2_precise (bump_DP.cpp:126-177): normalised by the maximum over a 4-year-resolution grid
+bool ksi_fct2_precise(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, const vec& DPl, ld q, vec& ksi_pg)
+{
+    if (nu_p.empty() || nu_g.empty()) return false;
+    const ld resol = 1e6 / (4 * 365. * 86400.);
+    const ld fmin = (vmin(nu_p) >= vmin(nu_g)) ? vmin(nu_g) : vmin(nu_p);
+    const ld fmax = (vmax(nu_p) >= vmax(nu_g)) ? vmax(nu_p) : vmax(nu_g);
+    const int Ndata = (int)((fmax - fmin) / resol);
+    if (Ndata < 1) return false;
+    const vec nu_highres = linspaced(Ndata, (double)fmin, (double)fmax);
+    vec ksi_highres;
+    ksi_sum(nu, nu_p, nu_g, Dnu_p, DPl, q, ksi_pg);
+    ksi_sum(nu_highres, nu_p, nu_g, Dnu_p, DPl, q, ksi_highres);
+    const ld norm_coef = vmax(ksi_highres);
+    for (double& v : ksi_pg) { v = v / (double)norm_coef; if (v > 1) v = 1; }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------- tk::spline
+// cubic spline through (x, y) with f'' = 0 at both ends: type 1 = cspline (C2), type 2 = cspline_hermite (C1, 3-point slopes)
+struct Spline {
+    vec x, y, b, c, d;
+    double c0 = 0.0;
+    void set_coeffs_from_b()                                                       // spline.h:219-240
+    {
+        const size_t n = b.size();
+        c.resize(n); d.resize(n);
+        for (size_t i = 0; i + 1 < n; i++) {
+            const double h = x[i + 1] - x[i];
+            c[i] = (3.0 * (y[i + 1] - y[i]) / h - (2.0 * b[i] + b[i + 1])) / h;
+            d[i] = ((b[i + 1] - b[i]) / (3.0 * h) - 2.0 / 3.0 * c[i]) / h;
+        }
+        c0 = c[0];
+    }
+    bool set_points(const vec& xs, const vec& ys, int type)                        // spline.h:242-412
+    {
+        x = xs; y = ys;
+        const int n = (int)x.size();
+        if (n < 3) return false;
+        for (int i = 0; i + 1 < n; i++) if (!(x[(size_t)i] < x[(size_t)i + 1])) return false;
+        if (type == 1) {
+            // tridiagonal system for c[] (band_matrix with one lower and one upper diagonal), solved like band_matrix::lu_solve
+            // (spline.h:685-761): rows scaled to a unit diagonal, Gauss elimination without pivoting, two triangular solves
+            vec lo((size_t)n, 0.0), di((size_t)n, 0.0), up((size_t)n, 0.0), rhs((size_t)n, 0.0), sd((size_t)n, 0.0);
+            for (int i = 1; i < n - 1; i++) {
+                lo[(size_t)i] = 1.0 / 3.0 * (x[(size_t)i] - x[(size_t)i - 1]);
+                di[(size_t)i] = 2.0 / 3.0 * (x[(size_t)i + 1] - x[(size_t)i - 1]);
+                up[(size_t)i] = 1.0 / 3.0 * (x[(size_t)i + 1] - x[(size_t)i]);
+                rhs[(size_t)i] = (y[(size_t)i + 1] - y[(size_t)i]) / (x[(size_t)i + 1] - x[(size_t)i]) - (y[(size_t)i] - y[(size_t)i - 1]) / (x[(size_t)i] - x[(size_t)i - 1]);
+            }
+            di[0] = 2.0; up[0] = 0.0; rhs[0] = 0.0;                                 // 2 c[0] = f'' = 0
+            di[(size_t)n - 1] = 2.0; lo[(size_t)n - 1] = 0.0; rhs[(size_t)n - 1] = 0.0;
+            for (int i = 0; i < n; i++) {
+                sd[(size_t)i] = 1.0 / di[(size_t)i];
+                if (i >= 1) lo[(size_t)i] *= sd[(size_t)i];
+                if (i < n - 1) up[(size_t)i] *= sd[(size_t)i];
+                di[(size_t)i] = 1.0;
+            }
+            for (int k = 0; k + 1 < n; k++) {
+                const double f = -lo[(size_t)k + 1] / di[(size_t)k];
+                lo[(size_t)k + 1] = -f;
+                di[(size_t)k + 1] = di[(size_t)k + 1] + f * up[(size_t)k];
+            }
+            vec yy((size_t)n);
+            for (int i = 0; i < n; i++) { double sum = 0; if (i >= 1) sum += lo[(size_t)i] * yy[(size_t)i - 1]; yy[(size_t)i] = (rhs[(size_t)i] * sd[(size_t)i]) - sum; }
+            c.assign((size_t)n, 0.0);
+            for (int i = n - 1; i >= 0; i--) { double sum = 0; if (i < n - 1) sum += up[(size_t)i] * c[(size_t)i + 1]; c[(size_t)i] = (yy[(size_t)i] - sum) / di[(size_t)i]; }
+            b.assign((size_t)n, 0.0); d.assign((size_t)n, 0.0);
+            for (int i = 0; i < n - 1; i++) {
+                d[(size_t)i] = 1.0 / 3.0 * (c[(size_t)i + 1] - c[(size_t)i]) / (x[(size_t)i + 1] - x[(size_t)i]);
+                b[(size_t)i] = (y[(size_t)i + 1] - y[(size_t)i]) / (x[(size_t)i + 1] - x[(size_t)i]) - 1.0 / 3.0 * (2.0 * c[(size_t)i] + c[(size_t)i + 1]) * (x[(size_t)i + 1] - x[(size_t)i]);
+            }
+            const double h = x[(size_t)n - 1] - x[(size_t)n - 2];
+            d[(size_t)n - 1] = 0.0;
+            b[(size_t)n - 1] = 3.0 * d[(size_t)n - 2] * h * h + 2.0 * c[(size_t)n - 2] * h + b[(size_t)n - 2];
+            c0 = c[0];
+            return true;
+        }
+        if (type == 2) {
+            b.assign((size_t)n, 0.0); c.assign((size_t)n, 0.0); d.assign((size_t)n, 0.0);
+            for (int i = 1; i < n - 1; i++) {
+                const double h = x[(size_t)i + 1] - x[(size_t)i], hl = x[(size_t)i] - x[(size_t)i - 1];
+                b[(size_t)i] = -h / (hl * (hl + h)) * y[(size_t)i - 1] + (h - hl) / (hl * h) * y[(size_t)i] + hl / (h * (hl + h)) * y[(size_t)i + 1];
+            }
+            { const double h = x[1] - x[0]; b[0] = 0.5 * (-b[1] - 0.5 * 0.0 * h + 3.0 * (y[1] - y[0]) / h); }
+            {
+                const double h = x[(size_t)n - 1] - x[(size_t)n - 2];
+                b[(size_t)n - 1] = 0.5 * (-b[(size_t)n - 2] + 0.5 * 0.0 * h + 3.0 * (y[(size_t)n - 1] - y[(size_t)n - 2]) / h);
+                c[(size_t)n - 1] = 0.5 * 0.0;
+            }
+            d[(size_t)n - 1] = 0.0;
+            const double c_last = c[(size_t)n - 1];
+            set_coeffs_from_b();
+            c[(size_t)n - 1] = c_last; d[(size_t)n - 1] = 0.0;                     // set_coeffs_from_b leaves the last entries as set above
+            return true;
+        }
+        return false;
+    }
+    double operator()(double xv) const                                              // spline.h:480-503
+    {
+        const size_t n = x.size();
+        const long it = (long)(std::upper_bound(x.begin(), x.end(), xv) - x.begin());
+        const size_t idx = (size_t)std::max(it - 1, 0L);
+        const double h = xv - x[idx];
+        if (xv < x[0]) return (c0 * h + b[0]) * h + y[0];
+        if (xv > x[n - 1]) return (c[n - 1] * h + b[n - 1]) * h + y[n - 1];
+        return ((d[idx] * h + c[idx]) * h + b[idx]) * h + y[idx];
+    }
+};
+
+// Appourchaux et al. 2014 / 2016 width relation as the model functions evaluate it (models.cpp:4788-4794, 4974-4977)
+inline double app_width(double f, const double g[6])
+{
+    const double lnGamma0 = g[2] * std::log(f / g[0]) + std::log(g[3]);
+    const double e = 2. * std::log(f / g[1]) / std::log(g[4] / g[0]);
+    const double lnLorentz = -std::log(g[5]) / (1. + std::pow(e, 2));
+    return std::exp(lnGamma0 + lnLorentz);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Replaces: solve_mm_asymptotic_O2from_l0 (external/ARMM/solver_mm.cpp:624-746) with sigma_p = 0, returns_pg_freqs = true.
+// Arrays of capacity `cap`; counts in n_m, n_p, n_g.  Returns TAMCMC_ERR_ARG when a capacity is too small, TAMCMC_ERR_NONFINITE
+// where the reference gives up ("impossible star", no p mode in range).
+int tamcmc_host_armm_solve_from_l0(const double* nu_l0, int n_l0, int el, double delta0l, double DPl, double alpha, double q, double resol,
+                                   double freq_min, double freq_max, int cap, double* nu_m, int* n_m, double* nu_p, double* dnup, int* n_p,
+                                   double* nu_g, int* n_g)
+{
+    if (!nu_l0 || n_l0 < 2 || !nu_m || !n_m || cap < 1) return TAMCMC_ERR_ARG;
+    Eigensols S;
+    solve_from_l0(vec(nu_l0, nu_l0 + n_l0), el, delta0l, DPl, alpha, q, resol, freq_min, freq_max, S);
+    if (!S.ok) return TAMCMC_ERR_NONFINITE;
+    if ((int)S.nu_m.size() > cap || (int)S.nu_p.size() > cap || (int)S.nu_g.size() > cap) return TAMCMC_ERR_ARG;
+    *n_m = (int)S.nu_m.size(); std::copy(S.nu_m.begin(), S.nu_m.end(), nu_m);
+    if (n_p) *n_p = (int)S.nu_p.size();
+    if (nu_p) std::copy(S.nu_p.begin(), S.nu_p.end(), nu_p);
+    if (dnup) std::copy(S.dnup.begin(), S.dnup.end(), dnup);
+    if (n_g) *n_g = (int)S.nu_g.size();
+    if (nu_g) std::copy(S.nu_g.begin(), S.nu_g.end(), nu_g);
+    return TAMCMC_OK;
+}
+
+// Replaces: solve_mm_asymptotic_O2p (external/ARMM/solver_mm.cpp:470-604) with sigma_p = 0, returns_pg_freqs = true.
+int tamcmc_host_armm_solve_O2p(double Dnu_p, double epsilon, int el, double delta0l, double alpha_p, double nmax, double DPl, double alpha,
+                               double q, double fmin, double fmax, double resol, int cap, double* nu_m, int* n_m, double* nu_p, double* dnup,
+                               int* n_p, double* nu_g, int* n_g)
+{
+    if (!nu_m || !n_m || cap < 1) return TAMCMC_ERR_ARG;
+    Eigensols S;
+    const int rc = solve_O2p(Dnu_p, epsilon, el, delta0l, alpha_p, nmax, DPl, alpha, q, fmin, fmax, resol, S);
+    if (rc) return rc;
+    if (!S.ok) return TAMCMC_ERR_NONFINITE;
+    if ((int)S.nu_m.size() > cap || (int)S.nu_p.size() > cap || (int)S.nu_g.size() > cap) return TAMCMC_ERR_ARG;
+    *n_m = (int)S.nu_m.size(); std::copy(S.nu_m.begin(), S.nu_m.end(), nu_m);
+    if (n_p) *n_p = (int)S.nu_p.size();
+    if (nu_p) std::copy(S.nu_p.begin(), S.nu_p.end(), nu_p);
+    if (dnup) std::copy(S.dnup.begin(), S.dnup.end(), dnup);
+    if (n_g) *n_g = (int)S.nu_g.size();
+    if (nu_g) std::copy(S.nu_g.begin(), S.nu_g.end(), nu_g);
+    return TAMCMC_OK;
+}
+
+// Replaces: tk::spline set_boundary(second_deriv, 0, second_deriv, 0) + set_points(x, y, cspline | cspline_hermite) + operator()
+// (external/spline/src/spline.h), as the bias of the l=1 mixed modes uses it (models.cpp:4834-4843, 4870-4874).  type: 1 cubic, 2 Hermite.
+int tamcmc_host_spline_eval(const double* x, const double* y, int n, int type, const double* xq, int nq, double* out)
+{
+    if (!x || !y || !xq || !out || n < 3 || nq < 0) return TAMCMC_ERR_ARG;
+    Spline s;
+    if (!s.set_points(vec(x, x + n), vec(y, y + n), type)) return TAMCMC_ERR_ARG;
+    for (int i = 0; i < nq; i++) out[i] = s(xq[i]);
+    return TAMCMC_OK;
+}
+
+// Replaces: the host half of model_RGB_asympt_aj_AppWidth_HarveyLike_v4 (model_id 25, models.cpp:4684-4927) and of
+// model_RGB_asympt_aj_CteWidth_HarveyLike_v4 (model_id 27, models.cpp:4334-4556): params / plength in those models' layout
+//   params = [H(Nmax) | V_l(lmax) | fl0(Nfl0) | l=1 block(Nfl1) = delta0l, DPl, alpha_g, q, -, -, Wfactor, Hfactor, fref[Nferr], ferr[Nferr]
+//             | fl2 | fl3 | split(Nsplit) = rot_env, rot_core, a2_env, a2_core, a3_env, a4_env, a5_env, a6_env, eta_switch, asym
+//             | width(Nwidth) | noise(Nnoise) | inc | cfg = trunc_c, do_amp, sigma_limit, model_type, bias_type, Nferr]
+// -> ONE mode-table row of `capacity` modes (row_out: TAMCMC_MT_HEADER + Nnoise + TAMCMC_MT_STRIDE * capacity doubles), modes in the
+// reference's call order (all l=0, the mixed l=1 modes, l=2, l=3).  step = x[2] - x[1] of the spectrum (models.cpp:4714): the
+// resolution of the mixed-mode solver's grid.  *nmodes_out receives the number of modes (the l=1 count varies from chain to chain);
+// TAMCMC_ERR_ARG with *nmodes_out set when it exceeds `capacity`.
+int tamcmc_host_expand_rgb_v4(int model_id, const double* params, const int* plength, double step, int capacity, double* row_out,
+                              int* nmodes_out)
+{
+    if (!params || !plength || !row_out || capacity < 1) return TAMCMC_ERR_ARG;
+    if (model_id != 25 && model_id != 27) return TAMCMC_ERR_MODEL;
+    const bool app = (model_id == 25);
+    const int Nmax = plength[0], lmax = plength[1], Nfl0 = plength[2], Nfl1 = plength[3], Nfl2 = plength[4], Nfl3 = plength[5];
+    const int Nsplit = plength[6], Nwidth = plength[7], Nnoise = plength[8], Ninc = plength[9], Ncfg = plength[10];
+    const int Nf = Nfl0 + Nfl1 + Nfl2 + Nfl3;
+    const int o_cfg = Nmax + lmax + Nf + Nsplit + Nwidth + Nnoise + Ninc;
+    if (Nmax < 2 || Nfl0 != Nmax || lmax < 1 || lmax > 3 || Nsplit < 10 || Nnoise < 1 || Ncfg < 6 || Nwidth < (app ? 6 : 1) || Nfl1 < 8) return TAMCMC_ERR_ARG;
+    const double trunc_c = params[o_cfg];
+    const bool do_amp = params[o_cfg + 1] != 0.0;
+    const double model_type = params[o_cfg + 3], bias_type = params[o_cfg + 4];
+    const int Nferr = (int)params[o_cfg + 5];
+    if (Nferr < 0 || Nfl1 < 8 + 2 * Nferr) return TAMCMC_ERR_ARG;
+    const ld pi = M_PI;
+    const int o_w = Nmax + lmax + Nf + Nsplit;
+    double gp[6] = {0, 0, 0, 0, 0, 0};
+    if (app) for (int k = 0; k < 6; k++) gp[k] = std::abs(params[o_w + k]);
+    const double inclination = std::abs(params[Nmax + lmax + Nf + Nsplit + Nwidth + Nnoise]);
+    const double Vl1 = std::abs(params[Nmax]);
+    const double Vl2 = (lmax >= 2) ? std::abs(params[Nmax + 1]) : 0.0, Vl3 = (lmax >= 3) ? std::abs(params[Nmax + 2]) : 0.0;
+
+    // ---- l = 0: frequencies, widths, heights (models.cpp:4784-4803 / 4433-4442) ----
+    const vec fl0_all(params + Nmax + lmax, params + Nmax + lmax + Nfl0);
+    vec Wl0_all((size_t)Nmax), Hl0_all((size_t)Nmax);
+    for (int n = 0; n < Nmax; n++) Wl0_all[(size_t)n] = app ? app_width(fl0_all[(size_t)n], gp) : std::abs(params[o_w]);
+    for (int n = 0; n < Nmax; n++)
+        Hl0_all[(size_t)n] = do_amp ? std::abs(params[n] * ((1.0 / Wl0_all[(size_t)n]) / (double)pi)) : std::abs(params[n]);
+
+    // ---- mixed modes (models.cpp:4811-4866) ----
+    const int o_l1 = Nmax + lmax + Nfl0;
+    const double delta0l = params[o_l1], DPl = std::abs(params[o_l1 + 1]), alpha_g = std::abs(params[o_l1 + 2]), q_star = std::abs(params[o_l1 + 3]);
+    const double Wfactor = std::abs(params[o_l1 + 6]), Hfactor = std::abs(params[o_l1 + 7]);
+    const int o_s = Nmax + lmax + Nf;
+    const double rot_env = std::abs(params[o_s]), rot_core = std::abs(params[o_s + 1]);
+    const double a2_env = params[o_s + 2], a3_env = params[o_s + 4], a4_env = params[o_s + 5], a5_env = params[o_s + 6], a6_env = params[o_s + 7];
+    const double eta_switch = params[o_s + 8], asym = params[o_s + 9];
+    vec fref_all((size_t)Nferr), ferr_all((size_t)Nferr);
+    for (int i = 0; i < Nferr; i++) { fref_all[(size_t)i] = params[o_l1 + 8 + i]; ferr_all[(size_t)i] = params[o_l1 + 8 + Nferr + i]; }
+    Spline bias;
+    if (bias_type != 0) {
+        if (bias_type != 1 && bias_type != 2) return TAMCMC_ERR_MODEL;          // (the reference would evaluate an unset spline)
+        if (!bias.set_points(fref_all, ferr_all, (int)bias_type)) return TAMCMC_ERR_ARG;      // tk::spline asserts >= 3 strictly increasing points
+    }
+    const double fmin = vmin(fl0_all), fmax = vmax(fl0_all);
+    Eigensols S;
+    if (app || model_type == 0) {
+        double rfit[2];
+        linfit(linspaced(Nmax, 0.0, (double)(Nmax - 1)), fl0_all, rfit);
+        const double Dnu_p = rfit[0];
+        const int n0 = (int)std::floor(rfit[1] / Dnu_p);
+        const double epsilon_p = rfit[1] / Dnu_p - n0;
+        if (fmin - Dnu_p < 0) return TAMCMC_ERR_NONFINITE;                       // "THE ARMM WILL NOT CONVERGE": the reference exits (models.cpp:4852-4858)
+        if (model_type == 0) {
+            const int rc = solve_O2p(Dnu_p, epsilon_p, 1, delta0l, 0, 0., DPl, alpha_g, q_star, fmin - Dnu_p, fmax + Dnu_p, step, S);
+            if (rc) return rc;
+        }
+    }
+    if (model_type != 0) solve_from_l0(fl0_all, 1, delta0l, DPl, alpha_g, q_star, step, fmin, fmax, S);
+    if (!S.ok || S.nu_m.empty()) return TAMCMC_ERR_NONFINITE;                    // no mixed mode: the reference indexes empty vectors from here on
+    vec fl1_all = S.nu_m;
+    if (bias_type != 0) for (double& f : fl1_all) f = f + bias(f);              // models.cpp:4868-4874
+    vec ksi_pg;
+    if (!ksi_fct2_precise(fl1_all, S.nu_p, S.nu_g, S.dnup, S.dPg, q_star, ksi_pg)) return TAMCMC_ERR_NONFINITE;
+    const size_t N1 = fl1_all.size();
+    // h_l_rgb (bump_DP.cpp:235-253)
+    vec h1_h0((size_t)N1);
+    for (size_t i = 0; i < N1; i++) {
+        double v = std::sqrt(1.0 - (double)(ld)Hfactor * ksi_pg[i]);
+        if (v > 0 - 1e-5 && v < 0 + 1e-5) v = 1e-10;
+        h1_h0[i] = v;
+    }
+    // heights of the l=1 modes: l=0 heights interpolated with zero anchors outside the comb (models.cpp:4879-4905)
+    vec f_interp((size_t)Nmax + 4), h_interp((size_t)Nmax + 4);
+    f_interp[0] = fmin * 0.6; f_interp[1] = fmin * 0.8; f_interp[(size_t)Nmax + 2] = fmax * 1.2; f_interp[(size_t)Nmax + 3] = fmax * 1.4;
+    h_interp[0] = 0; h_interp[1] = Hl0_all[0] / 4; h_interp[(size_t)Nmax + 2] = Hl0_all[(size_t)Nmax - 1] / 4; h_interp[(size_t)Nmax + 3] = 0;
+    for (int j = 0; j < Nmax; j++) { f_interp[(size_t)j + 2] = fl0_all[(size_t)j]; h_interp[(size_t)j + 2] = Hl0_all[(size_t)j]; }
+    vec Hl1_all(N1), Wl1_all(N1), a1_l1(N1);
+    for (size_t i = 0; i < N1; i++) {
+        const double tmp = tamcmc_host::lin_interpol(f_interp.data(), h_interp.data(), Nmax + 4, fl1_all[i]);
+        const double Hl1p = (tmp < 0) ? 0.0 : std::abs(tmp);
+        Hl1_all[i] = h1_h0[i] * (Hl1p * Vl1);
+        // gamma_l_fct2 (bump_DP.cpp:203-223): long double arithmetic around the interpolated l=0 width
+        const ld width0_at_l = tamcmc_host::lin_interpol(fl0_all.data(), Wl0_all.data(), Nmax, fl1_all[i]);
+        Wl1_all[i] = (double)(width0_at_l * (1. - (ld)Wfactor * ksi_pg[i]) / std::sqrt(h1_h0[i]));
+        // dnu_rot_2zones (bump_DP.cpp:531-537), then abs (models.cpp:4909)
+        a1_l1[i] = std::abs(ksi_pg[i] * (double)((ld)rot_core / 2 - (ld)rot_env) + (double)(ld)rot_env);
+    }
+    const double eta0 = (eta_switch == 1) ? tamcmc_host::eta0_fct(fl0_all.data(), Nmax) : 0.0;
+
+    // ---- the row: header, noise, then one record per optimum_lorentzian_calc_aj call (models.cpp:4931-5006) ----
+    const int nmodes = Nfl0 + (int)N1 + Nfl2 + Nfl3;
+    if (nmodes_out) *nmodes_out = nmodes;
+    if (nmodes > capacity) return TAMCMC_ERR_ARG;
+    const int row_len = TAMCMC_MT_HEADER + Nnoise + TAMCMC_MT_STRIDE * capacity;
+    std::memset(row_out, 0, sizeof(double) * (size_t)row_len);
+    row_out[0] = nmodes; row_out[1] = inclination; row_out[2] = trunc_c; row_out[3] = asym;
+    for (int k = 0; k < Nnoise; k++) row_out[TAMCMC_MT_HEADER + k] = params[Nmax + lmax + Nf + Nsplit + Nwidth + k];
+    double* rec = row_out + TAMCMC_MT_HEADER + Nnoise;
+    int j = 0;
+    for (int n = 0; n < Nfl0; n++, j++) { double* r = rec + (size_t)TAMCMC_MT_STRIDE * j; r[0] = 0; r[1] = fl0_all[(size_t)n]; r[2] = Hl0_all[(size_t)n]; r[3] = Wl0_all[(size_t)n]; }
+    for (size_t n = 0; n < N1; n++, j++) {
+        double* r = rec + (size_t)TAMCMC_MT_STRIDE * j;
+        r[0] = 1; r[1] = fl1_all[n]; r[2] = std::abs(Hl1_all[n]); r[3] = Wl1_all[n]; r[4] = a1_l1[n]; r[10] = eta0;
+    }
+    for (int l = 2; l <= 3; l++) {
+        const int Nfl = (l == 2) ? Nfl2 : Nfl3;
+        const int off = Nmax + lmax + Nfl0 + Nfl1 + ((l == 3) ? Nfl2 : 0);
+        const double Vl = (l == 2) ? Vl2 : Vl3;
+        for (int n = 0; n < Nfl; n++, j++) {
+            double* r = rec + (size_t)TAMCMC_MT_STRIDE * j;
+            const double fl = std::abs(params[off + n]);
+            if (!app && n >= Nmax) return TAMCMC_ERR_ARG;                        // the CteWidth model reads Wl0_all[n] (models.cpp:4597, 4617)
+            const double W = app ? app_width(fl, gp) : Wl0_all[(size_t)n];
+            const double Hi = tamcmc_host::lin_interpol(fl0_all.data(), Hl0_all.data(), Nmax, fl);
+            const double H = do_amp ? (double)fabsl(Hi / (pi * W) * Vl) : std::abs(Hi * Vl);
+            r[0] = l; r[1] = fl; r[2] = H; r[3] = W; r[4] = rot_env; r[5] = a2_env; r[6] = a3_env; r[7] = a4_env;
+            if (l == 3) { r[8] = a5_env; r[9] = a6_env; }
+            r[10] = eta0;
+        }
+    }
+    return TAMCMC_OK;
+}
+
+}  // extern "C"

@@ -59,6 +59,13 @@ class Ref:
         L.ref_max_threads.restype = C.c_int
         L.ref_likelihood_chi_square.restype = C.c_longdouble
         L.ref_likelihood_chi_square.argtypes = [_dp, _dp, _dp, C.c_long]
+        if hasattr(L, "ref_solve_mm_from_l0"):
+            L.ref_solve_mm_from_l0.restype = C.c_int
+            L.ref_solve_mm_from_l0.argtypes = [_dp, C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_int, _dp, _ip, _dp, _dp, _ip, _dp, _ip]
+            L.ref_solve_mm_O2p.restype = C.c_int
+            L.ref_solve_mm_O2p.argtypes = [C.c_double, C.c_double, C.c_int] + [C.c_double] * 9 + [C.c_int, _dp, _ip, _dp, _dp, _ip, _dp, _ip]
+            L.ref_ksi_fct2.argtypes = [_dp, C.c_int, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_double, _dp]
+            L.ref_spline_eval.argtypes = [_dp, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp]
         if hasattr(L, "ref_Alm"):
             L.ref_Alm.restype = C.c_double
             L.ref_Alm.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
@@ -117,6 +124,35 @@ class Ref:
     def chi_square(self, y, model, sigma):
         y, model, sigma = _d(y), _d(model), _d(sigma)
         return float(self.L.ref_likelihood_chi_square(_p(y), _p(model), _p(sigma), len(y)))
+
+    @staticmethod
+    def single_thread():
+        """One OpenMP thread for the calls that follow: the reference's zeta sums (bump_DP.cpp:137-163) and its model loops
+        accumulate under `omp critical`, i.e. in schedule order."""
+        C.CDLL("libgomp.so.1").omp_set_num_threads(1)
+
+    def _sols(self, fn, args, cap=4096):
+        o = [np.zeros(cap) for _ in range(4)]
+        n = [C.c_int(0) for _ in range(3)]
+        rc = fn(*args, cap, _p(o[0]), C.byref(n[0]), _p(o[1]), _p(o[2]), C.byref(n[1]), _p(o[3]), C.byref(n[2]))
+        assert rc == 0
+        return o[0][:n[0].value].copy(), o[1][:n[1].value].copy(), o[2][:n[1].value].copy(), o[3][:n[2].value].copy()
+
+    def solve_mm_from_l0(self, nu_l0, el, delta0l, DPl, alpha, q, resol, fmin, fmax):
+        """solve_mm_asymptotic_O2from_l0 (external/ARMM/solver_mm.cpp:624): -> nu_m, nu_p, dnup, nu_g."""
+        f = _d(nu_l0)
+        return self._sols(self.L.ref_solve_mm_from_l0, (_p(f), len(f), int(el), float(delta0l), float(DPl), float(alpha), float(q), float(resol), float(fmin), float(fmax)))
+
+    def solve_mm_O2p(self, Dnu_p, epsilon, el, delta0l, alpha_p, nmax, DPl, alpha, q, fmin, fmax, resol):
+        """solve_mm_asymptotic_O2p (external/ARMM/solver_mm.cpp:470): -> nu_m, nu_p, dnup, nu_g."""
+        return self._sols(self.L.ref_solve_mm_O2p, (float(Dnu_p), float(epsilon), int(el), float(delta0l), float(alpha_p), float(nmax), float(DPl), float(alpha),
+                                                    float(q), float(fmin), float(fmax), float(resol)))
+
+    def spline_eval(self, x, y, xq, kind=1):
+        x, y, xq = _d(x), _d(y), _d(xq)
+        o = np.zeros(len(xq))
+        self.L.ref_spline_eval(_p(x), _p(y), len(x), int(kind), _p(xq), len(xq), _p(o))
+        return o
 
     def Alm(self, l, m, theta0, delta, filter_code=0):
         """The reference's direct integral Alm() (activity.cpp:221-246); radians."""

@@ -57,15 +57,17 @@ int main(int argc, char** argv)
     for (int m = 0; m < Nmodels; m++) {
         std::memcpy(md.params_row(0, m), &P[(size_t)m * Nparams], sizeof(double) * Nparams);
         md.logPrior[m] = logPrior[m];
-        md.init_logLikelihood[m] = -12345.0 - m;
     }
     const int rc = md.generate_models();
     if (rc != TAMCMC_OK) { std::printf("generate_models rc=%d\n", rc); return 1; }
     int bad = 0;
     for (int m = 0; m < Nmodels; m++) {
         if (std::isinf(logPrior[m])) {
-            // prior short-circuit (model_def.cpp:476-480): init_logLikelihood reused, logPosterior = -inf
-            if (md.logLikelihood[m] != -12345.0 - m || md.logPosterior[m] != -INFINITY) { std::printf("chain %d: short-circuit not honoured\n", m); bad++; }
+            // prior short-circuit (model_def.cpp:476-480): init_logLikelihood reused, logPosterior = -inf.  init_logLikelihood is
+            // what the reference's constructor computes for EVERY chain from the initial parameters "whatever the situation"
+            // (model_def.cpp:142-153) -- here the same vectors, so the oracle's value
+            const double rel0 = std::fabs(md.init_logLikelihood[m] - L_ref[m]) / std::fabs(L_ref[m]);
+            if (md.logLikelihood[m] != md.init_logLikelihood[m] || !(rel0 < 1e-10) || md.logPosterior[m] != -INFINITY) { std::printf("chain %d: short-circuit not honoured\n", m); bad++; }
             continue;
         }
         const double rel = std::fabs(md.logLikelihood[m] - L_ref[m]) / std::fabs(L_ref[m]);
