@@ -193,6 +193,136 @@ def run_reference(args):
     return 0
 
 
+def timed_device_steps(torch, dist, stream, flush, steps, fn):
+    """steps x (L2 flush, CUDA events on the launch stream around fn()); -> total ms, max over ranks."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(steps):
+        flush.zero_()
+        ev0[i].record(stream)
+        fn()
+        ev1[i].record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return ms
+
+
+def extra_c3_bin_sharded(torch, dist, pkg, stream, flush, rank, world, local_rank, steps):
+    """BASELINE config C3 (configs[2]): ONE 10^6-bin ajAlm spectrum, 10 chains, bin-sharded over the ranks.  The path's only
+    exchange step -- one sum per chain -- runs inside the fused kernel over NVLink peer memory (tamcmc_gpu_exchange_*, CUDA IPC
+    buffers; handles travel once through torch.distributed): no collective launch on the data path.  Strong scaling: the work
+    is fixed, `value` = 10 evaluations per step / max-over-ranks device time.  Checked against the REFERENCE's log-likelihoods
+    (tests/golden/reference_c3_c5_fullsize.json)."""
+    import importlib.util
+    import tempfile
+    from importlib import import_module
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    O = _oracle.get()
+    shard = import_module("tamcmc_c_b200.sharding")
+    spec = importlib.util.spec_from_file_location("make_golden_c3_c5", os.path.join(ROOT, "tests", "golden", "make_golden_c3_c5.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_c3_c5_fullsize.json")))["c3"]
+    gdir = tempfile.mkdtemp(prefix="alm_grids_r%d_" % rank)
+    pkg.AlmGrids.make(gdir, 0)
+    pkg.AlmGrids.make(gdir, 2)
+    grids = pkg.AlmGrids(gdir)
+    synth = pkg.synth
+    params, pl, x, y, P, T = mod.c3_inputs(synth, O, lambda l, m, t0, de, fc, user: grids(l, m, t0, de, fc))
+    Nch, N = mod.C3_CHAINS, len(x)
+    cap = int(pl[2:6].sum())
+    nn = int(pl[8])
+    t0 = time.perf_counter()
+    rows = np.stack([pkg.expand_ajAlm(P[c], pl, cap, alm=grids)[0] for c in range(Nch)])
+    host_expand_ms = 1e3 * (time.perf_counter() - t0)
+    mpl = synth.mode_table_plength(cap, nn, 0)
+    if world > 1:
+        rc, _, tr = O.mode_table_model(rows[0], nn, 0, x, trace=True)
+        lo, hi = shard.bin_shards(N, world, shard.bin_work(N, *tr))[rank]
+        star = pkg.Star.shard(synth.MODEL_MODE_TABLE, mpl, rows.shape[1], x, y, lo, hi)
+    else:
+        lo, hi = 0, N
+        star = pkg.Star(synth.MODEL_MODE_TABLE, mpl, rows.shape[1], x, y)
+    with pkg.Context(star, Nch, T, device=local_rank) as ctx:
+        if world > 1:
+            mine = torch.from_numpy(ctx.exchange_handle().copy()).cuda()
+            allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.exchange_attach(rank, world, torch.stack(allh).cpu().numpy())
+            dist.barrier()
+        P_host = ctx.pack_params([rows])
+        d_rows = torch.tensor(P_host, device="cuda")
+        d_L = torch.zeros(Nch, dtype=torch.float64, device="cuda")
+        ms = timed_device_steps(torch, dist, stream, flush, steps, lambda: ctx.eval_device(d_rows.data_ptr(), d_L.data_ptr(), stream=stream.cuda_stream))
+        L = d_L.cpu().numpy()
+        Lr = np.array(gold["logL_reference"])
+        err = float(np.max(np.abs(L - Lr) / np.abs(Lr)))
+        # end to end through the host entry (rows staged by the call, results through the mapped mirror)
+        for _ in range(3):
+            ctx.eval(P_host)
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.eval(P_host)
+        e2e_ms = 1e3 * (time.perf_counter() - t0)
+        if dist:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t[0])
+    grids.close()
+    return {"workload": "C3: MS_Global ajAlm (gate, decompose_Alm=1, Alm from the re-made 1-degree grids), 33 modes l<=2, 10^6 bins, 10 chains",
+            "n_gpus": world, "scaling": "strong (one spectrum, bins sharded)", "bins_this_rank": [int(lo), int(hi)],
+            "value": Nch * steps / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms / steps, "steps": steps,
+            "e2e": {"value": Nch * steps / (e2e_ms * 1e-3), "ms_per_step": e2e_ms / steps},
+            "collective": "none: per-chain sums exchanged by the fused kernel's last CTA through CUDA-IPC peer buffers over NVLink, summed in rank order" if world > 1 else "none (single GPU)",
+            "max_rel_err_vs_reference_logL": err, "parity_ok": bool(err < 1e-10), "host_expand_ms_all_chains": host_expand_ms}
+
+
+def extra_c5_star_sharded(torch, dist, pkg, stream, flush, rank, world, local_rank, steps, nstars=256):
+    """BASELINE config C5 (configs[4]): 256 independent stars x 10 chains x 250k bins, stars sharded over the ranks (star s ->
+    rank s mod world), no communication.  Strong scaling of the fixed 256-star batch."""
+    from importlib import import_module
+    shard = import_module("tamcmc_c_b200.sharding")
+    synth = pkg.synth
+    mine = shard.star_shard(nstars, rank, world)
+    T = synth.tcoefs(NCHAINS, LAMBDA_T)
+    stars, Ps = [], []
+    p0, pl0 = synth.classic_params(np.random.default_rng(0))
+    x = synth.freq_axis(NBINS, 500.0)
+    with pkg.Context(pkg.Star(3, pl0, len(p0), x, np.ones(NBINS)), 1, [1.0], device=local_rank) as c0:
+        for s in mine:
+            rng = np.random.default_rng(12345 + s)
+            dnu = rng.uniform(60.0, 100.0)
+            params, pl = synth.classic_params(rng, f0=620.0 + 0.4 * dnu, dnu=dnu)
+            y = synth.chi2_2dof_spectrum(rng, c0.model(params))
+            stars.append(pkg.Star(3, pl, len(params), x, y))
+            Ps.append(synth.perturb_chains(rng, params, pl, NCHAINS))
+    with pkg.Context(stars, NCHAINS, T, device=local_rank) as ctx:
+        P_host = ctx.pack_params(Ps)
+        L, st = ctx.eval(P_host)
+        ok = bool((st == 0).all() and np.all(np.isfinite(L)))
+        d_p = torch.tensor(P_host, device="cuda")
+        d_L = torch.zeros(len(mine) * NCHAINS, dtype=torch.float64, device="cuda")
+        ms = timed_device_steps(torch, dist, stream, flush, steps, lambda: ctx.eval_device(d_p.data_ptr(), d_L.data_ptr(), stream=stream.cuda_stream))
+        pairs = ctx.pairs_last()
+    return {"workload": "C5: %d independent main-sequence stars (Dnu 60-100 microHz) x 10 chains x 250k bins" % nstars, "n_gpus": world,
+            "scaling": "strong (fixed batch, stars sharded, no collective)", "stars_this_rank": len(mine),
+            "value": nstars * NCHAINS * steps / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms / steps, "steps": steps,
+            "alg_tflops_this_rank": algorithmic_flops(pairs, 0.0, NBINS * len(mine), NCHAINS) * steps / (ms * 1e-3) / 1e12, "all_ok": ok}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +331,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stars-per-gpu", type=int, default=1, help="independent C2 stars batched per launch on each GPU")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 (bin-sharded) and C5 (256 stars) blocks of the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 50:
@@ -220,8 +351,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
 
     # ---- inputs: this rank's independent star(s); y = M_true * Exp(1) with M_true from the GPU model entry ----
     S = args.stars_per_gpu
@@ -309,6 +441,16 @@ def main():
     nprof, expand_ms, whittle_ms = ctx.kernel_ms()
     ctx.set_profiling(False)
 
+    # ---- the two other multi-GPU configs of BASELINE.json (C3 bin-sharded with its exchange step, C5 star-sharded) ----
+    ctx_main_params = None
+    extra = {}
+    if not args.no_extra:
+        for name, fn, st in (("c3_bin_sharded", extra_c3_bin_sharded, 200), ("c5_star_sharded", extra_c5_star_sharded, 20)):
+            try:
+                extra[name] = fn(torch, dist, pkg, stream, flush, rank, world, local_rank, st)
+            except Exception as e:           # the headline line must survive a failing extra block
+                extra[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
     # ---- max over ranks, aggregate ----
     t_dev, t_e2e = dev_ms, e2e_s * 1e3
     if dist:
@@ -361,6 +503,7 @@ def main():
                          "hbm": {"achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "algorithmic_bytes_per_launch": alg_bytes}},
             "clocks": clocks,
+            "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(synth)

@@ -151,6 +151,26 @@ int tamcmc_gpu_eval_device(tamcmc_gpu_ctx *ctx, const double *d_params, const un
 int tamcmc_gpu_pt_swap_device(tamcmc_gpu_ctx *ctx, int star, int A, double u, double *d_params, double *d_logL,
                               double *d_logPrior, int *d_swapped, void *stream);
 
+/* ---- the exchange step of a bin-sharded spectrum (one sum per chain, <= 192 bytes) over NVLink peer memory ----
+ * Every rank holds a context created with tamcmc_gpu_star.N_global / bin_offset (its bin range of the same spectrum, same
+ * Nchains, Tcoefs, p, likelihood).  Once the exchange is attached, an evaluation with raw_sum == 0 returns the log-likelihood
+ * of the WHOLE spectrum on every rank: the last CTA of the rank's fused kernel writes its chains' local sums S into the exchange
+ * buffer of every rank (peer stores), publishes a flag, waits for the other ranks' flags, adds the sums in rank order (bitwise
+ * identical results on all ranks, run to run) and applies -p S / Tcoefs[m] (model_def.cpp:399-401) -- no collective launch, no
+ * host round trip.  All ranks must evaluate in lock step (same number of evaluations); a rank that never arrives ends the wait
+ * after ~2 s with NaN results and TAMCMC_ERR_NONFINITE.
+ *   _create : allocates this rank's exchange buffer; handle_out receives its 64-byte CUDA IPC handle, to be sent to the other
+ *             ranks by whatever the caller uses for plumbing (torch.distributed all_gather, MPI, a file)
+ *   _attach : handles = world x 64 bytes, rank order (entry `rank` is ignored); opens the peers' buffers (cudaIpcOpenMemHandle)
+ *   _attach_ptrs : the same for ranks that live in ONE process (e.g. one thread per GPU): bufs[r] = tamcmc_gpu_exchange_buffer()
+ *             of rank r's context, peer access already enabled by the caller */
+#define TAMCMC_XCHG_HANDLE_BYTES 64
+#define TAMCMC_XCHG_MAX_RANKS 8
+int tamcmc_gpu_exchange_create(tamcmc_gpu_ctx *ctx, void *handle_out);
+int tamcmc_gpu_exchange_attach(tamcmc_gpu_ctx *ctx, int rank, int world, const void *handles);
+int tamcmc_gpu_exchange_attach_ptrs(tamcmc_gpu_ctx *ctx, int rank, int world, void *const *bufs);
+void *tamcmc_gpu_exchange_buffer(tamcmc_gpu_ctx *ctx);
+
 /* Waits for the context's own stream (after tamcmc_gpu_eval_device with stream == NULL) and, when
  * profiling is on, accumulates the CUDA-event durations of that evaluation's kernels. */
 int tamcmc_gpu_sync(tamcmc_gpu_ctx *ctx);

@@ -26,4 +26,7 @@ for r in range(reps):
         print(json.dumps({"variant": name, "rep": r, "us_per_step": round(1e3 * j["ms_per_step"], 2), "evals_per_s": round(j["value"]),
                           "e2e_us": round(1e3 * j["e2e"]["ms_per_step"], 2), "fused_us": round(1e3 * j["roofline"]["kernel_ms"], 2),
                           "expand_us": round(1e3 * j["roofline"]["expand_kernel_ms"], 2), "frac": round(j["roofline"]["frac"], 3),
-                          "sm_mhz": j["clocks"]["sm_mhz"]}), flush=True)
+                          "sm_mhz": j["clocks"]["sm_mhz"],
+                          "c3_us": round(1e3 * j["extra"]["c3_bin_sharded"]["ms_per_step"], 2) if "c3_bin_sharded" in j.get("extra", {}) and "ms_per_step" in j["extra"]["c3_bin_sharded"] else j.get("extra", {}).get("c3_bin_sharded"),
+                          "c3_err": j.get("extra", {}).get("c3_bin_sharded", {}).get("max_rel_err_vs_reference_logL"),
+                          "c5_evals": round(j["extra"]["c5_star_sharded"]["value"]) if "value" in j.get("extra", {}).get("c5_star_sharded", {}) else j.get("extra", {}).get("c5_star_sharded")}), flush=True)

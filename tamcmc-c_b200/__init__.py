@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "tamcmc_gpu_params_stride", "tamcmc_gpu_nstars", "tamcmc_gpu_nchains", "tamcmc_gpu_pairs_last",
     "tamcmc_gpu_set_profiling", "tamcmc_gpu_get_kernel_ms", "tamcmc_gpu_launch_count",
     "tamcmc_gpu_debug_trace", "tamcmc_gpu_fp64_peak", "tamcmc_gpu_strerror", "tamcmc_gpu_last_error", "tamcmc_gpu_abi_version",
+    "tamcmc_gpu_exchange_create", "tamcmc_gpu_exchange_attach", "tamcmc_gpu_exchange_attach_ptrs", "tamcmc_gpu_exchange_buffer",
     "tamcmc_host_alm", "tamcmc_host_expand_ajAlm",
     "tamcmc_host_expand_rgb_v4", "tamcmc_host_armm_solve_from_l0", "tamcmc_host_armm_solve_O2p", "tamcmc_host_spline_eval",
     "tamcmc_alm_grids_load", "tamcmc_alm_grids_free", "tamcmc_alm_grids_eval", "tamcmc_alm_grids_shape", "tamcmc_alm_grids_nodes",
@@ -120,6 +121,14 @@ def lib():
     L.tamcmc_gpu_strerror.argtypes = [C.c_int]
     L.tamcmc_gpu_last_error.restype = C.c_char_p
     L.tamcmc_gpu_abi_version.restype = C.c_int
+    L.tamcmc_gpu_exchange_create.restype = C.c_int
+    L.tamcmc_gpu_exchange_create.argtypes = [vp, vp]
+    L.tamcmc_gpu_exchange_attach.restype = C.c_int
+    L.tamcmc_gpu_exchange_attach.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.tamcmc_gpu_exchange_attach_ptrs.restype = C.c_int
+    L.tamcmc_gpu_exchange_attach_ptrs.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.tamcmc_gpu_exchange_buffer.restype = vp
+    L.tamcmc_gpu_exchange_buffer.argtypes = [vp]
     L.tamcmc_host_alm.restype = C.c_double
     L.tamcmc_host_alm.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
     L.tamcmc_host_expand_ajAlm.restype = C.c_int
@@ -292,6 +301,22 @@ class Context:
     def eval_device(self, d_params_ptr, d_logL_ptr, d_active_ptr=None, raw_sum=False, stream=None):
         rc = lib().tamcmc_gpu_eval_device(self.h, C.c_void_p(d_params_ptr), C.c_void_p(d_active_ptr) if d_active_ptr else None,
                                           C.c_void_p(d_logL_ptr), 1 if raw_sum else 0, C.c_void_p(stream) if stream else None)
+        if rc != OK:
+            _raise(rc)
+
+    def exchange_handle(self):
+        """Allocates this rank's exchange buffer of a bin-sharded spectrum; returns its 64-byte CUDA IPC handle (numpy uint8)."""
+        h = np.zeros(64, dtype=np.uint8)
+        rc = lib().tamcmc_gpu_exchange_create(self.h, h.ctypes.data_as(C.c_void_p))
+        if rc != OK:
+            _raise(rc)
+        return h
+
+    def exchange_attach(self, rank, world, handles):
+        """handles: uint8 [world, 64] in rank order (all_gather of exchange_handle()).  Afterwards eval / eval_device
+        return the log-likelihood of the WHOLE spectrum on every rank (peer-memory exchange inside the fused kernel)."""
+        hb = np.ascontiguousarray(handles, dtype=np.uint8).reshape(world, 64)
+        rc = lib().tamcmc_gpu_exchange_attach(self.h, int(rank), int(world), hb.ctypes.data_as(C.c_void_p))
         if rc != OK:
             _raise(rc)
 

@@ -104,6 +104,7 @@ struct tamcmc_gpu_ctx {
     // device
     StarDesc* d_stars = nullptr;
     unsigned int* d_queue = nullptr;
+    unsigned int* d_bgqueue = nullptr;        // background-only tiles (nullptr: every tile goes through the ring)
     TileRec* d_tilerec = nullptr;
     unsigned int* d_epoch = nullptr;
     unsigned long long* d_trace = nullptr;   // profiling aid (TAMCMC_TRACE builds)
@@ -135,13 +136,14 @@ struct tamcmc_gpu_ctx {
     // zero-copy host path of tamcmc_gpu_eval: parameters are read by the expander straight from mapped pinned memory and
     // the last CTA of the fused kernel writes results + a completion flag back into mapped pinned memory
     bool zero_copy = true;           // TAMCMC_GPU_NO_ZEROCOPY=1 selects the DMA path (H2D + D2H copies + stream sync)
+    bool stage_params = false;       // zero-copy results, but the parameter block is copied to the device first (large rows)
     unsigned char* h_mirror = nullptr;   // [SC] double logL | [SC] int status | pad to 64 | (reserved word) | pad to 128 | uint flag
     double* dm_logL = nullptr; int* dm_status = nullptr; unsigned int* dm_overflow = nullptr; unsigned int* dm_flag = nullptr;
     double* dh_params = nullptr; unsigned char* dh_active = nullptr;    // device addresses of h_params / h_active
     unsigned int epoch_host = 1;     // mirrors the device epoch: advanced once per fused-kernel launch
     // CUDA graphs of the device-side sequence (memset, expand, tile lists, fused kernel, finalize), keyed by the
     // buffer pointers of the call
-    struct GraphEntry { const double* p; const unsigned char* a; double* o; int raw; bool prof; cudaGraphExec_t exec; };
+    struct GraphEntry { const double* p; const unsigned char* a; double* o; int raw; bool prof; bool mirror; cudaGraphExec_t exec; };
     GraphEntry graphs[4] = {};
     int ngraphs = 0;
     int stagger_ns = 0;               // TAMCMC_GPU_STAGGER_NS (tuning aid)
@@ -150,6 +152,12 @@ struct tamcmc_gpu_ctx {
     bool use_graphs = true;
     bool use_pdl = false;            // programmatic dependent launch expand -> fused kernel: measured no gain inside a CUDA graph
                                      // (profiles/r1/NOTES.md); TAMCMC_GPU_PDL=1 enables it
+    // exchange of a bin-sharded spectrum (tamcmc_gpu_exchange_*): peer-mapped buffers of all ranks, this rank's counter
+    int xworld = 1, xrank = 0, xstride = 0;
+    void* x_own = nullptr;                    // this rank's exchange buffer (cudaMalloc; exported through cudaIpc)
+    void* x_peer[TAMCMC_XCHG_MAX_WORLD] = {};  // every rank's buffer as mapped here (x_peer[xrank] == x_own)
+    bool x_ipc[TAMCMC_XCHG_MAX_WORLD] = {};    // opened with cudaIpcOpenMemHandle (closed at destroy)
+    unsigned int* d_xepoch = nullptr;
     // measurement
     bool profiling = false;
     long nlaunch_prof = 0;
@@ -182,6 +190,7 @@ ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const uns
     a.tiles_stride = c->tiles_stride; a.max_tiles = c->max_tiles; a.trace = c->d_trace ? c->d_trace + 64 * 2048 : nullptr;
     a.ksi_part = c->d_ksi; a.ksi_slices = c->ksi_slices; a.ksi_slice_bins = c->ksi_slice_bins;
     a.far_ratio = c->far_ratio;
+    a.bgqueue = c->d_bgqueue;
     return a;
 }
 
@@ -192,7 +201,7 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, boo
     a.x = c->d_x; a.y = c->d_y; a.lnx = c->d_lnx; a.wsig = c->d_wsig; a.likelihood = c->likelihood;
     a.modes = c->d_modes; a.comps = c->d_comps; a.noise = c->d_noise;
     a.asym_flag = c->d_asym; a.Tcoefs = c->d_Tcoefs;
-    a.queue = c->d_queue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec;
+    a.queue = c->d_queue; a.bgqueue = c->d_bgqueue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec;
     a.partial = c->d_partial;
     a.out = d_out; a.model_out = c->d_model;
     a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
@@ -203,15 +212,17 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, boo
     // the host mirror costs a system-scope fence at the end of the launch: only the host-buffer entry point asks for it
     a.host_logL = mirror ? c->dm_logL : nullptr; a.host_status = mirror ? c->dm_status : nullptr;
     a.host_overflow = mirror ? c->dm_overflow : nullptr; a.host_flag = mirror ? c->dm_flag : nullptr;
+    a.xworld = c->xworld; a.xrank = c->xrank; a.xepoch = c->d_xepoch; a.xstride = c->xstride;
+    for (int r = 0; r < TAMCMC_XCHG_MAX_WORLD; r++) a.xpeer[r] = reinterpret_cast<unsigned long long>(c->x_peer[r]);
     return a;
 }
 
 // expand + fused kernel (tile lists, model, Whittle sums, per-chain finalisation, queue re-arm), enqueued on `st`
 int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
-                     int raw_sum, cudaStream_t st, bool prof, bool capturing)
+                     int raw_sum, cudaStream_t st, bool prof, bool capturing, bool mirror)
 {
     ExpandArgs ea = make_expand_args(c, d_params, d_active, d_logL);
-    WhittleArgs wa = make_whittle_args(c, d_logL, raw_sum, c->zero_copy && d_params == c->dh_params);
+    WhittleArgs wa = make_whittle_args(c, d_logL, raw_sum, mirror);
     // profiling: CUDA events between the kernels.  Inside a captured graph they become event-record NODES
     // (cudaEventRecordExternal), so the durations are those of the replayed graph -- the configuration that is benchmarked --
     // without the host launch latency a per-kernel cudaEventRecord pair on a stream adds to a kernel this short.
@@ -236,16 +247,16 @@ void resync_epoch(tamcmc_gpu_ctx* c)
 
 // One evaluation on `st`: the kernels are replayed as one CUDA graph (with event-record nodes between them while profiling).
 int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* d_active, double* d_logL,
-                int raw_sum, cudaStream_t st)
+                int raw_sum, cudaStream_t st, bool mirror = false)
 {
     // the host's copy of the launch epoch (what the last CTA of THIS launch will publish) advances only once the launch has
     // been accepted: a failed capture / instantiate / launch leaves host and device counters in step
     auto launched_ok = [c]() { c->launches += c->d_ksi ? 3 : 2; const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; };
     const bool prof = c->profiling && st == c->stream;
-    if (!c->use_graphs) { const int rc = enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof, false); if (rc == TAMCMC_OK) launched_ok(); else resync_epoch(c); return rc; }
+    if (!c->use_graphs) { const int rc = enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof, false, mirror); if (rc == TAMCMC_OK) launched_ok(); else resync_epoch(c); return rc; }
     for (int i = 0; i < c->ngraphs; i++) {
         const tamcmc_gpu_ctx::GraphEntry& g = c->graphs[i];
-        if (g.p == d_params && g.a == d_active && g.o == d_logL && g.raw == raw_sum && g.prof == prof) { CK(cudaGraphLaunch(g.exec, st)); launched_ok(); return TAMCMC_OK; }
+        if (g.p == d_params && g.a == d_active && g.o == d_logL && g.raw == raw_sum && g.prof == prof && g.mirror == mirror) { CK(cudaGraphLaunch(g.exec, st)); launched_ok(); return TAMCMC_OK; }
     }
     if (c->ngraphs == 4) {           // evict the oldest
         cudaGraphExecDestroy(c->graphs[0].exec);
@@ -255,12 +266,12 @@ int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* 
     cudaGraph_t graph = nullptr;
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, c->stream, prof, true);
+    const int rc = enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, c->stream, prof, true, mirror);
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture");
     tamcmc_gpu_ctx::GraphEntry g;
-    g.p = d_params; g.a = d_active; g.o = d_logL; g.raw = raw_sum; g.prof = prof; g.exec = nullptr;
+    g.p = d_params; g.a = d_active; g.o = d_logL; g.raw = raw_sum; g.prof = prof; g.mirror = mirror; g.exec = nullptr;
     e = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail_cuda(e, "cudaGraphInstantiate");
@@ -440,7 +451,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     if (c->modes_stride < 1) c->modes_stride = 1;       // envelope models only: keep the mode tables non-empty
     c->max_tiles = c->tiles_stride;
     // the expander stages one parameter row + the per-tile cost array in (at most 96 KB of) shared memory
-    if (sizeof(double) * (size_t)c->params_stride + sizeof(int) * (size_t)(c->max_tiles + 2) > 96u * 1024u) { delete c; return TAMCMC_ERR_ARG; }
+    if (sizeof(double) * (size_t)c->params_stride + sizeof(int) * 2 * (size_t)(c->max_tiles + 2) > 96u * 1024u) { delete c; return TAMCMC_ERR_ARG; }
     if ((size_t)nstars * (size_t)Nchains * (size_t)c->tiles_stride > 0xfffffff0ull) { delete c; return TAMCMC_ERR_ARG; }
     c->total_bins_padded = off;
     const int SC = c->SC();
@@ -456,6 +467,12 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     CKC(cudaMalloc(&c->d_stars, sizeof(StarDesc) * nstars));
     c->qcap = (unsigned int)((size_t)SC * (size_t)c->tiles_stride);
     CKC(cudaMalloc(&c->d_queue, sizeof(unsigned int) * TAMCMC_NBUCKETS * (size_t)c->qcap));
+    {
+        // background-only tiles bypass the ring for the chi(2,2p) likelihood (TAMCMC_GPU_BG_FAST=0 keeps them in it)
+        bool bg_fast = likelihood_id == TAMCMC_LIKELIHOOD_CHI22P;
+        if (const char* e = std::getenv("TAMCMC_GPU_BG_FAST")) bg_fast = bg_fast && !(e[0] == '0');
+        if (bg_fast) CKC(cudaMalloc(&c->d_bgqueue, sizeof(unsigned int) * (size_t)c->qcap));
+    }
     CKC(cudaMalloc(&c->d_qctl, sizeof(QueueCtl)));
     CKC(cudaMalloc(&c->d_epoch, sizeof(unsigned int)));
     { const unsigned int one = 1u; CKC(cudaMemcpy(c->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice)); }
@@ -508,6 +525,11 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         c->dm_overflow = reinterpret_cast<unsigned int*>(dm + c->mirror_flag_off() - 64);
         c->dm_flag = reinterpret_cast<unsigned int*>(dm + c->mirror_flag_off());
     }
+    // Host entry: small parameter blocks (C2: 11 KB) are read by the expander straight from mapped pinned memory; a large one
+    // (red-giant mode tables: 10 chains x 2000 doubles = 160 KB of dependent PCIe reads) goes through ONE cudaMemcpyAsync into
+    // device memory instead, results still come back through the mapped mirror + flag (no D2H copy, no stream sync)
+    c->stage_params = sizeof(double) * (size_t)SC * c->params_stride > (size_t)32 * 1024;
+    if (const char* e = std::getenv("TAMCMC_GPU_STAGE_PARAMS")) c->stage_params = (e[0] == '1');
     if (const char* e = std::getenv("TAMCMC_GPU_NO_ZEROCOPY")) c->zero_copy = !(e[0] == '1');
     CKC(cudaMallocHost(&c->h_out, c->out_bytes()));
     CKC(cudaMallocHost(&c->h_qctl, sizeof(QueueCtl)));
@@ -554,10 +576,12 @@ void tamcmc_gpu_destroy(tamcmc_gpu_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_qctl); cudaFree(c->d_epoch); cudaFree(c->d_tilerec); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx); cudaFree(c->d_wsig);
+    cudaFree(c->d_stars); cudaFree(c->d_queue); cudaFree(c->d_bgqueue); cudaFree(c->d_qctl); cudaFree(c->d_epoch); cudaFree(c->d_tilerec); cudaFree(c->d_trace); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_lnx); cudaFree(c->d_wsig);
     cudaFree(c->d_params); cudaFree(c->d_active); cudaFree(c->d_modes); cudaFree(c->d_comps); cudaFree(c->d_noise);
     cudaFree(c->d_asym); cudaFree(c->d_Tcoefs); cudaFree(c->d_partial); cudaFree(c->d_ksi); cudaFree(c->d_out);
     cudaFree(c->d_model);
+    for (int r = 0; r < TAMCMC_XCHG_MAX_WORLD; r++) if (c->x_ipc[r] && c->x_peer[r]) cudaIpcCloseMemHandle(c->x_peer[r]);
+    cudaFree(c->x_own); cudaFree(c->d_xepoch);
     if (c->h_params) cudaFreeHost(c->h_params);
     if (c->h_active) cudaFreeHost(c->h_active);
     if (c->h_mirror) cudaFreeHost(c->h_mirror);
@@ -585,7 +609,14 @@ int tamcmc_gpu_eval_begin(tamcmc_gpu_ctx* c, const double* params, const unsigne
     if (c->zero_copy) {
         // ---- zero-copy: no DMA copies, no stream synchronisation.  The expander reads the rows over PCIe; the last CTA
         // of the fused kernel writes logL/status into the mapped mirror and publishes the launch's epoch in the flag ----
-        { int rc = launch_eval(c, c->dh_params, active_mask ? c->dh_active : nullptr, c->d_logL(), 0, c->stream); if (rc) return rc; }
+        const double* dp = c->dh_params;
+        const unsigned char* da = active_mask ? c->dh_active : nullptr;
+        if (c->stage_params) {
+            CK(cudaMemcpyAsync(c->d_params, c->h_params, pbytes, cudaMemcpyHostToDevice, c->stream));
+            dp = c->d_params;
+            if (active_mask) { CK(cudaMemcpyAsync(c->d_active, c->h_active, (size_t)SC, cudaMemcpyHostToDevice, c->stream)); da = c->d_active; }
+        }
+        { int rc = launch_eval(c, dp, da, c->d_logL(), 0, c->stream, true); if (rc) return rc; }
         c->pending = 1;
     } else {
         CK(cudaMemcpyAsync(c->d_params, c->h_params, pbytes, cudaMemcpyHostToDevice, c->stream));
@@ -799,6 +830,60 @@ int tamcmc_gpu_pt_swap_device(tamcmc_gpu_ctx* c, int star, int A, double u, doub
     c->launches += 1;
     return TAMCMC_OK;
 }
+
+// ---- exchange step of a bin-sharded spectrum over NVLink peer memory ----
+int tamcmc_gpu_exchange_create(tamcmc_gpu_ctx* c, void* handle_out)
+{
+    if (!c || !handle_out || c->pending) return TAMCMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == TAMCMC_XCHG_HANDLE_BYTES, "handle size of the ABI");
+    if (!c->x_own) {
+        c->xstride = ((c->SC() + 7) / 8) * 8;
+        CK(cudaMalloc(&c->x_own, tamcmc_xchg_bytes(c->xstride)));
+        CK(cudaMemset(c->x_own, 0, tamcmc_xchg_bytes(c->xstride)));
+        CK(cudaMalloc(&c->d_xepoch, sizeof(unsigned int)));
+        CK(cudaMemset(c->d_xepoch, 0, sizeof(unsigned int)));
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->x_own));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return TAMCMC_OK;
+}
+
+static int exchange_finish_attach(tamcmc_gpu_ctx* c, int rank, int world)
+{
+    c->xrank = rank; c->xworld = world;
+    // the kernel parameters change: graphs captured without the exchange are dropped
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < c->ngraphs; i++) cudaGraphExecDestroy(c->graphs[i].exec);
+    c->ngraphs = 0;
+    return TAMCMC_OK;
+}
+
+int tamcmc_gpu_exchange_attach(tamcmc_gpu_ctx* c, int rank, int world, const void* handles)
+{
+    if (!c || !handles || !c->x_own || world < 1 || world > TAMCMC_XCHG_MAX_WORLD || rank < 0 || rank >= world || c->pending) return TAMCMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { c->x_peer[r] = c->x_own; c->x_ipc[r] = false; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * TAMCMC_XCHG_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->x_peer[r] = p; c->x_ipc[r] = true;
+    }
+    return exchange_finish_attach(c, rank, world);
+}
+
+int tamcmc_gpu_exchange_attach_ptrs(tamcmc_gpu_ctx* c, int rank, int world, void* const* bufs)
+{
+    if (!c || !bufs || !c->x_own || world < 1 || world > TAMCMC_XCHG_MAX_WORLD || rank < 0 || rank >= world || c->pending) return TAMCMC_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r < world; r++) { c->x_peer[r] = (r == rank) ? c->x_own : bufs[r]; c->x_ipc[r] = false; }
+    return exchange_finish_attach(c, rank, world);
+}
+
+void* tamcmc_gpu_exchange_buffer(tamcmc_gpu_ctx* c) { return c ? c->x_own : nullptr; }
 
 int tamcmc_gpu_sync(tamcmc_gpu_ctx* c)
 {

@@ -454,19 +454,27 @@ __device__ __noinline__ double nu_aj(int l, int m, double fc, const double* a /*
 // Taylor series in u = x - xc of one Harvey-like term H / (1 + (tau' x)^p) (noise_models.cpp:30-31),
 // valid on the tile when |u|/xc is small against the distance to the nearest singularity
 // (x = 0 and (tau' x)^p = -1).  Returns false when the tile must use the per-bin exp() path.
-__device__ __noinline__ bool harvey_series(double H, double lnsc, double pw, double cpi, double spi, const double* binom,
-                              double xc, double lnxc, double umax, double* out /*NB, accumulated*/)
+// does the series of one term converge on the tile?  (*zc_out = (tau' xc)^p for the caller)
+__device__ __noinline__ bool harvey_series_ok(double lnsc, double pw, double cpi, double spi, double xc, double lnxc, double umax, double* zc_out)
 {
-    constexpr int NB = TAMCMC_BG_TERMS;
     if (!(xc > 0.0)) return false;
     const double L = lnsc + lnxc;
     const double tx = exp(L);            // tau' * xc
     const double zc = exp(pw * L);       // (tau' * xc)^p
+    *zc_out = zc;
     if (!(zc < 1e30) || !(tx > 0.0)) return false;
     const double itx = 1.0 / tx;
     const double dr = cpi * itx - 1.0, di = spi * itx;
     const double rho = fmin(1.0, sqrt(dr * dr + di * di));
-    if (!(umax <= 0.04 * rho * xc)) return false;     // 0.04^NB = 1e-14 truncation
+    return umax <= 0.04 * rho * xc;      // 0.04^NB = 1e-14 truncation
+}
+
+__device__ __noinline__ bool harvey_series(double H, double lnsc, double pw, double cpi, double spi, const double* binom,
+                              double xc, double lnxc, double umax, double* out /*NB, accumulated*/)
+{
+    constexpr int NB = TAMCMC_BG_TERMS;
+    double zc;
+    if (!harvey_series_ok(lnsc, pw, cpi, spi, xc, lnxc, umax, &zc)) return false;
     double q[NB], g[NB];
     q[0] = 1.0 + zc;
 #pragma unroll
@@ -505,6 +513,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     CompRec* comps = A.comps + (size_t)sc * A.modes_stride * TAMCMC_MAX_COMP_PER_MODE;
     NoiseRec* noise = A.noise + sc;
     int* tcost = reinterpret_cast<int*>(sp + A.params_stride);   // [ntiles + 1] difference array -> cost
+    int* tcover = tcost + (A.max_tiles + 2);                     // [ntiles + 1] difference array -> number of mode windows over the tile
 
     ETRACE(0);
     // ---- blockIdx.y >= 1: background CTAs.  One thread per tile of this chain builds the tile record
@@ -551,8 +560,8 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     __shared__ double slot_nu[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
     __shared__ double slot_A[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
     __shared__ unsigned char slot_cls[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
-    __shared__ int s_red[EXP_THREADS / 32];
-    __shared__ unsigned int s_bcnt[TAMCMC_NBUCKETS], s_bbase[TAMCMC_NBUCKETS];
+    __shared__ int s_red[EXP_THREADS / 32], s_red2[EXP_THREADS / 32];
+    __shared__ unsigned int s_bcnt[TAMCMC_NBUCKETS], s_bbase[TAMCMC_NBUCKETS], s_bgcnt, s_bgbase;
     static_assert(TAMCMC_NBUCKETS == (1 << TAMCMC_NBUCKETS_LOG2), "tile class is packed into the low bits");
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -577,7 +586,19 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     {
         const double* g = A.params + (size_t)sc * A.params_stride;
         for (int k = tid; k < A.params_stride; k += blockDim.x) sp[k] = g[k];
-        for (int k = tid; k <= ntiles; k += blockDim.x) tcost[k] = 0;
+        for (int k = tid; k <= ntiles; k += blockDim.x) { tcost[k] = 0; tcover[k] = 0; }
+    }
+    if (A.bgqueue && sd.nmodes_cap > 0) {
+        // phase 3 looks at the centre and the ends of every tile no mode touches (does its background series converge?): start those
+        // lines' way into L2 now, so that the look costs an L2 hit at the end of the kernel instead of a trip to HBM
+        for (int t = tid; t < ntiles; t += blockDim.x) {
+            const int lb0 = t * sd.tile_bins, nvalid = min(sd.tile_bins, sd.Nloc - lb0);
+            const double* xs = A.x + sd.off + lb0;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + (nvalid >> 1)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xs));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + sd.tile_bins - 1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.lnx + sd.off + lb0 + (nvalid >> 1)));
+        }
     }
     __syncthreads();
     ETRACE(1);
@@ -890,6 +911,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 const int lo = max(i0, sd.bin0) - sd.bin0, hi = min(i1, sd.bin0 + sd.Nloc) - sd.bin0;
                 if (hi > lo) {
                     int t0 = lo / sd.tile_bins, t1 = (hi - 1) / sd.tile_bins + 1;
+                    atomicAdd(&tcover[t0], 1); atomicAdd(&tcover[t1], -1);      // every tile the window touches, near or far
                     if (far_capable && A.far_ratio > 0.0 && ns == 0) {
                         // the fused kernel merges this mode per bin only in the tiles whose centre lies within far_ratio half
                         // tiles of its components; elsewhere it costs nothing per bin (a scheduling weight, not a result)
@@ -924,49 +946,79 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     if (enqueue) {
         // inclusive scan of the difference array (serial per warp-strided chunk would need carries; ntiles is
         // a few hundred: one warp scans it in 32-wide steps with a running carry)
-        if (warp == 0) {
+        if (warp == 0 || warp == 1) {
+            // warp 0: cost of every tile; warp 1: how many mode windows lie over it (0 = a background-only tile)
+            int* arr = (warp == 0) ? tcost : tcover;
+            const int add = (warp == 0) ? TILE_BASE_COST : 0;
             int carry = 0;
             for (int t0 = 0; t0 < ntiles; t0 += 32) {
                 const int t = t0 + lane;
-                int v = (t < ntiles) ? tcost[t] : 0;
+                int v = (t < ntiles) ? arr[t] : 0;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
                 v += carry;
-                if (t < ntiles) tcost[t] = v + TILE_BASE_COST;
+                if (t < ntiles) arr[t] = v + add;
                 carry = __shfl_sync(0xffffffffu, v, 31);
             }
         }
         __syncthreads();
-        int mx = 0;
-        for (int t = tid; t < ntiles; t += blockDim.x) mx = max(mx, tcost[t]);
+        int mx = 0, nfree = 0;                      // heaviest tile; tiles no mode window touches
+        for (int t = tid; t < ntiles; t += blockDim.x) { mx = max(mx, tcost[t]); nfree += (tcover[t] == 0); }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
-        if (lane == 0) s_red[warp] = mx;
+        for (int d = 16; d > 0; d >>= 1) { mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d)); nfree += __shfl_down_sync(0xffffffffu, nfree, d); }
+        if (lane == 0) { s_red[warp] = mx; s_red2[warp] = nfree; }
         __syncthreads();
-        mx = 0;
-        for (int w = 0; w < EXP_THREADS / 32; w++) mx = max(mx, s_red[w]);
+        mx = 0; nfree = 0;
+        for (int w = 0; w < EXP_THREADS / 32; w++) { mx = max(mx, s_red[w]); nfree += s_red2[w]; }
         // cost class of every tile (sixteenths of the chain's heaviest tile, heaviest first) and its rank inside the class,
         // counted in shared memory; then ONE global atomic per class reserves the chain's slots in the queue
         if (tid < TAMCMC_NBUCKETS) s_bcnt[tid] = 0u;
+        if (tid == TAMCMC_NBUCKETS) s_bgcnt = 0u;
         __syncthreads();
+        // Background-only tiles (no window over them; the Lorentzian models with the chi(2,2p) likelihood) leave the ring: they go to
+        // the second queue, which the fused kernel's consumer warps drain one tile per warp (whittle.cu, bg_phase).  Class
+        // TAMCMC_NBUCKETS marks them below.
+        // ... when they are at least a quarter of the chain's tiles: below that the ring absorbs them for less than the series test of
+        // every such tile costs at the end of this kernel (C2: 14 of 163 tiles, +1.8 us on the expander for -0.5 us on the fused kernel)
+        const bool bg_fast = A.bgqueue != nullptr && nmodes > 0 && 4 * nfree >= ntiles;
         const int rounds = (ntiles + blockDim.x - 1) / blockDim.x;
         for (int r = 0; r < rounds; r++) {
             const int t = r * blockDim.x + tid;
             if (t < ntiles) {
-                const int q = (TAMCMC_NBUCKETS * (tcost[t] - TILE_BASE_COST)) / max(mx - TILE_BASE_COST, 1);
-                const int cls = min(max(TAMCMC_NBUCKETS - 1 - q, 0), TAMCMC_NBUCKETS - 1);
-                const unsigned rank = atomicAdd(&s_bcnt[cls], 1u);
-                tcost[t] = (int)((rank << TAMCMC_NBUCKETS_LOG2) | (unsigned)cls);          // ntiles <= 16384: rank fits
+                bool bg = bg_fast && tcover[t] == 0;
+                if (bg) {
+                    // only tiles whose background SERIES converges take the warp-per-tile path (the exact per-bin terms near x = 0
+                    // cost several times more per bin: one such tile on one warp would be the tail of the whole phase).  Same test
+                    // on the same inputs as the background CTAs make for the tile record (blockIdx.y >= 1 above).
+                    const int lb0 = t * sd.tile_bins, nvalid = min(sd.tile_bins, sd.Nloc - lb0);
+                    const double* xs = A.x + sd.off + lb0;
+                    const double xc = xs[nvalid >> 1];
+                    const double umax = fmax(fabs(xs[0] - xc), fabs(xs[sd.tile_bins - 1] - xc));
+                    const double lnxc = A.lnx[sd.off + lb0 + (nvalid >> 1)];
+                    for (int h = 0; bg && h < noise->nh; h++) { double zc; bg = harvey_series_ok(noise->lnsc[h], noise->pw[h], noise->cpi[h], noise->spi[h], xc, lnxc, umax, &zc); }
+                }
+                if (bg) {
+                    const unsigned rank = atomicAdd(&s_bgcnt, 1u);
+                    tcost[t] = (int)((rank << (TAMCMC_NBUCKETS_LOG2 + 1)) | (unsigned)TAMCMC_NBUCKETS);
+                } else {
+                    const int q = (TAMCMC_NBUCKETS * (tcost[t] - TILE_BASE_COST)) / max(mx - TILE_BASE_COST, 1);
+                    const int cls = min(max(TAMCMC_NBUCKETS - 1 - q, 0), TAMCMC_NBUCKETS - 1);
+                    const unsigned rank = atomicAdd(&s_bcnt[cls], 1u);
+                    tcost[t] = (int)((rank << (TAMCMC_NBUCKETS_LOG2 + 1)) | (unsigned)cls);      // ntiles <= 16384: rank fits
+                }
             }
         }
         __syncthreads();
         if (tid < TAMCMC_NBUCKETS) s_bbase[tid] = s_bcnt[tid] ? atomicAdd(&A.qctl->count[tid], s_bcnt[tid]) : 0u;
+        if (tid == TAMCMC_NBUCKETS) s_bgbase = s_bgcnt ? atomicAdd(&A.qctl->bg_count, s_bgcnt) : 0u;
         __syncthreads();
         for (int r = 0; r < rounds; r++) {
             const int t = r * blockDim.x + tid;
             if (t < ntiles) {
-                const unsigned v = (unsigned)tcost[t], cls = v & (TAMCMC_NBUCKETS - 1u), rank = v >> TAMCMC_NBUCKETS_LOG2;
-                A.queue[(size_t)cls * A.qcap + s_bbase[cls] + rank] = (unsigned)sc * (unsigned)A.tiles_stride + (unsigned)t;
+                const unsigned v = (unsigned)tcost[t], cls = v & (2u * TAMCMC_NBUCKETS - 1u), rank = v >> (TAMCMC_NBUCKETS_LOG2 + 1);
+                const unsigned item = (unsigned)sc * (unsigned)A.tiles_stride + (unsigned)t;
+                if (cls == TAMCMC_NBUCKETS) A.bgqueue[s_bgbase + rank] = item;
+                else A.queue[(size_t)cls * A.qcap + s_bbase[cls] + rank] = item;
             }
         }
     }
@@ -1019,7 +1071,7 @@ cudaError_t tamcmc_expand_configure()
 
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st)
 {
-    const size_t smem = sizeof(double) * (size_t)a.params_stride + sizeof(int) * (size_t)(a.max_tiles + 2);
+    const size_t smem = sizeof(double) * (size_t)a.params_stride + sizeof(int) * 2 * (size_t)(a.max_tiles + 2);
     dim3 grid((unsigned)nblocks, 1u + (unsigned)((a.max_tiles + EXP_THREADS - 1) / EXP_THREADS), 1u);
     if (a.ksi_part) {       // some star runs the Kallinger2014 model: its normalisation sums come first
         dim3 kgrid((unsigned)nblocks, (unsigned)a.ksi_slices, 1u);

@@ -29,6 +29,8 @@ struct ExpandArgs {
     int ksi_slices;
     int ksi_slice_bins;              // bins per pre-pass CTA: the smallest power-of-two multiple of TAMCMC_KSI_SLICE that fits the grid in one wave
     double far_ratio;                // far-field folding of the fused kernel (0 = off): only used to weigh the tiles of the work queue
+    unsigned int* bgqueue;           // [qcap] work items of the background-only tiles (QueueCtl.bg_count of them); nullptr: every tile goes
+                                     // through the ring (chi_square likelihood, TAMCMC_GPU_BG_FAST=0)
 };
 
 struct WhittleArgs {
@@ -43,6 +45,7 @@ struct WhittleArgs {
     const int* asym_flag;
     const double* Tcoefs;            // [Nchains]
     const unsigned int* queue;
+    const unsigned int* bgqueue;     // background-only tiles (see ExpandArgs)
     const TileRec* tilerec;
     QueueCtl* qctl;
     unsigned int qcap;
@@ -67,7 +70,18 @@ struct WhittleArgs {
     int raw_sum;                     // 1: out = S = sum(ln M + y/M) over LOCAL bins (bin-sharded contexts)
     double far_ratio;                // > 0: modes whose components all lie >= far_ratio * umax from a tile's centre are folded into
                                      // the tile's polynomial instead of being merged per bin (whittle.cu); 0 = every component per bin
+    // bin-sharded contexts with an attached exchange (capi.cu, tamcmc_gpu_exchange_*): the last CTA of every rank writes its chains'
+    // local sums into the exchange buffer of EVERY rank over NVLink peer memory, waits for the other ranks' flags, adds the sums
+    // in rank order (bitwise identical on every rank) and applies -p S / T -- the path's one exchange step, no collective launch
+    int xworld, xrank;               // xworld <= 1: no exchange
+    unsigned long long xpeer[TAMCMC_XCHG_MAX_WORLD];   // device addresses of the ranks' exchange buffers as mapped in THIS process
+    unsigned int* xepoch;            // this rank's exchange counter (device): every rank advances it once per evaluation
+    int xstride;                     // doubles per (parity, rank) block of an exchange buffer (>= nsc)
 };
+
+// exchange buffer of one rank: double S[2][TAMCMC_XCHG_MAX_WORLD][xstride], then unsigned flag[2][TAMCMC_XCHG_MAX_WORLD]
+__host__ __device__ inline size_t tamcmc_xchg_flag_offset(int xstride) { return sizeof(double) * 2u * TAMCMC_XCHG_MAX_WORLD * (size_t)xstride; }
+__host__ __device__ inline size_t tamcmc_xchg_bytes(int xstride) { return tamcmc_xchg_flag_offset(xstride) + sizeof(unsigned int) * 2u * TAMCMC_XCHG_MAX_WORLD; }
 
 cudaError_t tamcmc_upload_tables(const double* P_hi, const double* P_lo, const double* Q);
 cudaError_t tamcmc_upload_dmm_tables(const double* coef, const double* nnum, const double* nden);

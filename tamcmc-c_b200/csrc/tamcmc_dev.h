@@ -30,6 +30,7 @@
 #endif
 #define TAMCMC_THREADS (TAMCMC_CONSUMERS + 32 * TAMCMC_PRODUCERS)
 #define TAMCMC_BINS_PER_THREAD (TAMCMC_TILE / TAMCMC_CONSUMERS)
+#define TAMCMC_XCHG_MAX_WORLD 8      // ranks of one bin-sharded spectrum (the GPUs of one NVSwitch box)
 #define TAMCMC_MAX_TILES 16384       // tiles per star the expander's cost scan supports (16.7M bins)
 #ifndef TAMCMC_MIN_CTAS
 #define TAMCMC_MIN_CTAS 1            // resident CTAs per SM the fused kernel is compiled for (full-size tiles)
@@ -136,4 +137,6 @@ struct __align__(16) TileRec {
 #define TAMCMC_NBUCKETS 16           // work-queue cost classes, heaviest first (fine classes = near-sorted pops = short tail)
 #define TAMCMC_NBUCKETS_LOG2 4
 // Zero between evaluations: the last CTA of the fused kernel to finish resets it.
-struct QueueCtl { unsigned int count[TAMCMC_NBUCKETS]; unsigned int head; unsigned int ctas_done; unsigned int pad[2]; };
+// bg_count / bg_head: the second queue, of BACKGROUND-ONLY tiles (no mode window touches them): the fused kernel's consumer
+// warps drain it one tile per WARP straight from global memory before they enter the ring (whittle.cu, bg_phase).
+struct QueueCtl { unsigned int count[TAMCMC_NBUCKETS]; unsigned int head; unsigned int ctas_done; unsigned int bg_count; unsigned int bg_head; };

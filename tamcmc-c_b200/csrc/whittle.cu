@@ -582,6 +582,161 @@ __device__ __noinline__ double gauss_envelope(const NoiseRec* nz, double x)
 }
 
 // ------------------------------------------------------------------------------------------------
+// background-only tiles: ONE WARP PER TILE, straight from global memory
+// ------------------------------------------------------------------------------------------------
+// A tile no mode window touches has no component list: its model is the background alone.  Sent through the ring it still
+// pays the whole per-tile protocol (claim, records, TMA, barriers, 12 warps in step: ~1.5-2 us for ~90 FP64 instructions per
+// thread), and a long spectrum is mostly such tiles (BASELINE config C3: 85 % of 6510).  The expander lists them in a second
+// queue instead (expand.cu, phase 3) and every consumer warp drains that queue before it enters the ring: a warp pops a tile,
+// reads its x, y with coalesced 128-bit loads (48 bins per lane: deep instruction-level parallelism, no barrier, no shared
+// memory), evaluates the background like the ring's epilogue does -- tile polynomial, or the exact per-bin terms where the series
+// does not converge -- forms the Whittle terms and leaves the tile's partial.  The producers build the first ring tiles
+// meanwhile, so the phase also fills the kernel's start-up.  Fixed order inside a warp: results stay bitwise reproducible.
+struct BgArgs {      // what bg_phase reads, by value: a reference to the kernel's parameter block would force a local copy of all of it
+    const unsigned int* bgqueue; QueueCtl* qctl; const StarDesc* stars; const TileRec* tilerec; const NoiseRec* noise;
+    const double *x, *y, *lnx; double *partial, *model_out; int tiles_stride, Nchains;
+};
+
+// Whittle terms of one bin of a background-only tile: y / M and 1 / M split into mantissa and exponent (see the ring's epilogue)
+struct BgSums {
+    double s1 = 0.0, pm = 1.0;
+    int pe = 0, bad = 0;
+    __device__ __forceinline__ void add(double y, double minv)
+    {
+        s1 = fma(y, minv, s1);
+        const int hi = __double2hiint(minv);
+        const int k = (hi & 0x7ff00000) - 0x3ff00000;
+        pm *= __hiloint2double(hi - k, __double2loint(minv));
+        pe += k >> 20;
+        bad |= hi;
+    }
+    __device__ __forceinline__ void fold()          // the mantissa product back into [1, 2)
+    {
+        const int hi = __double2hiint(pm);
+        const int k = (hi & 0x7ff00000) - 0x3ff00000;
+        pm = __hiloint2double(hi - k, __double2loint(pm));
+        pe += k >> 20;
+    }
+};
+
+template <bool WRITE_MODEL, int TILE>
+__device__ __noinline__ void bg_phase(const BgArgs A, int lane)
+{
+    const unsigned nbg = A.qctl->bg_count;            // final: the expander grid completed before this grid started
+    for (;;) {
+        unsigned idx = 0;
+        if (lane == 0) idx = atomicAdd(&A.qctl->bg_head, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= nbg) return;
+        const unsigned item = A.bgqueue[idx];
+        const int sc = (int)(item / (unsigned)A.tiles_stride);
+        const int tile = (int)(item - (unsigned)sc * (unsigned)A.tiles_stride);
+        const StarDesc* sd = A.stars + sc / A.Nchains;
+        const TileRec* tr = A.tilerec + item;
+        const NoiseRec* nz = A.noise + sc;
+        const int lb0 = tile * TILE;
+        const long long off = sd->off + lb0;
+        const int nvalid = min(TILE, sd->Nloc - lb0);
+        const double xc = tr->xc, N0 = nz->N0;
+        const double* __restrict__ xs = A.x + off + 2 * lane;
+        const double* __restrict__ ys = A.y + off + 2 * lane;
+        BgSums S;
+        if (tr->series_ok) {
+            // ---- tile polynomial (the usual case).  4 pairs per lane and array in a chunk; the NEXT chunk's loads are in flight
+            // while this one is evaluated (16 x 512 B per warp) ----
+            double cf[NB];
+#pragma unroll
+            for (int k = 0; k < NB; k++) cf[k] = tr->bg[k];
+            constexpr int CH = 4;
+            double2 xv[CH], yv[CH], xn[CH], yn[CH];
+#pragma unroll
+            for (int c = 0; c < CH; c++) { xv[c] = __ldg(reinterpret_cast<const double2*>(xs + 64 * c)); yv[c] = __ldg(reinterpret_cast<const double2*>(ys + 64 * c)); }
+#pragma unroll 1
+            for (int k0 = 0; k0 < TILE / 64; k0 += CH) {
+                if (k0 + CH < TILE / 64) {
+#pragma unroll
+                    for (int c = 0; c < CH; c++) {
+                        xn[c] = __ldg(reinterpret_cast<const double2*>(xs + 64 * (k0 + CH + c)));
+                        yn[c] = __ldg(reinterpret_cast<const double2*>(ys + 64 * (k0 + CH + c)));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2 * CH; j++) {
+                    const int bb = 2 * lane + 64 * (k0 + (j >> 1)) + (j & 1);
+                    const double u = ((j & 1) ? xv[j >> 1].y : xv[j >> 1].x) - xc;
+                    double acc = cf[NB - 1];
+#pragma unroll
+                    for (int k = NB - 2; k >= 0; k--) acc = fma(acc, u, cf[k]);
+                    const double num = acc + N0;
+                    if (WRITE_MODEL) { if (bb < nvalid) A.model_out[lb0 + bb] = num; }
+                    if (bb < nvalid) S.add((j & 1) ? yv[j >> 1].y : yv[j >> 1].x, fast_rcp(num));
+                }
+                S.fold();
+#pragma unroll
+                for (int c = 0; c < CH; c++) { xv[c] = xn[c]; yv[c] = yn[c]; }
+            }
+        } else {
+            // ---- the exact per-bin terms where the series does not converge (near x = 0), merged into one fraction like the ring's
+            // epilogue; one term at a time over the chunk's bins, so its parameters are read once per chunk ----
+            const double* __restrict__ lx = A.lnx + off + 2 * lane;
+            const int nh = nz->nh;
+            constexpr int CH = 2;
+#pragma unroll 1
+            for (int k0 = 0; k0 < TILE / 64; k0 += CH) {
+                double x[2 * CH], lnx[2 * CH], Nn[2 * CH], Dn[2 * CH];
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(xs + 64 * (k0 + c)));
+                    const double2 w = __ldg(reinterpret_cast<const double2*>(lx + 64 * (k0 + c)));
+                    x[2 * c] = v.x; x[2 * c + 1] = v.y; lnx[2 * c] = w.x; lnx[2 * c + 1] = w.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 2 * CH; j++) { Nn[j] = 0.0; Dn[j] = 1.0; }
+                for (int h = 0; h < nh; h++) {
+                    const double H = nz->H[h], ls = nz->lnsc[h], pw = nz->pw[h], isc = nz->isc[h];
+                    const bool p4 = (pw == 4.0), p2 = (pw == 2.0);
+#pragma unroll
+                    for (int j = 0; j < 2 * CH; j++) {
+                        double z;
+                        if (p4 || p2) { const double q = ((x[j] - xc) + xc) * isc, q2 = q * q; z = fmin(p4 ? q2 * q2 : q2, 2.5e30); }     // (u + xc like the ring)
+                        else { const double arg = fmin(pw * (ls + lnx[j]), 70.0); z = (pw == 0.0) ? 1.0 : exp(arg); }
+                        const double t = 1.0 + z;
+                        Nn[j] = fma(Nn[j], t, H * Dn[j]);
+                        Dn[j] *= t;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const double2 yv = __ldg(reinterpret_cast<const double2*>(ys + 64 * (k0 + c)));
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int j = 2 * c + r, bb = 2 * lane + 64 * (k0 + c) + r;
+                        const double num = fma(N0, Dn[j], Nn[j]);       // (D <= (1 + 2.5e30)^8: no renormalisation needed; N may be exactly 0)
+                        if (WRITE_MODEL) { if (bb < nvalid) A.model_out[lb0 + bb] = num / Dn[j]; }
+                        if (bb < nvalid) S.add(r ? yv.y : yv.x, Dn[j] * fast_rcp(num));
+                    }
+                }
+                S.fold();
+            }
+        }
+        double s1 = S.s1, pm = (S.bad < 0) ? nan("") : S.pm;       // a non-positive model bin: NaN like log() of it (likelihoods.cpp:23)
+        int pe = S.pe;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s1 += __shfl_down_sync(0xffffffffu, s1, d);
+            pm *= __shfl_down_sync(0xffffffffu, pm, d);     // 32 mantissas in [1, 2) stay below 2^32
+            pe += __shfl_down_sync(0xffffffffu, pe, d);
+        }
+        if (lane == 0) {
+            const int hi = __double2hiint(pm);
+            const int k = (hi & 0x7ff00000) - 0x3ff00000;
+            double* part = A.partial + 3 * ((size_t)sc * A.tiles_stride + tile);
+            part[0] = s1; part[1] = __hiloint2double(hi - k, __double2loint(pm)); part[2] = (double)(pe + (k >> 20));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // consumer warps
 // ------------------------------------------------------------------------------------------------
 template <bool WRITE_MODEL, int BPT>
@@ -944,7 +1099,7 @@ __device__ void finalize_chains(const WhittleArgs& A, int warp, int lane, int nw
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
         if (lane == 0) {
-            if (A.raw_sum) A.out[sc] = acc;
+            if (A.raw_sum || A.xworld > 1) A.out[sc] = acc;          // the local sum S: all-reduced by the caller / exchanged below
             else if (A.likelihood == 1) A.out[sc] = ((-acc) / 2) / A.Tcoefs[sc % A.Nchains];        // likelihoods.cpp:36-37, model_def.cpp:405
             else {
                 const double pl = (double)(long long)A.p;
@@ -952,6 +1107,59 @@ __device__ void finalize_chains(const WhittleArgs& A, int warp, int lane, int nw
             }
         }
     }
+}
+
+// The exchange step of a bin-sharded spectrum, run by the last CTA of every rank once its chains' LOCAL sums S
+// are in A.out: (1) the sums go into block [parity][rank] of the exchange buffer of every rank (peer stores over NVLink; own
+// buffer included), (2) after a system-scope fence the rank's flag [parity][rank] of every buffer takes the new epoch value,
+// (3) the CTA waits for all flags of its own buffer, (4) adds the ranks' sums in RANK ORDER -- every rank gets the same bits --
+// and (5) applies the likelihood's factor and 1 / Tcoefs like finalize_chains.  Two parities: a rank one evaluation ahead never
+// overwrites values a slower rank still has to read.  A peer that never shows up (its process died) ends the wait after ~2 s:
+// NaN results and TAMCMC_ST_NONFINITE for every chain, instead of a kernel that spins for ever.
+__device__ void exchange_and_finalize(const WhittleArgs& A, int tid)
+{
+    __shared__ unsigned int s_epoch, s_timeout;
+    if (tid == 0) { const unsigned e = *A.xepoch + 1u; s_epoch = e ? e : 1u; s_timeout = 0u; }
+    __syncthreads();
+    const unsigned e = s_epoch;
+    const int par = (int)(e & 1u), W = A.xworld, R = A.xrank;
+    const size_t blk = ((size_t)par * TAMCMC_XCHG_MAX_WORLD + (size_t)R) * (size_t)A.xstride;
+    for (int p = 0; p < W; p++) {
+        double* dst = reinterpret_cast<double*>(A.xpeer[p]) + blk;
+        for (int i = tid; i < A.nsc; i += NT) dst[i] = (A.status[i] != 0) ? 0.0 : A.out[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < W) {
+        volatile unsigned int* f = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<unsigned char*>(A.xpeer[tid]) + tamcmc_xchg_flag_offset(A.xstride))
+                                   + par * TAMCMC_XCHG_MAX_WORLD + R;
+        *f = e;
+    }
+    if (tid < W) {
+        volatile unsigned int* f = reinterpret_cast<volatile unsigned int*>(reinterpret_cast<unsigned char*>(A.xpeer[R]) + tamcmc_xchg_flag_offset(A.xstride))
+                                   + par * TAMCMC_XCHG_MAX_WORLD + tid;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*f != e) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) { atomicExch(&s_timeout, 1u); break; }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    const bool dead = s_timeout != 0u;
+    const double* own = reinterpret_cast<const double*>(A.xpeer[R]) + (size_t)par * TAMCMC_XCHG_MAX_WORLD * (size_t)A.xstride;
+    for (int i = tid; i < A.nsc; i += NT) {
+        if (dead) { A.out[i] = nan(""); const_cast<int*>(A.status)[i] |= TAMCMC_ST_NONFINITE; continue; }
+        if (A.status[i] != 0) continue;                                   // the expander already put NaN there
+        double S = 0.0;
+        for (int r = 0; r < W; r++) S += __ldcv(own + (size_t)r * A.xstride + i);
+        if (A.likelihood == 1) A.out[i] = ((-S) / 2) / A.Tcoefs[i % A.Nchains];
+        else A.out[i] = (-(double)(long long)A.p * S) / A.Tcoefs[i % A.Nchains];
+    }
+    __syncthreads();
+    if (tid == 0) *A.xepoch = e;
 }
 
 // Full-size tiles: one CTA per SM.  Half-size tiles: compiled for TWO resident CTAs per SM (64 registers per thread, 2 x 107 KB
@@ -977,7 +1185,22 @@ __global__ void __launch_bounds__(NT, (BPT == BPT_MAX) ? TAMCMC_MIN_CTAS : TAMCM
     // prologue above overlaps the expander's tail); everything below reads the expander's output.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid >= NC) producer_loop<NC * BPT>(A, sm, (tid - NC) >> 5, tid & 31);
-    else consumer_loop<WRITE_MODEL, BPT>(A, sm, tid);
+    else {
+        if (A.bgqueue) {                                                  // background-only tiles first, one per warp
+#ifdef TAMCMC_TRACE
+            if ((tid & 31) == 0 && (tid >> 5) < 2) TRACE(58 + 2 * (tid >> 5), gtime());      // warps 0, 1: begin / end of the background phase
+#endif
+            BgArgs b;
+            b.bgqueue = A.bgqueue; b.qctl = A.qctl; b.stars = A.stars; b.tilerec = A.tilerec; b.noise = A.noise;
+            b.x = A.x; b.y = A.y; b.lnx = A.lnx; b.partial = A.partial; b.model_out = A.model_out;
+            b.tiles_stride = A.tiles_stride; b.Nchains = A.Nchains;
+            bg_phase<WRITE_MODEL, NC * BPT>(b, tid & 31);
+#ifdef TAMCMC_TRACE
+            if ((tid & 31) == 0 && (tid >> 5) < 2) TRACE(59 + 2 * (tid >> 5), gtime());
+#endif
+        }
+        consumer_loop<WRITE_MODEL, BPT>(A, sm, tid);
+    }
 
     // ---- the LAST CTA to finish turns the per-tile partials into the per-chain results and re-arms the queue ----
     __shared__ unsigned int s_last;
@@ -987,6 +1210,7 @@ __global__ void __launch_bounds__(NT, (BPT == BPT_MAX) ? TAMCMC_MIN_CTAS : TAMCM
     if (!s_last) return;
     __threadfence();
     finalize_chains(A, tid >> 5, tid & 31, NT / 32);
+    if (A.xworld > 1 && !A.raw_sum) exchange_and_finalize(A, tid);
     if (A.host_flag) {
         // host mirror: every writer fences its own stores at system scope, the barrier orders them before the flag
         __syncthreads();
@@ -999,7 +1223,7 @@ __global__ void __launch_bounds__(NT, (BPT == BPT_MAX) ? TAMCMC_MIN_CTAS : TAMCM
         QueueCtl* q = A.qctl;
 #pragma unroll
         for (int k = 0; k < TAMCMC_NBUCKETS; k++) q->count[k] = 0u;
-        q->head = 0u; q->ctas_done = 0u;
+        q->head = 0u; q->ctas_done = 0u; q->bg_count = 0u; q->bg_head = 0u;
         unsigned e = *A.epoch + 1u;
         e = e ? e : 1u;
         *A.epoch = e;                                   // next launch's ready-flag value (never 0)

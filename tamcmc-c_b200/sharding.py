@@ -16,8 +16,10 @@ def star_shard(nstars, rank, world):
     return [s for s in range(nstars) if s % world == rank]
 
 
-def bin_work(N, l, i0, i1, base=1.0):
-    """Per-bin work estimate: `base` (background + Whittle terms) plus (2l+1) per covering mode."""
+def bin_work(N, l, i0, i1, base=15.0):
+    """Per-bin work estimate: `base` for the fixed per-tile phases (tile switch, background polynomial, Whittle terms) plus
+    (2l+1) per covering mode.  base = 15: measured on B200 (profiles/trace_tiles.py, C2): a tile costs ~1.86 us + 0.12 us per
+    listed component, i.e. the fixed part weighs as much as ~15 components."""
     d = np.zeros(N + 1)
     for ll, a, b in zip(l, i0, i1):
         d[a] += 2 * ll + 1
