@@ -241,6 +241,7 @@ struct ModeTmp {
     int hoff;              // model 13: offset of the per-m heights in the parameter vector
     int n;
     int i0, i1, bad;       // bit-exact window of set_imin_imax (pass A), bad != 0: imax - imin <= 0
+    double sg;             // 2 / W, once per mode (2 * (1 / W) == 2 / W bit for bit: a scaling by two is exact)
 };
 
 // Called by ONE FULL WARP: lane k handles Harvey term k; live terms (tau != 0, noise_models.cpp:29) are compacted in
@@ -508,6 +509,10 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int sc = blockIdx.x;                 // star*Nchains + chain
     const int star = sc / A.Nchains;
+    // the first element of the parameter row this thread will stage: requested BEFORE the star descriptor is needed, so that the
+    // two trips to memory overlap (both are cold: ~1 us each with L2 flushed)
+    double p_first = 0.0;
+    if (blockIdx.y == 0 && threadIdx.x >= 96 && (int)threadIdx.x - 96 < A.params_stride) p_first = A.params[(size_t)sc * A.params_stride + (threadIdx.x - 96)];
     const StarDesc sd = A.stars[star];
     ModeRec* modes = A.modes + (size_t)sc * A.modes_stride;
     CompRec* comps = A.comps + (size_t)sc * A.modes_stride * TAMCMC_MAX_COMP_PER_MODE;
@@ -553,13 +558,8 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     }
 
     __shared__ Common cm;
-    __shared__ int s_status;
+    __shared__ int s_status, s_status1b;     // s_status1b: raised by the scalar warps (phase 1b)
     __shared__ ModeTmp mt[EXP_BATCH];
-    __shared__ double slot_s[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
-    __shared__ double slot_ia[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
-    __shared__ double slot_nu[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
-    __shared__ double slot_A[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
-    __shared__ unsigned char slot_cls[EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE];
     __shared__ int s_red[EXP_THREADS / 32], s_red2[EXP_THREADS / 32];
     __shared__ unsigned int s_bcnt[TAMCMC_NBUCKETS], s_bbase[TAMCMC_NBUCKETS], s_bgcnt, s_bgbase;
     static_assert(TAMCMC_NBUCKETS == (1 << TAMCMC_NBUCKETS_LOG2), "tile class is packed into the low bits");
@@ -579,370 +579,389 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     const int o_modes = TAMCMC_MT_HDR + Nnoise;      // mode table: first mode record
     const int ntiles = sd.ntiles;
 
-    if (tid == 0) {
-        s_status = 0;
-        if (A.active && !A.active[sc]) s_status = TAMCMC_ST_INACTIVE;
-    }
-    {
-        const double* g = A.params + (size_t)sc * A.params_stride;
-        for (int k = tid; k < A.params_stride; k += blockDim.x) sp[k] = g[k];
-        for (int k = tid; k <= ntiles; k += blockDim.x) { tcost[k] = 0; tcover[k] = 0; }
-    }
-    if (A.bgqueue && sd.nmodes_cap > 0) {
-        // phase 3 looks at the centre and the ends of every tile no mode touches (does its background series converge?): start those
-        // lines' way into L2 now, so that the look costs an L2 hit at the end of the kernel instead of a trip to HBM
-        for (int t = tid; t < ntiles; t += blockDim.x) {
-            const int lb0 = t * sd.tile_bins, nvalid = min(sd.tile_bins, sd.Nloc - lb0);
-            const double* xs = A.x + sd.off + lb0;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + (nvalid >> 1)));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(xs));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + sd.tile_bins - 1));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.lnx + sd.off + lb0 + (nvalid >> 1)));
-        }
-    }
-    __syncthreads();
-    ETRACE(1);
-    const bool inactive = (s_status & TAMCMC_ST_INACTIVE) != 0;
+    // Warps 0-2 ("scalar warps") do not stage anything: they compute the chain's m-height ratios, eta0 and the noise record --
+    // long dependent FP64 chains (sincos, logarithms, divides; cold code) -- straight from the GLOBAL parameter row, starting at
+    // once, while warps 3-15 stage the row in shared memory, file the scalars (phase 1a) and run pass A of the first batch.  The two
+    // groups meet at the barrier in front of the per-component pass.
+    const bool scalar_warp = warp < 3;
+    const bool inactive = A.active && !A.active[sc];
+    const double* gp = A.params + (size_t)sc * A.params_stride;
+    auto stage_sync = []() { asm volatile("bar.sync 1, %0;" ::"n"(EXP_THREADS - 96) : "memory"); };      // warps 3..15 only
     const double* params = sp;
     const double* fl0_all = params + Nmax + lmax;
     const double* Wl0_all = params + o_width;
-
-    // ---------------- phase 1a: the scalars pass A needs (one thread; everything here is a parameter read) ----------------
-    if (!inactive) {
-        if (tid >= 97 && tid <= 99) {
-            const int l = tid - 96;
-            const bool have = mode_table ? false : (model == 11 || model == 14) ? false : (lmax >= l);
-            cm.Vl[l] = have ? fabs(params[Nmax + l - 1]) : 1.0;
-        } else if (tid == 96) {
-            cm.eta_from_fit = 0; cm.eta0 = 0.0;
-            cm.trunc_c = mode_table ? params[2] : params[o_cfg];
-            cm.do_amp = mode_table ? 0 : (params[o_cfg + 1] != 0.0);
-            cm.ratios[0][0] = 1.0;
-            cm.Vl[0] = 1.0;
-            cm.status = 0;
-            cm.a1 = cm.a3 = cm.a11 = cm.a12 = 0.0;
-            switch (model) {
-            case 3: case 12: case 13:    // models.cpp:2011-2016, 2219-2222, 2396-2399
-                cm.a1 = fabs(params[o_split]);
-                cm.eta_from_fit = 1;
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 6:                      // models.cpp:87-91
-                cm.a11 = fabs(params[o_split]);
-                cm.a12 = fabs(params[o_split + 6]);
-                cm.eta_from_fit = 1;
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 7: case 8:              // a1n / a1nl etaa3: models.cpp:290-296, 1075-1081 (splittings per radial order: pass A)
-                cm.eta_from_fit = 1;
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 14:                     // model_MS_local_Hnlm: models.cpp:3242-3245
-                cm.a1 = fabs(params[o_split]);
-                cm.eta0 = params[o_split + 1];
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 11:                     // models.cpp:3059-3075 (Nvis plays the role of lmax)
-                cm.a1 = params[o_split + 3] * params[o_split + 3] + params[o_split + 4] * params[o_split + 4];
-                cm.eta0 = params[o_split + 1];
-                cm.a3 = params[o_split + 2];
-                cm.asym = params[o_split + 5];
-                break;
-            case 23:                     // models.cpp:1257-1270
-                for (int k = 0; k < 12; k++) cm.aterm[k] = params[o_split + k];
-                cm.asym = params[o_split + 13];
-                cm.eta_from_fit = (params[o_split + 12] == 1) ? 1 : 0; cm.eta0 = 0.0;
-                break;
-            case TAMCMC_MODEL_ID_KALLINGER_GAUSS: case TAMCMC_MODEL_ID_HARVEY_GAUSS:   // no modes: background + Gaussian envelope
-                cm.asym = 0.0;
-                cm.eta0 = 0.0;
-                break;
-            case TAMCMC_MODEL_ID_MODE_TABLE:   // modes already resolved by a host expander (e.g. models.cpp:4788-4911)
-                cm.asym = params[3];
-                cm.eta0 = 0.0;
-                if (!(params[0] >= 0.0 && params[0] <= (double)sd.nmodes_cap)) cm.status = TAMCMC_ST_BADCFG;
-                break;
-            default:
-                cm.status = TAMCMC_ST_BADCFG;
-                cm.eta0 = 0; cm.asym = 0;
-                break;
-            }
-            if (cm.status) atomicOr(&s_status, cm.status);
-        }
-    }
-    __syncthreads();
-    const bool run = !inactive && !(s_status & TAMCMC_ST_BADCFG);
-
-    // ---------------- phase 1b (warps 0-2) beside pass A of the first batch (warps 4-7): the m-height ratios, eta0 and the
-    // noise record are long dependent FP64 chains that pass A does not read ----------------
-    if (!inactive) {
-        if (tid < 15) {
-            // warp 0, lanes 0..14: the 3+5+7 entries of amplitude_ratio(l, inc), l = 1..3 (or the ratio parameters)
-            const int l = (tid < 3) ? 1 : (tid < 8) ? 2 : 3;
-            const int i = tid - ((l == 1) ? 0 : (l == 2) ? 3 : 8) - l;       // m = -l..l
-            const bool have = mode_table ? true : (model == 11) ? (pl[2 + l] >= 1) : (model == 14) ? false : (lmax >= l);
-            if (have) {
-                if (mode_table) {
-                    cm.ratios[l][i + l] = d_amplitude_ratio_entry(l, i, params[1]);
-                } else if (model == 12) {
-                    // models.cpp:2196-2214: m-ratios read from the "inclination" block, symmetric in m
-                    const int base = (l == 1) ? 0 : (l == 2) ? 2 : 5;
-                    cm.ratios[l][i + l] = fabs(params[o_inc + base + (i < 0 ? -i : i)]);
-                } else if (model != 13) {
-                    double inc;
-                    if (model == 11) {       // models.cpp:3057-3058
-                        const double PI = 3.141592653589793238462643383279502884;
-                        inc = atan(params[o_split + 4] / params[o_split + 3]) * 180. / PI;
-                    } else inc = params[o_inc];
-                    cm.ratios[l][i + l] = d_amplitude_ratio_entry(l, i, inc);
-                }
-            }
-            ETRACE_T(8, 14);
-        } else if (tid >= 32 && tid < 64) {
-            // warp 1: eta0 by the whole warp (models that use it), then lane 0 files the scalar parameters
-            const bool need_eta = (model == 3 || model == 12 || model == 13 || model == 6 || model == 7 || model == 8) ||
-                                  (model == 23 && params[o_split + 12] == 1);
-            const double eta_w = need_eta ? d_eta0_fct_warp(fl0_all, Nfl0, tid - 32) : 0.0;
-            if (tid == 32 && cm.eta_from_fit) cm.eta0 = eta_w;
-            ETRACE_T(9, 32);
-        } else if (tid >= 64 && tid < 96) {
-            // warp 2: Harvey-like background parameters, one lane per term
-            if (model == TAMCMC_MODEL_ID_KALLINGER_GAUSS)
-                emit_kallinger(noise, params, A.ksi_part + (size_t)sc * A.ksi_slices * 3, (sd.Nloc + A.ksi_slice_bins - 1) / A.ksi_slice_bins,
-                               sd.step, sd.xlast, &s_status, tid - 64);
-            else if (model == TAMCMC_MODEL_ID_HARVEY_GAUSS) emit_harvey_gauss(noise, params, &s_status, tid - 64);
-            else emit_noise(noise, params + o_noise, Nnoise, (model == 11 || model == 14) ? 0 : (Nnoise - 1) / 3, &s_status, tid - 64);
-            ETRACE_T(10, 64);
-        }
-    }
-
-    ETRACE(2);
-    // ---------------- phase 2: modes in batches of 128; three passes per batch ----------------
     const int nmodes = sd.nmodes_cap;
-    const int nmodes_live = (mode_table && run) ? (int)params[0] : nmodes;     // mode table: per-chain mode count
+    if (scalar_warp) {
+        if (tid == 64) s_status1b = 0;
+        __syncwarp();
+        if (!inactive) {
+            if (tid < 15) {
+                // warp 0, lanes 0..14: the 3+5+7 entries of amplitude_ratio(l, inc), l = 1..3 (or the ratio parameters)
+                const int l = (tid < 3) ? 1 : (tid < 8) ? 2 : 3;
+                const int i = tid - ((l == 1) ? 0 : (l == 2) ? 3 : 8) - l;       // m = -l..l
+                const bool have = mode_table ? true : (model == 11) ? (pl[2 + l] >= 1) : (model == 14) ? false : (lmax >= l);
+                if (have) {
+                    if (mode_table) {
+                        cm.ratios[l][i + l] = d_amplitude_ratio_entry(l, i, gp[1]);
+                    } else if (model == 12) {
+                        // models.cpp:2196-2214: m-ratios read from the "inclination" block, symmetric in m
+                        const int base = (l == 1) ? 0 : (l == 2) ? 2 : 5;
+                        cm.ratios[l][i + l] = fabs(gp[o_inc + base + (i < 0 ? -i : i)]);
+                    } else if (model != 13) {
+                        double inc;
+                        if (model == 11) {       // models.cpp:3057-3058
+                            const double PI = 3.141592653589793238462643383279502884;
+                            inc = atan(gp[o_split + 4] / gp[o_split + 3]) * 180. / PI;
+                        } else inc = gp[o_inc];
+                        cm.ratios[l][i + l] = d_amplitude_ratio_entry(l, i, inc);
+                    }
+                }
+                ETRACE_T(8, 14);
+            } else if (tid >= 32 && tid < 64) {
+                // warp 1: eta0 by the whole warp (models that use it), then lane 0 files the scalar parameters
+                const bool need_eta = (model == 3 || model == 12 || model == 13 || model == 6 || model == 7 || model == 8) ||
+                                      (model == 23 && gp[o_split + 12] == 1);
+                const double eta_w = need_eta ? d_eta0_fct_warp(gp + Nmax + lmax, Nfl0, tid - 32) : 0.0;
+                if (tid == 32 && need_eta) cm.eta0 = eta_w;          // need_eta == cm.eta_from_fit of phase 1a (same rule)
+                ETRACE_T(9, 32);
+            } else if (tid >= 64 && tid < 96) {
+                // warp 2: Harvey-like background parameters, one lane per term
+                if (model == TAMCMC_MODEL_ID_KALLINGER_GAUSS)
+                    emit_kallinger(noise, gp, A.ksi_part + (size_t)sc * A.ksi_slices * 3, (sd.Nloc + A.ksi_slice_bins - 1) / A.ksi_slice_bins,
+                                   sd.step, sd.xlast, &s_status1b, tid - 64);
+                else if (model == TAMCMC_MODEL_ID_HARVEY_GAUSS) emit_harvey_gauss(noise, gp, &s_status1b, tid - 64);
+                else emit_noise(noise, gp + o_noise, Nnoise, (model == 11 || model == 14) ? 0 : (Nnoise - 1) / 3, &s_status1b, tid - 64);
+                ETRACE_T(10, 64);
+            }
+        }
+    } else {
+        if (tid == 96) s_status = inactive ? TAMCMC_ST_INACTIVE : 0;
+        for (int k = tid - 96 + (EXP_THREADS - 96); k < A.params_stride; k += EXP_THREADS - 96) sp[k] = gp[k];
+        if (tid - 96 < A.params_stride) sp[tid - 96] = p_first;
+        for (int k = tid - 96; k <= ntiles; k += EXP_THREADS - 96) { tcost[k] = 0; tcover[k] = 0; }
+        if (A.bgqueue && sd.nmodes_cap > 0) {
+            // phase 3 looks at the centre and the ends of every tile no mode touches (does its background series converge?): start those
+            // lines' way into L2 now, so that the look costs an L2 hit at the end of the kernel instead of a trip to HBM
+            for (int t = tid - 96; t < ntiles; t += EXP_THREADS - 96) {
+                const int lb0 = t * sd.tile_bins, nvalid = min(sd.tile_bins, sd.Nloc - lb0);
+                const double* xs = A.x + sd.off + lb0;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + (nvalid >> 1)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(xs));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + sd.tile_bins - 1));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.lnx + sd.off + lb0 + (nvalid >> 1)));
+            }
+        }
+        stage_sync();
+        ETRACE_T(1, 96);
+        // ---------------- phase 1a: the scalars pass A needs (one thread; everything here is a parameter read) ----------------
+        if (!inactive) {
+            if (tid >= 97 && tid <= 99) {
+                const int l = tid - 96;
+                const bool have = mode_table ? false : (model == 11 || model == 14) ? false : (lmax >= l);
+                cm.Vl[l] = have ? fabs(params[Nmax + l - 1]) : 1.0;
+            } else if (tid == 96) {
+                cm.eta_from_fit = 0;
+                cm.trunc_c = mode_table ? params[2] : params[o_cfg];
+                cm.do_amp = mode_table ? 0 : (params[o_cfg + 1] != 0.0);
+                cm.ratios[0][0] = 1.0;
+                cm.Vl[0] = 1.0;
+                cm.status = 0;
+                double eta_other = 0.0;          // eta0 of the models that do not take it from the large-separation fit
+                cm.a1 = cm.a3 = cm.a11 = cm.a12 = 0.0;
+                switch (model) {
+                case 3: case 12: case 13:    // models.cpp:2011-2016, 2219-2222, 2396-2399
+                    cm.a1 = fabs(params[o_split]);
+                    cm.eta_from_fit = 1;
+                    cm.a3 = params[o_split + 2];
+                    cm.asym = params[o_split + 5];
+                    break;
+                case 6:                      // models.cpp:87-91
+                    cm.a11 = fabs(params[o_split]);
+                    cm.a12 = fabs(params[o_split + 6]);
+                    cm.eta_from_fit = 1;
+                    cm.a3 = params[o_split + 2];
+                    cm.asym = params[o_split + 5];
+                    break;
+                case 7: case 8:              // a1n / a1nl etaa3: models.cpp:290-296, 1075-1081 (splittings per radial order: pass A)
+                    cm.eta_from_fit = 1;
+                    cm.a3 = params[o_split + 2];
+                    cm.asym = params[o_split + 5];
+                    break;
+                case 14:                     // model_MS_local_Hnlm: models.cpp:3242-3245
+                    cm.a1 = fabs(params[o_split]);
+                    eta_other = params[o_split + 1];
+                    cm.a3 = params[o_split + 2];
+                    cm.asym = params[o_split + 5];
+                    break;
+                case 11:                     // models.cpp:3059-3075 (Nvis plays the role of lmax)
+                    cm.a1 = params[o_split + 3] * params[o_split + 3] + params[o_split + 4] * params[o_split + 4];
+                    eta_other = params[o_split + 1];
+                    cm.a3 = params[o_split + 2];
+                    cm.asym = params[o_split + 5];
+                    break;
+                case 23:                     // models.cpp:1257-1270
+                    for (int k = 0; k < 12; k++) cm.aterm[k] = params[o_split + k];
+                    cm.asym = params[o_split + 13];
+                    cm.eta_from_fit = (params[o_split + 12] == 1) ? 1 : 0;
+                    break;
+                case TAMCMC_MODEL_ID_KALLINGER_GAUSS: case TAMCMC_MODEL_ID_HARVEY_GAUSS:   // no modes: background + Gaussian envelope
+                    cm.asym = 0.0;
+                    break;
+                case TAMCMC_MODEL_ID_MODE_TABLE:   // modes already resolved by a host expander (e.g. models.cpp:4788-4911)
+                    cm.asym = params[3];
+                    if (!(params[0] >= 0.0 && params[0] <= (double)sd.nmodes_cap)) cm.status = TAMCMC_ST_BADCFG;
+                    break;
+                default:
+                    cm.status = TAMCMC_ST_BADCFG;
+                    cm.asym = 0;
+                    break;
+                }
+                if (!cm.eta_from_fit) cm.eta0 = eta_other;      // (the fit's value is written by warp 1: one writer either way)
+                if (cm.status) atomicOr(&s_status, cm.status);
+            }
+        }
+        stage_sync();
+    }
+    ETRACE_T(2, 96);
+    // ---------------- phase 2: modes in batches of 128: pass A (one thread per mode), then ONE pass over the (mode, m) slots ----------------
+    // (every thread must meet the same barriers: `inactive` comes from global memory and is the same for all of them; what the
+    // two groups found -- unknown model, bad mode count, too many Harvey terms -- is looked at after the first barrier)
+    bool run = !inactive;
     for (int base = 0; run && base < nmodes; base += EXP_BATCH) {
-        // ---- pass A: one thread per mode: degree, frequency, width, height rule, splittings ----
-        {
-            // threads 128..255 (warps 4-7): warps 0-2 are still busy with phase 1b during the first batch
-            const int ta = tid - EXP_BATCH;
-            const bool mine = ta >= 0 && ta < EXP_BATCH;
-            const int j = base + ta;
-            static_assert(2 * EXP_BATCH <= EXP_THREADS, "one scratch slot per mode of a batch, on warps 4..7");
-            ModeTmp& t = mt[mine ? ta : 0];      // filled in place in shared memory (the other threads idle here)
-            if (mine) t.have = 0;
-            if (mode_table && mine && j < nmodes_live) {
-                // one optimum_lorentzian_calc_aj call of the host model function (e.g. models.cpp:4937, 4952, 4977, 5001)
-                const double* r = params + o_modes + TAMCMC_MT_STRIDE * j;
-                const int l = (int)r[0];
-                if (!(r[0] >= 0.0 && r[0] <= 3.0) || !(r[2] >= 0.0) || !(r[3] >= 0.0)) atomicOr(&s_status, (r[0] == r[0] && r[2] == r[2] && r[3] == r[3]) ? TAMCMC_ST_BADCFG : TAMCMC_ST_NONFINITE);
-                else {
-                    t.have = 1; t.l = l; t.n = j; t.fc = r[1]; t.H = r[2]; t.W = r[3];
-                    for (int k = 0; k < 6; k++) t.a[k] = r[4 + k];
-                    t.eta0 = r[10]; t.eta_cm = 0; t.fsw = r[4]; t.f_s = 0.0;
-                    t.hoff = o_modes + TAMCMC_MT_STRIDE * j + 11 + 3;     // extra[m] = params[hoff + m]
-                }
-            } else if (!mode_table && mine && j < nmodes) {
-                int l, n;
-                if (model == 3 || model == 12 || model == 13 || model == 6 || model == 7 || model == 8) {
-                    l = j % (lmax + 1); n = j / (lmax + 1);          // n-major, l interleaved (models.cpp:2026-2085)
-                } else {
-                    // l-major: all l=0, then l=1, ... (models.cpp:1287-1376, 3082-3134)
-                    int r = j; l = 0;
-                    while (l < 3 && r >= pl[2 + l]) { r -= pl[2 + l]; l++; }
-                    n = r;
-                }
-                const int o_fl = Nmax + lmax + (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0);
-                const double fc = params[o_fl + n];
-                t.have = 1; t.l = l; t.n = n; t.fc = fc; t.hoff = -1; t.eta0 = 0.0; t.eta_cm = 1;     // cm.eta0 is read in pass B
-                for (int k = 0; k < 6; k++) t.a[k] = 0.0;
-                if (model == 14) {
-                    // models.cpp:3256-3318: individual widths; heights H(n,l,|m|) at params[base_l + (l+1) n + |m|] with
-                    // base_l = Nfl0, Nfl0+Nfl1, Nfl0+Nfl1+Nfl2 exactly as the reference indexes them (:3270, 3285, 3303)
-                    const int idx = (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0) + n;
-                    t.W = fabs(params[o_width + idx]);
-                    t.H = -1.0;
-                    t.hoff = idx - n + (l + 1) * n;
-                    t.f_s = cm.a1; t.fsw = cm.a1;
-                } else if (model == 11) {
-                    // models.cpp:3082-3134: individual heights and widths per mode
-                    const int idx = (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0) + n;
-                    t.W = fabs(params[o_width + idx]);
-                    t.H = cm.do_amp ? amp_to_height(params[idx], t.W) : fabs(params[idx]);
-                    t.f_s = cm.a1; t.fsw = cm.a1;
-                } else if (model == 23) {
-                    // models.cpp:1287-1376
-                    if (l == 0) {
-                        t.W = fabs(Wl0_all[n]);
-                        t.H = cm.do_amp ? amp_to_height(params[n], t.W) : fabs(params[n]);
-                        t.eta0 = 0.0; t.eta_cm = 0;
-                    } else {
-                        t.W = fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
-                        const double Hi = d_lin_interpol(fl0_all, params, Nmax, fc);
-                        const double PI = 3.14159265358979323846;
-                        t.H = cm.do_amp ? fabs(Hi / (PI * t.W) * cm.Vl[l]) : fabs(Hi * cm.Vl[l]);
-                        const int na = 2 * l;            // l=1: a1,a2; l=2: a1..a4; l=3: a1..a6
-                        for (int k = 0; k < na; k++) t.a[k] = cm.aterm[2 * k] + cm.aterm[2 * k + 1] * (fc * 1e-3);
+        if (!scalar_warp || base > 0) {
+            const bool okA = !((s_status | (base > 0 ? s_status1b : 0)) & TAMCMC_ST_BADCFG);
+            const int nmodes_live = !okA ? 0 : mode_table ? (int)params[0] : nmodes;     // mode table: per-chain mode count
+            // ---- pass A: one thread per mode: degree, frequency, width, height rule, splittings ----
+            {
+                // threads 128..255 (warps 4-7): warps 0-2 are still busy with phase 1b during the first batch
+                const int ta = tid - EXP_BATCH;
+                const bool mine = ta >= 0 && ta < EXP_BATCH;
+                const int j = base + ta;
+                static_assert(2 * EXP_BATCH <= EXP_THREADS, "one scratch slot per mode of a batch, on warps 4..7");
+                ModeTmp& t = mt[mine ? ta : 0];      // filled in place in shared memory (the other threads idle here)
+                if (mine) t.have = 0;
+                if (mode_table && mine && j < nmodes_live) {
+                    // one optimum_lorentzian_calc_aj call of the host model function (e.g. models.cpp:4937, 4952, 4977, 5001)
+                    const double* r = params + o_modes + TAMCMC_MT_STRIDE * j;
+                    const int l = (int)r[0];
+                    if (!(r[0] >= 0.0 && r[0] <= 3.0) || !(r[2] >= 0.0) || !(r[3] >= 0.0)) atomicOr(&s_status, (r[0] == r[0] && r[2] == r[2] && r[3] == r[3]) ? TAMCMC_ST_BADCFG : TAMCMC_ST_NONFINITE);
+                    else {
+                        t.have = 1; t.l = l; t.n = j; t.fc = r[1]; t.H = r[2]; t.W = r[3];
+                        for (int k = 0; k < 6; k++) t.a[k] = r[4 + k];
+                        t.eta0 = r[10]; t.eta_cm = 0; t.fsw = r[4]; t.f_s = 0.0;
+                        t.hoff = o_modes + TAMCMC_MT_STRIDE * j + 11 + 3;     // extra[m] = params[hoff + m]
                     }
-                    t.f_s = 0.0;
-                    t.fsw = t.a[0];                       // optimum_lorentzian_calc_aj: window uses a1 (build_lorentzian.cpp:513)
-                } else {
-                    // Classic family and a1l: widths interpolated on the l=0 ladder, heights H[n]*V_l
-                    t.W = (l == 0) ? fabs(Wl0_all[n]) : fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
-                    if (model == 6) {                     // build_lorentzian.cpp:58-66, 383-396
-                        t.f_s = (l == 0) ? 0.0 : (l == 1) ? cm.a11 : (l == 2) ? cm.a12 : (cm.a11 + cm.a12) / 2.;
-                    } else if (model == 7 || model == 8) {
-                        // splittings per radial order (models.cpp:290-291, 317-318; 1075-1076, 1099-1100)
-                        const double a11 = fabs(params[o_split + 6 + n]);
-                        const double a12 = (model == 8) ? fabs(params[o_split + 6 + Nmax + n]) : a11;
-                        t.f_s = (l == 0) ? 0.0 : (l == 1) ? a11 : (l == 2) ? a12 : (a11 + a12) / 2.;
-                    } else t.f_s = cm.a1;
-                    t.fsw = t.f_s;
-                    if (model == 13) {
-                        // models.cpp:2409-2470: per-m heights from the parameter vector, |H|/(pi W) if do_amp
+                } else if (!mode_table && mine && j < nmodes_live) {
+                    int l, n;
+                    if (model == 3 || model == 12 || model == 13 || model == 6 || model == 7 || model == 8) {
+                        l = j % (lmax + 1); n = j / (lmax + 1);          // n-major, l interleaved (models.cpp:2026-2085)
+                    } else {
+                        // l-major: all l=0, then l=1, ... (models.cpp:1287-1376, 3082-3134)
+                        int r = j; l = 0;
+                        while (l < 3 && r >= pl[2 + l]) { r -= pl[2 + l]; l++; }
+                        n = r;
+                    }
+                    const int o_fl = Nmax + lmax + (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0);
+                    const double fc = params[o_fl + n];
+                    t.have = 1; t.l = l; t.n = n; t.fc = fc; t.hoff = -1; t.eta0 = 0.0; t.eta_cm = 1;     // cm.eta0 is read in pass B
+                    for (int k = 0; k < 6; k++) t.a[k] = 0.0;
+                    if (model == 14) {
+                        // models.cpp:3256-3318: individual widths; heights H(n,l,|m|) at params[base_l + (l+1) n + |m|] with
+                        // base_l = Nfl0, Nfl0+Nfl1, Nfl0+Nfl1+Nfl2 exactly as the reference indexes them (:3270, 3285, 3303)
+                        const int idx = (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0) + n;
+                        t.W = fabs(params[o_width + idx]);
                         t.H = -1.0;
-                        t.hoff = (l == 0) ? n : o_inc + (l + 1) * n;
+                        t.hoff = idx - n + (l + 1) * n;
+                        t.f_s = cm.a1; t.fsw = cm.a1;
+                    } else if (model == 11) {
+                        // models.cpp:3082-3134: individual heights and widths per mode
+                        const int idx = (l >= 1 ? Nfl0 : 0) + (l >= 2 ? Nfl1 : 0) + (l >= 3 ? Nfl2 : 0) + n;
+                        t.W = fabs(params[o_width + idx]);
+                        t.H = cm.do_amp ? amp_to_height(params[idx], t.W) : fabs(params[idx]);
+                        t.f_s = cm.a1; t.fsw = cm.a1;
+                    } else if (model == 23) {
+                        // models.cpp:1287-1376
+                        if (l == 0) {
+                            t.W = fabs(Wl0_all[n]);
+                            t.H = cm.do_amp ? amp_to_height(params[n], t.W) : fabs(params[n]);
+                            t.eta0 = 0.0; t.eta_cm = 0;
+                        } else {
+                            t.W = fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
+                            const double Hi = d_lin_interpol(fl0_all, params, Nmax, fc);
+                            const double PI = 3.14159265358979323846;
+                            t.H = cm.do_amp ? fabs(Hi / (PI * t.W) * cm.Vl[l]) : fabs(Hi * cm.Vl[l]);
+                            const int na = 2 * l;            // l=1: a1,a2; l=2: a1..a4; l=3: a1..a6
+                            for (int k = 0; k < na; k++) t.a[k] = cm.aterm[2 * k] + cm.aterm[2 * k + 1] * (fc * 1e-3);
+                        }
+                        t.f_s = 0.0;
+                        t.fsw = t.a[0];                       // optimum_lorentzian_calc_aj: window uses a1 (build_lorentzian.cpp:513)
                     } else {
-                        if (l == 0) t.H = cm.do_amp ? amp_to_height(params[n], t.W) : fabs(params[n]);
-                        else t.H = cm.do_amp ? amp_to_height(params[n], t.W) * cm.Vl[l] : fabs(params[n] * cm.Vl[l]);
+                        // Classic family and a1l: widths interpolated on the l=0 ladder, heights H[n]*V_l
+                        t.W = (l == 0) ? fabs(Wl0_all[n]) : fabs(d_lin_interpol(fl0_all, Wl0_all, Nmax, fc));
+                        if (model == 6) {                     // build_lorentzian.cpp:58-66, 383-396
+                            t.f_s = (l == 0) ? 0.0 : (l == 1) ? cm.a11 : (l == 2) ? cm.a12 : (cm.a11 + cm.a12) / 2.;
+                        } else if (model == 7 || model == 8) {
+                            // splittings per radial order (models.cpp:290-291, 317-318; 1075-1076, 1099-1100)
+                            const double a11 = fabs(params[o_split + 6 + n]);
+                            const double a12 = (model == 8) ? fabs(params[o_split + 6 + Nmax + n]) : a11;
+                            t.f_s = (l == 0) ? 0.0 : (l == 1) ? a11 : (l == 2) ? a12 : (a11 + a12) / 2.;
+                        } else t.f_s = cm.a1;
+                        t.fsw = t.f_s;
+                        if (model == 13) {
+                            // models.cpp:2409-2470: per-m heights from the parameter vector, |H|/(pi W) if do_amp
+                            t.H = -1.0;
+                            t.hoff = (l == 0) ? n : o_inc + (l + 1) * n;
+                        } else {
+                            if (l == 0) t.H = cm.do_amp ? amp_to_height(params[n], t.W) : fabs(params[n]);
+                            else t.H = cm.do_amp ? amp_to_height(params[n], t.W) * cm.Vl[l] : fabs(params[n] * cm.Vl[l]);
+                        }
                     }
                 }
+                ETRACE_T(11, EXP_BATCH + 5);
+                // bit-exact window (build_lorentzian.cpp:595-649), one thread per mode
+                if (mine && t.have) {
+                    t.bad = d_set_imin_imax(sd.x0, sd.xlast, sd.Nglob, t.l, t.fc, t.W, t.fsw, cm.trunc_c, sd.step, &t.i0, &t.i1);
+                    t.sg = 2.0 / t.W;
+                }
             }
-            ETRACE_T(11, EXP_BATCH + 5);
-            // bit-exact window (build_lorentzian.cpp:595-649), one thread per mode
-            if (mine && t.have)
-                t.bad = d_set_imin_imax(sd.x0, sd.xlast, sd.Nglob, t.l, t.fc, t.W, t.fsw, cm.trunc_c, sd.step, &t.i0, &t.i1);
         }
         __syncthreads();
+        if (base == 0) {
+            // the two groups meet: from here on everybody sees the staged row, cm and both status words
+            run = !((s_status | s_status1b) & TAMCMC_ST_BADCFG);
+            if (!run) break;
+        }
         ETRACE(3);
-        // ---- pass B: one thread per (mode, m) slot: nu_nlm and height ----
-        for (int sl = tid; sl < EXP_BATCH * TAMCMC_MAX_COMP_PER_MODE; sl += blockDim.x) {
-            const int jj = sl / TAMCMC_MAX_COMP_PER_MODE, k = sl - jj * TAMCMC_MAX_COMP_PER_MODE;
+        // ---- per-component pass: 8 lanes per mode (lane k <-> m = k - l, lane 7 idle), so that a mode's records, its component
+        // order (FAST first), the extent of its centres and its tile costs come out of ONE pass with warp votes instead of a second,
+        // serial per-mode pass behind a barrier ----
+        const double inv_step = 1.0 / sd.step, inv_T = 1.0 / (double)sd.tile_bins;       // scheduling weights only (never a window)
+#pragma unroll 2
+        for (int sl = tid; sl < EXP_BATCH * 8; sl += EXP_THREADS) {
+            const int jj = sl >> 3, k = sl & 7;
             const ModeTmp& t = mt[jj];
-            if (!t.have || k > 2 * t.l) continue;
             const int l = t.l, m = k - l;
-            double nu, h;
-            const double eta0 = t.eta_cm ? cm.eta0 : t.eta0;
-            if (model == 23) nu = nu_aj(l, m, t.fc, t.a, eta0);
-            else if (mode_table) { nu = nu_aj(l, m, t.fc, t.a, eta0); if (l != 0) nu = nu + params[t.hoff + m]; }   // build_lorentzian.cpp:182-190
-            else nu = nu_a1etaa3(l, m, t.fc, t.f_s, eta0, cm.a3);
-            if (t.H >= 0.0) h = t.H * cm.ratios[l][k];
-            else {
-                const double PI = 3.141592653589793238462643383279502884;
-                h = (l == 0) ? params[t.hoff] : params[t.hoff + (m < 0 ? -m : m)];
-                if (cm.do_amp) h = h / (PI * t.W);
-                h = fabs(h);
-            }
-            slot_nu[sl] = nu; slot_A[sl] = h;
-            slot_s[sl] = (2.0 / t.W) / sqrt(h); slot_ia[sl] = 1.0 / h;     // scaled FAST form (used if the slot qualifies)
-            // classification against the mode's window.  FAST: t' = (1+e^2)/A stays inside [1e-8, 1e16] over the whole
-            // window, so 16 merges between two exponent renormalisations cannot leave the FP64 range.  WIDE (very narrow
-            // modes, e.g. red-giant mixed modes far narrower than a bin): t' inside [1e-16, 1e32], same scaled form, but the
-            // segments that hold such a mode renormalise every 4 merges.  Everything else live: general (SLOW) form.
+            const bool live = t.have && k <= 2 * l;
+            double nu = 0.0, h = 0.0, cs = 0.0, ia = 0.0;
             unsigned char cls = SLOT_DEAD;
-            if (!isfinite(h) || !isfinite(nu)) cls = SLOT_NONFINITE;
-            else if (h != 0.0 && t.W > 0.0) {               // else: contributes exactly 0 (gamma == 0: DESIGN.md deviations)
-                const double xlo = sd.x0 + (double)t.i0 * sd.step, xhi = sd.x0 + (double)t.i1 * sd.step;
-                const double emax = (2.0 / t.W) * fmax(fabs(xlo - nu), fabs(xhi - nu));
-                if (!(emax < 1e100)) cls = SLOT_NONFINITE;
-                else if (h >= 1e-8 && h <= 1e8 && emax < 1e4) cls = SLOT_FAST;
-                else if (h >= 1e-16 && h <= 1e16 && emax < 1e8) cls = SLOT_WIDE;
-                else cls = SLOT_SLOW;
-            }
-            slot_cls[sl] = cls;
-        }
-        __syncthreads();
-        ETRACE(4);
-        // ---- pass C: one thread per mode: bit-exact window, component classification, tables ----
-        if (tid < EXP_BATCH && !mt[tid].have && base + tid < nmodes) {
-            // unused slot of a mode table (or a rejected record): an empty record, so stale data is never listed
-            ModeRec mr;
-            mr.i0 = 0; mr.i1 = 0; mr.ncomp = 0; mr.nfast = 0; mr.l = 0; mr.pad = 0;
-            mr.numin = 1.0; mr.numax = 0.0;
-            mr.fc = 0; mr.gamma = 0; mr.qa = 0; mr.qb0 = 1; mr.qc = 0;
-            modes[base + tid] = mr;
-        }
-        if (tid < EXP_BATCH && mt[tid].have) {
-            const ModeTmp& t = mt[tid];
-            const int j = base + tid;
-            const int l = t.l;
-            ModeRec mr;
-            const int i0 = t.i0, i1 = t.i1, bad = t.bad;
-            if (bad) atomicOr(&s_status, TAMCMC_ST_WINDOW);
-            mr.i0 = i0; mr.i1 = i1; mr.l = l; mr.fc = t.fc; mr.gamma = t.W;
-            mr.qa = cm.asym / t.fc;
-            mr.qb0 = 1.0 - cm.asym;
-            { const double k2 = 0.5 * t.W * cm.asym / t.fc; mr.qc = k2 * k2; }
-            mr.pad = 0;
-            if (!isfinite(t.fc) || !isfinite(t.W) || (cm.asym != 0.0 && (!isfinite(mr.qa) || !isfinite(mr.qc))))
-                atomicOr(&s_status, TAMCMC_ST_NONFINITE);
-            const double sg = 2.0 / t.W;
-            CompRec* out = comps + (size_t)j * TAMCMC_MAX_COMP_PER_MODE;
-            int nf = 0, ns = 0, wide = 0;
-            double numin = 1e300, numax = -1e300;        // extent of the FAST components' centres (far-field test of the fused kernel)
-            // FAST/WIDE components first, then the SLOW ones (classes from pass B)
-            for (int pass = 0; pass < 2; pass++)
-                for (int k = 0; k <= 2 * l; k++) {
-                    const int sl = tid * TAMCMC_MAX_COMP_PER_MODE + k;
-                    const unsigned char cls = slot_cls[sl];
-                    if (cls == SLOT_NONFINITE) { if (pass == 0) atomicOr(&s_status, TAMCMC_ST_NONFINITE); continue; }
-                    if (cls == SLOT_DEAD) continue;
-                    const bool fast = (cls == SLOT_FAST || cls == SLOT_WIDE);
-                    if (fast != (pass == 0)) continue;
-                    CompRec cr;
-                    cr.nu = slot_nu[sl]; cr.m = k - l;
-                    if (fast) {
-                        cr.flags = TAMCMC_CF_FAST; cr.s = slot_s[sl]; cr.a = slot_ia[sl]; nf++; wide |= (cls == SLOT_WIDE);
-                        numin = fmin(numin, cr.nu); numax = fmax(numax, cr.nu);
-                    }
-                    else { cr.flags = TAMCMC_CF_SLOW; cr.s = sg; cr.a = slot_A[sl]; ns++; }
-                    out[nf + ns - 1] = cr;
+            if (live) {
+                const double eta0 = t.eta_cm ? cm.eta0 : t.eta0;
+                if (model == 23) nu = nu_aj(l, m, t.fc, t.a, eta0);
+                else if (mode_table) { nu = nu_aj(l, m, t.fc, t.a, eta0); if (l != 0) nu = nu + params[t.hoff + m]; }   // build_lorentzian.cpp:182-190
+                else nu = nu_a1etaa3(l, m, t.fc, t.f_s, eta0, cm.a3);
+                if (t.H >= 0.0) h = t.H * cm.ratios[l][k];
+                else {
+                    const double PI = 3.141592653589793238462643383279502884;
+                    h = (l == 0) ? params[t.hoff] : params[t.hoff + (m < 0 ? -m : m)];
+                    if (cm.do_amp) h = h / (PI * t.W);
+                    h = fabs(h);
                 }
-            mr.nfast = nf | (wide << 16); mr.ncomp = nf + ns;      // bit 16: the mode has WIDE fast components
-            // numin > numax: the mode is never folded into a tile's far-field polynomial (no FAST components or WIDE dynamic range)
-            const bool far_capable = nf > 0 && !wide;
-            mr.numin = far_capable ? numin : 1.0; mr.numax = far_capable ? numax : 0.0;
-            modes[j] = mr;
-            // per-tile cost: difference array over the LOCAL tiles this window touches
-            if (!bad && mr.ncomp > 0) {
-                const int lo = max(i0, sd.bin0) - sd.bin0, hi = min(i1, sd.bin0 + sd.Nloc) - sd.bin0;
-                if (hi > lo) {
-                    int t0 = lo / sd.tile_bins, t1 = (hi - 1) / sd.tile_bins + 1;
-                    atomicAdd(&tcover[t0], 1); atomicAdd(&tcover[t1], -1);      // every tile the window touches, near or far
-                    if (far_capable && A.far_ratio > 0.0 && ns == 0) {
-                        // the fused kernel merges this mode per bin only in the tiles whose centre lies within far_ratio half
-                        // tiles of its components; elsewhere it costs nothing per bin (a scheduling weight, not a result)
-                        const double T = (double)sd.tile_bins, Rb = A.far_ratio * 0.5 * T + 0.5 * T;
-                        const double bmin = (numin - sd.x0) / sd.step - (double)sd.bin0, bmax = (numax - sd.x0) / sd.step - (double)sd.bin0;
-                        const double tl = floor((bmin - Rb) / T), th = ceil((bmax + Rb) / T) + 1.0;
-                        if (tl > (double)t0) t0 = (int)fmin(tl, (double)t1);
-                        if (th < (double)t1) t1 = (int)fmax(th, (double)t0);
-                    }
-                    if (t1 > t0) {
-                        atomicAdd(&tcost[t0], mr.ncomp);
-                        atomicAdd(&tcost[t1], -mr.ncomp);
-                    }
+                cs = t.sg / sqrt(h); ia = 1.0 / h;                   // scaled FAST form (used if the slot qualifies)
+                // classification against the mode's window.  FAST: t' = (1+e^2)/A stays inside [1e-8, 1e16] over the whole
+                // window, so 16 merges between two exponent renormalisations cannot leave the FP64 range.  WIDE (very narrow
+                // modes, e.g. red-giant mixed modes far narrower than a bin): t' inside [1e-16, 1e32], same scaled form, but the
+                // segments that hold such a mode renormalise every 4 merges.  Everything else live: general (SLOW) form.
+                if (!isfinite(h) || !isfinite(nu)) cls = SLOT_NONFINITE;
+                else if (h != 0.0 && t.W > 0.0) {               // else: contributes exactly 0 (gamma == 0: DESIGN.md deviations)
+                    const double xlo = sd.x0 + (double)t.i0 * sd.step, xhi = sd.x0 + (double)t.i1 * sd.step;
+                    const double emax = t.sg * fmax(fabs(xlo - nu), fabs(xhi - nu));
+                    if (!(emax < 1e100)) cls = SLOT_NONFINITE;
+                    else if (h >= 1e-8 && h <= 1e8 && emax < 1e4) cls = SLOT_FAST;
+                    else if (h >= 1e-16 && h <= 1e16 && emax < 1e8) cls = SLOT_WIDE;
+                    else cls = SLOT_SLOW;
+                }
+            }
+            // votes of the mode's 8 lanes
+            const int gsh = (lane >> 3) << 3;
+            const bool isfast = (cls == SLOT_FAST || cls == SLOT_WIDE);
+            const unsigned fastm = (__ballot_sync(0xffffffffu, isfast) >> gsh) & 0xffu;
+            const unsigned slowm = (__ballot_sync(0xffffffffu, cls == SLOT_SLOW) >> gsh) & 0xffu;
+            const unsigned widem = (__ballot_sync(0xffffffffu, cls == SLOT_WIDE) >> gsh) & 0xffu;
+            const unsigned nonfm = (__ballot_sync(0xffffffffu, cls == SLOT_NONFINITE) >> gsh) & 0xffu;
+            double numin = isfast ? nu : 1e300, numax = isfast ? nu : -1e300;          // extent of the FAST components' centres
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) { numin = fmin(numin, __shfl_xor_sync(0xffffffffu, numin, d)); numax = fmax(numax, __shfl_xor_sync(0xffffffffu, numax, d)); }
+            const int j = base + jj;
+            const int nf = __popc(fastm), ns = __popc(slowm);
+            if (isfast || cls == SLOT_SLOW) {
+                // FAST/WIDE components first (in m order), then the SLOW ones
+                CompRec cr;
+                cr.nu = nu; cr.m = m;
+                if (isfast) { cr.flags = TAMCMC_CF_FAST; cr.s = cs; cr.a = ia; }
+                else { cr.flags = TAMCMC_CF_SLOW; cr.s = t.sg; cr.a = h; }
+                const int pos = isfast ? __popc(fastm & ((1u << k) - 1u)) : nf + __popc(slowm & ((1u << k) - 1u));
+                comps[(size_t)j * TAMCMC_MAX_COMP_PER_MODE + pos] = cr;
+            }
+            if (k == 0 && !t.have && j < nmodes) {
+                // unused slot of a mode table (or a rejected record): an empty record, so stale data is never listed
+                ModeRec mr;
+                mr.i0 = 0; mr.i1 = 0; mr.ncomp = 0; mr.nfast = 0; mr.l = 0; mr.pad = 0;
+                mr.numin = 1.0; mr.numax = 0.0;
+                mr.fc = 0; mr.gamma = 0; mr.qa = 0; mr.qb0 = 1; mr.qc = 0;
+                modes[j] = mr;
+            }
+            if (k == 0 && t.have) {
+                ModeRec mr;
+                const int i0 = t.i0, i1 = t.i1, bad = t.bad;
+                if (bad) atomicOr(&s_status, TAMCMC_ST_WINDOW);
+                if (nonfm) atomicOr(&s_status, TAMCMC_ST_NONFINITE);
+                mr.i0 = i0; mr.i1 = i1; mr.l = l; mr.fc = t.fc; mr.gamma = t.W;
+                if (cm.asym != 0.0) {
+                    mr.qa = cm.asym / t.fc;
+                    const double k2 = 0.5 * t.W * cm.asym / t.fc;
+                    mr.qc = k2 * k2;
+                } else { mr.qa = 0.0; mr.qc = 0.0; }      // symmetric profiles: the fused kernel never reads q(x) of such a chain (asym_flag == 0)
+                mr.qb0 = 1.0 - cm.asym;
+                mr.pad = 0;
+                if (!isfinite(t.fc) || !isfinite(t.W) || (cm.asym != 0.0 && (!isfinite(mr.qa) || !isfinite(mr.qc))))
+                    atomicOr(&s_status, TAMCMC_ST_NONFINITE);
+                const int wide = widem ? 1 : 0;
+                mr.nfast = nf | (wide << 16); mr.ncomp = nf + ns;      // bit 16: the mode has WIDE fast components
+                // numin > numax: the mode is never folded into a tile's far-field polynomial (no FAST components or WIDE dynamic range)
+                const bool far_capable = nf > 0 && !wide;
+                mr.numin = far_capable ? numin : 1.0; mr.numax = far_capable ? numax : 0.0;
+                modes[j] = mr;
+                // per-tile cost: difference array over the LOCAL tiles this window touches
+                if (!bad && mr.ncomp > 0) {
+                    const int lo = max(i0, sd.bin0) - sd.bin0, hi = min(i1, sd.bin0 + sd.Nloc) - sd.bin0;
+                    if (hi > lo) {
+                        int t0 = lo / sd.tile_bins, t1 = (hi - 1) / sd.tile_bins + 1;
+                        atomicAdd(&tcover[t0], 1); atomicAdd(&tcover[t1], -1);      // every tile the window touches, near or far
+                        if (far_capable && A.far_ratio > 0.0 && ns == 0) {
+                            // the fused kernel merges this mode per bin only in the tiles whose centre lies within far_ratio half
+                            // tiles of its components; elsewhere it costs nothing per bin (a scheduling weight, not a result)
+                            const double T = (double)sd.tile_bins, Rb = A.far_ratio * 0.5 * T + 0.5 * T;
+                            const double bmin = (numin - sd.x0) * inv_step - (double)sd.bin0, bmax = (numax - sd.x0) * inv_step - (double)sd.bin0;
+                            const double tl = floor((bmin - Rb) * inv_T), th = ceil((bmax + Rb) * inv_T) + 1.0;
+                            if (tl > (double)t0) t0 = (int)fmin(tl, (double)t1);
+                            if (th < (double)t1) t1 = (int)fmax(th, (double)t0);
+                        }
+                        if (t1 > t0) {
+                            atomicAdd(&tcost[t0], mr.ncomp);
+                            atomicAdd(&tcost[t1], -mr.ncomp);
+                        }
 #if TAMCMC_EDGE_COST > 0
-                    // a tile that holds a window edge merges the mode under masks (general entries): about twice a plain merge
-                    {
-                        const int e0 = lo / sd.tile_bins, e1 = (hi - 1) / sd.tile_bins;
-                        if (lo % sd.tile_bins) { atomicAdd(&tcost[e0], TAMCMC_EDGE_COST * mr.ncomp); atomicAdd(&tcost[e0 + 1], -TAMCMC_EDGE_COST * mr.ncomp); }
-                        if (hi % sd.tile_bins) { atomicAdd(&tcost[e1], TAMCMC_EDGE_COST * mr.ncomp); atomicAdd(&tcost[e1 + 1], -TAMCMC_EDGE_COST * mr.ncomp); }
-                    }
+                        // a tile that holds a window edge merges the mode under masks (general entries): about twice a plain merge
+                        {
+                            const int e0 = lo / sd.tile_bins, e1 = (hi - 1) / sd.tile_bins;
+                            if (lo % sd.tile_bins) { atomicAdd(&tcost[e0], TAMCMC_EDGE_COST * mr.ncomp); atomicAdd(&tcost[e0 + 1], -TAMCMC_EDGE_COST * mr.ncomp); }
+                            if (hi % sd.tile_bins) { atomicAdd(&tcost[e1], TAMCMC_EDGE_COST * mr.ncomp); atomicAdd(&tcost[e1 + 1], -TAMCMC_EDGE_COST * mr.ncomp); }
+                        }
 #endif
+                    }
                 }
             }
         }
+        ETRACE(4);
         __syncthreads();
     }
 
     __syncthreads();       // phase 1b has no barrier of its own when no batch ran (envelope models, masked chains)
     ETRACE(5);
     // ---------------- phase 3: tile costs -> heavy-first work queue ----------------
-    const bool enqueue = run && (s_status == 0);
+    const int status_all = s_status | s_status1b;
+    run = !inactive && !(status_all & TAMCMC_ST_BADCFG);
+    const bool enqueue = run && (status_all == 0);
     if (enqueue) {
         // inclusive scan of the difference array (serial per warp-strided chunk would need carries; ntiles is
         // a few hundred: one warp scans it in 32-wide steps with a running carry)
@@ -1025,9 +1044,9 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     __syncthreads();
     ETRACE(6);
     if (tid == 0) {
-        A.status[sc] = s_status;
+        A.status[sc] = status_all;
         A.asym_flag[sc] = (!inactive && cm.asym != 0.0) ? 1 : 0;
-        if (s_status != 0) A.out_logL[sc] = nan("");
+        if (status_all != 0) A.out_logL[sc] = nan("");
     }
 }
 
