@@ -14,12 +14,14 @@ python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err || { echo "ben
 cat $OUT/${TAG}_bench.json
 python bench.py --impl reference --steps 10 --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
 cat $OUT/${TAG}_bench_reference.json
-BCMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+BCMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extra"
 $BCMD > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $BCMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:tamcmc_whittle_kernel -s 4 -c 2 -f -o $OUT/${TAG}_whittle $BCMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:tamcmc_expand_kernel -s 4 -c 2 -f -o $OUT/${TAG}_expand $BCMD > $OUT/${TAG}_ncu_expand.log 2>&1
+echo "ncu expand rc=$?"
 python profiles/bench_configs.py --configs c1,c4,c3,c5,env --steps 50 > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err
 cat $OUT/${TAG}_configs.jsonl | cut -c1-200
 python profiles/far_accuracy.py > $OUT/${TAG}_far_accuracy.json 2> $OUT/${TAG}_far_accuracy.err; head -c 600 $OUT/${TAG}_far_accuracy.json

@@ -40,7 +40,7 @@ if os.path.exists(p):
     step = {k: v for k, v in agg.items() if "expand" in k or "ksi_kernel" in k or ("whittle_kernel<0" in k) or "whittle_kernel<(bool)0" in k}
     tot = sum(v[1] / v[0] for v in step.values()) or 1.0
     with open(os.path.join(dst, "launch_shares.txt"), "w") as f:
-        f.write("ncu --metrics gpu__time_duration.sum --clock-control none, command: python bench.py --steps 5 --warmup 3 --no-cpu-baseline\n")
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none, command: python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extra\n")
         f.write("per-launch times are cold-cache and serialised; one evaluation (step) = tamcmc_expand_kernel + tamcmc_whittle_kernel<0, bins per thread>\n\n")
         for k, v in agg.items():
             f.write("%-50s launches %4d  avg %9.2f us\n" % (k, v[0], v[1] / v[0] / 1e3))
@@ -48,6 +48,12 @@ if os.path.exists(p):
         for k, v in step.items():
             f.write("  %-48s %5.1f %%\n" % (k, 100 * (v[1] / v[0]) / tot))
     print(open(os.path.join(dst, "launch_shares.txt")).read())
+
+# ---- full capture of the expander ----
+rep = os.path.join(src, tag + "_expand.ncu-rep")
+if os.path.exists(rep):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "ncu_summary.py"), rep], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    open(os.path.join(dst, "expand_ncu_full_summary.txt"), "w").write(out)
 
 # ---- full capture of the fused kernel ----
 rep = os.path.join(src, tag + "_whittle.ncu-rep")
