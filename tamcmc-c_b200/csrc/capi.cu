@@ -73,6 +73,7 @@ int upload_tables(int device)
         CK(tamcmc_upload_dmm_tables(&coef[0][0][0], &nnum[0][0], &nden[0]));
     }
     CK(tamcmc_expand_configure());
+    { int per_sm = 0; CK(tamcmc_whittle_tiles_configure(&per_sm)); }
     { int g = 0, gh = 0; CK(tamcmc_whittle_configure(&g, &gh)); const int d = (device < 64 && device >= 0) ? device : 0; g_grid_ctas[d] = g; g_grid_ctas_half[d] = gh; }
     if (device >= 0 && device < 64) g_tables_uploaded[device] = true;
     return TAMCMC_OK;
@@ -150,6 +151,9 @@ struct tamcmc_gpu_ctx {
     int look = 3, look_end = 3;       // producer look-ahead in tiles (TAMCMC_GPU_LOOK / TAMCMC_GPU_LOOK_END = 1 .. producers - 1; tuning aid)
     double far_ratio = TAMCMC_FAR_RATIO_DEFAULT;   // far-field folding (TAMCMC_GPU_FAR_RATIO; 0 = off)
     bool use_graphs = true;
+    bool use_tiles = true;           // fused kernel: one CTA per tile (whittle_tiles.cu); TAMCMC_GPU_KERNEL=ring selects the persistent
+                                     // producer / consumer ring of whittle.cu
+    unsigned int nitems_max = 0;     // work items a launch can have: sum over the stars of ntiles x Nchains
     bool use_pdl = false;            // programmatic dependent launch expand -> fused kernel: measured no gain inside a CUDA graph
                                      // (profiles/r1/NOTES.md); TAMCMC_GPU_PDL=1 enables it
     // exchange of a bin-sharded spectrum (tamcmc_gpu_exchange_*): peer-mapped buffers of all ranks, this rank's counter
@@ -190,7 +194,8 @@ ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const uns
     a.tiles_stride = c->tiles_stride; a.max_tiles = c->max_tiles; a.trace = c->d_trace ? c->d_trace + 64 * 2048 : nullptr;
     a.ksi_part = c->d_ksi; a.ksi_slices = c->ksi_slices; a.ksi_slice_bins = c->ksi_slice_bins;
     a.far_ratio = c->far_ratio;
-    a.bgqueue = c->d_bgqueue;
+    a.bgqueue = c->use_tiles ? nullptr : c->d_bgqueue;
+    a.mark_bgonly = c->use_tiles ? 1 : 0;
     return a;
 }
 
@@ -201,7 +206,7 @@ WhittleArgs make_whittle_args(tamcmc_gpu_ctx* c, double* d_out, int raw_sum, boo
     a.x = c->d_x; a.y = c->d_y; a.lnx = c->d_lnx; a.wsig = c->d_wsig; a.likelihood = c->likelihood;
     a.modes = c->d_modes; a.comps = c->d_comps; a.noise = c->d_noise;
     a.asym_flag = c->d_asym; a.Tcoefs = c->d_Tcoefs;
-    a.queue = c->d_queue; a.bgqueue = c->d_bgqueue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec;
+    a.queue = c->d_queue; a.bgqueue = c->use_tiles ? nullptr : c->d_bgqueue; a.qctl = c->d_qctl; a.qcap = c->qcap; a.tilerec = c->d_tilerec;
     a.partial = c->d_partial;
     a.out = d_out; a.model_out = c->d_model;
     a.p = c->p; a.Nchains = c->Nchains; a.modes_stride = c->modes_stride; a.tiles_stride = c->tiles_stride;
@@ -230,7 +235,8 @@ int enqueue_sequence(tamcmc_gpu_ctx* c, const double* d_params, const unsigned c
     if (prof) CK(REC(0));
     CK(tamcmc_launch_expand(ea, c->SC(), st));
     if (prof) CK(REC(1));
-    CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, c->tile_bins, st, c->use_pdl && !prof));
+    if (c->use_tiles) CK(tamcmc_launch_whittle_tiles(wa, c->nitems_max, false, c->tile_bins, st));
+    else CK(tamcmc_launch_whittle(wa, c->grid_ctas, false, c->tile_bins, st, c->use_pdl && !prof));
     if (prof) CK(REC(2));
 #undef REC
     return TAMCMC_OK;
@@ -251,7 +257,7 @@ int launch_eval(tamcmc_gpu_ctx* c, const double* d_params, const unsigned char* 
 {
     // the host's copy of the launch epoch (what the last CTA of THIS launch will publish) advances only once the launch has
     // been accepted: a failed capture / instantiate / launch leaves host and device counters in step
-    auto launched_ok = [c]() { c->launches += c->d_ksi ? 3 : 2; const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; };
+    auto launched_ok = [c]() { c->launches += (c->d_ksi ? 3 : 2) + (c->use_tiles ? 1 : 0); const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; };
     const bool prof = c->profiling && st == c->stream;
     if (!c->use_graphs) { const int rc = enqueue_sequence(c, d_params, d_active, d_logL, raw_sum, st, prof, false, mirror); if (rc == TAMCMC_OK) launched_ok(); else resync_epoch(c); return rc; }
     for (int i = 0; i < c->ngraphs; i++) {
@@ -370,6 +376,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     tamcmc_gpu_ctx* c = new tamcmc_gpu_ctx();
     c->device = device; c->nstars = nstars; c->Nchains = Nchains; c->p = p; c->likelihood = likelihood_id;
     if (const char* e = std::getenv("TAMCMC_GPU_NO_GRAPH")) c->use_graphs = !(e[0] == '1');
+    if (const char* e = std::getenv("TAMCMC_GPU_KERNEL")) c->use_tiles = !(std::strcmp(e, "ring") == 0);
     if (const char* e = std::getenv("TAMCMC_GPU_PDL")) c->use_pdl = (e[0] == '1');
     if (const char* e = std::getenv("TAMCMC_GPU_STAGGER_NS")) c->stagger_ns = std::atoi(e);
     if (const char* e = std::getenv("TAMCMC_GPU_LOOK")) { const int v = std::atoi(e); if (v >= 1 && v < TAMCMC_PRODUCERS) c->look = v; }
@@ -448,6 +455,8 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         if (sd.Nloc > maxN) maxN = sd.Nloc;
     }
     c->total_tiles = tiles;
+    c->nitems_max = (unsigned int)((size_t)tiles * (size_t)Nchains);
+    if ((size_t)nstars * (size_t)Nchains * (size_t)c->tiles_stride >= 0x80000000ull) c->use_tiles = false;      // bit 31 of a queue entry is a flag there
     if (c->modes_stride < 1) c->modes_stride = 1;       // envelope models only: keep the mode tables non-empty
     c->max_tiles = c->tiles_stride;
     // the expander stages one parameter row + the per-tile cost array in (at most 96 KB of) shared memory
@@ -697,7 +706,8 @@ int tamcmc_gpu_model(tamcmc_gpu_ctx* c, int star, const double* params_row, doub
     { int rc = expand_single(c, star, params_row); if (rc) return rc; }
     const StarDesc& sd = c->h_stars[star];
     WhittleArgs wa = make_whittle_args(c, c->d_logL(), 0, false);
-    { const cudaError_t e = tamcmc_launch_whittle(wa, c->grid_ctas, true, c->tile_bins, c->stream, false); if (e != cudaSuccess) { resync_epoch(c); return fail_cuda(e, "tamcmc_launch_whittle"); } }
+    { const cudaError_t e = c->use_tiles ? tamcmc_launch_whittle_tiles(wa, c->nitems_max, true, c->tile_bins, c->stream)
+                                         : tamcmc_launch_whittle(wa, c->grid_ctas, true, c->tile_bins, c->stream, false); if (e != cudaSuccess) { resync_epoch(c); return fail_cuda(e, "tamcmc_launch_whittle"); } }
     c->launches += 1;
     { const unsigned e = c->epoch_host + 1u; c->epoch_host = e ? e : 1u; }       // only after the launch was accepted
     CK(cudaMemcpyAsync(c->h_out, c->d_out, c->out_bytes(), cudaMemcpyDeviceToHost, c->stream));

@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
                 const unsigned v = (unsigned)tcost[t], cls = v & (2u * TAMCMC_NBUCKETS - 1u), rank = v >> (TAMCMC_NBUCKETS_LOG2 + 1);
                 const unsigned item = (unsigned)sc * (unsigned)A.tiles_stride + (unsigned)t;
                 if (cls == TAMCMC_NBUCKETS) A.bgqueue[s_bgbase + rank] = item;
-                else A.queue[(size_t)cls * A.qcap + s_bbase[cls] + rank] = item;
+                else A.queue[(size_t)cls * A.qcap + s_bbase[cls] + rank] = item | ((A.mark_bgonly && tcover[t] == 0) ? 0x80000000u : 0u);
             }
         }
     }

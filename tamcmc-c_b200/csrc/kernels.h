@@ -31,6 +31,8 @@ struct ExpandArgs {
     double far_ratio;                // far-field folding of the fused kernel (0 = off): only used to weigh the tiles of the work queue
     unsigned int* bgqueue;           // [qcap] work items of the background-only tiles (QueueCtl.bg_count of them); nullptr: every tile goes
                                      // through the ring (chi_square likelihood, TAMCMC_GPU_BG_FAST=0)
+    int mark_bgonly;                 // 1: bit 31 of a queue entry marks a tile no mode window touches (the one-CTA-per-tile kernel of
+                                     // whittle_tiles.cu skips the mode lists of such a tile)
 };
 
 struct WhittleArgs {
@@ -93,6 +95,10 @@ cudaError_t tamcmc_whittle_configure(int* grid_full, int* grid_half);   // one-t
 // pdl: programmatic dependent launch behind the expand kernel on the same stream
 // tile_bins: TAMCMC_TILE or TAMCMC_TILE / 2 (the context's tile size, StarDesc.tile_bins)
 cudaError_t tamcmc_launch_whittle(const WhittleArgs& a, int grid_ctas, bool write_model, int tile_bins, cudaStream_t st, bool pdl);
+// one CTA per tile (whittle_tiles.cu): nitems_max = upper bound of the work items the expander can enqueue (CTAs beyond the
+// queue's actual length only take part in the end-of-launch protocol)
+cudaError_t tamcmc_whittle_tiles_configure(int* ctas_per_sm);
+cudaError_t tamcmc_launch_whittle_tiles(const WhittleArgs& a, unsigned nitems_max, bool write_model, int tile_bins, cudaStream_t st);
 cudaError_t tamcmc_launch_wsig(double* sigma_in_weights_out, long long n, cudaStream_t st);   // in place: w = 1/sigma^2
 cudaError_t tamcmc_launch_lnx(const double* x, double* lnx, long long n, cudaStream_t st);
 // DFMA throughput microbenchmark: returns achieved FP64 TFLOP/s (2 flops per DFMA)
