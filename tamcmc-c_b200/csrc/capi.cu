@@ -151,8 +151,8 @@ struct tamcmc_gpu_ctx {
     int look = 3, look_end = 3;       // producer look-ahead in tiles (TAMCMC_GPU_LOOK / TAMCMC_GPU_LOOK_END = 1 .. producers - 1; tuning aid)
     double far_ratio = TAMCMC_FAR_RATIO_DEFAULT;   // far-field folding (TAMCMC_GPU_FAR_RATIO; 0 = off)
     bool use_graphs = true;
-    bool use_tiles = true;           // fused kernel: one CTA per tile (whittle_tiles.cu); TAMCMC_GPU_KERNEL=ring selects the persistent
-                                     // producer / consumer ring of whittle.cu
+    bool use_tiles = false;          // TAMCMC_GPU_KERNEL=tiles: the all-warps-on-one-tile schedule of whittle_tiles.cu instead of the
+                                     // producer / consumer ring of whittle.cu (same results; measured slower, profiles/r2/NOTES.md)
     unsigned int nitems_max = 0;     // work items a launch can have: sum over the stars of ntiles x Nchains
     bool use_pdl = false;            // programmatic dependent launch expand -> fused kernel: measured no gain inside a CUDA graph
                                      // (profiles/r1/NOTES.md); TAMCMC_GPU_PDL=1 enables it
@@ -376,7 +376,7 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
     tamcmc_gpu_ctx* c = new tamcmc_gpu_ctx();
     c->device = device; c->nstars = nstars; c->Nchains = Nchains; c->p = p; c->likelihood = likelihood_id;
     if (const char* e = std::getenv("TAMCMC_GPU_NO_GRAPH")) c->use_graphs = !(e[0] == '1');
-    if (const char* e = std::getenv("TAMCMC_GPU_KERNEL")) c->use_tiles = !(std::strcmp(e, "ring") == 0);
+    if (const char* e = std::getenv("TAMCMC_GPU_KERNEL")) c->use_tiles = (std::strcmp(e, "tiles") == 0);
     if (const char* e = std::getenv("TAMCMC_GPU_PDL")) c->use_pdl = (e[0] == '1');
     if (const char* e = std::getenv("TAMCMC_GPU_STAGGER_NS")) c->stagger_ns = std::atoi(e);
     if (const char* e = std::getenv("TAMCMC_GPU_LOOK")) { const int v = std::atoi(e); if (v >= 1 && v < TAMCMC_PRODUCERS) c->look = v; }
