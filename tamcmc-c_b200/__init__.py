@@ -16,6 +16,7 @@ import numpy as np
 
 from . import synth  # noqa: F401  (synthetic inputs; numpy only)
 from . import formats  # noqa: F401  (readers for the reference's simplest on-disk inputs; numpy only)
+from . import model_setup  # noqa: F401  (parsed .model file -> parameter vector, plength, relax flags, prior table; numpy only)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TAMCMC_GPU_LIB selects another build of the SAME CUDA library (e.g. the -DTAMCMC_TRACE profiling build)
