@@ -453,6 +453,256 @@ def build_init_ms_global(mf, resol):
             "extra_priors": extra, "inputs_names": allp.names, "priors_names": allp.pnames, "numax": numax, "err_numax": err_numax}
 
 
+_RGB_SPLIT_POS = {"rot_env": 0, "Rot_env": 0, "a1_env": 0, "rot_core": 1, "Rot_core": 1, "a1_core": 1, "a2_core": 2, "a2_env": 3,
+                  "a3_env": 4, "a4_env": 5, "a5_env": 6, "a6_env": 7}          # settings_aj_splittings_RGB, io_asymptotic.cpp:877-984
+_RGB_SPLIT_NAME = {0: "rot_env", 1: "rot_core", 2: "a2_core", 3: "a2_env", 4: "a3_env", 5: "a4_env", 6: "a5_env", 7: "a6_env"}
+_RGB_L1_POS = {"DP1": 1, "alpha_g": 2, "q": 3, "sigma_Hl1": 4, "Wfactor": 6, "Hfactor": 7}      # global parameters of the l=1 mixed modes (:513-560)
+RGB_V4_MODELS = {"model_RGB_asympt_aj_AppWidth_HarveyLike_v4": 25, "model_RGB_asympt_aj_CteWidth_HarveyLike_v4": 27}      # -> tamcmc_host_expand_rgb_v4 ids
+
+
+def set_width_app2016_params_v2(numax, err_numax):
+    """io_ms_global.cpp:1625-1716: initial guesses and priors of the six parameters of the Appourchaux et al. 2016 width relation"""
+    w = Block(6)
+    out = [abs(numax), abs(numax), abs(4. / 2150. * numax + (1. - 1000. * 4. / 2150.)), abs(0.8 / 2150. * numax + (4.5 - 1000. * 0.8 / 2150.)),
+           abs(3400. / 2150. * numax + (1000. - 1000. * 3400. / 2150.)), abs(2.8 / 2200. * numax + (1. - 2.8 / 2200. * 1.))]
+    if numax < 800:
+        out[3] = out[3] / 5
+    pri = [[out[0], err_numax], [out[1], err_numax], [0, 6], [0, 10], [out[4], out[4] * 0.25], [0., 15]]
+    kinds = ["Gaussian", "Gaussian", "Uniform", "Uniform", "Gaussian", "Uniform"]
+    for k, nm in enumerate(("numax", "nudip", "alpha", "Gamma_alpha", "Wdip", "DeltaGammadip")):
+        w.fill("width:Appourchaux_v2:" + nm, kinds[k], out[k], pri[k] + [EMPTY, EMPTY], k, 0)
+    return w
+
+
+def build_init_asymptotic(mf, resol):
+    """The red-giant dialect: build_init_asymptotic (tamcmc/sources/io_asymptotic.cpp:32-875) for the two models it still
+    accepts, model_RGB_asympt_aj_{AppWidth,CteWidth}_HarveyLike_v4 (every other name makes the reference exit, :86-92, :139-141).
+    The l=1 block of the frequency section holds the global parameters of the mixed modes (delta01, DP1, alpha_g, q, sigma_Hl1, -,
+    Wfactor, Hfactor) followed by the nodes (fref) and values (ferr) of the bias spline taken from the hyper-prior rows; the result
+    is the vector tamcmc_host_expand_rgb_v4 (csrc/host_rgb.cpp) turns into a mode-table row."""
+    Hmin, Hmax = 1.0, 10000.0
+    NG = 7                                          # Nmixedmodes_g_params
+    Dnu = mf["Dnu"]
+    sigma_limit = Dnu / 10.
+    numax, err_numax = mf["numax"], mf["err_numax"]
+    names, cpri, mc = mf["common_names"], mf["common_names_priors"], mf["modes_common"]
+    els = np.asarray(mf["els"])
+    lmax = int(els.max())
+    fullname, do_amp, dwa = " ", 0, 0
+    for i, nm in enumerate(names):
+        if nm == "model_fullname":
+            fullname = cpri[i]
+            if fullname == "model_RGB_asympt_aj_AppWidth_HarveyLike_v4":
+                dwa = 2
+                if numax <= 0:
+                    raise ValueError("%s needs a positive numax (!n line) (io_asymptotic.cpp:97-106)" % fullname)
+            elif fullname == "model_RGB_asympt_aj_CteWidth_HarveyLike_v4":
+                dwa = 1
+                if numax != -9999 and numax <= 0:
+                    raise ValueError("%s: numax must be positive or absent (io_asymptotic.cpp:113-122)" % fullname)
+        if nm == "fit_squareAmplitude_instead_Height":
+            if cpri[i] != "bool":
+                _fatal(nm, "bool")
+            do_amp = int(mc[i, 0])
+    if fullname not in RGB_V4_MODELS:
+        raise ValueError("model name %r: only the two *_aj_*Width_HarveyLike_v4 models are accepted (io_asymptotic.cpp:135-141)" % fullname)
+    vis, inc = Block(lmax), Block(1)
+
+    eig = np.asarray(mf["eigen_params"], dtype=np.float64)
+    f_inputs, f_min, f_max, w_inputs, h_inputs, f_relax, w_relax, h_relax = [], [], [], [], [], [], [], []
+    Nf_el = [0, 0, 0, 0]
+    for el in range(lmax + 1):
+        pos0 = [k for k in range(len(els)) if els[k] == el]
+        f_el = [mf["freqs_ref"][k] for k in pos0]
+        pos_el = [k for k in range(eig.shape[0]) if int(eig[k, 0]) == el]
+        Nf_el[el] = len(pos_el)
+        for k in pos_el:
+            f_inputs.append(eig[k, 1]); f_min.append(eig[k, 2]); f_max.append(eig[k, 3])
+            if el == 0:
+                w_inputs.append(eig[k, 4]); h_inputs.append(eig[k, 5])
+            hits = [j for j in range(len(f_el)) if eig[k, 1] - 1e-2 <= f_el[j] <= eig[k, 1] + 1e-2]
+            if len(hits) != 1:
+                raise ValueError("the frequency %r is not unique in / absent from the relax list (io_asymptotic.cpp:176-188)" % eig[k, 1])
+            f_relax.append(bool(mf["relax_freq"][pos0[hits[0]]]))
+            if el == 0:
+                w_relax.append(bool(mf["relax_gamma"][pos0[hits[0]]])); h_relax.append(bool(mf["relax_H"][pos0[hits[0]]]))
+    if do_amp:
+        h_name = "Amplitude_l0_rgb"
+        h_inputs = [float(PI_LD * LD(w_inputs[k]) * LD(h_inputs[k])) for k in range(len(h_inputs))]
+    else:
+        h_name = "Height_l0_rgb"
+    height = Block(len(h_relax))
+    width = Block(1 if dwa == 1 else 6)
+
+    # ---- the bias spline: nodes and values from the hyper-prior rows (:254-285) ----
+    hp, hpn = np.asarray(mf["hyper_priors"], dtype=np.float64), list(mf["hyper_priors_names"])
+    nrows = hp.shape[0]
+    Nfix = 0
+    for i in range(nrows - 1):
+        if hp[i + 1, 0] < hp[i, 0]:
+            raise ValueError("the reference frequencies of the bias spline must increase (io_asymptotic.cpp:259-262)")
+        if hpn[i] == "Fix":
+            Nfix += 1
+    if Nfix != len(hpn) - 1 and Nfix != 0:
+        raise ValueError("either all or none of the bias values may be fixed (io_asymptotic.cpp:267-270)")
+    fref = hp[:, 0].copy()
+    ferr = np.zeros(nrows) if hp.shape[1] == 1 else hp[:, 1].copy()
+    Nmm = NG + 2 * nrows + 1
+    freq = Block(Nf_el[0] + Nmm + Nf_el[2] + Nf_el[3])
+    tmp = [Hmin, Hmax, EMPTY, EMPTY]
+    for k in range(len(h_inputs)):
+        height.fill(h_name, "Jeffreys" if h_relax[k] else "Fix", h_inputs[k], tmp, k, 0)
+    cpt = 0
+    tmp = [EMPTY] * 4                      # (the reference's tmpXd still holds the height bounds when a fixed frequency is filled first: "Fix" ignores it)
+    for k in range(len(f_inputs)):
+        if k < Nf_el[0] or k >= Nf_el[0] + Nf_el[1]:
+            if f_relax[k]:
+                tmp = [f_min[k], f_max[k], 0.0025 * Dnu, 0.0025 * Dnu]
+                freq.fill("Frequency_RGB_l", "GUG", f_inputs[k], tmp, cpt, 0)
+            else:
+                freq.fill("Frequency_RGB_l", "Fix", f_inputs[k], tmp, cpt, 0)
+            cpt += 1
+        elif k == Nf_el[0]:
+            cpt += Nmm
+    cpt = Nf_el[0] + NG + 1
+    for k in range(nrows):
+        freq.fill("fref_bias", "Fix", fref[k], [EMPTY] * 4, cpt, 0)
+        cpt += 1
+    if hp.shape[1] == 1:
+        freq.fill("ferr_bias", "Uniform", ferr[0], [-Dnu / 2, Dnu / 20, EMPTY, EMPTY], cpt, 0); cpt += 1
+        for k in range(1, nrows - 1):
+            freq.fill("ferr_bias", "Uniform", ferr[k], [-Dnu / 20, Dnu / 20, EMPTY, EMPTY], cpt, 0); cpt += 1
+        freq.fill("ferr_bias", "Uniform", ferr[nrows - 1], [-Dnu / 20, Dnu / 2, EMPTY, EMPTY], cpt, 0); cpt += 1
+    else:
+        for k in range(nrows):
+            tmp = [EMPTY] * 4
+            for c in range(hp.shape[1] - 2):
+                tmp[c] = hp[k, 2 + c]
+            freq.fill("ferr_bias", hpn[k], ferr[k], tmp, cpt, 0); cpt += 1
+    if numax <= 0:
+        numax = _getnumax(freq.inputs[:Nf_el[0]], height.inputs)
+    elif err_numax <= 0:
+        err_numax = 0.05 * numax
+    snlm = Block(10)
+    extra = np.array([1, 2., 0.2, 0, 3], dtype=np.float64)           # :419-432 (extra_priors[4] = 3 for both v4 models)
+
+    trunc_c, model_type, bias_type = -1.0, -1, -1
+    nsplit = 0
+    for i, nm in enumerate(names):
+        pr, row = cpri[i], mc[i]
+        if nm in ("freq_smoothness", "Freq_smoothness"):
+            if pr != "bool":
+                _fatal("freq_smoothness", "bool")
+            extra[0], extra[1] = row[0], row[1]
+        if nm == "trunc_c":
+            if pr != "Fix":
+                _fatal("trunc_c", "Fix")
+            trunc_c = row[0]
+        if nm == "model_type":
+            if pr != "Fix":
+                _fatal("model_type", "Fix")
+            model_type = int(row[0])
+        if nm == "bias_type":
+            if pr != "Fix":
+                _fatal("bias_type", "Fix")
+            bias_type = int(row[0]) if Nfix != len(hpn) - 1 else 0
+        if nm in ("Frequency", "frequency"):
+            if pr not in ("GUG", "Uniform"):
+                _fatal(nm, "GUG or Uniform")
+            pe = 0
+            for k in range(len(f_inputs)):
+                if k < Nf_el[0] or k >= Nf_el[0] + Nf_el[1]:
+                    t4 = [f_min[k], f_max[k], row[3], row[4]] if pr == "GUG" else [f_min[k], f_max[k], EMPTY, EMPTY]
+                    freq.fill("Frequency_l", pr if f_relax[k] else "Fix", f_inputs[k], t4, pe, 0)
+                    pe += 1
+                elif k == Nf_el[0]:
+                    pe += Nmm
+        if nm == "delta01":
+            if pr == "Fix_Auto":
+                freq.fill("delta01", "Uniform", 0.5 * Dnu / 100, [-1. * Dnu / 100, 1. * Dnu / 100, EMPTY, EMPTY], Nf_el[0], 0)
+            else:
+                freq.fill("delta01", pr, row[0], row, Nf_el[0], 1)
+        if nm in _RGB_L1_POS:
+            if pr == "Fix_Auto":
+                _fatal(nm, "Fix_Auto")
+            freq.fill(nm, pr, row[0], row, Nf_el[0] + _RGB_L1_POS[nm], 1)
+        if nm in ("height", "Height", "amplitude", "Amplitude"):
+            if pr == "Fix_Auto":
+                _fatal(nm, "Fix_Auto")
+            for k in range(len(h_inputs)):
+                if h_relax[k]:
+                    height.fill(h_name, pr, h_inputs[k], row, k, 0)
+                else:
+                    height.fill(h_name, "Fix", h_inputs[k], row, k, 1)
+        if nm in ("width", "Width") and dwa == 1:
+            if pr != "Fix_Auto":
+                raise ValueError("the constant-width model takes Width Fix_Auto only (io_asymptotic.cpp:637-641)")
+            mean = 0.0
+            for k in range(len(w_inputs)):
+                mean = mean + w_inputs[k] / len(w_inputs)
+            width.fill("Width_l", "Jeffreys", mean, [resol, Dnu / 3., EMPTY, EMPTY], 0, 0)
+        if nm in _RGB_SPLIT_POS:
+            nsplit += 1
+            if pr == "Fix_Auto":
+                raise ValueError("Fix_Auto requested for %s: not allowed" % nm)
+            p0 = _RGB_SPLIT_POS[nm]
+            snlm.fill(_RGB_SPLIT_NAME[p0], pr, row[0], row, p0, 1)
+        if nm in ("asphericity_eta", "Asphericity_eta"):
+            snlm.names[8] = "eta0_switch"; snlm.pnames[8] = "Fix"; snlm.relax[8] = 0; snlm.inputs[8] = 0
+        if nm == "eta0_switch":
+            if pr != "Fix":
+                raise ValueError("eta0_switch must be Fix 0 or 1 (io_asymptotic.cpp:973-981)")
+            snlm.fill("eta0_switch", pr, row[0], row, 8, 1)
+        if nm in ("asymetry", "Asymetry"):
+            if pr == "Fix_Auto":
+                _fatal("asymetry", "Fix_Auto")
+            snlm.fill("Lorentzian_asymetry", pr, row[0], row, 9, 1)
+        for l in (1, 2, 3):
+            if nm in ("visibility_l%d" % l, "Visibility_l%d" % l):
+                if pr == "Fix_Auto":
+                    _fatal("visibility_l%d" % l, "Fix_Auto")
+                if lmax >= l:
+                    vis.fill("Visibility_l%d" % l, pr, row[0], row, l - 1, 1)
+        if nm in ("inclination", "Inclination"):
+            if pr == "Fix_Auto":
+                _fatal("inclination", "Fix_Auto")
+            inc.fill("Inclination", pr, 89.99999 if row[0] >= 90 else row[0], row, 0, 1)
+    if nsplit != 8:
+        raise ValueError("set rot_env, rot_core, a2_core, a2_env, a3_env, a4_env, a5_env, a6_env (8 parameters) (io_asymptotic.cpp:741-745)")
+    noise = set_noise_params(np.asarray(mf["noise_s2"], dtype=np.float64), mf["noise_params"])
+    if (model_type == -1) != (bias_type == -1):
+        raise ValueError("model_type and bias_type must be given together (io_asymptotic.cpp:772-776)")
+    if dwa == 2:
+        width = set_width_app2016_params_v2(numax, err_numax)
+    ncfg = 3 if (model_type == -1 and bias_type == -1) else 6
+    plength = np.array([len(h_inputs), lmax, Nf_el[0], Nmm, Nf_el[2], Nf_el[3], len(snlm), len(width), len(noise), len(inc), ncfg], dtype=np.int64)
+    allp = Block(int(plength.sum()))
+    p0 = 0
+    for blk in (height, vis, freq, snlm, width, noise, inc):
+        n = len(blk)
+        allp.names[p0:p0 + n] = blk.names
+        allp.pnames[p0:p0 + n] = blk.pnames
+        allp.inputs[p0:p0 + n] = blk.inputs
+        allp.relax[p0:p0 + n] = blk.relax
+        allp.priors[:, p0:p0 + n] = blk.priors
+        p0 += n
+    allp.fill("Truncation parameter", "Fix", trunc_c, mc[0], p0, 1)
+    if allp.inputs[p0] <= 0:
+        allp.inputs[p0] = 10000.
+    allp.fill("Switch for fit of Amplitudes or Heights", "Fix", do_amp, mc[0], p0 + 1, 1)
+    allp.fill("Maximum limit on random values generated by N(0,sigma_m)", "Fix", sigma_limit, [EMPTY] * 5, p0 + 2, 1)
+    if model_type != -1:
+        allp.fill("model type ", "Fix", model_type, [EMPTY] * 5, p0 + 3, 1)
+    if bias_type != -1:
+        allp.fill("bias type ", "Fix", bias_type, [EMPTY] * 5, p0 + 4, 1)
+        allp.fill("Nferr ", "Fix", nrows, [EMPTY] * 5, p0 + 5, 1)
+    if bias_type == 0 and Nfix != len(hpn) - 1:
+        for k in [j for j, nm in enumerate(allp.names) if nm == "ferr_bias"]:
+            allp.fill("ferr_bias", "Fix", 0, [EMPTY] * 5, k, 1)
+    return {"model_fullname": fullname, "inputs": allp.inputs, "relax": allp.relax, "priors": allp.priors, "plength": plength,
+            "extra_priors": extra, "inputs_names": allp.names, "priors_names": allp.pnames, "numax": numax, "err_numax": err_numax}
+
+
 def _proj(a1, inc_deg, fn):
     """sqrt(a1) * cos / sin (inc * pi / 180) as io_ms_global.cpp:1204-1216 evaluates it: the angle and its cosine in long double"""
     return float(LD(math.sqrt(a1)) * fn(LD(inc_deg) * PI_LD / LD(180.)))

@@ -6,7 +6,8 @@ Cases: two of the `.model` files the reference ships (aj and ajAlm models), and 
 parameters rewritten for the other model families the function knows (Classic, Classic_v2, Classic_v3, a1l / a1n / a1nl etaa3,
 a1etaa3 with and without the sqrt(a1) cos i / sin i keywords, amplitudes instead of heights with explicit frequency and width
 priors and a numax line).  The text of every case's `.model` file is stored with the reference's answer, so the test needs
-neither the reference tree nor the library.  Writes tests/golden/reference_ms_global_init.json."""
+neither the reference tree nor the library.  The same for the red-giant dialect (build_init_asymptotic, io_asymptotic.cpp:32-875)
+on the reference's fixture 10722175 and variants.  Writes tests/golden/reference_ms_global_init.json."""
 import ctypes as C
 import json
 import os
@@ -21,13 +22,13 @@ REF = "/root/reference/test/inputs"
 RESOL = 0.0317                                  # an arbitrary spectrum resolution (only the Fix_Auto width prior uses it)
 
 
-def ref_build(lib, path, resol):
+def ref_build(lib, path, resol, fn="refio_build_init_ms_global"):
     cap = 1024
     n = C.c_int(0)
     inputs = np.zeros(cap); relax = np.zeros(cap, dtype=np.int32); priors = np.zeros((4, cap)); pl = np.zeros(11, dtype=np.int32); ex = np.zeros(10)
     names = C.create_string_buffer(cap * 64); pn = C.create_string_buffer(cap * 32); full = C.create_string_buffer(128)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.refio_build_init_ms_global(path.encode(), C.c_double(resol), cap, C.byref(n), vp(inputs), vp(relax), vp(priors), vp(pl), vp(ex), names, pn, full)
+    rc = getattr(lib, fn)(path.encode(), C.c_double(resol), cap, C.byref(n), vp(inputs), vp(relax), vp(priors), vp(pl), vp(ex), names, pn, full)
     assert rc == 0, rc
     N = n.value
     return {"model_fullname": full.value.decode(), "inputs": inputs[:N].tolist(), "relax": relax[:N].tolist(), "priors": priors[:, :N].tolist(),
@@ -84,17 +85,42 @@ def main():
              "shipped_ajAlm_kplr003427720": open(os.path.join(REF, "kplr003427720_kasoc-psd_slc_v1_ajAlm_gate.model")).read()}
     for name, common in VARIANTS.items():
         cases["variant_" + name] = variant_text(base, common, "!n 3000.0 120.0" if name == "classic_amplitudes" else None)
+    # the red-giant dialect (build_init_asymptotic, io_asymptotic.cpp:32-875): the reference's fixture 10722175 with and without the
+    # bias spline, the constant-width model, amplitudes + an explicit frequency prior
+    rgb = open(os.path.join(REF, "RGB", "v1.86.0", "10722175.model")).read()
+    cases["rgb_shipped_10722175"] = rgb
+    cases["rgb_shipped_10722175_nobias"] = open(os.path.join(REF, "RGB", "v1.86.0", "10722175_nobias.model")).read()
+    cases["rgb_variant_ctewidth"] = rgb.replace("model_RGB_asympt_aj_AppWidth_HarveyLike_v4", "model_RGB_asympt_aj_CteWidth_HarveyLike_v4")
+    cases["rgb_variant_amplitudes_frequency"] = rgb.rstrip("\n") + "\n fit_squareAmplitude_instead_Height bool 1\n Frequency GUG -1 -1 -1 0.05 0.07\n"
     out = {"resol": RESOL, "generator": "tests/golden/make_golden_ms_global_init.py", "cases": {}}
     for name, text in cases.items():
         with tempfile.NamedTemporaryFile("w", suffix=".model", delete=False) as f:
             f.write(text)
         sys.stdout.flush()
-        r = ref_build(lib, f.name, RESOL)
+        kind = "asymptotic" if name.startswith("rgb_") else "ms_global"
+        r = ref_build(lib, f.name, RESOL, "refio_build_init_" + kind)
         os.unlink(f.name)
-        out["cases"][name] = {"model_text": text, "reference": r}
+        out["cases"][name] = {"kind": kind, "model_text": text, "reference": r}
         print("%-36s %-52s N = %d" % (name, r["model_fullname"], len(r["inputs"])), file=sys.stderr)
     with open(os.path.join(HERE, "reference_ms_global_init.json"), "w") as f:
         json.dump(out, f)
+    # the spectrum the reference's OWN model function (model_RGB_asympt_aj_AppWidth_HarveyLike_v4, models.cpp:4684-5079) returns for
+    # the vector its OWN build_init_asymptotic makes of the fixture's .model file, on the frequency axis of reference_rgb_vectors.npz
+    # (the fixture's 80-128 microHz slice): the GPU test goes .model text -> model_setup -> host expander -> GPU and lands on it
+    os.environ["OMP_NUM_THREADS"] = "1"
+    sys.path.insert(0, os.path.dirname(HERE))
+    import _refshim
+    R = _refshim.get()
+    x = np.load(os.path.join(HERE, "reference_rgb_vectors.npz"))["x"]
+    step = float(x[2] - x[1])
+    with tempfile.NamedTemporaryFile("w", suffix=".model", delete=False) as f:
+        f.write(cases["rgb_shipped_10722175"])
+    r = ref_build(lib, f.name, step, "refio_build_init_asymptotic")
+    os.unlink(f.name)
+    rc, M = R.call_model(25, np.array(r["inputs"]), np.array(r["plength"], dtype=np.int32), x)
+    assert rc == 0 and np.all(np.isfinite(M))
+    np.savez_compressed(os.path.join(HERE, "reference_rgb_model_from_model_file.npz"), model=M, resol=step, params=np.array(r["inputs"]))
+    print("rgb model from the .model file: range %.4g..%.4g" % (M.min(), M.max()), file=sys.stderr)
 
 
 if __name__ == "__main__":
