@@ -456,3 +456,140 @@ def read_tabulated_prior(path):
     if body.shape[1] != x.size + 1:
         raise ValueError("2-D table: every row must hold the y value and one PDF value per x")
     return {"labels": labels, "units": units, "ndim": 2, "x": x, "y": body[:, 0].copy(), "pdf": body[:, 1:].copy()}
+
+
+# ------------------------------------------------------------------------------------------------
+# The other binary outputs of a run: statistical criteria, parallel-tempering log, proposal law, models
+# (Outputs::write_bin_stat_criteria outputs.cpp:1472-1550, write_bin_parallel_temp_params :1336-1404,
+#  write_bin_prop_params :1029-1229, write_bin_models :1406-1470).  Every file is a headerless stream of native little-endian
+# values beside an ASCII `.hdr`; the stems are <dir><root><suffix> with the suffixes of the control file
+# (config_default.cfg: _stat_criteria, _parallel_tempering, _proposals, _models).
+# ------------------------------------------------------------------------------------------------
+def stat_criteria_header_text(Nchains, Nsamples_done):
+    labels = "".join("%s[%d]   " % (lab, i) for lab in ("logLikelihood", "logPrior", "logPosteriors") for i in range(Nchains))
+    return ("# This is the header of the BINARY output file for the statistical information.\n"
+            "# This file contains values for the logLikelihood (columns 0:Nchains-1), logPrior (columns Nchains:2*Nchains-1) and logPosterior (columns 2*Nchains:3*Nchains-1),  \n"
+            "! Nsamples_done=%d\n! Nchains= %d\n! labels= %s\n" % (Nsamples_done, Nchains, labels))
+
+
+def write_stat_criteria(stem, logL, logPrior, logPost, Nsamples_done=None, append=False, file_ext="bin"):
+    """logL / logPrior / logPost: [Nsamples, Nchains].  Per sample the file holds the three rows one after the other."""
+    logL, logPrior, logPost = (np.atleast_2d(np.asarray(a, dtype="<f8")) for a in (logL, logPrior, logPost))
+    assert logL.shape == logPrior.shape == logPost.shape
+    if not append:
+        with open(stem + ".hdr", "w") as f:
+            f.write(stat_criteria_header_text(logL.shape[1], logL.shape[0] if Nsamples_done is None else Nsamples_done))
+    with open(stem + "." + file_ext, "ab" if append else "wb") as f:
+        f.write(np.concatenate([logL, logPrior, logPost], axis=1).astype("<f8").tobytes())
+
+
+def read_stat_criteria(stem, file_ext="bin"):
+    """-> {'Nchains', 'Nsamples_done', 'logLikelihood' [N, Nchains], 'logPrior', 'logPosterior'}"""
+    hdr = {}
+    for l in open(stem + ".hdr"):
+        if l.startswith("!") and "=" in l:
+            k, v = l[1:].split("=", 1)
+            hdr[k.strip()] = v.strip()
+    nch = int(hdr["Nchains"])
+    a = np.fromfile(stem + "." + file_ext, dtype="<f8").reshape(-1, 3 * nch)
+    return {"Nchains": nch, "Nsamples_done": int(hdr["Nsamples_done"]), "logLikelihood": a[:, :nch].copy(), "logPrior": a[:, nch:2 * nch].copy(),
+            "logPosterior": a[:, 2 * nch:].copy()}
+
+
+# one record per sample: attempt_mixing (bool, 1 byte), chain0 (int32), Pswitch (double), switched (bool): 14 bytes, unpadded
+PT_RECORD = np.dtype([("attempt_mixing", "?"), ("chain0", "<i4"), ("Pswitch", "<f8"), ("switched", "?")])
+
+
+def parallel_tempering_header_text(Tcoefs, Nsamples_done):
+    return ("# This is the header of the BINARY output file for the parameters of the parallel tempering.\n"
+            "# This file contains values for \n"
+            "# Correspondance between chain0=[0:Nchains-1] and temperature Tcoefs[chain] \n"
+            "! Nsamples_done=%d\n! Tcoefs = %s\n! labels= attempt_mixing    chain0    Pswitch    switched \n" % (Nsamples_done, _eigen_row(np.asarray(Tcoefs, dtype=np.float64), False)))
+
+
+def write_parallel_tempering(stem, Tcoefs, attempt_mixing, chain0, Pswitch, switched, Nsamples_done=None, append=False, file_ext="bin"):
+    rec = np.zeros(len(chain0), dtype=PT_RECORD)
+    rec["attempt_mixing"], rec["chain0"], rec["Pswitch"], rec["switched"] = attempt_mixing, chain0, Pswitch, switched
+    if not append:
+        with open(stem + ".hdr", "w") as f:
+            f.write(parallel_tempering_header_text(Tcoefs, len(rec) if Nsamples_done is None else Nsamples_done))
+    with open(stem + "." + file_ext, "ab" if append else "wb") as f:
+        f.write(rec.tobytes())
+
+
+def read_parallel_tempering(stem, file_ext="bin"):
+    """-> (header dict with Tcoefs and Nsamples_done, structured array of PT_RECORD)"""
+    hdr = {}
+    for l in open(stem + ".hdr"):
+        if l.startswith("!") and "=" in l:
+            k, v = l[1:].split("=", 1)
+            hdr[k.strip()] = v.strip()
+    out = {"Nsamples_done": int(hdr["Nsamples_done"]), "Tcoefs": np.array([float(t) for t in hdr["Tcoefs"].split()])}
+    return out, np.fromfile(stem + "." + file_ext, dtype=PT_RECORD)
+
+
+def _proposal_header(what, Nchains, Nvars, Nsamples_done, var_names):
+    first = "# This is the header of the BINARY output file for the parameters of the proposal law. These may vary if the MALA algorithm is learning.\n"
+    if what == "sigmas":
+        return first + "# This file contains only values for sigma[0:Nchains-1]\n! Nchains= %d\n! Nsamples_done=%d\n" % (Nchains, Nsamples_done)
+    if what == "moves":
+        return (first + "# This file contains only values for Pmove[0:Nchains-1] (first) and for moved[0:Nchains-1] (second group of Nchain values)\n"
+                "! Nchains= %d\n! Nsamples_done=%d\n" % (Nchains, Nsamples_done))
+    second = {"mus": "# This file contains only values for mu[0:Nchains-1][ 0:Nvars-1]. Each matrix is in a different file, indexed by the chain number\n",
+              "covarmats": "# This file contains only values for covarmat[0:Nchains-1][ 0:Nvars-1][ 0:Nvars-1]. Each matrix is in a different file, indexed by the chain number\n"}[what]
+    return first + second + "! Nchains= %d\n! Nvars= %d\n! Nsamples_done=%d\n! variable_names=%s\n" % (Nchains, Nvars, Nsamples_done, "".join(n + "   " for n in var_names))
+
+
+def write_proposals(stem, sigmas, mus, covarmats, Pmoves, moveds, var_names, Nsamples_done=None, append=False, file_ext="bin"):
+    """The proposal law over a run (Outputs::write_bin_prop_params): sigmas [N, Nchains]; mus [N, Nchains, Nvars]; covarmats
+    [N, Nchains, Nvars, Nvars]; Pmoves [N, Nchains] doubles and moveds [N, Nchains] booleans, interleaved per sample.
+    Files: <stem>_sigmas / _moves (one each), <stem>_mus_chain-k / _covarmats_chain-k (one per chain), four `.hdr`."""
+    sigmas = np.atleast_2d(np.asarray(sigmas, dtype="<f8")); Pmoves = np.atleast_2d(np.asarray(Pmoves, dtype="<f8"))
+    mus = np.asarray(mus, dtype="<f8"); covarmats = np.asarray(covarmats, dtype="<f8"); moveds = np.atleast_2d(np.asarray(moveds, dtype=bool))
+    N, nch = sigmas.shape
+    nv = mus.shape[2]
+    assert mus.shape == (N, nch, nv) and covarmats.shape == (N, nch, nv, nv) and Pmoves.shape == (N, nch) and moveds.shape == (N, nch)
+    done = N if Nsamples_done is None else Nsamples_done
+    mode = "ab" if append else "wb"
+    if not append:
+        for what in ("sigmas", "moves", "mus", "covarmats"):
+            with open("%s_%s.hdr" % (stem, what), "w") as f:
+                f.write(_proposal_header(what, nch, nv, done, var_names))
+    with open("%s_sigmas.%s" % (stem, file_ext), mode) as f:
+        f.write(sigmas.tobytes())
+    with open("%s_moves.%s" % (stem, file_ext), mode) as f:
+        for i in range(N):
+            f.write(Pmoves[i].tobytes() + moveds[i].astype("?").tobytes())
+    for k in range(nch):
+        with open("%s_mus_chain-%d.%s" % (stem, k, file_ext), mode) as f:
+            f.write(np.ascontiguousarray(mus[:, k, :]).tobytes())
+        with open("%s_covarmats_chain-%d.%s" % (stem, k, file_ext), mode) as f:
+            f.write(np.ascontiguousarray(covarmats[:, k, :, :]).tobytes())          # row by row (ind_row outer, ind_col inner)
+
+
+def read_proposals(stem, file_ext="bin"):
+    hdr = {}
+    for l in open(stem + "_mus.hdr"):
+        if l.startswith("!") and "=" in l:
+            k, v = l[1:].split("=", 1)
+            hdr[k.strip()] = v.strip()
+    nch, nv = int(hdr["Nchains"]), int(hdr["Nvars"])
+    sig = np.fromfile("%s_sigmas.%s" % (stem, file_ext), dtype="<f8").reshape(-1, nch)
+    mv = np.fromfile("%s_moves.%s" % (stem, file_ext), dtype=np.dtype([("Pmove", "<f8", (nch,)), ("moved", "?", (nch,))]))
+    mus = np.stack([np.fromfile("%s_mus_chain-%d.%s" % (stem, k, file_ext), dtype="<f8").reshape(-1, nv) for k in range(nch)], axis=1)
+    cov = np.stack([np.fromfile("%s_covarmats_chain-%d.%s" % (stem, k, file_ext), dtype="<f8").reshape(-1, nv, nv) for k in range(nch)], axis=1)
+    return {"Nchains": nch, "Nvars": nv, "Nsamples_done": int(hdr["Nsamples_done"]), "variable_names": hdr["variable_names"].split(),
+            "sigmas": sig, "Pmoves": mv["Pmove"].copy(), "moveds": mv["moved"].copy(), "mus": mus, "covarmats": cov}
+
+
+def write_models(stem, models, append=False, file_ext="bin"):
+    """models [N, Nchains, Ndata]: one file per chain, <stem>_models_chain-k (Outputs::write_bin_models).  (The reference opens
+    the models' header with an empty file name, outputs.cpp:1419,1438: no `.hdr` is ever written for them.)"""
+    models = np.asarray(models, dtype="<f8")
+    for k in range(models.shape[1]):
+        with open("%s_models_chain-%d.%s" % (stem, k, file_ext), "ab" if append else "wb") as f:
+            f.write(np.ascontiguousarray(models[:, k, :]).tobytes())
+
+
+def read_models(stem, Nchains, Ndata, file_ext="bin"):
+    return np.stack([np.fromfile("%s_models_chain-%d.%s" % (stem, k, file_ext), dtype="<f8").reshape(-1, Ndata) for k in range(Nchains)], axis=1)

@@ -412,3 +412,56 @@ def test_tabulated_prior_matches_reference():
     assert not bad, bad[:3]
     lowest = -1.7976931348623157e308
     assert sum(1 for v in want if v == lowest) > 8 and sum(1 for v in want if np.isfinite(v) and v != lowest) > 80 and any(np.isinf(v) for v in want)
+
+
+def test_remaining_binary_outputs_round_trip(pkg, tmp_path):
+    """Statistical criteria, parallel-tempering log, proposal law and models of a run (Outputs::write_bin_stat_criteria
+    outputs.cpp:1472-1550, write_bin_parallel_temp_params :1336-1404, write_bin_prop_params :1029-1229, write_bin_models
+    :1406-1470): record sizes and orders as the reference writes them, headers with its keys, an append continues the streams."""
+    F = pkg.formats
+    rng = np.random.default_rng(8)
+    N, nch, nv, nd = 7, 3, 4, 11
+    names = ["Height_l0", "Frequency_l", "Width_l0", "Inclination"]
+    # ---- statistical criteria: per sample Nchains logL, Nchains logPrior, Nchains logPosterior ----
+    L, P = rng.normal(-1e5, 10, (N, nch)), rng.normal(-20, 1, (N, nch))
+    stem = str(tmp_path / "star_stat_criteria")
+    F.write_stat_criteria(stem, L[:4], P[:4], (L + P)[:4], Nsamples_done=4)
+    F.write_stat_criteria(stem, L[4:], P[4:], (L + P)[4:], append=True)
+    assert os.path.getsize(stem + ".bin") == N * 3 * nch * 8
+    raw = np.fromfile(stem + ".bin", dtype="<f8")
+    assert np.array_equal(raw[:nch], L[0]) and np.array_equal(raw[nch:2 * nch], P[0]) and np.array_equal(raw[3 * nch:4 * nch], L[1])
+    s = F.read_stat_criteria(stem)
+    assert s["Nchains"] == nch and s["Nsamples_done"] == 4
+    assert np.array_equal(s["logLikelihood"], L) and np.array_equal(s["logPrior"], P) and np.array_equal(s["logPosterior"], L + P)
+    hdr = open(stem + ".hdr").read().splitlines()
+    assert hdr[0] == "# This is the header of the BINARY output file for the statistical information."
+    assert hdr[4].startswith("! labels= logLikelihood[0]   logLikelihood[1]   logLikelihood[2]   logPrior[0]   ") and hdr[4].rstrip().endswith("logPosteriors[2]")
+    # ---- parallel tempering: 14-byte records bool, int32, double, bool ----
+    T = pkg.synth.tcoefs(nch, 1.7)
+    att = rng.random(N) < 0.5; c0 = rng.integers(0, nch - 1, N).astype(np.int32); ps = rng.random(N); sw = att & (rng.random(N) < 0.5)
+    stem = str(tmp_path / "star_parallel_tempering")
+    F.write_parallel_tempering(stem, T, att, c0, ps, sw)
+    assert F.PT_RECORD.itemsize == 14 and os.path.getsize(stem + ".bin") == 14 * N
+    h, rec = F.read_parallel_tempering(stem)
+    assert np.allclose(h["Tcoefs"], T, rtol=1e-5) and h["Nsamples_done"] == N          # (the header prints 6 significant digits, like Eigen)
+    assert np.array_equal(rec["attempt_mixing"], att) and np.array_equal(rec["chain0"], c0) and np.array_equal(rec["Pswitch"], ps) and np.array_equal(rec["switched"], sw)
+    b = open(stem + ".bin", "rb").read()
+    assert b[0] == int(att[0]) and np.frombuffer(b[1:5], dtype="<i4")[0] == c0[0] and np.frombuffer(b[5:13], dtype="<f8")[0] == ps[0] and b[13] == int(sw[0])
+    assert open(stem + ".hdr").read().splitlines()[-1] == "! labels= attempt_mixing    chain0    Pswitch    switched "
+    # ---- proposal law ----
+    sig = rng.random((N, nch)); mu = rng.normal(size=(N, nch, nv)); A = rng.normal(size=(N, nch, nv, nv)); cov = A @ np.swapaxes(A, 2, 3)
+    pm = rng.random((N, nch)); mvd = rng.random((N, nch)) < pm
+    stem = str(tmp_path / "star_proposals")
+    F.write_proposals(stem, sig, mu, cov, pm, mvd, names)
+    assert os.path.getsize(stem + "_moves.bin") == N * nch * 9 and os.path.getsize(stem + "_covarmats_chain-2.bin") == N * nv * nv * 8
+    r = F.read_proposals(stem)
+    assert r["variable_names"] == names and r["Nvars"] == nv and r["Nchains"] == nch
+    for k, ref in (("sigmas", sig), ("mus", mu), ("covarmats", cov), ("Pmoves", pm), ("moveds", mvd)):
+        assert np.array_equal(r[k], ref), k
+    assert np.array_equal(np.fromfile(stem + "_covarmats_chain-1.bin", dtype="<f8")[:nv], cov[0, 1, 0, :])      # row by row
+    assert "! Nvars= %d" % nv in open(stem + "_covarmats.hdr").read() and "Pmove[0:Nchains-1]" in open(stem + "_moves.hdr").read()
+    # ---- models ----
+    M = rng.random((N, nch, nd))
+    stem = str(tmp_path / "star")
+    F.write_models(stem, M[:3]); F.write_models(stem, M[3:], append=True)
+    assert np.array_equal(F.read_models(stem, nch, nd), M)
