@@ -131,6 +131,13 @@ int tamcmc_gpu_eval(tamcmc_gpu_ctx *ctx, const double *params, const unsigned ch
  * free again on return) and launches; _end waits, fills logL_out / status_out and returns what tamcmc_gpu_eval returns.
  * tamcmc_gpu_eval == _begin + _end.  One evaluation in flight per context: a second _begin before _end is TAMCMC_ERR_ARG. */
 int tamcmc_gpu_eval_begin(tamcmc_gpu_ctx *ctx, const double *params, const unsigned char *active_mask);
+
+/* The context's own staging block for parameter rows: pinned host memory, [nstars][Nchains][*stride_out] doubles, valid
+ * until tamcmc_gpu_destroy.  A caller that BUILDS its rows (the host expanders tamcmc_host_expand_rgb_v4 /
+ * tamcmc_host_expand_ajAlm, or Model_def-style code that assembles `params` per chain, model_def.cpp:466-482) writes them here
+ * and passes this pointer as `params` to tamcmc_gpu_eval / _eval_begin: the call then skips its host-side copy of the block
+ * (126 KB per step for ten 78-mode red-giant mode tables).  The block must not be rewritten between _begin and _end. */
+double *tamcmc_gpu_params_staging(tamcmc_gpu_ctx *ctx, int *stride_out);
 int tamcmc_gpu_eval_end(tamcmc_gpu_ctx *ctx, double *logL_out, int *status_out);
 
 /* Same evaluation with DEVICE-resident inputs/outputs on the caller's CUDA stream (cudaStream_t

@@ -31,7 +31,7 @@ CHAIN_WINDOW, CHAIN_NONFINITE, CHAIN_BADCFG, CHAIN_INACTIVE = 1, 2, 4, 8
 
 # every symbol include/tamcmc_gpu.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "tamcmc_gpu_create", "tamcmc_gpu_destroy", "tamcmc_gpu_eval", "tamcmc_gpu_eval_begin", "tamcmc_gpu_eval_end", "tamcmc_gpu_eval_device", "tamcmc_gpu_pt_swap_device",
+    "tamcmc_gpu_create", "tamcmc_gpu_destroy", "tamcmc_gpu_eval", "tamcmc_gpu_eval_begin", "tamcmc_gpu_params_staging", "tamcmc_gpu_eval_end", "tamcmc_gpu_eval_device", "tamcmc_gpu_pt_swap_device",
     "tamcmc_gpu_sync", "tamcmc_gpu_model", "tamcmc_gpu_windows", "tamcmc_gpu_components",
     "tamcmc_gpu_params_stride", "tamcmc_gpu_nstars", "tamcmc_gpu_nchains", "tamcmc_gpu_pairs_last",
     "tamcmc_gpu_set_profiling", "tamcmc_gpu_get_kernel_ms", "tamcmc_gpu_launch_count",
@@ -138,6 +138,8 @@ def lib():
     L.tamcmc_host_expand_rgb_v4.argtypes = [C.c_int, _dp, _ip, C.c_double, C.c_int, _dp, _ip]
     L.tamcmc_host_armm_solve_from_l0.restype = C.c_int
     L.tamcmc_host_armm_solve_from_l0.argtypes = [_dp, C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_int, _dp, _ip, _dp, _dp, _ip, _dp, _ip]
+    L.tamcmc_gpu_params_staging.restype = _dp
+    L.tamcmc_gpu_params_staging.argtypes = [vp, _ip]
     L.tamcmc_host_armm_solve_O2p.restype = C.c_int
     L.tamcmc_host_armm_solve_O2p.argtypes = [C.c_double, C.c_double, C.c_int] + [C.c_double] * 9 + [C.c_int, _dp, _ip, _dp, _dp, _ip, _dp, _ip]
     L.tamcmc_host_spline_eval.restype = C.c_int
@@ -272,6 +274,16 @@ class Context:
             _raise(rc)
         self.last_rc = rc
         return out, st
+
+    def params_staging(self):
+        """The context's pinned staging block as a numpy view [nstars, Nchains, params_stride]: rows written here and passed to
+        eval() / bind_host_buffers() skip the host-side copy of the call (tamcmc_gpu_params_staging)."""
+        st = C.c_int(0)
+        ptr = lib().tamcmc_gpu_params_staging(self.h, C.byref(st))
+        if not ptr:
+            _raise(ERR_ARG)
+        n = self.nstars * self.Nchains * st.value
+        return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(self.nstars, self.Nchains, st.value)
 
     def bind_host_buffers(self, params, logL_out, status_out=None, active=None):
         """Pre-convert caller-owned contiguous host arrays to C pointers for repeated evaluations: returns a zero-argument

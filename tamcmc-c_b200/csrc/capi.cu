@@ -607,13 +607,20 @@ int tamcmc_gpu_nstars(const tamcmc_gpu_ctx* c) { return c ? c->nstars : 0; }
 int tamcmc_gpu_nchains(const tamcmc_gpu_ctx* c) { return c ? c->Nchains : 0; }
 long tamcmc_gpu_launch_count(const tamcmc_gpu_ctx* c) { return c ? c->launches : 0; }
 
+double* tamcmc_gpu_params_staging(tamcmc_gpu_ctx* c, int* stride_out)
+{
+    if (!c) return nullptr;
+    if (stride_out) *stride_out = c->params_stride;
+    return c->h_params;
+}
+
 int tamcmc_gpu_eval_begin(tamcmc_gpu_ctx* c, const double* params, const unsigned char* active_mask)
 {
     if (!c || !params || c->pending) return TAMCMC_ERR_ARG;
     CK(cudaSetDevice(c->device));
     const int SC = c->SC();
     const size_t pbytes = sizeof(double) * (size_t)SC * c->params_stride;
-    std::memcpy(c->h_params, params, pbytes);
+    if (params != c->h_params) std::memcpy(c->h_params, params, pbytes);      // (rows built in place: tamcmc_gpu_params_staging)
     if (active_mask) std::memcpy(c->h_active, active_mask, (size_t)SC);
     if (c->zero_copy) {
         // ---- zero-copy: no DMA copies, no stream synchronisation.  The expander reads the rows over PCIe; the last CTA

@@ -232,9 +232,6 @@ __global__ void __launch_bounds__(NC, TAMCMC_TILES_MIN_CTAS) tamcmc_whittle_tile
             const double xc = tr->xc, umax = tr->umax;
             const int series_ok = tr->series_ok;
             const bool asym = cw[CTX_ASYM] != 0ull;
-            const double N0 = __longlong_as_double((long long)cw[CTX_NZ + 1]);
-            const bool gauss = (unsigned)(cw[CTX_NZ] >> 32) != 0u;
-            const NoiseRec* nz = A.noise + sc;
             const int lb0 = tile * TILE;
             const int nvalid = min(TILE, Nloc - lb0);
             const long long off = soff + lb0;
@@ -244,29 +241,34 @@ __global__ void __launch_bounds__(NC, TAMCMC_TILES_MIN_CTAS) tamcmc_whittle_tile
             const int next_sc = have_next ? (int)((qnext & 0x7fffffffu) / (unsigned)A.tiles_stride) : -1;
             const bool next_tables = have_next && !(qnext >> 31);
 
-            // this thread's bins: b(j) = 2*tid + 2*NC*(j>>1) + (j&1), read as 128-bit pairs, requested now; x is first used by the merge
-            // loops (u = x - xc waits there), y by the epilogue
-            double u[BPT], yv[BPT], N[BPT], D[BPT];
+            // this thread's bins: b(j) = 2*tid + 2*NC*(j>>1) + (j&1), read as 128-bit pairs
+            double u[BPT], N[BPT], D[BPT];
 #pragma unroll
-            for (int pj = 0; pj < BPT / 2; pj++) {
-                const double2 v = __ldg(reinterpret_cast<const double2*>(A.x + off + 2 * tid + 2 * NC * pj));
-                const double2 w = __ldg(reinterpret_cast<const double2*>(A.y + off + 2 * tid + 2 * NC * pj));
-                u[2 * pj] = v.x; u[2 * pj + 1] = v.y;
-                yv[2 * pj] = w.x; yv[2 * pj + 1] = w.y;
-            }
-#pragma unroll
-            for (int j = 0; j < BPT; j++) { N[j] = 0.0; D[j] = 1.0; }
+            for (int j = 0; j < BPT; j++) { N[j] = 0.0; D[j] = 1.0; u[j] = 0.0; }
             bool have_u = false;             // u still holds x
-
-            // warp 0, one item ahead: the records of the next item (stored into the other context slot at the end of this item) and
-            // the queue entry of the item after it -- none of these loads is waited for before this item's work is done
+            bool requested = false;          // this item's global loads are under way
             unsigned long long w_next = 0ull;
             unsigned q_after = QENT_NONE;
-            if (warp == 0) {
-                if (have_next) w_next = ctx_word(A, qnext, lane);
-                q_after = qent_ahead;
-                qent_ahead = (idx + 3u * G < ntot) ? queue_entry(A, idx + 3u * G, cum_inc, lane) : QENT_NONE;
-            }
+            // The item's global loads.  x is requested here and first used by the merge loops (u = x - xc waits there); y is only needed
+            // by the epilogue: its lines start their way into L2 and the registers are claimed there.  Warp 0, one item ahead: the
+            // records of the next item (stored into the other context slot at the end of this item) and the queue entry of the item
+            // after it -- none of these loads is waited for before this item's work is done.  All of them are issued AFTER thread 0
+            // has started the table copies of the first pass (the proxy fence in front of a bulk copy waits for the thread's
+            // outstanding loads: behind them it would cost a trip to DRAM on every tile).
+            auto request_item_loads = [&]() {
+                requested = true;
+#pragma unroll
+                for (int pj = 0; pj < BPT / 2; pj++) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(A.x + off + 2 * tid + 2 * NC * pj));
+                    u[2 * pj] = v.x; u[2 * pj + 1] = v.y;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.y + off + 2 * tid + 2 * NC * pj));
+                }
+                if (warp == 0) {
+                    if (have_next) w_next = ctx_word(A, qnext, lane);
+                    q_after = qent_ahead;
+                    qent_ahead = (idx + 3u * G < ntot) ? queue_entry(A, idx + 3u * G, cum_inc, lane) : QENT_NONE;
+                }
+            };
 
             // tile polynomial: background series; the far field is added per pass by the owner thread of each coefficient
             if (tid < NFAR * RED_LANES && (tid & (RED_LANES - 1)) == 0) {
@@ -297,6 +299,7 @@ __global__ void __launch_bounds__(NC, TAMCMC_TILES_MIN_CTAS) tamcmc_whittle_tile
                     if (tid == 0 && n_sc >= 0) issue_tables(A, sm, stg ^ 1, n_sc, n_base);
                     pf_sc = n_sc; pf_base = n_base;
                 }
+                if (!requested) request_item_loads();
                 if (stg) { mbar_wait(&sm.full[1], ph1); ph1 ^= 1u; } else { mbar_wait(&sm.full[0], ph0); ph0 ^= 1u; }
                 unit++;
 
@@ -579,11 +582,22 @@ __global__ void __launch_bounds__(NC, TAMCMC_TILES_MIN_CTAS) tamcmc_whittle_tile
             }
 
             // ---- epilogue ----
+            if (!requested) request_item_loads();
             if (!have_u) {
 #pragma unroll
                 for (int j = 0; j < BPT; j++) u[j] -= xc;
             }
             if (nmodes == 0) __syncthreads();            // (no pass ran: the tile polynomial written above becomes visible here)
+            double yv[BPT];
+#pragma unroll
+            for (int pj = 0; pj < BPT / 2; pj++) {
+                const double2 w = __ldg(reinterpret_cast<const double2*>(A.y + off + 2 * tid + 2 * NC * pj));
+                yv[2 * pj] = w.x; yv[2 * pj + 1] = w.y;
+            }
+            // what only the epilogue needs comes from the staged context here, not from registers held across the passes
+            const double N0 = __longlong_as_double((long long)cw[CTX_NZ + 1]);
+            const bool gauss = (unsigned)(cw[CTX_NZ] >> 32) != 0u;
+            const NoiseRec* nz = A.noise + sc;
             double bgv[BPT];
             if (any_far) {
                 double acc[BPT];

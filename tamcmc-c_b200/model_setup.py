@@ -13,8 +13,8 @@ Restates `build_init_MS_Global` (tamcmc/sources/io_ms_global.cpp:362-1400) with 
 feed the driver (host/mcmc_driver.hpp, host/priors.hpp).  Covered: every model name the function accepts except the two
 Appourchaux-width variants (`model_MS_Global_a1etaa3_AppWidth_HarveyLike_v1/_v2`, which no GPU model id serves).  Where the
 reference prints a message and calls exit(), this raises ValueError with the same diagnosis.  New code: the reference's blocks of
-`if (name == ...)` are table-driven here; pinned value for value on the reference's own function through
-oracle/_ref/libtamcmc_refio.so (tests/test_model_setup.py, tests/golden/reference_ms_global_init.json)."""
+`if (name == ...)` are table-driven here; pinned value for value on the reference's own function, compiled from its own sources
+(tests/test_model_setup.py, tests/golden/reference_ms_global_init.json)."""
 import math
 
 import numpy as np

@@ -503,3 +503,25 @@ def test_tiles_schedule_matches_ring_and_oracle(pkg, oracle, monkeypatch, asym, 
         a, b = res[("ring", ratio)], res[("tiles", ratio)]
         assert np.max(np.abs(a[0] - b[0]) / np.abs(a[0])) < 1e-12
         assert np.max(np.abs(a[1] - b[1]) / np.abs(a[1])) < 1e-12
+
+
+def test_rows_built_in_the_staging_block(pkg, oracle):
+    """tamcmc_gpu_params_staging: rows written into the context's own pinned block and passed back as `params` give the same
+    results as rows passed from the caller's memory (the call only skips its host-side copy)."""
+    params, pl, x = _cases.ms_case(pkg.synth, 3, seed=4, N=20000)
+    rc, M = oracle.call_model(3, params, pl, x)[:2]
+    rng = np.random.default_rng(2)
+    y = pkg.synth.chi2_2dof_spectrum(rng, M)
+    P = pkg.synth.perturb_chains(rng, params, pl, 3)
+    T = pkg.synth.tcoefs(3, 1.5)
+    with _ctx(pkg, 3, params, pl, x, y, 3, T) as ctx:
+        L0, st0 = ctx.eval(P)
+        S = ctx.params_staging()
+        assert S.shape == (1, 3, ctx.params_stride)
+        S[...] = 0.0
+        S[0, :, :P.shape[1]] = P
+        L1, st1 = ctx.eval(S)
+        assert np.array_equal(L0, L1) and np.array_equal(st0, st1)
+        S[0, 1, :P.shape[1]] = P[2]                     # rewritten in place: the next call sees it
+        L2, _ = ctx.eval(S)
+        assert L2[0, 1] * T[1] == pytest.approx(L0[0, 2] * T[2], rel=1e-12)
