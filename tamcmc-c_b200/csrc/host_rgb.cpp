@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -90,13 +91,28 @@ struct PminusG {
         const double gnu = (Dnu_d * std::atan(t)) / pi_d;
         return pnu - gnu;
     }
+    // X / pi as a function of nu (decreasing), and its inverse: the tangent has its poles where this is m + 1/2, m integer.  Between
+    // two poles g falls from +Dnu/2 to -Dnu/2, so p - g rises with a slope > 1: it changes sign at most once there, from - to +;
+    // at a pole it jumps from + to -.  (Only used to LOCATE poles to within a grid step; every sign is taken from operator().)
+    double u_of(double nu) const { return (1.0 / nu - inv_g) * 1e6 / DPl_d; }
+    double nu_of_u(double u) const { return 1.0 / (u * DPl_d / 1e6 + inv_g); }
+    bool usable() const { return DPl_d > 0 && q_d > 0 && Dnu_d > 0 && std::isfinite(inv_g) && inv_g > 0; }
 };
+
+// Does a pole of the tangent lie inside [a, b] (with a safety margin of `pad` on both sides)?
+bool pole_inside(const PminusG& F, double a, double b, double pad)
+{
+    const double lo = a - pad, hi = b + pad;
+    if (!(lo > 0)) return true;
+    const double u_hi = F.u_of(lo), u_lo = F.u_of(hi);          // u decreases with nu
+    return std::floor(u_hi - 0.5) >= std::ceil(u_lo - 0.5);
+}
 
 // lin_interpol(f(nu_local), nu_local, 0) (tamcmc/sources/interpol.cpp:13-43) with f evaluated ON DEMAND: the function reads
 // both end values, then either walks from the left until it brackets zero (an increasing crossing) or -- when f runs from + to
 // -, which is what the jump of g at a pole of the tangent looks like -- only the first and the last two values.  Same
 // comparisons and arithmetic as lin_interpol on the full vector; a fraction of the tan / atan calls.
-double interp_zero_lazy(const vec& y /*nu_local*/, const PminusG& F, vec& val, std::vector<unsigned char>& have)
+double interp_zero_lazy(const vec& y /*nu_local*/, const PminusG& F, vec& val, std::vector<unsigned char>& have, bool monotone)
 {
     const int Nx = (int)y.size();
     val.assign((size_t)Nx, 0.0); have.assign((size_t)Nx, 0);
@@ -105,6 +121,20 @@ double interp_zero_lazy(const vec& y /*nu_local*/, const PminusG& F, vec& val, s
     int i = 0;
     double a = 0, b = 0;
     if (x_int >= X(0) && x_int <= X(Nx - 1)) {
+        // The reference walks from the left to the first i with X(i) <= 0 <= X(i+1).  Where p - g is monotone on the whole local
+        // range (no pole of the tangent inside it) and no value is exactly zero, that i is the one sign change: found by bisection,
+        // with the same values in the same comparisons at the end.  Anything else (a pole in range, an exact zero): the walk.
+        if (monotone && X(0) < 0.0 && X(Nx - 1) > 0.0 && Nx >= 3) {
+            int lo = 0, hi = Nx - 1;
+            bool exact_zero = false;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) / 2;
+                const double v = X(mid);
+                if (v == 0.0) { exact_zero = true; break; }
+                if (v < 0.0) lo = mid; else hi = mid;
+            }
+            if (!exact_zero) i = std::min(lo, Nx - 2);
+        }
         while ((x_int < X(i) || x_int > X(i + 1)) && i < Nx - 2) i = i + 1;
         a = (y[(size_t)i + 1] - y[(size_t)i]) / (X(i + 1) - X(i));
         b = y[(size_t)i] - a * X(i);
@@ -120,6 +150,60 @@ ld gnu_scalar(ld nu, ld nu_g, ld Dnu_p, ld DPl, ld q)
     const ld pi = 3.141592653589793238L;
     const ld X = pi * (1. / nu - 1. / nu_g) * 1e6 / DPl;
     return Dnu_p * atanl(q * tanl(X)) / pi;
+}
+
+// TAMCMC_ARMM_EXACT_SCAN=1 (read once): evaluate p - g on every grid point like the reference does, instead of locating the sign
+// changes by bisection between the poles of the tangent (same indices, same solutions: tests/test_rgb_expander.py runs both).
+const bool g_armm_fast = [] { const char* e = std::getenv("TAMCMC_ARMM_EXACT_SCAN"); return !(e && e[0] == '1'); }();
+
+// The indices sign_change() returns for f = p - g on the grid `nu`, without evaluating f everywhere: the poles of the tangent cut
+// the band into stretches where f rises monotonically (one - to + change at most, found by bisection on the grid index); around
+// each pole the four nearest grid values are taken and compared pair by pair exactly like sign_change does (the + to - jump).
+// Returns false -- and the caller falls back to the full scan -- when anything is not as assumed: an exact zero, a value that is
+// not finite, a stretch whose ends are not ordered like a rising function, too many poles for the grid.
+bool band_sign_changes(const vec& nu, const PminusG& F, vec& f, std::vector<long>& idx)
+{
+    idx.clear();
+    const long n = (long)nu.size();
+    if (!g_armm_fast || !F.usable() || n < 8) return false;
+    const double gstep = (nu[(size_t)n - 1] - nu[0]) / (double)(n - 1);
+    if (!(gstep > 0) || !(nu[0] > 0)) return false;
+    // boundaries: the band's ends and the grid neighbours of every pole inside the band
+    const double u_hi = F.u_of(nu[0]), u_lo = F.u_of(nu[(size_t)n - 1]);
+    const double m_hi = std::floor(u_hi - 0.5), m_lo = std::ceil(u_lo - 0.5);
+    if (!(std::isfinite(m_hi) && std::isfinite(m_lo)) || m_hi - m_lo > (double)n / 6.0) return false;      // poles closer than ~6 grid steps: scan
+    std::vector<long> B;
+    B.push_back(0); B.push_back(n - 1);
+    for (double m = m_hi; m >= m_lo; m -= 1.0) {
+        const double nup = F.nu_of_u(m + 0.5);
+        const long ip = (long)std::floor((nup - nu[0]) / gstep);
+        for (long k = ip - 1; k <= ip + 2; k++) if (k >= 0 && k <= n - 1) B.push_back(k);
+    }
+    std::sort(B.begin(), B.end());
+    B.erase(std::unique(B.begin(), B.end()), B.end());
+    std::vector<unsigned char> have((size_t)n, 0);
+    bool ok = true;
+    auto X = [&](long i) { if (!have[(size_t)i]) { f[(size_t)i] = F(nu[(size_t)i]); have[(size_t)i] = 1; if (!(f[(size_t)i] != 0.0) || !std::isfinite(f[(size_t)i])) ok = false; } return f[(size_t)i]; };
+    for (size_t k = 0; k + 1 < B.size() && ok; k++) {
+        const long a = B[k], b = B[k + 1];
+        const double fa = X(a), fb = X(b);
+        if (!ok) break;
+        if (b == a + 1) {
+            // neighbours: the two tests of sign_change (solver_mm.cpp:71-106); no value is zero here, so at most one fires
+            if (fb > 0 && fa < 0) idx.push_back(a);
+            if (fb < 0 && fa > 0) idx.push_back(a);
+        } else {
+            // a stretch without a pole: rising
+            if (fa > 0 && fb < 0) { ok = false; break; }                    // not what a rising function does: scan instead
+            if (fa < 0 && fb > 0) {
+                long lo = a, hi = b;
+                while (hi - lo > 1 && ok) { const long mid = lo + (hi - lo) / 2; if (X(mid) < 0) lo = mid; else hi = mid; }
+                if (ok) idx.push_back(lo);
+            }
+        }
+    }
+    if (!ok) { idx.clear(); return false; }
+    return true;
 }
 
 // solver_mm (solver_mm.cpp:326-449): intersections of p(nu) = nu - nu_p and g(nu) for ONE (p mode, g mode) pair.
@@ -152,13 +236,16 @@ void solver_mm(ld nu_p, ld nu_g, ld Dnu_p, ld DPl, ld q, ld numin, ld numax, ld 
     std::vector<unsigned char> have;
     std::vector<long> idx;
     const PminusG F(nu_p, nu_g, Dnu_p, DPl, q);
-    for (size_t i = 0; i < nu.size(); i++) f[i] = F(nu[i]);
-    sign_change(f, idx);
+    if (!band_sign_changes(nu, F, f, idx)) {             // the reference's own scan: every grid value, then sign_change
+        for (size_t i = 0; i < nu.size(); i++) f[i] = F(nu[i]);
+        sign_change(f, idx);
+    }
     for (size_t k = 0; k < idx.size(); k++) {
         const ld range_min = nu[(size_t)idx[k]] - 2 * resol, range_max = nu[(size_t)idx[k]] + 2 * resol;
         nu_local = linspaced((long)((range_max - range_min) / (resol * factor)), (double)range_min, (double)range_max);
         if (nu_local.size() < 2) continue;
-        const ld nu_m_proposed = interp_zero_lazy(nu_local, F, f_local, have);
+        const bool monotone = g_armm_fast && F.usable() && !pole_inside(F, nu_local.front(), nu_local.back(), 4.0 * (double)(resol * factor));
+        const ld nu_m_proposed = interp_zero_lazy(nu_local, F, f_local, have, monotone);
         const ld ysol_gnu = gnu_scalar(nu_m_proposed, nu_g, Dnu_p, DPl, q);
         const ld ysol_pnu = nu_m_proposed - nu_p;
         const ld ratio = ysol_gnu / ysol_pnu;
@@ -292,6 +379,35 @@ int solve_O2p(ld Dnu_p, ld epsilon, int el, ld delta0l, ld alpha_p, ld nmax, ld 
 //     front = ((1e-6 nu^2) DPl) / (q Dnu_p):
 // `up` depends on (nu, ng) only and `down` on (nu, np) only, so the Lp + Lg cosines of a frequency are taken once instead of
 // 2 Lp Lg times -- the same arguments give the same cosines, every other operation is unchanged.
+// W frequencies at a time: the cosines of a frequency stay scalar libm calls, the Lp x Lg divisions run in SIMD lanes, one lane per
+// frequency -- every lane performs exactly the scalar sequence of IEEE operations in the scalar order (per np a sum over ng, then
+// added to the total), so the results do not depend on the vector width.  Compiled for AVX-512 / AVX2 / baseline x86-64 with
+// run-time dispatch (the library must load on any host).
+constexpr int KSI_W = 8;
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx512f", "avx2", "default")))
+#endif
+void ksi_block(size_t Lp, size_t Lg, const double* cu2 /*[Lg][W]*/, const double* nd /*[Lg][W]*/, const double* cd2 /*[Lp][W]*/,
+               const double* qD /*[Lp]*/, double* tot /*[W]*/)
+{
+    double t[KSI_W];
+    for (int w = 0; w < KSI_W; w++) t[w] = 0.0;
+    for (size_t p = 0; p < Lp; p++) {
+        double loc[KSI_W];
+        for (int w = 0; w < KSI_W; w++) loc[w] = 0.0;
+        const double qd = qD[p];
+        const double* cd = cd2 + p * KSI_W;
+        for (size_t g = 0; g < Lg; g++) {
+            const double* cu = cu2 + g * KSI_W;
+            const double* n_ = nd + g * KSI_W;
+#pragma omp simd
+            for (int w = 0; w < KSI_W; w++) loc[w] += 1.0 / (1.0 + (n_[w] / qd) * (cu[w] / cd[w]));
+        }
+        for (int w = 0; w < KSI_W; w++) t[w] += loc[w];
+    }
+    for (int w = 0; w < KSI_W; w++) tot[w] = t[w];
+}
+
 void ksi_sum(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, const vec& DPl, ld q, vec& out)
 {
     const ld pi = M_PI;
@@ -302,26 +418,26 @@ void ksi_sum(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, 
     for (size_t p = 0; p < Lp; p++) qD[p] = (double)(q * (ld)Dnu_p[p]);
     out.assign(nu.size(), 0.0);
     const long N = (long)nu.size();
+    const long NB = (N + KSI_W - 1) / KSI_W;
 #ifdef _OPENMP
 #pragma omp parallel
 #endif
     {
-        std::vector<double> cu2(Lg), cd2(Lp), nd(Lg);
+        std::vector<double> cu2(Lg * KSI_W), cd2(Lp * KSI_W), nd(Lg * KSI_W);
+        double tot[KSI_W];
 #ifdef _OPENMP
 #pragma omp for schedule(static)
 #endif
-        for (long i = 0; i < N; i++) {
-            const double v = nu[(size_t)i];
-            const double inv = 1.0 / v, sq = 1e-6 * (v * v);
-            for (size_t g = 0; g < Lg; g++) { const double c = std::cos((c_up * (inv - inv_g[g])) / DPl[g]); cu2[g] = c * c; nd[g] = sq * DPl[g]; }
-            for (size_t p = 0; p < Lp; p++) { const double c = std::cos((pi_d * (v - nu_p[p])) / Dnu_p[p]); cd2[p] = c * c; }
-            double tot = 0.0;
-            for (size_t p = 0; p < Lp; p++) {
-                double loc = 0.0;
-                for (size_t g = 0; g < Lg; g++) loc += 1.0 / (1.0 + (nd[g] / qD[p]) * (cu2[g] / cd2[p]));
-                tot += loc;
+        for (long b = 0; b < NB; b++) {
+            for (int w = 0; w < KSI_W; w++) {
+                const long i = std::min(b * KSI_W + w, N - 1);           // (the last block repeats the last frequency in its spare lanes)
+                const double v = nu[(size_t)i];
+                const double inv = 1.0 / v, sq = 1e-6 * (v * v);
+                for (size_t g = 0; g < Lg; g++) { const double c = std::cos((c_up * (inv - inv_g[g])) / DPl[g]); cu2[g * KSI_W + w] = c * c; nd[g * KSI_W + w] = sq * DPl[g]; }
+                for (size_t p = 0; p < Lp; p++) { const double c = std::cos((pi_d * (v - nu_p[p])) / Dnu_p[p]); cd2[p * KSI_W + w] = c * c; }
             }
-            out[(size_t)i] = tot;
+            ksi_block(Lp, Lg, cu2.data(), nd.data(), cd2.data(), qD.data(), tot);
+            for (int w = 0; w < KSI_W; w++) { const long i = b * KSI_W + w; if (i < N) out[(size_t)i] = tot[w]; }
         }
     }
 }

@@ -171,3 +171,35 @@ def test_gpu_from_reference_parameter_vector(pkg, oracle, model_id):
             assert np.max(np.abs(M - models[i]) / np.abs(models[i])) < 1e-10
             Lr = oracle.call_likelihood(y, models[i], 1.0, T[i])
             assert abs(L[0, i] - Lr) <= 1e-10 * abs(Lr)
+
+
+def test_bisection_between_the_tangent_poles_gives_the_scan_rows(pkg, tmp_path):
+    """The mixed-mode solver locates the sign changes of p - g by bisection between the poles of the tangent and brackets each
+    root by bisection on the local grid (host_rgb.cpp: band_sign_changes, interp_zero_lazy); TAMCMC_ARMM_EXACT_SCAN=1 evaluates
+    every grid point and walks to the bracket like the reference does.  Same rows bit for bit, on the four recorded vectors and on
+    perturbed ones (other DP1, q, alpha_g, delta01: other pole positions)."""
+    import subprocess
+    import sys
+    G = np.load(GOLD)
+    step = float(G["x"][2] - G["x"][1])
+    rng = np.random.default_rng(77)
+    cases = []
+    for i in range(int(G["ncases"])):
+        params, pl = G["params%d" % i], G["plength%d" % i]
+        cases.append((params, pl))
+        for _ in range(3):
+            p = params.copy()
+            o1 = int(pl[:2].sum()) + int(pl[2])             # l=1 block: delta01, DP1, alpha_g, q
+            p[o1] = rng.uniform(-0.05, 0.05); p[o1 + 1] *= rng.uniform(0.93, 1.07); p[o1 + 2] = rng.uniform(0.0, 0.9); p[o1 + 3] = rng.uniform(0.05, 0.4)
+            cases.append((p, pl))
+    np.savez(tmp_path / "cases.npz", **{"p%d" % k: c[0] for k, c in enumerate(cases)}, **{"l%d" % k: c[1] for k, c in enumerate(cases)}, n=len(cases), step=step)
+    script = ("import sys, numpy as np\nsys.path.insert(0, %r)\nimport __graft_entry__ as g\npkg = g.load_package()\n"
+              "C = np.load(%r)\nout = {}\n"
+              "for k in range(int(C['n'])):\n    row, nm = pkg.expand_rgb_v4(25, C['p%%d' %% k], C['l%%d' %% k], float(C['step']), 120)\n    out['r%%d' %% k] = row\n"
+              "np.savez(%r, **out)\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "cases.npz"), str(tmp_path / "exact.npz"))
+    env = dict(os.environ, TAMCMC_ARMM_EXACT_SCAN="1")
+    subprocess.run([sys.executable, "-c", script], check=True, env=env)
+    E = np.load(tmp_path / "exact.npz")
+    for k, (p, pl) in enumerate(cases):
+        row, nm = pkg.expand_rgb_v4(25, p, pl, step, 120)
+        assert np.array_equal(row, E["r%d" % k]), k
