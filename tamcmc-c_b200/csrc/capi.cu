@@ -151,6 +151,7 @@ struct tamcmc_gpu_ctx {
     int look = 3, look_end = 3;       // producer look-ahead in tiles (TAMCMC_GPU_LOOK / TAMCMC_GPU_LOOK_END = 1 .. producers - 1; tuning aid)
     double far_ratio = TAMCMC_FAR_RATIO_DEFAULT;   // far-field folding (TAMCMC_GPU_FAR_RATIO; 0 = off)
     bool use_graphs = true;
+    int uniform_model = -1;          // model id shared by all stars (-1: mixed): the expander has builds specialised for 3, 23 and the mode table
     bool use_tiles = false;          // TAMCMC_GPU_KERNEL=tiles: the all-warps-on-one-tile schedule of whittle_tiles.cu instead of the
                                      // producer / consumer ring of whittle.cu (same results; measured slower, profiles/r2/NOTES.md)
     unsigned int nitems_max = 0;     // work items a launch can have: sum over the stars of ntiles x Nchains
@@ -196,6 +197,7 @@ ExpandArgs make_expand_args(tamcmc_gpu_ctx* c, const double* d_params, const uns
     a.far_ratio = c->far_ratio;
     a.bgqueue = c->use_tiles ? nullptr : c->d_bgqueue;
     a.mark_bgonly = c->use_tiles ? 1 : 0;
+    a.uniform_model = c->uniform_model;
     return a;
 }
 
@@ -455,6 +457,9 @@ int tamcmc_gpu_create(int device, int nstars, const tamcmc_gpu_star* stars, int 
         if (sd.Nloc > maxN) maxN = sd.Nloc;
     }
     c->total_tiles = tiles;
+    c->uniform_model = c->h_stars.empty() ? -1 : c->h_stars[0].model_id;
+    for (const StarDesc& sd : c->h_stars) if (sd.model_id != c->uniform_model) c->uniform_model = -1;
+    if (const char* e = std::getenv("TAMCMC_GPU_GENERIC_EXPANDER")) if (e[0] == '1') c->uniform_model = -1;
     c->nitems_max = (unsigned int)((size_t)tiles * (size_t)Nchains);
     if ((size_t)nstars * (size_t)Nchains * (size_t)c->tiles_stride >= 0x80000000ull) c->use_tiles = false;      // bit 31 of a queue entry is a flag there
     if (c->modes_stride < 1) c->modes_stride = 1;       // envelope models only: keep the mode tables non-empty

@@ -501,6 +501,10 @@ __device__ __noinline__ bool harvey_series(double H, double lnsc, double pw, dou
 // expand kernel: grid = nstars*Nchains CTAs, 128 threads.
 // dynamic shared memory: params row [params_stride] doubles, then per-tile cost ints [max_tiles + 1]
 // -------------------------------------------------------------------------------------------
+// MODEL: the model id every star of the launch shares (the common ones are compiled on their own: the unpacking of the other
+// families, a third of the kernel's code, drops out of the instruction stream of a launch that is bound by cold instruction
+// fetches), or -1: read it from the star descriptor.
+template <int MODEL>
 __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArgs A)
 {
     extern __shared__ double sp[];             // this chain's parameter row, staged once
@@ -528,13 +532,14 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
         __shared__ int s_dummy;
         if (A.active && !A.active[sc]) return;
         const int* pl = sd.plength;
-        const int o_noise = (sd.model_id == TAMCMC_MODEL_ID_MODE_TABLE) ? TAMCMC_MT_HDR : pl[0] + pl[1] + pl[2] + pl[3] + pl[4] + pl[5] + pl[6] + pl[7];
+        const int bmodel = (MODEL == -1) ? sd.model_id : MODEL;
+        const int o_noise = (bmodel == TAMCMC_MODEL_ID_MODE_TABLE) ? TAMCMC_MT_HDR : pl[0] + pl[1] + pl[2] + pl[3] + pl[4] + pl[5] + pl[6] + pl[7];
         if (threadIdx.x == 0) s_dummy = 0;
         __syncthreads();
-        const bool kallinger = sd.model_id == TAMCMC_MODEL_ID_KALLINGER_GAUSS;      // always the exact per-bin background
+        const bool kallinger = bmodel == TAMCMC_MODEL_ID_KALLINGER_GAUSS;      // always the exact per-bin background
         if (threadIdx.x < 32 && !kallinger) {
-            if (sd.model_id == TAMCMC_MODEL_ID_HARVEY_GAUSS) emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride, 7, 2, &s_dummy, threadIdx.x);
-            else emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (sd.model_id == 11 || sd.model_id == 14) ? 0 : (pl[8] - 1) / 3, &s_dummy, threadIdx.x);
+            if (bmodel == TAMCMC_MODEL_ID_HARVEY_GAUSS) emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride, 7, 2, &s_dummy, threadIdx.x);
+            else emit_noise(&s_nz, A.params + (size_t)sc * A.params_stride + o_noise, pl[8], (bmodel == 11 || bmodel == 14) ? 0 : (pl[8] - 1) / 3, &s_dummy, threadIdx.x);
         }
         __syncthreads();
         const int tile = (blockIdx.y - 1) * blockDim.x + threadIdx.x;
@@ -569,7 +574,7 @@ __global__ void __launch_bounds__(EXP_THREADS, 1) tamcmc_expand_kernel(ExpandArg
     const int Nmax = pl[0], lmax = pl[1], Nfl0 = pl[2], Nfl1 = pl[3], Nfl2 = pl[4], Nfl3 = pl[5];
     const int Nsplit = pl[6], Nwidth = pl[7], Nnoise = pl[8], Ninc = pl[9];
     const int Nf = Nfl0 + Nfl1 + Nfl2 + Nfl3;
-    const int model = sd.model_id;
+    const int model = (MODEL == -1) ? sd.model_id : MODEL;
     const bool mode_table = (model == TAMCMC_MODEL_ID_MODE_TABLE);
     const int o_split = Nmax + lmax + Nf;
     const int o_width = o_split + Nsplit;
@@ -1085,7 +1090,11 @@ cudaError_t tamcmc_launch_pt_swap(double* d_params_star, double* d_logL_star, do
 
 cudaError_t tamcmc_expand_configure()
 {
-    return cudaFuncSetAttribute(tamcmc_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(tamcmc_expand_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tamcmc_expand_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tamcmc_expand_kernel<23>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tamcmc_expand_kernel<TAMCMC_MODEL_ID_MODE_TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 }
 
 cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t st)
@@ -1096,6 +1105,11 @@ cudaError_t tamcmc_launch_expand(const ExpandArgs& a, int nblocks, cudaStream_t 
         dim3 kgrid((unsigned)nblocks, (unsigned)a.ksi_slices, 1u);
         tamcmc_ksi_kernel<<<kgrid, 256, 0, st>>>(a);
     }
-    tamcmc_expand_kernel<<<grid, EXP_THREADS, smem, st>>>(a);
+    switch (a.uniform_model) {
+    case 3: tamcmc_expand_kernel<3><<<grid, EXP_THREADS, smem, st>>>(a); break;
+    case 23: tamcmc_expand_kernel<23><<<grid, EXP_THREADS, smem, st>>>(a); break;
+    case TAMCMC_MODEL_ID_MODE_TABLE: tamcmc_expand_kernel<TAMCMC_MODEL_ID_MODE_TABLE><<<grid, EXP_THREADS, smem, st>>>(a); break;
+    default: tamcmc_expand_kernel<-1><<<grid, EXP_THREADS, smem, st>>>(a); break;
+    }
     return cudaGetLastError();
 }

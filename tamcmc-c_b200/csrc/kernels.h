@@ -31,6 +31,7 @@ struct ExpandArgs {
     double far_ratio;                // far-field folding of the fused kernel (0 = off): only used to weigh the tiles of the work queue
     unsigned int* bgqueue;           // [qcap] work items of the background-only tiles (QueueCtl.bg_count of them); nullptr: every tile goes
                                      // through the ring (chi_square likelihood, TAMCMC_GPU_BG_FAST=0)
+    int uniform_model;               // the model id all stars of the context share, or -1 (selects a model-specialised expander build)
     int mark_bgonly;                 // 1: bit 31 of a queue entry marks a tile no mode window touches (the one-CTA-per-tile kernel of
                                      // whittle_tiles.cu skips the mode lists of such a tile)
 };
