@@ -250,6 +250,33 @@ int tamcmc_host_armm_solve_O2p(double Dnu_p, double epsilon, int el, double delt
  * (models.cpp:4834-4843): type 1 = cspline, 2 = cspline_hermite; out[i] = spline(xq[i]) (linear extrapolation outside). */
 int tamcmc_host_spline_eval(const double *x, const double *y, int n, int type, const double *xq, int nq, double *out);
 
+/* ---- red-giant models: the same expander with its two heavy loops on the device, all chains of a step in one call ----
+ * Replaces: the per-chain OpenMP fan-out of generate_model (model_def.cpp:466-482, MALA.cpp:648) entering
+ * model_RGB_asympt_aj_{AppWidth,CteWidth}_HarveyLike_v4 (models.cpp:4684-4927, 4334-4556) once per chain.  The (p mode, g mode) pair loop
+ * of the mixed-mode solver (external/ARMM/solver_mm.cpp:558-573, 326-449) and the normalisation of the zeta function
+ * (external/ARMM/bump_DP.cpp:126-163) -- 99 % of the host expander's time -- run as two kernels over the chains of the step; the rest is the
+ * host code of tamcmc_host_expand_rgb_v4.  The pair loop reproduces the host solver's operations without FMA contraction, with tan / atan
+ * evaluated in double-double and rounded once: frequencies equal the host expander's except where glibc's tan / atan are not correctly
+ * rounded AND the solution sits on a rounding boundary (then 1 ulp); heights, widths and splittings agree to ~1e-15 (device cosines).
+ * params: [nchains][params_stride] vectors in the layout of models 25 / 27; rows_out: [nchains][row_stride] mode-table rows of `capacity`
+ * modes (normally the staging block of the evaluation context, tamcmc_gpu_params_staging); nmodes_out[c] (may be NULL); status_out[c] = what
+ * tamcmc_host_expand_rgb_v4 returns for that chain; path_out[c] (may be NULL): 0 = device solve, otherwise the chain was handed to the host
+ * solver of this library (flag bits of csrc/rgb_solver.cuh: an exact zero on a grid point, an unexpected shape, ...; -1: not exportable).
+ * No CUDA device: TAMCMC_ERR_CUDA from tamcmc_gpu_rgb_create. */
+typedef struct tamcmc_gpu_rgb tamcmc_gpu_rgb;
+int tamcmc_gpu_rgb_create(tamcmc_gpu_rgb **out, int device, int max_chains);
+void tamcmc_gpu_rgb_destroy(tamcmc_gpu_rgb *h);
+int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb *h, int model_id, const double *params, int params_stride, const int *plength, double step,
+                          int nchains, int capacity, double *rows_out, int row_stride, int *nmodes_out, int *status_out, int *path_out);
+/* host-clock milliseconds of the last tamcmc_gpu_rgb_expand: prepare (host), device (copies, two kernels, sync), finish (host), total */
+void tamcmc_gpu_rgb_timings(const tamcmc_gpu_rgb *h, double out[4]);
+const char *tamcmc_gpu_rgb_last_error(void);
+/* TEST HOOK, no GPU: the device solver's segment decomposition (csrc/rgb_solver.cuh) run on the host for one chain, with glibc's tan / atan
+ * (exact_trig = 0: reproduces tamcmc_host_expand_rgb_v4 bit for bit) or the double-double ones the device uses (1).  *flags_out: the flag
+ * bits that would have sent the chain to the host solver.  Never called by the product path. */
+int tamcmc_host_rgb_expand_emulated(int model_id, const double *params, const int *plength, double step, int capacity, double *row_out,
+                                    int *nmodes_out, int exact_trig, int *flags_out);
+
 /* ---- Alm from the precomputed grids (what the reference's ajAlm model actually uses) ----
  * Replaces: loadAllData + flatten_grid + init_2dgrid as run once by Config::Config (config.cpp:77-147;
  * external/Alm/Alm_cpp/Alm_interpol.cpp:11-79, bilinear_interpol.cpp:27-124): reads <grid_dir>/{gate,triangle}/A<l><m+l>.gz

@@ -166,12 +166,42 @@ def main():
                     rr = np.stack([pkg.expand_rgb_v4(25, p, pl, step_x, cap)[0] for p, pl in vecs])
                     ctx.eval(rr)
                 t_full = (time.perf_counter() - t0) * 1e3 / nrep
+                # the same step with the pair loop and the zeta normalisation on the device (tamcmc_gpu_rgb_expand), rows written
+                # straight into the context's staging block
+                Pmat = np.stack([p for p, _ in vecs])
+                stage = ctx.params_staging()[0]
+                with pkg.RgbExpander(25, vecs[0][1], step_x, cap, len(picks), device=lr) as rx:
+                    rows_d, nm_d, st_d, path_d = rx.expand(Pmat)
+                    fc_h = rows[:, 4 + nn:].reshape(len(picks), cap, 20)[:, :, 1]
+                    fc_d = rows_d[:, 4 + nn:].reshape(len(picks), cap, 20)[:, :, 1]
+                    rgb_dev = {"status_ok": bool((st_d == 0).all()), "chains_on_device": int((path_d == 0).sum()),
+                               "fc_identical_to_host_solver": int((fc_h == fc_d).sum()), "fc_total": int((fc_h != 0).sum()),
+                               "fc_max_diff_ulp": float(np.max(np.abs(fc_h - fc_d) / np.spacing(np.maximum(np.abs(fc_h), 1e-300)))),
+                               "rows_max_rel_diff": float(np.max(np.abs(rows - rows_d) / np.maximum(np.abs(rows), 1e-300)))}
+                    L_d, _ = ctx.eval(rows_d)
+                    rgb_dev["logL_max_rel_err_vs_oracle"] = float(np.max(np.abs(L_d[0] - L_ref) / np.abs(L_ref)))
+                    nrep_d = max(args.steps, 20)
+                    for _ in range(3):
+                        rx.expand(Pmat, rows_out=stage)
+                        ctx.eval(stage)
+                    acc = np.zeros(4)
+                    t0 = time.perf_counter()
+                    for _ in range(nrep_d):
+                        rx.expand(Pmat, rows_out=stage)
+                        tt = rx.timings()
+                        acc += [tt["prepare_ms"], tt["device_ms"], tt["finish_ms"], tt["total_ms"]]
+                        ctx.eval(stage)
+                    t_dev_full = (time.perf_counter() - t0) * 1e3 / nrep_d
+                    rgb_dev.update({"ms_per_step": t_dev_full, "value": len(picks) / (t_dev_full * 1e-3),
+                                    "expand_ms": {"prepare_host": acc[0] / nrep_d, "device": acc[1] / nrep_d, "finish_host": acc[2] / nrep_d,
+                                                  "total": acc[3] / nrep_d}})
             emit(name, "red-giant fixture 10722175, %d bins, %d chains, %d-%d modes/chain, model 25 from reference parameter vectors"
                  % (len(x), len(picks), int(rows[:, 0].min()), int(rows[:, 0].max())), len(picks), dev, e2e, pairs,
                  {"max_rel_err_vs_oracle": err,
                   "e2e_rows_in_staging": {"ms_per_step": timed.e2e_staged, "value": len(picks) / (timed.e2e_staged * 1e-3)},
                   "host_solve_ms_per_step": t_host, "e2e_with_host_solve": {"ms_per_step": t_full, "value": len(picks) / (t_full * 1e-3),
                                                                             "host_share": t_host / t_full, "host_threads": os.cpu_count()},
+                  "e2e_with_device_solve": rgb_dev,
                   "note": "single GPU (replicas only: SURVEY.md 8e). value / e2e: mode-table rows already resolved; e2e_with_host_solve: "
                           "tamcmc_host_expand_rgb_v4 (ARMM solver + zeta function, OpenMP) for every chain inside the timed region"})
 

@@ -39,6 +39,8 @@ ABI_SYMBOLS = [
     "tamcmc_gpu_exchange_create", "tamcmc_gpu_exchange_attach", "tamcmc_gpu_exchange_attach_ptrs", "tamcmc_gpu_exchange_buffer",
     "tamcmc_host_alm", "tamcmc_host_expand_ajAlm",
     "tamcmc_host_expand_rgb_v4", "tamcmc_host_armm_solve_from_l0", "tamcmc_host_armm_solve_O2p", "tamcmc_host_spline_eval",
+    "tamcmc_gpu_rgb_create", "tamcmc_gpu_rgb_destroy", "tamcmc_gpu_rgb_expand", "tamcmc_gpu_rgb_timings", "tamcmc_gpu_rgb_last_error",
+    "tamcmc_host_rgb_expand_emulated",
     "tamcmc_alm_grids_load", "tamcmc_alm_grids_free", "tamcmc_alm_grids_eval", "tamcmc_alm_grids_shape", "tamcmc_alm_grids_nodes",
     "tamcmc_alm_grids_make", "tamcmc_alm_grids_last_error",
 ]
@@ -136,6 +138,17 @@ def lib():
     L.tamcmc_host_expand_ajAlm.argtypes = [_dp, _ip, ALM_FN, vp, C.c_int, _dp, _ip]
     L.tamcmc_host_expand_rgb_v4.restype = C.c_int
     L.tamcmc_host_expand_rgb_v4.argtypes = [C.c_int, _dp, _ip, C.c_double, C.c_int, _dp, _ip]
+    L.tamcmc_gpu_rgb_create.restype = C.c_int
+    L.tamcmc_gpu_rgb_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+    L.tamcmc_gpu_rgb_destroy.restype = None
+    L.tamcmc_gpu_rgb_destroy.argtypes = [C.c_void_p]
+    L.tamcmc_gpu_rgb_expand.restype = C.c_int
+    L.tamcmc_gpu_rgb_expand.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, _ip, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int, _ip, _ip, _ip]
+    L.tamcmc_gpu_rgb_timings.restype = None
+    L.tamcmc_gpu_rgb_timings.argtypes = [C.c_void_p, _dp]
+    L.tamcmc_gpu_rgb_last_error.restype = C.c_char_p
+    L.tamcmc_host_rgb_expand_emulated.restype = C.c_int
+    L.tamcmc_host_rgb_expand_emulated.argtypes = [C.c_int, _dp, _ip, C.c_double, C.c_int, _dp, _ip, C.c_int, _ip]
     L.tamcmc_host_armm_solve_from_l0.restype = C.c_int
     L.tamcmc_host_armm_solve_from_l0.argtypes = [_dp, C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_int, _dp, _ip, _dp, _dp, _ip, _dp, _ip]
     L.tamcmc_gpu_params_staging.restype = _dp
@@ -470,6 +483,67 @@ def expand_rgb_v4(model_id, params, plength, step, capacity):
     if rc != OK:
         _raise(rc)
     return row, n.value
+
+
+def expand_rgb_v4_emulated(model_id, params, plength, step, capacity, exact_trig=1):
+    """TEST HOOK: the device solver's decomposition (csrc/rgb_solver.cuh) run on the host -> (row, nmodes, flags)."""
+    p = _d(params)
+    pl = np.ascontiguousarray(plength, dtype=np.int32)
+    row = np.zeros(synth.mode_table_nparams(capacity, int(pl[8])))
+    n, fl = C.c_int(0), C.c_int(0)
+    rc = lib().tamcmc_host_rgb_expand_emulated(int(model_id), p.ctypes.data_as(_dp), pl.ctypes.data_as(_ip), float(step), int(capacity),
+                                               row.ctypes.data_as(_dp), C.byref(n), int(exact_trig), C.byref(fl))
+    if rc != OK:
+        _raise(rc)
+    return row, n.value, fl.value
+
+
+class RgbExpander:
+    """tamcmc_gpu_rgb_*: the red-giant expander with the mixed-mode pair loop and the zeta normalisation on the device, all chains of a
+    step in one call.  expand(params[nchains][nparams]) -> (rows, nmodes, status, path); rows may be a caller-owned array (e.g. a view of
+    Context.params_staging()) so that the evaluation reads them in place."""
+
+    def __init__(self, model_id, plength, step, capacity, max_chains, device=0):
+        self.model_id, self.step, self.capacity, self.max_chains = int(model_id), float(step), int(capacity), int(max_chains)
+        self.pl = np.ascontiguousarray(plength, dtype=np.int32)
+        self.row_len = synth.mode_table_nparams(self.capacity, int(self.pl[8]))
+        self.h = C.c_void_p()
+        rc = lib().tamcmc_gpu_rgb_create(C.byref(self.h), int(device), self.max_chains)
+        if rc != OK:
+            raise TamcmcError(rc, (lib().tamcmc_gpu_rgb_last_error() or b"").decode())
+
+    def expand(self, params, rows_out=None):
+        P = np.ascontiguousarray(params, dtype=np.float64)
+        if P.ndim == 1:
+            P = P[None, :]
+        n = P.shape[0]
+        rows = np.zeros((n, self.row_len)) if rows_out is None else rows_out
+        assert rows.dtype == np.float64 and rows.shape[0] >= n and rows.strides[1] == 8
+        nm = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        path = np.zeros(n, dtype=np.int32)
+        rc = lib().tamcmc_gpu_rgb_expand(self.h, self.model_id, P.ctypes.data, P.strides[0] // 8, self.pl.ctypes.data_as(_ip), self.step, n,
+                                         self.capacity, rows.ctypes.data, rows.strides[0] // 8, nm.ctypes.data_as(_ip), st.ctypes.data_as(_ip),
+                                         path.ctypes.data_as(_ip))
+        if rc != OK:
+            raise TamcmcError(rc, (lib().tamcmc_gpu_rgb_last_error() or b"").decode())
+        return rows, nm, st, path
+
+    def timings(self):
+        t = np.zeros(4)
+        lib().tamcmc_gpu_rgb_timings(self.h, t.ctypes.data_as(_dp))
+        return dict(prepare_ms=t[0], device_ms=t[1], finish_ms=t[2], total_ms=t[3])
+
+    def close(self):
+        if self.h:
+            lib().tamcmc_gpu_rgb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def armm_solve_from_l0(nu_l0, el, delta0l, DPl, alpha, q, resol, freq_min, freq_max, cap=4096):

@@ -24,6 +24,7 @@
 // the reference -- so results do not depend on the thread count.
 #include "../../include/tamcmc_gpu.h"
 #include "host_math.hpp"
+#include "host_rgb.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -211,27 +212,52 @@ bool band_sign_changes(const vec& nu, const PminusG& F, vec& f, std::vector<long
 // the sign changes.  |g(nu)| = |Dnu atan(.)/pi| <= Dnu/2, so outside |nu - nu_p| <= Dnu/2 the difference has the sign of nu - nu_p
 // and cannot change sign: only the grid points of that band (plus a margin of a few points) are evaluated -- the same grid
 // values, hence the same sign-change indices and the same solutions, for less than a third of the tan / atan calls.
+// The coarse grid of one p mode and the band of it that can hold a sign change (see solver_mm below)
+struct BandGrid {
+    long n = 0, i_lo = 0, i_hi = -1;
+    double lo = 0, hi = 0, gstep = 0;
+    bool valid = false;
+    double grid(long i) const { return (i == n - 1) ? hi : lo + (double)i * gstep; }      // Eigen::VectorXd::LinSpaced(n, lo, hi)[i]
+};
+BandGrid band_of(ld nu_p, ld Dnu_p, ld numin, ld numax, ld resol)
+{
+    BandGrid B;
+    B.n = (numin >= 0) ? (long)((numax - numin) / resol) : (long)((numax) / resol);
+    B.lo = (numin >= 0) ? (double)numin : 0.0; B.hi = (double)numax;
+    if (B.n < 2) return B;
+    B.gstep = (B.hi - B.lo) / (double)(B.n - 1);
+    B.i_lo = 0; B.i_hi = B.n - 1;
+    const double half = 0.5 * std::fabs((double)Dnu_p) * (1.0 + 1e-9) + 4.0 * std::fabs(B.gstep);
+    const double a = ((double)nu_p - half - B.lo) / B.gstep, b = ((double)nu_p + half - B.lo) / B.gstep;
+    if (std::isfinite(a) && std::isfinite(b) && B.gstep > 0) {
+        B.i_lo = std::max(0L, (long)std::floor(a) - 2);
+        B.i_hi = std::min(B.n - 1, (long)std::ceil(b) + 2);
+    }
+    B.valid = !(B.i_hi < B.i_lo + 1);                                                    // else the band lies outside the grid: no sign change
+    return B;
+}
+// the local grid the reference refines a sign change at coarse frequency nu_idx on (solver_mm.cpp:402-410): long double arithmetic
+inline long local_grid(double nu_idx, ld resol, ld factor, double& range_min_d, double& range_max_d)
+{
+    const ld range_min = nu_idx - 2 * resol, range_max = nu_idx + 2 * resol;
+    range_min_d = (double)range_min; range_max_d = (double)range_max;
+    return (long)((range_max - range_min) / (resol * factor));
+}
+
+// solver_mm (solver_mm.cpp:326-449): intersections of p(nu) = nu - nu_p and g(nu) for ONE (p mode, g mode) pair.
+// The reference evaluates p - g on the whole grid [numin, numax] (3.5 large separations at the spectrum's resolution) and keeps
+// the sign changes.  |g(nu)| = |Dnu atan(.)/pi| <= Dnu/2, so outside |nu - nu_p| <= Dnu/2 the difference has the sign of nu - nu_p
+// and cannot change sign: only the grid points of that band (plus a margin of a few points) are evaluated -- the same grid
+// values, hence the same sign-change indices and the same solutions, for less than a third of the tan / atan calls.
 void solver_mm(ld nu_p, ld nu_g, ld Dnu_p, ld DPl, ld q, ld numin, ld numax, ld resol, ld factor, vec& nu_m)
 {
     nu_m.clear();
     if (!(nu_g >= numin && nu_g <= numax)) return;
-    const long n = (numin >= 0) ? (long)((numax - numin) / resol) : (long)((numax) / resol);
-    const double lo = (numin >= 0) ? (double)numin : 0.0, hi = (double)numax;
-    if (n < 2) return;
-    const double gstep = (hi - lo) / (double)(n - 1);
-    auto grid = [&](long i) { return (i == n - 1) ? hi : lo + (double)i * gstep; };      // Eigen::VectorXd::LinSpaced(n, lo, hi)[i]
-    long i_lo = 0, i_hi = n - 1;
-    {
-        const double half = 0.5 * std::fabs((double)Dnu_p) * (1.0 + 1e-9) + 4.0 * std::fabs(gstep);
-        const double a = ((double)nu_p - half - lo) / gstep, b = ((double)nu_p + half - lo) / gstep;
-        if (std::isfinite(a) && std::isfinite(b) && gstep > 0) {
-            i_lo = std::max(0L, (long)std::floor(a) - 2);
-            i_hi = std::min(n - 1, (long)std::ceil(b) + 2);
-        }
-        if (i_hi < i_lo + 1) return;                                                     // the band lies outside the grid: no sign change
-    }
+    const BandGrid G = band_of(nu_p, Dnu_p, numin, numax, resol);
+    if (!G.valid) return;
+    const long i_lo = G.i_lo, i_hi = G.i_hi;
     vec nu((size_t)(i_hi - i_lo + 1));
-    for (long i = i_lo; i <= i_hi; i++) nu[(size_t)(i - i_lo)] = grid(i);
+    for (long i = i_lo; i <= i_hi; i++) nu[(size_t)(i - i_lo)] = G.grid(i);
     vec f(nu.size()), nu_local, f_local;
     std::vector<unsigned char> have;
     std::vector<long> idx;
@@ -241,8 +267,9 @@ void solver_mm(ld nu_p, ld nu_g, ld Dnu_p, ld DPl, ld q, ld numin, ld numax, ld 
         sign_change(f, idx);
     }
     for (size_t k = 0; k < idx.size(); k++) {
-        const ld range_min = nu[(size_t)idx[k]] - 2 * resol, range_max = nu[(size_t)idx[k]] + 2 * resol;
-        nu_local = linspaced((long)((range_max - range_min) / (resol * factor)), (double)range_min, (double)range_max);
+        double rmin, rmax;
+        const long nloc = local_grid(nu[(size_t)idx[k]], resol, factor, rmin, rmax);
+        nu_local = linspaced(nloc, rmin, rmax);
         if (nu_local.size() < 2) continue;
         const bool monotone = g_armm_fast && F.usable() && !pole_inside(F, nu_local.front(), nu_local.back(), 4.0 * (double)(resol * factor));
         const ld nu_m_proposed = interp_zero_lazy(nu_local, F, f_local, have, monotone);
@@ -268,6 +295,22 @@ vec first_derivative(const vec& y)
     return d;
 }
 
+// keep what is inside [keep_min, keep_max], sort, std::unique with tolerance (solver_mm.cpp:575-590, 722-740)
+void sort_unique(vec& all, ld resol, ld keep_min, ld keep_max, vec& nu_m_all)
+{
+    vec kept;
+    for (double s : all)
+        if ((ld)s >= keep_min && (ld)s <= keep_max) kept.push_back(s);
+    std::sort(kept.begin(), kept.end());
+    const double tol = (double)(2 * resol);
+    nu_m_all.clear();
+    for (double s : kept)                                           // std::unique: compare with the last element KEPT
+        if (nu_m_all.empty() || !(std::abs(nu_m_all.back() - s) <= tol)) nu_m_all.push_back(s);
+}
+
+// the arguments of solve_pairs, kept when the pair loop is to run somewhere else (the device solver, rgb_device.cu)
+struct PairSetup { vec dnu_local; std::vector<ld> lo, hi; ld DPl = 0, q = 0, resol = 0; double fact = 0; ld keep_min = 0, keep_max = 0; bool set = false; };
+
 // the pair loop shared by the two entry points + sort + std::unique with tolerance (solver_mm.cpp:558-590, 706-740)
 // dnu_local[np]: the local large separation handed to solver_mm; centre +- zone[np] is the search range
 void solve_pairs(const vec& nu_p_all, const vec& nu_g_all, const vec& dnu_local, const std::vector<ld>& lo, const std::vector<ld>& hi, ld DPl, ld q,
@@ -284,13 +327,8 @@ void solve_pairs(const vec& nu_p_all, const vec& nu_g_all, const vec& dnu_local,
                       found[(size_t)(np * Ng + ng)]);
     vec all;
     for (const vec& v : found)
-        for (double s : v)
-            if ((ld)s >= keep_min && (ld)s <= keep_max) all.push_back(s);
-    std::sort(all.begin(), all.end());
-    const double tol = (double)(2 * resol);
-    nu_m_all.clear();
-    for (double s : all)                                            // std::unique: compare with the last element KEPT
-        if (nu_m_all.empty() || !(std::abs(nu_m_all.back() - s) <= tol)) nu_m_all.push_back(s);
+        for (double s : v) all.push_back(s);
+    sort_unique(all, resol, keep_min, keep_max, nu_m_all);
 }
 
 // ng range and search parameters common to both entry points (solver_mm.cpp:497-533, 649-683)
@@ -307,7 +345,7 @@ bool g_mode_setup(ld fmin, ld fmax, ld DPl, ld alpha, int& ng_min, int& ng_max, 
 }
 
 // solve_mm_asymptotic_O2from_l0 (solver_mm.cpp:624-746), sigma_p = 0
-void solve_from_l0(const vec& nu_l0_in, int el, ld delta0l, ld DPl, ld alpha, ld q, ld resol, ld freq_min, ld freq_max, Eigensols& S)
+void solve_from_l0(const vec& nu_l0_in, int el, ld delta0l, ld DPl, ld alpha, ld q, ld resol, ld freq_min, ld freq_max, Eigensols& S, PairSetup* defer = nullptr)
 {
     S = Eigensols();
     const size_t n0 = nu_l0_in.size();
@@ -336,12 +374,13 @@ void solve_from_l0(const vec& nu_l0_in, int el, ld delta0l, ld DPl, ld alpha, ld
     S.dPg.assign(S.nu_g.size(), (double)DPl);
     std::vector<ld> lo(S.nu_p.size()), hi(S.nu_p.size());
     for (size_t np = 0; np < S.nu_p.size(); np++) { lo[np] = S.nu_p[np] - Coeff * Dnu_p; hi[np] = S.nu_p[np] + Coeff * Dnu_p; }     // double arithmetic
+    if (defer) { *defer = PairSetup{S.dnup, lo, hi, DPl, q, resol, fact, freq_min, freq_max, true}; S.ok = true; return; }
     solve_pairs(S.nu_p, S.nu_g, S.dnup, lo, hi, DPl, q, resol, fact, freq_min, freq_max, S.nu_m);
     S.ok = true;
 }
 
 // solve_mm_asymptotic_O2p (solver_mm.cpp:470-604), sigma_p = 0
-int solve_O2p(ld Dnu_p, ld epsilon, int el, ld delta0l, ld alpha_p, ld nmax, ld DPl, ld alpha, ld q, ld fmin, ld fmax, ld resol, Eigensols& S)
+int solve_O2p(ld Dnu_p, ld epsilon, int el, ld delta0l, ld alpha_p, ld nmax, ld DPl, ld alpha, ld q, ld fmin, ld fmax, ld resol, Eigensols& S, PairSetup* defer = nullptr)
 {
     S = Eigensols();
     int np_min = (int)floorl(fmin / Dnu_p - epsilon - el / 2 - delta0l);         // el / 2: integer division like the reference
@@ -367,6 +406,7 @@ int solve_O2p(ld Dnu_p, ld epsilon, int el, ld delta0l, ld alpha_p, ld nmax, ld 
         dnu_local[np] = (double)(Dnu_p * (1.0 + alpha_p * (np + np_min - nmax)));
         lo[np] = S.nu_p[np] - Coeff * Dnu_p; hi[np] = S.nu_p[np] + Coeff * Dnu_p;                           // long double arithmetic (Dnu_p is)
     }
+    if (defer) { *defer = PairSetup{dnu_local, lo, hi, DPl, q, resol, fact, fmin, fmax, true}; S.ok = true; return TAMCMC_OK; }
     solve_pairs(S.nu_p, S.nu_g, dnu_local, lo, hi, DPl, q, resol, fact, fmin, fmax, S.nu_m);
     S.ok = true;
     return TAMCMC_OK;
@@ -443,19 +483,31 @@ void ksi_sum(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, 
 }
 
 // ksi_fct2(..., "precise") = ksi_fct2_precise (bump_DP.cpp:126-177): normalised by the maximum over a 4-year-resolution grid
-bool ksi_fct2_precise(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, const vec& DPl, ld q, vec& ksi_pg)
+// the high-resolution grid of ksi_fct2_precise (bump_DP.cpp:126-135): [fmin, fmax] over the p and g modes at 4-year resolution
+bool ksi_highres_grid(const vec& nu_p, const vec& nu_g, double& fmin_d, double& fmax_d, int& Ndata)
 {
     if (nu_p.empty() || nu_g.empty()) return false;
     const ld resol = 1e6 / (4 * 365. * 86400.);
     const ld fmin = (vmin(nu_p) >= vmin(nu_g)) ? vmin(nu_g) : vmin(nu_p);
     const ld fmax = (vmax(nu_p) >= vmax(nu_g)) ? vmax(nu_p) : vmax(nu_g);
-    const int Ndata = (int)((fmax - fmin) / resol);
-    if (Ndata < 1) return false;
-    const vec nu_highres = linspaced(Ndata, (double)fmin, (double)fmax);
-    vec ksi_highres;
+    Ndata = (int)((fmax - fmin) / resol);
+    fmin_d = (double)fmin; fmax_d = (double)fmax;
+    return Ndata >= 1;
+}
+
+// norm_in >= 0: the maximum over the high-resolution grid computed elsewhere (the device, rgb_device.cu)
+bool ksi_fct2_precise(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, const vec& DPl, ld q, vec& ksi_pg, double norm_in = -1.0)
+{
+    double fmin, fmax; int Ndata;
+    if (!ksi_highres_grid(nu_p, nu_g, fmin, fmax, Ndata)) return false;
     ksi_sum(nu, nu_p, nu_g, Dnu_p, DPl, q, ksi_pg);
-    ksi_sum(nu_highres, nu_p, nu_g, Dnu_p, DPl, q, ksi_highres);
-    const ld norm_coef = vmax(ksi_highres);
+    ld norm_coef = norm_in;
+    if (!(norm_in >= 0)) {
+        const vec nu_highres = linspaced(Ndata, fmin, fmax);
+        vec ksi_highres;
+        ksi_sum(nu_highres, nu_p, nu_g, Dnu_p, DPl, q, ksi_highres);
+        norm_coef = vmax(ksi_highres);
+    }
     for (double& v : ksi_pg) { v = v / (double)norm_coef; if (v > 1) v = 1; }
     return true;
 }
@@ -563,6 +615,234 @@ inline double app_width(double f, const double g[6])
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------- prepare / solve / finish
+// tamcmc_host_expand_rgb_v4 in three stages, so that the pair loop and the zeta normalisation -- 99 % of its time -- can run on the
+// device (rgb_device.cu: tamcmc_gpu_rgb_expand) between the first and the last: everything below is the host code of both paths.
+namespace tamcmc_rgb {
+
+struct Prep {
+    bool app = false;
+    int Nmax = 0, lmax = 0, Nfl0 = 0, Nfl1 = 0, Nfl2 = 0, Nfl3 = 0, Nsplit = 0, Nwidth = 0, Nnoise = 0, Nf = 0;
+    const double* params = nullptr;
+    double trunc_c = 0, inclination = 0, Vl1 = 0, Vl2 = 0, Vl3 = 0, gp[6] = {0, 0, 0, 0, 0, 0};
+    bool do_amp = false;
+    double bias_type = 0, q_star = 0, Wfactor = 0, Hfactor = 0, rot_env = 0, rot_core = 0;
+    double a2_env = 0, a3_env = 0, a4_env = 0, a5_env = 0, a6_env = 0, eta_switch = 0, asym = 0, fmin = 0, fmax = 0;
+    vec fl0_all, Wl0_all, Hl0_all;
+    Spline bias;
+    Eigensols S;
+    PairSetup setup;               // set when the solve was deferred
+};
+
+Prep* prep_new() { return new Prep(); }
+void prep_free(Prep* p) { delete p; }
+
+// Everything of model_RGB_asympt_aj_*Width_HarveyLike_v4 up to the mixed-mode solve (models.cpp:4700-4866 / 4350-4500).  With
+// defer_solve the pair loop is NOT run: P->setup holds its arguments and P->S the p and g modes.
+int prepare(Prep* Pp, int model_id, const double* params, const int* plength, double step, bool defer_solve)
+{
+    Prep& P = *Pp;
+    if (!params || !plength) return TAMCMC_ERR_ARG;
+    if (model_id != 25 && model_id != 27) return TAMCMC_ERR_MODEL;
+    P.params = params;
+    const bool app = P.app = (model_id == 25);
+    const int Nmax = P.Nmax = plength[0], lmax = P.lmax = plength[1], Nfl0 = P.Nfl0 = plength[2], Nfl1 = P.Nfl1 = plength[3];
+    P.Nfl2 = plength[4]; P.Nfl3 = plength[5];
+    const int Nsplit = P.Nsplit = plength[6], Nwidth = P.Nwidth = plength[7], Nnoise = P.Nnoise = plength[8], Ninc = plength[9], Ncfg = plength[10];
+    const int Nf = P.Nf = Nfl0 + Nfl1 + P.Nfl2 + P.Nfl3;
+    const int o_cfg = Nmax + lmax + Nf + Nsplit + Nwidth + Nnoise + Ninc;
+    if (Nmax < 2 || Nfl0 != Nmax || lmax < 1 || lmax > 3 || Nsplit < 10 || Nnoise < 1 || Ncfg < 6 || Nwidth < (app ? 6 : 1) || Nfl1 < 8) return TAMCMC_ERR_ARG;
+    P.trunc_c = params[o_cfg];
+    P.do_amp = params[o_cfg + 1] != 0.0;
+    const double model_type = params[o_cfg + 3];
+    P.bias_type = params[o_cfg + 4];
+    const int Nferr = (int)params[o_cfg + 5];
+    if (Nferr < 0 || Nfl1 < 8 + 2 * Nferr) return TAMCMC_ERR_ARG;
+    const ld pi = M_PI;
+    const int o_w = Nmax + lmax + Nf + Nsplit;
+    if (app) for (int k = 0; k < 6; k++) P.gp[k] = std::abs(params[o_w + k]);
+    P.inclination = std::abs(params[Nmax + lmax + Nf + Nsplit + Nwidth + Nnoise]);
+    P.Vl1 = std::abs(params[Nmax]);
+    P.Vl2 = (lmax >= 2) ? std::abs(params[Nmax + 1]) : 0.0; P.Vl3 = (lmax >= 3) ? std::abs(params[Nmax + 2]) : 0.0;
+
+    // ---- l = 0: frequencies, widths, heights (models.cpp:4784-4803 / 4433-4442) ----
+    P.fl0_all.assign(params + Nmax + lmax, params + Nmax + lmax + Nfl0);
+    const vec& fl0_all = P.fl0_all;
+    P.Wl0_all.resize((size_t)Nmax); P.Hl0_all.resize((size_t)Nmax);
+    for (int n = 0; n < Nmax; n++) P.Wl0_all[(size_t)n] = app ? app_width(fl0_all[(size_t)n], P.gp) : std::abs(params[o_w]);
+    for (int n = 0; n < Nmax; n++)
+        P.Hl0_all[(size_t)n] = P.do_amp ? std::abs(params[n] * ((1.0 / P.Wl0_all[(size_t)n]) / (double)pi)) : std::abs(params[n]);
+
+    // ---- mixed modes (models.cpp:4811-4866) ----
+    const int o_l1 = Nmax + lmax + Nfl0;
+    const double delta0l = params[o_l1], DPl = std::abs(params[o_l1 + 1]), alpha_g = std::abs(params[o_l1 + 2]);
+    const double q_star = P.q_star = std::abs(params[o_l1 + 3]);
+    P.Wfactor = std::abs(params[o_l1 + 6]); P.Hfactor = std::abs(params[o_l1 + 7]);
+    const int o_s = Nmax + lmax + Nf;
+    P.rot_env = std::abs(params[o_s]); P.rot_core = std::abs(params[o_s + 1]);
+    P.a2_env = params[o_s + 2]; P.a3_env = params[o_s + 4]; P.a4_env = params[o_s + 5]; P.a5_env = params[o_s + 6]; P.a6_env = params[o_s + 7];
+    P.eta_switch = params[o_s + 8]; P.asym = params[o_s + 9];
+    vec fref_all((size_t)Nferr), ferr_all((size_t)Nferr);
+    for (int i = 0; i < Nferr; i++) { fref_all[(size_t)i] = params[o_l1 + 8 + i]; ferr_all[(size_t)i] = params[o_l1 + 8 + Nferr + i]; }
+    if (P.bias_type != 0) {
+        if (P.bias_type != 1 && P.bias_type != 2) return TAMCMC_ERR_MODEL;      // (the reference would evaluate an unset spline)
+        if (!P.bias.set_points(fref_all, ferr_all, (int)P.bias_type)) return TAMCMC_ERR_ARG;      // tk::spline asserts >= 3 strictly increasing points
+    }
+    const double fmin = P.fmin = vmin(fl0_all), fmax = P.fmax = vmax(fl0_all);
+    PairSetup* defer = defer_solve ? &P.setup : nullptr;
+    P.setup = PairSetup();
+    if (app || model_type == 0) {
+        double rfit[2];
+        linfit(linspaced(Nmax, 0.0, (double)(Nmax - 1)), fl0_all, rfit);
+        const double Dnu_p = rfit[0];
+        const int n0 = (int)std::floor(rfit[1] / Dnu_p);
+        const double epsilon_p = rfit[1] / Dnu_p - n0;
+        if (fmin - Dnu_p < 0) return TAMCMC_ERR_NONFINITE;                       // "THE ARMM WILL NOT CONVERGE": the reference exits (models.cpp:4852-4858)
+        if (model_type == 0) {
+            const int rc = solve_O2p(Dnu_p, epsilon_p, 1, delta0l, 0, 0., DPl, alpha_g, q_star, fmin - Dnu_p, fmax + Dnu_p, step, P.S, defer);
+            if (rc) return rc;
+        }
+    }
+    if (model_type != 0) solve_from_l0(fl0_all, 1, delta0l, DPl, alpha_g, q_star, step, fmin, fmax, P.S, defer);
+    if (!P.S.ok) return TAMCMC_ERR_NONFINITE;
+    return TAMCMC_OK;
+}
+
+// The rest of the model function (models.cpp:4868-5006): bias, zeta function, heights / widths / splittings of the mixed modes, the row.
+// deferred: cand / ncand are the raw solutions of a deferred pair loop (any order; filtered, sorted and made unique here).
+// norm: max of the zeta sums over the 4-year-resolution grid (bump_DP.cpp:155-163) when it was computed elsewhere, < 0 to compute it here.
+int finish(Prep* Pp, bool deferred, const double* cand, int ncand, double norm, int capacity, double* row_out, int* nmodes_out)
+{
+    Prep& P = *Pp;
+    const double* params = P.params;
+    const bool app = P.app;
+    const int Nmax = P.Nmax, lmax = P.lmax, Nfl0 = P.Nfl0, Nfl1 = P.Nfl1, Nfl2 = P.Nfl2, Nfl3 = P.Nfl3, Nsplit = P.Nsplit, Nwidth = P.Nwidth, Nnoise = P.Nnoise, Nf = P.Nf;
+    const ld pi = M_PI;
+    const vec& fl0_all = P.fl0_all; const vec& Wl0_all = P.Wl0_all; const vec& Hl0_all = P.Hl0_all;
+    Eigensols& S = P.S;
+    if (deferred) {
+        if (!P.setup.set) return TAMCMC_ERR_NONFINITE;
+        vec all;
+        if (cand && ncand > 0) all.assign(cand, cand + ncand);
+        sort_unique(all, P.setup.resol, P.setup.keep_min, P.setup.keep_max, S.nu_m);
+    }
+    if (!S.ok || S.nu_m.empty()) return TAMCMC_ERR_NONFINITE;                    // no mixed mode: the reference indexes empty vectors from here on
+    vec fl1_all = S.nu_m;
+    if (P.bias_type != 0) for (double& f : fl1_all) f = f + P.bias(f);          // models.cpp:4868-4874
+    vec ksi_pg;
+    if (!ksi_fct2_precise(fl1_all, S.nu_p, S.nu_g, S.dnup, S.dPg, P.q_star, ksi_pg, norm)) return TAMCMC_ERR_NONFINITE;
+    const size_t N1 = fl1_all.size();
+    const double Hfactor = P.Hfactor, Wfactor = P.Wfactor, rot_env = P.rot_env, rot_core = P.rot_core, fmin = P.fmin, fmax = P.fmax;
+    const double Vl1 = P.Vl1, Vl2 = P.Vl2, Vl3 = P.Vl3;
+    // h_l_rgb (bump_DP.cpp:235-253)
+    vec h1_h0((size_t)N1);
+    for (size_t i = 0; i < N1; i++) {
+        double v = std::sqrt(1.0 - (double)(ld)Hfactor * ksi_pg[i]);
+        if (v > 0 - 1e-5 && v < 0 + 1e-5) v = 1e-10;
+        h1_h0[i] = v;
+    }
+    // heights of the l=1 modes: l=0 heights interpolated with zero anchors outside the comb (models.cpp:4879-4905)
+    vec f_interp((size_t)Nmax + 4), h_interp((size_t)Nmax + 4);
+    f_interp[0] = fmin * 0.6; f_interp[1] = fmin * 0.8; f_interp[(size_t)Nmax + 2] = fmax * 1.2; f_interp[(size_t)Nmax + 3] = fmax * 1.4;
+    h_interp[0] = 0; h_interp[1] = Hl0_all[0] / 4; h_interp[(size_t)Nmax + 2] = Hl0_all[(size_t)Nmax - 1] / 4; h_interp[(size_t)Nmax + 3] = 0;
+    for (int j = 0; j < Nmax; j++) { f_interp[(size_t)j + 2] = fl0_all[(size_t)j]; h_interp[(size_t)j + 2] = Hl0_all[(size_t)j]; }
+    vec Hl1_all(N1), Wl1_all(N1), a1_l1(N1);
+    for (size_t i = 0; i < N1; i++) {
+        const double tmp = tamcmc_host::lin_interpol(f_interp.data(), h_interp.data(), Nmax + 4, fl1_all[i]);
+        const double Hl1p = (tmp < 0) ? 0.0 : std::abs(tmp);
+        Hl1_all[i] = h1_h0[i] * (Hl1p * Vl1);
+        // gamma_l_fct2 (bump_DP.cpp:203-223): long double arithmetic around the interpolated l=0 width
+        const ld width0_at_l = tamcmc_host::lin_interpol(fl0_all.data(), Wl0_all.data(), Nmax, fl1_all[i]);
+        Wl1_all[i] = (double)(width0_at_l * (1. - (ld)Wfactor * ksi_pg[i]) / std::sqrt(h1_h0[i]));
+        // dnu_rot_2zones (bump_DP.cpp:531-537), then abs (models.cpp:4909)
+        a1_l1[i] = std::abs(ksi_pg[i] * (double)((ld)rot_core / 2 - (ld)rot_env) + (double)(ld)rot_env);
+    }
+    const double eta0 = (P.eta_switch == 1) ? tamcmc_host::eta0_fct(fl0_all.data(), Nmax) : 0.0;
+
+    // ---- the row: header, noise, then one record per optimum_lorentzian_calc_aj call (models.cpp:4931-5006) ----
+    const int nmodes = Nfl0 + (int)N1 + Nfl2 + Nfl3;
+    if (nmodes_out) *nmodes_out = nmodes;
+    if (nmodes > capacity) return TAMCMC_ERR_ARG;
+    const int row_len = TAMCMC_MT_HEADER + Nnoise + TAMCMC_MT_STRIDE * capacity;
+    std::memset(row_out, 0, sizeof(double) * (size_t)row_len);
+    row_out[0] = nmodes; row_out[1] = P.inclination; row_out[2] = P.trunc_c; row_out[3] = P.asym;
+    for (int k = 0; k < Nnoise; k++) row_out[TAMCMC_MT_HEADER + k] = params[Nmax + lmax + Nf + Nsplit + Nwidth + k];
+    double* rec = row_out + TAMCMC_MT_HEADER + Nnoise;
+    int j = 0;
+    for (int n = 0; n < Nfl0; n++, j++) { double* r = rec + (size_t)TAMCMC_MT_STRIDE * j; r[0] = 0; r[1] = fl0_all[(size_t)n]; r[2] = Hl0_all[(size_t)n]; r[3] = Wl0_all[(size_t)n]; }
+    for (size_t n = 0; n < N1; n++, j++) {
+        double* r = rec + (size_t)TAMCMC_MT_STRIDE * j;
+        r[0] = 1; r[1] = fl1_all[n]; r[2] = std::abs(Hl1_all[n]); r[3] = Wl1_all[n]; r[4] = a1_l1[n]; r[10] = eta0;
+    }
+    for (int l = 2; l <= 3; l++) {
+        const int Nfl = (l == 2) ? Nfl2 : Nfl3;
+        const int off = Nmax + lmax + Nfl0 + Nfl1 + ((l == 3) ? Nfl2 : 0);
+        const double Vl = (l == 2) ? Vl2 : Vl3;
+        for (int n = 0; n < Nfl; n++, j++) {
+            double* r = rec + (size_t)TAMCMC_MT_STRIDE * j;
+            const double fl = std::abs(params[off + n]);
+            if (!app && n >= Nmax) return TAMCMC_ERR_ARG;                        // the CteWidth model reads Wl0_all[n] (models.cpp:4597, 4617)
+            const double W = app ? app_width(fl, P.gp) : Wl0_all[(size_t)n];
+            const double Hi = tamcmc_host::lin_interpol(fl0_all.data(), Hl0_all.data(), Nmax, fl);
+            const double H = P.do_amp ? (double)fabsl(Hi / (pi * W) * Vl) : std::abs(Hi * Vl);
+            r[0] = l; r[1] = fl; r[2] = H; r[3] = W; r[4] = rot_env; r[5] = P.a2_env; r[6] = P.a3_env; r[7] = P.a4_env;
+            if (l == 3) { r[8] = P.a5_env; r[9] = P.a6_env; }
+            r[10] = eta0;
+        }
+    }
+    return TAMCMC_OK;
+}
+
+// What the device solver needs for one chain (rgb_device.cu), appended to T: one Band per p mode (coarse grid, band, constants of p - g),
+// the table of local grids over the band (the reference derives them in long double: solver_mm.cpp:402-410), one Pair per (p mode, g mode)
+// whose g mode lies in the p mode's search range (solver_mm.cpp:343), and the sums of the zeta normalisation.  false: solve on the host.
+bool export_task(const Prep* Pp, int chain, DeviceTask& T)
+{
+    const Prep& P = *Pp;
+    const PairSetup& U = P.setup;
+    const Eigensols& S = P.S;
+    if (!U.set || !g_armm_fast || S.nu_p.empty() || S.nu_g.empty()) return false;
+    const PminusG probe(S.nu_p[0], S.nu_g[0], U.dnu_local[0], U.DPl, U.q);
+    if (!probe.usable()) return false;
+    double kf0, kf1; int Ndata;
+    if (!ksi_highres_grid(S.nu_p, S.nu_g, kf0, kf1, Ndata)) return false;
+    const double pad = 4.0 * (double)(U.resol * (ld)U.fact);
+    const size_t bands0 = T.bands.size();
+    for (size_t np = 0; np < S.nu_p.size(); np++) {
+        const BandGrid G = band_of(S.nu_p[np], U.dnu_local[np], U.lo[np], U.hi[np], U.resol);
+        Band B;
+        B.nu_p = (double)(ld)S.nu_p[np]; B.Dnu = (double)(ld)U.dnu_local[np];
+        B.lo = G.lo; B.hi = G.hi; B.gstep = G.gstep; B.DPl = (double)U.DPl; B.q = (double)U.q; B.pad = pad;
+        B.n = (int)G.n; B.i_lo = (int)G.i_lo; B.nband = G.valid ? (int)(G.i_hi - G.i_lo + 1) : 0; B.tab_off = (int)T.tn.size(); B.chain = chain; B.pad_ = 0;
+        if (!(U.dnu_local[np] > 0) || G.n > 2000000000L) return false;
+        if (B.nband >= 8) {
+            const size_t o = T.tn.size();
+            T.tmin.resize(o + (size_t)B.nband); T.tmax.resize(o + (size_t)B.nband); T.tn.resize(o + (size_t)B.nband);
+            for (int i = 0; i < B.nband; i++) {
+                const long nl = local_grid(G.grid(G.i_lo + i), U.resol, (ld)U.fact, T.tmin[o + (size_t)i], T.tmax[o + (size_t)i]);
+                T.tn[o + (size_t)i] = (int)std::max(-1L, std::min(nl, 1000000000L));
+            }
+        } else if (B.nband > 0) return false;                        // a band of a few points: the host's full scan
+        T.bands.push_back(B);
+        for (size_t ng = 0; ng < S.nu_g.size(); ng++) {
+            const ld nu_g = S.nu_g[ng];
+            if (!(nu_g >= U.lo[np] && nu_g <= U.hi[np]) || B.nband == 0) continue;
+            Pair Q; Q.inv_g = 1.0 / (double)nu_g; Q.band = (int)(bands0 + np); Q.pad_ = 0;
+            T.pairs.push_back(Q);
+        }
+    }
+    KsiHdr K;
+    const ld pi = M_PI;
+    K.fmin = kf0; K.fmax = kf1; K.c_up = (double)(pi * 1e6); K.pi_d = (double)pi;
+    K.Lp = (int)S.nu_p.size(); K.Lg = (int)S.nu_g.size(); K.Ndata = Ndata; K.off_p = (int)(T.kp.size() / 3); K.off_g = (int)(T.kg.size() / 2); K.chain = chain;
+    for (size_t p = 0; p < S.nu_p.size(); p++) { T.kp.push_back(S.nu_p[p]); T.kp.push_back(S.dnup[p]); T.kp.push_back((double)(U.q * (ld)S.dnup[p])); }
+    for (size_t g = 0; g < S.nu_g.size(); g++) { T.kg.push_back((double)(1. / (ld)S.nu_g[g])); T.kg.push_back(S.dPg[g]); }
+    T.ksi.push_back(K);
+    return true;
+}
+
+}  // namespace tamcmc_rgb
+
 extern "C" {
 
 // Replaces: solve_mm_asymptotic_O2from_l0 (external/ARMM/solver_mm.cpp:624-746) with sigma_p = 0, returns_pg_freqs = true.
@@ -630,126 +910,10 @@ int tamcmc_host_expand_rgb_v4(int model_id, const double* params, const int* ple
                               int* nmodes_out)
 {
     if (!params || !plength || !row_out || capacity < 1) return TAMCMC_ERR_ARG;
-    if (model_id != 25 && model_id != 27) return TAMCMC_ERR_MODEL;
-    const bool app = (model_id == 25);
-    const int Nmax = plength[0], lmax = plength[1], Nfl0 = plength[2], Nfl1 = plength[3], Nfl2 = plength[4], Nfl3 = plength[5];
-    const int Nsplit = plength[6], Nwidth = plength[7], Nnoise = plength[8], Ninc = plength[9], Ncfg = plength[10];
-    const int Nf = Nfl0 + Nfl1 + Nfl2 + Nfl3;
-    const int o_cfg = Nmax + lmax + Nf + Nsplit + Nwidth + Nnoise + Ninc;
-    if (Nmax < 2 || Nfl0 != Nmax || lmax < 1 || lmax > 3 || Nsplit < 10 || Nnoise < 1 || Ncfg < 6 || Nwidth < (app ? 6 : 1) || Nfl1 < 8) return TAMCMC_ERR_ARG;
-    const double trunc_c = params[o_cfg];
-    const bool do_amp = params[o_cfg + 1] != 0.0;
-    const double model_type = params[o_cfg + 3], bias_type = params[o_cfg + 4];
-    const int Nferr = (int)params[o_cfg + 5];
-    if (Nferr < 0 || Nfl1 < 8 + 2 * Nferr) return TAMCMC_ERR_ARG;
-    const ld pi = M_PI;
-    const int o_w = Nmax + lmax + Nf + Nsplit;
-    double gp[6] = {0, 0, 0, 0, 0, 0};
-    if (app) for (int k = 0; k < 6; k++) gp[k] = std::abs(params[o_w + k]);
-    const double inclination = std::abs(params[Nmax + lmax + Nf + Nsplit + Nwidth + Nnoise]);
-    const double Vl1 = std::abs(params[Nmax]);
-    const double Vl2 = (lmax >= 2) ? std::abs(params[Nmax + 1]) : 0.0, Vl3 = (lmax >= 3) ? std::abs(params[Nmax + 2]) : 0.0;
-
-    // ---- l = 0: frequencies, widths, heights (models.cpp:4784-4803 / 4433-4442) ----
-    const vec fl0_all(params + Nmax + lmax, params + Nmax + lmax + Nfl0);
-    vec Wl0_all((size_t)Nmax), Hl0_all((size_t)Nmax);
-    for (int n = 0; n < Nmax; n++) Wl0_all[(size_t)n] = app ? app_width(fl0_all[(size_t)n], gp) : std::abs(params[o_w]);
-    for (int n = 0; n < Nmax; n++)
-        Hl0_all[(size_t)n] = do_amp ? std::abs(params[n] * ((1.0 / Wl0_all[(size_t)n]) / (double)pi)) : std::abs(params[n]);
-
-    // ---- mixed modes (models.cpp:4811-4866) ----
-    const int o_l1 = Nmax + lmax + Nfl0;
-    const double delta0l = params[o_l1], DPl = std::abs(params[o_l1 + 1]), alpha_g = std::abs(params[o_l1 + 2]), q_star = std::abs(params[o_l1 + 3]);
-    const double Wfactor = std::abs(params[o_l1 + 6]), Hfactor = std::abs(params[o_l1 + 7]);
-    const int o_s = Nmax + lmax + Nf;
-    const double rot_env = std::abs(params[o_s]), rot_core = std::abs(params[o_s + 1]);
-    const double a2_env = params[o_s + 2], a3_env = params[o_s + 4], a4_env = params[o_s + 5], a5_env = params[o_s + 6], a6_env = params[o_s + 7];
-    const double eta_switch = params[o_s + 8], asym = params[o_s + 9];
-    vec fref_all((size_t)Nferr), ferr_all((size_t)Nferr);
-    for (int i = 0; i < Nferr; i++) { fref_all[(size_t)i] = params[o_l1 + 8 + i]; ferr_all[(size_t)i] = params[o_l1 + 8 + Nferr + i]; }
-    Spline bias;
-    if (bias_type != 0) {
-        if (bias_type != 1 && bias_type != 2) return TAMCMC_ERR_MODEL;          // (the reference would evaluate an unset spline)
-        if (!bias.set_points(fref_all, ferr_all, (int)bias_type)) return TAMCMC_ERR_ARG;      // tk::spline asserts >= 3 strictly increasing points
-    }
-    const double fmin = vmin(fl0_all), fmax = vmax(fl0_all);
-    Eigensols S;
-    if (app || model_type == 0) {
-        double rfit[2];
-        linfit(linspaced(Nmax, 0.0, (double)(Nmax - 1)), fl0_all, rfit);
-        const double Dnu_p = rfit[0];
-        const int n0 = (int)std::floor(rfit[1] / Dnu_p);
-        const double epsilon_p = rfit[1] / Dnu_p - n0;
-        if (fmin - Dnu_p < 0) return TAMCMC_ERR_NONFINITE;                       // "THE ARMM WILL NOT CONVERGE": the reference exits (models.cpp:4852-4858)
-        if (model_type == 0) {
-            const int rc = solve_O2p(Dnu_p, epsilon_p, 1, delta0l, 0, 0., DPl, alpha_g, q_star, fmin - Dnu_p, fmax + Dnu_p, step, S);
-            if (rc) return rc;
-        }
-    }
-    if (model_type != 0) solve_from_l0(fl0_all, 1, delta0l, DPl, alpha_g, q_star, step, fmin, fmax, S);
-    if (!S.ok || S.nu_m.empty()) return TAMCMC_ERR_NONFINITE;                    // no mixed mode: the reference indexes empty vectors from here on
-    vec fl1_all = S.nu_m;
-    if (bias_type != 0) for (double& f : fl1_all) f = f + bias(f);              // models.cpp:4868-4874
-    vec ksi_pg;
-    if (!ksi_fct2_precise(fl1_all, S.nu_p, S.nu_g, S.dnup, S.dPg, q_star, ksi_pg)) return TAMCMC_ERR_NONFINITE;
-    const size_t N1 = fl1_all.size();
-    // h_l_rgb (bump_DP.cpp:235-253)
-    vec h1_h0((size_t)N1);
-    for (size_t i = 0; i < N1; i++) {
-        double v = std::sqrt(1.0 - (double)(ld)Hfactor * ksi_pg[i]);
-        if (v > 0 - 1e-5 && v < 0 + 1e-5) v = 1e-10;
-        h1_h0[i] = v;
-    }
-    // heights of the l=1 modes: l=0 heights interpolated with zero anchors outside the comb (models.cpp:4879-4905)
-    vec f_interp((size_t)Nmax + 4), h_interp((size_t)Nmax + 4);
-    f_interp[0] = fmin * 0.6; f_interp[1] = fmin * 0.8; f_interp[(size_t)Nmax + 2] = fmax * 1.2; f_interp[(size_t)Nmax + 3] = fmax * 1.4;
-    h_interp[0] = 0; h_interp[1] = Hl0_all[0] / 4; h_interp[(size_t)Nmax + 2] = Hl0_all[(size_t)Nmax - 1] / 4; h_interp[(size_t)Nmax + 3] = 0;
-    for (int j = 0; j < Nmax; j++) { f_interp[(size_t)j + 2] = fl0_all[(size_t)j]; h_interp[(size_t)j + 2] = Hl0_all[(size_t)j]; }
-    vec Hl1_all(N1), Wl1_all(N1), a1_l1(N1);
-    for (size_t i = 0; i < N1; i++) {
-        const double tmp = tamcmc_host::lin_interpol(f_interp.data(), h_interp.data(), Nmax + 4, fl1_all[i]);
-        const double Hl1p = (tmp < 0) ? 0.0 : std::abs(tmp);
-        Hl1_all[i] = h1_h0[i] * (Hl1p * Vl1);
-        // gamma_l_fct2 (bump_DP.cpp:203-223): long double arithmetic around the interpolated l=0 width
-        const ld width0_at_l = tamcmc_host::lin_interpol(fl0_all.data(), Wl0_all.data(), Nmax, fl1_all[i]);
-        Wl1_all[i] = (double)(width0_at_l * (1. - (ld)Wfactor * ksi_pg[i]) / std::sqrt(h1_h0[i]));
-        // dnu_rot_2zones (bump_DP.cpp:531-537), then abs (models.cpp:4909)
-        a1_l1[i] = std::abs(ksi_pg[i] * (double)((ld)rot_core / 2 - (ld)rot_env) + (double)(ld)rot_env);
-    }
-    const double eta0 = (eta_switch == 1) ? tamcmc_host::eta0_fct(fl0_all.data(), Nmax) : 0.0;
-
-    // ---- the row: header, noise, then one record per optimum_lorentzian_calc_aj call (models.cpp:4931-5006) ----
-    const int nmodes = Nfl0 + (int)N1 + Nfl2 + Nfl3;
-    if (nmodes_out) *nmodes_out = nmodes;
-    if (nmodes > capacity) return TAMCMC_ERR_ARG;
-    const int row_len = TAMCMC_MT_HEADER + Nnoise + TAMCMC_MT_STRIDE * capacity;
-    std::memset(row_out, 0, sizeof(double) * (size_t)row_len);
-    row_out[0] = nmodes; row_out[1] = inclination; row_out[2] = trunc_c; row_out[3] = asym;
-    for (int k = 0; k < Nnoise; k++) row_out[TAMCMC_MT_HEADER + k] = params[Nmax + lmax + Nf + Nsplit + Nwidth + k];
-    double* rec = row_out + TAMCMC_MT_HEADER + Nnoise;
-    int j = 0;
-    for (int n = 0; n < Nfl0; n++, j++) { double* r = rec + (size_t)TAMCMC_MT_STRIDE * j; r[0] = 0; r[1] = fl0_all[(size_t)n]; r[2] = Hl0_all[(size_t)n]; r[3] = Wl0_all[(size_t)n]; }
-    for (size_t n = 0; n < N1; n++, j++) {
-        double* r = rec + (size_t)TAMCMC_MT_STRIDE * j;
-        r[0] = 1; r[1] = fl1_all[n]; r[2] = std::abs(Hl1_all[n]); r[3] = Wl1_all[n]; r[4] = a1_l1[n]; r[10] = eta0;
-    }
-    for (int l = 2; l <= 3; l++) {
-        const int Nfl = (l == 2) ? Nfl2 : Nfl3;
-        const int off = Nmax + lmax + Nfl0 + Nfl1 + ((l == 3) ? Nfl2 : 0);
-        const double Vl = (l == 2) ? Vl2 : Vl3;
-        for (int n = 0; n < Nfl; n++, j++) {
-            double* r = rec + (size_t)TAMCMC_MT_STRIDE * j;
-            const double fl = std::abs(params[off + n]);
-            if (!app && n >= Nmax) return TAMCMC_ERR_ARG;                        // the CteWidth model reads Wl0_all[n] (models.cpp:4597, 4617)
-            const double W = app ? app_width(fl, gp) : Wl0_all[(size_t)n];
-            const double Hi = tamcmc_host::lin_interpol(fl0_all.data(), Hl0_all.data(), Nmax, fl);
-            const double H = do_amp ? (double)fabsl(Hi / (pi * W) * Vl) : std::abs(Hi * Vl);
-            r[0] = l; r[1] = fl; r[2] = H; r[3] = W; r[4] = rot_env; r[5] = a2_env; r[6] = a3_env; r[7] = a4_env;
-            if (l == 3) { r[8] = a5_env; r[9] = a6_env; }
-            r[10] = eta0;
-        }
-    }
-    return TAMCMC_OK;
+    tamcmc_rgb::Prep P;
+    int rc = tamcmc_rgb::prepare(&P, model_id, params, plength, step, /*defer_solve=*/false);
+    if (rc) return rc;
+    return tamcmc_rgb::finish(&P, false, nullptr, 0, -1.0, capacity, row_out, nmodes_out);
 }
 
 }  // extern "C"

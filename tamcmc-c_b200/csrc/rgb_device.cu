@@ -1,0 +1,317 @@
+// rgb_device.cu -- device half of the red-giant expander (BASELINE configs C1 / C4): tamcmc_gpu_rgb_expand.
+//
+// Replaces, for ALL chains of a step in one call, the two loops that are 99 % of model_RGB_asympt_aj_*Width_HarveyLike_v4's
+// set-up (tamcmc/sources/models.cpp:4684-4927, 4334-4556) and that the reference runs per chain under OpenMP:
+//   * the (p mode, g mode) pair loop of the asymptotic mixed-mode solver (external/ARMM/solver_mm.cpp:558-573 -> solver_mm :326-449):
+//     tamcmc_rgb_pairs_kernel, one warp per pair, one lane per segment (rgb_solver.cuh);
+//   * the normalisation of the zeta function: the maximum of the zeta sums over a 4-year-resolution grid
+//     (external/ARMM/bump_DP.cpp:126-163): tamcmc_rgb_ksi_max_kernel, one thread per grid frequency.
+// The host does what is left (host_rgb.cpp: prepare -> [device] -> finish): unpacking, l=0 widths, the p / g mode lists and the long
+// double grid set-up in front; filter / sort / unique of the solutions, bias spline, zeta at the ~50 mixed modes, heights, widths,
+// splittings and the mode-table rows behind.  Rows are written where the caller says -- normally the pinned staging block of the
+// evaluation context (tamcmc_gpu_params_staging), so tamcmc_gpu_eval reads them without another copy.
+// A chain the device flags (rgb_solver.cuh: an exact zero, an unexpected shape, ...) is solved by the host code of the same library
+// (tamcmc_host_expand_rgb_v4's own path), reported in path_out.  Compiled with -fmad=false: the solver's arithmetic must not contract.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tamcmc_gpu.h"
+#include "rgb_solver.cuh"
+
+using namespace tamcmc_rgb;
+
+namespace {
+
+constexpr int KSI_PCHUNK = 8;      // p modes whose sums a thread of the zeta kernel carries in registers at a time
+
+__global__ void __launch_bounds__(128) tamcmc_rgb_pairs_kernel(const Band* __restrict__ bands, const Pair* __restrict__ pairs, int npairs,
+                                                                const double* __restrict__ tmin, const double* __restrict__ tmax,
+                                                                const int* __restrict__ tn, double* __restrict__ cand, int cand_cap,
+                                                                int* __restrict__ count, int* __restrict__ flags)
+{
+    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+    if (warp >= npairs) return;
+    const Pair Q = pairs[warp];
+    const Band B = bands[Q.band];
+    int flag = 0;
+    double m_hi = 0, nu0 = 0, bstep = 0;
+    const int nseg = pair_segments(B, Q.inv_g, m_hi, nu0, bstep, flag);
+    double* out = cand + (size_t)B.chain * (size_t)cand_cap;
+    int* cnt = count + B.chain;
+    for (int j = lane; j < nseg; j += 32)
+        pair_segment<TrigLib, TrigCR>(B, Q.inv_g, tmin + B.tab_off, tmax + B.tab_off, tn + B.tab_off, j, nseg, m_hi, nu0, bstep,
+                                      [&](double s) {
+                                          const int k = atomicAdd(cnt, 1);
+                                          if (k < cand_cap) out[k] = s; else flag |= RGB_FLAG_OVERFLOW;
+                                      },
+                                      flag);
+    if (flag) atomicOr(flags + B.chain, flag);
+}
+
+// max over the grid of the zeta sums: sum over (np, ng) of ksi_fct1 (bump_DP.cpp:46-64) in the reference's single-thread order (per np a
+// sum over ng, then added to the total) with its operations (host_rgb.cpp ksi_sum); the cosines are the device library's
+__global__ void __launch_bounds__(128) tamcmc_rgb_ksi_max_kernel(const KsiHdr* __restrict__ hdrs, const double* __restrict__ kp,
+                                                                  const double* __restrict__ kg, unsigned long long* __restrict__ norm_bits)
+{
+    extern __shared__ double sm[];
+    const KsiHdr H = hdrs[blockIdx.y];
+    if ((int)(blockIdx.x * blockDim.x) >= H.Ndata) return;
+    double* s_p = sm;                       // [Lp][3]: nu_p, Dnu_p, q Dnu_p
+    double* s_g = sm + 3 * H.Lp;            // [Lg][2]: 1 / nu_g, DPl
+    for (int k = threadIdx.x; k < 3 * H.Lp; k += blockDim.x) s_p[k] = kp[3 * (size_t)H.off_p + k];
+    for (int k = threadIdx.x; k < 2 * H.Lg; k += blockDim.x) s_g[k] = kg[2 * (size_t)H.off_g + k];
+    __syncthreads();
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    double total = 0.0;
+    if (i < H.Ndata) {
+        // Eigen::VectorXd::LinSpaced(Ndata, fmin, fmax)[i]
+        const double v = (H.Ndata == 1 || i == H.Ndata - 1) ? H.fmax : H.fmin + (double)i * ((H.fmax - H.fmin) / (double)(H.Ndata - 1));
+        const double inv = 1.0 / v, sq = 1e-6 * (v * v);
+        for (int p0 = 0; p0 < H.Lp; p0 += KSI_PCHUNK) {
+            double cd2[KSI_PCHUNK], loc[KSI_PCHUNK];
+#pragma unroll
+            for (int k = 0; k < KSI_PCHUNK; k++) {
+                loc[k] = 0.0; cd2[k] = 1.0;
+                if (p0 + k < H.Lp) { const double c = cos((H.pi_d * (v - s_p[3 * (p0 + k)])) / s_p[3 * (p0 + k) + 1]); cd2[k] = c * c; }
+            }
+            for (int g = 0; g < H.Lg; g++) {
+                const double c = cos((H.c_up * (inv - s_g[2 * g])) / s_g[2 * g + 1]);
+                const double cu2 = c * c, nd = sq * s_g[2 * g + 1];
+#pragma unroll
+                for (int k = 0; k < KSI_PCHUNK; k++)
+                    if (p0 + k < H.Lp) loc[k] += 1.0 / (1.0 + (nd / s_p[3 * (p0 + k) + 2]) * (cu2 / cd2[k]));
+            }
+#pragma unroll
+            for (int k = 0; k < KSI_PCHUNK; k++) if (p0 + k < H.Lp) total += loc[k];
+        }
+    }
+    // the maximum does not depend on the order it is taken in; a NaN anywhere must survive (its bit pattern is above every finite value's)
+    unsigned long long b = (unsigned long long)__double_as_longlong(total);
+    if (total != total) b = 0x7ff8000000000000ull;
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o); b = (t > b) ? t : b; }
+    if ((threadIdx.x & 31) == 0) atomicMax(norm_bits + H.chain, b);
+}
+
+std::string g_err;
+
+#define RGB_CUDA(x)                                                                                                   \
+    do {                                                                                                              \
+        cudaError_t e_ = (x);                                                                                         \
+        if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return TAMCMC_ERR_CUDA; }   \
+    } while (0)
+
+size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+}  // namespace
+
+struct tamcmc_gpu_rgb {
+    int device = 0, max_chains = 0, cand_cap = 0;
+    cudaStream_t stream = nullptr;
+    char* h_in = nullptr; char* d_in = nullptr; size_t in_cap = 0;
+    char* h_out = nullptr; char* d_out = nullptr; size_t out_bytes = 0;
+    std::vector<Prep*> preps;
+    DeviceTask task;
+    std::vector<int> on_device;
+    double last_ms[4] = {0, 0, 0, 0};      // prepare, device, finish, total of the last call (host clock)
+};
+
+extern "C" {
+
+const char* tamcmc_gpu_rgb_last_error(void) { return g_err.c_str(); }
+
+// Replaces: nothing the reference has as one call -- the per-chain OpenMP fan-out of generate_model (model_def.cpp:466-482) entering
+// model_RGB_asympt_aj_*Width_HarveyLike_v4 once per chain; here the set-up of all chains of a step is one batched device solve.
+int tamcmc_gpu_rgb_create(tamcmc_gpu_rgb** out, int device, int max_chains)
+{
+    if (!out || max_chains < 1) return TAMCMC_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "no usable CUDA device"; return TAMCMC_ERR_CUDA; }
+    RGB_CUDA(cudaSetDevice(device));
+    tamcmc_gpu_rgb* h = new tamcmc_gpu_rgb();
+    h->device = device; h->max_chains = max_chains; h->cand_cap = 16384;
+    h->out_bytes = align16((size_t)max_chains * 16) + (size_t)max_chains * (size_t)h->cand_cap * 8;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_out, h->out_bytes);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_out, h->out_bytes);
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); delete h; return TAMCMC_ERR_CUDA; }
+    for (int c = 0; c < max_chains; c++) h->preps.push_back(prep_new());
+    *out = h;
+    return TAMCMC_OK;
+}
+
+void tamcmc_gpu_rgb_destroy(tamcmc_gpu_rgb* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (Prep* p : h->preps) prep_free(p);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// params: [nchains][params_stride] parameter vectors in the layout of models 25 / 27 (tamcmc_host_expand_rgb_v4); rows_out:
+// [nchains][row_stride] mode-table rows of `capacity` modes (row_stride >= TAMCMC_MT_HEADER + Nnoise + TAMCMC_MT_STRIDE * capacity).
+// status_out[c]: what tamcmc_host_expand_rgb_v4 would have returned for chain c; path_out[c] (may be NULL): 0 = solved on the device,
+// otherwise the rgb_solver.cuh flag bits (or -1: not exportable) that sent the chain to the host solver.  Returns TAMCMC_ERR_CUDA /
+// TAMCMC_ERR_ARG for a failed call, else TAMCMC_OK (per-chain outcomes are in status_out).
+int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params, int params_stride, const int* plength, double step,
+                          int nchains, int capacity, double* rows_out, int row_stride, int* nmodes_out, int* status_out, int* path_out)
+{
+    if (!h || !params || !plength || !rows_out || !status_out || nchains < 1 || nchains > h->max_chains || capacity < 1) return TAMCMC_ERR_ARG;
+    if (row_stride < TAMCMC_MT_HEADER + plength[8] + TAMCMC_MT_STRIDE * capacity) return TAMCMC_ERR_ARG;
+    RGB_CUDA(cudaSetDevice(h->device));
+    timespec t0, t1, t2, t3;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    // ---- stage 1 (host, one chain per thread): everything in front of the pair loop ----
+    h->on_device.assign((size_t)nchains, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < nchains; c++) status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, true);
+    DeviceTask& T = h->task;
+    T.clear();
+    for (int c = 0; c < nchains; c++) {
+        if (path_out) path_out[c] = -1;
+        if (status_out[c] != TAMCMC_OK) continue;
+        const size_t nb = T.bands.size(), npair = T.pairs.size(), nt = T.tn.size(), nk = T.ksi.size(), nkp = T.kp.size(), nkg = T.kg.size();
+        if (export_task(h->preps[(size_t)c], c, T)) h->on_device[(size_t)c] = 1;
+        else { T.bands.resize(nb); T.pairs.resize(npair); T.tmin.resize(nt); T.tmax.resize(nt); T.tn.resize(nt); T.ksi.resize(nk); T.kp.resize(nkp); T.kg.resize(nkg); }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    // ---- stage 2 (device): pair loop + zeta normalisation of every exported chain ----
+    const size_t hdr_bytes = align16((size_t)h->max_chains * 16);
+    unsigned long long* h_norm = (unsigned long long*)h->h_out;
+    int* h_count = (int*)(h->h_out + (size_t)h->max_chains * 8);
+    int* h_flag = h_count + h->max_chains;
+    double* h_cand = (double*)(h->h_out + hdr_bytes);
+    if (!T.pairs.empty() || !T.ksi.empty()) {
+        size_t off[9];
+        off[0] = 0;
+        off[1] = off[0] + align16(T.bands.size() * sizeof(Band));
+        off[2] = off[1] + align16(T.pairs.size() * sizeof(Pair));
+        off[3] = off[2] + align16(T.tmin.size() * 8);
+        off[4] = off[3] + align16(T.tmax.size() * 8);
+        off[5] = off[4] + align16(T.tn.size() * 4);
+        off[6] = off[5] + align16(T.ksi.size() * sizeof(KsiHdr));
+        off[7] = off[6] + align16(T.kp.size() * 8);
+        off[8] = off[7] + align16(T.kg.size() * 8);
+        if (off[8] > h->in_cap) {
+            if (h->d_in) cudaFree(h->d_in);
+            if (h->h_in) cudaFreeHost(h->h_in);
+            h->d_in = nullptr; h->h_in = nullptr;
+            h->in_cap = off[8] + off[8] / 2;
+            RGB_CUDA(cudaMalloc((void**)&h->d_in, h->in_cap));
+            RGB_CUDA(cudaMallocHost((void**)&h->h_in, h->in_cap));
+        }
+        std::memcpy(h->h_in + off[0], T.bands.data(), T.bands.size() * sizeof(Band));
+        std::memcpy(h->h_in + off[1], T.pairs.data(), T.pairs.size() * sizeof(Pair));
+        std::memcpy(h->h_in + off[2], T.tmin.data(), T.tmin.size() * 8);
+        std::memcpy(h->h_in + off[3], T.tmax.data(), T.tmax.size() * 8);
+        std::memcpy(h->h_in + off[4], T.tn.data(), T.tn.size() * 4);
+        std::memcpy(h->h_in + off[5], T.ksi.data(), T.ksi.size() * sizeof(KsiHdr));
+        std::memcpy(h->h_in + off[6], T.kp.data(), T.kp.size() * 8);
+        std::memcpy(h->h_in + off[7], T.kg.data(), T.kg.size() * 8);
+        RGB_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, off[8], cudaMemcpyHostToDevice, h->stream));
+        RGB_CUDA(cudaMemsetAsync(h->d_out, 0, hdr_bytes, h->stream));
+        unsigned long long* d_norm = (unsigned long long*)h->d_out;
+        int* d_count = (int*)(h->d_out + (size_t)h->max_chains * 8);
+        int* d_flag = d_count + h->max_chains;
+        double* d_cand = (double*)(h->d_out + hdr_bytes);
+        if (!T.ksi.empty()) {
+            int maxN = 0; size_t smem = 0;
+            for (const KsiHdr& K : T.ksi) { if (K.Ndata > maxN) maxN = K.Ndata; const size_t s = (size_t)(3 * K.Lp + 2 * K.Lg) * 8; if (s > smem) smem = s; }
+            if (smem > 200 * 1024) return TAMCMC_ERR_ARG;
+            if (smem > 48 * 1024) RGB_CUDA(cudaFuncSetAttribute(tamcmc_rgb_ksi_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const dim3 grid((unsigned)((maxN + 127) / 128), (unsigned)T.ksi.size());
+            tamcmc_rgb_ksi_max_kernel<<<grid, 128, smem, h->stream>>>((const KsiHdr*)(h->d_in + off[5]), (const double*)(h->d_in + off[6]),
+                                                                      (const double*)(h->d_in + off[7]), d_norm);
+        }
+        if (!T.pairs.empty()) {
+            const int npairs = (int)T.pairs.size();
+            tamcmc_rgb_pairs_kernel<<<(unsigned)((npairs + 3) / 4), 128, 0, h->stream>>>(
+                (const Band*)(h->d_in + off[0]), (const Pair*)(h->d_in + off[1]), npairs, (const double*)(h->d_in + off[2]),
+                (const double*)(h->d_in + off[3]), (const int*)(h->d_in + off[4]), d_cand, h->cand_cap, d_count, d_flag);
+        }
+        RGB_CUDA(cudaGetLastError());
+        // counts, flags and norms first; then only as many candidates as were found
+        RGB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, hdr_bytes, cudaMemcpyDeviceToHost, h->stream));
+        RGB_CUDA(cudaStreamSynchronize(h->stream));
+        for (int c = 0; c < nchains; c++) {
+            if (!h->on_device[(size_t)c] || h_flag[c] || h_count[c] <= 0) continue;
+            const int n = h_count[c] < h->cand_cap ? h_count[c] : h->cand_cap;
+            RGB_CUDA(cudaMemcpyAsync(h_cand + (size_t)c * h->cand_cap, d_cand + (size_t)c * h->cand_cap, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+        }
+        RGB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t2);
+    // ---- stage 3 (host, one chain per thread): the rest of the model function; flagged chains are solved by the host ----
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < nchains; c++) {
+        if (status_out[c] != TAMCMC_OK) continue;
+        double* row = rows_out + (size_t)c * row_stride;
+        int nm = 0;
+        double norm;
+        std::memcpy(&norm, &h_norm[c], 8);
+        const bool dev = h->on_device[(size_t)c] && h_flag[c] == 0 && h_count[c] <= h->cand_cap && norm == norm && norm > 0.0;
+        if (dev) {
+            status_out[c] = finish(h->preps[(size_t)c], true, h_cand + (size_t)c * h->cand_cap, h_count[c], norm, capacity, row, &nm);
+            if (path_out) path_out[c] = 0;
+        } else {
+            if (path_out) path_out[c] = h->on_device[(size_t)c] ? (h_flag[c] ? h_flag[c] : RGB_FLAG_NONFINITE) : -1;
+            status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, false);
+            if (status_out[c] == TAMCMC_OK) status_out[c] = finish(h->preps[(size_t)c], false, nullptr, 0, -1.0, capacity, row, &nm);
+        }
+        if (nmodes_out) nmodes_out[c] = nm;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t3);
+    auto ms = [](const timespec& a, const timespec& b) { return 1e3 * (double)(b.tv_sec - a.tv_sec) + 1e-6 * (double)(b.tv_nsec - a.tv_nsec); };
+    h->last_ms[0] = ms(t0, t1); h->last_ms[1] = ms(t1, t2); h->last_ms[2] = ms(t2, t3); h->last_ms[3] = ms(t0, t3);
+    return TAMCMC_OK;
+}
+
+// host-clock milliseconds of the stages of the last tamcmc_gpu_rgb_expand: prepare, device (copies + kernels + sync), finish, total
+void tamcmc_gpu_rgb_timings(const tamcmc_gpu_rgb* h, double out[4])
+{
+    for (int k = 0; k < 4; k++) out[k] = h ? h->last_ms[k] : 0.0;
+}
+
+// TEST HOOK (no GPU needed): the segment decomposition of rgb_solver.cuh run on the host for ONE chain, with glibc's tan / atan
+// (exact_trig = 0: must reproduce tamcmc_host_expand_rgb_v4 bit for bit) or the correctly rounded ones of dd_math.cuh (1: what the
+// device computes).  Not a product path: tamcmc_gpu_rgb_expand never calls it.
+int tamcmc_host_rgb_expand_emulated(int model_id, const double* params, const int* plength, double step, int capacity, double* row_out,
+                                    int* nmodes_out, int exact_trig, int* flags_out)
+{
+    if (!params || !plength || !row_out || capacity < 1) return TAMCMC_ERR_ARG;
+    Prep* P = prep_new();
+    int rc = prepare(P, model_id, params, plength, step, true);
+    DeviceTask T;
+    if (rc == TAMCMC_OK && !export_task(P, 0, T)) { prep_free(P); if (flags_out) *flags_out = -1; return TAMCMC_ERR_MODEL; }
+    int flag = 0;
+    std::vector<double> cand;
+    if (rc == TAMCMC_OK) {
+        for (const Pair& Q : T.pairs) {
+            const Band& B = T.bands[(size_t)Q.band];
+            double m_hi = 0, nu0 = 0, bstep = 0;
+            const int nseg = pair_segments(B, Q.inv_g, m_hi, nu0, bstep, flag);
+            for (int j = 0; j < nseg; j++) {
+                auto emit = [&](double s) { cand.push_back(s); };
+                if (exact_trig)
+                    pair_segment<TrigLib, TrigCR>(B, Q.inv_g, T.tmin.data() + B.tab_off, T.tmax.data() + B.tab_off, T.tn.data() + B.tab_off, j, nseg, m_hi, nu0, bstep, emit, flag);
+                else
+                    pair_segment<TrigLib, TrigLib>(B, Q.inv_g, T.tmin.data() + B.tab_off, T.tmax.data() + B.tab_off, T.tn.data() + B.tab_off, j, nseg, m_hi, nu0, bstep, emit, flag);
+            }
+        }
+        rc = finish(P, true, cand.data(), (int)cand.size(), -1.0, capacity, row_out, nmodes_out);
+    }
+    if (flags_out) *flags_out = flag;
+    prep_free(P);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+// rgb_solver.cuh -- the pair loop of the red-giant mixed-mode solver as independent SEGMENT tasks (host + device).
+//
+// Replaces (on the device): solver_mm of external/ARMM/solver_mm.cpp:326-449 as host_rgb.cpp restates it -- for one (p mode, g mode)
+// pair, the sign changes of f(nu) = p(nu) - g(nu) on the coarse grid of the p mode's band and, for each, the solution refined on the
+// local grid by the reference's lin_interpol (tamcmc/sources/interpol.cpp:13-43) and kept if g / p is within 0.1 % of 1.
+//
+// Decomposition.  g = Dnu atan(q tan(X)) / pi, X = pi 1e6 (1/nu - 1/nu_g) / DPl, jumps from +Dnu/2 to -Dnu/2 ... i.e. f jumps DOWN at
+// every pole of the tangent and rises with slope > 1 in between: between two poles f changes sign at most once (- to +), at a pole it
+// may change from + to -.  The poles are known analytically (X / pi = m + 1/2), so segment j of a pair = the stretch in front of
+// pole j (one bisection on the grid index) + the four grid points around pole j (compared pair by pair like sign_change,
+// solver_mm.cpp:71-106).  Segments are independent: one thread each, no communication; their solutions are appended to the chain's
+// candidate list, which the host filters, sorts and makes unique exactly like the reference (solver_mm.cpp:575-590).
+//
+// Arithmetic.  Every value that enters the interpolation is computed with the operations of the reference in its order (no FMA
+// contraction: this header is compiled with -fmad=false / -ffp-contract=off) and the correctly rounded tan / atan of dd_math.cuh;
+// searches only need the SIGN of f and use the fast library functions, re-evaluated exactly when |f| < 1e-9.  Anything the
+// decomposition does not expect (an exact zero, a stretch that does not rise, two poles in one local grid, a ratio test within 1e-6
+// of its bounds) raises the chain's flag and the host solves that chain.
+#pragma once
+#include "dd_math.cuh"
+#include "host_rgb.hpp"
+
+namespace tamcmc_rgb {
+
+struct TrigCR {
+    static TAMCMC_HD double tan_(double x) { return tamcmc_dd::tan_cr(x); }
+    static TAMCMC_HD double atan_(double x) { return tamcmc_dd::atan_cr(x); }
+};
+struct TrigLib {
+    static TAMCMC_HD double tan_(double x) { return tan(x); }
+    static TAMCMC_HD double atan_(double x) { return atan(x); }
+};
+
+#define TAMCMC_RGB_PI 3.141592653589793
+
+// p(nu) - g(nu) as the VectorXd versions of pnu_fct / gnu_fct compute one element (solver_mm.cpp:114-161; host_rgb.cpp PminusG)
+template <class TR>
+TAMCMC_HD_CALL double pmg(const Band& B, double inv_g, double nu)
+{
+    const double pnu = nu - B.nu_p;
+    const double X = ((TAMCMC_RGB_PI * (1.0 / nu - inv_g)) * 1e6) / B.DPl;
+    const double t = B.q * TR::tan_(X);
+    const double gnu = (B.Dnu * TR::atan_(t)) / TAMCMC_RGB_PI;
+    return pnu - gnu;
+}
+// a value whose sign is the sign of the exact value
+template <class FAST, class EXACT>
+TAMCMC_HD double pmg_sign(const Band& B, double inv_g, double nu)
+{
+    double v = pmg<FAST>(B, inv_g, nu);
+    if (!(fabs(v) > 1e-9)) v = pmg<EXACT>(B, inv_g, nu);
+    return v;
+}
+TAMCMC_HD double u_of(const Band& B, double inv_g, double nu) { return (1.0 / nu - inv_g) * 1e6 / B.DPl; }
+TAMCMC_HD double nu_of_u(const Band& B, double inv_g, double u) { return 1.0 / (u * B.DPl / 1e6 + inv_g); }
+TAMCMC_HD double band_nu(const Band& B, int i)                     // Eigen::VectorXd::LinSpaced(n, lo, hi)[i_lo + i]
+{
+    const int k = B.i_lo + i;
+    return (k == B.n - 1) ? B.hi : B.lo + (double)k * B.gstep;
+}
+
+enum { RGB_FLAG_ZERO = 1, RGB_FLAG_SHAPE = 2, RGB_FLAG_POLES = 4, RGB_FLAG_RATIO = 8, RGB_FLAG_OVERFLOW = 16, RGB_FLAG_NONFINITE = 32 };
+
+// lin_interpol(f(nu_local), nu_local, 0) on linspaced(Nx, lo, hi) (host_rgb.cpp interp_zero_lazy), then the 0.1 % test (solver_mm.cpp:421-431)
+template <class FAST, class EXACT>
+TAMCMC_HD bool local_solve(const Band& B, double inv_g, double lo, double hi, int Nx, double& sol, int& flag)
+{
+    if (Nx < 2) return false;
+    const double lstep = (hi - lo) / (double)(Nx - 1);
+    auto y = [&](int i) { return (i == Nx - 1) ? hi : lo + (double)i * lstep; };
+    auto S = [&](int i) { return pmg_sign<FAST, EXACT>(B, inv_g, y(i)); };
+    auto E = [&](int i) { return pmg<EXACT>(B, inv_g, y(i)); };
+    const double X0 = S(0), XN = S(Nx - 1);
+    if (!(X0 == X0) || !(XN == XN)) { flag |= RGB_FLAG_NONFINITE; return false; }
+    double a = 0.0, b = 0.0;
+    if (0.0 >= X0 && 0.0 <= XN) {
+        if (X0 == 0.0 || XN == 0.0) { flag |= RGB_FLAG_ZERO; return false; }
+        // the first i with f(i) <= 0 <= f(i+1): f rises except for a jump down at a pole of the tangent
+        const double uA = u_of(B, inv_g, y(0)), uB = u_of(B, inv_g, y(Nx - 1));          // uA > uB
+        const double mA = floor(uA - 0.5), mB = ceil(uB - 0.5);
+        if (!(mA - mB < 1.0)) { flag |= RGB_FLAG_POLES; return false; }                  // two poles (or not finite): the host's walk
+        int pts[7], np = 0;
+        pts[np++] = 0;
+        if (mA >= mB) {
+            const double nup = nu_of_u(B, inv_g, mA + 0.5);
+            const int il = (int)floor((nup - lo) / lstep);
+            for (int k = il - 1; k <= il + 2; k++) if (k > pts[np - 1] && k <= Nx - 1) pts[np++] = k;
+        }
+        if (Nx - 1 > pts[np - 1]) pts[np++] = Nx - 1;
+        int i = Nx - 2;
+        bool found = false;
+        double fa = X0;
+        for (int s = 0; s + 1 < np && !found; s++) {
+            const int pa = pts[s], pb = pts[s + 1];
+            const double fb = (pb == Nx - 1) ? XN : S(pb);
+            if (!(fb == fb) || fb == 0.0) { flag |= (fb == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return false; }
+            if (pb == pa + 1) {
+                if (fa < 0.0 && fb > 0.0) { i = pa; found = true; }
+            } else if (fa < 0.0 && fb > 0.0) {
+                int l = pa, h = pb;
+                while (h - l > 1) {
+                    const int mid = l + (h - l) / 2;
+                    const double v = S(mid);
+                    if (!(v == v) || v == 0.0) { flag |= (v == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return false; }
+                    if (v < 0.0) l = mid; else h = mid;
+                }
+                i = l; found = true;
+            } else if (fa > 0.0 && fb < 0.0) { flag |= RGB_FLAG_SHAPE; return false; }     // a stretch without a pole does not fall
+            fa = fb;
+        }
+        if (i > Nx - 2) i = Nx - 2;
+        const double Xi = E(i), Xi1 = E(i + 1);
+        a = (y(i + 1) - y(i)) / (Xi1 - Xi);
+        b = y(i) - a * Xi;
+    }
+    if (0.0 < X0 && !(0.0 > XN)) { const double Xa = E(0), Xb = E(1); a = (y(1) - y(0)) / (Xb - Xa); b = y(0) - a * Xa; }
+    if (0.0 > XN) { const double Xa = E(Nx - 1), Xb = E(Nx - 2); a = (y(Nx - 1) - y(Nx - 2)) / (Xa - Xb); b = y(Nx - 2) - a * Xb; }
+    const double x_int = 0.0;
+    const double nu_m = a * x_int + b;
+    // g / p within 0.1 % of 1 (the reference evaluates g in long double; a ratio that close to a bound goes to the host)
+    const double Xs = TAMCMC_RGB_PI * (1.0 / nu_m - inv_g) * 1e6 / B.DPl;
+    const double ratio = (B.Dnu * atan(B.q * tan(Xs)) / TAMCMC_RGB_PI) / (nu_m - B.nu_p);
+    if (fabs(ratio - 0.999) < 1e-6 || fabs(ratio - 1.001) < 1e-6) { flag |= RGB_FLAG_RATIO; return false; }
+    if (ratio >= 0.999 && ratio <= 1.001) { sol = nu_m; return true; }
+    return false;
+}
+
+// number of segments of a pair (poles of the tangent inside the band + 1); 0 and a flag when the decomposition does not apply
+TAMCMC_HD int pair_segments(const Band& B, double inv_g, double& m_hi, double& nu0, double& bstep, int& flag)
+{
+    const int nb = B.nband;
+    nu0 = band_nu(B, 0);
+    const double nuN = band_nu(B, nb - 1);
+    bstep = (nuN - nu0) / (double)(nb - 1);
+    if (!(bstep > 0.0) || !(nu0 > 0.0)) { flag |= RGB_FLAG_SHAPE; return 0; }
+    const double u_hi = u_of(B, inv_g, nu0), u_lo = u_of(B, inv_g, nuN);
+    m_hi = floor(u_hi - 0.5);
+    const double m_lo = ceil(u_lo - 0.5);
+    if (!(m_hi - m_lo <= (double)nb / 6.0) || !(m_hi - m_lo > -4.0)) { flag |= RGB_FLAG_POLES; return 0; }     // poles closer than ~6 grid steps (or NaN): the host's scan
+    const int npoles = (m_hi >= m_lo) ? (int)(m_hi - m_lo) + 1 : 0;
+    return npoles + 1;
+}
+
+// segment j of a pair: emit(solution) for every accepted intersection
+template <class FAST, class EXACT, class Emit>
+TAMCMC_HD void pair_segment(const Band& B, double inv_g, const double* tmin, const double* tmax, const int* tn, int j, int nseg, double m_hi,
+                            double nu0, double bstep, Emit&& emit, int& flag)
+{
+    const int nb = B.nband, npoles = nseg - 1;
+    auto ip_of = [&](int k) { return (int)floor((nu_of_u(B, inv_g, (m_hi - (double)k) + 0.5) - nu0) / bstep); };
+    auto S = [&](int i) { return pmg_sign<FAST, EXACT>(B, inv_g, band_nu(B, i)); };
+    int pts[7], np = 0;
+    int start = 0;
+    if (j > 0) { start = ip_of(j - 1) + 2; if (start < 0) start = 0; if (start > nb - 1) start = nb - 1; }
+    pts[np++] = start;
+    if (j < npoles) {
+        const int ip = ip_of(j);
+        for (int k = ip - 1; k <= ip + 2; k++) if (k > pts[np - 1] && k <= nb - 1) pts[np++] = k;
+    } else if (nb - 1 > pts[np - 1]) pts[np++] = nb - 1;
+    double fa = S(pts[0]);
+    if (!(fa == fa) || fa == 0.0 || isinf(fa)) { flag |= (fa == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return; }
+    for (int s = 0; s + 1 < np; s++) {
+        const int pa = pts[s], pb = pts[s + 1];
+        const double fb = S(pb);
+        if (!(fb == fb) || fb == 0.0 || isinf(fb)) { flag |= (fb == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return; }
+        int idx = -1;
+        if (pb == pa + 1) {
+            if ((fb > 0.0 && fa < 0.0) || (fb < 0.0 && fa > 0.0)) idx = pa;            // the two tests of sign_change; no value is zero here
+        } else {
+            if (fa > 0.0 && fb < 0.0) { flag |= RGB_FLAG_SHAPE; return; }
+            if (fa < 0.0 && fb > 0.0) {
+                int l = pa, h = pb;
+                while (h - l > 1) {
+                    const int mid = l + (h - l) / 2;
+                    const double v = S(mid);
+                    if (!(v == v) || v == 0.0 || isinf(v)) { flag |= (v == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return; }
+                    if (v < 0.0) l = mid; else h = mid;
+                }
+                idx = l;
+            }
+        }
+        if (idx >= 0) {
+            double sol;
+            if (local_solve<FAST, EXACT>(B, inv_g, tmin[idx], tmax[idx], tn[idx], sol, flag)) emit(sol);
+        }
+        fa = fb;
+    }
+}
+
+}  // namespace tamcmc_rgb

@@ -1,0 +1,178 @@
+"""Device red-giant expander (tamcmc_gpu_rgb_expand: csrc/rgb_device.cu, rgb_solver.cuh, dd_math.cuh) -- the pair loop of the ARMM
+mixed-mode solver (external/ARMM/solver_mm.cpp:326-449, 558-573) and the zeta normalisation (external/ARMM/bump_DP.cpp:126-163) on the
+GPU, all chains of a step in one call.
+
+CPU (no GPU): the double-double tan / atan the device uses are correctly rounded (against mpmath) and equal glibc's wherever glibc's are;
+the segment decomposition run on the host reproduces tamcmc_host_expand_rgb_v4 -- which is pinned bit for bit on the reference's own
+functions (tests/test_rgb_expander.py) -- bit for bit with glibc's tan / atan, and with the device's ones up to the stated 1 ulp.
+GPU: rows of tamcmc_gpu_rgb_expand against the host expander's (frequencies identical or 1 ulp, everything else 1e-12), model spectrum and
+logL from reference parameter vectors against the reference's own output at 1e-10."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden", "reference_rgb_vectors.npz")
+
+
+def _variants(G, n_per_case, seed=7):
+    """the fixture's reference parameter vectors + perturbed copies (delta0l, DPl, alpha_g, q, l=0 frequencies)"""
+    rng = np.random.default_rng(seed)
+    for case in range(int(G["ncases"])):
+        for rep in range(n_per_case):
+            params, pl = G["params%d" % case].copy(), G["plength%d" % case]
+            if rep:
+                Nmax, lmax, Nfl0 = int(pl[0]), int(pl[1]), int(pl[2])
+                o = Nmax + lmax + Nfl0
+                params[o] += rng.normal() * 0.02
+                params[o + 1] *= 1 + rng.normal() * 0.01
+                params[o + 2] += rng.normal() * 0.05
+                params[o + 3] *= 1 + rng.normal() * 0.1
+                params[Nmax + lmax:Nmax + lmax + Nfl0] += rng.normal(size=Nfl0) * 0.03
+            yield case, rep, params, pl
+
+
+def test_dd_tan_atan_are_correctly_rounded(tmp_path):
+    """tan_cr / atan_cr (csrc/dd_math.cuh, compiled for the host) against mpmath at 200 bits, and against glibc: they may only differ
+    where glibc is not correctly rounded."""
+    mp = pytest.importorskip("mpmath")
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "dd_math.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+int main(int argc, char** argv) {
+    std::mt19937_64 rng(2024);
+    const long N = atol(argv[1]);
+    std::uniform_real_distribution<double> U(-400.0, 400.0), L(-17.0, 17.0);
+    long bt = 0, ba = 0;
+    for (long i = 0; i < N; i++) {
+        const double x = U(rng), a = std::tan(x), b = tamcmc_dd::tan_cr(x);
+        double t = std::pow(10.0, L(rng)); if (i & 1) t = -t;
+        const double c = std::atan(t), d = tamcmc_dd::atan_cr(t);
+        if (a != b) bt++;
+        if (c != d) ba++;
+        if (i < 3000 || a != b) printf("tan %a %a\n", x, b);
+        if (i < 3000 || c != d) printf("atan %a %a\n", t, d);
+    }
+    printf("count %ld %ld\n", bt, ba);
+}''')
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "tamcmc-c_b200", "csrc"), str(src), "-o", str(exe)])
+    N = 400000
+    out = subprocess.check_output([str(exe), str(N)], text=True).split("\n")
+    mp.mp.prec = 200
+    checked = 0
+    for line in out:
+        f = line.split()
+        if len(f) == 3 and f[0] in ("tan", "atan"):
+            x, v = float.fromhex(f[1]), float.fromhex(f[2])
+            exact = mp.tan(mp.mpf(x)) if f[0] == "tan" else mp.atan(mp.mpf(x))
+            err = abs(mp.mpf(v) - exact)
+            assert err <= abs(mp.mpf(float(np.nextafter(v, np.inf))) - exact) and err <= abs(mp.mpf(float(np.nextafter(v, -np.inf))) - exact), (f[0], x)
+            checked += 1
+        elif len(f) == 3 and f[0] == "count":
+            # glibc 2.39: tan is not correctly rounded for ~0.25 % of the arguments, atan for ~0.02 %
+            assert int(f[1]) < 0.01 * N and int(f[2]) < 0.002 * N
+    assert checked >= 6000
+
+
+@pytest.mark.parametrize("model_id", [25, 27])
+def test_segment_decomposition_reproduces_the_host_solver(pkg, model_id):
+    G = np.load(GOLD)
+    step = G["x"][2] - G["x"][1]
+    n = 0
+    for case, rep, params, pl in _variants(G, 3):
+        try:
+            row, nm = pkg.expand_rgb_v4(model_id, params, pl, step, 120)
+        except pkg.TamcmcError:
+            continue
+        r0, nm0, fl0 = pkg.expand_rgb_v4_emulated(model_id, params, pl, step, 120, exact_trig=0)
+        assert fl0 == 0 and nm0 == nm and np.array_equal(r0, row), (case, rep)             # same operations, same library: same bits
+        r1, nm1, fl1 = pkg.expand_rgb_v4_emulated(model_id, params, pl, step, 120, exact_trig=1)
+        assert fl1 == 0 and nm1 == nm
+        nn = int(pl[8])
+        a, b = row[4 + nn:4 + nn + 20 * nm].reshape(nm, 20), r1[4 + nn:4 + nn + 20 * nm].reshape(nm, 20)
+        assert np.all(np.abs(a[:, 1] - b[:, 1]) <= np.spacing(a[:, 1])), (case, rep)          # frequencies: identical or 1 ulp
+        assert np.mean(a[:, 1] == b[:, 1]) > 0.95
+        np.testing.assert_allclose(b, a, rtol=1e-12, atol=0)
+        n += 1
+    assert n >= 10
+
+
+def test_gpu_rgb_symbols_fail_loudly_without_a_device(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    G = np.load(GOLD)
+    with pytest.raises(pkg.TamcmcError) as e:
+        pkg.RgbExpander(25, G["plength0"], 0.01, 100, 4)
+    assert e.value.status == pkg.ERR_CUDA
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model_id", [25, 27])
+def test_gpu_rgb_expand_matches_host_expander(pkg, model_id):
+    G = np.load(GOLD)
+    step = G["x"][2] - G["x"][1]
+    cases = [(c, r, p, pl) for c, r, p, pl in _variants(G, 4)]
+    pl = cases[0][3]
+    assert all(np.array_equal(pl, c[3]) for c in cases)
+    P = np.stack([c[2] for c in cases])
+    with pkg.RgbExpander(model_id, pl, step, 120, len(cases)) as rx:
+        rows, nm, st, path = rx.expand(P)
+        rows2, nm2, st2, path2 = rx.expand(P)
+        assert np.array_equal(rows, rows2) and np.array_equal(nm, nm2)                     # deterministic (the candidate order is not, the set is)
+    nn = int(pl[8])
+    ndev = 0
+    for i, (case, rep, params, _) in enumerate(cases):
+        try:
+            row, n = pkg.expand_rgb_v4(model_id, params, pl, step, 120)
+        except pkg.TamcmcError as e:
+            assert st[i] == e.status
+            continue
+        assert st[i] == 0 and nm[i] == n, (case, rep, st[i], nm[i], n)
+        ndev += int(path[i] == 0)
+        a, b = row[4 + nn:4 + nn + 20 * n].reshape(n, 20), rows[i, 4 + nn:4 + nn + 20 * n].reshape(n, 20)
+        assert np.array_equal(a[:, 0], b[:, 0])
+        assert np.all(np.abs(a[:, 1] - b[:, 1]) <= np.spacing(a[:, 1])), (case, rep)
+        assert np.mean(a[:, 1] == b[:, 1]) > 0.95
+        np.testing.assert_allclose(b, a, rtol=1e-12, atol=0)
+        assert np.array_equal(rows[i, :4 + nn], row[:4 + nn])
+    assert ndev >= len(cases) - 1                                                          # the device path is the one that ran
+
+
+@pytest.mark.gpu
+def test_gpu_rgb_params_to_logl_against_reference_model(pkg, oracle):
+    """reference parameter vectors -> tamcmc_gpu_rgb_expand (rows in the context's staging block) -> tamcmc_gpu_eval, against the
+    spectrum the reference's own model function returned for the same vectors (tests/golden/reference_rgb_vectors.npz)."""
+    G = np.load(GOLD)
+    x, y = G["x"], G["y"]
+    step = x[2] - x[1]
+    synth = pkg.synth
+    n = int(G["ncases"])
+    pl = G["plength0"]
+    if not all(np.array_equal(pl, G["plength%d" % i]) for i in range(n)):
+        pytest.skip("fixture cases differ in layout")
+    P = np.stack([G["params%d" % i] for i in range(n)])
+    cap, nn = 110, int(pl[8])
+    T = np.ones(n)
+    star = pkg.Star(synth.MODEL_MODE_TABLE, synth.mode_table_plength(cap, nn, 1), synth.mode_table_nparams(cap, nn), x, y)
+    with pkg.Context(star, n, T) as ctx, pkg.RgbExpander(25, pl, step, cap, n) as rx:
+        stage = ctx.params_staging()[0]
+        rows, nm, st, path = rx.expand(P, rows_out=stage)
+        assert (st == 0).all() and (path == 0).all()
+        L, cs = ctx.eval(stage)
+        assert (cs == 0).all()
+        for i in range(n):
+            M_ref = G["model%d" % i]
+            M = ctx.model(np.array(stage[i]))
+            assert np.max(np.abs(M - M_ref) / np.abs(M_ref)) < 1e-10, i
+            L_ref = oracle.call_likelihood(y, M_ref, 1.0, T[i])
+            assert abs(L[0, i] - L_ref) <= 1e-10 * abs(L_ref)
