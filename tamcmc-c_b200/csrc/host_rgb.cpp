@@ -793,9 +793,9 @@ int finish(Prep* Pp, bool deferred, const double* cand, int ncand, double norm, 
     return TAMCMC_OK;
 }
 
-// What the device solver needs for one chain (rgb_device.cu), appended to T: one Band per p mode (coarse grid, band, constants of p - g),
-// the table of local grids over the band (the reference derives them in long double: solver_mm.cpp:402-410), one Pair per (p mode, g mode)
-// whose g mode lies in the p mode's search range (solver_mm.cpp:343), and the sums of the zeta normalisation.  false: solve on the host.
+// What the device solver needs for one chain (rgb_device.cu), appended to T: one Band per p mode (coarse grid, band, constants of p - g
+// and of the local grids), one Pair per (p mode, g mode) whose g mode lies in the p mode's search range (solver_mm.cpp:343), and the sums
+// of the zeta normalisation.  false: solve on the host.
 bool export_task(const Prep* Pp, int chain, DeviceTask& T)
 {
     const Prep& P = *Pp;
@@ -806,30 +806,33 @@ bool export_task(const Prep* Pp, int chain, DeviceTask& T)
     if (!probe.usable()) return false;
     double kf0, kf1; int Ndata;
     if (!ksi_highres_grid(S.nu_p, S.nu_g, kf0, kf1, Ndata)) return false;
-    const double pad = 4.0 * (double)(U.resol * (ld)U.fact);
+    const ld D = U.resol * (ld)U.fact;                                   // the local grids' step, as solver_mm forms it (solver_mm.cpp:406)
+    const double Dh = (double)D, Dl = (double)(D - (ld)Dh);
     const size_t bands0 = T.bands.size();
     for (size_t np = 0; np < S.nu_p.size(); np++) {
         const BandGrid G = band_of(S.nu_p[np], U.dnu_local[np], U.lo[np], U.hi[np], U.resol);
         Band B;
         B.nu_p = (double)(ld)S.nu_p[np]; B.Dnu = (double)(ld)U.dnu_local[np];
-        B.lo = G.lo; B.hi = G.hi; B.gstep = G.gstep; B.DPl = (double)U.DPl; B.q = (double)U.q; B.pad = pad;
-        B.n = (int)G.n; B.i_lo = (int)G.i_lo; B.nband = G.valid ? (int)(G.i_hi - G.i_lo + 1) : 0; B.tab_off = (int)T.tn.size(); B.chain = chain; B.pad_ = 0;
+        B.lo = G.lo; B.hi = G.hi; B.gstep = G.gstep; B.DPl = (double)U.DPl; B.q = (double)U.q;
+        B.resol2 = (double)(2 * U.resol); B.Dh = Dh; B.Dl = Dl;
+        B.n = (int)G.n; B.i_lo = (int)G.i_lo; B.nband = G.valid ? (int)(G.i_hi - G.i_lo + 1) : 0; B.slot_off = T.nslots; B.chain = chain; B.lanes = 8;
         if (!(U.dnu_local[np] > 0) || G.n > 2000000000L) return false;
-        if (B.nband >= 8) {
-            const size_t o = T.tn.size();
-            T.tmin.resize(o + (size_t)B.nband); T.tmax.resize(o + (size_t)B.nband); T.tn.resize(o + (size_t)B.nband);
-            for (int i = 0; i < B.nband; i++) {
-                const long nl = local_grid(G.grid(G.i_lo + i), U.resol, (ld)U.fact, T.tmin[o + (size_t)i], T.tmax[o + (size_t)i]);
-                T.tn[o + (size_t)i] = (int)std::max(-1L, std::min(nl, 1000000000L));
-            }
-        } else if (B.nband > 0) return false;                        // a band of a few points: the host's full scan
-        T.bands.push_back(B);
+        if (B.nband > 0 && B.nband < 8) return false;                    // a band of a few points: the host's full scan
+        T.nslots += B.nband;
+        int first = 1;
         for (size_t ng = 0; ng < S.nu_g.size(); ng++) {
             const ld nu_g = S.nu_g[ng];
             if (!(nu_g >= U.lo[np] && nu_g <= U.hi[np]) || B.nband == 0) continue;
             Pair Q; Q.inv_g = 1.0 / (double)nu_g; Q.band = (int)(bands0 + np); Q.pad_ = 0;
+            if (first) {                                                 // segments of a pair of this band = poles of the tangent inside it + 1
+                const PminusG F(S.nu_p[np], nu_g, U.dnu_local[np], U.DPl, U.q);
+                const double npoles = std::floor(F.u_of(G.grid(G.i_lo)) - 0.5) - std::ceil(F.u_of(G.grid(G.i_hi)) - 0.5) + 1.0;
+                B.lanes = (npoles + 2.0 <= 8.0) ? 8 : (npoles + 2.0 <= 16.0) ? 16 : 32;
+                first = 0;
+            }
             T.pairs.push_back(Q);
         }
+        T.bands.push_back(B);
     }
     KsiHdr K;
     const ld pi = M_PI;
@@ -839,6 +842,12 @@ bool export_task(const Prep* Pp, int chain, DeviceTask& T)
     for (size_t g = 0; g < S.nu_g.size(); g++) { T.kg.push_back((double)(1. / (ld)S.nu_g[g])); T.kg.push_back(S.dPg[g]); }
     T.ksi.push_back(K);
     return true;
+}
+
+// TEST HOOK: the reference's long double local grid (local_grid above) for the emulation's self-check
+long local_grid_reference(const Prep* P, double nu_idx, double* lo, double* hi)
+{
+    return local_grid(nu_idx, P->setup.resol, (ld)P->setup.fact, *lo, *hi);
 }
 
 }  // namespace tamcmc_rgb

@@ -27,33 +27,64 @@ using namespace tamcmc_rgb;
 namespace {
 
 constexpr int KSI_PCHUNK = 8;      // p modes whose sums a thread of the zeta kernel carries in registers at a time
+constexpr unsigned long long SLOT_EMPTY = ~0ull;
 
-__global__ void __launch_bounds__(128) tamcmc_rgb_pairs_kernel(const Band* __restrict__ bands, const Pair* __restrict__ pairs, int npairs,
-                                                                const double* __restrict__ tmin, const double* __restrict__ tmax,
-                                                                const int* __restrict__ tn, double* __restrict__ cand, int cand_cap,
-                                                                int* __restrict__ count, int* __restrict__ flags)
+// One (p mode, g mode) pair per group of `lanes` threads, one segment per lane (rgb_solver.cuh).  A solution found from the sign change at
+// band index idx goes to the band's slot idx with atomicMin on its bit pattern (frequencies are positive: the order of the bits is the
+// order of the values): the g modes of one p mode all see the same intersections, each with its own rounding noise, and the reference
+// keeps the smallest of every cluster (sort + unique with a tolerance of two bins, solver_mm.cpp:575-590) -- the minimum per slot is that
+// value whenever a cluster does not straddle two coarse grid cells, and the host's sort + unique merges the slots when it does.
+__global__ void __launch_bounds__(128) tamcmc_rgb_pairs_kernel(const Band* __restrict__ bands, const Pair* __restrict__ pairs, int npairs, int lanes,
+                                                                unsigned long long* __restrict__ slots, int* __restrict__ flags)
 {
-    const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
-    if (warp >= npairs) return;
-    const Pair Q = pairs[warp];
+    const int t = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
+    const int pair = t / lanes, lane = t % lanes;
+    if (pair >= npairs) return;
+    const Pair Q = pairs[pair];
     const Band B = bands[Q.band];
     int flag = 0;
     double m_hi = 0, nu0 = 0, bstep = 0;
     const int nseg = pair_segments(B, Q.inv_g, m_hi, nu0, bstep, flag);
-    double* out = cand + (size_t)B.chain * (size_t)cand_cap;
-    int* cnt = count + B.chain;
-    for (int j = lane; j < nseg; j += 32)
-        pair_segment<TrigLib, TrigCR>(B, Q.inv_g, tmin + B.tab_off, tmax + B.tab_off, tn + B.tab_off, j, nseg, m_hi, nu0, bstep,
-                                      [&](double s) {
-                                          const int k = atomicAdd(cnt, 1);
-                                          if (k < cand_cap) out[k] = s; else flag |= RGB_FLAG_OVERFLOW;
+    unsigned long long* out = slots + B.slot_off;
+    for (int j = lane; j < nseg; j += lanes)
+        pair_segment<TrigLib, TrigCR>(B, Q.inv_g, j, nseg, m_hi, nu0, bstep,
+                                      [&](int idx, double s) {
+                                          if (s > 0.0) atomicMin(out + idx, (unsigned long long)__double_as_longlong(s));
+                                          else flag |= RGB_FLAG_NONFINITE;
                                       },
                                       flag);
     if (flag) atomicOr(flags + B.chain, flag);
 }
 
-// max over the grid of the zeta sums: sum over (np, ng) of ksi_fct1 (bump_DP.cpp:46-64) in the reference's single-thread order (per np a
-// sum over ng, then added to the total) with its operations (host_rgb.cpp ksi_sum); the cosines are the device library's
+// the non-empty slots of every band -> the chain's candidate list (any order: the host sorts)
+__global__ void __launch_bounds__(128) tamcmc_rgb_compact_kernel(const Band* __restrict__ bands, const unsigned long long* __restrict__ slots,
+                                                                  double* __restrict__ cand, int cand_cap, int* __restrict__ count, int* __restrict__ flags)
+{
+    const Band B = bands[blockIdx.x];
+    for (int i = threadIdx.x; i < B.nband; i += blockDim.x) {
+        const unsigned long long v = slots[B.slot_off + i];
+        if (v == SLOT_EMPTY) continue;
+        const int k = atomicAdd(count + B.chain, 1);
+        if (k < cand_cap) cand[(size_t)B.chain * cand_cap + k] = __longlong_as_double((long long)v);
+        else atomicOr(flags + B.chain, RGB_FLAG_OVERFLOW);
+    }
+}
+
+__device__ __forceinline__ double fast_rcp(double d)          // 1 / d to ~1 ulp: hardware seed + two Newton steps
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-d, r, 1.0);
+    return __fma_rn(r, e, r);
+}
+
+// max over the 4-year-resolution grid of the zeta sums (bump_DP.cpp:126-163): sum over (np, ng) of ksi_fct1 (bump_DP.cpp:46-64),
+//   1 / (1 + (nd / qd) (cu2 / cd2)) = A / (A + B),  A = qd cd2 (per p mode), B = nd cu2 (per g mode),
+// in the reference's order (per np a sum over ng, then added to the total) but with ONE reciprocal per term instead of three divisions:
+// the maximum agrees with the host's to ~1e-15 relative -- it scales every zeta value alike, i.e. heights / widths / splittings of the
+// mixed modes move by that much; frequencies do not depend on it.
 __global__ void __launch_bounds__(128) tamcmc_rgb_ksi_max_kernel(const KsiHdr* __restrict__ hdrs, const double* __restrict__ kp,
                                                                   const double* __restrict__ kg, unsigned long long* __restrict__ norm_bits)
 {
@@ -72,18 +103,17 @@ __global__ void __launch_bounds__(128) tamcmc_rgb_ksi_max_kernel(const KsiHdr* _
         const double v = (H.Ndata == 1 || i == H.Ndata - 1) ? H.fmax : H.fmin + (double)i * ((H.fmax - H.fmin) / (double)(H.Ndata - 1));
         const double inv = 1.0 / v, sq = 1e-6 * (v * v);
         for (int p0 = 0; p0 < H.Lp; p0 += KSI_PCHUNK) {
-            double cd2[KSI_PCHUNK], loc[KSI_PCHUNK];
+            double A[KSI_PCHUNK], loc[KSI_PCHUNK];
 #pragma unroll
             for (int k = 0; k < KSI_PCHUNK; k++) {
-                loc[k] = 0.0; cd2[k] = 1.0;
-                if (p0 + k < H.Lp) { const double c = cos((H.pi_d * (v - s_p[3 * (p0 + k)])) / s_p[3 * (p0 + k) + 1]); cd2[k] = c * c; }
+                loc[k] = 0.0; A[k] = 0.0;
+                if (p0 + k < H.Lp) { const double c = cos((H.pi_d * (v - s_p[3 * (p0 + k)])) / s_p[3 * (p0 + k) + 1]); A[k] = s_p[3 * (p0 + k) + 2] * (c * c); }
             }
             for (int g = 0; g < H.Lg; g++) {
                 const double c = cos((H.c_up * (inv - s_g[2 * g])) / s_g[2 * g + 1]);
-                const double cu2 = c * c, nd = sq * s_g[2 * g + 1];
+                const double Bg = (sq * s_g[2 * g + 1]) * (c * c);
 #pragma unroll
-                for (int k = 0; k < KSI_PCHUNK; k++)
-                    if (p0 + k < H.Lp) loc[k] += 1.0 / (1.0 + (nd / s_p[3 * (p0 + k) + 2]) * (cu2 / cd2[k]));
+                for (int k = 0; k < KSI_PCHUNK; k++) if (p0 + k < H.Lp) loc[k] += A[k] * fast_rcp(A[k] + Bg);
             }
 #pragma unroll
             for (int k = 0; k < KSI_PCHUNK; k++) if (p0 + k < H.Lp) total += loc[k];
@@ -110,9 +140,11 @@ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 struct tamcmc_gpu_rgb {
     int device = 0, max_chains = 0, cand_cap = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_ksi = nullptr;
     char* h_in = nullptr; char* d_in = nullptr; size_t in_cap = 0;
     char* h_out = nullptr; char* d_out = nullptr; size_t out_bytes = 0;
+    unsigned long long* d_slots = nullptr; size_t slots_cap = 0;
     std::vector<Prep*> preps;
     DeviceTask task;
     std::vector<int> on_device;
@@ -133,12 +165,15 @@ int tamcmc_gpu_rgb_create(tamcmc_gpu_rgb** out, int device, int max_chains)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "no usable CUDA device"; return TAMCMC_ERR_CUDA; }
     RGB_CUDA(cudaSetDevice(device));
     tamcmc_gpu_rgb* h = new tamcmc_gpu_rgb();
-    h->device = device; h->max_chains = max_chains; h->cand_cap = 16384;
+    h->device = device; h->max_chains = max_chains; h->cand_cap = 1024;
     h->out_bytes = align16((size_t)max_chains * 16) + (size_t)max_chains * (size_t)h->cand_cap * 8;
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_ksi, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_out, h->out_bytes);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_out, h->out_bytes);
-    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); delete h; return TAMCMC_ERR_CUDA; }
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); tamcmc_gpu_rgb_destroy(h); return TAMCMC_ERR_CUDA; }
     for (int c = 0; c < max_chains; c++) h->preps.push_back(prep_new());
     *out = h;
     return TAMCMC_OK;
@@ -153,7 +188,11 @@ void tamcmc_gpu_rgb_destroy(tamcmc_gpu_rgb* h)
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->d_slots) cudaFree(h->d_slots);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_ksi) cudaEventDestroy(h->ev_ksi);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
 }
 
@@ -179,9 +218,10 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
     for (int c = 0; c < nchains; c++) {
         if (path_out) path_out[c] = -1;
         if (status_out[c] != TAMCMC_OK) continue;
-        const size_t nb = T.bands.size(), npair = T.pairs.size(), nt = T.tn.size(), nk = T.ksi.size(), nkp = T.kp.size(), nkg = T.kg.size();
+        const size_t nb = T.bands.size(), npair = T.pairs.size(), nk = T.ksi.size(), nkp = T.kp.size(), nkg = T.kg.size();
+        const int ns = T.nslots;
         if (export_task(h->preps[(size_t)c], c, T)) h->on_device[(size_t)c] = 1;
-        else { T.bands.resize(nb); T.pairs.resize(npair); T.tmin.resize(nt); T.tmax.resize(nt); T.tn.resize(nt); T.ksi.resize(nk); T.kp.resize(nkp); T.kg.resize(nkg); }
+        else { T.bands.resize(nb); T.pairs.resize(npair); T.ksi.resize(nk); T.kp.resize(nkp); T.kg.resize(nkg); T.nslots = ns; }
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     // ---- stage 2 (device): pair loop + zeta normalisation of every exported chain ----
@@ -190,63 +230,64 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
     int* h_count = (int*)(h->h_out + (size_t)h->max_chains * 8);
     int* h_flag = h_count + h->max_chains;
     double* h_cand = (double*)(h->h_out + hdr_bytes);
-    if (!T.pairs.empty() || !T.ksi.empty()) {
-        size_t off[9];
+    if (!T.ksi.empty()) {
+        size_t off[6];
         off[0] = 0;
         off[1] = off[0] + align16(T.bands.size() * sizeof(Band));
         off[2] = off[1] + align16(T.pairs.size() * sizeof(Pair));
-        off[3] = off[2] + align16(T.tmin.size() * 8);
-        off[4] = off[3] + align16(T.tmax.size() * 8);
-        off[5] = off[4] + align16(T.tn.size() * 4);
-        off[6] = off[5] + align16(T.ksi.size() * sizeof(KsiHdr));
-        off[7] = off[6] + align16(T.kp.size() * 8);
-        off[8] = off[7] + align16(T.kg.size() * 8);
-        if (off[8] > h->in_cap) {
+        off[3] = off[2] + align16(T.ksi.size() * sizeof(KsiHdr));
+        off[4] = off[3] + align16(T.kp.size() * 8);
+        off[5] = off[4] + align16(T.kg.size() * 8);
+        if (off[5] > h->in_cap) {
             if (h->d_in) cudaFree(h->d_in);
             if (h->h_in) cudaFreeHost(h->h_in);
             h->d_in = nullptr; h->h_in = nullptr;
-            h->in_cap = off[8] + off[8] / 2;
+            h->in_cap = off[5] + off[5] / 2;
             RGB_CUDA(cudaMalloc((void**)&h->d_in, h->in_cap));
             RGB_CUDA(cudaMallocHost((void**)&h->h_in, h->in_cap));
         }
+        if ((size_t)T.nslots > h->slots_cap) {
+            if (h->d_slots) cudaFree(h->d_slots);
+            h->d_slots = nullptr;
+            h->slots_cap = (size_t)T.nslots + (size_t)T.nslots / 2 + 1024;
+            RGB_CUDA(cudaMalloc((void**)&h->d_slots, h->slots_cap * 8));
+        }
         std::memcpy(h->h_in + off[0], T.bands.data(), T.bands.size() * sizeof(Band));
         std::memcpy(h->h_in + off[1], T.pairs.data(), T.pairs.size() * sizeof(Pair));
-        std::memcpy(h->h_in + off[2], T.tmin.data(), T.tmin.size() * 8);
-        std::memcpy(h->h_in + off[3], T.tmax.data(), T.tmax.size() * 8);
-        std::memcpy(h->h_in + off[4], T.tn.data(), T.tn.size() * 4);
-        std::memcpy(h->h_in + off[5], T.ksi.data(), T.ksi.size() * sizeof(KsiHdr));
-        std::memcpy(h->h_in + off[6], T.kp.data(), T.kp.size() * 8);
-        std::memcpy(h->h_in + off[7], T.kg.data(), T.kg.size() * 8);
-        RGB_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, off[8], cudaMemcpyHostToDevice, h->stream));
+        std::memcpy(h->h_in + off[2], T.ksi.data(), T.ksi.size() * sizeof(KsiHdr));
+        std::memcpy(h->h_in + off[3], T.kp.data(), T.kp.size() * 8);
+        std::memcpy(h->h_in + off[4], T.kg.data(), T.kg.size() * 8);
+        RGB_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, off[5], cudaMemcpyHostToDevice, h->stream));
         RGB_CUDA(cudaMemsetAsync(h->d_out, 0, hdr_bytes, h->stream));
+        RGB_CUDA(cudaEventRecord(h->ev_in, h->stream));
         unsigned long long* d_norm = (unsigned long long*)h->d_out;
         int* d_count = (int*)(h->d_out + (size_t)h->max_chains * 8);
         int* d_flag = d_count + h->max_chains;
         double* d_cand = (double*)(h->d_out + hdr_bytes);
-        if (!T.ksi.empty()) {
+        {   // the zeta normalisation on its own stream: it does not depend on the pair loop
             int maxN = 0; size_t smem = 0;
             for (const KsiHdr& K : T.ksi) { if (K.Ndata > maxN) maxN = K.Ndata; const size_t s = (size_t)(3 * K.Lp + 2 * K.Lg) * 8; if (s > smem) smem = s; }
             if (smem > 200 * 1024) return TAMCMC_ERR_ARG;
             if (smem > 48 * 1024) RGB_CUDA(cudaFuncSetAttribute(tamcmc_rgb_ksi_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RGB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_in, 0));
             const dim3 grid((unsigned)((maxN + 127) / 128), (unsigned)T.ksi.size());
-            tamcmc_rgb_ksi_max_kernel<<<grid, 128, smem, h->stream>>>((const KsiHdr*)(h->d_in + off[5]), (const double*)(h->d_in + off[6]),
-                                                                      (const double*)(h->d_in + off[7]), d_norm);
+            tamcmc_rgb_ksi_max_kernel<<<grid, 128, smem, h->stream2>>>((const KsiHdr*)(h->d_in + off[2]), (const double*)(h->d_in + off[3]),
+                                                                       (const double*)(h->d_in + off[4]), d_norm);
+            RGB_CUDA(cudaEventRecord(h->ev_ksi, h->stream2));
         }
         if (!T.pairs.empty()) {
-            const int npairs = (int)T.pairs.size();
-            tamcmc_rgb_pairs_kernel<<<(unsigned)((npairs + 3) / 4), 128, 0, h->stream>>>(
-                (const Band*)(h->d_in + off[0]), (const Pair*)(h->d_in + off[1]), npairs, (const double*)(h->d_in + off[2]),
-                (const double*)(h->d_in + off[3]), (const int*)(h->d_in + off[4]), d_cand, h->cand_cap, d_count, d_flag);
+            const int npairs = (int)T.pairs.size(), nbands = (int)T.bands.size();
+            int lanes = 8;
+            for (const Band& B : T.bands) if (B.lanes > lanes) lanes = B.lanes;
+            RGB_CUDA(cudaMemsetAsync(h->d_slots, 0xff, (size_t)T.nslots * 8, h->stream));
+            const long nthreads = (long)npairs * lanes;
+            tamcmc_rgb_pairs_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, h->stream>>>(
+                (const Band*)(h->d_in + off[0]), (const Pair*)(h->d_in + off[1]), npairs, lanes, h->d_slots, d_flag);
+            tamcmc_rgb_compact_kernel<<<(unsigned)nbands, 128, 0, h->stream>>>((const Band*)(h->d_in + off[0]), h->d_slots, d_cand, h->cand_cap, d_count, d_flag);
         }
         RGB_CUDA(cudaGetLastError());
-        // counts, flags and norms first; then only as many candidates as were found
-        RGB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, hdr_bytes, cudaMemcpyDeviceToHost, h->stream));
-        RGB_CUDA(cudaStreamSynchronize(h->stream));
-        for (int c = 0; c < nchains; c++) {
-            if (!h->on_device[(size_t)c] || h_flag[c] || h_count[c] <= 0) continue;
-            const int n = h_count[c] < h->cand_cap ? h_count[c] : h->cand_cap;
-            RGB_CUDA(cudaMemcpyAsync(h_cand + (size_t)c * h->cand_cap, d_cand + (size_t)c * h->cand_cap, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
-        }
+        RGB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_ksi, 0));
+        RGB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
         RGB_CUDA(cudaStreamSynchronize(h->stream));
     }
     clock_gettime(CLOCK_MONOTONIC, &t2);
@@ -256,8 +297,8 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
         if (status_out[c] != TAMCMC_OK) continue;
         double* row = rows_out + (size_t)c * row_stride;
         int nm = 0;
-        double norm;
-        std::memcpy(&norm, &h_norm[c], 8);
+        double norm = 0.0;
+        if (h->on_device[(size_t)c]) std::memcpy(&norm, &h_norm[c], 8);
         const bool dev = h->on_device[(size_t)c] && h_flag[c] == 0 && h_count[c] <= h->cand_cap && norm == norm && norm > 0.0;
         if (dev) {
             status_out[c] = finish(h->preps[(size_t)c], true, h_cand + (size_t)c * h->cand_cap, h_count[c], norm, capacity, row, &nm);
@@ -283,7 +324,9 @@ void tamcmc_gpu_rgb_timings(const tamcmc_gpu_rgb* h, double out[4])
 
 // TEST HOOK (no GPU needed): the segment decomposition of rgb_solver.cuh run on the host for ONE chain, with glibc's tan / atan
 // (exact_trig = 0: must reproduce tamcmc_host_expand_rgb_v4 bit for bit) or the correctly rounded ones of dd_math.cuh (1: what the
-// device computes).  Not a product path: tamcmc_gpu_rgb_expand never calls it.
+// device computes), solutions reduced to the minimum per slot like the kernel does.  Every band index's local grid from the error-free
+// emulation of the reference's long double arithmetic is compared with the real thing (flag 128 on any difference).
+// Not a product path: tamcmc_gpu_rgb_expand never calls it.
 int tamcmc_host_rgb_expand_emulated(int model_id, const double* params, const int* plength, double step, int capacity, double* row_out,
                                     int* nmodes_out, int exact_trig, int* flags_out)
 {
@@ -295,18 +338,26 @@ int tamcmc_host_rgb_expand_emulated(int model_id, const double* params, const in
     int flag = 0;
     std::vector<double> cand;
     if (rc == TAMCMC_OK) {
+        std::vector<double> slots((size_t)T.nslots, -1.0);
+        for (const Band& B : T.bands)
+            for (int i = 0; i < B.nband; i++) {
+                double lo, hi, rlo, rhi; int n;
+                const bool ok = local_grid_ext(band_nu(B, i), B.resol2, B.Dh, B.Dl, lo, hi, n);
+                const long rn = local_grid_reference(P, band_nu(B, i), &rlo, &rhi);
+                if (!ok) { flag |= RGB_FLAG_EXT; continue; }
+                if (lo != rlo || hi != rhi || !((rn < 2 && n < 2) || rn == (long)n)) flag |= 128;
+            }
         for (const Pair& Q : T.pairs) {
             const Band& B = T.bands[(size_t)Q.band];
             double m_hi = 0, nu0 = 0, bstep = 0;
             const int nseg = pair_segments(B, Q.inv_g, m_hi, nu0, bstep, flag);
             for (int j = 0; j < nseg; j++) {
-                auto emit = [&](double s) { cand.push_back(s); };
-                if (exact_trig)
-                    pair_segment<TrigLib, TrigCR>(B, Q.inv_g, T.tmin.data() + B.tab_off, T.tmax.data() + B.tab_off, T.tn.data() + B.tab_off, j, nseg, m_hi, nu0, bstep, emit, flag);
-                else
-                    pair_segment<TrigLib, TrigLib>(B, Q.inv_g, T.tmin.data() + B.tab_off, T.tmax.data() + B.tab_off, T.tn.data() + B.tab_off, j, nseg, m_hi, nu0, bstep, emit, flag);
+                auto emit = [&](int idx, double s) { double& v = slots[(size_t)(B.slot_off + idx)]; if (v < 0.0 || s < v) v = s; };
+                if (exact_trig) pair_segment<TrigLib, TrigCR>(B, Q.inv_g, j, nseg, m_hi, nu0, bstep, emit, flag);
+                else pair_segment<TrigLib, TrigLib>(B, Q.inv_g, j, nseg, m_hi, nu0, bstep, emit, flag);
             }
         }
+        for (double v : slots) if (v >= 0.0) cand.push_back(v);
         rc = finish(P, true, cand.data(), (int)cand.size(), -1.0, capacity, row_out, nmodes_out);
     }
     if (flags_out) *flags_out = flag;

@@ -59,7 +59,59 @@ TAMCMC_HD double band_nu(const Band& B, int i)                     // Eigen::Vec
     return (k == B.n - 1) ? B.hi : B.lo + (double)k * B.gstep;
 }
 
-enum { RGB_FLAG_ZERO = 1, RGB_FLAG_SHAPE = 2, RGB_FLAG_POLES = 4, RGB_FLAG_RATIO = 8, RGB_FLAG_OVERFLOW = 16, RGB_FLAG_NONFINITE = 32 };
+// ---- the local grid of a sign change, as the reference derives it in long double (solver_mm.cpp:402-410; host_rgb.cpp local_grid):
+//   range_min = nu - 2 resol, range_max = nu + 2 resol                       (x87 extended: 64-bit mantissa)
+//   nu_local  = linspaced((long)((range_max - range_min) / (resol * factor)), (double)range_min, (double)range_max)
+// reproduced with error-free transformations.  a + b = s + e exactly (two_sum); rounding to 64 bits rounds e to a multiple of
+// ulp(s) / 2048 (ties to even: the parity is that of e's multiple because s is an even multiple), and the conversion to double gives s
+// unless the rounded e is exactly half an ulp of s (then the even neighbour).  The difference of the two extended values is exact; the
+// quotient by D = resol * factor (an extended value the host passes as two doubles) is compared with the nearest integer k through the
+// exact residual N - k D: the truncated extended quotient is k when N / D >= k - (half an extended ulp below k), else k - 1.
+// false (and the chain goes to the host) at a binade boundary, where the spacings above do not hold.
+struct ExtSum { double d, r; bool ok; };                 // the extended value is d + r, d its conversion to double
+TAMCMC_HD ExtSum ext_add(double a, double b)
+{
+    using namespace tamcmc_dd;
+    const dd se = two_sum(a, b);
+    const double s = se.hi, e = se.lo;
+    int ex;
+    const double fr = frexp(fabs(s), &ex);                    // |s| = fr 2^ex, fr in [0.5, 1)
+    ExtSum R;
+    R.ok = (fr != 0.5) && (s == s) && fabs(s) > 1e-290 && fabs(s) < 1e290;
+    const double u = ldexp(1.0, ex - 53);                     // ulp of s
+    const double M = ldexp(1.5, ex - 53 - 11 + 52);           // (e + M) - M rounds e to a multiple of u / 2048, ties to even
+    const double er = add_(add_(e, M), -M);
+    R.d = s; R.r = er;
+    if (fabs(er) == 0.5 * u) {                                // a tie of the second rounding: to the even double
+        const double t = s / u;                               // an integer below 2^53
+        const bool odd = fmod(t, 2.0) != 0.0;
+        if (odd) { R.d = (er > 0.0) ? s + u : s - u; R.r = (er > 0.0) ? -0.5 * u : 0.5 * u; }
+    }
+    return R;
+}
+TAMCMC_HD bool local_grid_ext(double nu, double resol2 /* 2 resol */, double Dh, double Dl /* resol * factor, extended */, double& lo, double& hi, int& n)
+{
+    using namespace tamcmc_dd;
+    const ExtSum A = ext_add(nu, -resol2), B = ext_add(nu, resol2);
+    lo = A.d; hi = B.d;
+    if (!A.ok || !B.ok || !(Dh > 0.0)) return false;
+    // N = range_max - range_min exactly: (B.d - A.d) + (B.r - A.r), both differences exact
+    const dd N = two_sum(B.d - A.d, B.r - A.r);
+    const double q0 = N.hi / Dh;
+    if (!(q0 == q0) || q0 >= 1.0e9) return false;
+    if (q0 < 1.5) { n = 0; return true; }                     // fewer than two points: the reference skips the sign change
+    const double k = rint(q0);
+    if (fabs(q0 - k) > 1e-6) { n = (int)q0; return true; }    // not next to an integer: the truncation cannot depend on the last bits
+    const dd P = two_prod(k, Dh);                             // k D = P.hi + P.lo + k Dl, every piece exact
+    const double rho = add_(add_(N.hi, -P.hi), add_(add_(N.lo, -P.lo), -mul_(k, Dl)));
+    int ek;
+    frexp(k - 0.5, &ek);                                      // k - 0.5 in [2^(ek-1), 2^ek): extended ulp there is 2^(ek-64)
+    const double h = ldexp(1.0, ek - 65);                     // half of it
+    n = (rho >= -h * Dh) ? (int)k : (int)k - 1;
+    return true;
+}
+
+enum { RGB_FLAG_ZERO = 1, RGB_FLAG_SHAPE = 2, RGB_FLAG_POLES = 4, RGB_FLAG_RATIO = 8, RGB_FLAG_OVERFLOW = 16, RGB_FLAG_NONFINITE = 32, RGB_FLAG_EXT = 64 };
 
 // lin_interpol(f(nu_local), nu_local, 0) on linspaced(Nx, lo, hi) (host_rgb.cpp interp_zero_lazy), then the 0.1 % test (solver_mm.cpp:421-431)
 template <class FAST, class EXACT>
@@ -143,8 +195,7 @@ TAMCMC_HD int pair_segments(const Band& B, double inv_g, double& m_hi, double& n
 
 // segment j of a pair: emit(solution) for every accepted intersection
 template <class FAST, class EXACT, class Emit>
-TAMCMC_HD void pair_segment(const Band& B, double inv_g, const double* tmin, const double* tmax, const int* tn, int j, int nseg, double m_hi,
-                            double nu0, double bstep, Emit&& emit, int& flag)
+TAMCMC_HD void pair_segment(const Band& B, double inv_g, int j, int nseg, double m_hi, double nu0, double bstep, Emit&& emit, int& flag)
 {
     const int nb = B.nband, npoles = nseg - 1;
     auto ip_of = [&](int k) { return (int)floor((nu_of_u(B, inv_g, (m_hi - (double)k) + 0.5) - nu0) / bstep); };
@@ -158,11 +209,11 @@ TAMCMC_HD void pair_segment(const Band& B, double inv_g, const double* tmin, con
         for (int k = ip - 1; k <= ip + 2; k++) if (k > pts[np - 1] && k <= nb - 1) pts[np++] = k;
     } else if (nb - 1 > pts[np - 1]) pts[np++] = nb - 1;
     double fa = S(pts[0]);
-    if (!(fa == fa) || fa == 0.0 || isinf(fa)) { flag |= (fa == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return; }
+    if (!(fa == fa) || fa == 0.0 || fabs(fa) > 1.0e300) { flag |= (fa == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return; }
     for (int s = 0; s + 1 < np; s++) {
         const int pa = pts[s], pb = pts[s + 1];
         const double fb = S(pb);
-        if (!(fb == fb) || fb == 0.0 || isinf(fb)) { flag |= (fb == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return; }
+        if (!(fb == fb) || fb == 0.0 || fabs(fb) > 1.0e300) { flag |= (fb == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return; }
         int idx = -1;
         if (pb == pa + 1) {
             if ((fb > 0.0 && fa < 0.0) || (fb < 0.0 && fa > 0.0)) idx = pa;            // the two tests of sign_change; no value is zero here
@@ -173,15 +224,17 @@ TAMCMC_HD void pair_segment(const Band& B, double inv_g, const double* tmin, con
                 while (h - l > 1) {
                     const int mid = l + (h - l) / 2;
                     const double v = S(mid);
-                    if (!(v == v) || v == 0.0 || isinf(v)) { flag |= (v == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return; }
+                    if (!(v == v) || v == 0.0 || fabs(v) > 1.0e300) { flag |= (v == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return; }
                     if (v < 0.0) l = mid; else h = mid;
                 }
                 idx = l;
             }
         }
         if (idx >= 0) {
-            double sol;
-            if (local_solve<FAST, EXACT>(B, inv_g, tmin[idx], tmax[idx], tn[idx], sol, flag)) emit(sol);
+            double sol, llo, lhi;
+            int ln;
+            if (!local_grid_ext(band_nu(B, idx), B.resol2, B.Dh, B.Dl, llo, lhi, ln)) { flag |= RGB_FLAG_EXT; return; }
+            if (local_solve<FAST, EXACT>(B, inv_g, llo, lhi, ln, sol, flag)) emit(idx, sol);
         }
         fa = fb;
     }

@@ -83,6 +83,19 @@ int main(int argc, char** argv) {
     assert checked >= 6000
 
 
+def test_long_double_local_grid_is_reproduced_exactly(tmp_path):
+    """local_grid_ext (csrc/rgb_solver.cuh): the reference's x87 extended-precision local grid (solver_mm.cpp:402-410) from error-free
+    transformations in double, against the real long double arithmetic on 3 million random (nu, resol, factor): range_min, range_max and
+    the truncated point count (which flips between 799 and 800 with the last bits of the quotient) must all be identical."""
+    exe = tmp_path / "lg"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "tamcmc-c_b200", "csrc"),
+                           os.path.join(HERE, "cpp", "local_grid_ext_check.cpp"), "-o", str(exe)])
+    out = subprocess.check_output([str(exe), "3000000"], text=True)
+    f = out.split()
+    assert "bad 0 notok 0" in out, out
+    assert int(f[7].rstrip(",")) > 1000 and int(f[9].rstrip(")")) > 1000, out          # both truncations occur
+
+
 @pytest.mark.parametrize("model_id", [25, 27])
 def test_segment_decomposition_reproduces_the_host_solver(pkg, model_id):
     G = np.load(GOLD)
@@ -170,9 +183,10 @@ def test_gpu_rgb_params_to_logl_against_reference_model(pkg, oracle):
         assert (st == 0).all() and (path == 0).all()
         L, cs = ctx.eval(stage)
         assert (cs == 0).all()
+        rows = np.array(stage[:n])                  # (tamcmc_gpu_model stages its own row in the same block)
         for i in range(n):
             M_ref = G["model%d" % i]
-            M = ctx.model(np.array(stage[i]))
+            M = ctx.model(rows[i])
             assert np.max(np.abs(M - M_ref) / np.abs(M_ref)) < 1e-10, i
             L_ref = oracle.call_likelihood(y, M_ref, 1.0, T[i])
             assert abs(L[0, i] - L_ref) <= 1e-10 * abs(L_ref)
