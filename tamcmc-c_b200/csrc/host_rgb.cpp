@@ -448,14 +448,40 @@ void ksi_block(size_t Lp, size_t Lg, const double* cu2 /*[Lg][W]*/, const double
     for (int w = 0; w < KSI_W; w++) tot[w] = t[w];
 }
 
+// the per-(p mode), per-(g mode) constants of the zeta sums, and the sums of ONE block of KSI_W frequencies
+struct KsiConst {
+    std::vector<double> inv_g, qD;
+    double c_up = 0, pi_d = 0;
+    KsiConst(const vec& nu_g, const vec& Dnu_p, ld q)
+    {
+        const ld pi = M_PI;
+        c_up = (double)(pi * 1e6); pi_d = (double)pi;
+        inv_g.resize(nu_g.size()); qD.resize(Dnu_p.size());
+        for (size_t g = 0; g < nu_g.size(); g++) inv_g[g] = (double)(1. / (ld)nu_g[g]);
+        for (size_t p = 0; p < Dnu_p.size(); p++) qD[p] = (double)(q * (ld)Dnu_p[p]);
+    }
+};
+struct KsiScratch { std::vector<double> cu2, cd2, nd; };
+void ksi_sum_block(long b, const vec& nu, const vec& nu_p, const vec& Dnu_p, const vec& DPl, const KsiConst& K, KsiScratch& W, vec& out)
+{
+    const size_t Lp = nu_p.size(), Lg = K.inv_g.size();
+    const long N = (long)nu.size();
+    W.cu2.resize(Lg * KSI_W); W.cd2.resize(Lp * KSI_W); W.nd.resize(Lg * KSI_W);
+    double tot[KSI_W];
+    for (int w = 0; w < KSI_W; w++) {
+        const long i = std::min(b * KSI_W + w, N - 1);           // (the last block repeats the last frequency in its spare lanes)
+        const double v = nu[(size_t)i];
+        const double inv = 1.0 / v, sq = 1e-6 * (v * v);
+        for (size_t g = 0; g < Lg; g++) { const double c = std::cos((K.c_up * (inv - K.inv_g[g])) / DPl[g]); W.cu2[g * KSI_W + w] = c * c; W.nd[g * KSI_W + w] = sq * DPl[g]; }
+        for (size_t p = 0; p < Lp; p++) { const double c = std::cos((K.pi_d * (v - nu_p[p])) / Dnu_p[p]); W.cd2[p * KSI_W + w] = c * c; }
+    }
+    ksi_block(Lp, Lg, W.cu2.data(), W.nd.data(), W.cd2.data(), K.qD.data(), tot);
+    for (int w = 0; w < KSI_W; w++) { const long i = b * KSI_W + w; if (i < N) out[(size_t)i] = tot[w]; }
+}
+
 void ksi_sum(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, const vec& DPl, ld q, vec& out)
 {
-    const ld pi = M_PI;
-    const size_t Lp = nu_p.size(), Lg = nu_g.size();
-    const double c_up = (double)(pi * 1e6), pi_d = (double)pi;
-    std::vector<double> inv_g(Lg), qD(Lp);
-    for (size_t g = 0; g < Lg; g++) inv_g[g] = (double)(1. / (ld)nu_g[g]);
-    for (size_t p = 0; p < Lp; p++) qD[p] = (double)(q * (ld)Dnu_p[p]);
+    const KsiConst K(nu_g, Dnu_p, q);
     out.assign(nu.size(), 0.0);
     const long N = (long)nu.size();
     const long NB = (N + KSI_W - 1) / KSI_W;
@@ -463,22 +489,11 @@ void ksi_sum(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, 
 #pragma omp parallel
 #endif
     {
-        std::vector<double> cu2(Lg * KSI_W), cd2(Lp * KSI_W), nd(Lg * KSI_W);
-        double tot[KSI_W];
+        KsiScratch W;
 #ifdef _OPENMP
 #pragma omp for schedule(static)
 #endif
-        for (long b = 0; b < NB; b++) {
-            for (int w = 0; w < KSI_W; w++) {
-                const long i = std::min(b * KSI_W + w, N - 1);           // (the last block repeats the last frequency in its spare lanes)
-                const double v = nu[(size_t)i];
-                const double inv = 1.0 / v, sq = 1e-6 * (v * v);
-                for (size_t g = 0; g < Lg; g++) { const double c = std::cos((c_up * (inv - inv_g[g])) / DPl[g]); cu2[g * KSI_W + w] = c * c; nd[g * KSI_W + w] = sq * DPl[g]; }
-                for (size_t p = 0; p < Lp; p++) { const double c = std::cos((pi_d * (v - nu_p[p])) / Dnu_p[p]); cd2[p * KSI_W + w] = c * c; }
-            }
-            ksi_block(Lp, Lg, cu2.data(), nd.data(), cd2.data(), qD.data(), tot);
-            for (int w = 0; w < KSI_W; w++) { const long i = b * KSI_W + w; if (i < N) out[(size_t)i] = tot[w]; }
-        }
+        for (long b = 0; b < NB; b++) ksi_sum_block(b, nu, nu_p, Dnu_p, DPl, K, W, out);
     }
 }
 
@@ -496,11 +511,13 @@ bool ksi_highres_grid(const vec& nu_p, const vec& nu_g, double& fmin_d, double& 
 }
 
 // norm_in >= 0: the maximum over the high-resolution grid computed elsewhere (the device, rgb_device.cu)
-bool ksi_fct2_precise(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, const vec& DPl, ld q, vec& ksi_pg, double norm_in = -1.0)
+// have_sums: ksi_pg already holds the zeta sums at `nu` (computed block by block elsewhere)
+bool ksi_fct2_precise(const vec& nu, const vec& nu_p, const vec& nu_g, const vec& Dnu_p, const vec& DPl, ld q, vec& ksi_pg, double norm_in = -1.0,
+                      bool have_sums = false)
 {
     double fmin, fmax; int Ndata;
     if (!ksi_highres_grid(nu_p, nu_g, fmin, fmax, Ndata)) return false;
-    ksi_sum(nu, nu_p, nu_g, Dnu_p, DPl, q, ksi_pg);
+    if (!have_sums) ksi_sum(nu, nu_p, nu_g, Dnu_p, DPl, q, ksi_pg);
     ld norm_coef = norm_in;
     if (!(norm_in >= 0)) {
         const vec nu_highres = linspaced(Ndata, fmin, fmax);
@@ -632,6 +649,8 @@ struct Prep {
     Spline bias;
     Eigensols S;
     PairSetup setup;               // set when the solve was deferred
+    vec fl1_all, ksi_raw;          // finish in stages: the mixed-mode frequencies (with bias) and the zeta sums at them
+    bool have_ksi = false;
 };
 
 Prep* prep_new() { return new Prep(); }
@@ -708,6 +727,55 @@ int prepare(Prep* Pp, int model_id, const double* params, const int* plength, do
     return TAMCMC_OK;
 }
 
+// First part of the rest: the mixed-mode frequencies (deferred: filter, sort, unique of the raw solutions; then the bias, models.cpp:4868-4874).
+int finish_modes(Prep* Pp, bool deferred, const double* cand, int ncand)
+{
+    Prep& P = *Pp;
+    Eigensols& S = P.S;
+    P.have_ksi = false;
+    if (deferred) {
+        if (!P.setup.set) return TAMCMC_ERR_NONFINITE;
+        vec all;
+        if (cand && ncand > 0) all.assign(cand, cand + ncand);
+        sort_unique(all, P.setup.resol, P.setup.keep_min, P.setup.keep_max, S.nu_m);
+    }
+    if (!S.ok || S.nu_m.empty()) return TAMCMC_ERR_NONFINITE;                    // no mixed mode: the reference indexes empty vectors from here on
+    P.fl1_all = S.nu_m;
+    if (P.bias_type != 0) for (double& f : P.fl1_all) f = f + P.bias(f);
+    P.ksi_raw.assign(P.fl1_all.size(), 0.0);
+    return TAMCMC_OK;
+}
+// The zeta sums at the mixed modes, one block of 8 frequencies at a time (so that a caller can spread the blocks of all its chains over
+// its threads): ksi_blocks() blocks, any order, then ksi_done().
+int ksi_blocks(const Prep* P) { return (int)((P->fl1_all.size() + KSI_W - 1) / KSI_W); }
+void ksi_block_compute(Prep* Pp, int b)
+{
+    Prep& P = *Pp;
+    const KsiConst K(P.S.nu_g, P.S.dnup, P.q_star);
+    KsiScratch W;
+    ksi_sum_block(b, P.fl1_all, P.S.nu_p, P.S.dnup, P.S.dPg, K, W, P.ksi_raw);
+}
+void ksi_done(Prep* P) { P->have_ksi = true; }
+// The exact zeta sums (host arithmetic, host cosines) at points `idx` of the 4-year-resolution grid, and their maximum: the device finds
+// WHERE the maximum is with its fast arithmetic, the value that normalises the zeta function is computed here like the reference does.
+double ksi_norm_at(const Prep* Pp, const int* idx, int n)
+{
+    const Prep& P = *Pp;
+    double f0, f1; int Ndata;
+    if (n < 1 || !ksi_highres_grid(P.S.nu_p, P.S.nu_g, f0, f1, Ndata)) return -1.0;
+    vec nu((size_t)n), out;
+    const double st = (Ndata > 1) ? (f1 - f0) / (double)(Ndata - 1) : 0.0;
+    for (int k = 0; k < n; k++) {
+        if (idx[k] < 0 || idx[k] >= Ndata) return -1.0;
+        nu[(size_t)k] = (Ndata == 1 || idx[k] == Ndata - 1) ? f1 : f0 + (double)idx[k] * st;          // linspaced(Ndata, f0, f1)[idx]
+    }
+    const KsiConst K(P.S.nu_g, P.S.dnup, P.q_star);
+    KsiScratch W;
+    out.assign((size_t)n, 0.0);
+    for (long b = 0; b < (long)((n + KSI_W - 1) / KSI_W); b++) ksi_sum_block(b, nu, P.S.nu_p, P.S.dnup, P.S.dPg, K, W, out);
+    return vmax(out);
+}
+
 // The rest of the model function (models.cpp:4868-5006): bias, zeta function, heights / widths / splittings of the mixed modes, the row.
 // deferred: cand / ncand are the raw solutions of a deferred pair loop (any order; filtered, sorted and made unique here).
 // norm: max of the zeta sums over the 4-year-resolution grid (bump_DP.cpp:155-163) when it was computed elsewhere, < 0 to compute it here.
@@ -720,17 +788,15 @@ int finish(Prep* Pp, bool deferred, const double* cand, int ncand, double norm, 
     const ld pi = M_PI;
     const vec& fl0_all = P.fl0_all; const vec& Wl0_all = P.Wl0_all; const vec& Hl0_all = P.Hl0_all;
     Eigensols& S = P.S;
-    if (deferred) {
-        if (!P.setup.set) return TAMCMC_ERR_NONFINITE;
-        vec all;
-        if (cand && ncand > 0) all.assign(cand, cand + ncand);
-        sort_unique(all, P.setup.resol, P.setup.keep_min, P.setup.keep_max, S.nu_m);
+    if (!P.have_ksi) {
+        const int rc = finish_modes(Pp, deferred, cand, ncand);
+        if (rc) return rc;
     }
-    if (!S.ok || S.nu_m.empty()) return TAMCMC_ERR_NONFINITE;                    // no mixed mode: the reference indexes empty vectors from here on
-    vec fl1_all = S.nu_m;
-    if (P.bias_type != 0) for (double& f : fl1_all) f = f + P.bias(f);          // models.cpp:4868-4874
-    vec ksi_pg;
-    if (!ksi_fct2_precise(fl1_all, S.nu_p, S.nu_g, S.dnup, S.dPg, P.q_star, ksi_pg, norm)) return TAMCMC_ERR_NONFINITE;
+    const vec& fl1_all = P.fl1_all;
+    vec ksi_pg = P.ksi_raw;
+    const bool have = P.have_ksi;
+    P.have_ksi = false;
+    if (!ksi_fct2_precise(fl1_all, S.nu_p, S.nu_g, S.dnup, S.dPg, P.q_star, ksi_pg, norm, have)) return TAMCMC_ERR_NONFINITE;
     const size_t N1 = fl1_all.size();
     const double Hfactor = P.Hfactor, Wfactor = P.Wfactor, rot_env = P.rot_env, rot_core = P.rot_core, fmin = P.fmin, fmax = P.fmax;
     const double Vl1 = P.Vl1, Vl2 = P.Vl2, Vl3 = P.Vl3;
@@ -815,7 +881,7 @@ bool export_task(const Prep* Pp, int chain, DeviceTask& T)
         B.nu_p = (double)(ld)S.nu_p[np]; B.Dnu = (double)(ld)U.dnu_local[np];
         B.lo = G.lo; B.hi = G.hi; B.gstep = G.gstep; B.DPl = (double)U.DPl; B.q = (double)U.q;
         B.resol2 = (double)(2 * U.resol); B.Dh = Dh; B.Dl = Dl;
-        B.n = (int)G.n; B.i_lo = (int)G.i_lo; B.nband = G.valid ? (int)(G.i_hi - G.i_lo + 1) : 0; B.slot_off = T.nslots; B.chain = chain; B.lanes = 8;
+        B.n = (int)G.n; B.i_lo = (int)G.i_lo; B.nband = G.valid ? (int)(G.i_hi - G.i_lo + 1) : 0; B.slot_off = T.nslots; B.chain = chain; B.nseg_est = 1; B.rep_inv_g = 0.0;
         if (!(U.dnu_local[np] > 0) || G.n > 2000000000L) return false;
         if (B.nband > 0 && B.nband < 8) return false;                    // a band of a few points: the host's full scan
         T.nslots += B.nband;
@@ -827,7 +893,8 @@ bool export_task(const Prep* Pp, int chain, DeviceTask& T)
             if (first) {                                                 // segments of a pair of this band = poles of the tangent inside it + 1
                 const PminusG F(S.nu_p[np], nu_g, U.dnu_local[np], U.DPl, U.q);
                 const double npoles = std::floor(F.u_of(G.grid(G.i_lo)) - 0.5) - std::ceil(F.u_of(G.grid(G.i_hi)) - 0.5) + 1.0;
-                B.lanes = (npoles + 2.0 <= 8.0) ? 8 : (npoles + 2.0 <= 16.0) ? 16 : 32;
+                B.nseg_est = (npoles >= 0.0 && npoles < 1.0e6) ? (int)npoles + 2 : 1;
+                B.rep_inv_g = Q.inv_g;
                 first = 0;
             }
             T.pairs.push_back(Q);
@@ -837,7 +904,8 @@ bool export_task(const Prep* Pp, int chain, DeviceTask& T)
     KsiHdr K;
     const ld pi = M_PI;
     K.fmin = kf0; K.fmax = kf1; K.c_up = (double)(pi * 1e6); K.pi_d = (double)pi;
-    K.Lp = (int)S.nu_p.size(); K.Lg = (int)S.nu_g.size(); K.Ndata = Ndata; K.off_p = (int)(T.kp.size() / 3); K.off_g = (int)(T.kg.size() / 2); K.chain = chain;
+    K.Lp = (int)S.nu_p.size(); K.Lg = (int)S.nu_g.size(); K.Ndata = Ndata; K.off_p = (int)(T.kp.size() / 3); K.off_g = (int)(T.kg.size() / 2); K.chain = chain; K.val_off = T.nvals; K.pad_ = 0;
+    T.nvals += Ndata;
     for (size_t p = 0; p < S.nu_p.size(); p++) { T.kp.push_back(S.nu_p[p]); T.kp.push_back(S.dnup[p]); T.kp.push_back((double)(U.q * (ld)S.dnup[p])); }
     for (size_t g = 0; g < S.nu_g.size(); g++) { T.kg.push_back((double)(1. / (ld)S.nu_g[g])); T.kg.push_back(S.dPg[g]); }
     T.ksi.push_back(K);

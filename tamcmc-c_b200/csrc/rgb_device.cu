@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/tamcmc_gpu.h"
@@ -29,44 +30,70 @@ namespace {
 constexpr int KSI_PCHUNK = 8;      // p modes whose sums a thread of the zeta kernel carries in registers at a time
 constexpr unsigned long long SLOT_EMPTY = ~0ull;
 
-// One (p mode, g mode) pair per group of `lanes` threads, one segment per lane (rgb_solver.cuh).  A solution found from the sign change at
-// band index idx goes to the band's slot idx with atomicMin on its bit pattern (frequencies are positive: the order of the bits is the
-// order of the values): the g modes of one p mode all see the same intersections, each with its own rounding noise, and the reference
-// keeps the smallest of every cluster (sort + unique with a tolerance of two bins, solver_mm.cpp:575-590) -- the minimum per slot is that
-// value whenever a cluster does not straddle two coarse grid cells, and the host's sort + unique merges the slots when it does.
+constexpr int TOP_CAP = 14;
+struct OutHdr { unsigned long long norm_bits; int count, flag, ntop, top[TOP_CAP], pad_; };     // per chain, 80 bytes
+constexpr int REC_CAP = 128;         // sign-change records per band (two or three per segment)
+
+// phase 1 (rgb_solver.cuh): the segments of every band, searched with the band's first g mode; one thread per segment
+__global__ void __launch_bounds__(64) tamcmc_rgb_search_kernel(const Band* __restrict__ bands, Record* __restrict__ recs, int* __restrict__ nrec,
+                                                               OutHdr* __restrict__ hdr)
+{
+    const Band B = bands[blockIdx.x];
+    if (B.nband == 0 || B.rep_inv_g == 0.0) return;
+    int flag = 0;
+    double m_hi = 0, nu0 = 0, bstep = 0;
+    const int nseg = pair_segments(B, B.rep_inv_g, m_hi, nu0, bstep, flag);
+    Record* out = recs + (size_t)blockIdx.x * REC_CAP;
+    for (int j = threadIdx.x; j < nseg; j += blockDim.x)
+        pair_segment<TrigLib, TrigCR>(B, B.rep_inv_g, j, nseg, m_hi, nu0, bstep,
+                                      [&](const Record& R) {
+                                          const int k = atomicAdd(nrec + blockIdx.x, 1);
+                                          if (k < REC_CAP) out[k] = R; else flag |= RGB_FLAG_OVERFLOW;
+                                      },
+                                      flag);
+    if (flag) atomicOr(&hdr[B.chain].flag, flag);
+}
+
+// phase 2: every record of a band for every g mode of the band, `lanes` threads per (p mode, g mode) pair.  A solution found from the sign
+// change at band index idx goes to the band's slot idx with atomicMin on its bit pattern (frequencies are positive: the order of the bits
+// is the order of the values): the reference keeps the smallest of every cluster of solutions (sort + unique with a tolerance of two
+// bins, solver_mm.cpp:575-590) -- the minimum per slot is that value whenever a cluster does not straddle two coarse grid cells, and the
+// host's sort + unique merges the slots when it does.
 __global__ void __launch_bounds__(128) tamcmc_rgb_pairs_kernel(const Band* __restrict__ bands, const Pair* __restrict__ pairs, int npairs, int lanes,
-                                                                unsigned long long* __restrict__ slots, int* __restrict__ flags)
+                                                                const Record* __restrict__ recs, const int* __restrict__ nrec,
+                                                                unsigned long long* __restrict__ slots, OutHdr* __restrict__ hdr)
 {
     const int t = (int)(blockIdx.x * (unsigned)blockDim.x + threadIdx.x);
     const int pair = t / lanes, lane = t % lanes;
     if (pair >= npairs) return;
     const Pair Q = pairs[pair];
+    int n = nrec[Q.band];
+    if (n > REC_CAP) n = REC_CAP;
+    if (lane >= n) return;
     const Band B = bands[Q.band];
     int flag = 0;
-    double m_hi = 0, nu0 = 0, bstep = 0;
-    const int nseg = pair_segments(B, Q.inv_g, m_hi, nu0, bstep, flag);
-    unsigned long long* out = slots + B.slot_off;
-    for (int j = lane; j < nseg; j += lanes)
-        pair_segment<TrigLib, TrigCR>(B, Q.inv_g, j, nseg, m_hi, nu0, bstep,
-                                      [&](int idx, double s) {
-                                          if (s > 0.0) atomicMin(out + idx, (unsigned long long)__double_as_longlong(s));
-                                          else flag |= RGB_FLAG_NONFINITE;
-                                      },
-                                      flag);
-    if (flag) atomicOr(flags + B.chain, flag);
+    for (int r = lane; r < n; r += lanes) {
+        const Record R = recs[(size_t)Q.band * REC_CAP + r];
+        double sol;
+        if (record_eval<TrigCR>(B, Q.inv_g, R, sol, flag)) {
+            if (sol > 0.0) atomicMin(slots + B.slot_off + R.idx, (unsigned long long)__double_as_longlong(sol));
+            else flag |= RGB_FLAG_NONFINITE;
+        }
+    }
+    if (flag) atomicOr(&hdr[B.chain].flag, flag);
 }
 
 // the non-empty slots of every band -> the chain's candidate list (any order: the host sorts)
 __global__ void __launch_bounds__(128) tamcmc_rgb_compact_kernel(const Band* __restrict__ bands, const unsigned long long* __restrict__ slots,
-                                                                  double* __restrict__ cand, int cand_cap, int* __restrict__ count, int* __restrict__ flags)
+                                                                  double* __restrict__ cand, int cand_cap, OutHdr* __restrict__ hdr)
 {
     const Band B = bands[blockIdx.x];
     for (int i = threadIdx.x; i < B.nband; i += blockDim.x) {
         const unsigned long long v = slots[B.slot_off + i];
         if (v == SLOT_EMPTY) continue;
-        const int k = atomicAdd(count + B.chain, 1);
+        const int k = atomicAdd(&hdr[B.chain].count, 1);
         if (k < cand_cap) cand[(size_t)B.chain * cand_cap + k] = __longlong_as_double((long long)v);
-        else atomicOr(flags + B.chain, RGB_FLAG_OVERFLOW);
+        else atomicOr(&hdr[B.chain].flag, RGB_FLAG_OVERFLOW);
     }
 }
 
@@ -86,7 +113,7 @@ __device__ __forceinline__ double fast_rcp(double d)          // 1 / d to ~1 ulp
 // the maximum agrees with the host's to ~1e-15 relative -- it scales every zeta value alike, i.e. heights / widths / splittings of the
 // mixed modes move by that much; frequencies do not depend on it.
 __global__ void __launch_bounds__(128) tamcmc_rgb_ksi_max_kernel(const KsiHdr* __restrict__ hdrs, const double* __restrict__ kp,
-                                                                  const double* __restrict__ kg, unsigned long long* __restrict__ norm_bits)
+                                                                  const double* __restrict__ kg, double* __restrict__ vals, OutHdr* __restrict__ hdr)
 {
     extern __shared__ double sm[];
     const KsiHdr H = hdrs[blockIdx.y];
@@ -123,7 +150,22 @@ __global__ void __launch_bounds__(128) tamcmc_rgb_ksi_max_kernel(const KsiHdr* _
     unsigned long long b = (unsigned long long)__double_as_longlong(total);
     if (total != total) b = 0x7ff8000000000000ull;
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o); b = (t > b) ? t : b; }
-    if ((threadIdx.x & 31) == 0) atomicMax(norm_bits + H.chain, b);
+    if (i < H.Ndata) vals[H.val_off + i] = total;
+    if ((threadIdx.x & 31) == 0) atomicMax(&hdr[H.chain].norm_bits, b);
+}
+
+// the grid points whose (fast) sum is within 1e-12 of the maximum: the host evaluates those exactly and takes the maximum of that
+__global__ void __launch_bounds__(128) tamcmc_rgb_ksi_top_kernel(const KsiHdr* __restrict__ hdrs, const double* __restrict__ vals, OutHdr* __restrict__ hdr)
+{
+    const KsiHdr H = hdrs[blockIdx.y];
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= H.Ndata) return;
+    const double mx = __longlong_as_double((long long)hdr[H.chain].norm_bits);
+    const double v = vals[H.val_off + i];
+    if (v >= mx * (1.0 - 1e-12)) {
+        const int k = atomicAdd(&hdr[H.chain].ntop, 1);
+        if (k < TOP_CAP) hdr[H.chain].top[k] = i;
+    }
 }
 
 std::string g_err;
@@ -145,6 +187,8 @@ struct tamcmc_gpu_rgb {
     char* h_in = nullptr; char* d_in = nullptr; size_t in_cap = 0;
     char* h_out = nullptr; char* d_out = nullptr; size_t out_bytes = 0;
     unsigned long long* d_slots = nullptr; size_t slots_cap = 0;
+    double* d_vals = nullptr; size_t vals_cap = 0;        // zeta sums over the normalisation grids
+    char* d_recs = nullptr; size_t recs_cap = 0;          // [bands] record counts, then [bands][REC_CAP] records
     std::vector<Prep*> preps;
     DeviceTask task;
     std::vector<int> on_device;
@@ -166,7 +210,7 @@ int tamcmc_gpu_rgb_create(tamcmc_gpu_rgb** out, int device, int max_chains)
     RGB_CUDA(cudaSetDevice(device));
     tamcmc_gpu_rgb* h = new tamcmc_gpu_rgb();
     h->device = device; h->max_chains = max_chains; h->cand_cap = 1024;
-    h->out_bytes = align16((size_t)max_chains * 16) + (size_t)max_chains * (size_t)h->cand_cap * 8;
+    h->out_bytes = align16((size_t)max_chains * sizeof(OutHdr)) + (size_t)max_chains * (size_t)h->cand_cap * 8;
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
@@ -189,6 +233,8 @@ void tamcmc_gpu_rgb_destroy(tamcmc_gpu_rgb* h)
     if (h->d_out) cudaFree(h->d_out);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->d_slots) cudaFree(h->d_slots);
+    if (h->d_recs) cudaFree(h->d_recs);
+    if (h->d_vals) cudaFree(h->d_vals);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_ksi) cudaEventDestroy(h->ev_ksi);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -225,10 +271,8 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     // ---- stage 2 (device): pair loop + zeta normalisation of every exported chain ----
-    const size_t hdr_bytes = align16((size_t)h->max_chains * 16);
-    unsigned long long* h_norm = (unsigned long long*)h->h_out;
-    int* h_count = (int*)(h->h_out + (size_t)h->max_chains * 8);
-    int* h_flag = h_count + h->max_chains;
+    const size_t hdr_bytes = align16((size_t)h->max_chains * sizeof(OutHdr));
+    const OutHdr* h_hdr = (const OutHdr*)h->h_out;
     double* h_cand = (double*)(h->h_out + hdr_bytes);
     if (!T.ksi.empty()) {
         size_t off[6];
@@ -260,10 +304,14 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
         RGB_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, off[5], cudaMemcpyHostToDevice, h->stream));
         RGB_CUDA(cudaMemsetAsync(h->d_out, 0, hdr_bytes, h->stream));
         RGB_CUDA(cudaEventRecord(h->ev_in, h->stream));
-        unsigned long long* d_norm = (unsigned long long*)h->d_out;
-        int* d_count = (int*)(h->d_out + (size_t)h->max_chains * 8);
-        int* d_flag = d_count + h->max_chains;
+        OutHdr* d_hdr = (OutHdr*)h->d_out;
         double* d_cand = (double*)(h->d_out + hdr_bytes);
+        if ((size_t)T.nvals > h->vals_cap) {
+            if (h->d_vals) cudaFree(h->d_vals);
+            h->d_vals = nullptr;
+            h->vals_cap = (size_t)T.nvals + (size_t)T.nvals / 2 + 1024;
+            RGB_CUDA(cudaMalloc((void**)&h->d_vals, h->vals_cap * 8));
+        }
         {   // the zeta normalisation on its own stream: it does not depend on the pair loop
             int maxN = 0; size_t smem = 0;
             for (const KsiHdr& K : T.ksi) { if (K.Ndata > maxN) maxN = K.Ndata; const size_t s = (size_t)(3 * K.Lp + 2 * K.Lg) * 8; if (s > smem) smem = s; }
@@ -272,18 +320,32 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
             RGB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_in, 0));
             const dim3 grid((unsigned)((maxN + 127) / 128), (unsigned)T.ksi.size());
             tamcmc_rgb_ksi_max_kernel<<<grid, 128, smem, h->stream2>>>((const KsiHdr*)(h->d_in + off[2]), (const double*)(h->d_in + off[3]),
-                                                                       (const double*)(h->d_in + off[4]), d_norm);
+                                                                       (const double*)(h->d_in + off[4]), h->d_vals, d_hdr);
+            tamcmc_rgb_ksi_top_kernel<<<grid, 128, 0, h->stream2>>>((const KsiHdr*)(h->d_in + off[2]), h->d_vals, d_hdr);
             RGB_CUDA(cudaEventRecord(h->ev_ksi, h->stream2));
         }
         if (!T.pairs.empty()) {
             const int npairs = (int)T.pairs.size(), nbands = (int)T.bands.size();
             int lanes = 8;
-            for (const Band& B : T.bands) if (B.lanes > lanes) lanes = B.lanes;
+            for (const Band& B : T.bands) if (2 * B.nseg_est + 2 > lanes) lanes = 2 * B.nseg_est + 2;       // root + pole per segment
+            lanes = (lanes + 7) & ~7;
+            if (lanes > REC_CAP) lanes = REC_CAP;
+            const size_t cnt_bytes = align16((size_t)nbands * 4), rec_bytes = cnt_bytes + (size_t)nbands * REC_CAP * sizeof(Record);
+            if (rec_bytes > h->recs_cap) {
+                if (h->d_recs) cudaFree(h->d_recs);
+                h->d_recs = nullptr;
+                h->recs_cap = rec_bytes + rec_bytes / 2;
+                RGB_CUDA(cudaMalloc((void**)&h->d_recs, h->recs_cap));
+            }
+            int* d_nrec = (int*)h->d_recs;
+            Record* d_rec = (Record*)(h->d_recs + cnt_bytes);
+            RGB_CUDA(cudaMemsetAsync(h->d_recs, 0, cnt_bytes, h->stream));
             RGB_CUDA(cudaMemsetAsync(h->d_slots, 0xff, (size_t)T.nslots * 8, h->stream));
+            tamcmc_rgb_search_kernel<<<(unsigned)nbands, 64, 0, h->stream>>>((const Band*)(h->d_in + off[0]), d_rec, d_nrec, d_hdr);
             const long nthreads = (long)npairs * lanes;
             tamcmc_rgb_pairs_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, h->stream>>>(
-                (const Band*)(h->d_in + off[0]), (const Pair*)(h->d_in + off[1]), npairs, lanes, h->d_slots, d_flag);
-            tamcmc_rgb_compact_kernel<<<(unsigned)nbands, 128, 0, h->stream>>>((const Band*)(h->d_in + off[0]), h->d_slots, d_cand, h->cand_cap, d_count, d_flag);
+                (const Band*)(h->d_in + off[0]), (const Pair*)(h->d_in + off[1]), npairs, lanes, d_rec, d_nrec, h->d_slots, d_hdr);
+            tamcmc_rgb_compact_kernel<<<(unsigned)nbands, 128, 0, h->stream>>>((const Band*)(h->d_in + off[0]), h->d_slots, d_cand, h->cand_cap, d_hdr);
         }
         RGB_CUDA(cudaGetLastError());
         RGB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_ksi, 0));
@@ -291,20 +353,38 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
         RGB_CUDA(cudaStreamSynchronize(h->stream));
     }
     clock_gettime(CLOCK_MONOTONIC, &t2);
-    // ---- stage 3 (host, one chain per thread): the rest of the model function; flagged chains are solved by the host ----
+    // ---- stage 3 (host): the rest of the model function; flagged chains are solved by the host code ----
+    // 3a, one chain per thread: the exact zeta normalisation at the grid points the device found, and the mixed-mode frequencies
+    std::vector<int>& dev = h->on_device;
+    std::vector<double> norm((size_t)nchains, -1.0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < nchains; c++) {
+        if (status_out[c] != TAMCMC_OK) continue;
+        const OutHdr& O = h_hdr[c];
+        if (dev[(size_t)c] && (O.flag != 0 || O.count > h->cand_cap || O.ntop < 1)) { if (path_out) path_out[c] = O.flag ? O.flag : RGB_FLAG_NONFINITE; dev[(size_t)c] = 0; }
+        if (dev[(size_t)c]) {
+            if (O.ntop <= TOP_CAP) norm[(size_t)c] = ksi_norm_at(h->preps[(size_t)c], O.top, O.ntop);      // else: finish() takes the maximum itself
+            status_out[c] = finish_modes(h->preps[(size_t)c], true, h_cand + (size_t)c * h->cand_cap, O.count);
+            if (path_out) path_out[c] = 0;
+        }
+    }
+    // 3b, the zeta sums at the mixed modes: blocks of 8 frequencies of all chains over all threads
+    std::vector<std::pair<int, int>> blocks;
+    for (int c = 0; c < nchains; c++)
+        if (dev[(size_t)c] && status_out[c] == TAMCMC_OK)
+            for (int b = 0; b < ksi_blocks(h->preps[(size_t)c]); b++) blocks.push_back({c, b});
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long k = 0; k < (long)blocks.size(); k++) ksi_block_compute(h->preps[(size_t)blocks[(size_t)k].first], blocks[(size_t)k].second);
+    // 3c, one chain per thread: heights, widths, splittings, rows
 #pragma omp parallel for schedule(dynamic, 1)
     for (int c = 0; c < nchains; c++) {
         if (status_out[c] != TAMCMC_OK) continue;
         double* row = rows_out + (size_t)c * row_stride;
         int nm = 0;
-        double norm = 0.0;
-        if (h->on_device[(size_t)c]) std::memcpy(&norm, &h_norm[c], 8);
-        const bool dev = h->on_device[(size_t)c] && h_flag[c] == 0 && h_count[c] <= h->cand_cap && norm == norm && norm > 0.0;
-        if (dev) {
-            status_out[c] = finish(h->preps[(size_t)c], true, h_cand + (size_t)c * h->cand_cap, h_count[c], norm, capacity, row, &nm);
-            if (path_out) path_out[c] = 0;
+        if (dev[(size_t)c]) {
+            ksi_done(h->preps[(size_t)c]);
+            status_out[c] = finish(h->preps[(size_t)c], true, nullptr, 0, norm[(size_t)c], capacity, row, &nm);
         } else {
-            if (path_out) path_out[c] = h->on_device[(size_t)c] ? (h_flag[c] ? h_flag[c] : RGB_FLAG_NONFINITE) : -1;
             status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, false);
             if (status_out[c] == TAMCMC_OK) status_out[c] = finish(h->preps[(size_t)c], false, nullptr, 0, -1.0, capacity, row, &nm);
         }
@@ -347,14 +427,25 @@ int tamcmc_host_rgb_expand_emulated(int model_id, const double* params, const in
                 if (!ok) { flag |= RGB_FLAG_EXT; continue; }
                 if (lo != rlo || hi != rhi || !((rn < 2 && n < 2) || rn == (long)n)) flag |= 128;
             }
+        std::vector<std::vector<Record>> recs(T.bands.size());
+        for (size_t b = 0; b < T.bands.size(); b++) {
+            const Band& B = T.bands[b];
+            if (B.nband == 0 || B.rep_inv_g == 0.0) continue;
+            double m_hi = 0, nu0 = 0, bstep = 0;
+            const int nseg = pair_segments(B, B.rep_inv_g, m_hi, nu0, bstep, flag);
+            for (int j = 0; j < nseg; j++) {
+                auto emit = [&](const Record& R) { recs[b].push_back(R); };
+                if (exact_trig) pair_segment<TrigLib, TrigCR>(B, B.rep_inv_g, j, nseg, m_hi, nu0, bstep, emit, flag);
+                else pair_segment<TrigLib, TrigLib>(B, B.rep_inv_g, j, nseg, m_hi, nu0, bstep, emit, flag);
+            }
+            if ((int)recs[b].size() > REC_CAP) flag |= RGB_FLAG_OVERFLOW;
+        }
         for (const Pair& Q : T.pairs) {
             const Band& B = T.bands[(size_t)Q.band];
-            double m_hi = 0, nu0 = 0, bstep = 0;
-            const int nseg = pair_segments(B, Q.inv_g, m_hi, nu0, bstep, flag);
-            for (int j = 0; j < nseg; j++) {
-                auto emit = [&](int idx, double s) { double& v = slots[(size_t)(B.slot_off + idx)]; if (v < 0.0 || s < v) v = s; };
-                if (exact_trig) pair_segment<TrigLib, TrigCR>(B, Q.inv_g, j, nseg, m_hi, nu0, bstep, emit, flag);
-                else pair_segment<TrigLib, TrigLib>(B, Q.inv_g, j, nseg, m_hi, nu0, bstep, emit, flag);
+            for (const Record& R : recs[(size_t)Q.band]) {
+                double sol;
+                const bool got = exact_trig ? record_eval<TrigCR>(B, Q.inv_g, R, sol, flag) : record_eval<TrigLib>(B, Q.inv_g, R, sol, flag);
+                if (got) { double& v = slots[(size_t)(B.slot_off + R.idx)]; if (v < 0.0 || sol < v) v = sol; }
             }
         }
         for (double v : slots) if (v >= 0.0) cand.push_back(v);

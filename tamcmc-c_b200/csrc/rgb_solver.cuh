@@ -11,6 +11,14 @@
 // solver_mm.cpp:71-106).  Segments are independent: one thread each, no communication; their solutions are appended to the chain's
 // candidate list, which the host filters, sorts and makes unique exactly like the reference (solver_mm.cpp:575-590).
 //
+// Two phases.  The g modes of one p mode see the SAME function up to rounding (tan has period pi and 1/nu_g = (ng + alpha) DPl 1e-6): the same
+// sign changes at the same grid indices, each with its own last bits -- and the reference keeps the smallest solution of every cluster,
+// so every (p mode, g mode) version has to be evaluated, but the SEARCH is done once: phase 1 runs the segments of a band with the
+// band's first g mode and leaves one record per sign change (coarse index, local grid, which two local points the interpolation
+// uses); phase 2 evaluates every record for every g mode of the band -- two exact values of f, one line, one ratio test: uniform work,
+// no divergence.  Phase 1 flags the chain when a value it decides on is smaller than 1e-11 (another g mode's rounding could decide
+// otherwise); phase 2 checks the signs of its two values against the record.
+//
 // Arithmetic.  Every value that enters the interpolation is computed with the operations of the reference in its order (no FMA
 // contraction: this header is compiled with -fmad=false / -ffp-contract=off) and the correctly rounded tan / atan of dd_math.cuh;
 // searches only need the SIGN of f and use the fast library functions, re-evaluated exactly when |f| < 1e-9.  Anything the
@@ -33,6 +41,11 @@ struct TrigLib {
 
 #define TAMCMC_RGB_PI 3.141592653589793
 
+struct Record { double lo, hi; int idx, n, kind, i; };     // kind 0: f(i) < 0 < f(i+1) on the local grid; 1: line through points 0, 1; 2: through n-2, n-1
+
+enum { RGB_FLAG_NEAR = 256, RGB_FLAG_VERIFY = 512, RGB_FLAG_ZERO = 1, RGB_FLAG_SHAPE = 2, RGB_FLAG_POLES = 4, RGB_FLAG_RATIO = 8, RGB_FLAG_OVERFLOW = 16, RGB_FLAG_NONFINITE = 32, RGB_FLAG_EXT = 64 };
+
+
 // p(nu) - g(nu) as the VectorXd versions of pnu_fct / gnu_fct compute one element (solver_mm.cpp:114-161; host_rgb.cpp PminusG)
 template <class TR>
 TAMCMC_HD_CALL double pmg(const Band& B, double inv_g, double nu)
@@ -43,12 +56,15 @@ TAMCMC_HD_CALL double pmg(const Band& B, double inv_g, double nu)
     const double gnu = (B.Dnu * TR::atan_(t)) / TAMCMC_RGB_PI;
     return pnu - gnu;
 }
-// a value whose sign is the sign of the exact value
+// a value whose sign is the sign of the exact value -- for EVERY g mode of the band, or the chain is flagged
 template <class FAST, class EXACT>
-TAMCMC_HD double pmg_sign(const Band& B, double inv_g, double nu)
+TAMCMC_HD double pmg_sign(const Band& B, double inv_g, double nu, int& flag)
 {
     double v = pmg<FAST>(B, inv_g, nu);
-    if (!(fabs(v) > 1e-9)) v = pmg<EXACT>(B, inv_g, nu);
+    if (!(fabs(v) > 1e-9)) {
+        v = pmg<EXACT>(B, inv_g, nu);
+        if (!(fabs(v) > 1e-11)) flag |= RGB_FLAG_NEAR;
+    }
     return v;
 }
 TAMCMC_HD double u_of(const Band& B, double inv_g, double nu) { return (1.0 / nu - inv_g) * 1e6 / B.DPl; }
@@ -111,62 +127,82 @@ TAMCMC_HD bool local_grid_ext(double nu, double resol2 /* 2 resol */, double Dh,
     return true;
 }
 
-enum { RGB_FLAG_ZERO = 1, RGB_FLAG_SHAPE = 2, RGB_FLAG_POLES = 4, RGB_FLAG_RATIO = 8, RGB_FLAG_OVERFLOW = 16, RGB_FLAG_NONFINITE = 32, RGB_FLAG_EXT = 64 };
 
-// lin_interpol(f(nu_local), nu_local, 0) on linspaced(Nx, lo, hi) (host_rgb.cpp interp_zero_lazy), then the 0.1 % test (solver_mm.cpp:421-431)
+// phase 1: which two points of linspaced(Nx, lo, hi) does lin_interpol(f(nu_local), nu_local, 0) (tamcmc/sources/interpol.cpp:13-43; host_rgb.cpp
+// interp_zero_lazy) draw its line through?  false: nothing to evaluate (or the chain is flagged)
 template <class FAST, class EXACT>
-TAMCMC_HD bool local_solve(const Band& B, double inv_g, double lo, double hi, int Nx, double& sol, int& flag)
+TAMCMC_HD bool local_search(const Band& B, double inv_g, double lo, double hi, int Nx, int& kind, int& ibr, int& flag)
 {
     if (Nx < 2) return false;
     const double lstep = (hi - lo) / (double)(Nx - 1);
     auto y = [&](int i) { return (i == Nx - 1) ? hi : lo + (double)i * lstep; };
-    auto S = [&](int i) { return pmg_sign<FAST, EXACT>(B, inv_g, y(i)); };
-    auto E = [&](int i) { return pmg<EXACT>(B, inv_g, y(i)); };
+    auto S = [&](int i) { return pmg_sign<FAST, EXACT>(B, inv_g, y(i), flag); };
     const double X0 = S(0), XN = S(Nx - 1);
     if (!(X0 == X0) || !(XN == XN)) { flag |= RGB_FLAG_NONFINITE; return false; }
-    double a = 0.0, b = 0.0;
-    if (0.0 >= X0 && 0.0 <= XN) {
-        if (X0 == 0.0 || XN == 0.0) { flag |= RGB_FLAG_ZERO; return false; }
-        // the first i with f(i) <= 0 <= f(i+1): f rises except for a jump down at a pole of the tangent
-        const double uA = u_of(B, inv_g, y(0)), uB = u_of(B, inv_g, y(Nx - 1));          // uA > uB
-        const double mA = floor(uA - 0.5), mB = ceil(uB - 0.5);
-        if (!(mA - mB < 1.0)) { flag |= RGB_FLAG_POLES; return false; }                  // two poles (or not finite): the host's walk
-        int pts[7], np = 0;
-        pts[np++] = 0;
-        if (mA >= mB) {
-            const double nup = nu_of_u(B, inv_g, mA + 0.5);
-            const int il = (int)floor((nup - lo) / lstep);
-            for (int k = il - 1; k <= il + 2; k++) if (k > pts[np - 1] && k <= Nx - 1) pts[np++] = k;
-        }
-        if (Nx - 1 > pts[np - 1]) pts[np++] = Nx - 1;
-        int i = Nx - 2;
-        bool found = false;
-        double fa = X0;
-        for (int s = 0; s + 1 < np && !found; s++) {
-            const int pa = pts[s], pb = pts[s + 1];
-            const double fb = (pb == Nx - 1) ? XN : S(pb);
-            if (!(fb == fb) || fb == 0.0) { flag |= (fb == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return false; }
-            if (pb == pa + 1) {
-                if (fa < 0.0 && fb > 0.0) { i = pa; found = true; }
-            } else if (fa < 0.0 && fb > 0.0) {
-                int l = pa, h = pb;
-                while (h - l > 1) {
-                    const int mid = l + (h - l) / 2;
-                    const double v = S(mid);
-                    if (!(v == v) || v == 0.0) { flag |= (v == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return false; }
-                    if (v < 0.0) l = mid; else h = mid;
-                }
-                i = l; found = true;
-            } else if (fa > 0.0 && fb < 0.0) { flag |= RGB_FLAG_SHAPE; return false; }     // a stretch without a pole does not fall
-            fa = fb;
-        }
-        if (i > Nx - 2) i = Nx - 2;
-        const double Xi = E(i), Xi1 = E(i + 1);
-        a = (y(i + 1) - y(i)) / (Xi1 - Xi);
-        b = y(i) - a * Xi;
+    if (X0 == 0.0 || XN == 0.0) { flag |= RGB_FLAG_ZERO; return false; }
+    if (0.0 > XN) { kind = 2; ibr = Nx - 2; return true; }                    // the last assignment of lin_interpol wins
+    if (0.0 < X0) { kind = 1; ibr = 0; return true; }
+    // X0 < 0 < XN: the first i with f(i) <= 0 <= f(i+1); f rises except for a jump down at a pole of the tangent
+    const double uA = u_of(B, inv_g, y(0)), uB = u_of(B, inv_g, y(Nx - 1));          // uA > uB
+    const double mA = floor(uA - 0.5), mB = ceil(uB - 0.5);
+    if (!(mA - mB < 1.0)) { flag |= RGB_FLAG_POLES; return false; }                  // two poles (or not finite): the host's walk
+    int pts[7], np = 0;
+    pts[np++] = 0;
+    if (mA >= mB) {
+        const double nup = nu_of_u(B, inv_g, mA + 0.5);
+        const int il = (int)floor((nup - lo) / lstep);
+        for (int k = il - 1; k <= il + 2; k++) if (k > pts[np - 1] && k <= Nx - 1) pts[np++] = k;
     }
-    if (0.0 < X0 && !(0.0 > XN)) { const double Xa = E(0), Xb = E(1); a = (y(1) - y(0)) / (Xb - Xa); b = y(0) - a * Xa; }
-    if (0.0 > XN) { const double Xa = E(Nx - 1), Xb = E(Nx - 2); a = (y(Nx - 1) - y(Nx - 2)) / (Xa - Xb); b = y(Nx - 2) - a * Xb; }
+    if (Nx - 1 > pts[np - 1]) pts[np++] = Nx - 1;
+    int i = Nx - 2;
+    bool found = false;
+    double fa = X0;
+    for (int s = 0; s + 1 < np && !found; s++) {
+        const int pa = pts[s], pb = pts[s + 1];
+        const double fb = (pb == Nx - 1) ? XN : S(pb);
+        if (!(fb == fb) || fb == 0.0) { flag |= (fb == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return false; }
+        if (pb == pa + 1) {
+            if (fa < 0.0 && fb > 0.0) { i = pa; found = true; }
+        } else if (fa < 0.0 && fb > 0.0) {
+            int l = pa, h = pb;
+            while (h - l > 1) {
+                const int mid = l + (h - l) / 2;
+                const double v = S(mid);
+                if (!(v == v) || v == 0.0) { flag |= (v == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return false; }
+                if (v < 0.0) l = mid; else h = mid;
+            }
+            i = l; found = true;
+        } else if (fa > 0.0 && fb < 0.0) { flag |= RGB_FLAG_SHAPE; return false; }     // a stretch without a pole does not fall
+        fa = fb;
+    }
+    if (!found) { flag |= RGB_FLAG_SHAPE; return false; }
+    if (i > Nx - 2) i = Nx - 2;
+    kind = 0; ibr = i;
+    return true;
+}
+
+// phase 2: the line through the record's two local points with THIS g mode's exact values of f, its zero, and the 0.1 % test
+// (solver_mm.cpp:421-431).  The signs of the two values must be what the record's kind says they are.
+template <class EXACT>
+TAMCMC_HD bool record_eval(const Band& B, double inv_g, const Record& R, double& sol, int& flag)
+{
+    const int Nx = R.n;
+    const double lo = R.lo, hi = R.hi;
+    const double lstep = (hi - lo) / (double)(Nx - 1);
+    auto y = [&](int i) { return (i == Nx - 1) ? hi : lo + (double)i * lstep; };
+    const int i = R.i;
+    const double Xa = pmg<EXACT>(B, inv_g, y(i)), Xb = pmg<EXACT>(B, inv_g, y(i + 1));
+    double a, b;
+    if (R.kind == 0) {
+        if (!(Xa < 0.0 && Xb > 0.0)) { flag |= RGB_FLAG_VERIFY; return false; }
+        a = (y(i + 1) - y(i)) / (Xb - Xa); b = y(i) - a * Xa;
+    } else if (R.kind == 1) {
+        if (!(Xa > 0.0)) { flag |= RGB_FLAG_VERIFY; return false; }
+        a = (y(1) - y(0)) / (Xb - Xa); b = y(0) - a * Xa;
+    } else {
+        if (!(Xb < 0.0)) { flag |= RGB_FLAG_VERIFY; return false; }
+        a = (y(Nx - 1) - y(Nx - 2)) / (Xb - Xa); b = y(Nx - 2) - a * Xa;
+    }
     const double x_int = 0.0;
     const double nu_m = a * x_int + b;
     // g / p within 0.1 % of 1 (the reference evaluates g in long double; a ratio that close to a bound goes to the host)
@@ -193,13 +229,13 @@ TAMCMC_HD int pair_segments(const Band& B, double inv_g, double& m_hi, double& n
     return npoles + 1;
 }
 
-// segment j of a pair: emit(solution) for every accepted intersection
+// phase 1, segment j of a band (with the band's first g mode): emit(record) for every sign change that has something to evaluate
 template <class FAST, class EXACT, class Emit>
 TAMCMC_HD void pair_segment(const Band& B, double inv_g, int j, int nseg, double m_hi, double nu0, double bstep, Emit&& emit, int& flag)
 {
     const int nb = B.nband, npoles = nseg - 1;
     auto ip_of = [&](int k) { return (int)floor((nu_of_u(B, inv_g, (m_hi - (double)k) + 0.5) - nu0) / bstep); };
-    auto S = [&](int i) { return pmg_sign<FAST, EXACT>(B, inv_g, band_nu(B, i)); };
+    auto S = [&](int i) { return pmg_sign<FAST, EXACT>(B, inv_g, band_nu(B, i), flag); };
     int pts[7], np = 0;
     int start = 0;
     if (j > 0) { start = ip_of(j - 1) + 2; if (start < 0) start = 0; if (start > nb - 1) start = nb - 1; }
@@ -231,10 +267,10 @@ TAMCMC_HD void pair_segment(const Band& B, double inv_g, int j, int nseg, double
             }
         }
         if (idx >= 0) {
-            double sol, llo, lhi;
-            int ln;
-            if (!local_grid_ext(band_nu(B, idx), B.resol2, B.Dh, B.Dl, llo, lhi, ln)) { flag |= RGB_FLAG_EXT; return; }
-            if (local_solve<FAST, EXACT>(B, inv_g, llo, lhi, ln, sol, flag)) emit(idx, sol);
+            Record R;
+            R.idx = idx;
+            if (!local_grid_ext(band_nu(B, idx), B.resol2, B.Dh, B.Dl, R.lo, R.hi, R.n)) { flag |= RGB_FLAG_EXT; return; }
+            if (local_search<FAST, EXACT>(B, inv_g, R.lo, R.hi, R.n, R.kind, R.i, flag)) emit(R);
         }
         fa = fb;
     }
