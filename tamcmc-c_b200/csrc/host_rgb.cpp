@@ -872,6 +872,7 @@ bool export_task(const Prep* Pp, int chain, DeviceTask& T)
     if (!probe.usable()) return false;
     double kf0, kf1; int Ndata;
     if (!ksi_highres_grid(S.nu_p, S.nu_g, kf0, kf1, Ndata)) return false;
+    for (double d : S.dPg) if (d != S.dPg[0]) return false;                // (the device's zeta kernel relies on the common period spacing)
     const ld D = U.resol * (ld)U.fact;                                   // the local grids' step, as solver_mm forms it (solver_mm.cpp:406)
     const double Dh = (double)D, Dl = (double)(D - (ld)Dh);
     const size_t bands0 = T.bands.size();

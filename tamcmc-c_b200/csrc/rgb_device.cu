@@ -27,30 +27,141 @@ using namespace tamcmc_rgb;
 
 namespace {
 
-constexpr int KSI_PCHUNK = 8;      // p modes whose sums a thread of the zeta kernel carries in registers at a time
 constexpr unsigned long long SLOT_EMPTY = ~0ull;
 
 constexpr int TOP_CAP = 14;
 struct OutHdr { unsigned long long norm_bits; int count, flag, ntop, top[TOP_CAP], pad_; };     // per chain, 80 bytes
 constexpr int REC_CAP = 128;         // sign-change records per band (two or three per segment)
 
-// phase 1 (rgb_solver.cuh): the segments of every band, searched with the band's first g mode; one thread per segment
-__global__ void __launch_bounds__(64) tamcmc_rgb_search_kernel(const Band* __restrict__ bands, Record* __restrict__ recs, int* __restrict__ nrec,
-                                                               OutHdr* __restrict__ hdr)
+// ---- phase 1 (rgb_solver.cuh: pair_segment + local_search), one WARP per segment.  The scalar code bisects; a warp probes 32 points of
+// the bracket at once (f rises on it: the negative probes are a prefix), so a 1000-point stretch takes two rounds instead of ten dependent
+// evaluations.  Same decisions, same records (the host emulation runs the scalar code; the rows must come out identical).
+#define RGB_FULL 0xffffffffu
+
+// the l with f(l) < 0 < f(l+1) on a stretch where f rises from f(l0) < 0 to f(h0) > 0; -1 with a flag when a probe is zero, not finite,
+// or the signs are not a prefix
+template <class F>
+__device__ int warp_ksection(F&& S, int l, int h, int lane, int& flag)
+{
+    while (h - l > 1) {
+        const int span = h - l - 1;
+        const bool all = span > 32;
+        const int probe = all ? l + (int)(((long)(h - l) * (lane + 1)) / 33) : l + 1 + lane;
+        const bool valid = all || lane < span;
+        const double v = valid ? S(probe) : 1.0;
+        const bool bad = valid && (!(v == v) || v == 0.0 || fabs(v) > 1.0e300);
+        if (__any_sync(RGB_FULL, bad)) { flag |= RGB_FLAG_ZERO; return -1; }
+        const unsigned neg = __ballot_sync(RGB_FULL, valid && v < 0.0);
+        const int nneg = __popc(neg), nvalid = all ? 32 : span;
+        if (neg != ((nneg == 32) ? 0xffffffffu : ((1u << nneg) - 1u))) { flag |= RGB_FLAG_SHAPE; return -1; }
+        const int below = __shfl_sync(RGB_FULL, probe, (nneg > 0) ? nneg - 1 : 0);
+        const int above = __shfl_sync(RGB_FULL, probe, (nneg < 32) ? nneg : 31);
+        if (nneg > 0) l = below;
+        if (nneg < nvalid) h = above;
+    }
+    return l;
+}
+
+// values of f at up to 7 points, one lane each, returned to every lane; false with a flag when one is zero or not finite
+template <class F>
+__device__ bool warp_values(F&& S, const int* pts, int np, double* fv, int lane, int& flag)
+{
+    const double mine = (lane < np) ? S(pts[lane]) : 1.0;
+    const bool bad = lane < np && (!(mine == mine) || mine == 0.0 || fabs(mine) > 1.0e300);
+    if (__any_sync(RGB_FULL, bad)) { flag |= (mine == 0.0) ? RGB_FLAG_ZERO : RGB_FLAG_NONFINITE; return false; }
+#pragma unroll
+    for (int k = 0; k < 7; k++) fv[k] = __shfl_sync(RGB_FULL, mine, k);
+    return true;
+}
+
+__device__ void warp_local(const Band& B, double inv_g, int idx, Record* out, int* nrec, int lane, int& flag)
+{
+    Record R;
+    R.idx = idx; R.kind = 0; R.i = 0;
+    if (!local_grid_ext(band_nu(B, idx), B.resol2, B.Dh, B.Dl, R.lo, R.hi, R.n)) { flag |= RGB_FLAG_EXT; return; }
+    const int Nx = R.n;
+    if (Nx < 2) return;
+    const double lo = R.lo, hi = R.hi, lstep = (hi - lo) / (double)(Nx - 1);
+    auto y = [&](int i) { return (i == Nx - 1) ? hi : lo + (double)i * lstep; };
+    auto S = [&](int i) { return pmg_sign<TrigLib, TrigCR>(B, inv_g, y(i), flag); };
+    const double uA = u_of(B, inv_g, y(0)), uB = u_of(B, inv_g, y(Nx - 1));
+    const double mA = floor(uA - 0.5), mB = ceil(uB - 0.5);
+    const bool manypoles = !(mA - mB < 1.0);
+    int pts[7], np = 0;
+    pts[np++] = 0;
+    if (!manypoles && mA >= mB) {
+        const double nup = nu_of_u(B, inv_g, mA + 0.5);
+        const int il = (int)floor((nup - lo) / lstep);
+        for (int k = il - 1; k <= il + 2; k++) if (k > pts[np - 1] && k <= Nx - 1) pts[np++] = k;
+    }
+    if (Nx - 1 > pts[np - 1]) pts[np++] = Nx - 1;
+    double fv[7];
+    if (!warp_values(S, pts, np, fv, lane, flag)) return;
+    const double X0 = fv[0], XN = fv[np - 1];
+    bool emit = false;
+    if (0.0 > XN) { R.kind = 2; R.i = Nx - 2; emit = true; }                 // the last assignment of lin_interpol wins
+    else if (0.0 < X0) { R.kind = 1; R.i = 0; emit = true; }
+    else {
+        if (manypoles) { flag |= RGB_FLAG_POLES; return; }
+        for (int s = 0; s + 1 < np && !emit; s++) {
+            const int pa = pts[s], pb = pts[s + 1];
+            const double fa = fv[s], fb = fv[s + 1];
+            if (pb == pa + 1) { if (fa < 0.0 && fb > 0.0) { R.i = pa; emit = true; } }
+            else if (fa < 0.0 && fb > 0.0) {
+                const int l = warp_ksection(S, pa, pb, lane, flag);
+                if (l < 0) return;
+                R.i = l; emit = true;
+            } else if (fa > 0.0 && fb < 0.0) { flag |= RGB_FLAG_SHAPE; return; }
+        }
+        if (!emit) { flag |= RGB_FLAG_SHAPE; return; }
+        if (R.i > Nx - 2) R.i = Nx - 2;
+        R.kind = 0;
+    }
+    if (lane == 0) {
+        const int k = atomicAdd(nrec, 1);
+        if (k < REC_CAP) out[k] = R; else flag |= RGB_FLAG_OVERFLOW;
+    }
+}
+
+__global__ void __launch_bounds__(512) tamcmc_rgb_search_kernel(const Band* __restrict__ bands, Record* __restrict__ recs, int* __restrict__ nrec,
+                                                                OutHdr* __restrict__ hdr)
 {
     const Band B = bands[blockIdx.x];
     if (B.nband == 0 || B.rep_inv_g == 0.0) return;
+    const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5), nwarps = (int)(blockDim.x >> 5);
+    const double inv_g = B.rep_inv_g;
     int flag = 0;
     double m_hi = 0, nu0 = 0, bstep = 0;
-    const int nseg = pair_segments(B, B.rep_inv_g, m_hi, nu0, bstep, flag);
+    const int nseg = pair_segments(B, inv_g, m_hi, nu0, bstep, flag);
     Record* out = recs + (size_t)blockIdx.x * REC_CAP;
-    for (int j = threadIdx.x; j < nseg; j += blockDim.x)
-        pair_segment<TrigLib, TrigCR>(B, B.rep_inv_g, j, nseg, m_hi, nu0, bstep,
-                                      [&](const Record& R) {
-                                          const int k = atomicAdd(nrec + blockIdx.x, 1);
-                                          if (k < REC_CAP) out[k] = R; else flag |= RGB_FLAG_OVERFLOW;
-                                      },
-                                      flag);
+    const int nb = B.nband, npoles = nseg - 1;
+    auto ip_of = [&](int k) { return (int)floor((nu_of_u(B, inv_g, (m_hi - (double)k) + 0.5) - nu0) / bstep); };
+    auto S = [&](int i) { return pmg_sign<TrigLib, TrigCR>(B, inv_g, band_nu(B, i), flag); };
+    for (int j = warp; j < nseg; j += nwarps) {
+        int pts[7], np = 0, start = 0;
+        if (j > 0) { start = ip_of(j - 1) + 2; if (start < 0) start = 0; if (start > nb - 1) start = nb - 1; }
+        pts[np++] = start;
+        if (j < npoles) {
+            const int ip = ip_of(j);
+            for (int k = ip - 1; k <= ip + 2; k++) if (k > pts[np - 1] && k <= nb - 1) pts[np++] = k;
+        } else if (nb - 1 > pts[np - 1]) pts[np++] = nb - 1;
+        double fv[7];
+        if (!warp_values(S, pts, np, fv, lane, flag)) break;
+        bool stop = false;
+        for (int s = 0; s + 1 < np && !stop; s++) {
+            const int pa = pts[s], pb = pts[s + 1];
+            const double fa = fv[s], fb = fv[s + 1];
+            int idx = -1;
+            if (pb == pa + 1) {
+                if ((fb > 0.0 && fa < 0.0) || (fb < 0.0 && fa > 0.0)) idx = pa;            // the two tests of sign_change; no value is zero here
+            } else {
+                if (fa > 0.0 && fb < 0.0) { flag |= RGB_FLAG_SHAPE; stop = true; }
+                else if (fa < 0.0 && fb > 0.0) { idx = warp_ksection(S, pa, pb, lane, flag); if (idx < 0) stop = true; }
+            }
+            if (idx >= 0) warp_local(B, inv_g, idx, out, nrec + blockIdx.x, lane, flag);
+        }
+        if (stop) break;
+    }
     if (flag) atomicOr(&hdr[B.chain].flag, flag);
 }
 
@@ -107,54 +218,44 @@ __device__ __forceinline__ double fast_rcp(double d)          // 1 / d to ~1 ulp
     return __fma_rn(r, e, r);
 }
 
-// max over the 4-year-resolution grid of the zeta sums (bump_DP.cpp:126-163): sum over (np, ng) of ksi_fct1 (bump_DP.cpp:46-64),
-//   1 / (1 + (nd / qd) (cu2 / cd2)) = A / (A + B),  A = qd cd2 (per p mode), B = nd cu2 (per g mode),
-// in the reference's order (per np a sum over ng, then added to the total) but with ONE reciprocal per term instead of three divisions:
-// the maximum agrees with the host's to ~1e-15 relative -- it scales every zeta value alike, i.e. heights / widths / splittings of the
-// mixed modes move by that much; frequencies do not depend on it.
+// WHERE the zeta sums (bump_DP.cpp:126-163) are largest on the 4-year-resolution grid.  One term of the sum over (np, ng) is
+//   ksi_fct1 (bump_DP.cpp:46-64) = 1 / (1 + (nd / qd) (cu2 / cd2)) = A / (A + B),  A = qd cd2 (per p mode), B = nd cu2 (per g mode),
+//   cu2 = cos^2(pi 1e6 (1/nu - 1/nu_g) / DPl),  1/nu_g = (ng + alpha) DPl 1e-6:
+// cos^2 has period pi, so cu2 -- and with the common DPl, B -- is the SAME for every g mode up to rounding: the reference adds Lg copies of
+// each p mode's term.  The kernel evaluates Lg * sum_p A_p / (A_p + B_0) (Lp + 1 cosines and Lp reciprocals per grid point instead of
+// Lp + Lg and 3 Lp Lg): good to ~1e-13 relative, which is enough to say where the maximum is; the value that normalises the zeta function
+// is then summed by the host, term by term like the reference, at the grid points the next kernel lists.
 __global__ void __launch_bounds__(128) tamcmc_rgb_ksi_max_kernel(const KsiHdr* __restrict__ hdrs, const double* __restrict__ kp,
                                                                   const double* __restrict__ kg, double* __restrict__ vals, OutHdr* __restrict__ hdr)
 {
-    extern __shared__ double sm[];
     const KsiHdr H = hdrs[blockIdx.y];
-    if ((int)(blockIdx.x * blockDim.x) >= H.Ndata) return;
-    double* s_p = sm;                       // [Lp][3]: nu_p, Dnu_p, q Dnu_p
-    double* s_g = sm + 3 * H.Lp;            // [Lg][2]: 1 / nu_g, DPl
-    for (int k = threadIdx.x; k < 3 * H.Lp; k += blockDim.x) s_p[k] = kp[3 * (size_t)H.off_p + k];
-    for (int k = threadIdx.x; k < 2 * H.Lg; k += blockDim.x) s_g[k] = kg[2 * (size_t)H.off_g + k];
-    __syncthreads();
     const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if ((int)(blockIdx.x * blockDim.x) >= H.Ndata) return;
     double total = 0.0;
     if (i < H.Ndata) {
         // Eigen::VectorXd::LinSpaced(Ndata, fmin, fmax)[i]
         const double v = (H.Ndata == 1 || i == H.Ndata - 1) ? H.fmax : H.fmin + (double)i * ((H.fmax - H.fmin) / (double)(H.Ndata - 1));
         const double inv = 1.0 / v, sq = 1e-6 * (v * v);
-        for (int p0 = 0; p0 < H.Lp; p0 += KSI_PCHUNK) {
-            double A[KSI_PCHUNK], loc[KSI_PCHUNK];
-#pragma unroll
-            for (int k = 0; k < KSI_PCHUNK; k++) {
-                loc[k] = 0.0; A[k] = 0.0;
-                if (p0 + k < H.Lp) { const double c = cos((H.pi_d * (v - s_p[3 * (p0 + k)])) / s_p[3 * (p0 + k) + 1]); A[k] = s_p[3 * (p0 + k) + 2] * (c * c); }
-            }
-            for (int g = 0; g < H.Lg; g++) {
-                const double c = cos((H.c_up * (inv - s_g[2 * g])) / s_g[2 * g + 1]);
-                const double Bg = (sq * s_g[2 * g + 1]) * (c * c);
-#pragma unroll
-                for (int k = 0; k < KSI_PCHUNK; k++) if (p0 + k < H.Lp) loc[k] += A[k] * fast_rcp(A[k] + Bg);
-            }
-#pragma unroll
-            for (int k = 0; k < KSI_PCHUNK; k++) if (p0 + k < H.Lp) total += loc[k];
+        const double inv_g0 = kg[2 * (size_t)H.off_g], DPl0 = kg[2 * (size_t)H.off_g + 1];
+        const double cu = cos((H.c_up * (inv - inv_g0)) / DPl0);
+        const double B = (sq * DPl0) * (cu * cu);
+        for (int p = 0; p < H.Lp; p++) {
+            const double* P = kp + 3 * ((size_t)H.off_p + p);
+            const double c = cos((H.pi_d * (v - P[0])) / P[1]);
+            const double A = P[2] * (c * c);
+            total += A * fast_rcp(A + B);
         }
+        total *= (double)H.Lg;
+        vals[H.val_off + i] = total;
     }
     // the maximum does not depend on the order it is taken in; a NaN anywhere must survive (its bit pattern is above every finite value's)
     unsigned long long b = (unsigned long long)__double_as_longlong(total);
     if (total != total) b = 0x7ff8000000000000ull;
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o); b = (t > b) ? t : b; }
-    if (i < H.Ndata) vals[H.val_off + i] = total;
     if ((threadIdx.x & 31) == 0) atomicMax(&hdr[H.chain].norm_bits, b);
 }
 
-// the grid points whose (fast) sum is within 1e-12 of the maximum: the host evaluates those exactly and takes the maximum of that
+// the grid points whose (fast) sum is within 1e-9 of the maximum: the host evaluates those exactly and takes the maximum of that
 __global__ void __launch_bounds__(128) tamcmc_rgb_ksi_top_kernel(const KsiHdr* __restrict__ hdrs, const double* __restrict__ vals, OutHdr* __restrict__ hdr)
 {
     const KsiHdr H = hdrs[blockIdx.y];
@@ -162,7 +263,7 @@ __global__ void __launch_bounds__(128) tamcmc_rgb_ksi_top_kernel(const KsiHdr* _
     if (i >= H.Ndata) return;
     const double mx = __longlong_as_double((long long)hdr[H.chain].norm_bits);
     const double v = vals[H.val_off + i];
-    if (v >= mx * (1.0 - 1e-12)) {
+    if (v >= mx * (1.0 - 1e-9)) {
         const int k = atomicAdd(&hdr[H.chain].ntop, 1);
         if (k < TOP_CAP) hdr[H.chain].top[k] = i;
     }
@@ -313,13 +414,11 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
             RGB_CUDA(cudaMalloc((void**)&h->d_vals, h->vals_cap * 8));
         }
         {   // the zeta normalisation on its own stream: it does not depend on the pair loop
-            int maxN = 0; size_t smem = 0;
-            for (const KsiHdr& K : T.ksi) { if (K.Ndata > maxN) maxN = K.Ndata; const size_t s = (size_t)(3 * K.Lp + 2 * K.Lg) * 8; if (s > smem) smem = s; }
-            if (smem > 200 * 1024) return TAMCMC_ERR_ARG;
-            if (smem > 48 * 1024) RGB_CUDA(cudaFuncSetAttribute(tamcmc_rgb_ksi_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int maxN = 0;
+            for (const KsiHdr& K : T.ksi) if (K.Ndata > maxN) maxN = K.Ndata;
             RGB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_in, 0));
             const dim3 grid((unsigned)((maxN + 127) / 128), (unsigned)T.ksi.size());
-            tamcmc_rgb_ksi_max_kernel<<<grid, 128, smem, h->stream2>>>((const KsiHdr*)(h->d_in + off[2]), (const double*)(h->d_in + off[3]),
+            tamcmc_rgb_ksi_max_kernel<<<grid, 128, 0, h->stream2>>>((const KsiHdr*)(h->d_in + off[2]), (const double*)(h->d_in + off[3]),
                                                                        (const double*)(h->d_in + off[4]), h->d_vals, d_hdr);
             tamcmc_rgb_ksi_top_kernel<<<grid, 128, 0, h->stream2>>>((const KsiHdr*)(h->d_in + off[2]), h->d_vals, d_hdr);
             RGB_CUDA(cudaEventRecord(h->ev_ksi, h->stream2));
@@ -341,7 +440,7 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
             Record* d_rec = (Record*)(h->d_recs + cnt_bytes);
             RGB_CUDA(cudaMemsetAsync(h->d_recs, 0, cnt_bytes, h->stream));
             RGB_CUDA(cudaMemsetAsync(h->d_slots, 0xff, (size_t)T.nslots * 8, h->stream));
-            tamcmc_rgb_search_kernel<<<(unsigned)nbands, 64, 0, h->stream>>>((const Band*)(h->d_in + off[0]), d_rec, d_nrec, d_hdr);
+            tamcmc_rgb_search_kernel<<<(unsigned)nbands, 512, 0, h->stream>>>((const Band*)(h->d_in + off[0]), d_rec, d_nrec, d_hdr);
             const long nthreads = (long)npairs * lanes;
             tamcmc_rgb_pairs_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, h->stream>>>(
                 (const Band*)(h->d_in + off[0]), (const Pair*)(h->d_in + off[1]), npairs, lanes, d_rec, d_nrec, h->d_slots, d_hdr);
