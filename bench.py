@@ -323,6 +323,69 @@ def extra_c5_star_sharded(torch, dist, pkg, stream, flush, rank, world, local_ra
             "alg_tflops_this_rank": algorithmic_flops(pairs, 0.0, NBINS * len(mine), NCHAINS) * steps / (ms * 1e-3) / 1e12, "all_ok": ok}
 
 
+def extra_c4_red_giant(torch, dist, pkg, stream, flush, rank, world, local_rank, steps):
+    """BASELINE config C4 (configs[3]; C1 = configs[0] is the same model on 5 chains): red-giant mixed-mode fit, model 25
+    (model_RGB_asympt_aj_AppWidth_HarveyLike_v4, models.cpp:4684-5079) on the reference's fixture 10722175, 10 chains, from REFERENCE
+    PARAMETER VECTORS.  A step = the asymptotic mixed-mode solve of every chain (tamcmc_gpu_rgb_expand: pair loop + zeta normalisation on
+    the device, rows written into the context's staging block) + the batched evaluation (tamcmc_gpu_eval), host buffers in, logL out.
+    Single GPU (replicas only): every rank runs its own replica, rank 0 reports."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    O = _oracle.get()
+    synth = pkg.synth
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_rgb_vectors.npz"))
+    x, y = gold["x"], gold["y"]
+    step_x = x[2] - x[1]
+    cap, nch = 110, 10
+    rng = np.random.default_rng(1)
+    pl = gold["plength2"]
+    P = np.stack([gold["params2"].copy() for _ in range(nch)])
+    P[:, :int(pl[0])] *= 1.0 + 0.02 * rng.standard_normal((nch, 1))          # heights jittered like the chains of a run
+    nn = int(pl[8])
+    T = synth.tcoefs(nch, LAMBDA_T)
+    rows_host = np.stack([pkg.expand_rgb_v4(25, P[c], pl, step_x, cap)[0] for c in range(nch)])
+    rc, L_ref = O.mode_table_eval_chains(rows_host, nn, 1, x, y, T)
+    star = pkg.Star(synth.MODEL_MODE_TABLE, synth.mode_table_plength(cap, nn, 1), rows_host.shape[1], x, y)
+    with pkg.Context(star, nch, T, device=local_rank) as ctx, pkg.RgbExpander(25, pl, step_x, cap, nch, device=local_rank) as rx:
+        stage = ctx.params_staging()[0]
+        rows_d, nm, st, path = rx.expand(P)
+        fc_h = rows_host[:, 4 + nn:].reshape(nch, cap, 20)[:, :, 1]
+        fc_d = rows_d[:, 4 + nn:].reshape(nch, cap, 20)[:, :, 1]
+        for _ in range(3):
+            rx.expand(P, rows_out=stage)
+            L, cs = ctx.eval(stage)
+        err = float(np.max(np.abs(L[0] - L_ref) / np.abs(L_ref)))
+        acc = np.zeros(4)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            rx.expand(P, rows_out=stage)
+            tt = rx.timings()
+            acc += [tt["prepare_ms"], tt["device_ms"], tt["finish_ms"], tt["total_ms"]]
+            ctx.eval(stage)
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        # the evaluation alone (rows resolved, device-resident), and the same step with the host solver
+        d_rows = torch.tensor(ctx.pack_params([rows_host]), device="cuda")
+        d_L = torch.zeros(nch, dtype=torch.float64, device="cuda")
+        ev_ms = timed_device_steps(torch, None, stream, flush, max(steps, 50), lambda: ctx.eval_device(d_rows.data_ptr(), d_L.data_ptr(), stream=stream.cuda_stream)) / max(steps, 50)
+        nrep = 3
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            rr = np.stack([pkg.expand_rgb_v4(25, P[c], pl, step_x, cap)[0] for c in range(nch)])
+            ctx.eval(rr)
+        host_ms = (time.perf_counter() - t0) * 1e3 / nrep
+    return {"workload": "C4: red-giant mixed-mode fit (model_RGB_asympt_aj_AppWidth_HarveyLike_v4, reference fixture 10722175: %d bins, %d-%d modes per chain), "
+                        "%d chains, from reference parameter vectors" % (len(x), int(nm.min()), int(nm.max()), nch),
+            "n_gpus": 1, "value": nch / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms, "steps": steps,
+            "step": "tamcmc_gpu_rgb_expand (mixed-mode pair loop + zeta normalisation on the device, host before / after) + tamcmc_gpu_eval, host buffers",
+            "expand_ms": {"prepare_host": acc[0] / steps, "device": acc[1] / steps, "finish_host": acc[2] / steps, "total": acc[3] / steps},
+            "evaluation_only_device_resident": {"ms_per_step": ev_ms, "value": nch / (ev_ms * 1e-3)},
+            "same_step_with_host_solver": {"ms_per_step": host_ms, "value": nch / (host_ms * 1e-3), "host_threads": os.cpu_count()},
+            "chains_solved_on_device": int((path == 0).sum()), "all_ok": bool((st == 0).all() and (cs == 0).all()),
+            "fc_identical_to_host_solver": "%d of %d" % (int(((fc_h == fc_d) & (fc_h != 0)).sum()), int((fc_h != 0).sum())),
+            "rows_max_rel_diff_vs_host_solver": float(np.max(np.abs(rows_host - rows_d) / np.maximum(np.abs(rows_host), 1e-300))),
+            "max_rel_err_vs_oracle_logL": err, "parity_ok": bool(err < 1e-10)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,7 +394,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stars-per-gpu", type=int, default=1, help="independent C2 stars batched per launch on each GPU")
-    ap.add_argument("--no-extra", action="store_true", help="skip the C3 (bin-sharded) and C5 (256 stars) blocks of the JSON line")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 (bin-sharded), C5 (256 stars) and C4 (red giant) blocks of the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 50:
@@ -445,7 +508,10 @@ def main():
     ctx_main_params = None
     extra = {}
     if not args.no_extra:
-        for name, fn, st in (("c3_bin_sharded", extra_c3_bin_sharded, 200), ("c5_star_sharded", extra_c5_star_sharded, 20)):
+        for name, fn, st in (("c3_bin_sharded", extra_c3_bin_sharded, 200), ("c5_star_sharded", extra_c5_star_sharded, 20),
+                             ("c4_red_giant", extra_c4_red_giant, 200)):
+            if name == "c4_red_giant" and world > 1:
+                continue                     # replicas only: reported at N = 1
             try:
                 extra[name] = fn(torch, dist, pkg, stream, flush, rank, world, local_rank, st)
             except Exception as e:           # the headline line must survive a failing extra block

@@ -28,10 +28,10 @@ using namespace tamcmc_rgb;
 namespace {
 
 constexpr unsigned long long SLOT_EMPTY = ~0ull;
-
 constexpr int TOP_CAP = 14;
 struct OutHdr { unsigned long long norm_bits; int count, flag, ntop, top[TOP_CAP], pad_; };     // per chain, 80 bytes
 constexpr int REC_CAP = 128;         // sign-change records per band (two or three per segment)
+
 
 // ---- phase 1 (rgb_solver.cuh: pair_segment + local_search), one WARP per segment.  The scalar code bisects; a warp probes 32 points of
 // the bracket at once (f rises on it: the negative probes are a prefix), so a 1000-point stretch takes two rounds instead of ten dependent
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(512) tamcmc_rgb_search_kernel(const Band* __re
     const int nb = B.nband, npoles = nseg - 1;
     auto ip_of = [&](int k) { return (int)floor((nu_of_u(B, inv_g, (m_hi - (double)k) + 0.5) - nu0) / bstep); };
     auto S = [&](int i) { return pmg_sign<TrigLib, TrigCR>(B, inv_g, band_nu(B, i), flag); };
-    for (int j = warp; j < nseg; j += nwarps) {
+    for (int j = (int)blockIdx.y * nwarps + warp; j < nseg; j += nwarps * (int)gridDim.y) {       // (two CTAs per band: ~one segment per warp)
         int pts[7], np = 0, start = 0;
         if (j > 0) { start = ip_of(j - 1) + 2; if (start < 0) start = 0; if (start > nb - 1) start = nb - 1; }
         pts[np++] = start;
@@ -194,16 +194,28 @@ __global__ void __launch_bounds__(128) tamcmc_rgb_pairs_kernel(const Band* __res
     if (flag) atomicOr(&hdr[B.chain].flag, flag);
 }
 
-// the non-empty slots of every band -> the chain's candidate list (any order: the host sorts)
+// the non-empty slots of every band -> the chain's candidate list (any order: the host sorts).  One block per band: the block counts
+// its solutions in shared memory and reserves its range of the chain's list with ONE global atomic.
 __global__ void __launch_bounds__(128) tamcmc_rgb_compact_kernel(const Band* __restrict__ bands, const unsigned long long* __restrict__ slots,
                                                                   double* __restrict__ cand, int cand_cap, OutHdr* __restrict__ hdr)
 {
+    __shared__ int s_n, s_base;
+    __shared__ unsigned long long s_v[REC_CAP];
     const Band B = bands[blockIdx.x];
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     for (int i = threadIdx.x; i < B.nband; i += blockDim.x) {
         const unsigned long long v = slots[B.slot_off + i];
         if (v == SLOT_EMPTY) continue;
-        const int k = atomicAdd(&hdr[B.chain].count, 1);
-        if (k < cand_cap) cand[(size_t)B.chain * cand_cap + k] = __longlong_as_double((long long)v);
+        const int k = atomicAdd(&s_n, 1);
+        if (k < REC_CAP) s_v[k] = v;
+    }
+    __syncthreads();
+    const int n = s_n < REC_CAP ? s_n : REC_CAP;           // (a band has at most REC_CAP records, hence at most REC_CAP solutions)
+    if (threadIdx.x == 0) s_base = (n > 0) ? atomicAdd(&hdr[B.chain].count, n) : 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        if (s_base + k < cand_cap) cand[(size_t)B.chain * cand_cap + s_base + k] = __longlong_as_double((long long)s_v[k]);
         else atomicOr(&hdr[B.chain].flag, RGB_FLAG_OVERFLOW);
     }
 }
@@ -440,7 +452,7 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
             Record* d_rec = (Record*)(h->d_recs + cnt_bytes);
             RGB_CUDA(cudaMemsetAsync(h->d_recs, 0, cnt_bytes, h->stream));
             RGB_CUDA(cudaMemsetAsync(h->d_slots, 0xff, (size_t)T.nslots * 8, h->stream));
-            tamcmc_rgb_search_kernel<<<(unsigned)nbands, 512, 0, h->stream>>>((const Band*)(h->d_in + off[0]), d_rec, d_nrec, d_hdr);
+            tamcmc_rgb_search_kernel<<<dim3((unsigned)nbands, 2), 512, 0, h->stream>>>((const Band*)(h->d_in + off[0]), d_rec, d_nrec, d_hdr);
             const long nthreads = (long)npairs * lanes;
             tamcmc_rgb_pairs_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, h->stream>>>(
                 (const Band*)(h->d_in + off[0]), (const Pair*)(h->d_in + off[1]), npairs, lanes, d_rec, d_nrec, h->d_slots, d_hdr);
