@@ -24,6 +24,13 @@ ncu --set full --clock-control none --import-source on -k regex:tamcmc_expand_ke
 echo "ncu expand rc=$?"
 python profiles/bench_configs.py --configs c1,c4,c3,c5,env --steps 50 > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err
 cat $OUT/${TAG}_configs.jsonl | cut -c1-200
+# the red-giant set-up kernels (tamcmc_gpu_rgb_expand): launch list and one full capture of the two heavy ones, from the C4 config
+RCMD="python profiles/bench_configs.py --configs c4 --steps 4"
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:tamcmc_rgb -c 40 --csv --log-file $OUT/${TAG}_rgb_launches.csv $RCMD > $OUT/${TAG}_ncu_rgb_launches.log 2>&1
+echo "ncu rgb launches rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k "regex:tamcmc_rgb_pairs_kernel|tamcmc_rgb_search_kernel" -s 4 -c 2 -f -o $OUT/${TAG}_rgb $RCMD > $OUT/${TAG}_ncu_rgb.log 2>&1
+echo "ncu rgb full rc=$?"
+timeout 200 python profiles/l2_modes.py > $OUT/${TAG}_l2_modes.json 2> $OUT/${TAG}_l2_modes.err; cat $OUT/${TAG}_l2_modes.json
 python profiles/far_accuracy.py > $OUT/${TAG}_far_accuracy.json 2> $OUT/${TAG}_far_accuracy.err; head -c 600 $OUT/${TAG}_far_accuracy.json
 TAMCMC_GPU_LIB=$PWD/tamcmc-c_b200/libtamcmc_gpu_trace.so timeout 120 python profiles/trace_timeline.py > $OUT/${TAG}_trace.txt 2>&1; tail -14 $OUT/${TAG}_trace.txt | cut -c1-160
 python __graft_entry__.py smoke 2>&1 | tail -2

@@ -119,6 +119,65 @@ def test_segment_decomposition_reproduces_the_host_solver(pkg, model_id):
     assert n >= 10
 
 
+def _synthetic_giants(G, ntrials, seed=11):
+    """other stars than the fixture: large separations of 3-18 microHz, period spacings of 60-95 s, couplings of 0.05-0.5, coarser and finer
+    spectra, both solver entry points and the three bias settings -- built on the fixture's parameter layout"""
+    rng = np.random.default_rng(seed)
+    pl, base = G["plength0"], G["params0"]
+    step = G["x"][2] - G["x"][1]
+    Nmax, lmax, Nfl0, Nfl1, Nfl2, Nfl3 = [int(v) for v in pl[:6]]
+    o0 = Nmax + lmax
+    o1 = o0 + Nfl0
+    o2 = o1 + Nfl1
+    o3 = o2 + Nfl2
+    for trial in range(ntrials):
+        p = base.copy()
+        Dnu = rng.uniform(3.0, 18.0)
+        numax = (Dnu / 0.267) ** (1 / 0.764)
+        n0 = int(numax / Dnu) - Nmax // 2
+        fl0 = (n0 + np.arange(Nmax) + rng.uniform(0.8, 1.3)) * Dnu + rng.normal(size=Nmax) * 0.01 * Dnu
+        p[o0:o0 + Nfl0] = fl0
+        p[o1] = rng.normal() * 0.02 * Dnu / 9
+        p[o1 + 1], p[o1 + 2], p[o1 + 3] = rng.uniform(60, 95), rng.uniform(0, 1), rng.uniform(0.05, 0.5)
+        Nferr = int(p[-1])
+        p[o1 + 8:o1 + 8 + Nferr] = np.linspace(fl0.min() - Dnu, fl0.max() + Dnu, Nferr)
+        p[o1 + 8 + Nferr:o1 + 8 + 2 * Nferr] = rng.normal(size=Nferr) * 0.02
+        if Nfl2 <= Nmax:
+            p[o2:o2 + Nfl2] = fl0[:Nfl2] - 0.12 * Dnu
+        if Nfl3 <= Nmax:
+            p[o3:o3 + Nfl3] = fl0[:Nfl3] + 0.2 * Dnu
+        p[-3], p[-2] = trial % 2, trial % 3
+        yield trial, p, pl, step * rng.choice([1.0, 1.0, 0.5, 2.0])
+
+
+def test_segment_decomposition_on_other_stars(pkg):
+    G = np.load(GOLD)
+    n = 0
+    for trial, p, pl, stp in _synthetic_giants(G, 12):
+        for model_id in (25, 27):
+            try:
+                row, nm = pkg.expand_rgb_v4(model_id, p, pl, stp, 400)
+            except pkg.TamcmcError:
+                continue
+            for exact in (0, 1):
+                try:
+                    r, nm2, fl = pkg.expand_rgb_v4_emulated(model_id, p, pl, stp, 400, exact_trig=exact)
+                except pkg.TamcmcError:
+                    continue                          # flagged part-way (e.g. poles a few grid steps apart): the device path hands the chain to the host
+                if fl:
+                    continue
+                assert nm2 == nm
+                nn = int(pl[8])
+                a, b = row[4 + nn:4 + nn + 20 * nm].reshape(nm, 20), r[4 + nn:4 + nn + 20 * nm].reshape(nm, 20)
+                if exact == 0:
+                    assert np.array_equal(r, row), trial
+                else:
+                    assert np.all(np.abs(a[:, 1] - b[:, 1]) <= np.spacing(a[:, 1])) and np.mean(a[:, 1] == b[:, 1]) > 0.95
+                    np.testing.assert_allclose(b, a, rtol=1e-12, atol=0)
+                n += 1
+    assert n >= 30
+
+
 def test_gpu_rgb_symbols_fail_loudly_without_a_device(pkg):
     import torch
     if torch.cuda.is_available():
@@ -159,6 +218,36 @@ def test_gpu_rgb_expand_matches_host_expander(pkg, model_id):
         np.testing.assert_allclose(b, a, rtol=1e-12, atol=0)
         assert np.array_equal(rows[i, :4 + nn], row[:4 + nn])
     assert ndev >= len(cases) - 1                                                          # the device path is the one that ran
+
+
+@pytest.mark.gpu
+def test_gpu_rgb_expand_on_other_stars(pkg):
+    """the synthetic giants of the CPU test through the kernels, chains with different numbers of modes in one call"""
+    G = np.load(GOLD)
+    cases = list(_synthetic_giants(G, 12))
+    pl = cases[0][2]
+    by_step = {}
+    for trial, p, _, stp in cases:
+        by_step.setdefault(float(stp), []).append(p)
+    nn = int(pl[8])
+    ndev = ntot = 0
+    for stp, plist in by_step.items():
+        P = np.stack(plist)
+        with pkg.RgbExpander(25, pl, stp, 400, len(plist)) as rx:
+            rows, nm, st, path = rx.expand(P)
+        for i, p in enumerate(plist):
+            try:
+                row, n = pkg.expand_rgb_v4(25, p, pl, stp, 400)
+            except pkg.TamcmcError as e:
+                assert st[i] == e.status
+                continue
+            assert st[i] == 0 and nm[i] == n
+            a, b = row[4 + nn:4 + nn + 20 * n].reshape(n, 20), rows[i, 4 + nn:4 + nn + 20 * n].reshape(n, 20)
+            assert np.all(np.abs(a[:, 1] - b[:, 1]) <= np.spacing(a[:, 1]))
+            np.testing.assert_allclose(b, a, rtol=1e-12, atol=0)
+            ndev += int(path[i] == 0)
+            ntot += 1
+    assert ntot >= 10 and ndev >= ntot - 3
 
 
 @pytest.mark.gpu
