@@ -469,8 +469,13 @@ void ksi_sum_block(long b, const vec& nu, const vec& nu_p, const vec& Dnu_p, con
     W.cu2.resize(Lg * KSI_W); W.cd2.resize(Lp * KSI_W); W.nd.resize(Lg * KSI_W);
     double tot[KSI_W];
     for (int w = 0; w < KSI_W; w++) {
-        const long i = std::min(b * KSI_W + w, N - 1);           // (the last block repeats the last frequency in its spare lanes)
-        const double v = nu[(size_t)i];
+        const long i = b * KSI_W + w;
+        if (i > N - 1 && w > 0) {                                // the last block repeats its last frequency in the spare lanes (copied, not recomputed)
+            for (size_t g = 0; g < Lg; g++) { W.cu2[g * KSI_W + w] = W.cu2[g * KSI_W + w - 1]; W.nd[g * KSI_W + w] = W.nd[g * KSI_W + w - 1]; }
+            for (size_t p = 0; p < Lp; p++) W.cd2[p * KSI_W + w] = W.cd2[p * KSI_W + w - 1];
+            continue;
+        }
+        const double v = nu[(size_t)std::min(i, N - 1)];
         const double inv = 1.0 / v, sq = 1e-6 * (v * v);
         for (size_t g = 0; g < Lg; g++) { const double c = std::cos((K.c_up * (inv - K.inv_g[g])) / DPl[g]); W.cu2[g * KSI_W + w] = c * c; W.nd[g * KSI_W + w] = sq * DPl[g]; }
         for (size_t p = 0; p < Lp; p++) { const double c = std::cos((K.pi_d * (v - nu_p[p])) / Dnu_p[p]); W.cd2[p * KSI_W + w] = c * c; }
