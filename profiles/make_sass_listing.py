@@ -22,7 +22,7 @@ def main():
     out = os.path.join(ROOT, "profiles", tag, "sass")
     os.makedirs(out, exist_ok=True)
     summary = []
-    for obj in ("expand.o", "whittle.o"):
+    for obj in ("expand.o", "whittle.o", "whittle_tiles.o", "rgb_device.o"):
         txt = subprocess.run(["cuobjdump", "-sass", os.path.join(BUILD, obj)], stdout=subprocess.PIPE, text=True, check=True).stdout
         cur, body = None, collections.OrderedDict()
         for line in txt.splitlines():

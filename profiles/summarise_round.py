@@ -18,7 +18,8 @@ src = os.path.join(ROOT, "gpurun_out")
 dst = os.path.join(ROOT, "profiles", rnd)
 os.makedirs(dst, exist_ok=True)
 for a, b in (("bench.json", "bench_default.json"), ("bench_reference.json", "bench_reference.json"), ("configs.jsonl", "bench_configs.jsonl"),
-             ("launches.csv", "launches_bench_steps5.csv"), ("trace.txt", "trace_timeline.txt")):
+             ("launches.csv", "launches_bench_steps5.csv"), ("trace.txt", "trace_timeline.txt"), ("l2_modes.json", "l2_modes.json"),
+             ("rgb_launches.csv", "launches_rgb_c4.csv")):
     p = os.path.join(src, "%s_%s" % (tag, a))
     if os.path.exists(p):
         shutil.copy(p, os.path.join(dst, b))
@@ -48,6 +49,31 @@ if os.path.exists(p):
         for k, v in step.items():
             f.write("  %-48s %5.1f %%\n" % (k, 100 * (v[1] / v[0]) / tot))
     print(open(os.path.join(dst, "launch_shares.txt")).read())
+
+# ---- the red-giant set-up kernels (tamcmc_gpu_rgb_expand, C4): launch list and the full capture of the search / pairs kernels ----
+p = os.path.join(src, tag + "_rgb_launches.csv")
+if os.path.exists(p):
+    rows = list(csv.reader(open(p)))
+    h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr, body = rows[h], rows[h + 1:]
+    ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in body:
+        if len(r) > iv:
+            k = r[ik].split("(")[0].split("::")[-1]
+            agg.setdefault(k, [0, 0.0])
+            agg[k][0] += 1
+            agg[k][1] += float(r[iv])
+    with open(os.path.join(dst, "launch_shares_rgb_c4.txt"), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -k regex:tamcmc_rgb, command: python profiles/bench_configs.py --configs c4 --steps 4\n")
+        f.write("one tamcmc_gpu_rgb_expand call (10 chains) = ksi_max + ksi_top on one stream, search + pairs + compact on the other\n\n")
+        for k, v in agg.items():
+            f.write("%-40s launches %4d  avg %9.2f us\n" % (k, v[0], v[1] / v[0] / 1e3))
+    print(open(os.path.join(dst, "launch_shares_rgb_c4.txt")).read())
+rep = os.path.join(src, tag + "_rgb.ncu-rep")
+if os.path.exists(rep):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "ncu_summary.py"), rep], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    open(os.path.join(dst, "rgb_ncu_full_summary.txt"), "w").write(out)
 
 # ---- full capture of the expander ----
 rep = os.path.join(src, tag + "_expand.ncu-rep")
