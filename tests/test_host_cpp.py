@@ -83,6 +83,55 @@ def test_cpp_mirror_matches_oracle(pkg, oracle, tmp_path):
     assert r.returncode == 0, r.stdout
 
 
+def _build_rgb():
+    exe = os.path.join(HERE, "cpp", "test_model_def_rgb")
+    src = os.path.join(HERE, "cpp", "test_model_def_rgb.cpp")
+    deps = [src, os.path.join(LIBDIR, "host", "model_def_rgb.hpp"), os.path.join(LIBDIR, "host", "model_def_gpu.hpp"), os.path.join(ROOT, "include", "tamcmc_gpu.h")]
+    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(d) for d in deps):
+        return exe
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", exe, src, "-L" + LIBDIR, "-ltamcmc_gpu",
+                           "-L" + cuda_lib, "-lcudart", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath," + cuda_lib])
+    return exe
+
+
+def test_cpp_rgb_mirror_builds_and_fails_loudly_without_gpu(pkg):
+    pkg.lib()
+    exe = _build_rgb()
+    if _have_gpu():
+        pytest.skip("CUDA device present: covered by the gpu-marked test")
+    r = subprocess.run([exe, "nogpu"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "status 3" in r.stdout, r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_rgb_mirror_matches_reference(pkg, oracle, tmp_path):
+    """ModelDefRGB (host/model_def_rgb.hpp): reference parameter vectors of the red-giant fixture -> device set-up + evaluation, against
+    the oracle's log-likelihoods of the host expander's rows and the spectrum the REFERENCE's model function returned."""
+    exe = _build_rgb()
+    G = np.load(os.path.join(HERE, "golden", "reference_rgb_vectors.npz"))
+    x, y = G["x"], G["y"]
+    pl = G["plength0"]
+    cases = [0, 1, 2, 3, 0]
+    assert all(np.array_equal(pl, G["plength%d" % i]) for i in cases)
+    P = np.stack([G["params%d" % i] for i in cases])
+    P[4, :int(pl[0])] *= 1.03
+    Nmodels, cap, nn = len(cases), 120, int(pl[8])
+    T = pkg.synth.tcoefs(Nmodels, 3.5)
+    rows = np.stack([pkg.expand_rgb_v4(25, P[m], pl, x[2] - x[1], cap)[0] for m in range(Nmodels)])
+    rc, L = oracle.mode_table_eval_chains(rows, nn, 1, x, y, T)
+    assert rc == 0
+    logPrior = np.array([-2.0, -np.inf, 0.0, -1.0, -0.5])
+    f = tmp_path / "case.bin"
+    hdr = np.concatenate([[25, len(x), Nmodels, P.shape[1], cap], pl.astype(float)])
+    with open(f, "wb") as fh:
+        for a in (hdr, x, y, T, P.ravel(), logPrior, L, G["model0"]):
+            fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    r = subprocess.run([exe, str(f)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    print(r.stdout)
+    assert r.returncode == 0 and "model_def_rgb: ok" in r.stdout, r.stdout
+
+
 def test_cpp_driver_builds(pkg):
     pkg.lib()
     _build_driver()
