@@ -363,6 +363,7 @@ def extra_c4_red_giant(torch, dist, pkg, stream, flush, rank, world, local_rank,
             acc += [tt["prepare_ms"], tt["device_ms"], tt["finish_ms"], tt["total_ms"]]
             ctx.eval(stage)
         ms = (time.perf_counter() - t0) * 1e3 / steps
+        n_setups, n_host = rx.counts()
         # the evaluation alone (rows resolved, device-resident), and the same step with the host solver
         d_rows = torch.tensor(ctx.pack_params([rows_host]), device="cuda")
         d_L = torch.zeros(nch, dtype=torch.float64, device="cuda")
@@ -380,7 +381,7 @@ def extra_c4_red_giant(torch, dist, pkg, stream, flush, rank, world, local_rank,
             "expand_ms": {"prepare_host": acc[0] / steps, "device": acc[1] / steps, "finish_host": acc[2] / steps, "total": acc[3] / steps},
             "evaluation_only_device_resident": {"ms_per_step": ev_ms, "value": nch / (ev_ms * 1e-3)},
             "same_step_with_host_solver": {"ms_per_step": host_ms, "value": nch / (host_ms * 1e-3), "host_threads": os.cpu_count()},
-            "chains_solved_on_device": int((path == 0).sum()), "all_ok": bool((st == 0).all() and (cs == 0).all()),
+            "chains_solved_on_device": int((path == 0).sum()), "chain_setups_total": n_setups, "chain_setups_handed_to_host_solver": n_host, "all_ok": bool((st == 0).all() and (cs == 0).all()),
             "fc_identical_to_host_solver": "%d of %d" % (int(((fc_h == fc_d) & (fc_h != 0)).sum()), int((fc_h != 0).sum())),
             "rows_max_rel_diff_vs_host_solver": float(np.max(np.abs(rows_host - rows_d) / np.maximum(np.abs(rows_host), 1e-300))),
             "max_rel_err_vs_oracle_logL": err, "parity_ok": bool(err < 1e-10)}

@@ -270,6 +270,8 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb *h, int model_id, const double *params,
                           int nchains, int capacity, double *rows_out, int row_stride, int *nmodes_out, int *status_out, int *path_out);
 /* host-clock milliseconds of the last tamcmc_gpu_rgb_expand: prepare (host), device (copies, two kernels, sync), finish (host), total */
 void tamcmc_gpu_rgb_timings(const tamcmc_gpu_rgb *h, double out[4]);
+/* chain set-ups asked for since create, and how many of them were handed to the host solver (path_out != 0) */
+void tamcmc_gpu_rgb_counts(const tamcmc_gpu_rgb *h, long *chains_total, long *chains_host);
 const char *tamcmc_gpu_rgb_last_error(void);
 /* TEST HOOK, no GPU: the device solver's segment decomposition (csrc/rgb_solver.cuh) run on the host for one chain, with glibc's tan / atan
  * (exact_trig = 0: reproduces tamcmc_host_expand_rgb_v4 bit for bit) or the double-double ones the device uses (1).  *flags_out: the flag

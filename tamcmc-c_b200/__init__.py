@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "tamcmc_gpu_exchange_create", "tamcmc_gpu_exchange_attach", "tamcmc_gpu_exchange_attach_ptrs", "tamcmc_gpu_exchange_buffer",
     "tamcmc_host_alm", "tamcmc_host_expand_ajAlm",
     "tamcmc_host_expand_rgb_v4", "tamcmc_host_armm_solve_from_l0", "tamcmc_host_armm_solve_O2p", "tamcmc_host_spline_eval",
-    "tamcmc_gpu_rgb_create", "tamcmc_gpu_rgb_destroy", "tamcmc_gpu_rgb_expand", "tamcmc_gpu_rgb_timings", "tamcmc_gpu_rgb_last_error",
+    "tamcmc_gpu_rgb_create", "tamcmc_gpu_rgb_destroy", "tamcmc_gpu_rgb_expand", "tamcmc_gpu_rgb_timings", "tamcmc_gpu_rgb_counts", "tamcmc_gpu_rgb_last_error",
     "tamcmc_host_rgb_expand_emulated",
     "tamcmc_alm_grids_load", "tamcmc_alm_grids_free", "tamcmc_alm_grids_eval", "tamcmc_alm_grids_shape", "tamcmc_alm_grids_nodes",
     "tamcmc_alm_grids_make", "tamcmc_alm_grids_last_error",
@@ -147,6 +147,8 @@ def lib():
     L.tamcmc_gpu_rgb_timings.restype = None
     L.tamcmc_gpu_rgb_timings.argtypes = [C.c_void_p, _dp]
     L.tamcmc_gpu_rgb_last_error.restype = C.c_char_p
+    L.tamcmc_gpu_rgb_counts.restype = None
+    L.tamcmc_gpu_rgb_counts.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]
     L.tamcmc_host_rgb_expand_emulated.restype = C.c_int
     L.tamcmc_host_rgb_expand_emulated.argtypes = [C.c_int, _dp, _ip, C.c_double, C.c_int, _dp, _ip, C.c_int, _ip]
     L.tamcmc_host_armm_solve_from_l0.restype = C.c_int
@@ -533,6 +535,12 @@ class RgbExpander:
         t = np.zeros(4)
         lib().tamcmc_gpu_rgb_timings(self.h, t.ctypes.data_as(_dp))
         return dict(prepare_ms=t[0], device_ms=t[1], finish_ms=t[2], total_ms=t[3])
+
+    def counts(self):
+        """(chain set-ups asked for, of which handed to the host solver) since this expander was created"""
+        a, b = C.c_long(0), C.c_long(0)
+        lib().tamcmc_gpu_rgb_counts(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def close(self):
         if self.h:

@@ -306,6 +306,7 @@ struct tamcmc_gpu_rgb {
     DeviceTask task;
     std::vector<int> on_device;
     double last_ms[4] = {0, 0, 0, 0};      // prepare, device, finish, total of the last call (host clock)
+    long chains_total = 0, chains_host = 0; // chain set-ups asked for / handed to the host solver since create
 };
 
 extern "C" {
@@ -501,6 +502,7 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
         }
         if (nmodes_out) nmodes_out[c] = nm;
     }
+    for (int c = 0; c < nchains; c++) { h->chains_total++; if (!dev[(size_t)c] && status_out[c] == TAMCMC_OK) h->chains_host++; }
     clock_gettime(CLOCK_MONOTONIC, &t3);
     auto ms = [](const timespec& a, const timespec& b) { return 1e3 * (double)(b.tv_sec - a.tv_sec) + 1e-6 * (double)(b.tv_nsec - a.tv_nsec); };
     h->last_ms[0] = ms(t0, t1); h->last_ms[1] = ms(t1, t2); h->last_ms[2] = ms(t2, t3); h->last_ms[3] = ms(t0, t3);
@@ -511,6 +513,14 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
 void tamcmc_gpu_rgb_timings(const tamcmc_gpu_rgb* h, double out[4])
 {
     for (int k = 0; k < 4; k++) out[k] = h ? h->last_ms[k] : 0.0;
+}
+
+// how many chain set-ups this handle was asked for, and how many of them the device flagged and the host solver of the library produced
+// (reported per call in path_out as well): the device path is the one that runs, and a caller can show it
+void tamcmc_gpu_rgb_counts(const tamcmc_gpu_rgb* h, long* chains_total, long* chains_host)
+{
+    if (chains_total) *chains_total = h ? h->chains_total : 0;
+    if (chains_host) *chains_host = h ? h->chains_host : 0;
 }
 
 // TEST HOOK (no GPU needed): the segment decomposition of rgb_solver.cuh run on the host for ONE chain, with glibc's tan / atan
