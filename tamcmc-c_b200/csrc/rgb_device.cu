@@ -293,25 +293,189 @@ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 }  // namespace
 
-struct tamcmc_gpu_rgb {
-    int device = 0, max_chains = 0, cand_cap = 0;
+// One group of chains in flight: its own buffers and streams, so that the host can finish one group while the device solves the other
+struct RgbGroup {
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_in = nullptr, ev_ksi = nullptr;
     char* h_in = nullptr; char* d_in = nullptr; size_t in_cap = 0;
-    char* h_out = nullptr; char* d_out = nullptr; size_t out_bytes = 0;
+    char* h_out = nullptr; char* d_out = nullptr;
     unsigned long long* d_slots = nullptr; size_t slots_cap = 0;
     double* d_vals = nullptr; size_t vals_cap = 0;        // zeta sums over the normalisation grids
     char* d_recs = nullptr; size_t recs_cap = 0;          // [bands] record counts, then [bands][REC_CAP] records
-    std::vector<Prep*> preps;
     DeviceTask task;
+    int c0 = 0, c1 = 0;                                    // chains [c0, c1) of the call
+    bool launched = false;
+};
+
+struct tamcmc_gpu_rgb {
+    int device = 0, max_chains = 0, cand_cap = 0;
+    size_t out_bytes = 0;
+    RgbGroup grp[2];
+    std::vector<Prep*> preps;
+    std::vector<DeviceTask> chain_task;    // one per chain, filled by the chain's own thread, then concatenated per group
     std::vector<int> on_device;
-    double last_ms[4] = {0, 0, 0, 0};      // prepare, device, finish, total of the last call (host clock)
+    double last_ms[4] = {0, 0, 0, 0};      // prepare, device (enqueue + first wait), finish, total of the last call (host clock)
     long chains_total = 0, chains_host = 0; // chain set-ups asked for / handed to the host solver since create
 };
+
+namespace {
+
+// chains [G.c0, G.c1): concatenate their tasks, copy them in, launch the kernels and the copy back; nothing waits here
+int rgb_enqueue(tamcmc_gpu_rgb* h, RgbGroup& G)
+{
+    DeviceTask& T = G.task;
+    T.clear();
+    G.launched = false;
+    for (int c = G.c0; c < G.c1; c++) {
+        if (!h->on_device[(size_t)c]) continue;
+        const DeviceTask& Tc = h->chain_task[(size_t)c];
+        const int band0 = (int)T.bands.size(), p0 = (int)(T.kp.size() / 3), g0 = (int)(T.kg.size() / 2);
+        for (Band B : Tc.bands) { B.slot_off += T.nslots; T.bands.push_back(B); }
+        for (Pair Q : Tc.pairs) { Q.band += band0; T.pairs.push_back(Q); }
+        for (KsiHdr K : Tc.ksi) { K.off_p += p0; K.off_g += g0; K.val_off += T.nvals; T.ksi.push_back(K); }
+        T.kp.insert(T.kp.end(), Tc.kp.begin(), Tc.kp.end());
+        T.kg.insert(T.kg.end(), Tc.kg.begin(), Tc.kg.end());
+        T.nslots += Tc.nslots; T.nvals += Tc.nvals;
+    }
+    if (T.ksi.empty()) return TAMCMC_OK;
+    const size_t hdr_bytes = align16((size_t)h->max_chains * sizeof(OutHdr));
+    size_t off[6];
+    off[0] = 0;
+    off[1] = off[0] + align16(T.bands.size() * sizeof(Band));
+    off[2] = off[1] + align16(T.pairs.size() * sizeof(Pair));
+    off[3] = off[2] + align16(T.ksi.size() * sizeof(KsiHdr));
+    off[4] = off[3] + align16(T.kp.size() * 8);
+    off[5] = off[4] + align16(T.kg.size() * 8);
+    if (off[5] > G.in_cap) {
+        if (G.d_in) cudaFree(G.d_in);
+        if (G.h_in) cudaFreeHost(G.h_in);
+        G.d_in = nullptr; G.h_in = nullptr;
+        G.in_cap = off[5] + off[5] / 2;
+        RGB_CUDA(cudaMalloc((void**)&G.d_in, G.in_cap));
+        RGB_CUDA(cudaMallocHost((void**)&G.h_in, G.in_cap));
+    }
+    if ((size_t)T.nslots > G.slots_cap) {
+        if (G.d_slots) cudaFree(G.d_slots);
+        G.d_slots = nullptr;
+        G.slots_cap = (size_t)T.nslots + (size_t)T.nslots / 2 + 1024;
+        RGB_CUDA(cudaMalloc((void**)&G.d_slots, G.slots_cap * 8));
+    }
+    if ((size_t)T.nvals > G.vals_cap) {
+        if (G.d_vals) cudaFree(G.d_vals);
+        G.d_vals = nullptr;
+        G.vals_cap = (size_t)T.nvals + (size_t)T.nvals / 2 + 1024;
+        RGB_CUDA(cudaMalloc((void**)&G.d_vals, G.vals_cap * 8));
+    }
+    std::memcpy(G.h_in + off[0], T.bands.data(), T.bands.size() * sizeof(Band));
+    std::memcpy(G.h_in + off[1], T.pairs.data(), T.pairs.size() * sizeof(Pair));
+    std::memcpy(G.h_in + off[2], T.ksi.data(), T.ksi.size() * sizeof(KsiHdr));
+    std::memcpy(G.h_in + off[3], T.kp.data(), T.kp.size() * 8);
+    std::memcpy(G.h_in + off[4], T.kg.data(), T.kg.size() * 8);
+    RGB_CUDA(cudaMemcpyAsync(G.d_in, G.h_in, off[5], cudaMemcpyHostToDevice, G.stream));
+    RGB_CUDA(cudaMemsetAsync(G.d_out, 0, hdr_bytes, G.stream));
+    RGB_CUDA(cudaEventRecord(G.ev_in, G.stream));
+    OutHdr* d_hdr = (OutHdr*)G.d_out;
+    double* d_cand = (double*)(G.d_out + hdr_bytes);
+    {   // the zeta normalisation on its own stream: it does not depend on the pair loop
+        int maxN = 0;
+        for (const KsiHdr& K : T.ksi) if (K.Ndata > maxN) maxN = K.Ndata;
+        RGB_CUDA(cudaStreamWaitEvent(G.stream2, G.ev_in, 0));
+        const dim3 grid((unsigned)((maxN + 127) / 128), (unsigned)T.ksi.size());
+        tamcmc_rgb_ksi_max_kernel<<<grid, 128, 0, G.stream2>>>((const KsiHdr*)(G.d_in + off[2]), (const double*)(G.d_in + off[3]),
+                                                                (const double*)(G.d_in + off[4]), G.d_vals, d_hdr);
+        tamcmc_rgb_ksi_top_kernel<<<grid, 128, 0, G.stream2>>>((const KsiHdr*)(G.d_in + off[2]), G.d_vals, d_hdr);
+        RGB_CUDA(cudaEventRecord(G.ev_ksi, G.stream2));
+    }
+    if (!T.pairs.empty()) {
+        const int npairs = (int)T.pairs.size(), nbands = (int)T.bands.size();
+        int lanes = 8;
+        for (const Band& B : T.bands) if (2 * B.nseg_est + 2 > lanes) lanes = 2 * B.nseg_est + 2;       // root + pole per segment
+        lanes = (lanes + 7) & ~7;
+        if (lanes > REC_CAP) lanes = REC_CAP;
+        const size_t cnt_bytes = align16((size_t)nbands * 4), rec_bytes = cnt_bytes + (size_t)nbands * REC_CAP * sizeof(Record);
+        if (rec_bytes > G.recs_cap) {
+            if (G.d_recs) cudaFree(G.d_recs);
+            G.d_recs = nullptr;
+            G.recs_cap = rec_bytes + rec_bytes / 2;
+            RGB_CUDA(cudaMalloc((void**)&G.d_recs, G.recs_cap));
+        }
+        int* d_nrec = (int*)G.d_recs;
+        Record* d_rec = (Record*)(G.d_recs + cnt_bytes);
+        RGB_CUDA(cudaMemsetAsync(G.d_recs, 0, cnt_bytes, G.stream));
+        RGB_CUDA(cudaMemsetAsync(G.d_slots, 0xff, (size_t)T.nslots * 8, G.stream));
+        tamcmc_rgb_search_kernel<<<dim3((unsigned)nbands, 2), 512, 0, G.stream>>>((const Band*)(G.d_in + off[0]), d_rec, d_nrec, d_hdr);
+        const long nthreads = (long)npairs * lanes;
+        tamcmc_rgb_pairs_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, G.stream>>>(
+            (const Band*)(G.d_in + off[0]), (const Pair*)(G.d_in + off[1]), npairs, lanes, d_rec, d_nrec, G.d_slots, d_hdr);
+        tamcmc_rgb_compact_kernel<<<(unsigned)nbands, 128, 0, G.stream>>>((const Band*)(G.d_in + off[0]), G.d_slots, d_cand, h->cand_cap, d_hdr);
+    }
+    RGB_CUDA(cudaGetLastError());
+    RGB_CUDA(cudaStreamWaitEvent(G.stream, G.ev_ksi, 0));
+    RGB_CUDA(cudaMemcpyAsync(G.h_out, G.d_out, hdr_bytes, cudaMemcpyDeviceToHost, G.stream));
+    {   // the candidate lists of this group's chains only
+        const size_t a = hdr_bytes + (size_t)G.c0 * h->cand_cap * 8, b = hdr_bytes + (size_t)G.c1 * h->cand_cap * 8;
+        RGB_CUDA(cudaMemcpyAsync(G.h_out + a, G.d_out + a, b - a, cudaMemcpyDeviceToHost, G.stream));
+    }
+    G.launched = true;
+    return TAMCMC_OK;
+}
+
+// wait for the group's results, then the rest of the model function for its chains (host); flagged chains are solved by the host code
+int rgb_collect(tamcmc_gpu_rgb* h, RgbGroup& G, int model_id, const double* params, int params_stride, const int* plength, double step,
+                int capacity, double* rows_out, int row_stride, int* nmodes_out, int* status_out, int* path_out)
+{
+    if (G.launched) RGB_CUDA(cudaStreamSynchronize(G.stream));
+    const size_t hdr_bytes = align16((size_t)h->max_chains * sizeof(OutHdr));
+    const OutHdr* h_hdr = (const OutHdr*)G.h_out;
+    const double* h_cand = (const double*)(G.h_out + hdr_bytes);
+    std::vector<int>& dev = h->on_device;
+    const int c0 = G.c0, c1 = G.c1;
+    std::vector<double> norm((size_t)h->max_chains, -1.0);
+    // 3a, one chain per thread: the exact zeta normalisation at the grid points the device found, and the mixed-mode frequencies
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = c0; c < c1; c++) {
+        if (status_out[c] != TAMCMC_OK) continue;
+        if (dev[(size_t)c] && !G.launched) dev[(size_t)c] = 0;
+        if (!dev[(size_t)c]) continue;
+        const OutHdr& O = h_hdr[c];
+        if (O.flag != 0 || O.count > h->cand_cap || O.ntop < 1) { if (path_out) path_out[c] = O.flag ? O.flag : RGB_FLAG_NONFINITE; dev[(size_t)c] = 0; continue; }
+        if (O.ntop <= TOP_CAP) norm[(size_t)c] = ksi_norm_at(h->preps[(size_t)c], O.top, O.ntop);      // else: finish() takes the maximum itself
+        status_out[c] = finish_modes(h->preps[(size_t)c], true, h_cand + (size_t)c * h->cand_cap, O.count);
+        if (path_out) path_out[c] = 0;
+    }
+    // 3b, the zeta sums at the mixed modes: blocks of 8 frequencies of all chains over all threads
+    std::vector<std::pair<int, int>> blocks;
+    for (int c = c0; c < c1; c++)
+        if (dev[(size_t)c] && status_out[c] == TAMCMC_OK)
+            for (int b = 0; b < ksi_blocks(h->preps[(size_t)c]); b++) blocks.push_back({c, b});
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long k = 0; k < (long)blocks.size(); k++) ksi_block_compute(h->preps[(size_t)blocks[(size_t)k].first], blocks[(size_t)k].second);
+    // 3c, one chain per thread: heights, widths, splittings, rows
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = c0; c < c1; c++) {
+        if (status_out[c] != TAMCMC_OK) continue;
+        double* row = rows_out + (size_t)c * row_stride;
+        int nm = 0;
+        if (dev[(size_t)c]) {
+            ksi_done(h->preps[(size_t)c]);
+            status_out[c] = finish(h->preps[(size_t)c], true, nullptr, 0, norm[(size_t)c], capacity, row, &nm);
+        } else {
+            status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, false);
+            if (status_out[c] == TAMCMC_OK) status_out[c] = finish(h->preps[(size_t)c], false, nullptr, 0, -1.0, capacity, row, &nm);
+        }
+        if (nmodes_out) nmodes_out[c] = nm;
+    }
+    for (int c = c0; c < c1; c++) { h->chains_total++; if (!dev[(size_t)c] && status_out[c] == TAMCMC_OK) h->chains_host++; }
+    return TAMCMC_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
 const char* tamcmc_gpu_rgb_last_error(void) { return g_err.c_str(); }
+
+void tamcmc_gpu_rgb_destroy(tamcmc_gpu_rgb* h);
 
 // Replaces: nothing the reference has as one call -- the per-chain OpenMP fan-out of generate_model (model_def.cpp:466-482) entering
 // model_RGB_asympt_aj_*Width_HarveyLike_v4 once per chain; here the set-up of all chains of a step is one batched device solve.
@@ -325,12 +489,15 @@ int tamcmc_gpu_rgb_create(tamcmc_gpu_rgb** out, int device, int max_chains)
     tamcmc_gpu_rgb* h = new tamcmc_gpu_rgb();
     h->device = device; h->max_chains = max_chains; h->cand_cap = 1024;
     h->out_bytes = align16((size_t)max_chains * sizeof(OutHdr)) + (size_t)max_chains * (size_t)h->cand_cap * 8;
-    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_ksi, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_out, h->out_bytes);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_out, h->out_bytes);
+    cudaError_t e = cudaSuccess;
+    for (RgbGroup& G : h->grp) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&G.stream2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&G.ev_in, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&G.ev_ksi, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&G.d_out, h->out_bytes);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&G.h_out, h->out_bytes);
+    }
     if (e != cudaSuccess) { g_err = cudaGetErrorString(e); tamcmc_gpu_rgb_destroy(h); return TAMCMC_ERR_CUDA; }
     for (int c = 0; c < max_chains; c++) h->preps.push_back(prep_new());
     *out = h;
@@ -342,17 +509,19 @@ void tamcmc_gpu_rgb_destroy(tamcmc_gpu_rgb* h)
     if (!h) return;
     cudaSetDevice(h->device);
     for (Prep* p : h->preps) prep_free(p);
-    if (h->d_in) cudaFree(h->d_in);
-    if (h->h_in) cudaFreeHost(h->h_in);
-    if (h->d_out) cudaFree(h->d_out);
-    if (h->h_out) cudaFreeHost(h->h_out);
-    if (h->d_slots) cudaFree(h->d_slots);
-    if (h->d_recs) cudaFree(h->d_recs);
-    if (h->d_vals) cudaFree(h->d_vals);
-    if (h->ev_in) cudaEventDestroy(h->ev_in);
-    if (h->ev_ksi) cudaEventDestroy(h->ev_ksi);
-    if (h->stream) cudaStreamDestroy(h->stream);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
+    for (RgbGroup& G : h->grp) {
+        if (G.d_in) cudaFree(G.d_in);
+        if (G.h_in) cudaFreeHost(G.h_in);
+        if (G.d_out) cudaFree(G.d_out);
+        if (G.h_out) cudaFreeHost(G.h_out);
+        if (G.d_slots) cudaFree(G.d_slots);
+        if (G.d_recs) cudaFree(G.d_recs);
+        if (G.d_vals) cudaFree(G.d_vals);
+        if (G.ev_in) cudaEventDestroy(G.ev_in);
+        if (G.ev_ksi) cudaEventDestroy(G.ev_ksi);
+        if (G.stream) cudaStreamDestroy(G.stream);
+        if (G.stream2) cudaStreamDestroy(G.stream2);
+    }
     delete h;
 }
 
@@ -361,6 +530,8 @@ void tamcmc_gpu_rgb_destroy(tamcmc_gpu_rgb* h)
 // status_out[c]: what tamcmc_host_expand_rgb_v4 would have returned for chain c; path_out[c] (may be NULL): 0 = solved on the device,
 // otherwise the rgb_solver.cuh flag bits (or -1: not exportable) that sent the chain to the host solver.  Returns TAMCMC_ERR_CUDA /
 // TAMCMC_ERR_ARG for a failed call, else TAMCMC_OK (per-chain outcomes are in status_out).
+// The chains go through in two groups: both are enqueued at once, and the host finishes the first group's rows (sort + unique, zeta at
+// the mixed modes, heights / widths / splittings) while the device solves the second.
 int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params, int params_stride, const int* plength, double step,
                           int nchains, int capacity, double* rows_out, int row_stride, int* nmodes_out, int* status_out, int* path_out)
 {
@@ -369,140 +540,32 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
     RGB_CUDA(cudaSetDevice(h->device));
     timespec t0, t1, t2, t3;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    // ---- stage 1 (host, one chain per thread): everything in front of the pair loop ----
+    // ---- stage 1 (host, one chain per thread): everything in front of the pair loop, and the chain's device task ----
     h->on_device.assign((size_t)nchains, 0);
+    if ((int)h->chain_task.size() < nchains) h->chain_task.resize((size_t)nchains);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int c = 0; c < nchains; c++) status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, true);
-    DeviceTask& T = h->task;
-    T.clear();
     for (int c = 0; c < nchains; c++) {
+        status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, true);
         if (path_out) path_out[c] = -1;
-        if (status_out[c] != TAMCMC_OK) continue;
-        const size_t nb = T.bands.size(), npair = T.pairs.size(), nk = T.ksi.size(), nkp = T.kp.size(), nkg = T.kg.size();
-        const int ns = T.nslots;
-        if (export_task(h->preps[(size_t)c], c, T)) h->on_device[(size_t)c] = 1;
-        else { T.bands.resize(nb); T.pairs.resize(npair); T.ksi.resize(nk); T.kp.resize(nkp); T.kg.resize(nkg); T.nslots = ns; }
+        DeviceTask& Tc = h->chain_task[(size_t)c];
+        Tc.clear();
+        if (status_out[c] == TAMCMC_OK && export_task(h->preps[(size_t)c], c, Tc)) h->on_device[(size_t)c] = 1;
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    // ---- stage 2 (device): pair loop + zeta normalisation of every exported chain ----
-    const size_t hdr_bytes = align16((size_t)h->max_chains * sizeof(OutHdr));
-    const OutHdr* h_hdr = (const OutHdr*)h->h_out;
-    double* h_cand = (double*)(h->h_out + hdr_bytes);
-    if (!T.ksi.empty()) {
-        size_t off[6];
-        off[0] = 0;
-        off[1] = off[0] + align16(T.bands.size() * sizeof(Band));
-        off[2] = off[1] + align16(T.pairs.size() * sizeof(Pair));
-        off[3] = off[2] + align16(T.ksi.size() * sizeof(KsiHdr));
-        off[4] = off[3] + align16(T.kp.size() * 8);
-        off[5] = off[4] + align16(T.kg.size() * 8);
-        if (off[5] > h->in_cap) {
-            if (h->d_in) cudaFree(h->d_in);
-            if (h->h_in) cudaFreeHost(h->h_in);
-            h->d_in = nullptr; h->h_in = nullptr;
-            h->in_cap = off[5] + off[5] / 2;
-            RGB_CUDA(cudaMalloc((void**)&h->d_in, h->in_cap));
-            RGB_CUDA(cudaMallocHost((void**)&h->h_in, h->in_cap));
-        }
-        if ((size_t)T.nslots > h->slots_cap) {
-            if (h->d_slots) cudaFree(h->d_slots);
-            h->d_slots = nullptr;
-            h->slots_cap = (size_t)T.nslots + (size_t)T.nslots / 2 + 1024;
-            RGB_CUDA(cudaMalloc((void**)&h->d_slots, h->slots_cap * 8));
-        }
-        std::memcpy(h->h_in + off[0], T.bands.data(), T.bands.size() * sizeof(Band));
-        std::memcpy(h->h_in + off[1], T.pairs.data(), T.pairs.size() * sizeof(Pair));
-        std::memcpy(h->h_in + off[2], T.ksi.data(), T.ksi.size() * sizeof(KsiHdr));
-        std::memcpy(h->h_in + off[3], T.kp.data(), T.kp.size() * 8);
-        std::memcpy(h->h_in + off[4], T.kg.data(), T.kg.size() * 8);
-        RGB_CUDA(cudaMemcpyAsync(h->d_in, h->h_in, off[5], cudaMemcpyHostToDevice, h->stream));
-        RGB_CUDA(cudaMemsetAsync(h->d_out, 0, hdr_bytes, h->stream));
-        RGB_CUDA(cudaEventRecord(h->ev_in, h->stream));
-        OutHdr* d_hdr = (OutHdr*)h->d_out;
-        double* d_cand = (double*)(h->d_out + hdr_bytes);
-        if ((size_t)T.nvals > h->vals_cap) {
-            if (h->d_vals) cudaFree(h->d_vals);
-            h->d_vals = nullptr;
-            h->vals_cap = (size_t)T.nvals + (size_t)T.nvals / 2 + 1024;
-            RGB_CUDA(cudaMalloc((void**)&h->d_vals, h->vals_cap * 8));
-        }
-        {   // the zeta normalisation on its own stream: it does not depend on the pair loop
-            int maxN = 0;
-            for (const KsiHdr& K : T.ksi) if (K.Ndata > maxN) maxN = K.Ndata;
-            RGB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_in, 0));
-            const dim3 grid((unsigned)((maxN + 127) / 128), (unsigned)T.ksi.size());
-            tamcmc_rgb_ksi_max_kernel<<<grid, 128, 0, h->stream2>>>((const KsiHdr*)(h->d_in + off[2]), (const double*)(h->d_in + off[3]),
-                                                                       (const double*)(h->d_in + off[4]), h->d_vals, d_hdr);
-            tamcmc_rgb_ksi_top_kernel<<<grid, 128, 0, h->stream2>>>((const KsiHdr*)(h->d_in + off[2]), h->d_vals, d_hdr);
-            RGB_CUDA(cudaEventRecord(h->ev_ksi, h->stream2));
-        }
-        if (!T.pairs.empty()) {
-            const int npairs = (int)T.pairs.size(), nbands = (int)T.bands.size();
-            int lanes = 8;
-            for (const Band& B : T.bands) if (2 * B.nseg_est + 2 > lanes) lanes = 2 * B.nseg_est + 2;       // root + pole per segment
-            lanes = (lanes + 7) & ~7;
-            if (lanes > REC_CAP) lanes = REC_CAP;
-            const size_t cnt_bytes = align16((size_t)nbands * 4), rec_bytes = cnt_bytes + (size_t)nbands * REC_CAP * sizeof(Record);
-            if (rec_bytes > h->recs_cap) {
-                if (h->d_recs) cudaFree(h->d_recs);
-                h->d_recs = nullptr;
-                h->recs_cap = rec_bytes + rec_bytes / 2;
-                RGB_CUDA(cudaMalloc((void**)&h->d_recs, h->recs_cap));
-            }
-            int* d_nrec = (int*)h->d_recs;
-            Record* d_rec = (Record*)(h->d_recs + cnt_bytes);
-            RGB_CUDA(cudaMemsetAsync(h->d_recs, 0, cnt_bytes, h->stream));
-            RGB_CUDA(cudaMemsetAsync(h->d_slots, 0xff, (size_t)T.nslots * 8, h->stream));
-            tamcmc_rgb_search_kernel<<<dim3((unsigned)nbands, 2), 512, 0, h->stream>>>((const Band*)(h->d_in + off[0]), d_rec, d_nrec, d_hdr);
-            const long nthreads = (long)npairs * lanes;
-            tamcmc_rgb_pairs_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, h->stream>>>(
-                (const Band*)(h->d_in + off[0]), (const Pair*)(h->d_in + off[1]), npairs, lanes, d_rec, d_nrec, h->d_slots, d_hdr);
-            tamcmc_rgb_compact_kernel<<<(unsigned)nbands, 128, 0, h->stream>>>((const Band*)(h->d_in + off[0]), h->d_slots, d_cand, h->cand_cap, d_hdr);
-        }
-        RGB_CUDA(cudaGetLastError());
-        RGB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_ksi, 0));
-        RGB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
-        RGB_CUDA(cudaStreamSynchronize(h->stream));
+    // ---- stage 2 (device): pair loop + zeta normalisation, both groups enqueued back to back ----
+    const int ngroups = (nchains >= 4) ? 2 : 1;
+    const int split = (ngroups == 2) ? (nchains + 1) / 2 : nchains;
+    h->grp[0].c0 = 0; h->grp[0].c1 = split; h->grp[1].c0 = split; h->grp[1].c1 = nchains;
+    for (int g = 0; g < ngroups; g++) { const int rc = rgb_enqueue(h, h->grp[g]); if (rc) return rc; }
+    // ---- stage 3 (host): group by group, as the results arrive ----
+    bool first = true;
+    for (int g = 0; g < ngroups; g++) {
+        RgbGroup& G = h->grp[g];
+        if (first && G.launched) { RGB_CUDA(cudaStreamSynchronize(G.stream)); clock_gettime(CLOCK_MONOTONIC, &t2); first = false; }
+        const int rc = rgb_collect(h, G, model_id, params, params_stride, plength, step, capacity, rows_out, row_stride, nmodes_out, status_out, path_out);
+        if (rc) return rc;
     }
-    clock_gettime(CLOCK_MONOTONIC, &t2);
-    // ---- stage 3 (host): the rest of the model function; flagged chains are solved by the host code ----
-    // 3a, one chain per thread: the exact zeta normalisation at the grid points the device found, and the mixed-mode frequencies
-    std::vector<int>& dev = h->on_device;
-    std::vector<double> norm((size_t)nchains, -1.0);
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int c = 0; c < nchains; c++) {
-        if (status_out[c] != TAMCMC_OK) continue;
-        const OutHdr& O = h_hdr[c];
-        if (dev[(size_t)c] && (O.flag != 0 || O.count > h->cand_cap || O.ntop < 1)) { if (path_out) path_out[c] = O.flag ? O.flag : RGB_FLAG_NONFINITE; dev[(size_t)c] = 0; }
-        if (dev[(size_t)c]) {
-            if (O.ntop <= TOP_CAP) norm[(size_t)c] = ksi_norm_at(h->preps[(size_t)c], O.top, O.ntop);      // else: finish() takes the maximum itself
-            status_out[c] = finish_modes(h->preps[(size_t)c], true, h_cand + (size_t)c * h->cand_cap, O.count);
-            if (path_out) path_out[c] = 0;
-        }
-    }
-    // 3b, the zeta sums at the mixed modes: blocks of 8 frequencies of all chains over all threads
-    std::vector<std::pair<int, int>> blocks;
-    for (int c = 0; c < nchains; c++)
-        if (dev[(size_t)c] && status_out[c] == TAMCMC_OK)
-            for (int b = 0; b < ksi_blocks(h->preps[(size_t)c]); b++) blocks.push_back({c, b});
-#pragma omp parallel for schedule(dynamic, 1)
-    for (long k = 0; k < (long)blocks.size(); k++) ksi_block_compute(h->preps[(size_t)blocks[(size_t)k].first], blocks[(size_t)k].second);
-    // 3c, one chain per thread: heights, widths, splittings, rows
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int c = 0; c < nchains; c++) {
-        if (status_out[c] != TAMCMC_OK) continue;
-        double* row = rows_out + (size_t)c * row_stride;
-        int nm = 0;
-        if (dev[(size_t)c]) {
-            ksi_done(h->preps[(size_t)c]);
-            status_out[c] = finish(h->preps[(size_t)c], true, nullptr, 0, norm[(size_t)c], capacity, row, &nm);
-        } else {
-            status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, false);
-            if (status_out[c] == TAMCMC_OK) status_out[c] = finish(h->preps[(size_t)c], false, nullptr, 0, -1.0, capacity, row, &nm);
-        }
-        if (nmodes_out) nmodes_out[c] = nm;
-    }
-    for (int c = 0; c < nchains; c++) { h->chains_total++; if (!dev[(size_t)c] && status_out[c] == TAMCMC_OK) h->chains_host++; }
+    if (first) clock_gettime(CLOCK_MONOTONIC, &t2);
     clock_gettime(CLOCK_MONOTONIC, &t3);
     auto ms = [](const timespec& a, const timespec& b) { return 1e3 * (double)(b.tv_sec - a.tv_sec) + 1e-6 * (double)(b.tv_nsec - a.tv_nsec); };
     h->last_ms[0] = ms(t0, t1); h->last_ms[1] = ms(t1, t2); h->last_ms[2] = ms(t2, t3); h->last_ms[3] = ms(t0, t3);
