@@ -431,39 +431,46 @@ int rgb_collect(tamcmc_gpu_rgb* h, RgbGroup& G, int model_id, const double* para
     std::vector<int>& dev = h->on_device;
     const int c0 = G.c0, c1 = G.c1;
     std::vector<double> norm((size_t)h->max_chains, -1.0);
-    // 3a, one chain per thread: the exact zeta normalisation at the grid points the device found, and the mixed-mode frequencies
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int c = c0; c < c1; c++) {
-        if (status_out[c] != TAMCMC_OK) continue;
-        if (dev[(size_t)c] && !G.launched) dev[(size_t)c] = 0;
-        if (!dev[(size_t)c]) continue;
-        const OutHdr& O = h_hdr[c];
-        if (O.flag != 0 || O.count > h->cand_cap || O.ntop < 1) { if (path_out) path_out[c] = O.flag ? O.flag : RGB_FLAG_NONFINITE; dev[(size_t)c] = 0; continue; }
-        if (O.ntop <= TOP_CAP) norm[(size_t)c] = ksi_norm_at(h->preps[(size_t)c], O.top, O.ntop);      // else: finish() takes the maximum itself
-        status_out[c] = finish_modes(h->preps[(size_t)c], true, h_cand + (size_t)c * h->cand_cap, O.count);
-        if (path_out) path_out[c] = 0;
-    }
-    // 3b, the zeta sums at the mixed modes: blocks of 8 frequencies of all chains over all threads
+    // one parallel region, three stages with a barrier between them
     std::vector<std::pair<int, int>> blocks;
-    for (int c = c0; c < c1; c++)
-        if (dev[(size_t)c] && status_out[c] == TAMCMC_OK)
-            for (int b = 0; b < ksi_blocks(h->preps[(size_t)c]); b++) blocks.push_back({c, b});
-#pragma omp parallel for schedule(dynamic, 1)
-    for (long k = 0; k < (long)blocks.size(); k++) ksi_block_compute(h->preps[(size_t)blocks[(size_t)k].first], blocks[(size_t)k].second);
-    // 3c, one chain per thread: heights, widths, splittings, rows
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int c = c0; c < c1; c++) {
-        if (status_out[c] != TAMCMC_OK) continue;
-        double* row = rows_out + (size_t)c * row_stride;
-        int nm = 0;
-        if (dev[(size_t)c]) {
-            ksi_done(h->preps[(size_t)c]);
-            status_out[c] = finish(h->preps[(size_t)c], true, nullptr, 0, norm[(size_t)c], capacity, row, &nm);
-        } else {
-            status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, false);
-            if (status_out[c] == TAMCMC_OK) status_out[c] = finish(h->preps[(size_t)c], false, nullptr, 0, -1.0, capacity, row, &nm);
+#pragma omp parallel
+    {
+        // 3a, one chain per thread: the exact zeta normalisation at the grid points the device found, and the mixed-mode frequencies
+#pragma omp for schedule(dynamic, 1)
+        for (int c = c0; c < c1; c++) {
+            if (status_out[c] != TAMCMC_OK) continue;
+            if (dev[(size_t)c] && !G.launched) dev[(size_t)c] = 0;
+            if (!dev[(size_t)c]) continue;
+            const OutHdr& O = h_hdr[c];
+            if (O.flag != 0 || O.count > h->cand_cap || O.ntop < 1) { if (path_out) path_out[c] = O.flag ? O.flag : RGB_FLAG_NONFINITE; dev[(size_t)c] = 0; continue; }
+            if (O.ntop <= TOP_CAP) norm[(size_t)c] = ksi_norm_at(h->preps[(size_t)c], O.top, O.ntop);      // else: finish() takes the maximum itself
+            status_out[c] = finish_modes(h->preps[(size_t)c], true, h_cand + (size_t)c * h->cand_cap, O.count);
+            if (path_out) path_out[c] = 0;
         }
-        if (nmodes_out) nmodes_out[c] = nm;
+        // 3b, the zeta sums at the mixed modes: blocks of 8 frequencies of all chains over all threads
+#pragma omp single
+        {
+            for (int c = c0; c < c1; c++)
+                if (dev[(size_t)c] && status_out[c] == TAMCMC_OK)
+                    for (int b = 0; b < ksi_blocks(h->preps[(size_t)c]); b++) blocks.push_back({c, b});
+        }
+#pragma omp for schedule(dynamic, 1)
+        for (long k = 0; k < (long)blocks.size(); k++) ksi_block_compute(h->preps[(size_t)blocks[(size_t)k].first], blocks[(size_t)k].second);
+        // 3c, one chain per thread: heights, widths, splittings, rows
+#pragma omp for schedule(dynamic, 1)
+        for (int c = c0; c < c1; c++) {
+            if (status_out[c] != TAMCMC_OK) continue;
+            double* row = rows_out + (size_t)c * row_stride;
+            int nm = 0;
+            if (dev[(size_t)c]) {
+                ksi_done(h->preps[(size_t)c]);
+                status_out[c] = finish(h->preps[(size_t)c], true, nullptr, 0, norm[(size_t)c], capacity, row, &nm);
+            } else {
+                status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, false);
+                if (status_out[c] == TAMCMC_OK) status_out[c] = finish(h->preps[(size_t)c], false, nullptr, 0, -1.0, capacity, row, &nm);
+            }
+            if (nmodes_out) nmodes_out[c] = nm;
+        }
     }
     for (int c = c0; c < c1; c++) { h->chains_total++; if (!dev[(size_t)c] && status_out[c] == TAMCMC_OK) h->chains_host++; }
     return TAMCMC_OK;
@@ -490,9 +497,13 @@ int tamcmc_gpu_rgb_create(tamcmc_gpu_rgb** out, int device, int max_chains)
     h->device = device; h->max_chains = max_chains; h->cand_cap = 1024;
     h->out_bytes = align16((size_t)max_chains * sizeof(OutHdr)) + (size_t)max_chains * (size_t)h->cand_cap * 8;
     cudaError_t e = cudaSuccess;
-    for (RgbGroup& G : h->grp) {
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&G.stream2, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);        // (greatest priority = lowest number)
+    for (int g = 0; g < 2; g++) {
+        RgbGroup& G = h->grp[g];
+        const int prio = (g == 0) ? prio_hi : prio_lo;            // the group the host waits for first goes first on the device
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&G.stream, cudaStreamNonBlocking, prio);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&G.stream2, cudaStreamNonBlocking, prio);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&G.ev_in, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&G.ev_ksi, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc((void**)&G.d_out, h->out_bytes);
@@ -530,8 +541,8 @@ void tamcmc_gpu_rgb_destroy(tamcmc_gpu_rgb* h)
 // status_out[c]: what tamcmc_host_expand_rgb_v4 would have returned for chain c; path_out[c] (may be NULL): 0 = solved on the device,
 // otherwise the rgb_solver.cuh flag bits (or -1: not exportable) that sent the chain to the host solver.  Returns TAMCMC_ERR_CUDA /
 // TAMCMC_ERR_ARG for a failed call, else TAMCMC_OK (per-chain outcomes are in status_out).
-// The chains go through in two groups: both are enqueued at once, and the host finishes the first group's rows (sort + unique, zeta at
-// the mixed modes, heights / widths / splittings) while the device solves the second.
+// From 16 chains on they go through in two groups: both are enqueued at once, and the host finishes the first group's rows (sort + unique,
+// zeta at the mixed modes, heights / widths / splittings) while the device solves the second.
 int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params, int params_stride, const int* plength, double step,
                           int nchains, int capacity, double* rows_out, int row_stride, int* nmodes_out, int* status_out, int* path_out)
 {
@@ -553,7 +564,8 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     // ---- stage 2 (device): pair loop + zeta normalisation, both groups enqueued back to back ----
-    const int ngroups = (nchains >= 4) ? 2 : 1;
+    // (measured at 10 chains: the second group's enqueue costs the host what the overlap saves -- one group below 16 chains)
+    const int ngroups = (nchains >= 16) ? 2 : 1;
     const int split = (ngroups == 2) ? (nchains + 1) / 2 : nchains;
     h->grp[0].c0 = 0; h->grp[0].c1 = split; h->grp[1].c0 = split; h->grp[1].c1 = nchains;
     for (int g = 0; g < ngroups; g++) { const int rc = rgb_enqueue(h, h->grp[g]); if (rc) return rc; }

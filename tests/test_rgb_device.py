@@ -193,7 +193,7 @@ def test_gpu_rgb_symbols_fail_loudly_without_a_device(pkg):
 def test_gpu_rgb_expand_matches_host_expander(pkg, model_id):
     G = np.load(GOLD)
     step = G["x"][2] - G["x"][1]
-    cases = [(c, r, p, pl) for c, r, p, pl in _variants(G, 4)]
+    cases = [(c, r, p, pl) for c, r, p, pl in _variants(G, 5)]          # 20 chains: two groups in flight (>= 16)
     pl = cases[0][3]
     assert all(np.array_equal(pl, c[3]) for c in cases)
     P = np.stack([c[2] for c in cases])
