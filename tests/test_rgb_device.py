@@ -251,6 +251,49 @@ def test_gpu_rgb_expand_on_other_stars(pkg):
 
 
 @pytest.mark.gpu
+def test_gpu_rgb_expand_over_a_cloud_of_proposals(pkg):
+    """What an MCMC run does: 120 parameter vectors scattered around the fixture's (every hyper-parameter of the mixed modes, the l=0
+    frequencies, heights, widths), six calls of 20 chains.  Every frequency within 1 ulp of the host solver's, at least 99 % identical;
+    the count of chains handed to the host solver is reported by the handle and stays small."""
+    G = np.load(GOLD)
+    step = G["x"][2] - G["x"][1]
+    pl = G["plength0"]
+    rng = np.random.default_rng(2024)
+    Nmax, lmax, Nfl0 = int(pl[0]), int(pl[1]), int(pl[2])
+    o = Nmax + lmax + Nfl0
+    nn = int(pl[8])
+    tot = same = 0
+    with pkg.RgbExpander(25, pl, step, 140, 20) as rx:
+        for call in range(6):
+            base = G["params%d" % (call % 4)]
+            P = np.tile(base, (20, 1))
+            P[:, o] += rng.normal(size=20) * 0.03
+            P[:, o + 1] *= 1 + rng.normal(size=20) * 0.01
+            P[:, o + 2] = np.abs(P[:, o + 2] + rng.normal(size=20) * 0.05)
+            P[:, o + 3] *= np.exp(rng.normal(size=20) * 0.1)
+            P[:, Nmax + lmax:o] += rng.normal(size=(20, Nfl0)) * 0.02
+            P[:, :Nmax] *= np.exp(rng.normal(size=(20, Nmax)) * 0.05)
+            rows, nm, st, path = rx.expand(P)
+            for i in range(20):
+                try:
+                    row, n = pkg.expand_rgb_v4(25, P[i], pl, step, 140)
+                except pkg.TamcmcError as e:
+                    assert st[i] == e.status
+                    continue
+                assert st[i] == 0 and nm[i] == n
+                a, b = row[4 + nn:4 + nn + 20 * n].reshape(n, 20), rows[i, 4 + nn:4 + nn + 20 * n].reshape(n, 20)
+                l1 = a[:, 0] == 1
+                assert np.all(np.abs(a[:, 1] - b[:, 1]) <= np.spacing(a[:, 1]))
+                np.testing.assert_allclose(b, a, rtol=1e-11, atol=0)
+                tot += int(l1.sum())
+                same += int((a[l1, 1] == b[l1, 1]).sum())
+        n_setups, n_host = rx.counts()
+    print("mixed-mode frequencies identical to the host solver: %d of %d; chains handed to the host solver: %d of %d" % (same, tot, n_host, n_setups))
+    assert tot > 3000 and same >= 0.99 * tot
+    assert n_setups == 120 and n_host <= 6
+
+
+@pytest.mark.gpu
 def test_gpu_rgb_params_to_logl_against_reference_model(pkg, oracle):
     """reference parameter vectors -> tamcmc_gpu_rgb_expand (rows in the context's staging block) -> tamcmc_gpu_eval, against the
     spectrum the reference's own model function returned for the same vectors (tests/golden/reference_rgb_vectors.npz)."""
