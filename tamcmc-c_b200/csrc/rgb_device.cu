@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(512) tamcmc_rgb_search_kernel(const Band* __re
     if (flag) atomicOr(&hdr[B.chain].flag, flag);
 }
 
-// phase 2: every record of a band for every g mode of the band, `lanes` threads per (p mode, g mode) pair.  A solution found from the sign
-// change at band index idx goes to the band's slot idx with atomicMin on its bit pattern (frequencies are positive: the order of the bits
-// is the order of the values): the reference keeps the smallest of every cluster of solutions (sort + unique with a tolerance of two
-// bins, solver_mm.cpp:575-590) -- the minimum per slot is that value whenever a cluster does not straddle two coarse grid cells, and the
-// host's sort + unique merges the slots when it does.
+// phase 2: every record of a band for every g mode of the band, `lanes` threads per (p mode, g mode) pair.  The solution of record r goes
+// to slot r of the band with atomicMin on its bit pattern (frequencies are positive: the order of the bits is the order of the values): the
+// reference keeps the smallest of every cluster of solutions (sort + unique with a tolerance of two bins, solver_mm.cpp:575-590) -- the
+// minimum per record (= per sign change of the coarse grid) is that value whenever a cluster does not straddle two coarse grid cells, and
+// the host's sort + unique merges the slots when it does.  [bands][REC_CAP] slots and the record counts go back to the host as they are.
 __global__ void __launch_bounds__(128) tamcmc_rgb_pairs_kernel(const Band* __restrict__ bands, const Pair* __restrict__ pairs, int npairs, int lanes,
                                                                 const Record* __restrict__ recs, const int* __restrict__ nrec,
                                                                 unsigned long long* __restrict__ slots, OutHdr* __restrict__ hdr)
@@ -187,37 +187,11 @@ __global__ void __launch_bounds__(128) tamcmc_rgb_pairs_kernel(const Band* __res
         const Record R = recs[(size_t)Q.band * REC_CAP + r];
         double sol;
         if (record_eval<TrigCR>(B, Q.inv_g, R, sol, flag)) {
-            if (sol > 0.0) atomicMin(slots + B.slot_off + R.idx, (unsigned long long)__double_as_longlong(sol));
+            if (sol > 0.0) atomicMin(slots + (size_t)Q.band * REC_CAP + r, (unsigned long long)__double_as_longlong(sol));
             else flag |= RGB_FLAG_NONFINITE;
         }
     }
     if (flag) atomicOr(&hdr[B.chain].flag, flag);
-}
-
-// the non-empty slots of every band -> the chain's candidate list (any order: the host sorts).  One block per band: the block counts
-// its solutions in shared memory and reserves its range of the chain's list with ONE global atomic.
-__global__ void __launch_bounds__(128) tamcmc_rgb_compact_kernel(const Band* __restrict__ bands, const unsigned long long* __restrict__ slots,
-                                                                  double* __restrict__ cand, int cand_cap, OutHdr* __restrict__ hdr)
-{
-    __shared__ int s_n, s_base;
-    __shared__ unsigned long long s_v[REC_CAP];
-    const Band B = bands[blockIdx.x];
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < B.nband; i += blockDim.x) {
-        const unsigned long long v = slots[B.slot_off + i];
-        if (v == SLOT_EMPTY) continue;
-        const int k = atomicAdd(&s_n, 1);
-        if (k < REC_CAP) s_v[k] = v;
-    }
-    __syncthreads();
-    const int n = s_n < REC_CAP ? s_n : REC_CAP;           // (a band has at most REC_CAP records, hence at most REC_CAP solutions)
-    if (threadIdx.x == 0) s_base = (n > 0) ? atomicAdd(&hdr[B.chain].count, n) : 0;
-    __syncthreads();
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        if (s_base + k < cand_cap) cand[(size_t)B.chain * cand_cap + s_base + k] = __longlong_as_double((long long)s_v[k]);
-        else atomicOr(&hdr[B.chain].flag, RGB_FLAG_OVERFLOW);
-    }
 }
 
 __device__ __forceinline__ double fast_rcp(double d)          // 1 / d to ~1 ulp: hardware seed + two Newton steps
@@ -298,17 +272,18 @@ struct RgbGroup {
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_in = nullptr, ev_ksi = nullptr;
     char* h_in = nullptr; char* d_in = nullptr; size_t in_cap = 0;
-    char* h_out = nullptr; char* d_out = nullptr;
-    unsigned long long* d_slots = nullptr; size_t slots_cap = 0;
+    char* h_out = nullptr; char* d_out = nullptr;          // [max_chains] OutHdr
+    char* h_res = nullptr; char* d_res = nullptr; size_t res_cap = 0;     // [bands] record counts, then [bands][REC_CAP] solution slots
+    std::vector<int> band_lo, band_hi;                     // per chain: its bands in `task`
     double* d_vals = nullptr; size_t vals_cap = 0;        // zeta sums over the normalisation grids
-    char* d_recs = nullptr; size_t recs_cap = 0;          // [bands] record counts, then [bands][REC_CAP] records
+    char* d_recs = nullptr; size_t recs_cap = 0;          // [bands][REC_CAP] records
     DeviceTask task;
     int c0 = 0, c1 = 0;                                    // chains [c0, c1) of the call
     bool launched = false;
 };
 
 struct tamcmc_gpu_rgb {
-    int device = 0, max_chains = 0, cand_cap = 0;
+    int device = 0, max_chains = 0;
     size_t out_bytes = 0;
     RgbGroup grp[2];
     std::vector<Prep*> preps;
@@ -326,6 +301,7 @@ int rgb_enqueue(tamcmc_gpu_rgb* h, RgbGroup& G)
     DeviceTask& T = G.task;
     T.clear();
     G.launched = false;
+    G.band_lo.assign((size_t)h->max_chains, 0); G.band_hi.assign((size_t)h->max_chains, 0);
     for (int c = G.c0; c < G.c1; c++) {
         if (!h->on_device[(size_t)c]) continue;
         const DeviceTask& Tc = h->chain_task[(size_t)c];
@@ -336,6 +312,7 @@ int rgb_enqueue(tamcmc_gpu_rgb* h, RgbGroup& G)
         T.kp.insert(T.kp.end(), Tc.kp.begin(), Tc.kp.end());
         T.kg.insert(T.kg.end(), Tc.kg.begin(), Tc.kg.end());
         T.nslots += Tc.nslots; T.nvals += Tc.nvals;
+        G.band_lo[(size_t)c] = band0; G.band_hi[(size_t)c] = (int)T.bands.size();
     }
     if (T.ksi.empty()) return TAMCMC_OK;
     const size_t hdr_bytes = align16((size_t)h->max_chains * sizeof(OutHdr));
@@ -354,11 +331,15 @@ int rgb_enqueue(tamcmc_gpu_rgb* h, RgbGroup& G)
         RGB_CUDA(cudaMalloc((void**)&G.d_in, G.in_cap));
         RGB_CUDA(cudaMallocHost((void**)&G.h_in, G.in_cap));
     }
-    if ((size_t)T.nslots > G.slots_cap) {
-        if (G.d_slots) cudaFree(G.d_slots);
-        G.d_slots = nullptr;
-        G.slots_cap = (size_t)T.nslots + (size_t)T.nslots / 2 + 1024;
-        RGB_CUDA(cudaMalloc((void**)&G.d_slots, G.slots_cap * 8));
+    const int nbands = (int)T.bands.size();
+    const size_t cnt_bytes = align16((size_t)nbands * 4), res_bytes = cnt_bytes + (size_t)nbands * REC_CAP * 8;
+    if (res_bytes > G.res_cap) {
+        if (G.d_res) cudaFree(G.d_res);
+        if (G.h_res) cudaFreeHost(G.h_res);
+        G.d_res = nullptr; G.h_res = nullptr;
+        G.res_cap = res_bytes + res_bytes / 2;
+        RGB_CUDA(cudaMalloc((void**)&G.d_res, G.res_cap));
+        RGB_CUDA(cudaMallocHost((void**)&G.h_res, G.res_cap));
     }
     if ((size_t)T.nvals > G.vals_cap) {
         if (G.d_vals) cudaFree(G.d_vals);
@@ -375,7 +356,6 @@ int rgb_enqueue(tamcmc_gpu_rgb* h, RgbGroup& G)
     RGB_CUDA(cudaMemsetAsync(G.d_out, 0, hdr_bytes, G.stream));
     RGB_CUDA(cudaEventRecord(G.ev_in, G.stream));
     OutHdr* d_hdr = (OutHdr*)G.d_out;
-    double* d_cand = (double*)(G.d_out + hdr_bytes);
     {   // the zeta normalisation on its own stream: it does not depend on the pair loop
         int maxN = 0;
         for (const KsiHdr& K : T.ksi) if (K.Ndata > maxN) maxN = K.Ndata;
@@ -386,36 +366,35 @@ int rgb_enqueue(tamcmc_gpu_rgb* h, RgbGroup& G)
         tamcmc_rgb_ksi_top_kernel<<<grid, 128, 0, G.stream2>>>((const KsiHdr*)(G.d_in + off[2]), G.d_vals, d_hdr);
         RGB_CUDA(cudaEventRecord(G.ev_ksi, G.stream2));
     }
+    if (res_bytes) {
+        RGB_CUDA(cudaMemsetAsync(G.d_res, 0, cnt_bytes, G.stream));
+        RGB_CUDA(cudaMemsetAsync(G.d_res + cnt_bytes, 0xff, res_bytes - cnt_bytes, G.stream));
+    }
     if (!T.pairs.empty()) {
-        const int npairs = (int)T.pairs.size(), nbands = (int)T.bands.size();
+        const int npairs = (int)T.pairs.size();
         int lanes = 8;
         for (const Band& B : T.bands) if (2 * B.nseg_est + 2 > lanes) lanes = 2 * B.nseg_est + 2;       // root + pole per segment
         lanes = (lanes + 7) & ~7;
         if (lanes > REC_CAP) lanes = REC_CAP;
-        const size_t cnt_bytes = align16((size_t)nbands * 4), rec_bytes = cnt_bytes + (size_t)nbands * REC_CAP * sizeof(Record);
+        const size_t rec_bytes = (size_t)nbands * REC_CAP * sizeof(Record);
         if (rec_bytes > G.recs_cap) {
             if (G.d_recs) cudaFree(G.d_recs);
             G.d_recs = nullptr;
             G.recs_cap = rec_bytes + rec_bytes / 2;
             RGB_CUDA(cudaMalloc((void**)&G.d_recs, G.recs_cap));
         }
-        int* d_nrec = (int*)G.d_recs;
-        Record* d_rec = (Record*)(G.d_recs + cnt_bytes);
-        RGB_CUDA(cudaMemsetAsync(G.d_recs, 0, cnt_bytes, G.stream));
-        RGB_CUDA(cudaMemsetAsync(G.d_slots, 0xff, (size_t)T.nslots * 8, G.stream));
+        int* d_nrec = (int*)G.d_res;
+        unsigned long long* d_slots = (unsigned long long*)(G.d_res + cnt_bytes);
+        Record* d_rec = (Record*)G.d_recs;
         tamcmc_rgb_search_kernel<<<dim3((unsigned)nbands, 2), 512, 0, G.stream>>>((const Band*)(G.d_in + off[0]), d_rec, d_nrec, d_hdr);
         const long nthreads = (long)npairs * lanes;
         tamcmc_rgb_pairs_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, G.stream>>>(
-            (const Band*)(G.d_in + off[0]), (const Pair*)(G.d_in + off[1]), npairs, lanes, d_rec, d_nrec, G.d_slots, d_hdr);
-        tamcmc_rgb_compact_kernel<<<(unsigned)nbands, 128, 0, G.stream>>>((const Band*)(G.d_in + off[0]), G.d_slots, d_cand, h->cand_cap, d_hdr);
+            (const Band*)(G.d_in + off[0]), (const Pair*)(G.d_in + off[1]), npairs, lanes, d_rec, d_nrec, d_slots, d_hdr);
     }
     RGB_CUDA(cudaGetLastError());
     RGB_CUDA(cudaStreamWaitEvent(G.stream, G.ev_ksi, 0));
     RGB_CUDA(cudaMemcpyAsync(G.h_out, G.d_out, hdr_bytes, cudaMemcpyDeviceToHost, G.stream));
-    {   // the candidate lists of this group's chains only
-        const size_t a = hdr_bytes + (size_t)G.c0 * h->cand_cap * 8, b = hdr_bytes + (size_t)G.c1 * h->cand_cap * 8;
-        RGB_CUDA(cudaMemcpyAsync(G.h_out + a, G.d_out + a, b - a, cudaMemcpyDeviceToHost, G.stream));
-    }
+    if (res_bytes) RGB_CUDA(cudaMemcpyAsync(G.h_res, G.d_res, res_bytes, cudaMemcpyDeviceToHost, G.stream));
     G.launched = true;
     return TAMCMC_OK;
 }
@@ -425,9 +404,10 @@ int rgb_collect(tamcmc_gpu_rgb* h, RgbGroup& G, int model_id, const double* para
                 int capacity, double* rows_out, int row_stride, int* nmodes_out, int* status_out, int* path_out)
 {
     if (G.launched) RGB_CUDA(cudaStreamSynchronize(G.stream));
-    const size_t hdr_bytes = align16((size_t)h->max_chains * sizeof(OutHdr));
     const OutHdr* h_hdr = (const OutHdr*)G.h_out;
-    const double* h_cand = (const double*)(G.h_out + hdr_bytes);
+    const int nbands = (int)G.task.bands.size();
+    const int* h_nrec = (const int*)G.h_res;
+    const unsigned long long* h_slots = (const unsigned long long*)(G.h_res + align16((size_t)nbands * 4));
     std::vector<int>& dev = h->on_device;
     const int c0 = G.c0, c1 = G.c1;
     std::vector<double> norm((size_t)h->max_chains, -1.0);
@@ -442,9 +422,17 @@ int rgb_collect(tamcmc_gpu_rgb* h, RgbGroup& G, int model_id, const double* para
             if (dev[(size_t)c] && !G.launched) dev[(size_t)c] = 0;
             if (!dev[(size_t)c]) continue;
             const OutHdr& O = h_hdr[c];
-            if (O.flag != 0 || O.count > h->cand_cap || O.ntop < 1) { if (path_out) path_out[c] = O.flag ? O.flag : RGB_FLAG_NONFINITE; dev[(size_t)c] = 0; continue; }
+            if (O.flag != 0 || O.ntop < 1) { if (path_out) path_out[c] = O.flag ? O.flag : RGB_FLAG_NONFINITE; dev[(size_t)c] = 0; continue; }
             if (O.ntop <= TOP_CAP) norm[(size_t)c] = ksi_norm_at(h->preps[(size_t)c], O.top, O.ntop);      // else: finish() takes the maximum itself
-            status_out[c] = finish_modes(h->preps[(size_t)c], true, h_cand + (size_t)c * h->cand_cap, O.count);
+            std::vector<double> cand;                      // the solutions of the chain's bands: one per record the ratio test kept
+            for (int b = G.band_lo[(size_t)c]; b < G.band_hi[(size_t)c]; b++) {
+                const int n = h_nrec[b] < REC_CAP ? h_nrec[b] : REC_CAP;
+                for (int r = 0; r < n; r++) {
+                    const unsigned long long v = h_slots[(size_t)b * REC_CAP + r];
+                    if (v != SLOT_EMPTY) { double d; std::memcpy(&d, &v, 8); cand.push_back(d); }
+                }
+            }
+            status_out[c] = finish_modes(h->preps[(size_t)c], true, cand.data(), (int)cand.size());
             if (path_out) path_out[c] = 0;
         }
         // 3b, the zeta sums at the mixed modes: blocks of 8 frequencies of all chains over all threads
@@ -494,8 +482,8 @@ int tamcmc_gpu_rgb_create(tamcmc_gpu_rgb** out, int device, int max_chains)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "no usable CUDA device"; return TAMCMC_ERR_CUDA; }
     RGB_CUDA(cudaSetDevice(device));
     tamcmc_gpu_rgb* h = new tamcmc_gpu_rgb();
-    h->device = device; h->max_chains = max_chains; h->cand_cap = 1024;
-    h->out_bytes = align16((size_t)max_chains * sizeof(OutHdr)) + (size_t)max_chains * (size_t)h->cand_cap * 8;
+    h->device = device; h->max_chains = max_chains;
+    h->out_bytes = align16((size_t)max_chains * sizeof(OutHdr));
     cudaError_t e = cudaSuccess;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);        // (greatest priority = lowest number)
@@ -525,7 +513,8 @@ void tamcmc_gpu_rgb_destroy(tamcmc_gpu_rgb* h)
         if (G.h_in) cudaFreeHost(G.h_in);
         if (G.d_out) cudaFree(G.d_out);
         if (G.h_out) cudaFreeHost(G.h_out);
-        if (G.d_slots) cudaFree(G.d_slots);
+        if (G.d_res) cudaFree(G.d_res);
+        if (G.h_res) cudaFreeHost(G.h_res);
         if (G.d_recs) cudaFree(G.d_recs);
         if (G.d_vals) cudaFree(G.d_vals);
         if (G.ev_in) cudaEventDestroy(G.ev_in);
