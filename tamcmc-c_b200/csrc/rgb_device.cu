@@ -3,9 +3,11 @@
 // Replaces, for ALL chains of a step in one call, the two loops that are 99 % of model_RGB_asympt_aj_*Width_HarveyLike_v4's
 // set-up (tamcmc/sources/models.cpp:4684-4927, 4334-4556) and that the reference runs per chain under OpenMP:
 //   * the (p mode, g mode) pair loop of the asymptotic mixed-mode solver (external/ARMM/solver_mm.cpp:558-573 -> solver_mm :326-449):
-//     tamcmc_rgb_pairs_kernel, one warp per pair, one lane per segment (rgb_solver.cuh);
+//     tamcmc_rgb_search_kernel (one warp per segment of a p mode's band: where the sign changes are) and tamcmc_rgb_pairs_kernel (every sign
+//     change evaluated exactly for every g mode, minimum per sign change) -- rgb_solver.cuh;
 //   * the normalisation of the zeta function: the maximum of the zeta sums over a 4-year-resolution grid
-//     (external/ARMM/bump_DP.cpp:126-163): tamcmc_rgb_ksi_max_kernel, one thread per grid frequency.
+//     (external/ARMM/bump_DP.cpp:126-163): tamcmc_rgb_ksi_max_kernel + tamcmc_rgb_ksi_top_kernel locate it (one thread per grid frequency),
+//     the host evaluates it there like the reference.
 // The host does what is left (host_rgb.cpp: prepare -> [device] -> finish): unpacking, l=0 widths, the p / g mode lists and the long
 // double grid set-up in front; filter / sort / unique of the solutions, bias spline, zeta at the ~50 mixed modes, heights, widths,
 // splittings and the mode-table rows behind.  Rows are written where the caller says -- normally the pinned staging block of the
