@@ -132,6 +132,60 @@ def test_cpp_rgb_mirror_matches_reference(pkg, oracle, tmp_path):
     assert r.returncode == 0 and "model_def_rgb: ok" in r.stdout, r.stdout
 
 
+def _build_rgb_driver():
+    exe = os.path.join(HERE, "cpp", "test_rgb_driver")
+    src = os.path.join(HERE, "cpp", "test_rgb_driver.cpp")
+    deps = [src, os.path.join(LIBDIR, "host", "mcmc_driver.hpp"), os.path.join(LIBDIR, "host", "model_def_gpu.hpp"), os.path.join(ROOT, "include", "tamcmc_gpu.h")]
+    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(d) for d in deps):
+        return exe
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fopenmp", "-o", exe, src, "-L" + LIBDIR, "-ltamcmc_gpu",
+                           "-L" + cuda_lib, "-lcudart", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath," + cuda_lib])
+    return exe
+
+
+def rgb_driver_case(path, nchains=5):
+    """the red-giant fixture as a fit: heights, l=0 frequencies, the four mixed-mode hyper-parameters, the two rotation rates and the
+    inclination relaxed inside uniform boxes"""
+    G = np.load(os.path.join(HERE, "golden", "reference_rgb_vectors.npz"))
+    x, y, params, pl = G["x"], G["y"], G["params0"], G["plength0"]
+    Nmax, lmax, Nfl0, Nfl1, Nfl2, Nfl3, Nsplit, Nwidth, Nnoise = [int(v) for v in pl[:9]]
+    o0 = Nmax + lmax
+    o1 = o0 + Nfl0
+    o_s = o0 + Nfl0 + Nfl1 + Nfl2 + Nfl3
+    o_inc = o_s + Nsplit + Nwidth + Nnoise
+    relax, err, lo, hi = [], [], [], []
+    for k in range(Nmax):                                  # heights
+        relax.append(k); err.append(0.05 * abs(params[k])); lo.append(0.2 * abs(params[k])); hi.append(5 * abs(params[k]))
+    for k in range(Nfl0):                                  # l=0 frequencies
+        relax.append(o0 + k); err.append(0.01); lo.append(params[o0 + k] - 0.5); hi.append(params[o0 + k] + 0.5)
+    for k, (e, a, b) in enumerate([(0.005, -0.3, 0.3), (0.02, params[o1 + 1] - 2, params[o1 + 1] + 2), (0.01, 0.0, 1.0), (0.005, 0.05, 0.6)]):
+        relax.append(o1 + k); err.append(e); lo.append(a); hi.append(b)        # delta0l, DPl, alpha_g, q
+    relax += [o_s, o_s + 1]; err += [0.01, 0.01]; lo += [0.0, 0.0]; hi += [1.0, 2.0]        # rot_env, rot_core
+    relax.append(o_inc); err.append(1.0); lo.append(0.0); hi.append(90.0)
+    hdr = np.concatenate([[25, len(x), nchains, len(params), 140, len(relax)], pl.astype(float)])
+    with open(path, "wb") as fh:
+        for a in (hdr, x, y, params, relax, err, lo, hi):
+            fh.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    return path
+
+
+def test_cpp_rgb_driver_builds(pkg):
+    pkg.lib()
+    _build_rgb_driver()
+
+
+@pytest.mark.gpu
+def test_cpp_driver_samples_a_red_giant_fit_with_the_device_setup(pkg, tmp_path):
+    """BASELINE C1 (the reference's RGBtests preset on fixture 10722175, 5 chains): the C++ driver with one tamcmc_gpu_rgb_expand +
+    one tamcmc_gpu_eval per step.  Same seed -> identical chains; the chain with the host solver is the same chain."""
+    exe = _build_rgb_driver()
+    f = rgb_driver_case(str(tmp_path / "case.bin"))
+    r = subprocess.run([exe, f, "600", "host"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    print(r.stdout)
+    assert r.returncode == 0 and "rgb driver: ok" in r.stdout, r.stdout
+
+
 def test_cpp_driver_builds(pkg):
     pkg.lib()
     _build_driver()
