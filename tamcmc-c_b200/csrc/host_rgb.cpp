@@ -895,7 +895,7 @@ bool export_task(const Prep* Pp, int chain, DeviceTask& T)
         for (size_t ng = 0; ng < S.nu_g.size(); ng++) {
             const ld nu_g = S.nu_g[ng];
             if (!(nu_g >= U.lo[np] && nu_g <= U.hi[np]) || B.nband == 0) continue;
-            Pair Q; Q.inv_g = 1.0 / (double)nu_g; Q.band = (int)(bands0 + np); Q.pad_ = 0;
+            Pair Q; Q.inv_g = 1.0 / (double)nu_g; Q.nu_g = (double)nu_g; Q.band = (int)(bands0 + np); Q.pad_ = 0;
             if (first) {                                                 // segments of a pair of this band = poles of the tangent inside it + 1
                 const PminusG F(S.nu_p[np], nu_g, U.dnu_local[np], U.DPl, U.q);
                 const double npoles = std::floor(F.u_of(G.grid(G.i_lo)) - 0.5) - std::ceil(F.u_of(G.grid(G.i_hi)) - 0.5) + 1.0;

@@ -10,7 +10,7 @@ namespace tamcmc_rgb {
 // as the reference forms it in long double, split into two doubles), 1 / nu_g of the band's first g mode (the search of phase 1 runs with
 // it), where the band's solution slots start (one per band index), and an estimate of the number of segments (poles of the tangent + 1)
 struct Band { double nu_p, Dnu, lo, hi, gstep, DPl, q, resol2, Dh, Dl, rep_inv_g; int n, i_lo, nband, slot_off, chain, nseg_est; };
-struct Pair { double inv_g; int band, pad_; };                                     // one (p mode, g mode): 1 / nu_g
+struct Pair { double inv_g, nu_g; int band, pad_; };                               // one (p mode, g mode): 1 / nu_g (double division), nu_g
 struct KsiHdr { double fmin, fmax, c_up, pi_d; int Lp, Lg, Ndata, off_p, off_g, chain, val_off, pad_; };   // the zeta normalisation of one chain (bump_DP.cpp:126-163)
 struct DeviceTask {
     std::vector<Band> bands;

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128) tamcmc_rgb_pairs_kernel(const Band* __res
     for (int r = lane; r < n; r += lanes) {
         const Record R = recs[(size_t)Q.band * REC_CAP + r];
         double sol;
-        if (record_eval<TrigCR>(B, Q.inv_g, R, sol, flag)) {
+        if (record_eval<TrigCR>(B, Q.inv_g, Q.nu_g, R, sol, flag)) {
             if (sol > 0.0) atomicMin(slots + (size_t)Q.band * REC_CAP + r, (unsigned long long)__double_as_longlong(sol));
             else flag |= RGB_FLAG_NONFINITE;
         }
@@ -631,7 +631,7 @@ int tamcmc_host_rgb_expand_emulated(int model_id, const double* params, const in
             const Band& B = T.bands[(size_t)Q.band];
             for (const Record& R : recs[(size_t)Q.band]) {
                 double sol;
-                const bool got = exact_trig ? record_eval<TrigCR>(B, Q.inv_g, R, sol, flag) : record_eval<TrigLib>(B, Q.inv_g, R, sol, flag);
+                const bool got = exact_trig ? record_eval<TrigCR>(B, Q.inv_g, Q.nu_g, R, sol, flag) : record_eval<TrigLib>(B, Q.inv_g, Q.nu_g, R, sol, flag);
                 if (got) { double& v = slots[(size_t)(B.slot_off + R.idx)]; if (v < 0.0 || sol < v) v = sol; }
             }
         }

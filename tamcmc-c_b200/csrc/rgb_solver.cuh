@@ -181,10 +181,34 @@ TAMCMC_HD bool local_search(const Band& B, double inv_g, double lo, double hi, i
     return true;
 }
 
+// g(nu) / p(nu) of a proposed solution, as the reference forms it in long double (gnu_fct for one frequency, solver_mm.cpp:172-180, then
+// :421-427), evaluated in double-double: X = pi 1e6 (1/nu - 1/nu_g) / DPl with its low part carried through the tangent to first order,
+// atan as the library value plus its double-double correction.  Good to ~1e-30; the reference's own extended-precision value differs
+// from it by its rounding errors, a few 1e-15 / |p| on the ratio at most.
+TAMCMC_HD_CALL double ratio_dd(const Band& B, double nu_g, double nu_m)
+{
+    using namespace tamcmc_dd;
+    const dd pi = {3.141592653589793, 1.2246467991473532e-16};
+    const dd one = {1.0, 0.0};
+    dd X = add(div(one, dd{nu_m, 0.0}), neg(div(one, dd{nu_g, 0.0})));
+    X = div(mul_d(mul(pi, X), 1e6), dd{B.DPl, 0.0});
+    const sc v = sincos_dd(X.hi);
+    dd t = div(v.s, v.c);
+    t = add(t, mul_d(add(one, mul(t, t)), X.lo));                       // tan(X.hi + X.lo)
+    const dd u = mul_d(t, B.q);
+    const double a0 = atan(u.hi);
+    const sc w = sincos_dd(a0);
+    const dd num = add(mul(w.c, u), neg(w.s)), den = add(w.c, mul(w.s, u));
+    const dd at = add_d(div(num, den), a0);                             // atan(u) = a0 + atan((u cos a0 - sin a0) / (cos a0 + u sin a0))
+    const dd g = div(mul_d(at, B.Dnu), pi);
+    const dd r = div(g, dd{nu_m - B.nu_p, 0.0});
+    return r.hi + r.lo;
+}
+
 // phase 2: the line through the record's two local points with THIS g mode's exact values of f, its zero, and the 0.1 % test
 // (solver_mm.cpp:421-431).  The signs of the two values must be what the record's kind says they are.
 template <class EXACT>
-TAMCMC_HD bool record_eval(const Band& B, double inv_g, const Record& R, double& sol, int& flag)
+TAMCMC_HD bool record_eval(const Band& B, double inv_g, double nu_g, const Record& R, double& sol, int& flag)
 {
     const int Nx = R.n;
     const double lo = R.lo, hi = R.hi;
@@ -205,10 +229,15 @@ TAMCMC_HD bool record_eval(const Band& B, double inv_g, const Record& R, double&
     }
     const double x_int = 0.0;
     const double nu_m = a * x_int + b;
-    // g / p within 0.1 % of 1 (the reference evaluates g in long double; a ratio that close to a bound goes to the host)
+    // g / p within 0.1 % of 1.  The reference evaluates g in long double: plain double decides unless the ratio is within 1e-6 of a bound,
+    // then the double-double value does, unless THAT is within the reach of the reference's own rounding errors (the chain goes to the host)
     const double Xs = TAMCMC_RGB_PI * (1.0 / nu_m - inv_g) * 1e6 / B.DPl;
-    const double ratio = (B.Dnu * atan(B.q * tan(Xs)) / TAMCMC_RGB_PI) / (nu_m - B.nu_p);
-    if (fabs(ratio - 0.999) < 1e-6 || fabs(ratio - 1.001) < 1e-6) { flag |= RGB_FLAG_RATIO; return false; }
+    double ratio = (B.Dnu * atan(B.q * tan(Xs)) / TAMCMC_RGB_PI) / (nu_m - B.nu_p);
+    if (fabs(ratio - 0.999) < 1e-6 || fabs(ratio - 1.001) < 1e-6) {
+        ratio = ratio_dd(B, nu_g, nu_m);
+        const double band = 4e-14 + 1.6e-13 / fabs(nu_m - B.nu_p);       // 4 x what 3e6 random cases need (tests/cpp/ratio_dd_check.cpp)
+        if (!(fabs(ratio - 0.999) > band && fabs(ratio - 1.001) > band)) { flag |= RGB_FLAG_RATIO; return false; }
+    }
     if (ratio >= 0.999 && ratio <= 1.001) { sol = nu_m; return true; }
     return false;
 }

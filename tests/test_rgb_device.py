@@ -96,6 +96,17 @@ def test_long_double_local_grid_is_reproduced_exactly(tmp_path):
     assert int(f[7].rstrip(",")) > 1000 and int(f[9].rstrip(")")) > 1000, out          # both truncations occur
 
 
+def test_borderline_ratio_test_in_double_double(tmp_path):
+    """ratio_dd (csrc/rgb_solver.cuh): g / p of a proposed solution in double-double against the reference's long double formula
+    (solver_mm.cpp:172-180, 421-427) on 10^6 random inputs -- within the extended-precision rounding errors (1e-14 + 4e-14 / |p|), a quarter
+    of the band inside which the device leaves the decision to the host."""
+    exe = tmp_path / "ratio"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "tamcmc-c_b200", "csrc"),
+                           os.path.join(HERE, "cpp", "ratio_dd_check.cpp"), "-o", str(exe)])
+    out = subprocess.check_output([str(exe), "1000000"], text=True)
+    assert " bad 0 " in out, out
+
+
 @pytest.mark.parametrize("model_id", [25, 27])
 def test_segment_decomposition_reproduces_the_host_solver(pkg, model_id):
     G = np.load(GOLD)
