@@ -585,31 +585,11 @@ template <bool WRITE_MODEL, int TILE>
 __device__ __noinline__ void bg_phase(const BgArgs A, int lane)
 {
     const unsigned nbg = A.qctl->bg_count;            // final: the expander grid completed before this grid started
-    unsigned idx = 0;
-    if (lane == 0) idx = atomicAdd(&A.qctl->bg_head, 1u);
-    idx = __shfl_sync(0xffffffffu, idx, 0);
     for (;;) {
+        unsigned idx = 0;
+        if (lane == 0) idx = atomicAdd(&A.qctl->bg_head, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= nbg) return;
-        // The NEXT tile is claimed now and looked at one chunk into this one (bg_prefetch below): the pop, the queue entry, the tile record
-        // and the first lines of its x and y -- four dependent round trips, the last one to HBM -- are then under this tile's arithmetic
-        // instead of in front of the next tile's.  (Every warp ends up claiming one index past the end: the head is reset with the queue.)
-        unsigned nxt = 0;
-        bool nxt_seen = false;
-        if (lane == 0) nxt = atomicAdd(&A.qctl->bg_head, 1u);
-        auto bg_prefetch = [&]() {
-            nxt = __shfl_sync(0xffffffffu, nxt, 0);
-            nxt_seen = true;
-            if (nxt >= nbg) return;
-            const unsigned it = A.bgqueue[nxt];
-            const int sc_n = (int)(it / (unsigned)A.tiles_stride);
-            const int tile_n = (int)(it - (unsigned)sc_n * (unsigned)A.tiles_stride);
-            const long long off_n = (A.stars + sc_n / A.Nchains)->off + (long long)tile_n * TILE;
-            const char* tr_n = reinterpret_cast<const char*>(A.tilerec + it);
-            if (lane < (int)((sizeof(TileRec) + 127) / 128)) asm volatile("prefetch.global.L2 [%0];" ::"l"(tr_n + 128 * lane));
-            // the first chunk of the tile: 4 x 64 doubles of x and of y = 16 lines each
-            const double* pf = (lane < 16) ? (A.x + off_n + 16 * lane) : (A.y + off_n + 16 * (lane - 16));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-        };
         const unsigned item = A.bgqueue[idx];
         const int sc = (int)(item / (unsigned)A.tiles_stride);
         const int tile = (int)(item - (unsigned)sc * (unsigned)A.tiles_stride);
@@ -656,7 +636,6 @@ __device__ __noinline__ void bg_phase(const BgArgs A, int lane)
                 S.fold();
 #pragma unroll
                 for (int c = 0; c < CH; c++) { xv[c] = xn[c]; yv[c] = yn[c]; }
-                if (k0 == 0) bg_prefetch();
             }
         } else {
             // ---- the exact per-bin terms where the series does not converge (near x = 0), merged into one fraction like the ring's
@@ -702,7 +681,6 @@ __device__ __noinline__ void bg_phase(const BgArgs A, int lane)
                 S.fold();
             }
         }
-        if (!nxt_seen) bg_prefetch();
         double s1 = S.s1, pm = (S.bad < 0) ? nan("") : S.pm;       // a non-positive model bin: NaN like log() of it (likelihoods.cpp:23)
         int pe = S.pe;
 #pragma unroll
@@ -717,7 +695,6 @@ __device__ __noinline__ void bg_phase(const BgArgs A, int lane)
             double* part = A.partial + 3 * ((size_t)sc * A.tiles_stride + tile);
             part[0] = s1; part[1] = __hiloint2double(hi - k, __double2loint(pm)); part[2] = (double)(pe + (k >> 20));
         }
-        idx = nxt;
     }
 }
 
