@@ -181,11 +181,12 @@ def run_reference(args):
     assert rc == 0 and np.all(np.isfinite(L))
     v = NCHAINS * args.steps / el
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "steps_requested": getattr(args, "steps_requested", args.steps),
             "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "chains": NCHAINS, "bins": NBINS},
             "cpu_baseline": {"value": v, "unit": "evals/s", "cores": min(cores, NCHAINS), "host_cores": cores, "kind": kind,
-                             "sample": "%d full 10-chain C2 steps; %s" % (args.steps, what),
+                             "sample": "%d full 10-chain C2 steps%s; %s" % (args.steps, " (bounded: %d were asked for)" % args.steps_requested if getattr(args, "steps_requested", args.steps) != args.steps else "", what),
                              "calibration_evals_per_s": calib},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -398,8 +399,9 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 (bin-sharded), C5 (256 stars) and C4 (red giant) blocks of the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
+        args.steps_requested = args.steps
         if args.steps > 50:
-            args.steps = 50          # bounded: a CPU step is ~0.1-0.3 s
+            args.steps = 50          # bounded sample: a CPU step is ~0.05-0.3 s; the line says so ("steps_requested", "sample")
         return run_reference(args)
 
     import torch
@@ -531,7 +533,7 @@ def main():
     if rank == 0:
         peak_tf = pkg.fp64_peak(local_rank)
         k_ms = whittle_ms / max(nprof, 1)
-        F = algorithmic_flops(pairs, 0.0, NBINS * S, NCHAINS)
+        F = algorithmic_flops(pairs, 0.0, NBINS * S, NCHAINS)      # P_asym = 0: synth.classic_params builds the C2 star with asym = 0
         achieved = F / (k_ms * 1e-3) / 1e12
         peaks = {}
         try:
