@@ -249,8 +249,10 @@ def extra_c3_bin_sharded(torch, dist, pkg, stream, flush, rank, world, local_ran
     host_expand_ms = 1e3 * (time.perf_counter() - t0)
     mpl = synth.mode_table_plength(cap, nn, 0)
     if world > 1:
-        rc, _, tr = O.mode_table_model(rows[0], nn, 0, x, trace=True)
-        lo, hi = shard.bin_shards(N, world, shard.bin_work(N, *tr))[rank]
+        # per-bin work from the library's own bin windows (tamcmc_gpu_windows on the whole spectrum), the same on every rank
+        with pkg.Context(pkg.Star(synth.MODEL_MODE_TABLE, mpl, rows.shape[1], x, y), 1, [1.0], device=local_rank) as cw:
+            _, wl, w0, w1 = cw.windows(rows[0])
+        lo, hi = shard.bin_shards(N, world, shard.bin_work(N, wl, w0, w1))[rank]
         star = pkg.Star.shard(synth.MODEL_MODE_TABLE, mpl, rows.shape[1], x, y, lo, hi)
     else:
         lo, hi = 0, N
