@@ -349,9 +349,13 @@ def mala_config(groups):
 #                       noise_s2 [<=10, 3] (right-aligned in 10 rows, -1 fill), and to the end of the file the common
 #                       parameters `name  prior_or_switch  values...` (up to 5 values, -9999 fill)
 # ------------------------------------------------------------------------------------------------
-def read_ms_global_model(path):
+def read_ms_global_model(path, slice_ind=None):
+    """slice_ind = None: the MS_Global / red-giant dialect (one '*' frequency range).  slice_ind = k: the LOCAL-fit dialect
+    (read_MCMC_file_local, io_local.cpp:25-327): the same walk, but the file lists one '*' range per slice and the k-th one is the
+    range that is analysed (io_local.cpp:76-88)."""
     with open(path) as f:
         lines = [l.strip() for l in f.read().splitlines()]
+    range_counter = 0
     out = {"ID": None, "Dnu": None, "C_l": None, "numax": -9999.0, "err_numax": -9999.0, "freq_range": None,
            "param_type": [], "els": [], "freqs_ref": [], "relax_freq": [], "relax_H": [], "relax_gamma": []}
     i, nhash = 0, 0
@@ -375,10 +379,15 @@ def read_ms_global_model(path):
             else:
                 out["Dnu"] = float(w[1])
         elif s[0] == "*":
-            if out["freq_range"] is not None:
-                raise ValueError("two frequency ranges (io_ms_global.cpp: only one '*' line is allowed)")
             w = s.split()
-            out["freq_range"] = (float(w[1]), float(w[2]))
+            if slice_ind is None:
+                if out["freq_range"] is not None:
+                    raise ValueError("two frequency ranges (io_ms_global.cpp: only one '*' line is allowed)")
+                out["freq_range"] = (float(w[1]), float(w[2]))
+            else:
+                if range_counter == slice_ind:
+                    out["freq_range"] = (float(w[1]), float(w[2]))
+                range_counter += 1
         else:
             w = s.split()
             if w[0] not in ("p", "g", "co"):
@@ -423,6 +432,19 @@ def read_ms_global_model(path):
     for k in ("els",):
         out[k] = np.array(out[k], dtype=np.int64)
     out["freqs_ref"] = np.array(out["freqs_ref"], dtype=np.float64)
+    return out
+
+
+def read_local_model(path, slice_ind=0):
+    """The local-fit `.model` dialect (read_MCMC_file_local, tamcmc/sources/io_local.cpp:25-327): the fields of MCMC_files for slice
+    `slice_ind` of the file.  (The reader the reference has today indexes the second word of every hyper-prior row: a file whose
+    'Extra parameters' block still holds its one-column rows -- like the shipped test/inputs/TF_3443483_local-v3.model -- makes it
+    read out of bounds; such rows are rejected here.)"""
+    out = read_ms_global_model(path, slice_ind=int(slice_ind))
+    if out["freq_range"] is None:
+        raise ValueError("slice %d: the file has fewer '*' frequency ranges" % slice_ind)
+    if len(out["hyper_priors_names"]) != len(out["hyper_priors"]):
+        raise ValueError("hyper-prior rows need a prior name in their second column (io_local.cpp:180: word[1])")
     return out
 
 

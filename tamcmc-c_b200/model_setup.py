@@ -12,7 +12,8 @@ Restates `build_init_MS_Global` (tamcmc/sources/io_ms_global.cpp:362-1400) with 
 `inputs` and `plength` are what `tamcmc_gpu_create` / `tamcmc_gpu_eval` take (include/tamcmc_gpu.h); `relax` and the prior table
 feed the driver (host/mcmc_driver.hpp, host/priors.hpp).  Covered: every model name the function accepts except the two
 Appourchaux-width variants (`model_MS_Global_a1etaa3_AppWidth_HarveyLike_v1/_v2`, which no GPU model id serves).  Where the
-reference prints a message and calls exit(), this raises ValueError with the same diagnosis.  New code: the reference's blocks of
+reference prints a message and calls exit(), this raises ValueError with the same diagnosis.  `build_init_asymptotic` (io_asymptotic.cpp:32-875)
+is the red-giant dialect, `build_init_local` (io_local.cpp:329-1238) the local-fit one (models 11 / 14; formats.read_local_model).  New code: the reference's blocks of
 `if (name == ...)` are table-driven here; pinned value for value on the reference's own function, compiled from its own sources
 (tests/test_model_setup.py, tests/golden/reference_ms_global_init.json)."""
 import math
@@ -722,3 +723,306 @@ GPU_MODEL_IDS = {
     "model_MS_Global_a1etaa3_HarveyLike_Classic_v3": 13, "model_MS_Global_a1l_etaa3_HarveyLike": 6, "model_MS_Global_a1n_etaa3_HarveyLike": 7,
     "model_MS_Global_a1nl_etaa3_HarveyLike": 8, "model_MS_Global_ajAlm_HarveyLike": 21, "model_MS_Global_aj_HarveyLike": 23,
 }
+
+
+# ================================================================================================================================
+# The LOCAL-fit dialect: build_init_local (tamcmc/sources/io_local.cpp:329-1176) with set_noise_params_local (:1178-1238)
+# ================================================================================================================================
+LOCAL_MODELS = {"model_MS_local_basic": 11, "model_MS_local_Hnlm": 14}       # model_fullname -> id of tamcmc_gpu_create (models_ctrl.list)
+
+
+def _fatal_local(var, kind):
+    raise ValueError("%s: %s (fatalerror_msg_io_local, io_local.cpp:1240-1260)" %
+                     (var, "Fix_Auto is not implemented for that parameter" if kind == "Fix_Auto" else "should always be defined as '%s'" % kind))
+
+
+def harvey_like(noise_params, x):
+    """tamcmc/sources/noise_models.cpp:15-39 on a zero spectrum: sum of Harvey-like profiles + white noise at the frequencies x"""
+    x = np.asarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    nh = (len(noise_params) - 1) // 3
+    for k in range(nh):
+        H, tc, p = noise_params[3 * k:3 * k + 3]
+        if tc != 0:
+            out = out + H * (1.0 / (np.array([math.pow(v, p) for v in (1e-3) * tc * x]) + 1.0))        # (libm's pow, like the reference)
+    return out + noise_params[-1]
+
+
+def set_noise_params_local(noise_params, freq_range):
+    """io_local.cpp:1178-1238: a local fit approximates the noise by a constant -- the mean of the file's noise model at the two ends of
+    the analysed range, Uniform between half its minimum and 1.5 times its maximum there."""
+    nz = Block(1)
+    nz.names[0], nz.pnames[0], nz.relax[0] = "White_Noise_N0", "Uniform", 1
+    noise_params = np.asarray(noise_params, dtype=np.float64)
+    n_skip = int(np.sum(np.abs(noise_params - (-2.0)) <= 1e-6))           # where_dbl(noise_params, -2, 1e-6)
+    noise_p = np.full(len(noise_params) - n_skip, EMPTY)
+    cpt = 0
+    for v in noise_params:
+        if v == -1:
+            noise_p[cpt] = 0
+            cpt += 1
+        if v >= 0:
+            noise_p[cpt] = v
+            cpt += 1
+    vals = harvey_like(noise_p, np.array([freq_range[0], freq_range[1]], dtype=np.float64))
+    nz.inputs[0] = vals.sum() / len(vals)
+    nz.priors[0, 0] = vals.min() * 0.5
+    nz.priors[1, 0] = vals.max() * 1.5
+    return nz
+
+
+def build_init_local(mf, resol):
+    """mf: the dictionary of formats.read_local_model (one slice of the file); resol: the spectrum's resolution.  Same return value as
+    build_init_ms_global.  The models are model_MS_local_basic (id 11) and model_MS_local_Hnlm (id 14): every mode of the slice has its
+    own height, width and frequency; no visibilities; the noise is one constant."""
+    Hmin, Hmax = 1.0, 10000.0
+    G = 6.667e-8
+    Dnu_sun, R_sun, M_sun = 135.1, 6.96342e5, 1.98855e30
+    rho_sun = float(LD(M_sun * 1e3) / ((LD(4) * PI_LD * LD(math.pow(R_sun * 1e5, 3))) / LD(3)))          # :337 (long double pi)
+    Dnu = mf["Dnu"] if mf["Dnu"] is not None else -9999.0
+    rho = math.pow(Dnu / Dnu_sun, 2.) * rho_sun
+    names, cpri, mc = mf["common_names"], mf["common_names_priors"], mf["modes_common"]
+    els = np.asarray(mf["els"])
+    lmax = int(els.max())
+    fr0, fr1 = mf["freq_range"]
+    trunc_c = -1.0
+
+    # ---- instructions that come before the set-up (:377-406) ----
+    fullname, do_amp = " ", 0
+    do_a11_eq_a12, do_avg_a1n = 1, 1
+    for i, nm in enumerate(names):
+        if nm == "model_fullname":
+            fullname = cpri[i]
+        if nm == "fit_squareAmplitude_instead_Height":
+            if cpri[i] != "bool":
+                _fatal_local(nm, "bool")
+            do_amp = int(bool(mc[i, 0]))
+    if fullname == " ":
+        raise ValueError("Model name empty: the .model file needs the model_fullname variable (io_local.cpp:402-405)")
+    hnlm = fullname == "model_MS_local_Hnlm"
+    inc = Block(1)
+
+    # ---- frequencies / widths / heights of the eigen table, degree by degree, matched with the relax list (:414-503) ----
+    eig = np.asarray(mf["eigen_params"], dtype=np.float64)
+    f_in, h_in, w_in, fmin_in, fmax_in = [[] for _ in range(4)], [[] for _ in range(4)], [[] for _ in range(4)], [[] for _ in range(4)], [[] for _ in range(4)]
+    f_rl, h_rl, w_rl = [[] for _ in range(4)], [[] for _ in range(4)], [[] for _ in range(4)]
+    for el in range(lmax + 1):
+        pos0 = [k for k in range(len(els)) if els[k] == el]
+        if not pos0:
+            continue
+        f_el = [mf["freqs_ref"][k] for k in pos0]
+        pos_el = [k for k in range(eig.shape[0]) if int(eig[k, 0]) == el]
+        for k in pos_el:
+            if el <= 3:
+                f_in[el].append(eig[k, 1]); fmin_in[el].append(eig[k, 2]); fmax_in[el].append(eig[k, 3]); w_in[el].append(eig[k, 4]); h_in[el].append(eig[k, 5])
+            hits = [j for j in range(len(f_el)) if eig[k, 1] - 1e-2 <= f_el[j] <= eig[k, 1] + 1e-2]      # where_dbl, string_handler.cpp:88-110
+            if len(hits) != 1:
+                raise ValueError("the frequency %r is not unique in / absent from the relax list (io_local.cpp:484-497)" % eig[k, 1])
+            if el <= 3:
+                f_rl[el].append(bool(mf["relax_freq"][pos0[hits[0]]])); w_rl[el].append(bool(mf["relax_gamma"][pos0[hits[0]]]))
+                h_rl[el].append(bool(mf["relax_H"][pos0[hits[0]]]))
+
+    # ---- only the modes strictly inside the analysed range (filter_range, string_handler.cpp:515-557; :510-560) ----
+    for el in range(4):
+        if not f_in[el]:
+            continue
+        keep = [k for k, f in enumerate(f_in[el]) if fr0 < f < fr1]
+        for lst in (h_in, w_in, fmin_in, fmax_in, f_rl, h_rl, w_rl, f_in):       # (f_in last: it is the filter's key)
+            lst[el] = [lst[el][k] for k in keep]
+    Nf_el = [len(f_in[el]) for el in range(4)]
+    if sum(len(h) for h in h_in) == 0:
+        raise ValueError("No parameters found in the specified frequency range (io_local.cpp:562-569)")
+
+    # ---- heights / amplitudes, widths, frequencies: the defaults (:574-668) ----
+    if do_amp:
+        h_name = "Amplitude_l"
+        for el in range(4):
+            h_in[el] = [float(PI_LD * LD(w_in[el][k]) * LD(h_in[el][k])) for k in range(len(h_in[el]))]
+    else:
+        h_name = "Height_l"
+    tmp = [Hmin, Hmax, EMPTY, EMPTY]
+
+    def fill_vect(blk, vals, relax, name, prior, prior_vals, pos, i0_if, i0_else):
+        """IO_models::fill_param_vect / fill_param_vect2 (io_models.cpp:79-118): prior_vals is one row for all, or one row per value"""
+        per_value = len(prior_vals) > 0 and hasattr(prior_vals[0], "__len__")
+        for k in range(len(vals)):
+            row = prior_vals[k] if per_value else prior_vals
+            if relax[k]:
+                blk.fill(name, prior, vals[k], row, k + pos, i0_if)
+            else:
+                blk.fill(name, "Fix", vals[k], row, k + pos, i0_else)
+
+    offs = [0, len(h_in[0]), len(h_in[0]) + len(h_in[1]), len(h_in[0]) + len(h_in[1]) + len(h_in[2])]
+    if hnlm:
+        height = Block(Nf_el[0] + Nf_el[1] * 2 + Nf_el[2] * 3 + Nf_el[3] * 4)
+        p0 = 0
+        fill_vect(height, h_in[0], h_rl[0], h_name, "Jeffreys", tmp, p0, 0, 0)
+    else:
+        height = Block(sum(Nf_el))
+        for el in range(4):
+            p0 = offs[el]
+            fill_vect(height, h_in[el], h_rl[el], h_name, "Jeffreys", tmp, p0, 0, 0)
+    width, freq = Block(sum(Nf_el)), Block(sum(Nf_el))
+    tmp = [resol, Dnu / 3., EMPTY, EMPTY] if Dnu > 0 else [resol, 20., EMPTY, EMPTY]
+    for el in range(4):
+        p0 = offs[el]
+        fill_vect(width, w_in[el], w_rl[el], "Width_l", "Jeffreys", tmp, p0, 0, 0)
+    for el in range(4):
+        p0 = offs[el]
+        for k in range(len(f_in[el])):
+            if f_rl[el][k]:
+                d = 0.01 * abs(fmax_in[el][k] - fmin_in[el][k])
+                tmp = [fmin_in[el][k], fmax_in[el][k], d, d]
+                freq.fill("Frequency_l", "GUG", f_in[el][k], tmp, k + p0, 0)
+            else:
+                freq.fill("Frequency_l", "Fix", f_in[el][k], tmp, k + p0, 0)
+    snlm = Block(6)                                                               # do_a11_eq_a12 == do_avg_a1n == 1 for both models (:671-673)
+    extra = np.array([0, 0, 0.2, 0], dtype=np.float64)                            # :693-698
+
+    # ---- the common parameters (:700-968) ----
+    pos_prior_height = -1
+    bool_a1sini = bool_a1cosi = False
+    for i, nm in enumerate(names):
+        pr, row = cpri[i], mc[i]
+        if nm == "trunc_c":
+            if pr != "Fix":
+                _fatal_local("trunc_c", "Fix")
+            trunc_c = row[0]
+        if nm in ("height", "Height", "amplitude", "Amplitude"):
+            amp = nm in ("amplitude", "Amplitude")
+            if pr == "Fix_Auto":
+                def auto_rows(hs):
+                    if amp:
+                        return [[float(PI_LD * LD(Dnu) / LD(3.) * LD(h) / LD(row[0])), float(PI_LD * LD(Dnu) / LD(3.) * LD(h) * LD(row[1])), EMPTY, EMPTY] for h in hs]
+                    return [[h / row[0], h * row[1], EMPTY, EMPTY] for h in hs]
+                if hnlm:
+                    pos_prior_height = i
+                    fill_vect(height, h_in[0], h_rl[0], h_name, "Jeffreys", auto_rows(h_in[0]), p0, 0, 0)
+                else:
+                    for el in range(4):
+                        p0 = offs[el]
+                        fill_vect(height, h_in[el], h_rl[el], h_name, "Jeffreys", auto_rows(h_in[el]), p0, 0, 0)
+            else:
+                if hnlm:
+                    pos_prior_height = i
+                    fill_vect(height, h_in[0], h_rl[0], h_name, pr, row, p0, 0, 0)
+                else:
+                    for el in range(4):
+                        p0 = offs[el]
+                        fill_vect(height, h_in[el], h_rl[el], h_name, pr, row, p0, 1, 1)
+        if nm in ("width", "Width"):
+            if pr == "Fix_Auto":
+                wname = "Jeffreys"
+                tmp = [resol, Dnu / 3, EMPTY, EMPTY] if Dnu > 0 else [resol, 20, EMPTY, EMPTY]
+            else:
+                wname = pr
+                tmp = list(row)
+            for el in range(4):
+                p0 = offs[el]
+                fill_vect(width, w_in[el], w_rl[el], "Width_l", wname, tmp, p0, 0, 1)
+        if nm in ("splitting_a1", "Splitting_a1"):
+            if pr == "Fix_Auto":
+                _fatal_local("splitting_a1", "Fix_Auto")
+            p0 = 0
+            snlm.fill("Splitting_a1", pr, row[0], row, p0, 1)
+        if nm in ("asphericity_eta", "Asphericity_eta"):
+            snlm.names[1] = "Asphericity_eta0"
+            if pr == "Fix_Auto":
+                snlm.pnames[1] = "Fix"
+                snlm.relax[1] = 0
+                if row[0] == 1:
+                    snlm.inputs[1] = 3. / (4. * math.pi * rho * G) if Dnu > 0 else 0.0
+                else:
+                    snlm.inputs[1] = 0
+            else:
+                p0 = 1
+                snlm.fill("Asphericity_eta", pr, row[0], row, p0, 1)
+        if nm in ("splitting_a3", "Splitting_a3"):
+            if pr == "Fix_Auto":
+                _fatal_local("splitting_a3", "Fix_Auto")
+            p0 = 2
+            snlm.fill("Splitting_a3", pr, row[0], row, p0, 1)
+        if nm in ("asymetry", "Asymetry"):
+            if pr == "Fix_Auto":
+                _fatal_local("asymetry", "Fix_Auto")
+            p0 = 5
+            snlm.fill("Lorentzian_asymetry", pr, row[0], row, p0, 1)
+        if nm in ("inclination", "Inclination"):
+            if pr == "Fix_Auto":
+                _fatal_local("inclination", "Fix_Auto")
+            p0 = 0
+            inc.fill("Inclination", pr, 89.99999 if row[0] >= 90 else row[0], row, p0, 1)
+        if nm == "sqrt(splitting_a1).cosi":
+            if pr == "Fix_Auto":
+                _fatal_local(nm, "Fix_Auto")
+            p0 = 3
+            snlm.fill(nm, pr, row[0], row, p0, 1)
+            bool_a1cosi = True
+        if nm == "sqrt(splitting_a1).sini":
+            if pr == "Fix_Auto":
+                _fatal_local(nm, "Fix_Auto")
+            p0 = 4
+            snlm.fill(nm, pr, row[0], row, p0, 1)
+            bool_a1sini = True
+
+    # ---- splitting_a1 + inclination -> sqrt(a1).cosi, sqrt(a1).sini (:971-1063) ----
+    if bool_a1cosi != bool_a1sini:
+        raise ValueError("both 'sqrt(splitting_a1).sini' and 'sqrt(splitting_a1).cosi' must appear (io_local.cpp:971-977)")
+    if not bool_a1cosi:
+        if fullname == "model_MS_local_basic":
+            ang = LD(inc.inputs[0]) * PI_LD / LD(180.)
+            c, s_ = float(LD(math.sqrt(snlm.inputs[0])) * np.cos(ang)), float(LD(math.sqrt(snlm.inputs[0])) * np.sin(ang))
+            if inc.pnames[0] == "Fix" and snlm.pnames[0] == "Fix":
+                snlm.fill("sqrt(splitting_a1).cosi", "Fix", c, snlm.priors[:, 0].copy(), 3, 0)
+                snlm.fill("sqrt(splitting_a1).sini", "Fix", s_, snlm.priors[:, 0].copy(), 4, 0)
+            else:
+                snlm.priors[1, 0] = math.sqrt(snlm.priors[1, 0])
+                snlm.fill("sqrt(splitting_a1).cosi", snlm.pnames[0], c, snlm.priors[:, 0].copy(), 3, 0)
+                snlm.fill("sqrt(splitting_a1).sini", snlm.pnames[0], s_, snlm.priors[:, 0].copy(), 4, 0)
+            if snlm.inputs[3] < 1e-2:
+                snlm.inputs[3] = 1e-2
+            if snlm.inputs[4] < 1e-2:
+                snlm.inputs[4] = 1e-2
+            inc.fill("Empty", "Fix", 0, inc.priors[:, 0].copy(), 0, 1)
+            snlm.fill("Empty", "Fix", 0, snlm.priors[:, 0].copy(), 0, 1)
+        if hnlm:
+            inc0 = inc.inputs[0]
+            inc.fill("Empty", "Fix", 0, inc.priors[:, 0].copy(), 0, 1)
+            ind = len(h_in[0])
+            if pos_prior_height <= 0:
+                tmp, tname = [Hmin, Hmax, EMPTY, EMPTY], "Jeffreys"
+            else:
+                tmp, tname = list(mc[pos_prior_height]), cpri[pos_prior_height]
+            for el in range(1, lmax + 1):
+                r = amplitude_ratio(el, inc0)
+                for en in range(Nf_el[el]):
+                    for em in range(el + 1):
+                        height.fill("H(%d,%d,%d)" % (en, el, em), tname, h_in[el][en] * r[el + em], tmp, ind, 0)
+                        ind += 1
+            extra[3] = 2
+    else:
+        inc.fill("Empty", "Fix", 0, inc.priors[:, 0].copy(), 0, 1)
+        snlm.fill("Empty", "Fix", 0, snlm.priors[:, 0].copy(), 0, 1)
+
+    noise = set_noise_params_local(mf["noise_params"], (fr0, fr1))
+
+    # ---- everything in one vector (:1076-1140) ----
+    nh = len(h_in[0]) + 2 * len(h_in[1]) + 3 * len(h_in[2]) + 4 * len(h_in[3]) if hnlm else sum(len(h) for h in h_in)
+    plength = np.array([nh, 0, Nf_el[0], Nf_el[1], Nf_el[2], Nf_el[3], len(snlm), sum(len(w) for w in w_in), len(noise), len(inc), 2], dtype=np.int64)
+    allp = Block(int(plength.sum()))
+    p0 = 0
+    for blk in (height, freq, snlm, width, noise, inc):
+        n = len(blk)
+        allp.names[p0:p0 + n] = blk.names
+        allp.pnames[p0:p0 + n] = blk.pnames
+        allp.inputs[p0:p0 + n] = blk.inputs
+        allp.relax[p0:p0 + n] = blk.relax
+        allp.priors[:, p0:p0 + n] = blk.priors
+        p0 += n
+    row0 = mc[0]
+    allp.fill("Truncation parameter", "Fix", trunc_c, row0, p0, 1)
+    if allp.inputs[p0] <= 0:
+        allp.inputs[p0] = 10000.
+    allp.fill("Switch for fit of Amplitudes or Heights", "Fix", do_amp, row0, p0 + 1, 1)
+    return {"model_fullname": fullname, "inputs": allp.inputs, "relax": allp.relax, "priors": allp.priors, "plength": plength,
+            "extra_priors": extra, "inputs_names": allp.names, "priors_names": allp.pnames, "numax": mf["numax"], "err_numax": mf.get("err_numax", EMPTY)}
