@@ -549,6 +549,7 @@ int tamcmc_gpu_rgb_expand(tamcmc_gpu_rgb* h, int model_id, const double* params,
     for (int c = 0; c < nchains; c++) {
         status_out[c] = prepare(h->preps[(size_t)c], model_id, params + (size_t)c * params_stride, plength, step, true);
         if (path_out) path_out[c] = -1;
+        if (nmodes_out) nmodes_out[c] = 0;
         DeviceTask& Tc = h->chain_task[(size_t)c];
         Tc.clear();
         if (status_out[c] == TAMCMC_OK && export_task(h->preps[(size_t)c], c, Tc)) h->on_device[(size_t)c] = 1;
