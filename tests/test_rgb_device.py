@@ -83,6 +83,27 @@ int main(int argc, char** argv) {
     assert checked >= 6000
 
 
+def test_dd_tan_atan_edge_cases(tmp_path):
+    """tan_cr next to 570 zeros and poles of the tangent (distances 1e-1 ... 1e-11), tiny and large arguments; atan_cr from 1e-300 to 1e280:
+    correctly rounded everywhere (mpmath, 400 bits)."""
+    mp = pytest.importorskip("mpmath")
+    exe = tmp_path / "edge"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "tamcmc-c_b200", "csrc"),
+                           os.path.join(HERE, "cpp", "dd_edge_cases.cpp"), "-o", str(exe)])
+    mp.mp.prec = 400
+    n = 0
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        k, x, v = line.split()
+        x, v = float.fromhex(x), float.fromhex(v)
+        exact = mp.tan(mp.mpf(x)) if k == "tan" else mp.atan(mp.mpf(x))
+        n += 1
+        if v == 0 and exact == 0:
+            continue
+        err = abs(mp.mpf(v) - exact)
+        assert err <= abs(mp.mpf(float(np.nextafter(v, np.inf))) - exact) and err <= abs(mp.mpf(float(np.nextafter(v, -np.inf))) - exact), (k, x)
+    assert n > 5000
+
+
 def test_long_double_local_grid_is_reproduced_exactly(tmp_path):
     """local_grid_ext (csrc/rgb_solver.cuh): the reference's x87 extended-precision local grid (solver_mm.cpp:402-410) from error-free
     transformations in double, against the real long double arithmetic on 3 million random (nu, resol, factor): range_min, range_max and
